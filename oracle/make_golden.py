@@ -1,0 +1,135 @@
+"""TEST INFRASTRUCTURE -- pins oracle/nmf_oracle.py against the real reference and writes fixtures.
+
+Run inside the build container (needs /root/reference):
+
+    python -m oracle.make_golden            # pin + write tests/golden/*.pt
+    python -m oracle.make_golden --full     # additionally pin one 4096-ray chunk at G=300 (no file)
+
+For each case it (1) builds a synthetic scene (nmf_b200/synthetic.py), (2) loads it into the
+*unmodified* reference ``TensorNeRF`` (oracle/ref_harness.py), lets the reference build its own
+occupancy volume (``updateAlphaMask``) and renders the rays with ``torch.manual_seed(seed)``,
+(3) renders the same rays with the restatement using ``TorchRNG`` under the same seed and asserts
+agreement, (4) stores inputs + reference outputs as a fixture.  The fixture is what
+``tests/test_oracle_golden.py`` replays on machines without the reference.
+"""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from nmf_b200 import synthetic  # noqa: E402
+from oracle import keyed_rng, nmf_oracle, ref_harness  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+IMAGE_KEYS = ["rgb_map", "acc_map", "depth", "world_normal", "normal", "termination_xyz", "surf_width",
+              "cross_section", "diffuse", "tint", "roughness", "spec", "albedo"]
+
+
+def reference_render(model, rays, focal, seed):
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        ims, stats = model(rays, focal, is_train=False, ndc_ray=False, N_samples=-1)
+    return ims, stats
+
+
+def load_scene_into_reference(state, meta, model_name):
+    t = ref_harness.build_reference_model(meta["aabb"], list(meta["near_far"]), grid_size=meta["grid_size"],
+                                          bg_resolution=meta["bg_resolution"], model_name=model_name)
+    missing = t.load_state_dict({k: v for k, v in state.items()}, strict=False)
+    bad = [k for k in missing.unexpected_keys]
+    assert not bad, bad
+    t.sampler.update(t.rf, init=True)
+    t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
+    t.eval()
+    return t
+
+
+def compare(ref_ims, ref_stats, ims, stats, tol):
+    worst = {}
+    for k, v in ref_ims.items():
+        a, b = v.float(), ims[k].float()
+        assert a.shape == b.shape, (k, a.shape, b.shape)
+        err = (a - b).abs().max().item() if a.numel() else 0.0
+        worst[k] = err
+    assert list(ref_stats["n_samples"]) == list(stats["n_samples"]), (ref_stats["n_samples"], stats["n_samples"])
+    bad = {k: e for k, e in worst.items() if e > tol.get(k, tol["default"])}
+    assert not bad, f"oracle disagrees with the reference: {bad}"
+    return worst
+
+
+def plain_state(meta, seed):
+    """weights of MLPRender_Fea(viewpe=2, feape=2, featureC=128) for the model=tensorf plumbing case"""
+    g = torch.Generator().manual_seed(77 + seed)
+    dims = [(128, 24 + 3 + 96 + 12), (128, 128), (3, 128)]
+    st = {}
+    for li, (o, i) in zip((0, 2, 4), dims):
+        st[f"model.diffuse_module.mlp.{li}.weight"] = (torch.rand(o, i, generator=g) * 2 - 1) / (i ** 0.5)
+        st[f"model.diffuse_module.mlp.{li}.bias"] = torch.zeros(o)
+    return st
+
+
+def run_case(name, scene_name, G, bg_res, n_rays, crop, model_name, seed, write):
+    state, meta = synthetic.make_scene(scene_name, grid_size=G, bg_resolution=bg_res)
+    if model_name == "tensorf":
+        state = {k: v for k, v in state.items() if not k.startswith("model.")}
+        state.update(plain_state(meta, seed))
+    ref = load_scene_into_reference(state, meta, model_name)
+    poses = synthetic.hemisphere_poses(4, seed=1)
+    focal = synthetic.focal_for(800)
+    rays = synthetic.camera_rays(poses[1], 800, 800, focal, crop=crop)
+    g = torch.Generator().manual_seed(5)
+    rays = rays[torch.randperm(rays.shape[0], generator=g)[:n_rays]].contiguous()
+    # edge cases the domain has: an axis-parallel ray (d == 0 components) and a ray that misses the box
+    rays[0] = torch.tensor([0.3, -4.0, 0.2, 0.0, 1.0, 0.0])
+    rays[1] = torch.tensor([5.0, 5.0, 5.0, 0.0, 0.0, 1.0])
+    t0 = time.time()
+    ref_ims, ref_stats = reference_render(ref, rays, focal, seed)
+    t_ref = time.time() - t0
+    alpha = ref.sampler.alphaMask.alpha_volume.detach().clone()
+    hp = dict(model="microfacet" if model_name == "microfacet_tensorf2" else "plain")
+    sc = nmf_oracle.Scene(state, meta["aabb"], meta["near_far"], meta["grid_size"], alpha_volume=alpha, **hp)
+    assert sc.n_samples == ref.sampler.nSamples and float(sc.stepsize) == float(ref.sampler.stepsize)
+    torch.manual_seed(seed)
+    t0 = time.time()
+    ims, stats = nmf_oracle.render_chunk(sc, rays, focal, keyed_rng.TorchRNG())
+    t_or = time.time() - t0
+    tol = dict(default=2e-5, termination_xyz=1e-6, surf_width=0, depth=1e-4)
+    worst = compare(ref_ims, ref_stats, ims, stats, tol)
+    # the oracle's own occupancy rebuild must equal the reference's, voxel for voxel
+    mine = nmf_oracle.build_alpha_volume(sc)
+    assert torch.equal(mine.reshape(-1), alpha.reshape(-1)), "occupancy volume mismatch"
+    print(f"[{name}] rays={n_rays} G={G} n_samples={ref_stats['n_samples']} ref {t_ref:.2f}s oracle {t_or:.2f}s")
+    print("   max |oracle - reference| per map:", {k: f"{e:.2e}" for k, e in worst.items()})
+    if write:
+        os.makedirs(GOLDEN_DIR, exist_ok=True)
+        fix = dict(name=name, scene=scene_name, grid_size=G, bg_resolution=bg_res, model=model_name, seed=seed,
+                   focal=focal, rays=rays, state={k: v.clone() for k, v in state.items()},
+                   aabb=meta["aabb"], near_far=meta["near_far"], alpha_volume=alpha.to(torch.uint8),
+                   ref_images={k: v.clone() for k, v in ref_ims.items()}, ref_n_samples=list(ref_stats["n_samples"]),
+                   torch_version=torch.__version__, max_abs_err_vs_reference=worst)
+        path = os.path.join(GOLDEN_DIR, f"{name}.pt")
+        torch.save(fix, path)
+        print(f"   wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+    return worst
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    ap.add_argument("--no-write", action="store_true")
+    a = ap.parse_args()
+    assert ref_harness.available(), "needs /root/reference"
+    w = not a.no_write
+    run_case("microfacet_g40", "lego", 40, 32, 384, (330, 470, 330, 470), "microfacet_tensorf2", 20211200, w)
+    run_case("microfacet_g56_ship", "ship", 56, 48, 256, (300, 500, 300, 500), "microfacet_tensorf2", 7, w)
+    run_case("plain_g64", "lego", 64, 32, 4096, (368, 432, 368, 432), "tensorf", 20211200, w)
+    if a.full:
+        run_case("microfacet_g300_full", "lego", 300, 512, 4096, None, "microfacet_tensorf2", 20211200, False)
+
+
+if __name__ == "__main__":
+    main()
