@@ -1,0 +1,209 @@
+/* nmf_b200 -- C ABI of the B200-native NMF per-ray render path.
+ *
+ * This is the drop-in boundary of the hot path.  The reference (half-potato/nmf) has no native
+ * operator boundary on this path: it is pure PyTorch behind hydra `_target_` plugin slots
+ * (SURVEY.md section 8b).  The Python plugin classes in `nmf_b200/` keep those slots and call the
+ * entry points below through ctypes; every entry point names the reference code it replaces
+ * (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is device memory unless the name ends in
+ *     `_host`; all buffers are caller-allocated (PyTorch owns them) and must stay alive until
+ *     the stream reaches the end of the call;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), launches a fixed
+ *     sequence of kernels and never synchronises, so a call can be captured in a CUDA graph;
+ *   - return value: 0 = ok, < 0 = NMF_E_* (argument problems, detected on the host before any
+ *     launch), > 0 = a cudaError_t from a launch.  Device-side capacity overflows are reported
+ *     in NmfCounters.error (checked by the caller after it synchronises);
+ *   - fp32 everywhere; integer / occupancy work is bit-exact with the reference's fp32 op order.
+ */
+#ifndef NMF_B200_H
+#define NMF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMF_ABI_VERSION 1
+
+#define NMF_OK 0
+#define NMF_E_ARG (-1)          /* null pointer / non-positive size                                   */
+#define NMF_E_UNSUPPORTED (-2)  /* shape outside what the kernels are compiled for                     */
+#define NMF_E_WORKSPACE (-3)    /* workspace buffer smaller than nmf_workspace_bytes() says            */
+
+#define NMF_DENSITY_COMP 16     /* configs/field/tensorf.yaml:6  density_n_comp                        */
+#define NMF_APP_COMP 24         /* configs/field/tensorf.yaml:7  appearance_n_comp                     */
+#define NMF_APP_DIM 24          /* configs/field/tensorf.yaml:8  app_dim                               */
+#define NMF_BRDF_IN 66          /* modules/brdf.py:96-120  24 + 2*(18+3)                               */
+#define NMF_BRDF_HID 64         /* configs/model/microfacet_tensorf2.yaml:93 hidden_w                  */
+#define NMF_MAX_STEPS 2048      /* dense steps per ray the march kernel keeps a bitmask for            */
+#define NMF_MAX_BOUNCE 400      /* modules/pt_selectors.py:39                                          */
+#define NMF_PLAIN_IN 135        /* modules/render_modules.py:201-235 with viewpe=2, feape=2            */
+#define NMF_PLAIN_HID 128       /* configs/model/tensorf.yaml featureC                                 */
+
+/* device error bits (NmfCounters.error) */
+#define NMF_DEV_E_SURVIVORS 1u  /* surviving-sample list overflowed                                    */
+#define NMF_DEV_E_BSAMPLES 2u   /* bounce-sample list overflowed                                       */
+#define NMF_DEV_E_BRAYS 4u      /* a chunk's bounce-ray region overflowed                              */
+
+/* ------------------------------------------------------------------------------------------------
+ * Scene: every weight the path reads, in the layouts the kernels gather from (DESIGN.md "HBM layout").
+ * Built once per weight update by nmf_b200/scene.py from a reference-format state_dict.
+ * plane p pairs matMode[p] = (0,1),(0,2),(1,2) with vecMode[p] = 2,1,0   (fields/tensoRF.py:40-41)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct NmfScene {
+  /* geometry: fields/tensor_base.py:56-62,219-232 ; samplers/alphagrid.py:96-103 */
+  float aabb0[3], aabb1[3];
+  float inv_aabb2[3];      /* 2 / (aabb1 - aabb0) */
+  float stepsize;          /* min(units) * step_ratio */
+  float near, far;
+  float distance_scale;    /* configs/field/tensorf.yaml:4 */
+  float density_shift;     /* tensor_base.py:85 */
+  int n_steps;             /* nSamples: dense steps per ray */
+  int plane_w[3], plane_h[3], line_n[3];
+
+  /* occupancy (samplers/alphagrid.py:6-60): bit (z*oh + y)*opitch + x of `occ_vox` is alpha_volume[z][y][x] > 0;
+   * `occ_cell` holds the OR over the 8 corners of cell (x0,y0,z0) (in-range corners only). opitch % 32 == 0. */
+  const uint32_t* occ_vox;
+  const uint32_t* occ_cell;
+  int ow, oh, od, opitch;
+  int has_occ;
+
+  /* density factors.  dval: [h][w][16] plane values; dpack: [h][w][4 groups][val4,dx4,dy4] where dx/dy are the
+   * smoothed-difference planes of modules/grid_sample_Cinf.py:218-242; lines: lval [n][16], lpack [n][4][val4,dy4] */
+  const float* dval[3];
+  const float* dpack[3];
+  const float* lval[3];
+  const float* lpack[3];
+  /* appearance factors: [h][w][24], [n][24]; basis_t: [72][24] = rf.basis_mat.weight transposed (tensoRF.py:293) */
+  const float* aval[3];
+  const float* alval[3];
+  const float* basis_t;
+
+  /* microfacet material heads (modules/render_modules.py:447-574): head_w [11][24] rows = diffuse(3), tint(3),
+   * f0(3), roughness(2); head_b [11] */
+  const float* head_w;
+  const float* head_b;
+  float diffuse_mul, diffuse_bias, tint_bias, f0_bias, roughness_bias;
+  /* BRDF MLP (modules/brdf.py:73-120): transposed weights w0t [66][64], w1t [64][64], w2t [64][4]; biases */
+  const float* brdf_w0t; const float* brdf_b0;
+  const float* brdf_w1t; const float* brdf_b1;
+  const float* brdf_w2t; const float* brdf_b2;
+  float brdf_bias;
+  float anoise;            /* models/microfacet.py:297 */
+  const float* sobol;      /* [1024][2] brdf_samplers/base.py:6-9 */
+  const float* sh_conv;    /* [9][3] clamped-cosine-convolved SH of the env (integral_equirect.py:324-360, sh.py:149-157) */
+
+  /* environment (modules/integral_equirect.py): sat [eh][ew][4] (rgb + pad) summed-area table of exp(bg)/1000 */
+  const float* env_sat;
+  int env_h, env_w;
+  float env_mipbias;
+  float env_top[3], env_bot[3];   /* mean of first / last row of exp(bg) (:498-502) */
+
+  /* model=tensorf plumbing config: view MLP 135->128->128->3 (modules/render_modules.py:201-235), transposed */
+  const float* plain_w0t; const float* plain_b0;
+  const float* plain_w1t; const float* plain_b1;
+  const float* plain_w2t; const float* plain_b2;
+
+  /* bounce budgets: models/microfacet.py:327-349, modules/pt_selectors.py:5-60 */
+  int rays_per_ray;        /* 128 */
+  int max_brdf_rays1;      /* max_brdf_rays[1] = 450000 */
+  int max_retrace;         /* max_retrace_rays[0] = 1000; 0 disables the secondary level */
+  int model;               /* 0 = microfacet, 1 = plain view-MLP (models/tensorf.py) */
+} NmfScene;
+
+/* per-call render parameters */
+typedef struct NmfRender {
+  int n_rays;
+  int chunk;               /* renderer.py:60 chunk (4096): bounds the scope of the per-chunk retrace selection */
+  float focal;
+  uint64_t seed;           /* keyed RNG: every random number is a function of (seed, ray id, step, bounce ray) */
+  uint64_t ray_id0;        /* global index of rays[0] (so that a sharded / batched render draws the same numbers) */
+  float skip_eps;          /* shade a sample only if w >= skip_eps / n_valid(ray); 0 = shade every valid sample */
+  float t_cut;             /* stop evaluating density once transmittance < t_cut; 0 = never */
+  int white_bg;            /* 1: primary background is white (tensor_nerf.py:215,478) */
+} NmfRender;
+
+/* outputs of one TensorNeRF.forward in eval mode (modules/tensor_nerf.py:448-566, 657-673); any pointer may be NULL */
+typedef struct NmfImages {
+  float* rgb_map;          /* (n,3) */
+  float* acc_map;          /* (n)   */
+  float* depth;            /* (n)   */
+  float* world_normal;     /* (n,3) */
+  float* normal;           /* (n,3) */
+  float* termination_xyz;  /* (n,4) */
+  int64_t* surf_width;     /* (n)   */
+  float* cross_section;    /* (n,3) */
+  float* diffuse;          /* (n,3) */
+  float* tint;             /* (n,3) */
+  float* roughness;        /* (n,3) */
+  float* spec;             /* (n,3) */
+  float* albedo;           /* (n,3) */
+} NmfImages;
+
+/* per-chunk statistics, written on the device (int32 [n_chunks] each unless stated) */
+typedef struct NmfCounters {
+  int* n_samples0;         /* statistics["n_samples"][0]: valid primary samples of the chunk (tensor_nerf.py:266) */
+  int* n_samples1;         /* statistics["n_samples"][1]: valid samples of the retraced rays                       */
+  int* n_cand;             /* in-AABB candidate steps (occupancy lookups), level 0 + level 1                       */
+  int* n_bounce_rays0;     /* bounce rays drawn at recur 0                                                        */
+  int* n_bounce_rays1;     /* bounce rays drawn at recur 1 (all go to the environment)                            */
+  int* n_retrace;          /* rays actually re-traced (<= max_retrace)                                            */
+  int* n_shaded;           /* [2] (not per chunk): samples that survived the weight cut at level 0 / 1            */
+  unsigned* error;         /* [1] NMF_DEV_E_* bits                                                                 */
+} NmfCounters;
+
+int nmf_abi_version(void);
+
+/* Bytes of scratch nmf_render_rays needs for `n_rays` rays in chunks of `chunk`. */
+size_t nmf_workspace_bytes(const NmfScene* scene, int n_rays, int chunk);
+
+/* The fused path: replaces renderer.chunk_renderer (renderer.py:56-106) + TensorNeRF.forward
+ * (modules/tensor_nerf.py:210-674) in eval mode for all chunks of `rays` at once.
+ * rays: (n_rays, 6) [origin, direction].  workspace: nmf_workspace_bytes() bytes, 256-byte aligned. */
+int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const float* rays, const NmfImages* out,
+                    const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same, with HOST buffers: copies `rays_host` in and every non-NULL image / counter out on `stream`
+ * (the copies are asynchronous only if the host buffers are pinned).  `out_host` / `counters_host` hold HOST
+ * pointers; `rays_dev`, `out_dev`, `counters_dev` are the device staging buffers of the same shapes. */
+int nmf_render_rays_host(const NmfScene* scene, const NmfRender* rp, const float* rays_host, float* rays_dev,
+                         const NmfImages* out_host, const NmfImages* out_dev, const NmfCounters* counters_host,
+                         const NmfCounters* counters_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- plugin-slot operators (unfused; what the reference's duck-typed plugins expose) ---- */
+
+/* AlphaGridSampler.sample in eval mode (samplers/alphagrid.py:131-207, 278-370): dense validity mask
+ * ray_valid (n_rays, n_steps) uint8, z_vals (n_rays, n_steps), and the number of valid samples per ray. */
+int nmf_sample_rays(const NmfScene* scene, const float* rays, int n_rays, float near_override, uint8_t* ray_valid,
+                    float* z_vals, int* n_valid, void* stream);
+
+/* TensorVMSplit.compute_densityfeature (fields/tensoRF.py:392-400 + tensor_base.py:83-93): xyz (n, stride) */
+int nmf_vm_density(const NmfScene* scene, const float* xyz, int n, int stride, int activate, float* sigma, void* stream);
+/* TensorVMSplit.compute_appfeature (fields/tensoRF.py:402-405): -> (n, 24) */
+int nmf_vm_appfeature(const NmfScene* scene, const float* xyz, int n, int stride, float* feat, void* stream);
+/* TensorBase.compute_normals (fields/tensor_base.py:107-129, modules/grid_sample_Cinf.py:109-281): -> (n, 3) */
+int nmf_vm_normals(const NmfScene* scene, const float* xyz, int n, int stride, float* normals, void* stream);
+/* IntegralEquirect.forward (modules/integral_equirect.py:409-504): dirs (n,3), mip (n) -> (n,3) */
+int nmf_env_lookup(const NmfScene* scene, const float* dirs, const float* mip, int n, float* rgb, void* stream);
+/* GGXSampler.sample (brdf_samplers/ggx.py:61-226) for one bounce ray per row: u (n,2), V (n,3), N (n,3), r (n)
+ * -> L (n,3), logpdf (n), half_local (n,3), diff_local (n,3) */
+int nmf_ggx_sample(const float* u, const float* V, const float* N, const float* r, int n, float* L, float* logpdf,
+                   float* half_local, float* diff_local, void* stream);
+/* MLPBRDF.forward (modules/brdf.py:177-261): feat (n,24), half_local (n,3), diff_local (n,3), rough (n) -> (n,3) */
+int nmf_brdf_mlp(const NmfScene* scene, const float* feat, const float* half_local, const float* diff_local,
+                 const float* rough, int n, float* out, void* stream);
+/* RandHydraMLPDiffuse.forward (modules/render_modules.py:519-574): feat (n,24) -> albedo, tint, f0 (n,3), r1 (n) */
+int nmf_material_heads(const NmfScene* scene, const float* feat, int n, float* albedo, float* tint, float* f0,
+                       float* r1, void* stream);
+/* occupancy rebuild, alpha stage of AlphaGridSampler.getDenseAlpha (samplers/alphagrid.py:209-247):
+ * alpha[z][y][x] = 1 - exp(-sigma(lattice point) * stepsize) on a (gz,gy,gx) lattice spanning the aabb */
+int nmf_dense_alpha(const NmfScene* scene, int gx, int gy, int gz, float* alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMF_B200_H */

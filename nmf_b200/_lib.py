@@ -1,0 +1,125 @@
+"""ctypes binding of libnmf_b200.so (the C ABI declared in include/nmf_b200.h).
+
+The product path has no CPU fallback: if the CUDA library is missing, `lib()` raises.  Build it with
+`python -m nmf_b200.build` (or `__graft_entry__.build()`); the .so lives in-tree next to this file.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnmf_b200.so")
+
+c_float3 = C.c_float * 3
+c_int3 = C.c_int * 3
+c_ptr3 = C.c_void_p * 3
+
+
+class NmfScene(C.Structure):
+    _fields_ = [
+        ("aabb0", c_float3), ("aabb1", c_float3), ("inv_aabb2", c_float3),
+        ("stepsize", C.c_float), ("near", C.c_float), ("far", C.c_float),
+        ("distance_scale", C.c_float), ("density_shift", C.c_float),
+        ("n_steps", C.c_int),
+        ("plane_w", c_int3), ("plane_h", c_int3), ("line_n", c_int3),
+        ("occ_vox", C.c_void_p), ("occ_cell", C.c_void_p),
+        ("ow", C.c_int), ("oh", C.c_int), ("od", C.c_int), ("opitch", C.c_int), ("has_occ", C.c_int),
+        ("dval", c_ptr3), ("dpack", c_ptr3), ("lval", c_ptr3), ("lpack", c_ptr3),
+        ("aval", c_ptr3), ("alval", c_ptr3), ("basis_t", C.c_void_p),
+        ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+        ("diffuse_mul", C.c_float), ("diffuse_bias", C.c_float), ("tint_bias", C.c_float),
+        ("f0_bias", C.c_float), ("roughness_bias", C.c_float),
+        ("brdf_w0t", C.c_void_p), ("brdf_b0", C.c_void_p), ("brdf_w1t", C.c_void_p), ("brdf_b1", C.c_void_p),
+        ("brdf_w2t", C.c_void_p), ("brdf_b2", C.c_void_p),
+        ("brdf_bias", C.c_float), ("anoise", C.c_float),
+        ("sobol", C.c_void_p), ("sh_conv", C.c_void_p),
+        ("env_sat", C.c_void_p), ("env_h", C.c_int), ("env_w", C.c_int), ("env_mipbias", C.c_float),
+        ("env_top", c_float3), ("env_bot", c_float3),
+        ("plain_w0t", C.c_void_p), ("plain_b0", C.c_void_p), ("plain_w1t", C.c_void_p), ("plain_b1", C.c_void_p),
+        ("plain_w2t", C.c_void_p), ("plain_b2", C.c_void_p),
+        ("rays_per_ray", C.c_int), ("max_brdf_rays1", C.c_int), ("max_retrace", C.c_int), ("model", C.c_int),
+    ]
+
+
+class NmfRender(C.Structure):
+    _fields_ = [
+        ("n_rays", C.c_int), ("chunk", C.c_int), ("focal", C.c_float),
+        ("seed", C.c_uint64), ("ray_id0", C.c_uint64),
+        ("skip_eps", C.c_float), ("t_cut", C.c_float), ("white_bg", C.c_int),
+    ]
+
+
+IMAGE_FIELDS = ["rgb_map", "acc_map", "depth", "world_normal", "normal", "termination_xyz", "surf_width",
+                "cross_section", "diffuse", "tint", "roughness", "spec", "albedo"]
+COUNTER_FIELDS = ["n_samples0", "n_samples1", "n_cand", "n_bounce_rays0", "n_bounce_rays1", "n_retrace",
+                  "n_shaded", "error"]
+
+
+class NmfImages(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in IMAGE_FIELDS]
+
+
+class NmfCounters(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in COUNTER_FIELDS]
+
+
+class NmfError(RuntimeError):
+    pass
+
+
+_ERRORS = {-1: "NMF_E_ARG (null pointer or non-positive size)",
+           -2: "NMF_E_UNSUPPORTED (shape outside what the kernels are compiled for)",
+           -3: "NMF_E_WORKSPACE (workspace too small)"}
+DEV_ERRORS = {1: "surviving-sample list overflowed", 2: "bounce-sample list overflowed",
+              4: "a chunk's bounce-ray region overflowed"}
+
+
+def check(status, what):
+    if status == 0:
+        return
+    if status < 0:
+        raise NmfError(f"{what}: {_ERRORS.get(status, status)}")
+    raise NmfError(f"{what}: CUDA error {status}")
+
+
+_lib = None
+
+
+def lib():
+    """Loads libnmf_b200.so; raises (loudly) when it has not been built -- there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NmfError(f"{LIB_PATH} is missing: build it with `python -m nmf_b200.build` "
+                       "(nmf_b200 has no CPU / PyTorch fallback for the render path)")
+    L = C.CDLL(LIB_PATH)
+    P, I, F = C.c_void_p, C.c_int, C.c_float
+    SP, RP = C.POINTER(NmfScene), C.POINTER(NmfRender)
+    IP, CP = C.POINTER(NmfImages), C.POINTER(NmfCounters)
+    sigs = {
+        "nmf_abi_version": (I, []),
+        "nmf_workspace_bytes": (C.c_size_t, [SP, I, I]),
+        "nmf_render_rays": (I, [SP, RP, P, IP, CP, P, C.c_size_t, P]),
+        "nmf_render_rays_host": (I, [SP, RP, P, P, IP, IP, CP, CP, P, C.c_size_t, P]),
+        "nmf_sample_rays": (I, [SP, P, I, F, P, P, P, P]),
+        "nmf_vm_density": (I, [SP, P, I, I, I, P, P]),
+        "nmf_vm_appfeature": (I, [SP, P, I, I, P, P]),
+        "nmf_vm_normals": (I, [SP, P, I, I, P, P]),
+        "nmf_env_lookup": (I, [SP, P, P, I, P, P]),
+        "nmf_ggx_sample": (I, [P, P, P, P, I, P, P, P, P, P]),
+        "nmf_brdf_mlp": (I, [SP, P, P, P, P, I, P, P]),
+        "nmf_material_heads": (I, [SP, P, I, P, P, P, P, P]),
+        "nmf_dense_alpha": (I, [SP, I, I, I, P, P]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    assert L.nmf_abi_version() == 1, "libnmf_b200.so ABI mismatch: rebuild"
+    _lib = L
+    return L
+
+
+EXPORTED = ["nmf_abi_version", "nmf_workspace_bytes", "nmf_render_rays", "nmf_render_rays_host", "nmf_sample_rays",
+            "nmf_vm_density", "nmf_vm_appfeature", "nmf_vm_normals", "nmf_env_lookup", "nmf_ggx_sample",
+            "nmf_brdf_mlp", "nmf_material_heads", "nmf_dense_alpha"]

@@ -1,0 +1,241 @@
+"""Device-side scene: packs a reference-format state_dict into the layouts the kernels gather from.
+
+Everything here runs once per weight update (or once per checkpoint load), not per ray: it is host
+orchestration in PyTorch (plumbing), the per-ray work is in csrc/.  Layouts are described in DESIGN.md
+("HBM layout") and in include/nmf_b200.h (struct NmfScene).
+
+Reference behaviour restated here (file:line relative to the reference tree):
+  * stepsize / nSamples                    fields/tensor_base.py:219-232
+  * smoothed-difference derivative planes  modules/grid_sample_Cinf.py:24-29,49-63,118-121,218-242
+  * summed-area table of exp(bg)/1000      modules/integral_equirect.py:263-273,431-433
+  * SH irradiance coefficients             modules/integral_equirect.py:324-360, modules/sh.py:97-157
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+MAT_MODE = ((0, 1), (0, 2), (1, 2))   # fields/tensoRF.py:40
+VEC_MODE = (2, 1, 0)                  # fields/tensoRF.py:41
+
+DEFAULT_HP = dict(
+    distance_scale=25.0, density_shift=-4.0, step_ratio=0.5,                 # configs/field/tensorf.yaml
+    rays_per_ray=128, max_brdf_rays=(650000, 450000), max_retrace_rays=(1000,), anoise=0.25,
+    diffuse_bias=-0.619, diffuse_mul=1.5, roughness_bias=-1.0, tint_bias=0.0, f0_bias=0.0,
+    brdf_bias=0.0,                                                            # configs/model/microfacet_tensorf2.yaml
+    alpha_mask_thres=1e-3, model="microfacet",
+)
+
+
+def derivative_stencils():
+    """The two 5x5 stencils GridSampler2D.backward builds for smoothing=1: a 3x3 Gaussian (std 1, normalised)
+    convolved with a central difference (grid_sample_Cinf.py:24-29, 49-63, 218-236).  Returns (Kx, Ky)."""
+    blur = torch.tensor([0.0, 1.0, 0.0])
+    edge = -1 * torch.tensor([1, 0.0, -1]) / 2
+    dy = (blur[None, :] * edge[:, None]).reshape(1, 1, 3, 3)
+    dx = dy.permute(0, 1, 3, 2)
+    n = torch.arange(0, 3) - (3 - 1.0) / 2.0
+    g1 = torch.exp(-(n ** 2) / 2.0)
+    smooth = torch.outer(g1, g1)
+    smooth = (smooth / smooth.sum()).reshape(1, 1, 3, 3)
+    comb = lambda k: -F.conv2d(smooth, k, stride=1, padding=2)
+    return comb(dx), comb(dy)
+
+
+def step_size_and_count(aabb, grid_size, step_ratio):
+    aabb_size = aabb[1] - aabb[0]
+    gs = torch.as_tensor(list(grid_size), dtype=torch.long, device=aabb.device)
+    units = aabb_size / (gs - 1)
+    stepsize = torch.min(units) * step_ratio
+    diag = torch.sqrt(torch.sum(torch.square(aabb_size)))
+    return stepsize, int((diag / stepsize).item()) + 1
+
+
+def pack_bits(vol):
+    """(D,H,W) bool -> (int32 words, pitch): bit (z*H + y)*pitch + x."""
+    D, H, W = vol.shape
+    pitch = (W + 31) // 32 * 32
+    v = torch.zeros(D, H, pitch, dtype=torch.int64, device=vol.device)
+    v[..., :W] = vol.to(torch.int64)
+    shifts = torch.arange(32, device=vol.device, dtype=torch.int64)
+    words = (v.view(D, H, pitch // 32, 32) << shifts).sum(dim=-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+    return words.contiguous().view(-1), pitch
+
+
+def build_sat(bg_mat, brightness, mul):
+    """exp activation and summed-area table (integral_equirect.py:263-273, 431-433).  The reference runs two fp32
+    cumsums; on CPU ATen accumulates each in double and rounds every prefix to fp32, which is reproduced here
+    on any device so that the table does not depend on the scan order of a device cumsum."""
+    x = (brightness + mul * bg_mat).to(torch.float32)
+    act = torch.exp(x.clip(max=20))
+    c1 = torch.cumsum((act / 1000).double(), dim=2).float()
+    sat = torch.cumsum(c1.double(), dim=3).float()
+    return act, sat
+
+
+class DeviceScene:
+    """Owns the packed device tensors and the NmfScene struct that points at them."""
+
+    def __init__(self, state, aabb, near_far, grid_size, alpha_volume=None, device="cuda", sh_conv=None, **hp):
+        self.hp = dict(DEFAULT_HP)
+        self.hp.update(hp)
+        dev = torch.device(device)
+        self.device = dev
+        f32 = lambda t: torch.as_tensor(t).detach().to(device=dev, dtype=torch.float32).contiguous()
+        self.keep = {}
+        s = _lib.NmfScene()
+        aabb = f32(aabb)
+        aabb_size = aabb[1] - aabb[0]
+        inv2 = 2.0 / aabb_size
+        self.grid_size = [int(g) for g in grid_size]
+        stepsize, n_steps = step_size_and_count(aabb, self.grid_size, self.hp["step_ratio"])
+        self.stepsize = float(stepsize)
+        self.n_steps = n_steps
+        for i in range(3):
+            s.aabb0[i] = float(aabb[0, i])
+            s.aabb1[i] = float(aabb[1, i])
+            s.inv_aabb2[i] = float(inv2[i])
+        s.stepsize = self.stepsize
+        s.near, s.far = float(near_far[0]), float(near_far[1])
+        s.distance_scale = float(self.hp["distance_scale"])
+        s.density_shift = float(self.hp["density_shift"])
+        s.n_steps = n_steps
+        self.aabb = aabb
+        self.near_far = (float(near_far[0]), float(near_far[1]))
+
+        kx, ky = derivative_stencils()
+        kx, ky = kx.to(dev), ky.to(dev)
+        conv = lambda img, k: F.conv2d(img.permute(1, 0, 2, 3), k, stride=1, padding=(2, 2)).permute(1, 0, 2, 3)
+        for p in range(3):
+            dp = f32(state[f"rf.density_rf.app_plane.{p}"])
+            dl = f32(state[f"rf.density_rf.app_line.{p}"])
+            ap = f32(state[f"rf.app_rf.app_plane.{p}"])
+            al = f32(state[f"rf.app_rf.app_line.{p}"])
+            if dp.shape[1] != 16 or ap.shape[1] != 24:
+                raise _lib.NmfError("kernels are compiled for density_n_comp=16, appearance_n_comp=24")
+            H, W = dp.shape[2], dp.shape[3]
+            N = dl.shape[2]
+            s.plane_w[p], s.plane_h[p], s.line_n[p] = W, H, N
+            dval = dp[0].permute(1, 2, 0).contiguous()                                   # (H,W,16)
+            pdx, pdy = conv(dp, kx)[0].permute(1, 2, 0), conv(dp, ky)[0].permute(1, 2, 0)
+            dpack = torch.stack([dval.view(H, W, 4, 4), pdx.reshape(H, W, 4, 4), pdy.reshape(H, W, 4, 4)], dim=3)
+            dpack = dpack.reshape(H, W, 4, 12).contiguous()                              # [val4, dx4, dy4] per group
+            lval = dl[0, :, :, 0].permute(1, 0).contiguous()                             # (N,16)
+            ldy = conv(dl, ky)[0, :, :, 0].permute(1, 0)
+            lpack = torch.stack([lval.view(N, 4, 4), ldy.reshape(N, 4, 4)], dim=2).reshape(N, 4, 8).contiguous()
+            aval = ap[0].permute(1, 2, 0).contiguous()                                   # (H,W,24)
+            alval = al[0, :, :, 0].permute(1, 0).contiguous()                            # (N,24)
+            for name, t, arr in (("dval", dval, s.dval), ("dpack", dpack, s.dpack), ("lval", lval, s.lval),
+                                 ("lpack", lpack, s.lpack), ("aval", aval, s.aval), ("alval", alval, s.alval)):
+                self.keep[f"{name}{p}"] = t
+                arr[p] = t.data_ptr()
+        basis = f32(state["rf.basis_mat.weight"])
+        if tuple(basis.shape) != (24, 72):
+            raise _lib.NmfError("kernels are compiled for app_dim=24")
+        self._ptr(s, "basis_t", basis.t().contiguous())
+
+        model = self.hp["model"]
+        s.model = 0 if model == "microfacet" else 1
+        if model == "microfacet":
+            g = lambda k: f32(state[k])
+            hw = torch.cat([g(f"model.diffuse_module.{h}_mlp.0.weight") for h in ("diffuse", "tint", "f0", "roughness")])
+            hb = torch.cat([g(f"model.diffuse_module.{h}_mlp.0.bias") for h in ("diffuse", "tint", "f0", "roughness")])
+            assert tuple(hw.shape) == (11, 24), hw.shape
+            self._ptr(s, "head_w", hw.contiguous())
+            self._ptr(s, "head_b", hb.contiguous())
+            for i, li in enumerate((0, 2, 4)):
+                w, b = g(f"model.brdf.mlp.{li}.weight"), g(f"model.brdf.mlp.{li}.bias")
+                self._ptr(s, f"brdf_w{i}t", w.t().contiguous())
+                self._ptr(s, f"brdf_b{i}", b)
+            assert tuple(self.keep["brdf_w0t"].shape) == (66, 64) and tuple(self.keep["brdf_w2t"].shape) == (64, 4)
+            sob = g("model.brdf_sampler.angs")
+            assert sob.shape[0] >= 400 and sob.shape[1] == 2
+            self._ptr(s, "sobol", sob)
+        else:
+            for i, li in enumerate((0, 2, 4)):
+                w, b = f32(state[f"model.diffuse_module.mlp.{li}.weight"]), f32(state[f"model.diffuse_module.mlp.{li}.bias"])
+                self._ptr(s, f"plain_w{i}t", w.t().contiguous())
+                self._ptr(s, f"plain_b{i}", b)
+            assert tuple(self.keep["plain_w0t"].shape) == (135, 128) and tuple(self.keep["plain_w2t"].shape) == (128, 3)
+        for k in ("diffuse_mul", "diffuse_bias", "tint_bias", "f0_bias", "roughness_bias", "brdf_bias", "anoise"):
+            setattr(s, k, float(self.hp[k]))
+        s.rays_per_ray = int(self.hp["rays_per_ray"])
+        s.max_brdf_rays1 = int(self.hp["max_brdf_rays"][1]) if len(self.hp["max_brdf_rays"]) > 1 else 0
+        s.max_retrace = int(self.hp["max_retrace_rays"][0]) if len(self.hp["max_retrace_rays"]) > 0 else 0
+
+        # environment
+        bg = f32(state["bg_module.bg_mat"])
+        to64 = lambda k, d: torch.as_tensor(state.get(k, d)).detach().to(device=dev, dtype=torch.float64)
+        brightness, mul = to64("bg_module.brightness", 0.0), to64("bg_module.mul", 1.0)
+        act, sat = build_sat(bg, brightness, mul)
+        eh, ew = bg.shape[-2], bg.shape[-1]
+        sat4 = torch.zeros(eh, ew, 4, device=dev, dtype=torch.float32)
+        sat4[..., :3] = sat[0].permute(1, 2, 0)
+        self._ptr(s, "env_sat", sat4.contiguous())
+        s.env_h, s.env_w = eh, ew
+        s.env_mipbias = float(to64("bg_module.mipbias", 1.0))
+        top, bot = act[0, :, 0, :].mean(dim=-1), act[0, :, -1, :].mean(dim=-1)
+        for i in range(3):
+            s.env_top[i] = float(top[i])
+            s.env_bot[i] = float(bot[i])
+        self.env_act = act
+        self.c = s
+        self.set_alpha_volume(alpha_volume)
+        if model == "microfacet":
+            if sh_conv is None:
+                sh_conv = self.sh_irradiance()
+            self._ptr(s, "sh_conv", f32(sh_conv))
+
+    def _ptr(self, s, name, t):
+        self.keep[name] = t
+        setattr(s, name, t.data_ptr())
+
+    def set_alpha_volume(self, alpha_volume):
+        """alpha_volume: (Gz,Gy,Gx) 0/1 (AlphaGridMask.alpha_volume, samplers/alphagrid.py:6-21) or None."""
+        s = self.c
+        if alpha_volume is None:
+            s.has_occ = 0
+            s.ow = s.oh = s.od = s.opitch = 0
+            s.occ_vox = s.occ_cell = None
+            self.alpha_volume = None
+            return
+        vol = torch.as_tensor(alpha_volume).to(self.device)
+        vol = vol.reshape(vol.shape[-3:]) > 0
+        D, H, W = vol.shape
+        pad = F.pad(vol.float()[None, None], (0, 1, 0, 1, 0, 1))
+        cell = F.max_pool3d(pad, kernel_size=2, stride=1)[0, 0] > 0
+        vox_bits, pitch = pack_bits(vol)
+        cell_bits, _ = pack_bits(cell)
+        self.keep["occ_vox"], self.keep["occ_cell"] = vox_bits, cell_bits
+        s.occ_vox, s.occ_cell = vox_bits.data_ptr(), cell_bits.data_ptr()
+        s.ow, s.oh, s.od, s.opitch, s.has_occ = W, H, D, pitch, 1
+        self.alpha_volume = vol
+
+    def sh_irradiance(self, G=100, mipval=-5.0):
+        """get_spherical_harmonics(100) (integral_equirect.py:324-360) convolved with the clamped-cosine lobe
+        (sh.py:149-157), divided by pi (models/microfacet.py:304-316): (9,3).  Uses the CUDA env lookup."""
+        from . import ops
+        dev = self.device
+        _t = torch.linspace(0, math.pi, G // 2)
+        _p = torch.linspace(0, 2 * math.pi, G)
+        theta, phi = torch.meshgrid(_t, _p, indexing="ij")
+        dirs = torch.stack([torch.sin(theta) * torch.cos(phi), torch.sin(theta) * torch.sin(phi), torch.cos(theta)],
+                           dim=-1).reshape(-1, 3).to(dev)
+        n = dirs.shape[0]
+        bg = ops.env_lookup(self, dirs, torch.full((n,), mipval, device=dev))
+        x, y, z = dirs.unbind(-1)
+        c2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+        ev = torch.stack([torch.full_like(x, 0.28209479177387814), 0.4886025119029199 * y, 0.4886025119029199 * z,
+                          0.4886025119029199 * x, c2[0] * (x * y), c2[1] * (y * z), c2[2] * (3 * (z * z) - 1),
+                          c2[3] * (x * z), c2[4] * (x * x - y * y)], dim=-1)
+        st = torch.sin(theta).reshape(n, 1, 1).to(dev)
+        coeffs = 2 * math.pi ** 2 * (bg.reshape(n, 1, 3) * ev.reshape(n, -1, 1) * st).mean(dim=0)
+        al2 = torch.tensor([math.pi] + [2 * math.pi / 3] * 3 + [math.pi / 4] * 5, device=dev)
+        return al2.reshape(-1, 1) * coeffs / math.pi
+
+    def ref(self):
+        return C.byref(self.c)

@@ -1,0 +1,154 @@
+"""The kernels' per-element math (nmf_b200/csrc/nmf_math.cuh, nmf_field.cuh), compiled for the host by
+tests/hostcheck, against the oracle.  No GPU needed: this catches arithmetic / layout mistakes before a GPU run.
+The same header functions are what the CUDA kernels call, the warp-level orchestration is covered by `-m gpu`."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import device_scene, load_fixture, oracle_scene
+from oracle import keyed_rng as KR
+from oracle import nmf_oracle as O
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.fixture(scope="module")
+def scenes():
+    fix = load_fixture("microfacet_g40")
+    osc = oracle_scene(fix)
+    dsc = device_scene(fix, "cpu", sh_conv=O.sh_irradiance_coeffs(osc))
+    return fix, osc, dsc
+
+
+def test_keyed_rng(hostcheck):
+    g = np.random.RandomState(0)
+    a = g.randint(0, 2 ** 63, size=1000, dtype=np.int64).astype(np.uint64)
+    b = g.randint(0, 5000, size=1000, dtype=np.int64).astype(np.uint64)
+    out = np.zeros(1000, dtype=np.uint64)
+    hostcheck.hc_mix64(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), 1000, out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, KR.mix64(a, b))
+    u = torch.zeros(1000)
+    hostcheck.hc_uniform(a.ctypes.data_as(C.c_void_p), C.c_uint32(KR.STREAM_BOUNCE), 1000, ptr(u))
+    assert torch.equal(u, KR.uniform(a, KR.STREAM_BOUNCE))
+    n = torch.zeros(1000)
+    hostcheck.hc_normal(a.ctypes.data_as(C.c_void_p), C.c_uint32(3), C.c_uint32(67), 1000, ptr(n))
+    assert torch.allclose(n, KR.normal(a, 3, 67), atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_g56_ship", "plain_g64"])
+def test_sampler_mask_bit_exact(hostcheck, name):
+    fix = load_fixture(name)
+    osc = oracle_scene(fix)
+    dsc = device_scene(fix, "cpu", sh_conv=torch.zeros(9, 3))
+    rays = fix["rays"][:512].contiguous()
+    for override in (None, 3 * float(osc.stepsize)):
+        _, valid, z, _ = O.sample_rays(osc, rays, fix["focal"], override)
+        S = osc.n_samples
+        assert dsc.n_steps == S and dsc.stepsize == float(osc.stepsize)
+        v = torch.zeros(rays.shape[0], S, dtype=torch.uint8)
+        zz = torch.zeros(rays.shape[0], S)
+        hostcheck.hc_sample_rays(dsc.ref(), ptr(rays), rays.shape[0], C.c_float(-1.0 if override is None else override),
+                                 ptr(v), ptr(zz))
+        assert torch.equal(zz, z)
+        assert torch.equal(v.bool(), valid), (v.bool() != valid).sum()
+        assert valid.sum() > 1000
+
+
+def test_sampler_mask_on_lattice_points(hostcheck, scenes):
+    """rays that run exactly along lattice planes (zero trilinear weights) and axis-parallel rays"""
+    fix, osc, dsc = scenes
+    G = fix["grid_size"]
+    lin = torch.linspace(-1.5, 1.5, G)
+    rays = []
+    for i in range(0, G, 3):
+        rays.append([float(lin[i]), -4.0, float(lin[(i * 7) % G]), 0.0, 1.0, 0.0])
+        rays.append([-4.0, float(lin[i]), float(lin[(i * 5) % G]), 1.0, 0.0, 0.0])
+        rays.append([float(lin[i]), float(lin[(i * 3) % G]), 4.0, 0.0, 0.0, -1.0])
+    rays = torch.tensor(rays)
+    _, valid, z, _ = O.sample_rays(osc, rays, fix["focal"])
+    v = torch.zeros(rays.shape[0], osc.n_samples, dtype=torch.uint8)
+    zz = torch.zeros(rays.shape[0], osc.n_samples)
+    hostcheck.hc_sample_rays(dsc.ref(), ptr(rays), rays.shape[0], C.c_float(-1.0), ptr(v), ptr(zz))
+    assert torch.equal(v.bool(), valid)
+    assert valid.sum() > 100
+
+
+def test_vm_queries(hostcheck, scenes):
+    fix, osc, dsc = scenes
+    xyz, valid, z, _ = O.sample_rays(osc, fix["rays"][:256], fix["focal"])
+    xyz = xyz.contiguous()
+    n = xyz.shape[0]
+    sig = torch.zeros(n)
+    hostcheck.hc_vm_density(dsc.ref(), ptr(xyz), n, 4, 1, ptr(sig))
+    ref = O.feature2density(osc, O.density_feature(osc, xyz))
+    assert torch.allclose(sig, ref, rtol=2e-5, atol=1e-6), (sig - ref).abs().max()
+    feat = torch.zeros(n, 24)
+    hostcheck.hc_vm_appfeature(dsc.ref(), ptr(xyz), n, 4, ptr(feat))
+    assert torch.allclose(feat, O.app_feature(osc, xyz), atol=2e-6)
+    nrm = torch.zeros(n, 3)
+    hostcheck.hc_vm_normals(dsc.ref(), ptr(xyz), n, 4, ptr(nrm))
+    refn = O.vm_normals(osc, xyz)
+    # normals of near-empty space are normalised noise; compare where the gradient is well defined
+    sel = ref > 1e-2
+    assert sel.sum() > 100
+    assert torch.allclose(nrm[sel], refn[sel], atol=2e-4), (nrm[sel] - refn[sel]).abs().max()
+
+
+def test_env_lookup(hostcheck, scenes):
+    fix, osc, dsc = scenes
+    g = torch.Generator().manual_seed(0)
+    n = 20000
+    d = O.unit(torch.randn(n, 3, generator=g))
+    # include poles, the seam and axis directions
+    d[:6] = torch.tensor([[0, 0, 1.0], [0, 0, -1.0], [-1.0, 1e-4, 0.0], [-1.0, -1e-4, 0.0], [1.0, 0, 0], [0, 1.0, 0]])
+    d[6:200, 2] = d[6:200, 2].sign() * 0.999
+    d[6:200] = O.unit(d[6:200])
+    mip = torch.rand(n, generator=g) * 14 - 10
+    out = torch.zeros(n, 3)
+    hostcheck.hc_env_lookup(dsc.ref(), ptr(d.contiguous()), ptr(mip), n, ptr(out))
+    ref = O.env_lookup(osc, d, mip)
+    err = (out - ref).abs() / (ref.abs() + 1e-2)
+    # fp32 SAT differences cancel catastrophically for sub-pixel boxes (SURVEY section 7 hard part 4)
+    assert err.max() < 5e-2 and err.mean() < 2e-4, (err.max(), err.mean())
+
+
+def test_ggx_and_bases(hostcheck):
+    g = torch.Generator().manual_seed(1)
+    n = 20000
+    N = O.unit(torch.randn(n, 3, generator=g))
+    N[:50] = torch.tensor([0.0, 0.0, 1.0])
+    N[50:100] = torch.tensor([0.0, 0.0, -1.0])
+    V = O.unit(torch.randn(n, 3, generator=g))
+    N = N * (V * N).sum(-1, keepdim=True).sign()
+    r = (torch.rand(n, 1, generator=g) * 0.49 + 0.01)
+    r[:10] = 0.01
+    u = torch.rand(n, 2, generator=g)
+    mask = torch.ones(n, 1, dtype=torch.bool)
+    L, cols, lpdf = O.ggx_sample(u[:, :1], u[:, 1:], V, N, r, mask)
+    H = O.unit((V + L) / 2)
+    to_local = cols.permute(0, 2, 1)
+    diff_l = torch.matmul(to_local, L.unsqueeze(-1)).squeeze(-1)
+    half_l = torch.matmul(to_local, H.unsqueeze(-1)).squeeze(-1)
+    oL, olp, oh, od = torch.zeros(n, 3), torch.zeros(n), torch.zeros(n, 3), torch.zeros(n, 3)
+    hostcheck.hc_ggx(ptr(u.contiguous()), ptr(V.contiguous()), ptr(N.contiguous()), ptr(r.contiguous()), n,
+                     ptr(oL), ptr(olp), ptr(oh), ptr(od))
+    ok = (oL - L).abs().max(dim=1).values < 1e-3
+    assert ok.float().mean() > 0.999        # grazing reflections amplify rounding
+    assert (oL - L).abs().median() < 1e-6
+    assert (olp - lpdf).abs().median() < 1e-5 and ((olp - lpdf).abs() < 1e-2).float().mean() > 0.999
+    assert (oh - half_l).abs().median() < 1e-6 and (od - diff_l).abs().median() < 1e-6
+    ish = torch.zeros(n, 18)
+    hostcheck.hc_ish18(ptr(half_l.contiguous()), ptr(r.contiguous()), n, ptr(ish))
+    assert torch.allclose(ish, O.ish18(half_l, r), atol=2e-6)
+    sh = torch.zeros(n, 9)
+    hostcheck.hc_sh9(ptr(N.contiguous()), n, ptr(sh))
+    assert torch.allclose(sh, O.sh9(N), atol=1e-6)
+    x = torch.rand(n, generator=g) * 2
+    y = torch.zeros(n)
+    hostcheck.hc_srgb(ptr(x), n, ptr(y))
+    assert torch.allclose(y, O.srgb(x, noclip=True), atol=1e-6)
