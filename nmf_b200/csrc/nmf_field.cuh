@@ -7,11 +7,17 @@
 
 #ifdef __CUDACC__
 typedef float4 nmf_f4;
-#define NMF_LD4(p) __ldg((const float4*)(p))
 #else
 struct nmf_f4 { float x, y, z, w; };
-#define NMF_LD4(p) (*(const nmf_f4*)(p))
 #endif
+NMF_HD nmf_f4 nmf_ld4(const float* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg((const float4*)p);     // read-only path, one 16-byte load
+#else
+  return *(const nmf_f4*)p;
+#endif
+}
+#define NMF_LD4(p) nmf_ld4(p)
 
 NMF_HD nmf_f4 nmf_f4_zero() { nmf_f4 r; r.x = r.y = r.z = r.w = 0.f; return r; }
 NMF_HD void nmf_f4_fma(nmf_f4& a, nmf_f4 v, float w) { a.x += v.x * w; a.y += v.y * w; a.z += v.z * w; a.w += v.w * w; }

@@ -1,0 +1,1326 @@
+// nmf_b200 -- sm_100a kernels of the NMF per-ray render path and the C ABI over them (include/nmf_b200.h).
+//
+// One call of nmf_render_rays renders every chunk of a ray batch with a fixed sequence of launches (no host
+// synchronisation, CUDA-graph capturable).  Phases (DESIGN.md "Kernels"):
+//   k_march<0>    warp per ray: slab test, dense step enumeration, AABB + occupancy-bit test (bit-exact),
+//                 VM density gather (4 lanes per sample), transmittance scan, warp-compacted survivor list
+//   k_shade<0>    8 lanes per surviving sample: appearance gather + basis GEMV, smoothed-gradient normal,
+//                 material heads, SH irradiance, bounce count, debug-map accumulation, bounce-sample records
+//   k_bounce<0>   thread per bounce ray: Sobol + GGX VNDF sample, ISH encodings, BRDF MLP, retrace score
+//   k_select      CTA per chunk: radix-select of the top max_retrace scores -> secondary rays
+//   k_march<1> .. k_bounce<1> (environment lookup fused) .. k_reduce<1>, k_finish1: the retraced rays
+//   k_incoming    per primary bounce ray: retraced radiance or environment lookup, Fresnel mix
+//   k_reduce<0>   per bounce sample: mean over its rays, composite into the pixel
+//   k_finish0     per ray: tonemap, background, auxiliary maps
+#include <cuda_runtime.h>
+
+#include "nmf_field.cuh"
+
+#define FULL 0xffffffffu
+#define NMF_BRAY_CAP_PER_RAY 160   // bounce rays per primary ray a chunk region can hold (typical: 57)
+#define NMF_SURV0_PER_RAY 64       // surviving samples per primary ray (typical: 10-20)
+#define NMF_BS0_PER_RAY 24         // bounce samples per primary ray (typical: 12)
+#define NMF_SURV1_PER_RAY 256      // per retraced ray
+#define NMF_BS1_PER_RAY 128
+
+struct Surv { uint32_t ray; uint32_t step; float w; };
+
+struct __align__(16) BSample {
+  float pos[3]; float w;
+  float V[3]; float rough;
+  float N[3]; int count;
+  float f0[3]; uint32_t ray;
+  float diffuse[3]; uint32_t roff;
+  float fresn[3]; uint32_t flags;
+  uint64_t key; uint32_t chunk; uint32_t pad;
+  float feat[24];
+};
+
+struct __align__(16) BRay {
+  float L[3]; float mip;
+  float bw[3]; float score;
+  float comb[3]; int slot;
+  float inc[3]; uint32_t owner;
+};
+
+// per-ray accumulators of level 0 (floats)
+enum { A_RGB = 0, A_WN = 3, A_CROSS = 6, A_DIFF = 9, A_TINT = 12, A_SPEC = 15, A_ALB = 18, A_ROUGH = 21, A_N = 24 };
+
+struct WS {
+  // counters (zeroed every call)
+  int* n_surv;        // [2]
+  int* n_bs;          // [2]
+  int* ray_count0;    // [n_chunks]
+  int* ray_count1;    // [n_chunks]
+  int* n_samples0;    // [n_chunks]
+  int* n_samples1;    // [n_chunks]
+  int* n_cand;        // [n_chunks]
+  int* n_sec;         // [n_chunks]
+  float* score_sum;   // [n_chunks]
+  double* wsum1;      // [n_chunks]
+  unsigned* error;    // [1]
+  size_t counters_bytes;
+  char* counters_base;
+  // level 0
+  float* tmin0; float* acc0; float* depth0; int* termk0; int* nvalid0; float* accum0;   // accum0 [n_rays][A_N]
+  Surv* surv0; BSample* bs0; BRay* brays0; uint32_t* owner0;
+  // level 1
+  float* rays1; float* mip1; uint64_t* key1; float* tmin1; float* acc1; int* nvalid1; float* accum1; float* rgb1;
+  Surv* surv1; BSample* bs1; BRay* brays1; uint32_t* owner1;
+  int n_chunks, n_rays1;
+  int cap_surv0, cap_bs0, cap_rays0;   // cap_rays0: per chunk
+  int cap_surv1, cap_bs1, cap_rays1;   // cap_rays1: per chunk
+  size_t total;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
+  int nc = (n_rays + chunk - 1) / chunk;
+  int maxre = s->model == 0 ? s->max_retrace : 0;
+  w.n_chunks = nc;
+  w.n_rays1 = nc * maxre;
+  w.cap_surv0 = n_rays * NMF_SURV0_PER_RAY;
+  w.cap_bs0 = n_rays * NMF_BS0_PER_RAY;
+  w.cap_rays0 = chunk * NMF_BRAY_CAP_PER_RAY;
+  w.cap_surv1 = w.n_rays1 * NMF_SURV1_PER_RAY;
+  w.cap_bs1 = w.n_rays1 * NMF_BS1_PER_RAY;
+  w.cap_rays1 = maxre > 0 ? s->max_brdf_rays1 + 1024 : 0;
+  w.counters_base = take(0);
+  w.n_surv = (int*)take(2 * sizeof(int));
+  w.n_bs = (int*)take(2 * sizeof(int));
+  w.ray_count0 = (int*)take(nc * sizeof(int));
+  w.ray_count1 = (int*)take(nc * sizeof(int));
+  w.n_samples0 = (int*)take(nc * sizeof(int));
+  w.n_samples1 = (int*)take(nc * sizeof(int));
+  w.n_cand = (int*)take(nc * sizeof(int));
+  w.n_sec = (int*)take(nc * sizeof(int));
+  w.score_sum = (float*)take(nc * sizeof(float));
+  w.wsum1 = (double*)take(nc * sizeof(double));
+  w.error = (unsigned*)take(sizeof(unsigned));
+  w.accum0 = (float*)take((size_t)n_rays * A_N * sizeof(float));
+  w.accum1 = (float*)take((size_t)w.n_rays1 * 4 * sizeof(float));
+  w.counters_bytes = off;   // everything up to here is zeroed at the start of a call
+  w.tmin0 = (float*)take((size_t)n_rays * 4);
+  w.acc0 = (float*)take((size_t)n_rays * 4);
+  w.depth0 = (float*)take((size_t)n_rays * 4);
+  w.termk0 = (int*)take((size_t)n_rays * 4);
+  w.nvalid0 = (int*)take((size_t)n_rays * 4);
+  w.surv0 = (Surv*)take((size_t)w.cap_surv0 * sizeof(Surv));
+  if (s->model == 0) {
+    w.bs0 = (BSample*)take((size_t)w.cap_bs0 * sizeof(BSample));
+    w.brays0 = (BRay*)take((size_t)nc * w.cap_rays0 * sizeof(BRay));
+    w.owner0 = (uint32_t*)take((size_t)nc * w.cap_rays0 * 4);
+    w.rays1 = (float*)take((size_t)w.n_rays1 * 6 * 4);
+    w.mip1 = (float*)take((size_t)w.n_rays1 * 4);
+    w.key1 = (uint64_t*)take((size_t)w.n_rays1 * 8);
+    w.tmin1 = (float*)take((size_t)w.n_rays1 * 4);
+    w.acc1 = (float*)take((size_t)w.n_rays1 * 4);
+    w.nvalid1 = (int*)take((size_t)w.n_rays1 * 4);
+    w.rgb1 = (float*)take((size_t)w.n_rays1 * 4 * 4);
+    w.surv1 = (Surv*)take((size_t)w.cap_surv1 * sizeof(Surv));
+    w.bs1 = (BSample*)take((size_t)w.cap_bs1 * sizeof(BSample));
+    w.brays1 = (BRay*)take((size_t)nc * w.cap_rays1 * sizeof(BRay));
+    w.owner1 = (uint32_t*)take((size_t)nc * w.cap_rays1 * 4);
+  }
+  w.total = off;
+}
+
+// ================================================================================================
+// k_march: samplers/alphagrid.py:131-207,278-370 + fields/tensoRF.py:392-400 + tensor_nerf.py:19-35
+// ================================================================================================
+struct MarchArgs {
+  const float* rays;       // level 0: (n,6); level 1: ws.rays1
+  int n;                   // rays (level 1: slots)
+  int group;               // rays per chunk (level 0: chunk; level 1: max_retrace)
+  const int* n_active;     // level 1: n_sec[chunk]
+  const uint64_t* keys;    // level 1
+  uint64_t seed, ray_id0;
+  float skip_eps, t_cut;
+  float* tmin; float* acc; float* depth; int* termk; int* nvalid;
+  int* n_samples; int* n_cand; double* wsum;
+  Surv* surv; int* n_surv; int cap_surv; unsigned* error;
+};
+
+template <int LEVEL>
+__global__ void __launch_bounds__(256) k_march(const NmfScene s, const MarchArgs a) {
+  __shared__ uint16_t s_list[8][NMF_MAX_STEPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = s.n_steps;
+  const unsigned lt = (1u << lane) - 1u;
+  uint16_t* list = s_list[warp];
+  for (int ray = blockIdx.x * 8 + warp; ray < a.n; ray += gridDim.x * 8) {
+    const int chunk = ray / a.group;
+    if (LEVEL == 1 && (ray - chunk * a.group) >= a.n_active[chunk]) continue;
+    float o[3], d[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { o[i] = __ldg(a.rays + (size_t)ray * 6 + i); d[i] = __ldg(a.rays + (size_t)ray * 6 + 3 + i); }
+    const float near_ = LEVEL == 0 ? s.near : NMF_MUL(3.0f, s.stepsize);     // tensor_nerf.py:302 override_near
+    const float tmin = nmf_ray_tmin(o, d, s.aabb0, s.aabb1, near_, s.far);
+    uint64_t key = 0;
+    if (LEVEL == 1) key = a.keys[ray];
+    // ---- pass A: enumerate the dense steps, keep those inside the box and in an occupied cell ----
+    int nv = 0, cand = 0;
+    float usum = 0.f;
+    for (int k0 = 0; k0 < S; k0 += 32) {
+      const int k = k0 + lane;
+      bool ok = false;
+      if (k < S) {
+        float p[3];
+        nmf_step_pos(o, d, nmf_step_z(tmin, s.stepsize, k), p);
+        if (nmf_inside(p, s.aabb0, s.aabb1)) {
+          ++cand;
+          ok = true;
+          if (s.has_occ) {
+            float xn[3];
+            nmf_normalize_xyz(s, p, xn);
+            ok = nmf_occupied(s.occ_vox, s.occ_cell, s.ow, s.oh, s.od, s.opitch, xn[0], xn[1], xn[2]);
+          }
+        }
+        if (LEVEL == 1) usum += nmf_uniform(nmf_mix64(key, (uint64_t)k), NMF_STREAM_BOUNCE);   // pt_selectors.py:25
+      }
+      const unsigned m = __ballot_sync(FULL, ok);
+      if (ok) list[nv + __popc(m & lt)] = (uint16_t)k;
+      nv += __popc(m);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cand += __shfl_xor_sync(FULL, cand, off);
+    // ---- pass B: density of the valid samples (4 lanes per sample), transmittance, weights ----
+    const int sub = lane & 3, sj = lane >> 2;
+    const float wcut = a.skip_eps > 0.f ? a.skip_eps / (float)max(nv, 1) : 0.f;
+    float T = 1.f, acc = 0.f, depth = 0.f, best_w = 0.f;
+    int best_k = 0;
+    for (int j0 = 0; j0 < nv; j0 += 8) {
+      const int j = j0 + sj;
+      const bool active = j < nv;
+      const int k = active ? (int)list[j] : 0;
+      const float z = nmf_step_z(tmin, s.stepsize, k);
+      float p[3], xn[3];
+      nmf_step_pos(o, d, z, p);
+      nmf_normalize_xyz(s, p, xn);
+      const NmfTaps t = nmf_vm_taps(s, xn);
+      float f = nmf_density_group(s, t, sub);
+      f += __shfl_xor_sync(FULL, f, 1);
+      f += __shfl_xor_sync(FULL, f, 2);
+      const float sigma = active ? nmf_feature2density(f, s.density_shift) : 0.f;
+      const float z1 = (k + 1 < S) ? nmf_step_z(tmin, s.stepsize, k + 1) : z;       // alphagrid.py:348-350
+      const float dist = NMF_SUB(z1, z) * s.distance_scale;
+      const float alpha = 1.0f - expf(-sigma * dist);                                // tensor_nerf.py:25
+      float incl = (1.0f - alpha) + 1e-10f;                                          // :28
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) {
+        const float v = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl *= v;
+      }
+      float excl = __shfl_up_sync(FULL, incl, 4);
+      if (lane < 4) excl = 1.f;
+      const float w = alpha * (T * excl);
+      T *= __shfl_sync(FULL, incl, 31);
+      const bool mine = active && sub == 0;
+      if (mine) {
+        acc += w;
+        depth += w * z;
+        if (w > best_w) { best_w = w; best_k = k; }
+      }
+      const bool keep = mine && w > 0.f && w >= wcut;
+      const unsigned km = __ballot_sync(FULL, keep);
+      if (km) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.n_surv, __popc(km));
+        base = __shfl_sync(FULL, base, 0);
+        if (keep) {
+          const int idx = base + __popc(km & lt);
+          if (idx < a.cap_surv) {
+            Surv sv; sv.ray = (uint32_t)ray; sv.step = (uint32_t)k; sv.w = w;
+            a.surv[idx] = sv;
+          } else {
+            atomicOr(a.error, NMF_DEV_E_SURVIVORS);
+          }
+        }
+      }
+      if (a.t_cut > 0.f && T < a.t_cut) break;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      acc += __shfl_xor_sync(FULL, acc, off);
+      depth += __shfl_xor_sync(FULL, depth, off);
+      const float ow = __shfl_xor_sync(FULL, best_w, off);
+      const int ok_ = __shfl_xor_sync(FULL, best_k, off);
+      if (ow > best_w || (ow == best_w && ok_ < best_k)) { best_w = ow; best_k = ok_; }
+    }
+    if (LEVEL == 1) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) usum += __shfl_xor_sync(FULL, usum, off);
+    }
+    if (lane == 0) {
+      // tensor_nerf.py:505-511: termination point = sample of maximal weight (first index on ties)
+      int tk = best_k;
+      if (!(best_w > 0.f)) tk = (nv > 0 && list[0] == 0) ? 0 : -1;
+      a.tmin[ray] = tmin;
+      a.acc[ray] = acc;
+      a.nvalid[ray] = nv;
+      if (LEVEL == 0) { a.depth[ray] = depth; a.termk[ray] = tk; }
+      if (nv) atomicAdd(a.n_samples + chunk, nv);
+      if (cand) atomicAdd(a.n_cand + chunk, cand);
+      if (LEVEL == 1) atomicAdd(a.wsum + chunk, (double)acc + 1e-3 * (double)usum);
+    }
+    __syncwarp();
+  }
+}
+
+// ================================================================================================
+// k_shade: fields/tensoRF.py:402-405, tensor_base.py:107-129, render_modules.py:553-560,
+//          models/microfacet.py:295-349, pt_selectors.py:5-60
+// ================================================================================================
+struct ShadeArgs {
+  const float* rays; const float* tmin;
+  const uint64_t* keys;     // level 1
+  uint64_t seed, ray_id0;
+  int group;                // rays per chunk at this level
+  const Surv* surv; const int* n_surv; int cap_surv;
+  float* accum;             // level 0: [n][A_N]
+  BSample* bs; int* n_bs; int cap_bs;
+  int* ray_count; int cap_rays; uint32_t* owner;
+  const int* n_samples; const double* wsum;   // level 1 budget
+  unsigned* error;
+};
+
+template <int LEVEL>
+__global__ void __launch_bounds__(256) k_shade(const NmfScene s, const ShadeArgs a) {
+  __shared__ float s_basis[72 * 24];
+  __shared__ float s_headw[11 * 24];
+  __shared__ float s_headb[11];
+  __shared__ float s_sh[27];
+  __shared__ float s_coef[32][73];
+  for (int i = threadIdx.x; i < 72 * 24; i += 256) s_basis[i] = s.basis_t[i];
+  for (int i = threadIdx.x; i < 11 * 24; i += 256) s_headw[i] = s.head_w[i];
+  if (threadIdx.x < 11) s_headb[threadIdx.x] = s.head_b[threadIdx.x];
+  if (threadIdx.x < 27) s_sh[threadIdx.x] = s.sh_conv[threadIdx.x];
+  __syncthreads();
+  const int n = min(*a.n_surv, a.cap_surv);
+  const int sidx = threadIdx.x >> 3, l = threadIdx.x & 7;
+  for (int base = blockIdx.x * 32; base < n; base += gridDim.x * 32) {
+    const int si = base + sidx;
+    const bool active = si < n;
+    Surv sv; sv.ray = 0; sv.step = 0; sv.w = 0.f;
+    if (active) sv = a.surv[si];
+    const int ray = (int)sv.ray, k = (int)sv.step;
+    const float w = sv.w;
+    float o[3], d[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { o[i] = __ldg(a.rays + (size_t)ray * 6 + i); d[i] = __ldg(a.rays + (size_t)ray * 6 + 3 + i); }
+    const float tmin = a.tmin[ray];
+    float p[3], xn[3];
+    nmf_step_pos(o, d, nmf_step_z(tmin, s.stepsize, k), p);
+    nmf_normalize_xyz(s, p, xn);
+    const NmfTaps t = nmf_vm_taps(s, xn);
+    // appearance coefficients: lanes 0..5 own 4 channels of each plane
+    if (l < 6) {
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
+        const nmf_f4 c = nmf_app_group(s, t, pl, l);
+        float* q = &s_coef[sidx][pl * 24 + 4 * l];
+        q[0] = c.x; q[1] = c.y; q[2] = c.z; q[3] = c.w;
+      }
+    }
+    // smoothed-gradient normal: lane = (channel group, plane row)
+    float grad[3] = {0.f, 0.f, 0.f};
+    nmf_normal_group(s, t, l & 3, l >> 2, grad);
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+      grad[0] += __shfl_xor_sync(FULL, grad[0], off);
+      grad[1] += __shfl_xor_sync(FULL, grad[1], off);
+      grad[2] += __shfl_xor_sync(FULL, grad[2], off);
+    }
+    const nmf_v3 nrm = nmf_normal_from_grad(s, grad);
+    __syncwarp();
+    // basis GEMV (tensoRF.py:405): lane l owns features l, l+8, l+16
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 72; ++j) {
+      const float c = s_coef[sidx][j];
+      f0 += s_basis[j * 24 + l] * c;
+      f1 += s_basis[j * 24 + l + 8] * c;
+      f2 += s_basis[j * 24 + l + 16] * c;
+    }
+    __syncwarp();
+    // material heads (render_modules.py:553-560)
+    float lin[11];
+#pragma unroll
+    for (int h = 0; h < 11; ++h) {
+      float v = s_headw[h * 24 + l] * f0 + s_headw[h * 24 + l + 8] * f1 + s_headw[h * 24 + l + 16] * f2;
+      v += __shfl_xor_sync(FULL, v, 1);
+      v += __shfl_xor_sync(FULL, v, 2);
+      v += __shfl_xor_sync(FULL, v, 4);
+      lin[h] = v + s_headb[h];
+    }
+    float albedo[3], f0v[3], diffuse[3], fresn[3];
+    const float rough = nmf_clampf(nmf_sigmoid(lin[9] + s.roughness_bias) / 2.0f, 1e-2f, 1.0f);
+    float sh[9];
+    nmf_sh9(nrm, sh);
+    const nmf_v3 V = nmf_mk3(-d[0], -d[1], -d[2]);
+    const float vn = nmf_dot(V, nrm);
+    const float cost = fabsf(vn);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      albedo[c] = nmf_clampf(nmf_sigmoid(s.diffuse_mul * lin[c] + s.diffuse_bias), 0.f, 1.f);
+      f0v[c] = nmf_sigmoid(lin[6 + c] + s.f0_bias);
+      float e = 0.f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) e += s_sh[i * 3 + c] * sh[i];
+      diffuse[c] = albedo[c] * e;                                      // microfacet.py:316
+      fresn[c] = nmf_fresnel(f0v[c], cost);
+    }
+    if (LEVEL == 0 && active) {
+      // debug / auxiliary maps (tensor_nerf.py:495-566, microfacet.py:639-647): 10 values over 8 lanes
+      float* acc = a.accum + (size_t)ray * A_N;
+      if (l < 3) atomicAdd(acc + A_WN + l, w * (l == 0 ? nrm.x : l == 1 ? nrm.y : nrm.z));
+      else if (l < 6) atomicAdd(acc + A_DIFF + (l - 3), w * (1.0f - fresn[l - 3]) * diffuse[l - 3]);
+      else if (l == 6) atomicAdd(acc + A_ROUGH, w * rough);
+      if (l >= 5) { const int c = l - 5; atomicAdd(acc + A_ALB + c, w * albedo[c]); }
+    }
+    // bounce count (pt_selectors.py:20-40)
+    const int chunk = ray / a.group;
+    const uint64_t rkey = LEVEL == 0 ? nmf_mix64(a.seed, a.ray_id0 + (uint64_t)ray) : a.keys[ray];
+    const uint64_t skey = nmf_mix64(rkey, (uint64_t)k);
+    const float U = nmf_uniform(skey, NMF_STREAM_BOUNCE);
+    float kf;
+    if (LEVEL == 0) {
+      kf = floorf(w * (float)s.rays_per_ray + U - 0.5f);
+    } else {
+      const int N = s.max_brdf_rays1 - a.n_samples[chunk];
+      const float wsum = fmaxf((float)a.wsum[chunk], 1e-3f);
+      const float wj = w + 1e-3f * U;
+      kf = N > 0 ? floorf(wj / wsum * (float)N + 1.0f) : floorf(wj / wsum * (float)s.max_brdf_rays1 + 0.5f);
+    }
+    const int count = active ? (int)nmf_clampf(kf, 0.f, (float)NMF_MAX_BOUNCE) : 0;
+    int slot = -1, roff = 0;
+    if (count > 0 && l == 0) {
+      slot = atomicAdd(a.n_bs, 1);
+      roff = atomicAdd(a.ray_count + chunk, count);
+      if (slot >= a.cap_bs) { atomicOr(a.error, NMF_DEV_E_BSAMPLES); slot = -1; }
+      else if (roff + count > a.cap_rays) { atomicOr(a.error, NMF_DEV_E_BRAYS); slot = -1; }
+    }
+    slot = __shfl_sync(FULL, slot, (threadIdx.x & 31) & ~7);
+    roff = __shfl_sync(FULL, roff, (threadIdx.x & 31) & ~7);
+    if (slot >= 0) {
+      BSample* b = a.bs + slot;
+      const float sgn = vn > 0.f ? 1.f : (vn < 0.f ? -1.f : 0.f);        // microfacet.py:354-356
+      if (l == 0) { b->pos[0] = p[0]; b->pos[1] = p[1]; b->pos[2] = p[2]; b->w = w; }
+      if (l == 1) { b->V[0] = V.x; b->V[1] = V.y; b->V[2] = V.z; b->rough = rough; }
+      if (l == 2) { b->N[0] = nrm.x * sgn; b->N[1] = nrm.y * sgn; b->N[2] = nrm.z * sgn; b->count = count; }
+      if (l == 3) { b->f0[0] = f0v[0]; b->f0[1] = f0v[1]; b->f0[2] = f0v[2]; b->ray = (uint32_t)ray; }
+      if (l == 4) { b->diffuse[0] = diffuse[0]; b->diffuse[1] = diffuse[1]; b->diffuse[2] = diffuse[2]; b->roff = (uint32_t)roff; }
+      if (l == 5) { b->fresn[0] = fresn[0]; b->fresn[1] = fresn[1]; b->fresn[2] = fresn[2]; b->flags = xn[2] < 0.f ? 1u : 0u; }
+      if (l == 6) { b->key = skey; b->chunk = (uint32_t)chunk; b->pad = 0; }
+      // appearance feature + noise (microfacet.py:297, keyed Box-Muller)
+      b->feat[l] = f0 + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + l, NMF_STREAM_NOISE_B + l);
+      b->feat[l + 8] = f1 + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + l + 8, NMF_STREAM_NOISE_B + l + 8);
+      b->feat[l + 16] = f2 + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + l + 16, NMF_STREAM_NOISE_B + l + 16);
+      uint32_t* ow = a.owner + (size_t)chunk * a.cap_rays + roff;
+      for (int j = l; j < count; j += 8) ow[j] = (uint32_t)slot;
+    }
+  }
+}
+
+// ================================================================================================
+// BRDF MLP 66 -> 64 -> 64 -> 4 (modules/brdf.py:73-120,237-239), one row per thread; weights in shared
+// memory (transposed, so that the 32 lanes broadcast-read 16 bytes of one weight row at a time)
+// ================================================================================================
+#define MLP_THREADS 128
+#define MLP_SMEM_FLOATS (66 * 64 + 64 + 64 * 64 + 64 + 64 * 4 + 4 + 66 * MLP_THREADS)
+
+__device__ __forceinline__ void mlp_load_weights(const NmfScene& s, float* sm) {
+  float* w0 = sm; float* b0 = w0 + 66 * 64; float* w1 = b0 + 64; float* b1 = w1 + 64 * 64; float* w2 = b1 + 64; float* b2 = w2 + 256;
+  for (int i = threadIdx.x; i < 66 * 64; i += blockDim.x) w0[i] = s.brdf_w0t[i];
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) w1[i] = s.brdf_w1t[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) w2[i] = s.brdf_w2t[i];
+  if (threadIdx.x < 64) { b0[threadIdx.x] = s.brdf_b0[threadIdx.x]; b1[threadIdx.x] = s.brdf_b1[threadIdx.x]; }
+  if (threadIdx.x < 4) b2[threadIdx.x] = s.brdf_b2[threadIdx.x];
+}
+// x: this thread's column of the [66][MLP_THREADS] staging buffer (x[k * MLP_THREADS]); overwritten
+__device__ __forceinline__ void mlp_forward(const float* sm, float* x, float brdf_bias, float* out3) {
+  const float* w0 = sm; const float* b0 = w0 + 66 * 64; const float* w1 = b0 + 64; const float* b1 = w1 + 64 * 64;
+  const float* w2 = b1 + 64; const float* b2 = w2 + 256;
+  float h[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) h[i] = b0[i];
+#pragma unroll 2
+  for (int k = 0; k < 66; ++k) {
+    const float xv = x[k * MLP_THREADS];
+    const float4* wr = (const float4*)(w0 + k * 64);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float4 wv = wr[q];
+      h[4 * q] += xv * wv.x; h[4 * q + 1] += xv * wv.y; h[4 * q + 2] += xv * wv.z; h[4 * q + 3] += xv * wv.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 64; ++i) { x[i * MLP_THREADS] = fmaxf(h[i], 0.f); h[i] = b1[i]; }
+#pragma unroll 2
+  for (int k = 0; k < 64; ++k) {
+    const float xv = x[k * MLP_THREADS];
+    const float4* wr = (const float4*)(w1 + k * 64);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float4 wv = wr[q];
+      h[4 * q] += xv * wv.x; h[4 * q + 1] += xv * wv.y; h[4 * q + 2] += xv * wv.z; h[4 * q + 3] += xv * wv.w;
+    }
+  }
+  float o0 = b2[0], o1 = b2[1], o2 = b2[2];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    const float hv = fmaxf(h[k], 0.f);
+    const float4 wv = *(const float4*)(w2 + 4 * k);
+    o0 += hv * wv.x; o1 += hv * wv.y; o2 += hv * wv.z;
+  }
+  out3[0] = nmf_sigmoid(o0 + brdf_bias);
+  out3[1] = nmf_sigmoid(o1 + brdf_bias);
+  out3[2] = nmf_sigmoid(o2 + brdf_bias);
+}
+__device__ __forceinline__ void mlp_encode(float* x, nmf_v3 half_l, nmf_v3 diff_l, float rough) {
+  // modules/brdf.py:216-225: [feat | ISH(half) | half | ISH(diff) | diff]; feat is already in rows 0..23
+  float e[18];
+  nmf_ish18(half_l, rough, e);
+#pragma unroll
+  for (int i = 0; i < 18; ++i) x[(24 + i) * MLP_THREADS] = e[i];
+  x[42 * MLP_THREADS] = half_l.x; x[43 * MLP_THREADS] = half_l.y; x[44 * MLP_THREADS] = half_l.z;
+  nmf_ish18(diff_l, rough, e);
+#pragma unroll
+  for (int i = 0; i < 18; ++i) x[(45 + i) * MLP_THREADS] = e[i];
+  x[63 * MLP_THREADS] = diff_l.x; x[64 * MLP_THREADS] = diff_l.y; x[65 * MLP_THREADS] = diff_l.z;
+}
+
+// ================================================================================================
+// k_bounce: brdf_samplers/base.py:11-20, ggx.py:61-268, models/microfacet.py:367-472 (+ :561-613 at level 1)
+// ================================================================================================
+struct BounceArgs {
+  const BSample* bs; BRay* brays; const uint32_t* owner; const int* ray_count; int cap_rays;
+  float* score_sum;
+};
+
+template <int LEVEL>
+__global__ void __launch_bounds__(MLP_THREADS) k_bounce(const NmfScene s, const BounceArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  mlp_load_weights(s, sm);
+  __syncthreads();
+  float* x = sm + (MLP_SMEM_FLOATS - 66 * MLP_THREADS) + threadIdx.x;
+  const int chunk = blockIdx.y;
+  const int n = min(a.ray_count[chunk], a.cap_rays);
+  BRay* region = a.brays + (size_t)chunk * a.cap_rays;
+  const uint32_t* owner = a.owner + (size_t)chunk * a.cap_rays;
+  float block_score = 0.f;
+  for (int r = blockIdx.x * MLP_THREADS + threadIdx.x; r < n; r += gridDim.x * MLP_THREADS) {
+    const uint32_t slot = owner[r];
+    const BSample* b = a.bs + slot;
+    const int j = r - (int)b->roff;
+    const float4 q0 = *(const float4*)b->pos, q1 = *(const float4*)b->V, q2 = *(const float4*)b->N;
+    const nmf_v3 V = nmf_mk3(q1.x, q1.y, q1.z), N = nmf_mk3(q2.x, q2.y, q2.z);
+    const float rough = q1.w, w = q0.w;
+    const int count = __float_as_int(q2.w);
+    const uint64_t skey = b->key;
+    const float u1 = nmf_wrap01(__ldg(s.sobol + 2 * j) + 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_U));
+    const float u2 = nmf_wrap01(__ldg(s.sobol + 2 * j + 1) + 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_V));
+    const NmfGGX g = nmf_ggx_sample(u1, u2, V, N, rough);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float4 f = *(const float4*)(b->feat + 4 * i);
+      x[(4 * i) * MLP_THREADS] = f.x; x[(4 * i + 1) * MLP_THREADS] = f.y; x[(4 * i + 2) * MLP_THREADS] = f.z; x[(4 * i + 3) * MLP_THREADS] = f.w;
+    }
+    mlp_encode(x, g.half_l, g.diff_l, rough);
+    float bw[3];
+    mlp_forward(sm, x, s.brdf_bias, bw);
+    const float mip = -logf((float)count) - g.logpdf;                    // microfacet.py:445-448
+    BRay* o = region + r;
+    float4 st0, st1;
+    st0.x = g.L.x; st0.y = g.L.y; st0.z = g.L.z; st0.w = mip;
+    st1.x = bw[0]; st1.y = bw[1]; st1.z = bw[2];
+    if (LEVEL == 0) {
+      // contribution estimate for the retrace selection (microfacet.py:480-504)
+      const float pdf = expf(g.logpdf);
+      const float per_ray = fmaxf(bw[0], fmaxf(bw[1], bw[2])) * (nmf_dot(V, N) > 0.f ? 1.f : 0.f) * pdf;
+      const float sc = per_ray * (w / ((float)count + 1e-8f));
+      st1.w = sc;
+      block_score += sc;
+      *(float4*)o->L = st0;
+      *(float4*)o->bw = st1;
+      o->slot = -1;
+      o->owner = slot;
+    } else {
+      // no further retrace at this depth: every bounce ray reads the environment (microfacet.py:561)
+      float inc[3];
+      nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, g.L, mip, inc);
+      const float ch = fabsf(nmf_dot(V, g.H));
+      const float4 q3 = *(const float4*)b->f0, q4 = *(const float4*)b->diffuse;
+      const float F0 = nmf_fresnel(q3.x, ch), F1 = nmf_fresnel(q3.y, ch), F2 = nmf_fresnel(q3.z, ch);
+      st1.w = 0.f;
+      float4 st2, st3;
+      st2.x = F0 * inc[0] * bw[0] + (1.f - F0) * q4.x;                   // microfacet.py:585-600
+      st2.y = F1 * inc[1] * bw[1] + (1.f - F1) * q4.y;
+      st2.z = F2 * inc[2] * bw[2] + (1.f - F2) * q4.z;
+      st2.w = __int_as_float(-1);
+      st3.x = inc[0]; st3.y = inc[1]; st3.z = inc[2]; st3.w = __uint_as_float(slot);
+      *(float4*)o->L = st0;
+      *(float4*)o->bw = st1;
+      *(float4*)o->comb = st2;
+      *(float4*)o->inc = st3;
+    }
+  }
+  if (LEVEL == 0) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) block_score += __shfl_xor_sync(FULL, block_score, off);
+    if ((threadIdx.x & 31) == 0 && block_score != 0.f) atomicAdd(a.score_sum + chunk, block_score);
+  }
+}
+
+// ================================================================================================
+// k_select: models/microfacet.py:475-559 -- per chunk, the max_retrace bounce rays of largest
+// (normalised contribution + U) become secondary rays.  Three-pass radix select on the float bits.
+// ================================================================================================
+struct SelectArgs {
+  const BSample* bs; BRay* brays; const int* ray_count; int cap_rays; const float* score_sum;
+  int max_retrace; int* n_sec;
+  float* rays1; float* mip1; uint64_t* key1;
+};
+
+__global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
+  __shared__ unsigned hist[2048];
+  __shared__ unsigned sh_prefix, sh_need, sh_slot, sh_eq;
+  const int chunk = blockIdx.x;
+  const int n = min(a.ray_count[chunk], a.cap_rays);
+  const int n_re = min(n, a.max_retrace);
+  if (threadIdx.x == 0) a.n_sec[chunk] = n_re;
+  if (n_re == 0) return;
+  BRay* region = a.brays + (size_t)chunk * a.cap_rays;
+  const float total = a.score_sum[chunk];
+  // pass 0: final score = cc / sum * n_re + U(ray key)   (microfacet.py:504-506)
+  for (int i = threadIdx.x; i < 2048; i += 1024) hist[i] = 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < n; r += 1024) {
+    BRay* o = region + r;
+    const BSample* b = a.bs + o->owner;
+    const uint64_t rkey = nmf_mix64(b->key, (uint64_t)(r - (int)b->roff) + NMF_STREAM_RAY0);
+    const float U = nmf_uniform(rkey, NMF_STREAM_TIE);
+    const float sc = (total > 0.f ? o->score / total * (float)n_re : 0.f) + U;
+    o->score = sc;
+    atomicAdd(&hist[__float_as_uint(sc) >> 21], 1u);
+  }
+  __syncthreads();
+  unsigned prefix = 0, need = (unsigned)n_re;
+  // digit 0: bits 31..21, digit 1: bits 20..10, digit 2: bits 9..0
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+    const int bins = pass == 2 ? 1024 : 2048;
+    if (pass > 0) {
+      for (int i = threadIdx.x; i < 2048; i += 1024) hist[i] = 0;
+      __syncthreads();
+      const unsigned hi_shift = pass == 1 ? 21 : 10;
+      for (int r = threadIdx.x; r < n; r += 1024) {
+        const unsigned bits = __float_as_uint(region[r].score);
+        if ((bits >> hi_shift) == prefix) atomicAdd(&hist[(bits >> shift) & (bins - 1)], 1u);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      unsigned cum = 0;
+      int b = bins - 1;
+      for (; b > 0; --b) {
+        if (cum + hist[b] >= need) break;
+        cum += hist[b];
+      }
+      sh_prefix = (prefix << (pass == 0 ? 0 : (pass == 1 ? 11 : 10))) | (unsigned)b;
+      sh_need = need - cum;
+    }
+    __syncthreads();
+    prefix = sh_prefix;
+    need = sh_need;
+    __syncthreads();
+  }
+  // prefix now holds the full 32-bit pattern of the threshold; `need` = how many rays equal to it are taken
+  if (threadIdx.x == 0) { sh_slot = 0; sh_eq = 0; }
+  __syncthreads();
+  const unsigned thr = prefix;
+  for (int r = threadIdx.x; r < n; r += 1024) {
+    BRay* o = region + r;
+    const unsigned bits = __float_as_uint(o->score);
+    bool take = bits > thr;
+    if (bits == thr) take = atomicAdd(&sh_eq, 1u) < need;
+    if (take) {
+      const unsigned sl = atomicAdd(&sh_slot, 1u);
+      if (sl < (unsigned)n_re) {
+        const BSample* b = a.bs + o->owner;
+        const size_t gi = (size_t)chunk * a.max_retrace + sl;
+        float* ry = a.rays1 + gi * 6;
+        ry[0] = b->pos[0] + o->L[0] * 5e-3f;                            // microfacet.py:449-452
+        ry[1] = b->pos[1] + o->L[1] * 5e-3f;
+        ry[2] = b->pos[2] + o->L[2] * 5e-3f;
+        ry[3] = o->L[0]; ry[4] = o->L[1]; ry[5] = o->L[2];
+        a.mip1[gi] = o->mip;
+        a.key1[gi] = nmf_mix64(b->key, (uint64_t)(r - (int)b->roff) + NMF_STREAM_RAY0);
+        o->slot = (int)sl;
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// k_incoming (level 0): models/microfacet.py:549-600 -- incoming radiance of every primary bounce ray
+// ================================================================================================
+struct IncomingArgs {
+  const BSample* bs; BRay* brays; const int* ray_count; int cap_rays; const float* rgb1; int max_retrace;
+};
+__global__ void __launch_bounds__(256) k_incoming(const NmfScene s, const IncomingArgs a) {
+  const int chunk = blockIdx.y;
+  const int n = min(a.ray_count[chunk], a.cap_rays);
+  BRay* region = a.brays + (size_t)chunk * a.cap_rays;
+  for (int r = blockIdx.x * 256 + threadIdx.x; r < n; r += gridDim.x * 256) {
+    BRay* o = region + r;
+    const float4 q0 = *(const float4*)o->L, q1 = *(const float4*)o->bw;
+    const int slot = o->slot;
+    const BSample* b = a.bs + o->owner;
+    const nmf_v3 L = nmf_mk3(q0.x, q0.y, q0.z);
+    float inc[3];
+    if (slot >= 0) {
+      const float* src = a.rgb1 + ((size_t)chunk * a.max_retrace + slot) * 4;
+      inc[0] = src[0]; inc[1] = src[1]; inc[2] = src[2];
+    } else {
+      nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, L, q0.w, inc);
+    }
+    const float4 qv = *(const float4*)b->V, q3 = *(const float4*)b->f0, q4 = *(const float4*)b->diffuse;
+    const nmf_v3 H = nmf_unit(nmf_mk3((qv.x + L.x) / 2.0f, (qv.y + L.y) / 2.0f, (qv.z + L.z) / 2.0f));
+    const float ch = fabsf(qv.x * H.x + qv.y * H.y + qv.z * H.z);
+    const float F0 = nmf_fresnel(q3.x, ch), F1 = nmf_fresnel(q3.y, ch), F2 = nmf_fresnel(q3.z, ch);
+    float4 st2, st3;
+    st2.x = F0 * inc[0] * q1.x + (1.f - F0) * q4.x;
+    st2.y = F1 * inc[1] * q1.y + (1.f - F1) * q4.y;
+    st2.z = F2 * inc[2] * q1.z + (1.f - F2) * q4.z;
+    st2.w = __int_as_float(slot);
+    st3.x = inc[0]; st3.y = inc[1]; st3.z = inc[2]; st3.w = __uint_as_float(o->owner);
+    *(float4*)o->comb = st2;
+    *(float4*)o->inc = st3;
+  }
+}
+
+// ================================================================================================
+// k_reduce: models/microfacet.py:565-613 + tensor_nerf.py:448-452,528,565 -- mean over the bounce rays of a
+// sample, weighted into its pixel
+// ================================================================================================
+struct ReduceArgs { const BSample* bs; const int* n_bs; int cap_bs; const BRay* brays; int cap_rays; float* accum; };
+template <int LEVEL>
+__global__ void __launch_bounds__(256) k_reduce(const ReduceArgs a) {
+  const int n = min(*a.n_bs, a.cap_bs);
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const BSample* b = a.bs + i;
+    const int count = b->count;
+    const BRay* r = a.brays + (size_t)b->chunk * a.cap_rays + b->roff;
+    float comb[3] = {0, 0, 0}, inc[3] = {0, 0, 0}, bw[3] = {0, 0, 0};
+    for (int j = 0; j < count; ++j) {
+      const float4 c = *(const float4*)r[j].comb;
+      comb[0] += c.x; comb[1] += c.y; comb[2] += c.z;
+      if (LEVEL == 0) {
+        const float4 q = *(const float4*)r[j].inc, v = *(const float4*)r[j].bw;
+        inc[0] += q.x; inc[1] += q.y; inc[2] += q.z;
+        bw[0] += v.x; bw[1] += v.y; bw[2] += v.z;
+      }
+    }
+    const float inv = 1.0f / (float)count, w = b->w;
+    if (LEVEL == 0) {
+      float* acc = a.accum + (size_t)b->ray * A_N;
+      const bool below = b->flags & 1u;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float rgb = comb[c] * inv;
+        atomicAdd(acc + A_RGB + c, w * rgb);
+        if (below) atomicAdd(acc + A_CROSS + c, w * nmf_clampf(rgb, 0.f, 1.f));
+        atomicAdd(acc + A_SPEC + c, w * inc[c] * inv);
+        atomicAdd(acc + A_TINT + c, w * b->fresn[c] * (bw[c] * inv));
+      }
+    } else {
+      float* acc = a.accum + (size_t)b->ray * 4;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) atomicAdd(acc + c, w * comb[c] * inv);
+    }
+  }
+}
+
+// retraced rays: linear radiance + (1 - acc) * env(d, mip)   (tensor_nerf.py:460-468, 657-659 with tonemap=False)
+__global__ void k_finish1(const NmfScene s, const float* rays1, const float* mip1, const float* acc1, const float* accum1,
+                          const int* n_sec, int max_retrace, int n, float* rgb1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int chunk = i / max_retrace;
+  if (i - chunk * max_retrace >= n_sec[chunk]) return;
+  float bg[3];
+  nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot,
+                  nmf_mk3(rays1[6 * i + 3], rays1[6 * i + 4], rays1[6 * i + 5]), mip1[i], bg);
+  const float t = 1.0f - acc1[i];
+  rgb1[4 * i] = accum1[4 * i] + t * bg[0];
+  rgb1[4 * i + 1] = accum1[4 * i + 1] + t * bg[1];
+  rgb1[4 * i + 2] = accum1[4 * i + 2] + t * bg[2];
+}
+
+// ================================================================================================
+// model=tensorf plumbing config: view MLP 135 -> 128 -> 128 -> 3 per surviving sample
+// (models/tensorf.py:70-97, modules/render_modules.py:201-235 with viewpe = feape = 2)
+// ================================================================================================
+struct PlainArgs { const float* rays; const float* tmin; const Surv* surv; const int* n_surv; int cap_surv; float* accum; };
+__global__ void __launch_bounds__(128) k_shade_plain(const NmfScene s, const PlainArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* xbuf = sm;                       // [135][128]
+  float* hbuf = sm + 135 * 128;           // [128][128]
+  const int n = min(*a.n_surv, a.cap_surv);
+  float* x = xbuf + threadIdx.x;
+  float* hb = hbuf + threadIdx.x;
+  for (int si = blockIdx.x * 128 + threadIdx.x; si < n; si += gridDim.x * 128) {
+    const Surv sv = a.surv[si];
+    const int ray = (int)sv.ray;
+    float o[3], d[3], p[3], xn[3];
+    for (int i = 0; i < 3; ++i) { o[i] = a.rays[(size_t)ray * 6 + i]; d[i] = a.rays[(size_t)ray * 6 + 3 + i]; }
+    nmf_step_pos(o, d, nmf_step_z(a.tmin[ray], s.stepsize, (int)sv.step), p);
+    nmf_normalize_xyz(s, p, xn);
+    const NmfTaps t = nmf_vm_taps(s, xn);
+    float coef[72];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+      for (int g = 0; g < 6; ++g) {
+        const nmf_f4 c = nmf_app_group(s, t, pl, g);
+        coef[pl * 24 + 4 * g] = c.x; coef[pl * 24 + 4 * g + 1] = c.y; coef[pl * 24 + 4 * g + 2] = c.z; coef[pl * 24 + 4 * g + 3] = c.w;
+      }
+    // x = [feat(24), view(3), sin(feat*1), sin(feat*2) interleaved per feature..., cos..., sin(view..), cos(view..)]
+    // positional_encoding (render_modules.py:38-44): pts = (p[...,None] * [1,2]).reshape(..., 2*C); cat(sin, cos)
+    for (int oo = 0; oo < 24; ++oo) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 72; ++j) acc += __ldg(s.basis_t + j * 24 + oo) * coef[j];
+      x[oo * 128] = acc;
+      x[(27 + 2 * oo) * 128] = sinf(acc);
+      x[(27 + 2 * oo + 1) * 128] = sinf(acc * 2.0f);
+      x[(27 + 48 + 2 * oo) * 128] = cosf(acc);
+      x[(27 + 48 + 2 * oo + 1) * 128] = cosf(acc * 2.0f);
+    }
+    for (int c = 0; c < 3; ++c) {
+      x[(24 + c) * 128] = d[c];
+      x[(123 + 2 * c) * 128] = sinf(d[c]);
+      x[(123 + 2 * c + 1) * 128] = sinf(d[c] * 2.0f);
+      x[(123 + 6 + 2 * c) * 128] = cosf(d[c]);
+      x[(123 + 6 + 2 * c + 1) * 128] = cosf(d[c] * 2.0f);
+    }
+    // layer 1 and 2 in two halves of 64 outputs to bound registers
+    for (int half = 0; half < 2; ++half) {
+      float h[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) h[i] = __ldg(s.plain_b0 + half * 64 + i);
+      for (int k = 0; k < 135; ++k) {
+        const float xv = x[k * 128];
+        const float4* wr = (const float4*)(s.plain_w0t + k * 128 + half * 64);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float4 wv = __ldg(wr + q);
+          h[4 * q] += xv * wv.x; h[4 * q + 1] += xv * wv.y; h[4 * q + 2] += xv * wv.z; h[4 * q + 3] += xv * wv.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) hb[(half * 64 + i) * 128] = fmaxf(h[i], 0.f);
+    }
+    float o3[3] = {__ldg(s.plain_b2), __ldg(s.plain_b2 + 1), __ldg(s.plain_b2 + 2)};
+    for (int half = 0; half < 2; ++half) {
+      float h[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) h[i] = __ldg(s.plain_b1 + half * 64 + i);
+      for (int k = 0; k < 128; ++k) {
+        const float xv = hb[k * 128];
+        const float4* wr = (const float4*)(s.plain_w1t + k * 128 + half * 64);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float4 wv = __ldg(wr + q);
+          h[4 * q] += xv * wv.x; h[4 * q + 1] += xv * wv.y; h[4 * q + 2] += xv * wv.z; h[4 * q + 3] += xv * wv.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float hv = fmaxf(h[i], 0.f);
+        const float* w2 = s.plain_w2t + (half * 64 + i) * 3;
+        o3[0] += hv * __ldg(w2); o3[1] += hv * __ldg(w2 + 1); o3[2] += hv * __ldg(w2 + 2);
+      }
+    }
+    float* acc = a.accum + (size_t)ray * A_N;
+    const bool below = xn[2] < 0.f;
+    for (int c = 0; c < 3; ++c) {
+      const float rgb = nmf_sigmoid(o3[c]);
+      atomicAdd(acc + A_RGB + c, sv.w * rgb);
+      if (below) atomicAdd(acc + A_CROSS + c, sv.w * nmf_clampf(rgb, 0.f, 1.f));
+    }
+  }
+}
+
+// ================================================================================================
+// k_finish0: modules/tensor_nerf.py:448-566, 657-673 (eval, white background) + tonemap.py:38-49
+// ================================================================================================
+struct FinishArgs {
+  const float* rays; const float* tmin; const float* acc; const float* depth; const int* termk; const int* nvalid;
+  const float* accum; int n; float focal; int model;
+};
+__global__ void k_finish0(const NmfScene s, const FinishArgs a, const NmfImages out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const float acc = a.acc[i];
+  const float t = 1.0f - acc;
+  const float* A = a.accum + (size_t)i * A_N;
+  if (out.acc_map) out.acc_map[i] = acc;
+  if (out.depth) out.depth[i] = a.depth[i];
+  if (out.surf_width) out.surf_width[i] = (int64_t)a.nvalid[i];
+  if (out.termination_xyz) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const int k = a.termk[i];
+    if (k >= 0) {
+      float o[3], d[3];
+      for (int c = 0; c < 3; ++c) { o[c] = a.rays[(size_t)i * 6 + c]; d[c] = a.rays[(size_t)i * 6 + 3 + c]; }
+      const float z = nmf_step_z(a.tmin[i], s.stepsize, k);
+      nmf_step_pos(o, d, z, v);
+      v[3] = z / a.focal;                                               // alphagrid.py:200
+    }
+    for (int c = 0; c < 4; ++c) out.termination_xyz[(size_t)i * 4 + c] = v[c];
+  }
+  for (int c = 0; c < 3; ++c) {
+    const size_t j = (size_t)i * 3 + c;
+    if (out.rgb_map) out.rgb_map[j] = nmf_clampf(nmf_srgb(A[A_RGB + c]), 0.f, 1.f) + t;   // bg = white
+    if (out.world_normal) out.world_normal[j] = acc * A[A_WN + c] + t;                    // tensor_nerf.py:497-499
+    if (out.normal) out.normal[j] = t;                                                    // no predicted normals
+    if (out.cross_section) out.cross_section[j] = A[A_CROSS + c];
+    if (a.model == 0) {
+      if (out.diffuse) out.diffuse[j] = A[A_DIFF + c] + t;
+      if (out.tint) out.tint[j] = A[A_TINT + c] + t;
+      if (out.roughness) out.roughness[j] = A[A_ROUGH] + t;
+      if (out.spec) out.spec[j] = A[A_SPEC + c] + t;
+      if (out.albedo) out.albedo[j] = A[A_ALB + c] + t;
+    }
+  }
+}
+
+__global__ void k_export_counters(const WS w, const NmfCounters c, int model) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < w.n_chunks) {
+    if (c.n_samples0) c.n_samples0[i] = w.n_samples0[i];
+    if (c.n_cand) c.n_cand[i] = w.n_cand[i];
+    if (c.n_samples1) c.n_samples1[i] = w.n_samples1[i];
+    if (c.n_bounce_rays0) c.n_bounce_rays0[i] = w.ray_count0[i];
+    if (c.n_bounce_rays1) c.n_bounce_rays1[i] = w.ray_count1[i];
+    if (c.n_retrace) c.n_retrace[i] = w.n_sec[i];
+  }
+  if (i == 0) {
+    if (c.n_shaded) { c.n_shaded[0] = w.n_surv[0]; c.n_shaded[1] = w.n_surv[1]; }
+    if (c.error) *c.error = *w.error;
+  }
+}
+
+// ================================================================================================
+// host side of the C ABI
+// ================================================================================================
+static int g_sms = 0;
+static int sm_count() {
+  if (!g_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+static int blocks_for(long long work_items, int per_block, int max_per_sm) {
+  long long b = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)sm_count() * max_per_sm;
+  if (b < 1) b = 1;
+  return (int)(b < cap ? b : cap);
+}
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+#define CKL() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+static int check_scene(const NmfScene* s) {
+  if (!s) return NMF_E_ARG;
+  if (s->n_steps <= 0 || s->n_steps > NMF_MAX_STEPS) return NMF_E_UNSUPPORTED;
+  for (int p = 0; p < 3; ++p)
+    if (!s->dval[p] || !s->lval[p] || s->plane_w[p] < 2 || s->plane_h[p] < 2 || s->line_n[p] < 2) return NMF_E_ARG;
+  if (s->has_occ && (!s->occ_vox || !s->occ_cell || (s->opitch & 31))) return NMF_E_ARG;
+  return NMF_OK;
+}
+
+extern "C" int nmf_abi_version(void) { return NMF_ABI_VERSION; }
+
+extern "C" size_t nmf_workspace_bytes(const NmfScene* scene, int n_rays, int chunk) {
+  if (!scene || n_rays <= 0 || chunk <= 0) return 0;
+  WS w;
+  carve(w, scene, n_rays, chunk, nullptr);
+  return w.total;
+}
+
+extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const float* rays, const NmfImages* out,
+                               const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream_) {
+  int st = check_scene(scene);
+  if (st) return st;
+  if (!rp || !rays || !out || !workspace || rp->n_rays <= 0 || rp->chunk <= 0) return NMF_E_ARG;
+  if (((uintptr_t)workspace & 255) != 0) return NMF_E_ARG;
+  const NmfScene& s = *scene;
+  if (s.model == 0 && (!s.aval[0] || !s.dpack[0] || !s.basis_t || !s.head_w || !s.brdf_w0t || !s.sobol || !s.sh_conv || !s.env_sat))
+    return NMF_E_ARG;
+  if (s.model == 1 && (!s.aval[0] || !s.basis_t || !s.plain_w0t)) return NMF_E_ARG;
+  if (s.model == 0 && s.max_retrace > 0 && s.max_brdf_rays1 <= 0) return NMF_E_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  WS w;
+  carve(w, scene, rp->n_rays, rp->chunk, (char*)workspace);
+  if (w.total > workspace_bytes) return NMF_E_WORKSPACE;
+  const int n = rp->n_rays, nc = w.n_chunks;
+  CK(cudaMemsetAsync(w.counters_base, 0, w.counters_bytes, stream));
+
+  MarchArgs m0 = {};
+  m0.rays = rays; m0.n = n; m0.group = rp->chunk; m0.seed = rp->seed; m0.ray_id0 = rp->ray_id0;
+  m0.skip_eps = rp->skip_eps; m0.t_cut = rp->t_cut;
+  m0.tmin = w.tmin0; m0.acc = w.acc0; m0.depth = w.depth0; m0.termk = w.termk0; m0.nvalid = w.nvalid0;
+  m0.n_samples = w.n_samples0; m0.n_cand = w.n_cand; m0.wsum = nullptr;
+  m0.surv = w.surv0; m0.n_surv = w.n_surv; m0.cap_surv = w.cap_surv0; m0.error = w.error;
+  k_march<0><<<blocks_for(n, 8, 8), 256, 0, stream>>>(s, m0);
+  CKL();
+
+  if (s.model == 0) {
+    ShadeArgs h0 = {};
+    h0.rays = rays; h0.tmin = w.tmin0; h0.seed = rp->seed; h0.ray_id0 = rp->ray_id0; h0.group = rp->chunk;
+    h0.surv = w.surv0; h0.n_surv = w.n_surv; h0.cap_surv = w.cap_surv0; h0.accum = w.accum0;
+    h0.bs = w.bs0; h0.n_bs = w.n_bs; h0.cap_bs = w.cap_bs0; h0.ray_count = w.ray_count0; h0.cap_rays = w.cap_rays0;
+    h0.owner = w.owner0; h0.error = w.error;
+    k_shade<0><<<sm_count() * 6, 256, 0, stream>>>(s, h0);
+    CKL();
+
+    const size_t mlp_smem = MLP_SMEM_FLOATS * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+      CK(cudaFuncSetAttribute(k_bounce<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem));
+      CK(cudaFuncSetAttribute(k_bounce<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem));
+      attr_done = true;
+    }
+    int gx = (sm_count() * 6 + nc - 1) / nc;
+    if (gx < 1) gx = 1;
+    BounceArgs b0 = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.score_sum};
+    k_bounce<0><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b0);
+    CKL();
+
+    if (s.max_retrace > 0) {
+      SelectArgs sa = {w.bs0, w.brays0, w.ray_count0, w.cap_rays0, w.score_sum, s.max_retrace, w.n_sec, w.rays1, w.mip1, w.key1};
+      k_select<<<nc, 1024, 0, stream>>>(sa);
+      CKL();
+      MarchArgs m1 = {};
+      m1.rays = w.rays1; m1.n = w.n_rays1; m1.group = s.max_retrace; m1.n_active = w.n_sec; m1.keys = w.key1;
+      m1.skip_eps = rp->skip_eps; m1.t_cut = rp->t_cut;
+      m1.tmin = w.tmin1; m1.acc = w.acc1; m1.depth = nullptr; m1.termk = nullptr; m1.nvalid = w.nvalid1;
+      m1.n_samples = w.n_samples1; m1.n_cand = w.n_cand; m1.wsum = w.wsum1;
+      m1.surv = w.surv1; m1.n_surv = w.n_surv + 1; m1.cap_surv = w.cap_surv1; m1.error = w.error;
+      k_march<1><<<blocks_for(w.n_rays1, 8, 8), 256, 0, stream>>>(s, m1);
+      CKL();
+      ShadeArgs h1 = {};
+      h1.rays = w.rays1; h1.tmin = w.tmin1; h1.keys = w.key1; h1.group = s.max_retrace;
+      h1.surv = w.surv1; h1.n_surv = w.n_surv + 1; h1.cap_surv = w.cap_surv1; h1.accum = nullptr;
+      h1.bs = w.bs1; h1.n_bs = w.n_bs + 1; h1.cap_bs = w.cap_bs1; h1.ray_count = w.ray_count1; h1.cap_rays = w.cap_rays1;
+      h1.owner = w.owner1; h1.n_samples = w.n_samples1; h1.wsum = w.wsum1; h1.error = w.error;
+      k_shade<1><<<sm_count() * 6, 256, 0, stream>>>(s, h1);
+      CKL();
+      BounceArgs b1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr};
+      k_bounce<1><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b1);
+      CKL();
+      ReduceArgs r1 = {w.bs1, w.n_bs + 1, w.cap_bs1, w.brays1, w.cap_rays1, w.accum1};
+      k_reduce<1><<<sm_count() * 4, 256, 0, stream>>>(r1);
+      CKL();
+      k_finish1<<<(w.n_rays1 + 127) / 128, 128, 0, stream>>>(s, w.rays1, w.mip1, w.acc1, w.accum1, w.n_sec, s.max_retrace,
+                                                           w.n_rays1, w.rgb1);
+      CKL();
+    }
+    IncomingArgs ia = {w.bs0, w.brays0, w.ray_count0, w.cap_rays0, w.rgb1, s.max_retrace};
+    int gxi = (sm_count() * 8 + nc - 1) / nc;
+    k_incoming<<<dim3(gxi, nc), 256, 0, stream>>>(s, ia);
+    CKL();
+    ReduceArgs r0 = {w.bs0, w.n_bs, w.cap_bs0, w.brays0, w.cap_rays0, w.accum0};
+    k_reduce<0><<<sm_count() * 4, 256, 0, stream>>>(r0);
+    CKL();
+  } else {
+    const size_t smem = (135 + 128) * 128 * sizeof(float);
+    static bool attr_done2 = false;
+    if (!attr_done2) {
+      CK(cudaFuncSetAttribute(k_shade_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_done2 = true;
+    }
+    PlainArgs pa = {rays, w.tmin0, w.surv0, w.n_surv, w.cap_surv0, w.accum0};
+    k_shade_plain<<<sm_count(), 128, smem, stream>>>(s, pa);
+    CKL();
+  }
+  FinishArgs fa = {rays, w.tmin0, w.acc0, w.depth0, w.termk0, w.nvalid0, w.accum0, n, rp->focal, s.model};
+  k_finish0<<<(n + 127) / 128, 128, 0, stream>>>(s, fa, *out);
+  CKL();
+  if (counters) {
+    k_export_counters<<<(nc + 127) / 128 > 0 ? (nc + 127) / 128 : 1, 128, 0, stream>>>(w, *counters, s.model);
+    CKL();
+  }
+  return NMF_OK;
+}
+
+extern "C" int nmf_render_rays_host(const NmfScene* scene, const NmfRender* rp, const float* rays_host, float* rays_dev,
+                                    const NmfImages* out_host, const NmfImages* out_dev, const NmfCounters* counters_host,
+                                    const NmfCounters* counters_dev, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!rp || !rays_host || !rays_dev || !out_host || !out_dev) return NMF_E_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t n = (size_t)rp->n_rays;
+  CK(cudaMemcpyAsync(rays_dev, rays_host, n * 6 * sizeof(float), cudaMemcpyHostToDevice, stream));
+  int st = nmf_render_rays(scene, rp, rays_dev, out_dev, counters_dev, workspace, workspace_bytes, stream_);
+  if (st) return st;
+#define D2H(field, elems, type) \
+  if (out_host->field && out_dev->field) CK(cudaMemcpyAsync(out_host->field, out_dev->field, n * (elems) * sizeof(type), cudaMemcpyDeviceToHost, stream));
+  D2H(rgb_map, 3, float) D2H(acc_map, 1, float) D2H(depth, 1, float) D2H(world_normal, 3, float) D2H(normal, 3, float)
+  D2H(termination_xyz, 4, float) D2H(surf_width, 1, int64_t) D2H(cross_section, 3, float) D2H(diffuse, 3, float)
+  D2H(tint, 3, float) D2H(roughness, 3, float) D2H(spec, 3, float) D2H(albedo, 3, float)
+#undef D2H
+  if (counters_host && counters_dev) {
+    const size_t nc = (n + rp->chunk - 1) / rp->chunk;
+#define C2H(field, cnt) \
+  if (counters_host->field && counters_dev->field) CK(cudaMemcpyAsync(counters_host->field, counters_dev->field, (cnt) * 4, cudaMemcpyDeviceToHost, stream));
+    C2H(n_samples0, nc) C2H(n_samples1, nc) C2H(n_cand, nc) C2H(n_bounce_rays0, nc) C2H(n_bounce_rays1, nc) C2H(n_retrace, nc)
+    C2H(n_shaded, 2) C2H(error, 1)
+#undef C2H
+  }
+  return NMF_OK;
+}
+
+// ================================================================================================
+// plugin-slot operators (unfused)
+// ================================================================================================
+__global__ void k_sample_rays(const NmfScene s, const float* rays, int n, float near_override, uint8_t* valid, float* zv, int* n_valid) {
+  const int lane = threadIdx.x & 31;
+  const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ray >= n) return;
+  float o[3], d[3];
+  for (int i = 0; i < 3; ++i) { o[i] = rays[(size_t)ray * 6 + i]; d[i] = rays[(size_t)ray * 6 + 3 + i]; }
+  const float tmin = nmf_ray_tmin(o, d, s.aabb0, s.aabb1, near_override >= 0.f ? near_override : s.near, s.far);
+  int nv = 0;
+  for (int k = lane; k < s.n_steps; k += 32) {
+    const float z = nmf_step_z(tmin, s.stepsize, k);
+    float p[3];
+    nmf_step_pos(o, d, z, p);
+    bool ok = nmf_inside(p, s.aabb0, s.aabb1);
+    if (ok && s.has_occ) {
+      float xn[3];
+      nmf_normalize_xyz(s, p, xn);
+      ok = nmf_occupied(s.occ_vox, s.occ_cell, s.ow, s.oh, s.od, s.opitch, xn[0], xn[1], xn[2]);
+    }
+    if (valid) valid[(size_t)ray * s.n_steps + k] = ok;
+    if (zv) zv[(size_t)ray * s.n_steps + k] = z;
+    nv += ok;
+  }
+  for (int off = 16; off > 0; off >>= 1) nv += __shfl_xor_sync(FULL, nv, off);
+  if (lane == 0 && n_valid) n_valid[ray] = nv;
+}
+extern "C" int nmf_sample_rays(const NmfScene* scene, const float* rays, int n_rays, float near_override, uint8_t* ray_valid,
+                               float* z_vals, int* n_valid, void* stream) {
+  int st = check_scene(scene);
+  if (st) return st;
+  if (!rays || n_rays <= 0) return NMF_E_ARG;
+  k_sample_rays<<<(n_rays + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*scene, rays, n_rays, near_override, ray_valid, z_vals, n_valid);
+  CKL();
+  return NMF_OK;
+}
+
+// 4 lanes per point (density), 8 lanes per point (appearance / normals): same lane maps as the fused kernels
+__global__ void k_vm_density(const NmfScene s, const float* xyz, int n, int stride, int activate, float* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t >> 2, sub = t & 3;
+  const bool active = i < n;
+  float xn[3];
+  nmf_normalize_xyz(s, xyz + (size_t)(active ? i : 0) * stride, xn);
+  const NmfTaps tp = nmf_vm_taps(s, xn);
+  float f = nmf_density_group(s, tp, sub);
+  f += __shfl_xor_sync(FULL, f, 1);
+  f += __shfl_xor_sync(FULL, f, 2);
+  if (active && sub == 0) out[i] = activate ? nmf_feature2density(f, s.density_shift) : f;
+}
+extern "C" int nmf_vm_density(const NmfScene* scene, const float* xyz, int n, int stride, int activate, float* sigma, void* stream) {
+  int st = check_scene(scene);
+  if (st) return st;
+  if (!xyz || !sigma || n <= 0 || stride < 3) return NMF_E_ARG;
+  k_vm_density<<<(n * 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*scene, xyz, n, stride, activate, sigma);
+  CKL();
+  return NMF_OK;
+}
+__global__ void k_vm_app(const NmfScene s, const float* xyz, int n, int stride, float* out) {
+  __shared__ float s_coef[32][73];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t >> 3, l = t & 7, sidx = threadIdx.x >> 3;
+  const bool active = i < n;
+  float xn[3];
+  nmf_normalize_xyz(s, xyz + (size_t)(active ? i : 0) * stride, xn);
+  const NmfTaps tp = nmf_vm_taps(s, xn);
+  if (l < 6) {
+    for (int pl = 0; pl < 3; ++pl) {
+      const nmf_f4 c = nmf_app_group(s, tp, pl, l);
+      float* q = &s_coef[sidx][pl * 24 + 4 * l];
+      q[0] = c.x; q[1] = c.y; q[2] = c.z; q[3] = c.w;
+    }
+  }
+  __syncwarp();
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+  for (int j = 0; j < 72; ++j) {
+    const float c = s_coef[sidx][j];
+    f0 += __ldg(s.basis_t + j * 24 + l) * c;
+    f1 += __ldg(s.basis_t + j * 24 + l + 8) * c;
+    f2 += __ldg(s.basis_t + j * 24 + l + 16) * c;
+  }
+  if (active) { out[(size_t)i * 24 + l] = f0; out[(size_t)i * 24 + l + 8] = f1; out[(size_t)i * 24 + l + 16] = f2; }
+}
+extern "C" int nmf_vm_appfeature(const NmfScene* scene, const float* xyz, int n, int stride, float* feat, void* stream) {
+  int st = check_scene(scene);
+  if (st) return st;
+  if (!xyz || !feat || n <= 0 || stride < 3 || !scene->aval[0] || !scene->basis_t) return NMF_E_ARG;
+  k_vm_app<<<(n * 8 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*scene, xyz, n, stride, feat);
+  CKL();
+  return NMF_OK;
+}
+__global__ void k_vm_normals(const NmfScene s, const float* xyz, int n, int stride, float* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t >> 3, l = t & 7;
+  const bool active = i < n;
+  float xn[3];
+  nmf_normalize_xyz(s, xyz + (size_t)(active ? i : 0) * stride, xn);
+  const NmfTaps tp = nmf_vm_taps(s, xn);
+  float grad[3] = {0.f, 0.f, 0.f};
+  nmf_normal_group(s, tp, l & 3, l >> 2, grad);
+  for (int off = 1; off < 8; off <<= 1) {
+    grad[0] += __shfl_xor_sync(FULL, grad[0], off);
+    grad[1] += __shfl_xor_sync(FULL, grad[1], off);
+    grad[2] += __shfl_xor_sync(FULL, grad[2], off);
+  }
+  const nmf_v3 nn = nmf_normal_from_grad(s, grad);
+  if (active && l == 0) { out[(size_t)i * 3] = nn.x; out[(size_t)i * 3 + 1] = nn.y; out[(size_t)i * 3 + 2] = nn.z; }
+}
+extern "C" int nmf_vm_normals(const NmfScene* scene, const float* xyz, int n, int stride, float* normals, void* stream) {
+  int st = check_scene(scene);
+  if (st) return st;
+  if (!xyz || !normals || n <= 0 || stride < 3 || !scene->dpack[0]) return NMF_E_ARG;
+  k_vm_normals<<<(n * 8 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*scene, xyz, n, stride, normals);
+  CKL();
+  return NMF_OK;
+}
+__global__ void k_env_lookup(const NmfScene s, const float* dirs, const float* mip, int n, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float rgb[3];
+  nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot,
+                  nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), mip[i], rgb);
+  out[3 * i] = rgb[0]; out[3 * i + 1] = rgb[1]; out[3 * i + 2] = rgb[2];
+}
+extern "C" int nmf_env_lookup(const NmfScene* scene, const float* dirs, const float* mip, int n, float* rgb, void* stream) {
+  if (!scene || !scene->env_sat || !dirs || !mip || !rgb || n <= 0) return NMF_E_ARG;
+  k_env_lookup<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*scene, dirs, mip, n, rgb);
+  CKL();
+  return NMF_OK;
+}
+__global__ void k_ggx(const float* u, const float* V, const float* N, const float* r, int n, float* L, float* logpdf,
+                      float* half_l, float* diff_l) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const NmfGGX g = nmf_ggx_sample(u[2 * i], u[2 * i + 1], nmf_mk3(V[3 * i], V[3 * i + 1], V[3 * i + 2]),
+                                  nmf_mk3(N[3 * i], N[3 * i + 1], N[3 * i + 2]), r[i]);
+  L[3 * i] = g.L.x; L[3 * i + 1] = g.L.y; L[3 * i + 2] = g.L.z;
+  logpdf[i] = g.logpdf;
+  if (half_l) { half_l[3 * i] = g.half_l.x; half_l[3 * i + 1] = g.half_l.y; half_l[3 * i + 2] = g.half_l.z; }
+  if (diff_l) { diff_l[3 * i] = g.diff_l.x; diff_l[3 * i + 1] = g.diff_l.y; diff_l[3 * i + 2] = g.diff_l.z; }
+}
+extern "C" int nmf_ggx_sample(const float* u, const float* V, const float* N, const float* r, int n, float* L, float* logpdf,
+                              float* half_local, float* diff_local, void* stream) {
+  if (!u || !V || !N || !r || !L || !logpdf || n <= 0) return NMF_E_ARG;
+  k_ggx<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(u, V, N, r, n, L, logpdf, half_local, diff_local);
+  CKL();
+  return NMF_OK;
+}
+__global__ void __launch_bounds__(MLP_THREADS) k_brdf_mlp(const NmfScene s, const float* feat, const float* half_l,
+                                                          const float* diff_l, const float* rough, int n, float* out) {
+  extern __shared__ __align__(16) float sm[];
+  mlp_load_weights(s, sm);
+  __syncthreads();
+  float* x = sm + (MLP_SMEM_FLOATS - 66 * MLP_THREADS) + threadIdx.x;
+  for (int i = blockIdx.x * MLP_THREADS + threadIdx.x; i < n; i += gridDim.x * MLP_THREADS) {
+    for (int k = 0; k < 24; ++k) x[k * MLP_THREADS] = feat[(size_t)i * 24 + k];
+    mlp_encode(x, nmf_mk3(half_l[3 * i], half_l[3 * i + 1], half_l[3 * i + 2]),
+               nmf_mk3(diff_l[3 * i], diff_l[3 * i + 1], diff_l[3 * i + 2]), rough[i]);
+    float bw[3];
+    mlp_forward(sm, x, s.brdf_bias, bw);
+    out[3 * i] = bw[0]; out[3 * i + 1] = bw[1]; out[3 * i + 2] = bw[2];
+  }
+}
+extern "C" int nmf_brdf_mlp(const NmfScene* scene, const float* feat, const float* half_local, const float* diff_local,
+                            const float* rough, int n, float* out, void* stream) {
+  if (!scene || !scene->brdf_w0t || !feat || !half_local || !diff_local || !rough || !out || n <= 0) return NMF_E_ARG;
+  const size_t smem = MLP_SMEM_FLOATS * sizeof(float);
+  static bool done = false;
+  if (!done) { CK(cudaFuncSetAttribute(k_brdf_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
+  k_brdf_mlp<<<blocks_for(n, MLP_THREADS, 3), MLP_THREADS, smem, (cudaStream_t)stream>>>(*scene, feat, half_local, diff_local, rough, n, out);
+  CKL();
+  return NMF_OK;
+}
+__global__ void k_heads(const NmfScene s, const float* feat, int n, float* albedo, float* tint, float* f0, float* r1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float lin[11];
+  for (int h = 0; h < 11; ++h) {
+    float v = s.head_b[h];
+    for (int k = 0; k < 24; ++k) v += s.head_w[h * 24 + k] * feat[(size_t)i * 24 + k];
+    lin[h] = v;
+  }
+  for (int c = 0; c < 3; ++c) {
+    albedo[3 * i + c] = nmf_clampf(nmf_sigmoid(s.diffuse_mul * lin[c] + s.diffuse_bias), 0.f, 1.f);
+    tint[3 * i + c] = nmf_sigmoid(lin[3 + c] + s.tint_bias);
+    f0[3 * i + c] = nmf_sigmoid(lin[6 + c] + s.f0_bias);
+  }
+  r1[i] = nmf_clampf(nmf_sigmoid(lin[9] + s.roughness_bias) / 2.0f, 1e-2f, 1.0f);
+}
+extern "C" int nmf_material_heads(const NmfScene* scene, const float* feat, int n, float* albedo, float* tint, float* f0,
+                                  float* r1, void* stream) {
+  if (!scene || !scene->head_w || !feat || !albedo || !tint || !f0 || !r1 || n <= 0) return NMF_E_ARG;
+  k_heads<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*scene, feat, n, albedo, tint, f0, r1);
+  CKL();
+  return NMF_OK;
+}
+// samplers/alphagrid.py:209-247: alpha on the (gz,gy,gx) lattice; lattice point = aabb0*(1-s) + aabb1*s, s = linspace(0,1,g)
+__global__ void k_dense_alpha(const NmfScene s, int gx, int gy, int gz, float* alpha) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = t >> 2;
+  const int sub = (int)(t & 3);
+  const long long total = (long long)gx * gy * gz;
+  const bool active = i < total;
+  const long long ii = active ? i : 0;
+  const int x = (int)(ii % gx), y = (int)((ii / gx) % gy), z = (int)(ii / ((long long)gx * gy));
+  // torch.linspace(0, 1, g): start + step*i for the first half, end - step*(g-1-i) for the second
+  auto lin = [](int i, int g) {
+    const float step = 1.0f / (float)(g - 1);
+    return i < g / 2 ? NMF_MUL(step, (float)i) : NMF_SUB(1.0f, NMF_MUL(step, (float)(g - 1 - i)));
+  };
+  const float sx = lin(x, gx), sy = lin(y, gy), sz = lin(z, gz);
+  float p[3], xn[3];
+  p[0] = NMF_ADD(NMF_MUL(s.aabb0[0], NMF_SUB(1.0f, sx)), NMF_MUL(s.aabb1[0], sx));
+  p[1] = NMF_ADD(NMF_MUL(s.aabb0[1], NMF_SUB(1.0f, sy)), NMF_MUL(s.aabb1[1], sy));
+  p[2] = NMF_ADD(NMF_MUL(s.aabb0[2], NMF_SUB(1.0f, sz)), NMF_MUL(s.aabb1[2], sz));
+  nmf_normalize_xyz(s, p, xn);
+  const NmfTaps tp = nmf_vm_taps(s, xn);
+  float f = nmf_density_group(s, tp, sub);
+  f += __shfl_xor_sync(FULL, f, 1);
+  f += __shfl_xor_sync(FULL, f, 2);
+  if (active && sub == 0) {
+    const float sigma = nmf_feature2density(f, s.density_shift);
+    alpha[i] = 1.0f - expf(-sigma * s.stepsize);                         // alphagrid.py:222 (no distance_scale)
+  }
+}
+extern "C" int nmf_dense_alpha(const NmfScene* scene, int gx, int gy, int gz, float* alpha, void* stream) {
+  int st = check_scene(scene);
+  if (st) return st;
+  if (!alpha || gx < 2 || gy < 2 || gz < 2) return NMF_E_ARG;
+  const long long total = (long long)gx * gy * gz * 4;
+  k_dense_alpha<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*scene, gx, gy, gz, alpha);
+  CKL();
+  return NMF_OK;
+}

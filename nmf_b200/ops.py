@@ -1,0 +1,185 @@
+"""Thin Python wrappers over the C ABI (include/nmf_b200.h): PyTorch tensors in, PyTorch tensors out.
+
+PyTorch is used for device memory and streams only; every function here launches hand-written sm_100a kernels
+from libnmf_b200.so on torch's current CUDA stream.  There is no fallback: CPU tensors are rejected.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+IMAGE_SHAPES = dict(rgb_map=(3,), acc_map=(), depth=(), world_normal=(3,), normal=(3,), termination_xyz=(4,),
+                    surf_width=(), cross_section=(3,), diffuse=(3,), tint=(3,), roughness=(3,), spec=(3,), albedo=(3,))
+PLAIN_KEYS = ["rgb_map", "acc_map", "depth", "world_normal", "normal", "termination_xyz", "surf_width", "cross_section"]
+DEFAULT_SKIP_EPS = 2e-5
+DEFAULT_T_CUT = 1e-5
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _f32(t, dev):
+    if not t.is_cuda:
+        raise _lib.NmfError("nmf_b200 ops take CUDA tensors (there is no CPU path)")
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def env_lookup(scene, dirs, mip):
+    """IntegralEquirect.forward (modules/integral_equirect.py:409-504)."""
+    d = _f32(dirs.reshape(-1, 3), scene.device)
+    m = _f32(mip.reshape(-1), scene.device)
+    out = torch.empty_like(d)
+    if d.shape[0]:
+        _lib.check(_lib.lib().nmf_env_lookup(scene.ref(), _p(d), _p(m), d.shape[0], _p(out), _stream()), "nmf_env_lookup")
+    return out
+
+
+def vm_density(scene, xyz, activate=True):
+    x = _f32(xyz, scene.device)
+    out = torch.empty(x.shape[0], device=x.device)
+    if x.shape[0]:
+        _lib.check(_lib.lib().nmf_vm_density(scene.ref(), _p(x), x.shape[0], x.shape[1], int(activate), _p(out), _stream()),
+                   "nmf_vm_density")
+    return out
+
+
+def vm_appfeature(scene, xyz):
+    x = _f32(xyz, scene.device)
+    out = torch.empty(x.shape[0], 24, device=x.device)
+    if x.shape[0]:
+        _lib.check(_lib.lib().nmf_vm_appfeature(scene.ref(), _p(x), x.shape[0], x.shape[1], _p(out), _stream()),
+                   "nmf_vm_appfeature")
+    return out
+
+
+def vm_normals(scene, xyz):
+    x = _f32(xyz, scene.device)
+    out = torch.empty(x.shape[0], 3, device=x.device)
+    if x.shape[0]:
+        _lib.check(_lib.lib().nmf_vm_normals(scene.ref(), _p(x), x.shape[0], x.shape[1], _p(out), _stream()),
+                   "nmf_vm_normals")
+    return out
+
+
+def sample_rays(scene, rays, override_near=None):
+    """AlphaGridSampler.sample, eval mode: (ray_valid (B,S) bool, z_vals (B,S), n_valid (B) int32)."""
+    r = _f32(rays[:, :6], scene.device)
+    B, S = r.shape[0], scene.n_steps
+    valid = torch.empty(B, S, dtype=torch.uint8, device=r.device)
+    z = torch.empty(B, S, device=r.device)
+    nv = torch.empty(B, dtype=torch.int32, device=r.device)
+    if B:
+        _lib.check(_lib.lib().nmf_sample_rays(scene.ref(), _p(r), B, -1.0 if override_near is None else float(override_near),
+                                              _p(valid), _p(z), _p(nv), _stream()), "nmf_sample_rays")
+    return valid.bool(), z, nv
+
+
+def ggx_sample(u, V, N, r):
+    dev = V.device
+    u, V, N, r = _f32(u, dev), _f32(V, dev), _f32(N, dev), _f32(r.reshape(-1), dev)
+    n = V.shape[0]
+    L, lp, hl, dl = torch.empty_like(V), torch.empty(n, device=dev), torch.empty_like(V), torch.empty_like(V)
+    if n:
+        _lib.check(_lib.lib().nmf_ggx_sample(_p(u), _p(V), _p(N), _p(r), n, _p(L), _p(lp), _p(hl), _p(dl), _stream()),
+                   "nmf_ggx_sample")
+    return L, lp, hl, dl
+
+
+def brdf_mlp(scene, feat, half_local, diff_local, rough):
+    dev = scene.device
+    f, h, d, r = _f32(feat, dev), _f32(half_local, dev), _f32(diff_local, dev), _f32(rough.reshape(-1), dev)
+    out = torch.empty(f.shape[0], 3, device=dev)
+    if f.shape[0]:
+        _lib.check(_lib.lib().nmf_brdf_mlp(scene.ref(), _p(f), _p(h), _p(d), _p(r), f.shape[0], _p(out), _stream()),
+                   "nmf_brdf_mlp")
+    return out
+
+
+def material_heads(scene, feat):
+    f = _f32(feat, scene.device)
+    n = f.shape[0]
+    a, t, f0 = (torch.empty(n, 3, device=f.device) for _ in range(3))
+    r1 = torch.empty(n, device=f.device)
+    if n:
+        _lib.check(_lib.lib().nmf_material_heads(scene.ref(), _p(f), n, _p(a), _p(t), _p(f0), _p(r1), _stream()),
+                   "nmf_material_heads")
+    return a, t, f0, r1
+
+
+def dense_alpha(scene, grid_size):
+    gx, gy, gz = (int(g) for g in grid_size)
+    out = torch.empty(gz, gy, gx, device=scene.device)
+    _lib.check(_lib.lib().nmf_dense_alpha(scene.ref(), gx, gy, gz, _p(out), _stream()), "nmf_dense_alpha")
+    return out
+
+
+class RenderBuffers:
+    """Output images, counters and scratch for batches of up to `n_rays` rays (grow-only cache per scene)."""
+
+    def __init__(self, scene, n_rays, chunk, keys):
+        dev = scene.device
+        self.n_rays, self.chunk = n_rays, chunk
+        self.n_chunks = (n_rays + chunk - 1) // chunk
+        self.images = {}
+        self.c_images = _lib.NmfImages()
+        for k in keys:
+            dt = torch.int64 if k == "surf_width" else torch.float32
+            self.images[k] = torch.empty((n_rays,) + IMAGE_SHAPES[k], dtype=dt, device=dev)
+            setattr(self.c_images, k, self.images[k].data_ptr())
+        self.counters = {}
+        self.c_counters = _lib.NmfCounters()
+        for k in _lib.COUNTER_FIELDS:
+            n = 2 if k == "n_shaded" else (1 if k == "error" else self.n_chunks)
+            self.counters[k] = torch.zeros(n, dtype=torch.int32, device=dev)
+            setattr(self.c_counters, k, self.counters[k].data_ptr())
+        nbytes = _lib.lib().nmf_workspace_bytes(scene.ref(), n_rays, chunk)
+        if nbytes == 0:
+            raise _lib.NmfError("nmf_workspace_bytes: bad arguments")
+        self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        off = (-self.workspace.data_ptr()) % 256
+        self.ws_ptr = self.workspace.data_ptr() + off
+        self.ws_bytes = nbytes
+
+
+def image_keys(scene):
+    return list(IMAGE_SHAPES) if scene.hp["model"] == "microfacet" else list(PLAIN_KEYS)
+
+
+def render_rays(scene, rays, focal, chunk=4096, seed=0, ray_id0=0, skip_eps=DEFAULT_SKIP_EPS, t_cut=DEFAULT_T_CUT,
+                buffers=None, check_errors=True):
+    """All chunks of `rays` (n,6) in one asynchronous call (nmf_render_rays).  Returns (images, stats):
+    images as in TensorNeRF.forward (eval), stats = dict(n_samples=[per-chunk [M0, M1]], counters...)."""
+    r = _f32(rays[:, :6], scene.device)
+    n = r.shape[0]
+    if buffers is None or buffers.n_rays < n or buffers.chunk != chunk:
+        buffers = RenderBuffers(scene, n, chunk, image_keys(scene))
+    rp = _lib.NmfRender(n_rays=n, chunk=chunk, focal=float(focal), seed=int(seed), ray_id0=int(ray_id0),
+                        skip_eps=float(skip_eps), t_cut=float(t_cut), white_bg=1)
+    st = _lib.lib().nmf_render_rays(scene.ref(), C.byref(rp), _p(r), C.byref(buffers.c_images), C.byref(buffers.c_counters),
+                                    C.c_void_p(buffers.ws_ptr), buffers.ws_bytes, _stream())
+    _lib.check(st, "nmf_render_rays")
+    images = {k: v[:n] for k, v in buffers.images.items()}
+    stats = dict(buffers=buffers)
+    if check_errors:
+        stats.update(read_counters(buffers, n, chunk))
+    return images, stats
+
+
+def read_counters(buffers, n, chunk):
+    """Synchronises; raises when a device-side list overflowed (results would be incomplete)."""
+    nc = (n + chunk - 1) // chunk
+    c = {k: v.cpu() for k, v in buffers.counters.items()}
+    err = int(c["error"][0])
+    if err:
+        msgs = [m for bit, m in _lib.DEV_ERRORS.items() if err & bit]
+        raise _lib.NmfError("nmf_render_rays: " + "; ".join(msgs) + " (render fewer rays per call)")
+    out = {k: c[k][:nc].tolist() for k in ("n_samples0", "n_samples1", "n_cand", "n_bounce_rays0", "n_bounce_rays1", "n_retrace")}
+    out["n_shaded"] = c["n_shaded"].tolist()
+    out["n_samples"] = [[a, b] for a, b in zip(out["n_samples0"], out["n_samples1"])]
+    return out
