@@ -113,6 +113,12 @@ typedef struct NmfScene {
   int max_brdf_rays1;      /* max_brdf_rays[1] = 450000 */
   int max_retrace;         /* max_retrace_rays[0] = 1000; 0 disables the secondary level */
   int model;               /* 0 = microfacet, 1 = plain view-MLP (models/tensorf.py) */
+
+  /* BRDF MLP operands for the tensor-core path: layers 0 and 1 in the canonical K-major operand layout of
+   * tcgen05.mma ([K/4][64 rows][4], K zero-padded 66 -> 72, values rounded to TF32); see csrc/nmf_mlp_tc.cuh */
+  const float* brdf_w0u;
+  const float* brdf_w1u;
+  int mlp_mode;            /* 0 = tcgen05 kind::tf32 (fp32 accumulate), 1 = fp32 SIMT */
 } NmfScene;
 
 /* per-call render parameters */
@@ -157,6 +163,15 @@ typedef struct NmfCounters {
 } NmfCounters;
 
 int nmf_abi_version(void);
+
+/* Optional phase timing for bench.py / profiling: when enabled, nmf_render_rays records a CUDA event on the caller's
+ * stream after each phase; nmf_profile_read (after the stream is synchronised) returns the elapsed milliseconds of
+ * the NMF_N_PHASES phases of the LAST call: march0, shade0, bounce0, select, march1, shade1, bounce1, reduce1,
+ * incoming0, reduce0, finish. */
+#define NMF_N_PHASES 11
+int nmf_profile_enable(int on);
+int nmf_profile_read(float* ms, int n);
+const char* nmf_profile_phase_name(int i);
 
 /* Bytes of scratch nmf_render_rays needs for `n_rays` rays in chunks of `chunk`. */
 size_t nmf_workspace_bytes(const NmfScene* scene, int n_rays, int chunk);

@@ -37,6 +37,7 @@ class NmfScene(C.Structure):
         ("plain_w0t", C.c_void_p), ("plain_b0", C.c_void_p), ("plain_w1t", C.c_void_p), ("plain_b1", C.c_void_p),
         ("plain_w2t", C.c_void_p), ("plain_b2", C.c_void_p),
         ("rays_per_ray", C.c_int), ("max_brdf_rays1", C.c_int), ("max_retrace", C.c_int), ("model", C.c_int),
+        ("brdf_w0u", C.c_void_p), ("brdf_w1u", C.c_void_p), ("mlp_mode", C.c_int),
     ]
 
 
@@ -69,6 +70,7 @@ class NmfError(RuntimeError):
 _ERRORS = {-1: "NMF_E_ARG (null pointer or non-positive size)",
            -2: "NMF_E_UNSUPPORTED (shape outside what the kernels are compiled for)",
            -3: "NMF_E_WORKSPACE (workspace too small)"}
+N_PHASES = 11
 DEV_ERRORS = {1: "surviving-sample list overflowed", 2: "bounce-sample list overflowed",
               4: "a chunk's bounce-ray region overflowed"}
 
@@ -98,6 +100,9 @@ def lib():
     IP, CP = C.POINTER(NmfImages), C.POINTER(NmfCounters)
     sigs = {
         "nmf_abi_version": (I, []),
+        "nmf_profile_enable": (I, [I]),
+        "nmf_profile_read": (I, [P, I]),
+        "nmf_profile_phase_name": (C.c_char_p, [I]),
         "nmf_workspace_bytes": (C.c_size_t, [SP, I, I]),
         "nmf_render_rays": (I, [SP, RP, P, IP, CP, P, C.c_size_t, P]),
         "nmf_render_rays_host": (I, [SP, RP, P, P, IP, IP, CP, CP, P, C.c_size_t, P]),
@@ -120,6 +125,6 @@ def lib():
     return L
 
 
-EXPORTED = ["nmf_abi_version", "nmf_workspace_bytes", "nmf_render_rays", "nmf_render_rays_host", "nmf_sample_rays",
+EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_profile_phase_name", "nmf_workspace_bytes", "nmf_render_rays", "nmf_render_rays_host", "nmf_sample_rays",
             "nmf_vm_density", "nmf_vm_appfeature", "nmf_vm_normals", "nmf_env_lookup", "nmf_ggx_sample",
             "nmf_brdf_mlp", "nmf_material_heads", "nmf_dense_alpha"]

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include "nmf_field.cuh"
+#include "nmf_mlp_tc.cuh"
 
 #define FULL 0xffffffffu
 #define NMF_BRAY_CAP_PER_RAY 160   // bounce rays per primary ray a chunk region can hold (typical: 57)
@@ -481,17 +482,20 @@ __device__ __forceinline__ void mlp_forward(const float* sm, float* x, float brd
   out3[1] = nmf_sigmoid(o1 + brdf_bias);
   out3[2] = nmf_sigmoid(o2 + brdf_bias);
 }
-__device__ __forceinline__ void mlp_encode(float* x, nmf_v3 half_l, nmf_v3 diff_l, float rough) {
-  // modules/brdf.py:216-225: [feat | ISH(half) | half | ISH(diff) | diff]; feat is already in rows 0..23
-  float e[18];
-  nmf_ish18(half_l, rough, e);
+// modules/brdf.py:216-225: x = [feat | ISH(half) | half | ISH(diff) | diff | 0-pad]; feat is already in x[0..23]
+__device__ __forceinline__ void mlp_encode(float (&x)[TC_K0], nmf_v3 half_l, nmf_v3 diff_l, float rough) {
+  nmf_ish18(half_l, rough, &x[24]);
+  x[42] = half_l.x; x[43] = half_l.y; x[44] = half_l.z;
+  nmf_ish18(diff_l, rough, &x[45]);
+  x[63] = diff_l.x; x[64] = diff_l.y; x[65] = diff_l.z;
 #pragma unroll
-  for (int i = 0; i < 18; ++i) x[(24 + i) * MLP_THREADS] = e[i];
-  x[42 * MLP_THREADS] = half_l.x; x[43 * MLP_THREADS] = half_l.y; x[44 * MLP_THREADS] = half_l.z;
-  nmf_ish18(diff_l, rough, e);
+  for (int i = 66; i < TC_K0; ++i) x[i] = 0.f;
+}
+// fp32 SIMT variant (scene.mlp_mode == 1): stage the row in this thread's shared-memory column, then mlp_forward
+__device__ __forceinline__ void mlp_simt(const float* sm, float* xcol, const float (&x)[TC_K0], float brdf_bias, float* out3) {
 #pragma unroll
-  for (int i = 0; i < 18; ++i) x[(45 + i) * MLP_THREADS] = e[i];
-  x[63 * MLP_THREADS] = diff_l.x; x[64 * MLP_THREADS] = diff_l.y; x[65 * MLP_THREADS] = diff_l.z;
+  for (int i = 0; i < 66; ++i) xcol[i * MLP_THREADS] = x[i];
+  mlp_forward(sm, xcol, brdf_bias, out3);
 }
 
 // ================================================================================================
@@ -502,37 +506,48 @@ struct BounceArgs {
   float* score_sum;
 };
 
-template <int LEVEL>
+template <int LEVEL, int TC>
 __global__ void __launch_bounds__(MLP_THREADS) k_bounce(const NmfScene s, const BounceArgs a) {
-  extern __shared__ __align__(16) float sm[];
-  mlp_load_weights(s, sm);
-  __syncthreads();
-  float* x = sm + (MLP_SMEM_FLOATS - 66 * MLP_THREADS) + threadIdx.x;
+  extern __shared__ __align__(128) float sm[];
+  TcMlp tc;
+  float* xcol = nullptr;
+  if (TC) {
+    tc_mlp_init(tc, sm, s.brdf_w0u, s.brdf_w1u, s.brdf_b0, s.brdf_b1, s.brdf_w2t, s.brdf_b2);
+  } else {
+    mlp_load_weights(s, sm);
+    __syncthreads();
+    xcol = sm + (MLP_SMEM_FLOATS - 66 * MLP_THREADS) + threadIdx.x;
+  }
   const int chunk = blockIdx.y;
   const int n = min(a.ray_count[chunk], a.cap_rays);
   BRay* region = a.brays + (size_t)chunk * a.cap_rays;
   const uint32_t* owner = a.owner + (size_t)chunk * a.cap_rays;
   float block_score = 0.f;
-  for (int r = blockIdx.x * MLP_THREADS + threadIdx.x; r < n; r += gridDim.x * MLP_THREADS) {
-    const uint32_t slot = owner[r];
+  for (int r0 = blockIdx.x * MLP_THREADS; r0 < n; r0 += gridDim.x * MLP_THREADS) {
+    const int r = r0 + threadIdx.x;
+    const bool active = r < n;
+    const uint32_t slot = active ? owner[r] : 0u;
     const BSample* b = a.bs + slot;
-    const int j = r - (int)b->roff;
+    const int j = active ? r - (int)b->roff : 0;
     const float4 q0 = *(const float4*)b->pos, q1 = *(const float4*)b->V, q2 = *(const float4*)b->N;
     const nmf_v3 V = nmf_mk3(q1.x, q1.y, q1.z), N = nmf_mk3(q2.x, q2.y, q2.z);
     const float rough = q1.w, w = q0.w;
-    const int count = __float_as_int(q2.w);
+    const int count = max(__float_as_int(q2.w), 1);
     const uint64_t skey = b->key;
     const float u1 = nmf_wrap01(__ldg(s.sobol + 2 * j) + 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_U));
     const float u2 = nmf_wrap01(__ldg(s.sobol + 2 * j + 1) + 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_V));
     const NmfGGX g = nmf_ggx_sample(u1, u2, V, N, rough);
+    float x[TC_K0];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const float4 f = *(const float4*)(b->feat + 4 * i);
-      x[(4 * i) * MLP_THREADS] = f.x; x[(4 * i + 1) * MLP_THREADS] = f.y; x[(4 * i + 2) * MLP_THREADS] = f.z; x[(4 * i + 3) * MLP_THREADS] = f.w;
+      x[4 * i] = f.x; x[4 * i + 1] = f.y; x[4 * i + 2] = f.z; x[4 * i + 3] = f.w;
     }
     mlp_encode(x, g.half_l, g.diff_l, rough);
     float bw[3];
-    mlp_forward(sm, x, s.brdf_bias, bw);
+    if (TC) tc_mlp_forward(tc, x, s.brdf_bias, bw);      // all 128 threads: the tile is one tensor-core GEMM
+    else if (active) mlp_simt(sm, xcol, x, s.brdf_bias, bw);
+    if (!active) continue;
     const float mip = -logf((float)count) - g.logpdf;                    // microfacet.py:445-448
     BRay* o = region + r;
     float4 st0, st1;
@@ -574,6 +589,7 @@ __global__ void __launch_bounds__(MLP_THREADS) k_bounce(const NmfScene s, const 
     for (int off = 16; off > 0; off >>= 1) block_score += __shfl_xor_sync(FULL, block_score, off);
     if ((threadIdx.x & 31) == 0 && block_score != 0.f) atomicAdd(a.score_sum + chunk, block_score);
   }
+  if (TC) tc_mlp_free(tc);
 }
 
 // ================================================================================================
@@ -768,7 +784,7 @@ __global__ void k_finish1(const NmfScene s, const float* rays1, const float* mip
 // ================================================================================================
 struct PlainArgs { const float* rays; const float* tmin; const Surv* surv; const int* n_surv; int cap_surv; float* accum; };
 __global__ void __launch_bounds__(128) k_shade_plain(const NmfScene s, const PlainArgs a) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(128) float sm[];
   float* xbuf = sm;                       // [135][128]
   float* hbuf = sm + 135 * 128;           // [128][128]
   const int n = min(*a.n_surv, a.cap_surv);
@@ -948,6 +964,38 @@ static int check_scene(const NmfScene* s) {
   return NMF_OK;
 }
 
+// ---- optional phase timing: CUDA events recorded on the caller's stream between the phases ----
+static const char* g_phase_names[NMF_N_PHASES] = {"march0", "shade0", "bounce0", "select", "march1", "shade1", "bounce1",
+                                                   "reduce1", "incoming0", "reduce0", "finish"};
+static cudaEvent_t g_ev[NMF_N_PHASES + 1];
+static bool g_ev_made = false, g_prof_on = false, g_ev_rec[NMF_N_PHASES + 1];
+static void prof_mark(int i, cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEventRecord(g_ev[i], st);
+  g_ev_rec[i] = true;
+}
+extern "C" int nmf_profile_enable(int on) {
+  if (on && !g_ev_made) {
+    for (int i = 0; i <= NMF_N_PHASES; ++i) CK(cudaEventCreate(&g_ev[i]));
+    g_ev_made = true;
+  }
+  g_prof_on = on != 0;
+  for (int i = 0; i <= NMF_N_PHASES; ++i) g_ev_rec[i] = false;
+  return NMF_OK;
+}
+extern "C" int nmf_profile_read(float* ms, int n) {
+  if (!ms || n < NMF_N_PHASES || !g_ev_made) return NMF_E_ARG;
+  int last = 0;
+  for (int i = 0; i < NMF_N_PHASES; ++i) {
+    ms[i] = 0.f;
+    if (!g_ev_rec[i + 1] || !g_ev_rec[last]) continue;
+    CK(cudaEventElapsedTime(&ms[i], g_ev[last], g_ev[i + 1]));
+    last = i + 1;
+  }
+  return NMF_OK;
+}
+extern "C" const char* nmf_profile_phase_name(int i) { return (i >= 0 && i < NMF_N_PHASES) ? g_phase_names[i] : ""; }
+
 extern "C" int nmf_abi_version(void) { return NMF_ABI_VERSION; }
 
 extern "C" size_t nmf_workspace_bytes(const NmfScene* scene, int n_rays, int chunk) {
@@ -964,7 +1012,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
   if (!rp || !rays || !out || !workspace || rp->n_rays <= 0 || rp->chunk <= 0) return NMF_E_ARG;
   if (((uintptr_t)workspace & 255) != 0) return NMF_E_ARG;
   const NmfScene& s = *scene;
-  if (s.model == 0 && (!s.aval[0] || !s.dpack[0] || !s.basis_t || !s.head_w || !s.brdf_w0t || !s.sobol || !s.sh_conv || !s.env_sat))
+  if (s.model == 0 && (!s.aval[0] || !s.dpack[0] || !s.basis_t || !s.head_w || !s.brdf_w0t || !s.brdf_w0u || !s.brdf_w1u || !s.sobol || !s.sh_conv || !s.env_sat))
     return NMF_E_ARG;
   if (s.model == 1 && (!s.aval[0] || !s.basis_t || !s.plain_w0t)) return NMF_E_ARG;
   if (s.model == 0 && s.max_retrace > 0 && s.max_brdf_rays1 <= 0) return NMF_E_ARG;
@@ -974,6 +1022,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
   if (w.total > workspace_bytes) return NMF_E_WORKSPACE;
   const int n = rp->n_rays, nc = w.n_chunks;
   CK(cudaMemsetAsync(w.counters_base, 0, w.counters_bytes, stream));
+  prof_mark(0, stream);
 
   MarchArgs m0 = {};
   m0.rays = rays; m0.n = n; m0.group = rp->chunk; m0.seed = rp->seed; m0.ray_id0 = rp->ray_id0;
@@ -983,6 +1032,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
   m0.surv = w.surv0; m0.n_surv = w.n_surv; m0.cap_surv = w.cap_surv0; m0.error = w.error;
   k_march<0><<<blocks_for(n, 8, 8), 256, 0, stream>>>(s, m0);
   CKL();
+  prof_mark(1, stream);
 
   if (s.model == 0) {
     ShadeArgs h0 = {};
@@ -992,24 +1042,31 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
     h0.owner = w.owner0; h0.error = w.error;
     k_shade<0><<<sm_count() * 6, 256, 0, stream>>>(s, h0);
     CKL();
+    prof_mark(2, stream);
 
-    const size_t mlp_smem = MLP_SMEM_FLOATS * sizeof(float);
+    const bool tcm = s.mlp_mode == 0;
+    const size_t mlp_smem = tcm ? (size_t)TC_SMEM_BYTES : MLP_SMEM_FLOATS * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
-      CK(cudaFuncSetAttribute(k_bounce<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem));
-      CK(cudaFuncSetAttribute(k_bounce<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem));
+      CK(cudaFuncSetAttribute(k_bounce<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MLP_SMEM_FLOATS * sizeof(float))));
+      CK(cudaFuncSetAttribute(k_bounce<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MLP_SMEM_FLOATS * sizeof(float))));
+      CK(cudaFuncSetAttribute(k_bounce<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+      CK(cudaFuncSetAttribute(k_bounce<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
       attr_done = true;
     }
     int gx = (sm_count() * 6 + nc - 1) / nc;
     if (gx < 1) gx = 1;
     BounceArgs b0 = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.score_sum};
-    k_bounce<0><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b0);
+    if (tcm) k_bounce<0, 1><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b0);
+    else k_bounce<0, 0><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b0);
     CKL();
+    prof_mark(3, stream);
 
     if (s.max_retrace > 0) {
       SelectArgs sa = {w.bs0, w.brays0, w.ray_count0, w.cap_rays0, w.score_sum, s.max_retrace, w.n_sec, w.rays1, w.mip1, w.key1};
       k_select<<<nc, 1024, 0, stream>>>(sa);
       CKL();
+      prof_mark(4, stream);
       MarchArgs m1 = {};
       m1.rays = w.rays1; m1.n = w.n_rays1; m1.group = s.max_retrace; m1.n_active = w.n_sec; m1.keys = w.key1;
       m1.skip_eps = rp->skip_eps; m1.t_cut = rp->t_cut;
@@ -1018,6 +1075,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
       m1.surv = w.surv1; m1.n_surv = w.n_surv + 1; m1.cap_surv = w.cap_surv1; m1.error = w.error;
       k_march<1><<<blocks_for(w.n_rays1, 8, 8), 256, 0, stream>>>(s, m1);
       CKL();
+      prof_mark(5, stream);
       ShadeArgs h1 = {};
       h1.rays = w.rays1; h1.tmin = w.tmin1; h1.keys = w.key1; h1.group = s.max_retrace;
       h1.surv = w.surv1; h1.n_surv = w.n_surv + 1; h1.cap_surv = w.cap_surv1; h1.accum = nullptr;
@@ -1025,23 +1083,29 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
       h1.owner = w.owner1; h1.n_samples = w.n_samples1; h1.wsum = w.wsum1; h1.error = w.error;
       k_shade<1><<<sm_count() * 6, 256, 0, stream>>>(s, h1);
       CKL();
+      prof_mark(6, stream);
       BounceArgs b1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr};
-      k_bounce<1><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b1);
+      if (tcm) k_bounce<1, 1><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b1);
+      else k_bounce<1, 0><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b1);
       CKL();
+      prof_mark(7, stream);
       ReduceArgs r1 = {w.bs1, w.n_bs + 1, w.cap_bs1, w.brays1, w.cap_rays1, w.accum1};
       k_reduce<1><<<sm_count() * 4, 256, 0, stream>>>(r1);
       CKL();
       k_finish1<<<(w.n_rays1 + 127) / 128, 128, 0, stream>>>(s, w.rays1, w.mip1, w.acc1, w.accum1, w.n_sec, s.max_retrace,
                                                            w.n_rays1, w.rgb1);
       CKL();
+      prof_mark(8, stream);
     }
     IncomingArgs ia = {w.bs0, w.brays0, w.ray_count0, w.cap_rays0, w.rgb1, s.max_retrace};
     int gxi = (sm_count() * 8 + nc - 1) / nc;
     k_incoming<<<dim3(gxi, nc), 256, 0, stream>>>(s, ia);
     CKL();
+    prof_mark(9, stream);
     ReduceArgs r0 = {w.bs0, w.n_bs, w.cap_bs0, w.brays0, w.cap_rays0, w.accum0};
     k_reduce<0><<<sm_count() * 4, 256, 0, stream>>>(r0);
     CKL();
+    prof_mark(10, stream);
   } else {
     const size_t smem = (135 + 128) * 128 * sizeof(float);
     static bool attr_done2 = false;
@@ -1052,6 +1116,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
     PlainArgs pa = {rays, w.tmin0, w.surv0, w.n_surv, w.cap_surv0, w.accum0};
     k_shade_plain<<<sm_count(), 128, smem, stream>>>(s, pa);
     CKL();
+    prof_mark(2, stream);
   }
   FinishArgs fa = {rays, w.tmin0, w.acc0, w.depth0, w.termk0, w.nvalid0, w.accum0, n, rp->focal, s.model};
   k_finish0<<<(n + 127) / 128, 128, 0, stream>>>(s, fa, *out);
@@ -1060,6 +1125,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
     k_export_counters<<<(nc + 127) / 128 > 0 ? (nc + 127) / 128 : 1, 128, 0, stream>>>(w, *counters, s.model);
     CKL();
   }
+  prof_mark(11, stream);
   return NMF_OK;
 }
 
@@ -1238,28 +1304,49 @@ extern "C" int nmf_ggx_sample(const float* u, const float* V, const float* N, co
   CKL();
   return NMF_OK;
 }
+template <int TC>
 __global__ void __launch_bounds__(MLP_THREADS) k_brdf_mlp(const NmfScene s, const float* feat, const float* half_l,
                                                           const float* diff_l, const float* rough, int n, float* out) {
-  extern __shared__ __align__(16) float sm[];
-  mlp_load_weights(s, sm);
-  __syncthreads();
-  float* x = sm + (MLP_SMEM_FLOATS - 66 * MLP_THREADS) + threadIdx.x;
-  for (int i = blockIdx.x * MLP_THREADS + threadIdx.x; i < n; i += gridDim.x * MLP_THREADS) {
-    for (int k = 0; k < 24; ++k) x[k * MLP_THREADS] = feat[(size_t)i * 24 + k];
-    mlp_encode(x, nmf_mk3(half_l[3 * i], half_l[3 * i + 1], half_l[3 * i + 2]),
-               nmf_mk3(diff_l[3 * i], diff_l[3 * i + 1], diff_l[3 * i + 2]), rough[i]);
-    float bw[3];
-    mlp_forward(sm, x, s.brdf_bias, bw);
-    out[3 * i] = bw[0]; out[3 * i + 1] = bw[1]; out[3 * i + 2] = bw[2];
+  extern __shared__ __align__(128) float sm[];
+  TcMlp tc;
+  float* xcol = nullptr;
+  if (TC) {
+    tc_mlp_init(tc, sm, s.brdf_w0u, s.brdf_w1u, s.brdf_b0, s.brdf_b1, s.brdf_w2t, s.brdf_b2);
+  } else {
+    mlp_load_weights(s, sm);
+    __syncthreads();
+    xcol = sm + (MLP_SMEM_FLOATS - 66 * MLP_THREADS) + threadIdx.x;
   }
+  for (int i0 = blockIdx.x * MLP_THREADS; i0 < n; i0 += gridDim.x * MLP_THREADS) {
+    const int i = i0 + threadIdx.x;
+    const bool active = i < n;
+    const int ii = active ? i : 0;
+    float x[TC_K0];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) x[k] = feat[(size_t)ii * 24 + k];
+    mlp_encode(x, nmf_mk3(half_l[3 * ii], half_l[3 * ii + 1], half_l[3 * ii + 2]),
+               nmf_mk3(diff_l[3 * ii], diff_l[3 * ii + 1], diff_l[3 * ii + 2]), rough[ii]);
+    float bw[3];
+    if (TC) tc_mlp_forward(tc, x, s.brdf_bias, bw);
+    else if (active) mlp_simt(sm, xcol, x, s.brdf_bias, bw);
+    if (active) { out[3 * i] = bw[0]; out[3 * i + 1] = bw[1]; out[3 * i + 2] = bw[2]; }
+  }
+  if (TC) tc_mlp_free(tc);
 }
 extern "C" int nmf_brdf_mlp(const NmfScene* scene, const float* feat, const float* half_local, const float* diff_local,
                             const float* rough, int n, float* out, void* stream) {
-  if (!scene || !scene->brdf_w0t || !feat || !half_local || !diff_local || !rough || !out || n <= 0) return NMF_E_ARG;
-  const size_t smem = MLP_SMEM_FLOATS * sizeof(float);
+  if (!scene || !scene->brdf_w0t || !scene->brdf_w0u || !scene->brdf_w1u || !feat || !half_local || !diff_local || !rough || !out || n <= 0)
+    return NMF_E_ARG;
   static bool done = false;
-  if (!done) { CK(cudaFuncSetAttribute(k_brdf_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
-  k_brdf_mlp<<<blocks_for(n, MLP_THREADS, 3), MLP_THREADS, smem, (cudaStream_t)stream>>>(*scene, feat, half_local, diff_local, rough, n, out);
+  if (!done) {
+    CK(cudaFuncSetAttribute(k_brdf_mlp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MLP_SMEM_FLOATS * sizeof(float))));
+    CK(cudaFuncSetAttribute(k_brdf_mlp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    done = true;
+  }
+  if (scene->mlp_mode == 0)
+    k_brdf_mlp<1><<<blocks_for(n, MLP_THREADS, 3), MLP_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(*scene, feat, half_local, diff_local, rough, n, out);
+  else
+    k_brdf_mlp<0><<<blocks_for(n, MLP_THREADS, 3), MLP_THREADS, MLP_SMEM_FLOATS * sizeof(float), (cudaStream_t)stream>>>(*scene, feat, half_local, diff_local, rough, n, out);
   CKL();
   return NMF_OK;
 }

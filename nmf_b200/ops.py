@@ -183,3 +183,15 @@ def read_counters(buffers, n, chunk):
     out["n_shaded"] = c["n_shaded"].tolist()
     out["n_samples"] = [[a, b] for a, b in zip(out["n_samples0"], out["n_samples1"])]
     return out
+
+
+def profile_enable(on=True):
+    _lib.check(_lib.lib().nmf_profile_enable(int(on)), "nmf_profile_enable")
+
+
+def profile_read():
+    """Elapsed milliseconds of the phases of the last nmf_render_rays call (synchronise the stream first)."""
+    L = _lib.lib()
+    arr = (C.c_float * _lib.N_PHASES)()
+    _lib.check(L.nmf_profile_read(arr, _lib.N_PHASES), "nmf_profile_read")
+    return {L.nmf_profile_phase_name(i).decode(): float(arr[i]) for i in range(_lib.N_PHASES)}

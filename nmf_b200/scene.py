@@ -66,6 +66,12 @@ def pack_bits(vol):
     return words.contiguous().view(-1), pitch
 
 
+def round_tf32(x):
+    """round-to-nearest (ties away, like cvt.rna.tf32.f32) of fp32 to the 10-bit TF32 mantissa"""
+    b = x.contiguous().view(torch.int32)
+    return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def build_sat(bg_mat, brightness, mul):
     """exp activation and summed-area table (integral_equirect.py:263-273, 431-433).  The reference runs two fp32
     cumsums; on CPU ATen accumulates each in double and rounds every prefix to fp32, which is reproduced here
@@ -152,6 +158,13 @@ class DeviceScene:
                 self._ptr(s, f"brdf_w{i}t", w.t().contiguous())
                 self._ptr(s, f"brdf_b{i}", b)
             assert tuple(self.keep["brdf_w0t"].shape) == (66, 64) and tuple(self.keep["brdf_w2t"].shape) == (64, 4)
+            # tensor-core operands (csrc/nmf_mlp_tc.cuh): W (64 out, K in) -> [K/4][64][4], K padded to 72, TF32-rounded
+            for i, kpad in ((0, 72), (1, 64)):
+                w = self.keep[f"brdf_w{i}t"].t()                                  # (64, K)
+                wp = torch.zeros(64, kpad, device=dev)
+                wp[:, :w.shape[1]] = w
+                self._ptr(s, f"brdf_w{i}u", round_tf32(wp).view(64, kpad // 4, 4).permute(1, 0, 2).contiguous())
+            s.mlp_mode = 0 if self.hp.get("mlp", "tf32") == "tf32" else 1
             sob = g("model.brdf_sampler.angs")
             assert sob.shape[0] >= 400 and sob.shape[1] == 2
             self._ptr(s, "sobol", sob)
@@ -214,6 +227,17 @@ class DeviceScene:
         s.occ_vox, s.occ_cell = vox_bits.data_ptr(), cell_bits.data_ptr()
         s.ow, s.oh, s.od, s.opitch, s.has_occ = W, H, D, pitch, 1
         self.alpha_volume = vol
+
+    def update_alpha_mask(self, grid_size=None):
+        """AlphaGridSampler.updateAlphaMask (samplers/alphagrid.py:249-276): dense alpha on the lattice (CUDA,
+        nmf_dense_alpha), 3^3 max-pool dilation, threshold -> 0/1 volume (Gz,Gy,Gx); installs it as the occupancy."""
+        from . import ops
+        gs = self.grid_size if grid_size is None else [int(g) for g in grid_size]
+        alpha = ops.dense_alpha(self, gs).clamp(0, 1)[None, None]
+        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1)[0, 0]
+        vol = (alpha >= self.hp["alpha_mask_thres"]).float()
+        self.set_alpha_volume(vol)
+        return vol
 
     def sh_irradiance(self, G=100, mipval=-5.0):
         """get_spherical_harmonics(100) (integral_equirect.py:324-360) convolved with the clamped-cosine lobe
