@@ -144,7 +144,7 @@ class DeviceScene:
             raise _lib.NmfError("kernels are compiled for app_dim=24")
         self._ptr(s, "basis_t", basis.t().contiguous())
 
-        model = self.hp["model"]
+        model = self.hp["model"]          # "microfacet" | "plain" | "field" (factors only: plugin-slot field queries)
         s.model = 0 if model == "microfacet" else 1
         if model == "microfacet":
             g = lambda k: f32(state[k])
@@ -168,7 +168,7 @@ class DeviceScene:
             sob = g("model.brdf_sampler.angs")
             assert sob.shape[0] >= 400 and sob.shape[1] == 2
             self._ptr(s, "sobol", sob)
-        else:
+        elif model == "plain":
             for i, li in enumerate((0, 2, 4)):
                 w, b = f32(state[f"model.diffuse_module.mlp.{li}.weight"]), f32(state[f"model.diffuse_module.mlp.{li}.bias"])
                 self._ptr(s, f"plain_w{i}t", w.t().contiguous())
@@ -180,7 +180,26 @@ class DeviceScene:
         s.max_brdf_rays1 = int(self.hp["max_brdf_rays"][1]) if len(self.hp["max_brdf_rays"]) > 1 else 0
         s.max_retrace = int(self.hp["max_retrace_rays"][0]) if len(self.hp["max_retrace_rays"]) > 0 else 0
 
-        # environment
+        self.c = s
+        self.set_alpha_volume(alpha_volume)
+        if "bg_module.bg_mat" in state:
+            self._set_env(state, sh_conv)
+
+    @classmethod
+    def env_only(cls, bg_mat, mipbias=1.0, brightness=0.0, mul=1.0, device="cuda"):
+        """A scene that only carries the environment tables (for the IntegralEquirect plugin used on its own)."""
+        self = cls.__new__(cls)
+        self.hp = dict(DEFAULT_HP, model="env")
+        self.device = torch.device(device)
+        self.keep = {}
+        self.c = _lib.NmfScene()
+        self._set_env({"bg_module.bg_mat": bg_mat, "bg_module.mipbias": mipbias, "bg_module.brightness": brightness,
+                       "bg_module.mul": mul}, None)
+        return self
+
+    def _set_env(self, state, sh_conv):
+        s, dev, model = self.c, self.device, self.hp["model"]
+        f32 = lambda t: torch.as_tensor(t).detach().to(device=dev, dtype=torch.float32).contiguous()
         bg = f32(state["bg_module.bg_mat"])
         to64 = lambda k, d: torch.as_tensor(state.get(k, d)).detach().to(device=dev, dtype=torch.float64)
         brightness, mul = to64("bg_module.brightness", 0.0), to64("bg_module.mul", 1.0)
@@ -196,8 +215,6 @@ class DeviceScene:
             s.env_top[i] = float(top[i])
             s.env_bot[i] = float(bot[i])
         self.env_act = act
-        self.c = s
-        self.set_alpha_volume(alpha_volume)
         if model == "microfacet":
             if sh_conv is None:
                 sh_conv = self.sh_irradiance()

@@ -1,0 +1,139 @@
+"""GPU: the hydra plugin slots (nmf_b200/plugins.py, config.py, renderer.py) against the oracle, used the way the
+reference's train.py / renderer.py use them."""
+import pytest
+import torch
+
+from conftest import load_fixture, oracle_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from nmf_b200 import config
+    fix = load_fixture("microfacet_g40")
+    G = fix["grid_size"]
+    t, cfg = config.build_model([f"field.grid_size=[{G},{G},{G}]", "model.arch.bg_module.bg_resolution=32"],
+                                aabb=fix["aabb"], near_far=list(fix["near_far"]))
+    t.load_state_dict(fix["state"], strict=False)
+    t = t.cuda().eval()
+    t.sampler.update(t.rf, init=True)
+    return fix, oracle_scene(fix), t
+
+
+def test_update_alpha_mask_matches_reference_volume(model):
+    fix, osc, t = model
+    t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
+    vol = t.sampler.alphaMask.alpha_volume.reshape(-1).cpu()
+    assert torch.equal(vol.to(torch.uint8), fix["alpha_volume"].reshape(-1)), (vol != fix["alpha_volume"].reshape(-1).float()).sum()
+
+
+def test_sampler_and_field_slots(model):
+    from oracle import nmf_oracle as O
+    fix, osc, t = model
+    rays = fix["rays"].cuda()
+    xyzs, ray_valid, S, z_vals, dists, whole_valid = t.sampler.sample(rays, fix["focal"], rf=t.rf)
+    oxyz, ovalid, oz, odists = O.sample_rays(osc, fix["rays"], fix["focal"])
+    assert S == osc.n_samples and torch.equal(ray_valid.cpu(), ovalid) and torch.equal(z_vals.cpu(), oz)
+    # positions bit-exact; the 4th coordinate z/focal is a torch division whose CUDA kernel multiplies by 1/focal
+    assert torch.equal(xyzs.cpu()[:, :3], oxyz[:, :3]) and torch.allclose(xyzs.cpu()[:, 3], oxyz[:, 3], rtol=1e-6)
+    assert torch.equal(dists.cpu(), odists) and bool(whole_valid.all())
+    sig = t.rf.compute_densityfeature(xyzs).cpu()
+    assert torch.allclose(sig, O.feature2density(osc, O.density_feature(osc, oxyz)), rtol=2e-5, atol=1e-6)
+    assert torch.allclose(t.rf.compute_appfeature(xyzs).cpu(), O.app_feature(osc, oxyz), atol=2e-6)
+    sel = sig > 1e-2
+    assert torch.allclose(t.rf.compute_normals(xyzs).cpu()[sel], O.vm_normals(osc, oxyz)[sel], atol=2e-4)
+
+
+def test_bg_module_slot(model):
+    from oracle import nmf_oracle as O
+    fix, osc, t = model
+    g = torch.Generator().manual_seed(3)
+    d = O.unit(torch.randn(4000, 3, generator=g))
+    mip = torch.rand(4000, generator=g) * 10 - 8
+    out = t.bg_module(d.cuda(), mip.cuda().reshape(-1, 1)).cpu()
+    ref = O.env_lookup(osc, d, mip)
+    err = (out - ref).abs() / (ref.abs() + 1e-2)
+    assert err.max() < 5e-2 and err.mean() < 2e-4
+    coeffs, conv = t.bg_module.get_spherical_harmonics(100)
+    assert torch.allclose((conv / 3.14159265).cpu(), O.sh_irradiance_coeffs(osc), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(t.bg_module.mean_color().cpu(), O.env_tables(osc)[0].reshape(3, -1).mean(dim=1), rtol=1e-5)
+
+
+def test_ggx_slot(model):
+    from oracle import nmf_oracle as O
+    fix, osc, t = model
+    g = torch.Generator().manual_seed(4)
+    n, m = 300, 7
+    N = O.unit(torch.randn(n, 3, generator=g))
+    V = O.unit(torch.randn(n, 3, generator=g))
+    N = N * (V * N).sum(-1, keepdim=True).sign()
+    r = torch.rand(n, 1, generator=g) * 0.4 + 0.02
+    u = torch.rand(n, m, 2, generator=g)
+    mask = torch.rand(n, m, generator=g) < 0.7
+    L, cols, lp = O.ggx_sample(u[..., 0], u[..., 1], V, N, r, mask)
+    oL, obasis, olp = t.model.brdf_sampler.sample(u[..., 0].cuda(), u[..., 1].cuda(), V.cuda(), N.cuda(), r.cuda(), r.cuda(), mask.cuda())
+    assert (oL.cpu() - L).abs().median() < 1e-6 and ((oL.cpu() - L).abs().max(dim=1).values < 1e-3).float().mean() > 0.99
+    assert (olp.cpu() - lp).abs().median() < 1e-5
+    assert torch.allclose(obasis.cpu(), cols, atol=1e-5)
+
+
+def test_forward_and_chunk_renderer(model):
+    from nmf_b200 import renderer
+    from oracle import keyed_rng as KR
+    from oracle import nmf_oracle as O
+    from test_gpu_parity import compare_images
+    fix, osc, t = model
+    t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
+    rays = fix["rays"].cuda()
+    t.seed, t._calls = 11, 0
+    ims, stats = t(rays, fix["focal"], is_train=False, ndc_ray=False, N_samples=-1)      # one chunk, like renderer.py:83
+    ref, ns = O.render_rays(osc, fix["rays"], fix["focal"], KR.KeyedRNG(), chunk=rays.shape[0], seed=11)
+    assert stats["n_samples"][0] == ns[0][0] and bool(stats["whole_valid"].all()) and stats["recur"] == 0
+    report, bad = compare_images(ims, ref)
+    assert not bad, bad
+    # chunked driver, device outputs and host outputs
+    ref2, ns2 = O.render_rays(osc, fix["rays"], fix["focal"], KR.KeyedRNG(), chunk=128, seed=11)
+    out, st = renderer.chunk_renderer(rays, t, fix["focal"], keys=["rgb_map", "depth", "n_samples"], chunk=128, is_train=False)
+    assert set(out) == {"rgb_map", "depth"} and [c[0] for c in st["n_samples"]] == [c[0] for c in ns2]
+    assert (out["rgb_map"].cpu() - ref2["rgb_map"]).abs().max() < 2e-3
+    out_h, _ = renderer.chunk_renderer(rays, t, fix["focal"], keys=None, chunk=128, render2completion=True)
+    assert not out_h["rgb_map"].is_cuda and torch.allclose(out_h["rgb_map"], out["rgb_map"].cpu(), atol=1e-5)
+    # host-buffer entry point (nmf_render_rays_host)
+    host = renderer.HostRenderer(t.scene(), rays.shape[0], 128)
+    ims_h, st_h = host.render(fix["rays"].contiguous().pin_memory(), fix["focal"], seed=11)
+    assert torch.allclose(ims_h["rgb_map"], out["rgb_map"].cpu(), atol=1e-5) and torch.equal(ims_h["surf_width"], ref2["surf_width"])
+    assert host.h2d_bytes == rays.shape[0] * 24 and host.d2h_bytes > 0
+
+
+def test_parameter_update_invalidates_scene(model):
+    fix, osc, t = model
+    rays = fix["rays"][:64].cuda()
+    a, _ = t.render_chunks(rays, fix["focal"], chunk=64)
+    a = a["rgb_map"].clone()
+    with torch.no_grad():
+        t.model.diffuse_module.diffuse_mlp[0].bias.add_(1.0)
+    b, _ = t.render_chunks(rays, fix["focal"], chunk=64)
+    assert (a - b["rgb_map"]).abs().max() > 1e-3
+    with torch.no_grad():
+        t.model.diffuse_module.diffuse_mlp[0].bias.sub_(1.0)
+
+
+def test_checkpoint_round_trip(model, tmp_path):
+    from nmf_b200 import config
+    from nmf_b200.plugins import TensorNeRF
+    fix, osc, t = model
+    G = fix["grid_size"]
+    cfg = config.compose([f"field.grid_size=[{G},{G},{G}]", "model.arch.bg_module.bg_resolution=32"])
+    p = str(tmp_path / "ckpt.th")
+    t.save(p, cfg.model.arch)
+    ck = torch.load(p, weights_only=False)
+    assert set(ck) == {"config", "state_dict"}
+    t2 = TensorNeRF.load(ck, near_far=list(fix["near_far"])).cuda().eval()
+    rays = fix["rays"][:64].cuda()
+    t.seed = t2.seed = 3
+    a, _ = t.render_chunks(rays, fix["focal"], chunk=64)
+    b, _ = t2.render_chunks(rays, fix["focal"], chunk=64)
+    assert torch.allclose(a["rgb_map"], b["rgb_map"], atol=1e-5) and torch.equal(a["surf_width"], b["surf_width"])

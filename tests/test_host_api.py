@@ -1,0 +1,122 @@
+"""CPU tests of the host side: C-ABI exports, config loader semantics, plugin state_dict keys, ray sharding (gloo)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_fixture
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    hdr = open(os.path.join(ROOT, "include", "nmf_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(nmf_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 15
+    L = ctypes.CDLL(os.path.join(ROOT, "nmf_b200", "libnmf_b200.so"))
+    for name in declared:
+        assert hasattr(L, name), f"{name} is declared in include/nmf_b200.h but not exported"
+    from nmf_b200 import _lib
+    assert sorted(_lib.EXPORTED) == declared
+    L.nmf_abi_version.restype = ctypes.c_int
+    assert L.nmf_abi_version() == 1
+
+
+def test_struct_mirror_matches_header_size():
+    """ctypes mirror of NmfScene / NmfRender vs the C compiler's layout"""
+    import subprocess, tempfile
+    from nmf_b200 import _lib
+    src = '#include <stdio.h>\n#include "nmf_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(NmfScene), sizeof(NmfRender), sizeof(NmfImages), sizeof(NmfCounters));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
+    assert sizes == [ctypes.sizeof(_lib.NmfScene), ctypes.sizeof(_lib.NmfRender), ctypes.sizeof(_lib.NmfImages),
+                     ctypes.sizeof(_lib.NmfCounters)]
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from nmf_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libnmf_b200.so")
+    with pytest.raises(_lib.NmfError):
+        _lib.lib()
+
+
+def test_ops_reject_cpu_tensors():
+    from nmf_b200 import _lib, ops
+    with pytest.raises(_lib.NmfError):
+        ops._f32(torch.zeros(3, 3), torch.device("cpu"))
+
+
+def test_config_compose_and_overrides():
+    from nmf_b200 import config
+    cfg = config.compose(["dataset=ship", "model.arch.model.anoise=0.1", "model.arch.bg_module.bg_resolution=64"])
+    assert cfg.dataset.near_far == [1, 6]
+    assert cfg.model.arch.model.anoise == 0.1 and cfg.model.arch.bg_module.bg_resolution == 64
+    # YAML 1.1 would read these as strings; OmegaConf (and this loader) read floats
+    assert cfg.model.arch.rf.lr == 2e-2 and cfg.model.arch.model.brdf.lr == 1e-3 and cfg.model.arch.recur_alpha_thres == 1e-3
+    assert cfg.model.arch.normal_module is None
+    assert cfg.model.arch.rf._target_ == "fields.tensoRF.TensorVMSplit"       # rf <- field splice (train.py:911)
+
+
+def test_plugins_keep_reference_state_dict_keys():
+    from nmf_b200 import config
+    fix = load_fixture("microfacet_g40")
+    G = fix["grid_size"]
+    t, _ = config.build_model([f"field.grid_size=[{G},{G},{G}]", "model.arch.bg_module.bg_resolution=32"],
+                              aabb=fix["aabb"], near_far=list(fix["near_far"]))
+    res = t.load_state_dict(fix["state"], strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    mine = t.state_dict()
+    for k, v in fix["state"].items():
+        assert tuple(mine[k].shape) == tuple(v.shape), k
+    assert t.rf.nSamples == 140 or t.rf.nSamples > 0
+    groups = t.get_optparam_groups()
+    assert len(groups) >= 8
+    plain = load_fixture("plain_g64")
+    t2, _ = config.build_model(["model=tensorf", "field.grid_size=[64,64,64]"], aabb=plain["aabb"], near_far=list(plain["near_far"]))
+    res = t2.load_state_dict(plain["state"], strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+
+
+def test_shard_chunks_partition():
+    from nmf_b200.distributed import shard_chunks
+    for n, chunk, world in ((640000, 4096, 8), (10000, 4096, 2), (4096, 4096, 4), (5, 4096, 3), (8192, 4096, 2)):
+        spans = [shard_chunks(n, chunk, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            assert a1 == b0 and a0 <= a1
+        for s0, s1 in spans:
+            assert s0 % chunk == 0 or s0 == n
+
+
+def _worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nmf_b200.distributed import render_sharded
+    n, chunk = 10000, 1024
+    rays = torch.arange(n * 6, dtype=torch.float32).reshape(n, 6)
+
+    def fake_render(r, ray_id0):      # a per-ray function of (ray, global id, chunk id): what the kernels guarantee
+        ids = torch.arange(ray_id0, ray_id0 + r.shape[0])
+        return {"rgb_map": torch.stack([r[:, 0], ids.float(), (ids // chunk).float()], -1), "acc_map": r[:, 5] * 2}
+
+    out = render_sharded(fake_render, rays, chunk)
+    if rank == 0:
+        torch.save(out, os.path.join(tmp, "out.pt"))
+    dist.destroy_process_group()
+
+
+def test_sharded_render_equals_single(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, 29611, str(tmp_path)), nprocs=2, join=True)
+    out = torch.load(os.path.join(str(tmp_path), "out.pt"))
+    n, chunk = 10000, 1024
+    rays = torch.arange(n * 6, dtype=torch.float32).reshape(n, 6)
+    ids = torch.arange(n)
+    assert torch.equal(out["rgb_map"], torch.stack([rays[:, 0], ids.float(), (ids // chunk).float()], -1))
+    assert torch.equal(out["acc_map"], rays[:, 5] * 2)
