@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NMF_ABI_VERSION 1
+#define NMF_ABI_VERSION 2
 
 #define NMF_OK 0
 #define NMF_E_ARG (-1)          /* null pointer / non-positive size                                   */
@@ -114,11 +114,13 @@ typedef struct NmfScene {
   int max_retrace;         /* max_retrace_rays[0] = 1000; 0 disables the secondary level */
   int model;               /* 0 = microfacet, 1 = plain view-MLP (models/tensorf.py) */
 
-  /* BRDF MLP operands for the tensor-core path: layers 0 and 1 in the canonical K-major operand layout of
-   * tcgen05.mma ([K/4][64 rows][4], K zero-padded 66 -> 72, values rounded to TF32); see csrc/nmf_mlp_tc.cuh */
-  const float* brdf_w0u;
-  const float* brdf_w1u;
-  int mlp_mode;            /* 0 = tcgen05 kind::tf32 (fp32 accumulate), 1 = fp32 SIMT */
+  /* BRDF MLP operands for the tensor-core path: fp16 weights of the three layers in the canonical K-major operand
+   * layout of tcgen05.mma ([K/8][rows][8 halves]; rows = 64, 64, 16; K zero-padded to 80; the bias of each layer
+   * sits in column 66, which multiplies a constant-1 input); see csrc/nmf_mlp_tc.cuh */
+  const void* brdf_w0u;
+  const void* brdf_w1u;
+  const void* brdf_w2u;
+  int mlp_mode;            /* 0 = tcgen05 kind::f16 (fp16 operands, fp32 accumulate), 1 = fp32 SIMT */
 } NmfScene;
 
 /* per-call render parameters */

@@ -37,7 +37,7 @@ class NmfScene(C.Structure):
         ("plain_w0t", C.c_void_p), ("plain_b0", C.c_void_p), ("plain_w1t", C.c_void_p), ("plain_b1", C.c_void_p),
         ("plain_w2t", C.c_void_p), ("plain_b2", C.c_void_p),
         ("rays_per_ray", C.c_int), ("max_brdf_rays1", C.c_int), ("max_retrace", C.c_int), ("model", C.c_int),
-        ("brdf_w0u", C.c_void_p), ("brdf_w1u", C.c_void_p), ("mlp_mode", C.c_int),
+        ("brdf_w0u", C.c_void_p), ("brdf_w1u", C.c_void_p), ("brdf_w2u", C.c_void_p), ("mlp_mode", C.c_int),
     ]
 
 
@@ -120,7 +120,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    assert L.nmf_abi_version() == 1, "libnmf_b200.so ABI mismatch: rebuild"
+    assert L.nmf_abi_version() == 2, "libnmf_b200.so ABI mismatch: rebuild"
     _lib = L
     return L
 

@@ -60,6 +60,8 @@ struct WS {
   float* score_sum;   // [n_chunks]
   double* wsum1;      // [n_chunks]
   unsigned* error;    // [1]
+  int* tile_start0;   // [n_chunks + 1]
+  int* tile_start1;   // [n_chunks + 1]
   size_t counters_bytes;
   char* counters_base;
   // level 0
@@ -101,6 +103,8 @@ static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base) {
   w.score_sum = (float*)take(nc * sizeof(float));
   w.wsum1 = (double*)take(nc * sizeof(double));
   w.error = (unsigned*)take(sizeof(unsigned));
+  w.tile_start0 = (int*)take((nc + 1) * sizeof(int));
+  w.tile_start1 = (int*)take((nc + 1) * sizeof(int));
   w.accum0 = (float*)take((size_t)n_rays * A_N * sizeof(float));
   w.accum1 = (float*)take((size_t)w.n_rays1 * 4 * sizeof(float));
   w.counters_bytes = off;   // everything up to here is zeroed at the start of a call
@@ -488,8 +492,9 @@ __device__ __forceinline__ void mlp_encode(float (&x)[TC_K0], nmf_v3 half_l, nmf
   x[42] = half_l.x; x[43] = half_l.y; x[44] = half_l.z;
   nmf_ish18(diff_l, rough, &x[45]);
   x[63] = diff_l.x; x[64] = diff_l.y; x[65] = diff_l.z;
+  x[TC_ONE] = 1.f;                      // carries the biases through the tensor-core GEMMs (nmf_mlp_tc.cuh)
 #pragma unroll
-  for (int i = 66; i < TC_K0; ++i) x[i] = 0.f;
+  for (int i = TC_ONE + 1; i < TC_K0; ++i) x[i] = 0.f;
 }
 // fp32 SIMT variant (scene.mlp_mode == 1): stage the row in this thread's shared-memory column, then mlp_forward
 __device__ __forceinline__ void mlp_simt(const float* sm, float* xcol, const float (&x)[TC_K0], float brdf_bias, float* out3) {
@@ -504,27 +509,60 @@ __device__ __forceinline__ void mlp_simt(const float* sm, float* xcol, const flo
 struct BounceArgs {
   const BSample* bs; BRay* brays; const uint32_t* owner; const int* ray_count; int cap_rays;
   float* score_sum;
+  const int* tile_start;    // [n_chunks + 1] exclusive prefix of the chunks' 128-ray tile counts (k_tile_prefix)
+  int n_chunks;
 };
 
+// tile_start[c] = number of 128-ray tiles in the bounce-ray regions of chunks < c, so that a persistent grid can
+// walk one flat, evenly sized work list instead of a (tiles x chunks) grid with ragged rows
+__global__ void __launch_bounds__(1024) k_tile_prefix(const int* ray_count, int cap_rays, int n_chunks, int* tile_start) {
+  __shared__ int s_part[1024];
+  const int per = (n_chunks + 1023) / 1024;
+  const int c0 = threadIdx.x * per;
+  int sum = 0;
+  for (int c = c0; c < min(c0 + per, n_chunks); ++c) sum += (min(ray_count[c], cap_rays) + MLP_THREADS - 1) / MLP_THREADS;
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = s_part[threadIdx.x] - sum;
+  for (int c = c0; c < min(c0 + per, n_chunks); ++c) {
+    tile_start[c] = run;
+    run += (min(ray_count[c], cap_rays) + MLP_THREADS - 1) / MLP_THREADS;
+  }
+  if (threadIdx.x == 1023) tile_start[n_chunks] = s_part[1023];
+}
+
 template <int LEVEL, int TC>
-__global__ void __launch_bounds__(MLP_THREADS) k_bounce(const NmfScene s, const BounceArgs a) {
+__global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfScene s, const BounceArgs a) {
   extern __shared__ __align__(128) float sm[];
   TcMlp tc;
   float* xcol = nullptr;
   if (TC) {
-    tc_mlp_init(tc, sm, s.brdf_w0u, s.brdf_w1u, s.brdf_b0, s.brdf_b1, s.brdf_w2t, s.brdf_b2);
+    tc_mlp_init(tc, sm, s.brdf_w0u, s.brdf_w1u, s.brdf_w2u);
   } else {
     mlp_load_weights(s, sm);
     __syncthreads();
     xcol = sm + (MLP_SMEM_FLOATS - 66 * MLP_THREADS) + threadIdx.x;
   }
-  const int chunk = blockIdx.y;
-  const int n = min(a.ray_count[chunk], a.cap_rays);
-  BRay* region = a.brays + (size_t)chunk * a.cap_rays;
-  const uint32_t* owner = a.owner + (size_t)chunk * a.cap_rays;
-  float block_score = 0.f;
-  for (int r0 = blockIdx.x * MLP_THREADS; r0 < n; r0 += gridDim.x * MLP_THREADS) {
-    const int r = r0 + threadIdx.x;
+  const int n_tiles = a.tile_start[a.n_chunks];
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // chunk of this tile: last c with tile_start[c] <= tile
+    int lo = 0, hi = a.n_chunks;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(a.tile_start + mid) <= tile) lo = mid; else hi = mid;
+    }
+    const int chunk = lo;
+    const int n = min(a.ray_count[chunk], a.cap_rays);
+    BRay* region = a.brays + (size_t)chunk * a.cap_rays;
+    const uint32_t* owner = a.owner + (size_t)chunk * a.cap_rays;
+    float block_score = 0.f;
+    const int r = (tile - __ldg(a.tile_start + chunk)) * MLP_THREADS + threadIdx.x;
     const bool active = r < n;
     const uint32_t slot = active ? owner[r] : 0u;
     const BSample* b = a.bs + slot;
@@ -547,7 +585,7 @@ __global__ void __launch_bounds__(MLP_THREADS) k_bounce(const NmfScene s, const 
     float bw[3];
     if (TC) tc_mlp_forward(tc, x, s.brdf_bias, bw);      // all 128 threads: the tile is one tensor-core GEMM
     else if (active) mlp_simt(sm, xcol, x, s.brdf_bias, bw);
-    if (!active) continue;
+    if (active) {
     const float mip = -logf((float)count) - g.logpdf;                    // microfacet.py:445-448
     BRay* o = region + r;
     float4 st0, st1;
@@ -559,7 +597,7 @@ __global__ void __launch_bounds__(MLP_THREADS) k_bounce(const NmfScene s, const 
       const float per_ray = fmaxf(bw[0], fmaxf(bw[1], bw[2])) * (nmf_dot(V, N) > 0.f ? 1.f : 0.f) * pdf;
       const float sc = per_ray * (w / ((float)count + 1e-8f));
       st1.w = sc;
-      block_score += sc;
+      block_score = sc;
       *(float4*)o->L = st0;
       *(float4*)o->bw = st1;
       o->slot = -1;
@@ -583,11 +621,12 @@ __global__ void __launch_bounds__(MLP_THREADS) k_bounce(const NmfScene s, const 
       *(float4*)o->comb = st2;
       *(float4*)o->inc = st3;
     }
-  }
-  if (LEVEL == 0) {
+    }
+    if (LEVEL == 0) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) block_score += __shfl_xor_sync(FULL, block_score, off);
-    if ((threadIdx.x & 31) == 0 && block_score != 0.f) atomicAdd(a.score_sum + chunk, block_score);
+      for (int off = 16; off > 0; off >>= 1) block_score += __shfl_xor_sync(FULL, block_score, off);
+      if ((threadIdx.x & 31) == 0 && block_score != 0.f) atomicAdd(a.score_sum + chunk, block_score);
+    }
   }
   if (TC) tc_mlp_free(tc);
 }
@@ -1012,7 +1051,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
   if (!rp || !rays || !out || !workspace || rp->n_rays <= 0 || rp->chunk <= 0) return NMF_E_ARG;
   if (((uintptr_t)workspace & 255) != 0) return NMF_E_ARG;
   const NmfScene& s = *scene;
-  if (s.model == 0 && (!s.aval[0] || !s.dpack[0] || !s.basis_t || !s.head_w || !s.brdf_w0t || !s.brdf_w0u || !s.brdf_w1u || !s.sobol || !s.sh_conv || !s.env_sat))
+  if (s.model == 0 && (!s.aval[0] || !s.dpack[0] || !s.basis_t || !s.head_w || !s.brdf_w0t || !s.brdf_w0u || !s.brdf_w1u || !s.brdf_w2u || !s.sobol || !s.sh_conv || !s.env_sat))
     return NMF_E_ARG;
   if (s.model == 1 && (!s.aval[0] || !s.basis_t || !s.plain_w0t)) return NMF_E_ARG;
   if (s.model == 0 && s.max_retrace > 0 && s.max_brdf_rays1 <= 0) return NMF_E_ARG;
@@ -1054,11 +1093,13 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
       CK(cudaFuncSetAttribute(k_bounce<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
       attr_done = true;
     }
-    int gx = (sm_count() * 6 + nc - 1) / nc;
-    if (gx < 1) gx = 1;
-    BounceArgs b0 = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.score_sum};
-    if (tcm) k_bounce<0, 1><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b0);
-    else k_bounce<0, 0><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b0);
+    // persistent grid over the flat tile list: 5 CTAs per SM with the fp16 operand tiles, 3 with the fp32 SIMT staging
+    const int gb = sm_count() * (tcm ? 5 : 3);
+    k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count0, w.cap_rays0, nc, w.tile_start0);
+    CKL();
+    BounceArgs b0 = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.score_sum, w.tile_start0, nc};
+    if (tcm) k_bounce<0, 1><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b0);
+    else k_bounce<0, 0><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b0);
     CKL();
     prof_mark(3, stream);
 
@@ -1084,9 +1125,11 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
       k_shade<1><<<sm_count() * 6, 256, 0, stream>>>(s, h1);
       CKL();
       prof_mark(6, stream);
-      BounceArgs b1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr};
-      if (tcm) k_bounce<1, 1><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b1);
-      else k_bounce<1, 0><<<dim3(gx, nc), MLP_THREADS, mlp_smem, stream>>>(s, b1);
+      k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count1, w.cap_rays1, nc, w.tile_start1);
+      CKL();
+      BounceArgs b1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr, w.tile_start1, nc};
+      if (tcm) k_bounce<1, 1><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b1);
+      else k_bounce<1, 0><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b1);
       CKL();
       prof_mark(7, stream);
       ReduceArgs r1 = {w.bs1, w.n_bs + 1, w.cap_bs1, w.brays1, w.cap_rays1, w.accum1};
@@ -1311,7 +1354,7 @@ __global__ void __launch_bounds__(MLP_THREADS) k_brdf_mlp(const NmfScene s, cons
   TcMlp tc;
   float* xcol = nullptr;
   if (TC) {
-    tc_mlp_init(tc, sm, s.brdf_w0u, s.brdf_w1u, s.brdf_b0, s.brdf_b1, s.brdf_w2t, s.brdf_b2);
+    tc_mlp_init(tc, sm, s.brdf_w0u, s.brdf_w1u, s.brdf_w2u);
   } else {
     mlp_load_weights(s, sm);
     __syncthreads();
@@ -1335,7 +1378,7 @@ __global__ void __launch_bounds__(MLP_THREADS) k_brdf_mlp(const NmfScene s, cons
 }
 extern "C" int nmf_brdf_mlp(const NmfScene* scene, const float* feat, const float* half_local, const float* diff_local,
                             const float* rough, int n, float* out, void* stream) {
-  if (!scene || !scene->brdf_w0t || !scene->brdf_w0u || !scene->brdf_w1u || !feat || !half_local || !diff_local || !rough || !out || n <= 0)
+  if (!scene || !scene->brdf_w0t || !scene->brdf_w0u || !scene->brdf_w1u || !scene->brdf_w2u || !feat || !half_local || !diff_local || !rough || !out || n <= 0)
     return NMF_E_ARG;
   static bool done = false;
   if (!done) {

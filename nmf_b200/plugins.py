@@ -464,7 +464,7 @@ class TensorNeRF(nn.Module):
         self.lr_scale, self.hdr, self.eval_batch_size = lr_scale, hdr, eval_batch_size
         self.recur_stepmul, self.recur_alpha_thres = recur_stepmul, recur_alpha_thres
         self.near_far = list(near_far)
-        self.skip_eps, self.t_cut, self.seed, self.mlp = ops.DEFAULT_SKIP_EPS, ops.DEFAULT_T_CUT, 20211200, "tf32"
+        self.skip_eps, self.t_cut, self.seed, self.mlp = ops.DEFAULT_SKIP_EPS, ops.DEFAULT_T_CUT, 20211200, "f16"
         self._scene, self._scene_key, self._bufs, self._calls = None, None, None, 0
 
     def get_device(self):

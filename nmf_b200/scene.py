@@ -158,13 +158,17 @@ class DeviceScene:
                 self._ptr(s, f"brdf_w{i}t", w.t().contiguous())
                 self._ptr(s, f"brdf_b{i}", b)
             assert tuple(self.keep["brdf_w0t"].shape) == (66, 64) and tuple(self.keep["brdf_w2t"].shape) == (64, 4)
-            # tensor-core operands (csrc/nmf_mlp_tc.cuh): W (64 out, K in) -> [K/4][64][4], K padded to 72, TF32-rounded
-            for i, kpad in ((0, 72), (1, 64)):
-                w = self.keep[f"brdf_w{i}t"].t()                                  # (64, K)
-                wp = torch.zeros(64, kpad, device=dev)
-                wp[:, :w.shape[1]] = w
-                self._ptr(s, f"brdf_w{i}u", round_tf32(wp).view(64, kpad // 4, 4).permute(1, 0, 2).contiguous())
-            s.mlp_mode = 0 if self.hp.get("mlp", "tf32") == "tf32" else 1
+            # tensor-core operands (csrc/nmf_mlp_tc.cuh): W (rows out, K in) -> fp16 [K/8][rows][8], K zero-padded to 80,
+            # bias in column 66 (it multiplies the constant-1 input); layer 3 padded from 4 to 16 output rows
+            for i, rows in ((0, 64), (1, 64), (2, 16)):
+                w = self.keep[f"brdf_w{i}t"].t()                                  # (out, K)
+                wp = torch.zeros(rows, 80, device=dev)
+                wp[:w.shape[0], :w.shape[1]] = w
+                wp[:w.shape[0], 66] = self.keep[f"brdf_b{i}"]
+                self._ptr(s, f"brdf_w{i}u", wp.half().view(rows, 10, 8).permute(1, 0, 2).contiguous())
+            if self.hp.get("mlp", "f16") not in ("f16", "fp32"):
+                raise _lib.NmfError("mlp must be 'f16' (tcgen05, fp16 operands / fp32 accumulate) or 'fp32' (SIMT)")
+            s.mlp_mode = 0 if self.hp.get("mlp", "f16") == "f16" else 1
             sob = g("model.brdf_sampler.angs")
             assert sob.shape[0] >= 400 and sob.shape[1] == 2
             self._ptr(s, "sobol", sob)

@@ -102,7 +102,7 @@ def test_ggx_and_brdf(case):
     assert (olp - lpdf).abs().median() < 1e-5
     feat = torch.randn(n, 24, generator=g) * 0.3
     ref = O.brdf_mlp(osc, feat, half_l, diff_l, r)
-    # default: tcgen05 kind::tf32 (10-bit mantissa operands, fp32 accumulate); mlp="fp32" is the SIMT fp32 variant
+    # default: tcgen05 kind::f16 (fp16 operands = 10-bit mantissa, fp32 accumulate); mlp="fp32" is the SIMT fp32 variant
     bw = ops.brdf_mlp(dsc, feat.cuda(), half_l.cuda(), diff_l.cuda(), r.cuda()).cpu()
     assert (bw - ref).abs().max() < 1e-3 and (bw - ref).abs().mean() < 1e-4, (bw - ref).abs().max()
     dsc32 = device_scene(fix, "cuda:0", mlp="fp32")
