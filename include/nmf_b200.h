@@ -72,7 +72,7 @@ typedef struct NmfScene {
   int ow, oh, od, opitch;
   int has_occ;
 
-  /* density factors.  dval: [h][w][16] plane values; dpack: [h][w][4 groups][val4,dx4,dy4] where dx/dy are the
+  /* density factors.  dval: [h][w][16] plane values; dpack: [h][w][val16 | dx16 | dy16] where dx/dy are the
    * smoothed-difference planes of modules/grid_sample_Cinf.py:218-242; lines: lval [n][16], lpack [n][4][val4,dy4] */
   const float* dval[3];
   const float* dpack[3];

@@ -84,34 +84,49 @@ NMF_HD nmf_f4 nmf_app_group(const NmfScene& s, const NmfTaps& t, int p, int g) {
   nmf_f4 o; o.x = pv.x * lv.x; o.y = pv.y * lv.y; o.z = pv.z * lv.z; o.w = pv.w * lv.w;
   return o;
 }
-// gradient of the density feature wrt normalised coordinates, restricted to channel group g and to the plane rows
-// y-tap `half` (0: row i0, 1: row i1) / the matching line tap: tensor_base.py:107-129 with the smoothed-difference
-// backward of grid_sample_Cinf.py:218-281.  Summing over g in 0..3 and half in 0..1 gives d(feature)/d(xn).
-NMF_HD void nmf_normal_group(const NmfScene& s, const NmfTaps& t, int g, int half, float* grad) {
+// x-taps of a bilinear lookup as a PAIR of adjacent texels (base, base + 1) with weights (wa, wb), so that the two
+// texels of a row are one contiguous span of memory.  Out-of-range taps keep weight 0 (zeros padding); at the right
+// border (i0 = size - 1, weight-0 i1) the pair slides to (size - 2, size - 1).
+struct NmfPair { int base; float wa, wb; };
+NMF_HD NmfPair nmf_pair_setup(const NmfLerp& l, int size) {
+  NmfPair q;
+  q.base = l.i0 < size - 2 ? l.i0 : size - 2;
+  q.wa = (l.i0 == q.base ? l.w0 : 0.f) + (l.i1 == q.base ? l.w1 : 0.f);
+  q.wb = (l.i0 == q.base + 1 ? l.w0 : 0.f) + (l.i1 == q.base + 1 ? l.w1 : 0.f);
+  return q;
+}
+// gradient of the density feature wrt normalised coordinates (tensor_base.py:107-129 with the smoothed-difference
+// backward of grid_sample_Cinf.py:218-281), the share of lane `l` of an 8-lane group; summing over l = 0..7 gives
+// d(feature)/d(xn).  dpack is [h][w][val16 | dx16 | dy16]: the two x-taps of a row are 96 contiguous floats that the
+// 8 lanes read as three 128-byte pieces (lane l takes bytes 16 l .. 16 l + 15 of a piece):
+//   piece 0 = tex0.val | tex0.dx     piece 1 = tex0.dy | tex1.val     piece 2 = tex1.dx | tex1.dy
+// so lane (g = l & 3, hi = l >> 2) sees channel group g of (val, dy, dx) [hi = 0] or (dx, val, dy) [hi = 1].
+NMF_HD void nmf_normal_lane(const NmfScene& s, const NmfTaps& t, int l, float* grad) {
+  const int g = l & 3;
+  const bool hi = l >= 4;
 #pragma unroll
   for (int p = 0; p < 3; ++p) {
     const int w = s.plane_w[p];
-    const NmfLerp& lx = t.px[p];
     const NmfLerp& ly = t.py[p];
     const NmfLerp& ll = t.pl[p];
-    int yi = half ? ly.i1 : ly.i0;
-    float wy = half ? ly.w1 : ly.w0;
-    const float* r = s.dpack[p] + ((size_t)yi * w) * 48 + 12 * g;
-    const float* ta = r + (size_t)lx.i0 * 48;
-    const float* tb = r + (size_t)lx.i1 * 48;
-    float wa = wy * lx.w0, wb = wy * lx.w1;
-    nmf_f4 val = nmf_f4_zero(), dx = nmf_f4_zero(), dy = nmf_f4_zero();
-    nmf_f4_fma(val, NMF_LD4(ta), wa); nmf_f4_fma(dx, NMF_LD4(ta + 4), wa); nmf_f4_fma(dy, NMF_LD4(ta + 8), wa);
-    nmf_f4_fma(val, NMF_LD4(tb), wb); nmf_f4_fma(dx, NMF_LD4(tb + 4), wb); nmf_f4_fma(dy, NMF_LD4(tb + 8), wb);
-    // full line value / derivative (both taps): cheap, and keeps the two halves symmetric
+    const NmfPair px = nmf_pair_setup(t.px[p], w);
+    // line value and smoothed derivative of channel group g (both taps)
     const float* l0 = s.lpack[p] + (size_t)ll.i0 * 32 + 8 * g;
     const float* l1 = s.lpack[p] + (size_t)ll.i1 * 32 + 8 * g;
     nmf_f4 lv = nmf_f4_zero(), ld = nmf_f4_zero();
     nmf_f4_fma(lv, NMF_LD4(l0), ll.w0); nmf_f4_fma(ld, NMF_LD4(l0 + 4), ll.w0);
     nmf_f4_fma(lv, NMF_LD4(l1), ll.w1); nmf_f4_fma(ld, NMF_LD4(l1 + 4), ll.w1);
-    grad[NMF_MAT0(p)] += nmf_f4_dot(lv, dx);
-    grad[NMF_MAT1(p)] += nmf_f4_dot(lv, dy);
-    grad[NMF_VEC(p)] += nmf_f4_dot(val, ld);
+    const float* r0 = s.dpack[p] + ((size_t)ly.i0 * w + px.base) * 48 + 4 * l;
+    const float* r1 = s.dpack[p] + ((size_t)ly.i1 * w + px.base) * 48 + 4 * l;
+    nmf_f4 a0 = nmf_f4_zero(), a1 = nmf_f4_zero(), a2 = nmf_f4_zero();
+    nmf_f4_fma(a0, NMF_LD4(r0), ly.w0); nmf_f4_fma(a1, NMF_LD4(r0 + 32), ly.w0); nmf_f4_fma(a2, NMF_LD4(r0 + 64), ly.w0);
+    nmf_f4_fma(a0, NMF_LD4(r1), ly.w1); nmf_f4_fma(a1, NMF_LD4(r1 + 32), ly.w1); nmf_f4_fma(a2, NMF_LD4(r1 + 64), ly.w1);
+    const float e0 = px.wa * nmf_f4_dot(a0, hi ? lv : ld);                 // tex0: dx [hi] or val
+    const float e1 = (hi ? px.wb : px.wa) * nmf_f4_dot(a1, hi ? ld : lv);  // tex1.val [hi] or tex0.dy
+    const float e2 = px.wb * nmf_f4_dot(a2, lv);                           // tex1: dy [hi] or dx
+    grad[NMF_VEC(p)] += hi ? e1 : e0;
+    grad[NMF_MAT0(p)] += hi ? e0 : e2;
+    grad[NMF_MAT1(p)] += hi ? e2 : e1;
   }
 }
 // n = normalize(-(g * invaabbSize))  (tensor_base.py:126-128)

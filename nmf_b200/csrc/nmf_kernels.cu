@@ -293,73 +293,148 @@ struct ShadeArgs {
   unsigned* error;
 };
 
+// Two phases per warp, 32 surviving samples at a time:
+//   gather  8 lanes per sample, 4 samples per round, 8 rounds: the 72 appearance coefficients (6 lanes x 16-byte taps)
+//           and the smoothed-gradient normal (three 128-byte pieces per plane row over the 8 lanes).  Every two rounds
+//           the basis contraction feat[8 x 24] = coef[8 x 72] * basis_t[72 x 24] (tensoRF.py:405) runs on the tensor
+//           cores as 3xTF32 (mma.sync m16n8k8: hi*hi + lo*hi + hi*lo, fp32 accumulate => fp32-level accuracy);
+//           features and normal are parked in shared memory
+//   shade   1 lane per sample: material heads, SH irradiance, Fresnel, keyed bounce count, debug-map atomics, the
+//           bounce-sample record -- nothing here is computed redundantly by the lanes of a group
+// The kernel is bound by L1 data-pipe wavefronts (profiles/), which is what this structure minimises: a scalar GEMV
+// re-reads both operands from shared memory for every 3 FMAs, the MMA fragments are read once per 8 samples.
+#define SHADE_COEF_LD 76       // floats per staged coefficient row: A-fragment reads (row g, col t) are conflict-free
+#define SHADE_FEAT_LD 27       // 24 features + normal per parked sample: lane-per-sample reads are conflict-free
+#define SHADE_SMEM_FLOATS (2 * 72 * 24 + 11 * 24 + 16 + 32 + 8 * 8 * SHADE_COEF_LD + 8 * 32 * SHADE_FEAT_LD)
+__device__ __forceinline__ uint32_t shade_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void shade_mma(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  // rows 8..15 of the A tile are not used (8 samples per batch): a1 = a3 = 0
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
 template <int LEVEL>
-__global__ void __launch_bounds__(256) k_shade(const NmfScene s, const ShadeArgs a) {
-  __shared__ float s_basis[72 * 24];
-  __shared__ float s_headw[11 * 24];
-  __shared__ float s_headb[11];
-  __shared__ float s_sh[27];
-  __shared__ float s_coef[32][73];
-  for (int i = threadIdx.x; i < 72 * 24; i += 256) s_basis[i] = s.basis_t[i];
+__global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeArgs a) {
+  extern __shared__ __align__(16) float shade_sm[];
+  uint32_t* s_bhi = (uint32_t*)shade_sm;                 // [72][24] TF32 high part of basis_t
+  uint32_t* s_blo = s_bhi + 72 * 24;                     // [72][24] TF32 low part
+  float* s_headw = (float*)(s_blo + 72 * 24);            // [11][24]
+  float* s_headb = s_headw + 11 * 24;                    // [11] (+5 pad)
+  float* s_sh = s_headb + 16;                            // [27] (+5 pad)
+  float* s_coef_all = s_sh + 32;                         // [8 warps][8 samples][SHADE_COEF_LD]
+  float* s_feat_all = s_coef_all + 8 * 8 * SHADE_COEF_LD;   // [8 warps][32 samples][SHADE_FEAT_LD]
+  for (int i = threadIdx.x; i < 72 * 24; i += 256) {
+    const float b = s.basis_t[i];
+    const uint32_t hi = shade_tf32(b);
+    s_bhi[i] = hi;
+    s_blo[i] = shade_tf32(b - __uint_as_float(hi));
+  }
   for (int i = threadIdx.x; i < 11 * 24; i += 256) s_headw[i] = s.head_w[i];
   if (threadIdx.x < 11) s_headb[threadIdx.x] = s.head_b[threadIdx.x];
   if (threadIdx.x < 27) s_sh[threadIdx.x] = s.sh_conv[threadIdx.x];
   __syncthreads();
   const int n = min(*a.n_surv, a.cap_surv);
-  const int sidx = threadIdx.x >> 3, l = threadIdx.x & 7;
-  for (int base = blockIdx.x * 32; base < n; base += gridDim.x * 32) {
-    const int si = base + sidx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 3, l = lane & 7;
+  float* s_coef = s_coef_all + warp * 8 * SHADE_COEF_LD;
+  float* s_feat = s_feat_all + warp * 32 * SHADE_FEAT_LD;
+  for (int wbase = (blockIdx.x * 8 + warp) * 32; wbase < n; wbase += gridDim.x * 256) {
+    // ---------------- gather phase ----------------
+#pragma unroll 1
+    for (int round = 0; round < 8; ++round) {
+      const int si = wbase + round * 4 + grp;
+      Surv sv; sv.ray = 0; sv.step = 0; sv.w = 0.f;
+      if (si < n) sv = a.surv[si];
+      const int ray = (int)sv.ray;
+      float o[3], d[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { o[i] = __ldg(a.rays + (size_t)ray * 6 + i); d[i] = __ldg(a.rays + (size_t)ray * 6 + 3 + i); }
+      float p[3], xn[3];
+      nmf_step_pos(o, d, nmf_step_z(a.tmin[ray], s.stepsize, (int)sv.step), p);
+      nmf_normalize_xyz(s, p, xn);
+      const NmfTaps t = nmf_vm_taps(s, xn);
+      // appearance coefficients: lanes 0..5 own 4 channels of each plane
+      const int row = (round & 1) * 4 + grp;
+      if (l < 6) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          const nmf_f4 c = nmf_app_group(s, t, pl, l);
+          *(float4*)&s_coef[row * SHADE_COEF_LD + pl * 24 + 4 * l] = c;
+        }
+      }
+      // smoothed-gradient normal, this lane's share
+      float grad[3] = {0.f, 0.f, 0.f};
+      nmf_normal_lane(s, t, l, grad);
+#pragma unroll
+      for (int off = 1; off < 8; off <<= 1) {
+        grad[0] += __shfl_xor_sync(FULL, grad[0], off);
+        grad[1] += __shfl_xor_sync(FULL, grad[1], off);
+        grad[2] += __shfl_xor_sync(FULL, grad[2], off);
+      }
+      if (l == 0) {
+        const nmf_v3 nrm = nmf_normal_from_grad(s, grad);
+        float* no = s_feat + (round * 4 + grp) * SHADE_FEAT_LD + 24;
+        no[0] = nrm.x; no[1] = nrm.y; no[2] = nrm.z;
+      }
+      __syncwarp();
+      if (round & 1) {
+        // basis contraction of the 8 staged samples: lane (g, tq) holds A(row g, cols tq, tq+4), B(rows tq, tq+4, col g)
+        const int g = lane >> 2, tq = lane & 3;
+        float c[3][4];
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+#pragma unroll 3
+        for (int ks = 0; ks < 9; ++ks) {
+          const float a0 = s_coef[g * SHADE_COEF_LD + 8 * ks + tq], a2 = s_coef[g * SHADE_COEF_LD + 8 * ks + tq + 4];
+          const uint32_t a0h = shade_tf32(a0), a2h = shade_tf32(a2);
+          const uint32_t a0l = shade_tf32(a0 - __uint_as_float(a0h)), a2l = shade_tf32(a2 - __uint_as_float(a2h));
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt) {
+            const int b0i = (8 * ks + tq) * 24 + 8 * nt + g, b1i = b0i + 4 * 24;
+            const uint32_t bh0 = s_bhi[b0i], bh1 = s_bhi[b1i], bl0 = s_blo[b0i], bl1 = s_blo[b1i];
+            shade_mma(c[nt], a0l, a2l, bh0, bh1);
+            shade_mma(c[nt], a0h, a2h, bl0, bl1);
+            shade_mma(c[nt], a0h, a2h, bh0, bh1);
+          }
+        }
+        float* fo = s_feat + ((round >> 1) * 8 + g) * SHADE_FEAT_LD + 2 * tq;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) { fo[8 * nt] = c[nt][0]; fo[8 * nt + 1] = c[nt][1]; }
+        __syncwarp();
+      }
+    }
+    // ---------------- shade phase: one lane per sample ----------------
+    const int si = wbase + lane;
     const bool active = si < n;
     Surv sv; sv.ray = 0; sv.step = 0; sv.w = 0.f;
     if (active) sv = a.surv[si];
     const int ray = (int)sv.ray, k = (int)sv.step;
     const float w = sv.w;
-    float o[3], d[3];
+    float o[3], d[3], p[3], xn[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) { o[i] = __ldg(a.rays + (size_t)ray * 6 + i); d[i] = __ldg(a.rays + (size_t)ray * 6 + 3 + i); }
-    const float tmin = a.tmin[ray];
-    float p[3], xn[3];
-    nmf_step_pos(o, d, nmf_step_z(tmin, s.stepsize, k), p);
+    nmf_step_pos(o, d, nmf_step_z(a.tmin[ray], s.stepsize, k), p);
     nmf_normalize_xyz(s, p, xn);
-    const NmfTaps t = nmf_vm_taps(s, xn);
-    // appearance coefficients: lanes 0..5 own 4 channels of each plane
-    if (l < 6) {
+    float f[24];
 #pragma unroll
-      for (int pl = 0; pl < 3; ++pl) {
-        const nmf_f4 c = nmf_app_group(s, t, pl, l);
-        float* q = &s_coef[sidx][pl * 24 + 4 * l];
-        q[0] = c.x; q[1] = c.y; q[2] = c.z; q[3] = c.w;
-      }
-    }
-    // smoothed-gradient normal: lane = (channel group, plane row)
-    float grad[3] = {0.f, 0.f, 0.f};
-    nmf_normal_group(s, t, l & 3, l >> 2, grad);
-#pragma unroll
-    for (int off = 1; off < 8; off <<= 1) {
-      grad[0] += __shfl_xor_sync(FULL, grad[0], off);
-      grad[1] += __shfl_xor_sync(FULL, grad[1], off);
-      grad[2] += __shfl_xor_sync(FULL, grad[2], off);
-    }
-    const nmf_v3 nrm = nmf_normal_from_grad(s, grad);
-    __syncwarp();
-    // basis GEMV (tensoRF.py:405): lane l owns features l, l+8, l+16
-    float f0 = 0.f, f1 = 0.f, f2 = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < 72; ++j) {
-      const float c = s_coef[sidx][j];
-      f0 += s_basis[j * 24 + l] * c;
-      f1 += s_basis[j * 24 + l + 8] * c;
-      f2 += s_basis[j * 24 + l + 16] * c;
-    }
-    __syncwarp();
-    // material heads (render_modules.py:553-560)
+    for (int i = 0; i < 24; ++i) f[i] = s_feat[lane * SHADE_FEAT_LD + i];
+    const nmf_v3 nrm = nmf_mk3(s_feat[lane * SHADE_FEAT_LD + 24], s_feat[lane * SHADE_FEAT_LD + 25], s_feat[lane * SHADE_FEAT_LD + 26]);
+    // material heads (render_modules.py:553-560); the tint head (rows 3..5) and the second roughness output (row 10)
+    // feed nothing on this path (fresnel mode, r2 = r1: microfacet.py:360)
     float lin[11];
 #pragma unroll
     for (int h = 0; h < 11; ++h) {
-      float v = s_headw[h * 24 + l] * f0 + s_headw[h * 24 + l + 8] * f1 + s_headw[h * 24 + l + 16] * f2;
-      v += __shfl_xor_sync(FULL, v, 1);
-      v += __shfl_xor_sync(FULL, v, 2);
-      v += __shfl_xor_sync(FULL, v, 4);
+      if ((h >= 3 && h < 6) || h == 10) { lin[h] = 0.f; continue; }
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const float4 wv = *(const float4*)&s_headw[h * 24 + 4 * q];
+        v += wv.x * f[4 * q]; v += wv.y * f[4 * q + 1]; v += wv.z * f[4 * q + 2]; v += wv.w * f[4 * q + 3];
+      }
       lin[h] = v + s_headb[h];
     }
     float albedo[3], f0v[3], diffuse[3], fresn[3];
@@ -380,16 +455,19 @@ __global__ void __launch_bounds__(256) k_shade(const NmfScene s, const ShadeArgs
       fresn[c] = nmf_fresnel(f0v[c], cost);
     }
     if (LEVEL == 0 && active) {
-      // debug / auxiliary maps (tensor_nerf.py:495-566, microfacet.py:639-647): 10 values over 8 lanes
+      // debug / auxiliary maps (tensor_nerf.py:495-566, microfacet.py:639-647)
       float* acc = a.accum + (size_t)ray * A_N;
-      if (l < 3) atomicAdd(acc + A_WN + l, w * (l == 0 ? nrm.x : l == 1 ? nrm.y : nrm.z));
-      else if (l < 6) atomicAdd(acc + A_DIFF + (l - 3), w * (1.0f - fresn[l - 3]) * diffuse[l - 3]);
-      else if (l == 6) atomicAdd(acc + A_ROUGH, w * rough);
-      if (l >= 5) { const int c = l - 5; atomicAdd(acc + A_ALB + c, w * albedo[c]); }
+      atomicAdd(acc + A_WN, w * nrm.x); atomicAdd(acc + A_WN + 1, w * nrm.y); atomicAdd(acc + A_WN + 2, w * nrm.z);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        atomicAdd(acc + A_DIFF + c, w * (1.0f - fresn[c]) * diffuse[c]);
+        atomicAdd(acc + A_ALB + c, w * albedo[c]);
+      }
+      atomicAdd(acc + A_ROUGH, w * rough);
     }
     // bounce count (pt_selectors.py:20-40)
     const int chunk = ray / a.group;
-    const uint64_t rkey = LEVEL == 0 ? nmf_mix64(a.seed, a.ray_id0 + (uint64_t)ray) : a.keys[ray];
+    const uint64_t rkey = LEVEL == 0 ? nmf_mix64(a.seed, a.ray_id0 + (uint64_t)ray) : (active ? a.keys[ray] : 0ull);
     const uint64_t skey = nmf_mix64(rkey, (uint64_t)k);
     const float U = nmf_uniform(skey, NMF_STREAM_BOUNCE);
     float kf;
@@ -402,32 +480,74 @@ __global__ void __launch_bounds__(256) k_shade(const NmfScene s, const ShadeArgs
       kf = N > 0 ? floorf(wj / wsum * (float)N + 1.0f) : floorf(wj / wsum * (float)s.max_brdf_rays1 + 0.5f);
     }
     const int count = active ? (int)nmf_clampf(kf, 0.f, (float)NMF_MAX_BOUNCE) : 0;
+    // allocate the bounce-sample slot (one atomic per warp) and the sample's range in its chunk's bounce-ray region
+    // (one atomic per warp when all bouncing samples of the warp belong to one chunk, the common case)
+    const unsigned bm = __ballot_sync(FULL, count > 0);
     int slot = -1, roff = 0;
-    if (count > 0 && l == 0) {
-      slot = atomicAdd(a.n_bs, 1);
-      roff = atomicAdd(a.ray_count + chunk, count);
-      if (slot >= a.cap_bs) { atomicOr(a.error, NMF_DEV_E_BSAMPLES); slot = -1; }
-      else if (roff + count > a.cap_rays) { atomicOr(a.error, NMF_DEV_E_BRAYS); slot = -1; }
+    if (bm) {
+      const int leader = __ffs(bm) - 1;
+      const unsigned lt = (1u << lane) - 1u;
+      int sbase = 0;
+      if (lane == leader) sbase = atomicAdd(a.n_bs, __popc(bm));
+      sbase = __shfl_sync(FULL, sbase, leader);
+      const int chunk0 = __shfl_sync(FULL, chunk, leader);
+      const bool same = __all_sync(FULL, count == 0 || chunk == chunk0);
+      if (same) {
+        int incl = count;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int v = __shfl_up_sync(FULL, incl, off);
+          if (lane >= off) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        int rbase = 0;
+        if (lane == leader) rbase = atomicAdd(a.ray_count + chunk0, total);
+        rbase = __shfl_sync(FULL, rbase, leader);
+        roff = rbase + incl - count;
+      } else if (count > 0) {
+        roff = atomicAdd(a.ray_count + chunk, count);
+      }
+      if (count > 0) {
+        slot = sbase + __popc(bm & lt);
+        if (slot >= a.cap_bs) { atomicOr(a.error, NMF_DEV_E_BSAMPLES); slot = -1; }
+        else if (roff + count > a.cap_rays) { atomicOr(a.error, NMF_DEV_E_BRAYS); slot = -1; }
+      }
     }
-    slot = __shfl_sync(FULL, slot, (threadIdx.x & 31) & ~7);
-    roff = __shfl_sync(FULL, roff, (threadIdx.x & 31) & ~7);
     if (slot >= 0) {
       BSample* b = a.bs + slot;
       const float sgn = vn > 0.f ? 1.f : (vn < 0.f ? -1.f : 0.f);        // microfacet.py:354-356
-      if (l == 0) { b->pos[0] = p[0]; b->pos[1] = p[1]; b->pos[2] = p[2]; b->w = w; }
-      if (l == 1) { b->V[0] = V.x; b->V[1] = V.y; b->V[2] = V.z; b->rough = rough; }
-      if (l == 2) { b->N[0] = nrm.x * sgn; b->N[1] = nrm.y * sgn; b->N[2] = nrm.z * sgn; b->count = count; }
-      if (l == 3) { b->f0[0] = f0v[0]; b->f0[1] = f0v[1]; b->f0[2] = f0v[2]; b->ray = (uint32_t)ray; }
-      if (l == 4) { b->diffuse[0] = diffuse[0]; b->diffuse[1] = diffuse[1]; b->diffuse[2] = diffuse[2]; b->roff = (uint32_t)roff; }
-      if (l == 5) { b->fresn[0] = fresn[0]; b->fresn[1] = fresn[1]; b->fresn[2] = fresn[2]; b->flags = xn[2] < 0.f ? 1u : 0u; }
-      if (l == 6) { b->key = skey; b->chunk = (uint32_t)chunk; b->pad = 0; }
-      // appearance feature + noise (microfacet.py:297, keyed Box-Muller)
-      b->feat[l] = f0 + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + l, NMF_STREAM_NOISE_B + l);
-      b->feat[l + 8] = f1 + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + l + 8, NMF_STREAM_NOISE_B + l + 8);
-      b->feat[l + 16] = f2 + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + l + 16, NMF_STREAM_NOISE_B + l + 16);
-      uint32_t* ow = a.owner + (size_t)chunk * a.cap_rays + roff;
-      for (int j = l; j < count; j += 8) ow[j] = (uint32_t)slot;
+      float4* q = (float4*)b;
+      q[0] = make_float4(p[0], p[1], p[2], w);
+      q[1] = make_float4(V.x, V.y, V.z, rough);
+      q[2] = make_float4(nrm.x * sgn, nrm.y * sgn, nrm.z * sgn, __int_as_float(count));
+      q[3] = make_float4(f0v[0], f0v[1], f0v[2], __uint_as_float((uint32_t)ray));
+      q[4] = make_float4(diffuse[0], diffuse[1], diffuse[2], __uint_as_float((uint32_t)roff));
+      q[5] = make_float4(fresn[0], fresn[1], fresn[2], __uint_as_float(xn[2] < 0.f ? 1u : 0u));
+      b->key = skey; b->chunk = (uint32_t)chunk; b->pad = 0;
+      // appearance feature + noise (microfacet.py:297, keyed Box-Muller); a rolled loop over the parked features keeps
+      // the 24 inlined Box-Muller bodies out of the instruction stream (the kernel is instruction-cache sensitive)
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {
+        const float* fq = s_feat + lane * SHADE_FEAT_LD + 4 * i;
+        float4 v;
+        v.x = fq[0] + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + 4 * i, NMF_STREAM_NOISE_B + 4 * i);
+        v.y = fq[1] + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + 4 * i + 1, NMF_STREAM_NOISE_B + 4 * i + 1);
+        v.z = fq[2] + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + 4 * i + 2, NMF_STREAM_NOISE_B + 4 * i + 2);
+        v.w = fq[3] + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + 4 * i + 3, NMF_STREAM_NOISE_B + 4 * i + 3);
+        *(float4*)(b->feat + 4 * i) = v;
+      }
     }
+    // ray -> bounce-sample map of the allocated ranges, written by the whole warp
+    unsigned todo = __ballot_sync(FULL, slot >= 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int c_cnt = __shfl_sync(FULL, count, src), c_slot = __shfl_sync(FULL, slot, src);
+      const int c_roff = __shfl_sync(FULL, roff, src), c_chunk = __shfl_sync(FULL, chunk, src);
+      uint32_t* ow = a.owner + (size_t)c_chunk * a.cap_rays + c_roff;
+      for (int j = lane; j < c_cnt; j += 32) ow[j] = (uint32_t)c_slot;
+    }
+    __syncwarp();
   }
 }
 
@@ -1074,25 +1194,27 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
   prof_mark(1, stream);
 
   if (s.model == 0) {
-    ShadeArgs h0 = {};
-    h0.rays = rays; h0.tmin = w.tmin0; h0.seed = rp->seed; h0.ray_id0 = rp->ray_id0; h0.group = rp->chunk;
-    h0.surv = w.surv0; h0.n_surv = w.n_surv; h0.cap_surv = w.cap_surv0; h0.accum = w.accum0;
-    h0.bs = w.bs0; h0.n_bs = w.n_bs; h0.cap_bs = w.cap_bs0; h0.ray_count = w.ray_count0; h0.cap_rays = w.cap_rays0;
-    h0.owner = w.owner0; h0.error = w.error;
-    k_shade<0><<<sm_count() * 6, 256, 0, stream>>>(s, h0);
-    CKL();
-    prof_mark(2, stream);
-
     const bool tcm = s.mlp_mode == 0;
     const size_t mlp_smem = tcm ? (size_t)TC_SMEM_BYTES : MLP_SMEM_FLOATS * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
+      CK(cudaFuncSetAttribute(k_shade<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SHADE_SMEM_FLOATS * sizeof(float))));
+      CK(cudaFuncSetAttribute(k_shade<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SHADE_SMEM_FLOATS * sizeof(float))));
       CK(cudaFuncSetAttribute(k_bounce<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MLP_SMEM_FLOATS * sizeof(float))));
       CK(cudaFuncSetAttribute(k_bounce<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MLP_SMEM_FLOATS * sizeof(float))));
       CK(cudaFuncSetAttribute(k_bounce<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
       CK(cudaFuncSetAttribute(k_bounce<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
       attr_done = true;
     }
+    ShadeArgs h0 = {};
+    h0.rays = rays; h0.tmin = w.tmin0; h0.seed = rp->seed; h0.ray_id0 = rp->ray_id0; h0.group = rp->chunk;
+    h0.surv = w.surv0; h0.n_surv = w.n_surv; h0.cap_surv = w.cap_surv0; h0.accum = w.accum0;
+    h0.bs = w.bs0; h0.n_bs = w.n_bs; h0.cap_bs = w.cap_bs0; h0.ray_count = w.ray_count0; h0.cap_rays = w.cap_rays0;
+    h0.owner = w.owner0; h0.error = w.error;
+    k_shade<0><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h0);
+    CKL();
+    prof_mark(2, stream);
+
     // persistent grid over the flat tile list: 5 CTAs per SM with the fp16 operand tiles, 3 with the fp32 SIMT staging
     const int gb = sm_count() * (tcm ? 5 : 3);
     k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count0, w.cap_rays0, nc, w.tile_start0);
@@ -1122,7 +1244,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
       h1.surv = w.surv1; h1.n_surv = w.n_surv + 1; h1.cap_surv = w.cap_surv1; h1.accum = nullptr;
       h1.bs = w.bs1; h1.n_bs = w.n_bs + 1; h1.cap_bs = w.cap_bs1; h1.ray_count = w.ray_count1; h1.cap_rays = w.cap_rays1;
       h1.owner = w.owner1; h1.n_samples = w.n_samples1; h1.wsum = w.wsum1; h1.error = w.error;
-      k_shade<1><<<sm_count() * 6, 256, 0, stream>>>(s, h1);
+      k_shade<1><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h1);
       CKL();
       prof_mark(6, stream);
       k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count1, w.cap_rays1, nc, w.tile_start1);
@@ -1298,7 +1420,7 @@ __global__ void k_vm_normals(const NmfScene s, const float* xyz, int n, int stri
   nmf_normalize_xyz(s, xyz + (size_t)(active ? i : 0) * stride, xn);
   const NmfTaps tp = nmf_vm_taps(s, xn);
   float grad[3] = {0.f, 0.f, 0.f};
-  nmf_normal_group(s, tp, l & 3, l >> 2, grad);
+  nmf_normal_lane(s, tp, l, grad);
   for (int off = 1; off < 8; off <<= 1) {
     grad[0] += __shfl_xor_sync(FULL, grad[0], off);
     grad[1] += __shfl_xor_sync(FULL, grad[1], off);

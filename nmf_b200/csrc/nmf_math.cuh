@@ -51,7 +51,11 @@ NMF_HD float nmf_uniform(uint64_t key, uint32_t stream) {
 NMF_HD float nmf_normal(uint64_t key, uint32_t sa, uint32_t sb) {
   float u1 = ((float)(uint32_t)(nmf_mix64(key, sa) >> 40) + 1.0f) * 5.9604644775390625e-8f;
   float u2 = nmf_uniform(key, sb);
+#ifdef __CUDA_ARCH__
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);   // cos(2 pi u2) without cosf's range-reduction slow path
+#else
   return sqrtf(-2.0f * logf(u1)) * cosf(6.2831855f * u2);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -284,47 +288,57 @@ NMF_HD NmfEnvBox nmf_env_box(nmf_v3 u, float sa, int h, int w, float mipbias) {
   bx.cy = -theta / 3.1415927f * 2.0f;
   return bx;
 }
+// One axis-aligned box (x0,y0)-(x1,y1): integral_equirect.py:18-39   (tr + bl - tl - br) / size
 template <class Tap>
-NMF_HD void nmf_env_box1(Tap& tap, float blx, float bly, float brx, float bry, float tlx, float tly, float trx, float try_,
-                         float inv_size, float* out) {
-  // integral_equirect.py:18-39   (tr + bl - tl - br) / size
+NMF_HD void nmf_env_box1(Tap& tap, float x0, float y0, float x1, float y1, float inv_size, float* out) {
   float acc[3] = {0.f, 0.f, 0.f};
-  tap(trx, try_, 1.0f, acc);
-  tap(blx, bly, 1.0f, acc);
-  tap(tlx, tly, -1.0f, acc);
-  tap(brx, bry, -1.0f, acc);
+  tap(x1, y1, 1.0f, acc);
+  tap(x0, y0, 1.0f, acc);
+  tap(x0, y1, -1.0f, acc);
+  tap(x1, y0, -1.0f, acc);
   out[0] += acc[0] * inv_size;
   out[1] += acc[1] * inv_size;
   out[2] += acc[2] * inv_size;
 }
-template <class Tap>
-NMF_HD void nmf_env_box_lr(Tap& tap, float blx, float bly, float brx, float bry, float tlx, float tly, float trx, float try_,
-                           float inv_size, float* out) {
-  // integral_equirect.py:42-93  left/right wrap-around
-  nmf_env_box1(tap, blx, bly, brx, bry, tlx, tly, trx, try_, inv_size, out);
-  if (trx > 1.0f) nmf_env_box1(tap, -1.0f, bly, brx - 2.0f, bry, -1.0f, tly, trx - 2.0f, try_, inv_size, out);
-  if (blx < -1.0f) nmf_env_box1(tap, blx + 2.0f, bly, 1.0f, bry, tlx + 2.0f, tly, 1.0f, try_, inv_size, out);
-}
+// The box, its pole overhangs (integral_equirect.py:96-173: mirrored across the pole and shifted by half a turn) and
+// the left/right wrap-around pieces of each (:42-93): up to 9 boxes, summed in the reference's order.  Written as
+// rolled loops around ONE box evaluation: most lookups are a single box, and nine inlined copies of the 16-tap body
+// cost more in instruction fetch than the loop costs in control flow.
 template <class Tap>
 NMF_HD void nmf_env_integrate(Tap& tap, const NmfEnvBox& bx, float* out) {
-  // integral_equirect.py:96-173  pole overhang: mirrored box shifted by half a turn
-  float hx = bx.sw / 2.0f, hy = bx.sh / 2.0f;
-  float blx = bx.cx - hx, bly = bx.cy - hy;
-  float trx = bx.cx + hx, try_ = bx.cy + hy;
-  float brx = bx.cx + hx, bry = bx.cy - hy;
-  float tlx = bx.cx - hx, tly = bx.cy + hy;
-  float inv_size = 1.0f / bx.size;
+  const float hx = bx.sw / 2.0f, hy = bx.sh / 2.0f;
+  const float bx0 = bx.cx - hx, by0 = bx.cy - hy, bx1 = bx.cx + hx, by1 = bx.cy + hy;
+  const float inv_size = 1.0f / bx.size;
+  const float rot = bx0 > 0.0f ? -1.0f : 1.0f;
   out[0] = out[1] = out[2] = 0.0f;
-  nmf_env_box_lr(tap, blx, bly, brx, bry, tlx, tly, trx, try_, inv_size, out);
-  if (tly > 1.0f) {
-    float rot = tlx > 0.0f ? -1.0f : 1.0f;
-    float over = nmf_clampf(tly - 1.0f, 0.0f, 0.5f);
-    nmf_env_box_lr(tap, blx + rot, 1.0f - over, brx + rot, 1.0f - over, tlx + rot, 1.0f, trx + rot, 1.0f, inv_size, out);
-  }
-  if (bly < -1.0f) {
-    float rot = tlx > 0.0f ? -1.0f : 1.0f;
-    float over = nmf_clampf(-1.0f - bly, 0.0f, 0.5f);
-    nmf_env_box_lr(tap, blx + rot, -1.0f, brx + rot, -1.0f, tlx + rot, -1.0f + over, trx + rot, -1.0f + over, inv_size, out);
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int part = 0; part < 3; ++part) {
+    float x0 = bx0, x1 = bx1, y0 = by0, y1 = by1;
+    if (part == 1) {
+      if (!(by1 > 1.0f)) continue;
+      const float over = nmf_clampf(by1 - 1.0f, 0.0f, 0.5f);
+      x0 = bx0 + rot; x1 = bx1 + rot; y0 = 1.0f - over; y1 = 1.0f;
+    } else if (part == 2) {
+      if (!(by0 < -1.0f)) continue;
+      const float over = nmf_clampf(-1.0f - by0, 0.0f, 0.5f);
+      x0 = bx0 + rot; x1 = bx1 + rot; y0 = -1.0f; y1 = -1.0f + over;
+    }
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (int wrap = 0; wrap < 3; ++wrap) {
+      float u0 = x0, u1 = x1;
+      if (wrap == 1) {
+        if (!(x1 > 1.0f)) continue;
+        u0 = -1.0f; u1 = x1 - 2.0f;
+      } else if (wrap == 2) {
+        if (!(x0 < -1.0f)) continue;
+        u0 = x0 + 2.0f; u1 = 1.0f;
+      }
+      nmf_env_box1(tap, u0, y0, u1, y1, inv_size, out);
+    }
   }
 }
 // bilinear tap of the channel-last SAT ([h][w][4]) at clip(p, -1, 1), align_corners=True

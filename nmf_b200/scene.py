@@ -128,8 +128,7 @@ class DeviceScene:
             s.plane_w[p], s.plane_h[p], s.line_n[p] = W, H, N
             dval = dp[0].permute(1, 2, 0).contiguous()                                   # (H,W,16)
             pdx, pdy = conv(dp, kx)[0].permute(1, 2, 0), conv(dp, ky)[0].permute(1, 2, 0)
-            dpack = torch.stack([dval.view(H, W, 4, 4), pdx.reshape(H, W, 4, 4), pdy.reshape(H, W, 4, 4)], dim=3)
-            dpack = dpack.reshape(H, W, 4, 12).contiguous()                              # [val4, dx4, dy4] per group
+            dpack = torch.cat([dval, pdx, pdy], dim=2).contiguous()                      # (H,W,48): [val16 | dx16 | dy16]
             lval = dl[0, :, :, 0].permute(1, 0).contiguous()                             # (N,16)
             ldy = conv(dl, ky)[0, :, :, 0].permute(1, 0)
             lpack = torch.stack([lval.view(N, 4, 4), ldy.reshape(N, 4, 4)], dim=2).reshape(N, 4, 8).contiguous()

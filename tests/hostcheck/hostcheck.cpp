@@ -75,8 +75,7 @@ void hc_vm_normals(const NmfScene* s, const float* xyz, int n, int stride, float
     nmf_normalize_xyz(*s, xyz + (size_t)i * stride, xn);
     NmfTaps t = nmf_vm_taps(*s, xn);
     float grad[3] = {0.f, 0.f, 0.f};
-    for (int g = 0; g < 4; ++g)
-      for (int h = 0; h < 2; ++h) nmf_normal_group(*s, t, g, h, grad);
+    for (int l = 0; l < 8; ++l) nmf_normal_lane(*s, t, l, grad);
     nmf_v3 nn = nmf_normal_from_grad(*s, grad);
     out[3 * i] = nn.x; out[3 * i + 1] = nn.y; out[3 * i + 2] = nn.z;
   }
