@@ -168,7 +168,7 @@ int nmf_abi_version(void);
 
 /* Optional phase timing for bench.py / profiling: when enabled, nmf_render_rays records a CUDA event on the caller's
  * stream after each phase; nmf_profile_read (after the stream is synchronised) returns the elapsed milliseconds of
- * the NMF_N_PHASES phases of the LAST call: march0, shade0, bounce0, select, march1, shade1, bounce1, reduce1,
+ * the NMF_N_PHASES phases of the LAST call: march0, shade0, bounce0, select, march1, shade1, bounce1, finish1,
  * incoming0, reduce0, finish. */
 #define NMF_N_PHASES 11
 int nmf_profile_enable(int on);

@@ -8,9 +8,9 @@
 //                 material heads, SH irradiance, bounce count, debug-map accumulation, bounce-sample records
 //   k_bounce<0>   thread per bounce ray: Sobol + GGX VNDF sample, ISH encodings, BRDF MLP, retrace score
 //   k_select      CTA per chunk: radix-select of the top max_retrace scores -> secondary rays
-//   k_march<1> .. k_bounce<1> (environment lookup fused) .. k_reduce<1>, k_finish1: the retraced rays
-//   k_incoming    per primary bounce ray: retraced radiance or environment lookup, Fresnel mix
-//   k_reduce<0>   per bounce sample: mean over its rays, composite into the pixel
+//   k_march<1> .. k_bounce<1> (environment lookup + per-sample mean fused), k_finish1: the retraced rays
+//   k_incoming    per primary bounce ray: retraced radiance or environment lookup, Fresnel mix, per-sample sums
+//   k_reduce0     per bounce sample: mean over its rays, composite into the pixel
 //   k_finish0     per ray: tonemap, background, auxiliary maps
 #include <cuda_runtime.h>
 
@@ -35,13 +35,12 @@ struct __align__(16) BSample {
   float fresn[3]; uint32_t flags;
   uint64_t key; uint32_t chunk; uint32_t pad;
   float feat[24];
+  float rgbsum[4];              // level 0: sum over the sample's bounce rays of their combined radiance (k_incoming)
 };
 
-struct __align__(16) BRay {
+struct __align__(16) BRay {     // level-0 bounce ray (level-1 rays are reduced inside k_bounce<1> and never stored)
   float L[3]; float mip;
-  float bw[3]; float score;
-  float comb[3]; int slot;
-  float inc[3]; uint32_t owner;
+  float bw[3]; int slot;        // slot: index of the secondary ray that re-traces it, -1 = environment
 };
 
 // per-ray accumulators of level 0 (floats)
@@ -66,10 +65,10 @@ struct WS {
   char* counters_base;
   // level 0
   float* tmin0; float* acc0; float* depth0; int* termk0; int* nvalid0; float* accum0;   // accum0 [n_rays][A_N]
-  Surv* surv0; BSample* bs0; BRay* brays0; uint32_t* owner0;
+  Surv* surv0; BSample* bs0; BRay* brays0; uint32_t* owner0; float2* scu0;   // scu0: (retrace score, tie-break U) per ray
   // level 1
   float* rays1; float* mip1; uint64_t* key1; float* tmin1; float* acc1; int* nvalid1; float* accum1; float* rgb1;
-  Surv* surv1; BSample* bs1; BRay* brays1; uint32_t* owner1;
+  Surv* surv1; BSample* bs1; uint32_t* owner1;
   int n_chunks, n_rays1;
   int cap_surv0, cap_bs0, cap_rays0;   // cap_rays0: per chunk
   int cap_surv1, cap_bs1, cap_rays1;   // cap_rays1: per chunk
@@ -118,6 +117,7 @@ static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base) {
     w.bs0 = (BSample*)take((size_t)w.cap_bs0 * sizeof(BSample));
     w.brays0 = (BRay*)take((size_t)nc * w.cap_rays0 * sizeof(BRay));
     w.owner0 = (uint32_t*)take((size_t)nc * w.cap_rays0 * 4);
+    w.scu0 = (float2*)take((size_t)nc * w.cap_rays0 * sizeof(float2));
     w.rays1 = (float*)take((size_t)w.n_rays1 * 6 * 4);
     w.mip1 = (float*)take((size_t)w.n_rays1 * 4);
     w.key1 = (uint64_t*)take((size_t)w.n_rays1 * 8);
@@ -127,7 +127,6 @@ static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base) {
     w.rgb1 = (float*)take((size_t)w.n_rays1 * 4 * 4);
     w.surv1 = (Surv*)take((size_t)w.cap_surv1 * sizeof(Surv));
     w.bs1 = (BSample*)take((size_t)w.cap_bs1 * sizeof(BSample));
-    w.brays1 = (BRay*)take((size_t)nc * w.cap_rays1 * sizeof(BRay));
     w.owner1 = (uint32_t*)take((size_t)nc * w.cap_rays1 * 4);
   }
   w.total = off;
@@ -524,6 +523,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       q[4] = make_float4(diffuse[0], diffuse[1], diffuse[2], __uint_as_float((uint32_t)roff));
       q[5] = make_float4(fresn[0], fresn[1], fresn[2], __uint_as_float(xn[2] < 0.f ? 1u : 0u));
       b->key = skey; b->chunk = (uint32_t)chunk; b->pad = 0;
+      if (LEVEL == 0) *(float4*)b->rgbsum = make_float4(0.f, 0.f, 0.f, 0.f);
       // appearance feature + noise (microfacet.py:297, keyed Box-Muller); a rolled loop over the parked features keeps
       // the 24 inlined Box-Muller bodies out of the instruction stream (the kernel is instruction-cache sensitive)
 #pragma unroll 1
@@ -626,9 +626,25 @@ __device__ __forceinline__ void mlp_simt(const float* sm, float* xcol, const flo
 // ================================================================================================
 // k_bounce: brdf_samplers/base.py:11-20, ggx.py:61-268, models/microfacet.py:367-472 (+ :561-613 at level 1)
 // ================================================================================================
+// Sum of v over the run of lanes that share `key` (runs are contiguous: bounce rays of one sample are consecutive);
+// the first lane of each run ends up with the run's total.
+__device__ __forceinline__ void seg_reduce3(float (&v)[3], uint32_t key, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t ok = __shfl_down_sync(FULL, key, off);
+    const float a0 = __shfl_down_sync(FULL, v[0], off), a1 = __shfl_down_sync(FULL, v[1], off), a2 = __shfl_down_sync(FULL, v[2], off);
+    if (lane + off < 32 && ok == key) { v[0] += a0; v[1] += a1; v[2] += a2; }
+  }
+}
+__device__ __forceinline__ bool seg_head(uint32_t key, int lane) {
+  const uint32_t prev = __shfl_up_sync(FULL, key, 1);
+  return lane == 0 || prev != key;
+}
+
 struct BounceArgs {
   const BSample* bs; BRay* brays; const uint32_t* owner; const int* ray_count; int cap_rays;
-  float* score_sum;
+  float* score_sum; float2* scu;     // level 0: retrace scores
+  float* accum1;                     // level 1: per retraced ray rgb accumulators [n_rays1][4]
   const int* tile_start;    // [n_chunks + 1] exclusive prefix of the chunks' 128-ray tile counts (k_tile_prefix)
   int n_chunks;
 };
@@ -681,7 +697,6 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
     const int n = min(a.ray_count[chunk], a.cap_rays);
     BRay* region = a.brays + (size_t)chunk * a.cap_rays;
     const uint32_t* owner = a.owner + (size_t)chunk * a.cap_rays;
-    float block_score = 0.f;
     const int r = (tile - __ldg(a.tile_start + chunk)) * MLP_THREADS + threadIdx.x;
     const bool active = r < n;
     const uint32_t slot = active ? owner[r] : 0u;
@@ -705,47 +720,47 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
     float bw[3];
     if (TC) tc_mlp_forward(tc, x, s.brdf_bias, bw);      // all 128 threads: the tile is one tensor-core GEMM
     else if (active) mlp_simt(sm, xcol, x, s.brdf_bias, bw);
-    if (active) {
     const float mip = -logf((float)count) - g.logpdf;                    // microfacet.py:445-448
-    BRay* o = region + r;
-    float4 st0, st1;
-    st0.x = g.L.x; st0.y = g.L.y; st0.z = g.L.z; st0.w = mip;
-    st1.x = bw[0]; st1.y = bw[1]; st1.z = bw[2];
     if (LEVEL == 0) {
-      // contribution estimate for the retrace selection (microfacet.py:480-504)
-      const float pdf = expf(g.logpdf);
-      const float per_ray = fmaxf(bw[0], fmaxf(bw[1], bw[2])) * (nmf_dot(V, N) > 0.f ? 1.f : 0.f) * pdf;
-      const float sc = per_ray * (w / ((float)count + 1e-8f));
-      st1.w = sc;
-      block_score = sc;
-      *(float4*)o->L = st0;
-      *(float4*)o->bw = st1;
-      o->slot = -1;
-      o->owner = slot;
-    } else {
-      // no further retrace at this depth: every bounce ray reads the environment (microfacet.py:561)
-      float inc[3];
-      nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, g.L, mip, inc);
-      const float ch = fabsf(nmf_dot(V, g.H));
-      const float4 q3 = *(const float4*)b->f0, q4 = *(const float4*)b->diffuse;
-      const float F0 = nmf_fresnel(q3.x, ch), F1 = nmf_fresnel(q3.y, ch), F2 = nmf_fresnel(q3.z, ch);
-      st1.w = 0.f;
-      float4 st2, st3;
-      st2.x = F0 * inc[0] * bw[0] + (1.f - F0) * q4.x;                   // microfacet.py:585-600
-      st2.y = F1 * inc[1] * bw[1] + (1.f - F1) * q4.y;
-      st2.z = F2 * inc[2] * bw[2] + (1.f - F2) * q4.z;
-      st2.w = __int_as_float(-1);
-      st3.x = inc[0]; st3.y = inc[1]; st3.z = inc[2]; st3.w = __uint_as_float(slot);
-      *(float4*)o->L = st0;
-      *(float4*)o->bw = st1;
-      *(float4*)o->comb = st2;
-      *(float4*)o->inc = st3;
-    }
-    }
-    if (LEVEL == 0) {
+      float sc = 0.f;
+      if (active) {
+        // contribution estimate for the retrace selection (microfacet.py:480-504) and its tie-break uniform (:506)
+        const float pdf = expf(g.logpdf);
+        const float per_ray = fmaxf(bw[0], fmaxf(bw[1], bw[2])) * (nmf_dot(V, N) > 0.f ? 1.f : 0.f) * pdf;
+        sc = per_ray * (w / ((float)count + 1e-8f));
+        BRay* o = region + r;
+        *(float4*)o->L = make_float4(g.L.x, g.L.y, g.L.z, mip);
+        *(float4*)o->bw = make_float4(bw[0], bw[1], bw[2], __int_as_float(-1));
+        const uint64_t rkey = nmf_mix64(skey, (uint64_t)j + NMF_STREAM_RAY0);
+        a.scu[(size_t)chunk * a.cap_rays + r] = make_float2(sc, nmf_uniform(rkey, NMF_STREAM_TIE));
+      }
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) block_score += __shfl_xor_sync(FULL, block_score, off);
-      if ((threadIdx.x & 31) == 0 && block_score != 0.f) atomicAdd(a.score_sum + chunk, block_score);
+      for (int off = 16; off > 0; off >>= 1) sc += __shfl_xor_sync(FULL, sc, off);
+      if ((threadIdx.x & 31) == 0 && sc != 0.f) atomicAdd(a.score_sum + chunk, sc);
+    } else {
+      // no further retrace at this depth: every bounce ray reads the environment (microfacet.py:561); the mean over
+      // the rays of a sample (microfacet.py:565-613) is a segmented warp reduction, weighted into the retraced ray's
+      // pixel (tensor_nerf.py:448-452) -- level-1 bounce rays never touch HBM
+      float comb[3] = {0.f, 0.f, 0.f};
+      if (active) {
+        float inc[3];
+        nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, g.L, mip, inc);
+        const float ch = fabsf(nmf_dot(V, g.H));
+        const float4 q3 = *(const float4*)b->f0, q4 = *(const float4*)b->diffuse;
+        const float F0 = nmf_fresnel(q3.x, ch), F1 = nmf_fresnel(q3.y, ch), F2 = nmf_fresnel(q3.z, ch);
+        comb[0] = F0 * inc[0] * bw[0] + (1.f - F0) * q4.x;                 // microfacet.py:585-600
+        comb[1] = F1 * inc[1] * bw[1] + (1.f - F1) * q4.y;
+        comb[2] = F2 * inc[2] * bw[2] + (1.f - F2) * q4.z;
+      }
+      const int lane = threadIdx.x & 31;
+      const uint32_t key = active ? slot : 0xFFFFFFFFu;
+      seg_reduce3(comb, key, lane);
+      const bool head = seg_head(key, lane);     // every lane takes part in the shuffle
+      if (active && head) {
+        const float sw = w / (float)count;
+        float* acc = a.accum1 + (size_t)b->ray * 4;
+        atomicAdd(acc, sw * comb[0]); atomicAdd(acc + 1, sw * comb[1]); atomicAdd(acc + 2, sw * comb[2]);
+      }
     }
   }
   if (TC) tc_mlp_free(tc);
@@ -756,8 +771,8 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
 // (normalised contribution + U) become secondary rays.  Three-pass radix select on the float bits.
 // ================================================================================================
 struct SelectArgs {
-  const BSample* bs; BRay* brays; const int* ray_count; int cap_rays; const float* score_sum;
-  int max_retrace; int* n_sec;
+  const BSample* bs; BRay* brays; const uint32_t* owner; float2* scu; const int* ray_count; int cap_rays;
+  const float* score_sum; int max_retrace; int* n_sec;
   float* rays1; float* mip1; uint64_t* key1;
 };
 
@@ -770,18 +785,24 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
   if (threadIdx.x == 0) a.n_sec[chunk] = n_re;
   if (n_re == 0) return;
   BRay* region = a.brays + (size_t)chunk * a.cap_rays;
+  float2* scu = a.scu + (size_t)chunk * a.cap_rays;
   const float total = a.score_sum[chunk];
-  // pass 0: final score = cc / sum * n_re + U(ray key)   (microfacet.py:504-506)
+  const int lane = threadIdx.x & 31;
+  // pass 0: final score = cc / sum * n_re + U(ray key)   (microfacet.py:504-506); histogram of its top 11 bits.
+  // The scores crowd into a handful of exponent bins, so equal bins of a warp are merged into one shared atomic.
   for (int i = threadIdx.x; i < 2048; i += 1024) hist[i] = 0;
   __syncthreads();
-  for (int r = threadIdx.x; r < n; r += 1024) {
-    BRay* o = region + r;
-    const BSample* b = a.bs + o->owner;
-    const uint64_t rkey = nmf_mix64(b->key, (uint64_t)(r - (int)b->roff) + NMF_STREAM_RAY0);
-    const float U = nmf_uniform(rkey, NMF_STREAM_TIE);
-    const float sc = (total > 0.f ? o->score / total * (float)n_re : 0.f) + U;
-    o->score = sc;
-    atomicAdd(&hist[__float_as_uint(sc) >> 21], 1u);
+  for (int r0 = 0; r0 < n; r0 += 1024) {
+    const int r = r0 + threadIdx.x;
+    unsigned bin = 0xFFFFFFFFu;
+    if (r < n) {
+      const float2 v = scu[r];
+      const float sc = (total > 0.f ? v.x / total * (float)n_re : 0.f) + v.y;
+      scu[r].x = sc;
+      bin = __float_as_uint(sc) >> 21;
+    }
+    const unsigned m = __match_any_sync(FULL, bin);
+    if (r < n && lane == __ffs(m) - 1) atomicAdd(&hist[bin], (unsigned)__popc(m));
   }
   __syncthreads();
   unsigned prefix = 0, need = (unsigned)n_re;
@@ -794,7 +815,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
       __syncthreads();
       const unsigned hi_shift = pass == 1 ? 21 : 10;
       for (int r = threadIdx.x; r < n; r += 1024) {
-        const unsigned bits = __float_as_uint(region[r].score);
+        const unsigned bits = __float_as_uint(scu[r].x);
         if ((bits >> hi_shift) == prefix) atomicAdd(&hist[(bits >> shift) & (bins - 1)], 1u);
       }
       __syncthreads();
@@ -819,21 +840,22 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
   __syncthreads();
   const unsigned thr = prefix;
   for (int r = threadIdx.x; r < n; r += 1024) {
-    BRay* o = region + r;
-    const unsigned bits = __float_as_uint(o->score);
+    const unsigned bits = __float_as_uint(scu[r].x);
     bool take = bits > thr;
     if (bits == thr) take = atomicAdd(&sh_eq, 1u) < need;
     if (take) {
       const unsigned sl = atomicAdd(&sh_slot, 1u);
       if (sl < (unsigned)n_re) {
-        const BSample* b = a.bs + o->owner;
+        BRay* o = region + r;
+        const BSample* b = a.bs + a.owner[(size_t)chunk * a.cap_rays + r];
+        const float4 q = *(const float4*)o->L;
         const size_t gi = (size_t)chunk * a.max_retrace + sl;
         float* ry = a.rays1 + gi * 6;
-        ry[0] = b->pos[0] + o->L[0] * 5e-3f;                            // microfacet.py:449-452
-        ry[1] = b->pos[1] + o->L[1] * 5e-3f;
-        ry[2] = b->pos[2] + o->L[2] * 5e-3f;
-        ry[3] = o->L[0]; ry[4] = o->L[1]; ry[5] = o->L[2];
-        a.mip1[gi] = o->mip;
+        ry[0] = b->pos[0] + q.x * 5e-3f;                                // microfacet.py:449-452
+        ry[1] = b->pos[1] + q.y * 5e-3f;
+        ry[2] = b->pos[2] + q.z * 5e-3f;
+        ry[3] = q.x; ry[4] = q.y; ry[5] = q.z;
+        a.mip1[gi] = q.w;
         a.key1[gi] = nmf_mix64(b->key, (uint64_t)(r - (int)b->roff) + NMF_STREAM_RAY0);
         o->slot = (int)sl;
       }
@@ -842,81 +864,86 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
 }
 
 // ================================================================================================
-// k_incoming (level 0): models/microfacet.py:549-600 -- incoming radiance of every primary bounce ray
+// k_incoming (level 0): models/microfacet.py:549-613 -- incoming radiance of every primary bounce ray (re-traced
+// radiance or environment lookup), Fresnel mix, and the per-sample sums over the rays (segmented warp reduction):
+// spec / tint debug maps go straight to the pixel accumulators, the combined radiance to the sample's rgbsum
 // ================================================================================================
 struct IncomingArgs {
-  const BSample* bs; BRay* brays; const int* ray_count; int cap_rays; const float* rgb1; int max_retrace;
+  BSample* bs; const BRay* brays; const uint32_t* owner; const int* ray_count; int cap_rays; const float* rgb1; int max_retrace;
+  float* accum; const int* tile_start; int n_chunks;
 };
-__global__ void __launch_bounds__(256) k_incoming(const NmfScene s, const IncomingArgs a) {
-  const int chunk = blockIdx.y;
-  const int n = min(a.ray_count[chunk], a.cap_rays);
-  BRay* region = a.brays + (size_t)chunk * a.cap_rays;
-  for (int r = blockIdx.x * 256 + threadIdx.x; r < n; r += gridDim.x * 256) {
-    BRay* o = region + r;
-    const float4 q0 = *(const float4*)o->L, q1 = *(const float4*)o->bw;
-    const int slot = o->slot;
-    const BSample* b = a.bs + o->owner;
-    const nmf_v3 L = nmf_mk3(q0.x, q0.y, q0.z);
-    float inc[3];
-    if (slot >= 0) {
-      const float* src = a.rgb1 + ((size_t)chunk * a.max_retrace + slot) * 4;
-      inc[0] = src[0]; inc[1] = src[1]; inc[2] = src[2];
-    } else {
-      nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, L, q0.w, inc);
+__global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, const IncomingArgs a) {
+  const int n_tiles = a.tile_start[a.n_chunks];
+  const int lane = threadIdx.x & 31;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int lo = 0, hi = a.n_chunks;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(a.tile_start + mid) <= tile) lo = mid; else hi = mid;
     }
-    const float4 qv = *(const float4*)b->V, q3 = *(const float4*)b->f0, q4 = *(const float4*)b->diffuse;
-    const nmf_v3 H = nmf_unit(nmf_mk3((qv.x + L.x) / 2.0f, (qv.y + L.y) / 2.0f, (qv.z + L.z) / 2.0f));
-    const float ch = fabsf(qv.x * H.x + qv.y * H.y + qv.z * H.z);
-    const float F0 = nmf_fresnel(q3.x, ch), F1 = nmf_fresnel(q3.y, ch), F2 = nmf_fresnel(q3.z, ch);
-    float4 st2, st3;
-    st2.x = F0 * inc[0] * q1.x + (1.f - F0) * q4.x;
-    st2.y = F1 * inc[1] * q1.y + (1.f - F1) * q4.y;
-    st2.z = F2 * inc[2] * q1.z + (1.f - F2) * q4.z;
-    st2.w = __int_as_float(slot);
-    st3.x = inc[0]; st3.y = inc[1]; st3.z = inc[2]; st3.w = __uint_as_float(o->owner);
-    *(float4*)o->comb = st2;
-    *(float4*)o->inc = st3;
+    const int chunk = lo;
+    const int n = min(a.ray_count[chunk], a.cap_rays);
+    const int r = (tile - __ldg(a.tile_start + chunk)) * MLP_THREADS + threadIdx.x;
+    const bool active = r < n;
+    float comb[3] = {0.f, 0.f, 0.f}, inc[3] = {0.f, 0.f, 0.f}, bw[3] = {0.f, 0.f, 0.f};
+    uint32_t key = 0xFFFFFFFFu;
+    BSample* b = a.bs;
+    if (active) {
+      const BRay* o = a.brays + (size_t)chunk * a.cap_rays + r;
+      const float4 q0 = *(const float4*)o->L, q1 = *(const float4*)o->bw;
+      const int slot = __float_as_int(q1.w);
+      key = a.owner[(size_t)chunk * a.cap_rays + r];
+      b = a.bs + key;
+      const nmf_v3 L = nmf_mk3(q0.x, q0.y, q0.z);
+      if (slot >= 0) {
+        const float* src = a.rgb1 + ((size_t)chunk * a.max_retrace + slot) * 4;
+        inc[0] = src[0]; inc[1] = src[1]; inc[2] = src[2];
+      } else {
+        nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, L, q0.w, inc);
+      }
+      const float4 qv = *(const float4*)b->V, q3 = *(const float4*)b->f0, q4 = *(const float4*)b->diffuse;
+      const nmf_v3 H = nmf_unit(nmf_mk3((qv.x + L.x) / 2.0f, (qv.y + L.y) / 2.0f, (qv.z + L.z) / 2.0f));
+      const float ch = fabsf(qv.x * H.x + qv.y * H.y + qv.z * H.z);
+      const float F0 = nmf_fresnel(q3.x, ch), F1 = nmf_fresnel(q3.y, ch), F2 = nmf_fresnel(q3.z, ch);
+      comb[0] = F0 * inc[0] * q1.x + (1.f - F0) * q4.x;                  // microfacet.py:585-600
+      comb[1] = F1 * inc[1] * q1.y + (1.f - F1) * q4.y;
+      comb[2] = F2 * inc[2] * q1.z + (1.f - F2) * q4.z;
+      bw[0] = q1.x; bw[1] = q1.y; bw[2] = q1.z;
+    }
+    seg_reduce3(comb, key, lane);
+    seg_reduce3(inc, key, lane);
+    seg_reduce3(bw, key, lane);
+    const bool head = seg_head(key, lane);       // every lane takes part in the shuffle
+    if (active && head) {
+      const float4 q0 = *(const float4*)b->pos, q2 = *(const float4*)b->N, q3 = *(const float4*)b->f0, q5 = *(const float4*)b->fresn;
+      const float sw = q0.w / (float)max(__float_as_int(q2.w), 1);
+      float* acc = a.accum + (size_t)__float_as_uint(q3.w) * A_N;
+      atomicAdd(b->rgbsum, comb[0]); atomicAdd(b->rgbsum + 1, comb[1]); atomicAdd(b->rgbsum + 2, comb[2]);
+      atomicAdd(acc + A_SPEC, sw * inc[0]); atomicAdd(acc + A_SPEC + 1, sw * inc[1]); atomicAdd(acc + A_SPEC + 2, sw * inc[2]);
+      atomicAdd(acc + A_TINT, sw * q5.x * bw[0]); atomicAdd(acc + A_TINT + 1, sw * q5.y * bw[1]);
+      atomicAdd(acc + A_TINT + 2, sw * q5.z * bw[2]);
+    }
   }
 }
 
 // ================================================================================================
-// k_reduce: models/microfacet.py:565-613 + tensor_nerf.py:448-452,528,565 -- mean over the bounce rays of a
-// sample, weighted into its pixel
+// k_reduce0: tensor_nerf.py:448-452,528 -- per bounce sample: mean radiance of its rays, weighted into the pixel
+// (and into the cross-section map, which clips the sample's colour first)
 // ================================================================================================
-struct ReduceArgs { const BSample* bs; const int* n_bs; int cap_bs; const BRay* brays; int cap_rays; float* accum; };
-template <int LEVEL>
-__global__ void __launch_bounds__(256) k_reduce(const ReduceArgs a) {
+struct ReduceArgs { const BSample* bs; const int* n_bs; int cap_bs; float* accum; };
+__global__ void __launch_bounds__(256) k_reduce0(const ReduceArgs a) {
   const int n = min(*a.n_bs, a.cap_bs);
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
     const BSample* b = a.bs + i;
-    const int count = b->count;
-    const BRay* r = a.brays + (size_t)b->chunk * a.cap_rays + b->roff;
-    float comb[3] = {0, 0, 0}, inc[3] = {0, 0, 0}, bw[3] = {0, 0, 0};
-    for (int j = 0; j < count; ++j) {
-      const float4 c = *(const float4*)r[j].comb;
-      comb[0] += c.x; comb[1] += c.y; comb[2] += c.z;
-      if (LEVEL == 0) {
-        const float4 q = *(const float4*)r[j].inc, v = *(const float4*)r[j].bw;
-        inc[0] += q.x; inc[1] += q.y; inc[2] += q.z;
-        bw[0] += v.x; bw[1] += v.y; bw[2] += v.z;
-      }
-    }
-    const float inv = 1.0f / (float)count, w = b->w;
-    if (LEVEL == 0) {
-      float* acc = a.accum + (size_t)b->ray * A_N;
-      const bool below = b->flags & 1u;
+    const float4 sum = *(const float4*)b->rgbsum;
+    const float inv = 1.0f / (float)b->count, w = b->w;
+    float* acc = a.accum + (size_t)b->ray * A_N;
+    const bool below = b->flags & 1u;
+    const float rgb[3] = {sum.x * inv, sum.y * inv, sum.z * inv};
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float rgb = comb[c] * inv;
-        atomicAdd(acc + A_RGB + c, w * rgb);
-        if (below) atomicAdd(acc + A_CROSS + c, w * nmf_clampf(rgb, 0.f, 1.f));
-        atomicAdd(acc + A_SPEC + c, w * inc[c] * inv);
-        atomicAdd(acc + A_TINT + c, w * b->fresn[c] * (bw[c] * inv));
-      }
-    } else {
-      float* acc = a.accum + (size_t)b->ray * 4;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) atomicAdd(acc + c, w * comb[c] * inv);
+    for (int c = 0; c < 3; ++c) {
+      atomicAdd(acc + A_RGB + c, w * rgb[c]);
+      if (below) atomicAdd(acc + A_CROSS + c, w * nmf_clampf(rgb[c], 0.f, 1.f));
     }
   }
 }
@@ -1125,7 +1152,7 @@ static int check_scene(const NmfScene* s) {
 
 // ---- optional phase timing: CUDA events recorded on the caller's stream between the phases ----
 static const char* g_phase_names[NMF_N_PHASES] = {"march0", "shade0", "bounce0", "select", "march1", "shade1", "bounce1",
-                                                   "reduce1", "incoming0", "reduce0", "finish"};
+                                                   "finish1", "incoming0", "reduce0", "finish"};
 static cudaEvent_t g_ev[NMF_N_PHASES + 1];
 static bool g_ev_made = false, g_prof_on = false, g_ev_rec[NMF_N_PHASES + 1];
 static void prof_mark(int i, cudaStream_t st) {
@@ -1219,14 +1246,14 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
     const int gb = sm_count() * (tcm ? 5 : 3);
     k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count0, w.cap_rays0, nc, w.tile_start0);
     CKL();
-    BounceArgs b0 = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.score_sum, w.tile_start0, nc};
+    BounceArgs b0 = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.score_sum, w.scu0, nullptr, w.tile_start0, nc};
     if (tcm) k_bounce<0, 1><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b0);
     else k_bounce<0, 0><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b0);
     CKL();
     prof_mark(3, stream);
 
     if (s.max_retrace > 0) {
-      SelectArgs sa = {w.bs0, w.brays0, w.ray_count0, w.cap_rays0, w.score_sum, s.max_retrace, w.n_sec, w.rays1, w.mip1, w.key1};
+      SelectArgs sa = {w.bs0, w.brays0, w.owner0, w.scu0, w.ray_count0, w.cap_rays0, w.score_sum, s.max_retrace, w.n_sec, w.rays1, w.mip1, w.key1};
       k_select<<<nc, 1024, 0, stream>>>(sa);
       CKL();
       prof_mark(4, stream);
@@ -1249,26 +1276,22 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
       prof_mark(6, stream);
       k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count1, w.cap_rays1, nc, w.tile_start1);
       CKL();
-      BounceArgs b1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr, w.tile_start1, nc};
+      BounceArgs b1 = {w.bs1, nullptr, w.owner1, w.ray_count1, w.cap_rays1, nullptr, nullptr, w.accum1, w.tile_start1, nc};
       if (tcm) k_bounce<1, 1><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b1);
       else k_bounce<1, 0><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b1);
       CKL();
       prof_mark(7, stream);
-      ReduceArgs r1 = {w.bs1, w.n_bs + 1, w.cap_bs1, w.brays1, w.cap_rays1, w.accum1};
-      k_reduce<1><<<sm_count() * 4, 256, 0, stream>>>(r1);
-      CKL();
       k_finish1<<<(w.n_rays1 + 127) / 128, 128, 0, stream>>>(s, w.rays1, w.mip1, w.acc1, w.accum1, w.n_sec, s.max_retrace,
                                                            w.n_rays1, w.rgb1);
       CKL();
       prof_mark(8, stream);
     }
-    IncomingArgs ia = {w.bs0, w.brays0, w.ray_count0, w.cap_rays0, w.rgb1, s.max_retrace};
-    int gxi = (sm_count() * 8 + nc - 1) / nc;
-    k_incoming<<<dim3(gxi, nc), 256, 0, stream>>>(s, ia);
+    IncomingArgs ia = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.rgb1, s.max_retrace, w.accum0, w.tile_start0, nc};
+    k_incoming<<<sm_count() * 8, MLP_THREADS, 0, stream>>>(s, ia);
     CKL();
     prof_mark(9, stream);
-    ReduceArgs r0 = {w.bs0, w.n_bs, w.cap_bs0, w.brays0, w.cap_rays0, w.accum0};
-    k_reduce<0><<<sm_count() * 4, 256, 0, stream>>>(r0);
+    ReduceArgs r0 = {w.bs0, w.n_bs, w.cap_bs0, w.accum0};
+    k_reduce0<<<sm_count() * 4, 256, 0, stream>>>(r0);
     CKL();
     prof_mark(10, stream);
   } else {
