@@ -36,6 +36,10 @@ struct __align__(16) BSample {
   uint64_t key; uint32_t chunk; uint32_t pad;
   float feat[24];
   float rgbsum[4];              // level 0: sum over the sample's bounce rays of their combined radiance (k_incoming)
+  // what GGX sampling and the ISH encodings need per SAMPLE, computed once in k_shade instead of once per bounce ray:
+  // frame[0..17] = t, b, V_l, Vs, T1, T2 (nmf_ggx_frame), [18] = a, [19..20] = ISH scales s1, s2, [21..22] = the
+  // per-sample Sobol offsets 0.25 * U (brdf_samplers/base.py:16-19)
+  float frame[24];
 };
 
 struct __align__(16) BRay {     // level-0 bounce ray (level-1 rays are reduced inside k_bounce<1> and never stored)
@@ -407,6 +411,8 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       }
     }
     // ---------------- shade phase: one lane per sample ----------------
+    // Written compactly (rolled channel / noise loops, results stored where they are consumed) because this kernel
+    // is instruction-cache bound: the code of both phases has to stream through a 32 KB cache (profiles/).
     const int si = wbase + lane;
     const bool active = si < n;
     Surv sv; sv.ray = 0; sv.step = 0; sv.w = 0.f;
@@ -418,52 +424,11 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
     for (int i = 0; i < 3; ++i) { o[i] = __ldg(a.rays + (size_t)ray * 6 + i); d[i] = __ldg(a.rays + (size_t)ray * 6 + 3 + i); }
     nmf_step_pos(o, d, nmf_step_z(a.tmin[ray], s.stepsize, k), p);
     nmf_normalize_xyz(s, p, xn);
-    float f[24];
-#pragma unroll
-    for (int i = 0; i < 24; ++i) f[i] = s_feat[lane * SHADE_FEAT_LD + i];
-    const nmf_v3 nrm = nmf_mk3(s_feat[lane * SHADE_FEAT_LD + 24], s_feat[lane * SHADE_FEAT_LD + 25], s_feat[lane * SHADE_FEAT_LD + 26]);
-    // material heads (render_modules.py:553-560); the tint head (rows 3..5) and the second roughness output (row 10)
-    // feed nothing on this path (fresnel mode, r2 = r1: microfacet.py:360)
-    float lin[11];
-#pragma unroll
-    for (int h = 0; h < 11; ++h) {
-      if ((h >= 3 && h < 6) || h == 10) { lin[h] = 0.f; continue; }
-      float v = 0.f;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const float4 wv = *(const float4*)&s_headw[h * 24 + 4 * q];
-        v += wv.x * f[4 * q]; v += wv.y * f[4 * q + 1]; v += wv.z * f[4 * q + 2]; v += wv.w * f[4 * q + 3];
-      }
-      lin[h] = v + s_headb[h];
-    }
-    float albedo[3], f0v[3], diffuse[3], fresn[3];
-    const float rough = nmf_clampf(nmf_sigmoid(lin[9] + s.roughness_bias) / 2.0f, 1e-2f, 1.0f);
-    float sh[9];
-    nmf_sh9(nrm, sh);
+    float* fs = s_feat + lane * SHADE_FEAT_LD;
+    float* hs = s_coef + lane * 9;         // per-channel head results, parked in the (now idle) coefficient staging rows
+    const nmf_v3 nrm = nmf_mk3(fs[24], fs[25], fs[26]);
     const nmf_v3 V = nmf_mk3(-d[0], -d[1], -d[2]);
     const float vn = nmf_dot(V, nrm);
-    const float cost = fabsf(vn);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      albedo[c] = nmf_clampf(nmf_sigmoid(s.diffuse_mul * lin[c] + s.diffuse_bias), 0.f, 1.f);
-      f0v[c] = nmf_sigmoid(lin[6 + c] + s.f0_bias);
-      float e = 0.f;
-#pragma unroll
-      for (int i = 0; i < 9; ++i) e += s_sh[i * 3 + c] * sh[i];
-      diffuse[c] = albedo[c] * e;                                      // microfacet.py:316
-      fresn[c] = nmf_fresnel(f0v[c], cost);
-    }
-    if (LEVEL == 0 && active) {
-      // debug / auxiliary maps (tensor_nerf.py:495-566, microfacet.py:639-647)
-      float* acc = a.accum + (size_t)ray * A_N;
-      atomicAdd(acc + A_WN, w * nrm.x); atomicAdd(acc + A_WN + 1, w * nrm.y); atomicAdd(acc + A_WN + 2, w * nrm.z);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        atomicAdd(acc + A_DIFF + c, w * (1.0f - fresn[c]) * diffuse[c]);
-        atomicAdd(acc + A_ALB + c, w * albedo[c]);
-      }
-      atomicAdd(acc + A_ROUGH, w * rough);
-    }
     // bounce count (pt_selectors.py:20-40)
     const int chunk = ray / a.group;
     const uint64_t rkey = LEVEL == 0 ? nmf_mix64(a.seed, a.ray_id0 + (uint64_t)ray) : (active ? a.keys[ray] : 0ull);
@@ -512,30 +477,71 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
         else if (roff + count > a.cap_rays) { atomicOr(a.error, NMF_DEV_E_BRAYS); slot = -1; }
       }
     }
+    BSample* b = a.bs + (slot >= 0 ? slot : 0);
+    float* acc = LEVEL == 0 ? a.accum + (size_t)ray * A_N : nullptr;
+    // roughness head (render_modules.py:553-560; r2 = r1, microfacet.py:360)
+    float lin = s_headb[9];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) lin += s_headw[9 * 24 + i] * fs[i];
+    const float rough = nmf_clampf(nmf_sigmoid(lin + s.roughness_bias) / 2.0f, 1e-2f, 1.0f);
+    float sh[9];
+    nmf_sh9(nrm, sh);
+    const float cost = fabsf(vn);
+    // per colour channel: albedo head (row c), f0 head (row 6 + c), SH irradiance, Fresnel; the tint head (rows 3..5)
+    // feeds nothing on this path (fresnel mode)
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      float la = s_headb[c], lf = s_headb[6 + c];
+#pragma unroll
+      for (int i = 0; i < 24; ++i) {
+        const float fv = fs[i];
+        la += s_headw[c * 24 + i] * fv;
+        lf += s_headw[(6 + c) * 24 + i] * fv;
+      }
+      const float albedo = nmf_clampf(nmf_sigmoid(s.diffuse_mul * la + s.diffuse_bias), 0.f, 1.f);
+      const float f0v = nmf_sigmoid(lf + s.f0_bias);
+      float e = 0.f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) e += s_sh[i * 3 + c] * sh[i];
+      const float diffuse = albedo * e;                                  // microfacet.py:316
+      const float fresn = nmf_fresnel(f0v, cost);
+      if (LEVEL == 0 && active) {
+        // debug / auxiliary maps (tensor_nerf.py:495-566, microfacet.py:639-647)
+        atomicAdd(acc + A_WN + c, w * (c == 0 ? nrm.x : c == 1 ? nrm.y : nrm.z));
+        atomicAdd(acc + A_DIFF + c, w * (1.0f - fresn) * diffuse);
+        atomicAdd(acc + A_ALB + c, w * albedo);
+      }
+      hs[c] = f0v; hs[3 + c] = diffuse; hs[6 + c] = fresn;             // parked: the record is written with 16-byte stores
+    }
+    if (LEVEL == 0 && active) atomicAdd(acc + A_ROUGH, w * rough);
     if (slot >= 0) {
-      BSample* b = a.bs + slot;
       const float sgn = vn > 0.f ? 1.f : (vn < 0.f ? -1.f : 0.f);        // microfacet.py:354-356
+      const nmf_v3 Nf = nmf_mk3(nrm.x * sgn, nrm.y * sgn, nrm.z * sgn);
       float4* q = (float4*)b;
       q[0] = make_float4(p[0], p[1], p[2], w);
       q[1] = make_float4(V.x, V.y, V.z, rough);
-      q[2] = make_float4(nrm.x * sgn, nrm.y * sgn, nrm.z * sgn, __int_as_float(count));
-      q[3] = make_float4(f0v[0], f0v[1], f0v[2], __uint_as_float((uint32_t)ray));
-      q[4] = make_float4(diffuse[0], diffuse[1], diffuse[2], __uint_as_float((uint32_t)roff));
-      q[5] = make_float4(fresn[0], fresn[1], fresn[2], __uint_as_float(xn[2] < 0.f ? 1u : 0u));
+      q[2] = make_float4(Nf.x, Nf.y, Nf.z, __int_as_float(count));
+      q[3] = make_float4(hs[0], hs[1], hs[2], __uint_as_float((uint32_t)ray));
+      q[4] = make_float4(hs[3], hs[4], hs[5], __uint_as_float((uint32_t)roff));
+      q[5] = make_float4(hs[6], hs[7], hs[8], __uint_as_float(xn[2] < 0.f ? 1u : 0u));
       b->key = skey; b->chunk = (uint32_t)chunk; b->pad = 0;
       if (LEVEL == 0) *(float4*)b->rgbsum = make_float4(0.f, 0.f, 0.f, 0.f);
-      // appearance feature + noise (microfacet.py:297, keyed Box-Muller); a rolled loop over the parked features keeps
-      // the 24 inlined Box-Muller bodies out of the instruction stream (the kernel is instruction-cache sensitive)
+      // per-sample part of the GGX sampler and of the ISH encodings, shared by all bounce rays of the sample
+      const NmfGGXFrame fr = nmf_ggx_frame(V, Nf, rough);
+      float s1, s2;
+      nmf_ish_scales(rough, &s1, &s2);
+      float4* fq = (float4*)b->frame;
+      fq[0] = make_float4(fr.t.x, fr.t.y, fr.t.z, fr.b.x);
+      fq[1] = make_float4(fr.b.y, fr.b.z, fr.V_l.x, fr.V_l.y);
+      fq[2] = make_float4(fr.V_l.z, fr.Vs.x, fr.Vs.y, fr.Vs.z);
+      fq[3] = make_float4(fr.T1.x, fr.T1.y, fr.T1.z, fr.T2.x);
+      fq[4] = make_float4(fr.T2.y, fr.T2.z, fr.a, s1);
+      fq[5] = make_float4(s2, 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_U), 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_V), 0.f);
+      // appearance feature + noise (microfacet.py:297, keyed Box-Muller), one feature per trip of a rolled loop
 #pragma unroll 1
-      for (int i = 0; i < 6; ++i) {
-        const float* fq = s_feat + lane * SHADE_FEAT_LD + 4 * i;
-        float4 v;
-        v.x = fq[0] + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + 4 * i, NMF_STREAM_NOISE_B + 4 * i);
-        v.y = fq[1] + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + 4 * i + 1, NMF_STREAM_NOISE_B + 4 * i + 1);
-        v.z = fq[2] + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + 4 * i + 2, NMF_STREAM_NOISE_B + 4 * i + 2);
-        v.w = fq[3] + s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + 4 * i + 3, NMF_STREAM_NOISE_B + 4 * i + 3);
-        *(float4*)(b->feat + 4 * i) = v;
-      }
+      for (int i = 0; i < 24; ++i) fs[i] += s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + i, NMF_STREAM_NOISE_B + i);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) *(float4*)(b->feat + 4 * i) = make_float4(fs[4 * i], fs[4 * i + 1], fs[4 * i + 2], fs[4 * i + 3]);
     }
     // ray -> bounce-sample map of the allocated ranges, written by the whole warp
     unsigned todo = __ballot_sync(FULL, slot >= 0);
@@ -607,14 +613,19 @@ __device__ __forceinline__ void mlp_forward(const float* sm, float* x, float brd
   out3[2] = nmf_sigmoid(o2 + brdf_bias);
 }
 // modules/brdf.py:216-225: x = [feat | ISH(half) | half | ISH(diff) | diff | 0-pad]; feat is already in x[0..23]
-__device__ __forceinline__ void mlp_encode(float (&x)[TC_K0], nmf_v3 half_l, nmf_v3 diff_l, float rough) {
-  nmf_ish18(half_l, rough, &x[24]);
+__device__ __forceinline__ void mlp_encode_s(float (&x)[TC_K0], nmf_v3 half_l, nmf_v3 diff_l, float s1, float s2) {
+  nmf_ish18_s(half_l, s1, s2, &x[24]);
   x[42] = half_l.x; x[43] = half_l.y; x[44] = half_l.z;
-  nmf_ish18(diff_l, rough, &x[45]);
+  nmf_ish18_s(diff_l, s1, s2, &x[45]);
   x[63] = diff_l.x; x[64] = diff_l.y; x[65] = diff_l.z;
   x[TC_ONE] = 1.f;                      // carries the biases through the tensor-core GEMMs (nmf_mlp_tc.cuh)
 #pragma unroll
   for (int i = TC_ONE + 1; i < TC_K0; ++i) x[i] = 0.f;
+}
+__device__ __forceinline__ void mlp_encode(float (&x)[TC_K0], nmf_v3 half_l, nmf_v3 diff_l, float rough) {
+  float s1, s2;
+  nmf_ish_scales(rough, &s1, &s2);
+  mlp_encode_s(x, half_l, diff_l, s1, s2);
 }
 // fp32 SIMT variant (scene.mlp_mode == 1): stage the row in this thread's shared-memory column, then mlp_forward
 __device__ __forceinline__ void mlp_simt(const float* sm, float* xcol, const float (&x)[TC_K0], float brdf_bias, float* out3) {
@@ -626,19 +637,25 @@ __device__ __forceinline__ void mlp_simt(const float* sm, float* xcol, const flo
 // ================================================================================================
 // k_bounce: brdf_samplers/base.py:11-20, ggx.py:61-268, models/microfacet.py:367-472 (+ :561-613 at level 1)
 // ================================================================================================
-// Sum of v over the run of lanes that share `key` (runs are contiguous: bounce rays of one sample are consecutive);
-// the first lane of each run ends up with the run's total.
-__device__ __forceinline__ void seg_reduce3(float (&v)[3], uint32_t key, int lane) {
+// Segments = runs of lanes that share `key` (bounce rays of one sample are consecutive).  seg_setup finds, with one
+// ballot, whether this lane starts a run and the last lane of its run; seg_sum3 then leaves the run's total in its
+// first lane using value shuffles only.  All 32 lanes must call both.
+struct Seg { bool head; int last; };
+__device__ __forceinline__ Seg seg_setup(uint32_t key, int lane) {
+  Seg g;
+  const uint32_t prev = __shfl_up_sync(FULL, key, 1);
+  g.head = lane == 0 || prev != key;
+  const unsigned heads = __ballot_sync(FULL, g.head);
+  const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+  g.last = above ? __ffs(above) - 2 : 31;
+  return g;
+}
+__device__ __forceinline__ void seg_sum3(float (&v)[3], const Seg& g, int lane) {
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
-    const uint32_t ok = __shfl_down_sync(FULL, key, off);
     const float a0 = __shfl_down_sync(FULL, v[0], off), a1 = __shfl_down_sync(FULL, v[1], off), a2 = __shfl_down_sync(FULL, v[2], off);
-    if (lane + off < 32 && ok == key) { v[0] += a0; v[1] += a1; v[2] += a2; }
+    if (lane + off <= g.last) { v[0] += a0; v[1] += a1; v[2] += a2; }
   }
-}
-__device__ __forceinline__ bool seg_head(uint32_t key, int lane) {
-  const uint32_t prev = __shfl_up_sync(FULL, key, 1);
-  return lane == 0 || prev != key;
 }
 
 struct BounceArgs {
@@ -707,16 +724,23 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
     const float rough = q1.w, w = q0.w;
     const int count = max(__float_as_int(q2.w), 1);
     const uint64_t skey = b->key;
-    const float u1 = nmf_wrap01(__ldg(s.sobol + 2 * j) + 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_U));
-    const float u2 = nmf_wrap01(__ldg(s.sobol + 2 * j + 1) + 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_V));
-    const NmfGGX g = nmf_ggx_sample(u1, u2, V, N, rough);
+    const float4* fq = (const float4*)b->frame;
+    const float4 f0 = fq[0], f1 = fq[1], f2 = fq[2], f3 = fq[3], f4 = fq[4], f5 = fq[5];
+    NmfGGXFrame fr;
+    fr.t = nmf_mk3(f0.x, f0.y, f0.z); fr.b = nmf_mk3(f0.w, f1.x, f1.y); fr.V_l = nmf_mk3(f1.z, f1.w, f2.x);
+    fr.Vs = nmf_mk3(f2.y, f2.z, f2.w); fr.T1 = nmf_mk3(f3.x, f3.y, f3.z); fr.T2 = nmf_mk3(f3.w, f4.x, f4.y);
+    fr.a = f4.z;
+    const float ish1 = f4.w, ish2 = f5.x;
+    const float u1 = nmf_wrap01(__ldg(s.sobol + 2 * j) + f5.y);
+    const float u2 = nmf_wrap01(__ldg(s.sobol + 2 * j + 1) + f5.z);
+    const NmfGGX g = nmf_ggx_sample_f(fr, u1, u2, V, N, rough);
     float x[TC_K0];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const float4 f = *(const float4*)(b->feat + 4 * i);
       x[4 * i] = f.x; x[4 * i + 1] = f.y; x[4 * i + 2] = f.z; x[4 * i + 3] = f.w;
     }
-    mlp_encode(x, g.half_l, g.diff_l, rough);
+    mlp_encode_s(x, g.half_l, g.diff_l, ish1, ish2);
     float bw[3];
     if (TC) tc_mlp_forward(tc, x, s.brdf_bias, bw);      // all 128 threads: the tile is one tensor-core GEMM
     else if (active) mlp_simt(sm, xcol, x, s.brdf_bias, bw);
@@ -754,9 +778,9 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
       }
       const int lane = threadIdx.x & 31;
       const uint32_t key = active ? slot : 0xFFFFFFFFu;
-      seg_reduce3(comb, key, lane);
-      const bool head = seg_head(key, lane);     // every lane takes part in the shuffle
-      if (active && head) {
+      const Seg seg = seg_setup(key, lane);      // every lane takes part in the shuffles
+      seg_sum3(comb, seg, lane);
+      if (active && seg.head) {
         const float sw = w / (float)count;
         float* acc = a.accum1 + (size_t)b->ray * 4;
         atomicAdd(acc, sw * comb[0]); atomicAdd(acc + 1, sw * comb[1]); atomicAdd(acc + 2, sw * comb[2]);
@@ -910,11 +934,11 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
       comb[2] = F2 * inc[2] * q1.z + (1.f - F2) * q4.z;
       bw[0] = q1.x; bw[1] = q1.y; bw[2] = q1.z;
     }
-    seg_reduce3(comb, key, lane);
-    seg_reduce3(inc, key, lane);
-    seg_reduce3(bw, key, lane);
-    const bool head = seg_head(key, lane);       // every lane takes part in the shuffle
-    if (active && head) {
+    const Seg seg = seg_setup(key, lane);        // every lane takes part in the shuffles
+    seg_sum3(comb, seg, lane);
+    seg_sum3(inc, seg, lane);
+    seg_sum3(bw, seg, lane);
+    if (active && seg.head) {
       const float4 q0 = *(const float4*)b->pos, q2 = *(const float4*)b->N, q3 = *(const float4*)b->f0, q5 = *(const float4*)b->fresn;
       const float sw = q0.w / (float)max(__float_as_int(q2.w), 1);
       float* acc = a.accum + (size_t)__float_as_uint(q3.w) * A_N;

@@ -174,15 +174,18 @@ NMF_HD void nmf_sh9(nmf_v3 d, float* o) {
   o[7] = -1.0925484305920792f * (x * z);
   o[8] = 0.5462742152960396f * (x * x - y * y);
 }
-NMF_HD void nmf_ish18(nmf_v3 v, float rough, float* o) {
+// roughness attenuation of degrees 1 and 2: exp(-l(l+1)/2/kappa), kappa = 1/(rough + 1e-3)  (sh.py:268-275)
+NMF_HD void nmf_ish_scales(float rough, float* s1, float* s2) {
   float kappa = 1.0f / (rough + 1e-3f);
+  float kk = kappa + 1e-8f;
+  *s1 = expf(-1.0f / kk);
+  *s2 = expf(-3.0f / kk);
+}
+NMF_HD void nmf_ish18_s(nmf_v3 v, float s1, float s2, float* o) {
   float x = v.x, y = v.y, z = v.z;
   float xx = x * x, yy = y * y, zz = z * z;
   float x4 = xx * xx, y4 = yy * yy, z4 = zz * zz;
-  float kk = kappa + 1e-8f;
   float s0 = 1.0f;                      // exp(-0)
-  float s1 = expf(-1.0f / kk);          // exp(-l(l+1)/2/kappa), l = 1
-  float s2 = expf(-3.0f / kk);          // l = 2
   o[0] = s0 * 0.28209479177387814f;
   o[1] = -s1 * 0.488603f * x;
   o[2] = s1 * 0.488603f * z;
@@ -201,6 +204,11 @@ NMF_HD void nmf_ish18(nmf_v3 v, float rough, float* o) {
   o[15] = (0.473087f * xx - 0.473087f * yy) * (7.0f * zz - 1.0f);
   o[16] = 1.77013f * x * z * (xx - 3.0f * yy);
   o[17] = 0.625836f * x4 - 3.755016f * xx * yy + 0.625836f * y4;
+}
+NMF_HD void nmf_ish18(nmf_v3 v, float rough, float* o) {
+  float s1, s2;
+  nmf_ish_scales(rough, &s1, &s2);
+  nmf_ish18_s(v, s1, s2, o);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -225,16 +233,25 @@ NMF_HD float nmf_ggx_pdf(nmf_v3 L_l, nmf_v3 V_l, nmf_v3 H_l, float r) {
   float logD = -logf(fmaxf(invG * invD, NMF_EPS)) - logf(fmaxf(4.0f * V_l.z, NMF_EPS));
   return L_l.z > 0.0f ? expf(logD) : 0.0f;
 }
-NMF_HD NmfGGX nmf_ggx_sample(float u1, float u2, nmf_v3 V, nmf_v3 N, float r) {
-  NmfGGX g;
+// The part of the sampler that only depends on the shaded sample (V, N, roughness), not on the bounce ray:
+// tangent frame, view vector in the local / stretched frame, the orthonormal basis of the VNDF disk (ggx.py:83-140)
+struct NmfGGXFrame { nmf_v3 t, b, V_l, Vs, T1, T2; float a; };
+NMF_HD NmfGGXFrame nmf_ggx_frame(nmf_v3 V, nmf_v3 N, float r) {
+  NmfGGXFrame f;
   nmf_v3 up = (fabsf(N.z) < 0.999f) ? nmf_mk3(0.f, 0.f, 1.f) : nmf_mk3(-1.f, 0.f, 0.f);
-  nmf_v3 t = nmf_unit(nmf_cross(up, N));
-  nmf_v3 b = nmf_unit(nmf_cross(N, t));
-  nmf_v3 V_l = nmf_mk3(nmf_dot(t, V), nmf_dot(b, V), nmf_dot(N, V));
-  nmf_v3 Vs = nmf_unit(nmf_mk3(r * V_l.x, r * V_l.y, V_l.z));
-  nmf_v3 T1 = (Vs.z < 0.999f) ? nmf_unit(nmf_cross(Vs, nmf_mk3(0.f, 0.f, 1.f))) : nmf_mk3(-1.f, 0.f, 0.f);
-  nmf_v3 T2 = nmf_unit(nmf_cross(T1, Vs));
-  float a = fminf(1.0f / fmaxf(1.0f + Vs.z, 1e-8f), 1e4f);
+  f.t = nmf_unit(nmf_cross(up, N));
+  f.b = nmf_unit(nmf_cross(N, f.t));
+  f.V_l = nmf_mk3(nmf_dot(f.t, V), nmf_dot(f.b, V), nmf_dot(N, V));
+  f.Vs = nmf_unit(nmf_mk3(r * f.V_l.x, r * f.V_l.y, f.V_l.z));
+  f.T1 = (f.Vs.z < 0.999f) ? nmf_unit(nmf_cross(f.Vs, nmf_mk3(0.f, 0.f, 1.f))) : nmf_mk3(-1.f, 0.f, 0.f);
+  f.T2 = nmf_unit(nmf_cross(f.T1, f.Vs));
+  f.a = fminf(1.0f / fmaxf(1.0f + f.Vs.z, 1e-8f), 1e4f);
+  return f;
+}
+NMF_HD NmfGGX nmf_ggx_sample_f(const NmfGGXFrame& f, float u1, float u2, nmf_v3 V, nmf_v3 N, float r) {
+  NmfGGX g;
+  const nmf_v3 t = f.t, b = f.b, V_l = f.V_l, Vs = f.Vs, T1 = f.T1, T2 = f.T2;
+  const float a = f.a;
   float rad = sqrtf(u1);
   bool lo = u2 < a;
   float phi = lo ? (u2 / a * NMF_PI) : ((u2 - a) / (1.0f - a) * NMF_PI + NMF_PI);
@@ -256,6 +273,9 @@ NMF_HD NmfGGX nmf_ggx_sample(float u1, float u2, nmf_v3 V, nmf_v3 N, float r) {
   g.H = H2;
   g.half_l = nmf_mk3(nmf_dot(t, H2), nmf_dot(b, H2), nmf_dot(N, H2));
   return g;
+}
+NMF_HD NmfGGX nmf_ggx_sample(float u1, float u2, nmf_v3 V, nmf_v3 N, float r) {
+  return nmf_ggx_sample_f(nmf_ggx_frame(V, N, r), u1, u2, V, N, r);
 }
 // (u, v) of bounce ray j: brdf_samplers/base.py:11-20  (sobol[j] + 0.25 * U) mod 1
 NMF_HD float nmf_wrap01(float x) { return x - floorf(x); }
