@@ -36,13 +36,16 @@ NMF_HD void nmf_normalize_xyz(const NmfScene& s, const float* p, float* xn) {   
   xn[2] = nmf_norm_coord(p[2], s.aabb0[2], s.inv_aabb2[2]);
 }
 NMF_HD NmfTaps nmf_vm_taps(const NmfScene& s, const float* xn) {                // tensoRF.py:161-179
+  // every factor that is indexed by axis a has grid[a] texels along it (plane p: width grid[mat0(p)], height
+  // grid[mat1(p)]; line p: grid[vec(p)]; checked by the host before any launch), so the nine bilinear set-ups of
+  // the three plane/line pairs are three set-ups, one per axis
+  const NmfLerp lx = nmf_lerp_setup(xn[0], s.plane_w[0]);
+  const NmfLerp ly = nmf_lerp_setup(xn[1], s.plane_h[0]);
+  const NmfLerp lz = nmf_lerp_setup(xn[2], s.plane_h[1]);
   NmfTaps t;
-#pragma unroll
-  for (int p = 0; p < 3; ++p) {
-    t.px[p] = nmf_lerp_setup(xn[NMF_MAT0(p)], s.plane_w[p]);
-    t.py[p] = nmf_lerp_setup(xn[NMF_MAT1(p)], s.plane_h[p]);
-    t.pl[p] = nmf_lerp_setup(xn[NMF_VEC(p)], s.line_n[p]);
-  }
+  t.px[0] = lx; t.py[0] = ly; t.pl[0] = lz;      // plane (x, y), line z
+  t.px[1] = lx; t.py[1] = lz; t.pl[1] = ly;      // plane (x, z), line y
+  t.px[2] = ly; t.py[2] = lz; t.pl[2] = lx;      // plane (y, z), line x
   return t;
 }
 // bilinear tap of a channel-last plane: `stride` floats per texel, `off` float offset of this lane's 4 channels

@@ -134,6 +134,22 @@ NMF_HD bool nmf_occupied(const uint32_t* vox, const uint32_t* cell, int w, int h
   return false;
 }
 
+// The common case of nmf_occupied split in two, so that a kernel can issue the loads of several steps before it
+// consumes any of them: nmf_occ_fast returns true when all eight trilinear weights are positive (one bit of the
+// cell field answers); *word = index of the 32-bit word to load (or -1: the cell is out of range => not occupied).
+NMF_HD bool nmf_occ_fast(int w, int h, int d, int pitch, float cx, float cy, float cz, long long* word, int* shift) {
+  float ix = nmf_unnorm(cx, w), iy = nmf_unnorm(cy, h), iz = nmf_unnorm(cz, d);
+  float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
+  int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
+  float tx = ix - fx0, ty = iy - fy0, tz = iz - fz0;   // exact
+  if (!(tx > 0.0f && ty > 0.0f && tz > 0.0f && x0 >= 0 && y0 >= 0 && z0 >= 0)) return false;
+  if (x0 >= w || y0 >= h || z0 >= d) { *word = -1; *shift = 0; return true; }
+  size_t i = ((size_t)z0 * h + y0) * (size_t)pitch + x0;
+  *word = (long long)(i >> 5);
+  *shift = (int)(i & 31);
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // A3 bilinear taps of F.grid_sample(align_corners=True, zeros padding): fields/tensoRF.py:181-205
 // ------------------------------------------------------------------------------------------------
