@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NMF_ABI_VERSION 2
+#define NMF_ABI_VERSION 3
 
 #define NMF_OK 0
 #define NMF_E_ARG (-1)          /* null pointer / non-positive size                                   */
@@ -162,6 +162,11 @@ typedef struct NmfCounters {
   int* n_retrace;          /* rays actually re-traced (<= max_retrace)                                            */
   int* n_shaded;           /* [2] (not per chunk): samples that survived the weight cut at level 0 / 1            */
   unsigned* error;         /* [1] NMF_DEV_E_* bits                                                                 */
+  /* float [n_chunks][4]: the sums behind the statistics TensorNeRF.forward returns without debug maps
+   * (modules/tensor_nerf.py:567-649): [0] ori_loss = sum w*min(v.n,0)^2, [1] 3*diffuse_reg = sum of the diffuse map,
+   * [2] sum over samples and channels of the tint debug value (brdf_reg = [2] / (3*n_samples0)), [3] sum of acc
+   * (prediction_loss = 2*[3] without a normal module) */
+  float* stat4;
 } NmfCounters;
 
 int nmf_abi_version(void);
@@ -219,6 +224,22 @@ int nmf_material_heads(const NmfScene* scene, const float* feat, int n, float* a
 /* occupancy rebuild, alpha stage of AlphaGridSampler.getDenseAlpha (samplers/alphagrid.py:209-247):
  * alpha[z][y][x] = 1 - exp(-sigma(lattice point) * stepsize) on a (gz,gy,gx) lattice spanning the aabb */
 int nmf_dense_alpha(const NmfScene* scene, int gx, int gy, int gz, float* alpha, void* stream);
+
+/* ---- the callers either side of the path ---- */
+
+/* Ray generation of one view on the device: dataLoader/ray_utils.py:23-43 (get_ray_directions: pixel centres + 0.5,
+ * ((i - cx) / fx, (j - cy) / fy, 1)), dataLoader/blender.py:108-110 (normalise), ray_utils.py:67-89 (get_rays).
+ * c2w_host: HOST pointer to the 3x4 row-major camera-to-world matrix already in the OpenCV convention
+ * (blender.py:146: transform_matrix @ diag(1,-1,-1,1)).  pixel_ids (device, optional): ray i is pixel pixel_ids[i]
+ * (row-major id = y * W + x), e.g. the shuffle of renderer.py:130-132; NULL = all n = H*W pixels in order.
+ * rays: (n, 6) device output [origin, unit direction]. */
+int nmf_generate_rays(const float* c2w_host, int H, int W, float fx, float fy, float cx, float cy, const int* pixel_ids,
+                      int n, float* rays, void* stream);
+
+/* Evaluation metric of renderer.py:399-401 on the device: sum over rays and channels of
+ * (floor(clip(rgb, 0, 1) * 255) / 255 - clip(gt, 0, 1))^2 in fp64 -> sum_sq[0] (device).  gt is indexed by
+ * pixel_ids[i] when given (rgb is in render order, gt in image order).  PSNR = -10 log10(sum_sq / (3 n)). */
+int nmf_image_sq_error(const float* rgb, const float* gt, const int* pixel_ids, int n, double* sum_sq, void* stream);
 
 #ifdef __cplusplus
 }

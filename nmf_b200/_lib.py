@@ -52,7 +52,7 @@ class NmfRender(C.Structure):
 IMAGE_FIELDS = ["rgb_map", "acc_map", "depth", "world_normal", "normal", "termination_xyz", "surf_width",
                 "cross_section", "diffuse", "tint", "roughness", "spec", "albedo"]
 COUNTER_FIELDS = ["n_samples0", "n_samples1", "n_cand", "n_bounce_rays0", "n_bounce_rays1", "n_retrace",
-                  "n_shaded", "error"]
+                  "n_shaded", "error", "stat4"]
 
 
 class NmfImages(C.Structure):
@@ -115,16 +115,18 @@ def lib():
         "nmf_brdf_mlp": (I, [SP, P, P, P, P, I, P, P]),
         "nmf_material_heads": (I, [SP, P, I, P, P, P, P, P]),
         "nmf_dense_alpha": (I, [SP, I, I, I, P, P]),
+        "nmf_generate_rays": (I, [P, I, I, F, F, F, F, P, I, P, P]),
+        "nmf_image_sq_error": (I, [P, P, P, I, P, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    assert L.nmf_abi_version() == 2, "libnmf_b200.so ABI mismatch: rebuild"
+    assert L.nmf_abi_version() == 3, "libnmf_b200.so ABI mismatch: rebuild"
     _lib = L
     return L
 
 
 EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_profile_phase_name", "nmf_workspace_bytes", "nmf_render_rays", "nmf_render_rays_host", "nmf_sample_rays",
             "nmf_vm_density", "nmf_vm_appfeature", "nmf_vm_normals", "nmf_env_lookup", "nmf_ggx_sample",
-            "nmf_brdf_mlp", "nmf_material_heads", "nmf_dense_alpha"]
+            "nmf_brdf_mlp", "nmf_material_heads", "nmf_dense_alpha", "nmf_generate_rays", "nmf_image_sq_error"]

@@ -48,7 +48,8 @@ struct __align__(16) BRay {     // level-0 bounce ray (level-1 rays are reduced 
 };
 
 // per-ray accumulators of level 0 (floats)
-enum { A_RGB = 0, A_WN = 3, A_CROSS = 6, A_DIFF = 9, A_TINT = 12, A_SPEC = 15, A_ALB = 18, A_ROUGH = 21, A_N = 24 };
+// A_ORI / A_TINTU feed the A19 statistics: sum w * min(v.n, 0)^2 and the UNWEIGHTED sum of the per-sample tint
+enum { A_RGB = 0, A_WN = 3, A_CROSS = 6, A_DIFF = 9, A_TINT = 12, A_SPEC = 15, A_ALB = 18, A_ROUGH = 21, A_ORI = 22, A_TINTU = 23, A_N = 24 };
 
 struct WS {
   // counters (zeroed every call)
@@ -63,6 +64,7 @@ struct WS {
   float* score_sum;   // [n_chunks]
   double* wsum1;      // [n_chunks]
   unsigned* error;    // [1]
+  float* stat4;       // [n_chunks][4] A19 statistics: sum of w*min(v.n,0)^2, of the diffuse map, of the sample tints, of acc
   int* tile_start0;   // [n_chunks + 1]
   int* tile_start1;   // [n_chunks + 1]
   size_t counters_bytes;
@@ -106,6 +108,7 @@ static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base) {
   w.score_sum = (float*)take(nc * sizeof(float));
   w.wsum1 = (double*)take(nc * sizeof(double));
   w.error = (unsigned*)take(sizeof(unsigned));
+  w.stat4 = (float*)take((size_t)nc * 4 * sizeof(float));
   w.tile_start0 = (int*)take((nc + 1) * sizeof(int));
   w.tile_start1 = (int*)take((nc + 1) * sizeof(int));
   w.accum0 = (float*)take((size_t)n_rays * A_N * sizeof(float));
@@ -548,7 +551,10 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       }
       hs[c] = f0v; hs[3 + c] = diffuse; hs[6 + c] = fresn;             // parked: the record is written with 16-byte stores
     }
-    if (LEVEL == 0 && active) atomicAdd(acc + A_ROUGH, w * rough);
+    if (LEVEL == 0 && active) {
+      atomicAdd(acc + A_ROUGH, w * rough);
+      if (vn < 0.f) atomicAdd(acc + A_ORI, w * (vn * vn));               // tensor_nerf.py:573-583 ori_loss
+    }
     if (slot >= 0) {
       const float sgn = vn > 0.f ? 1.f : (vn < 0.f ? -1.f : 0.f);        // microfacet.py:354-356
       const nmf_v3 Nf = nmf_mk3(nrm.x * sgn, nrm.y * sgn, nrm.z * sgn);
@@ -981,6 +987,7 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
       atomicAdd(acc + A_SPEC, sw * inc[0]); atomicAdd(acc + A_SPEC + 1, sw * inc[1]); atomicAdd(acc + A_SPEC + 2, sw * inc[2]);
       atomicAdd(acc + A_TINT, sw * q5.x * bw[0]); atomicAdd(acc + A_TINT + 1, sw * q5.y * bw[1]);
       atomicAdd(acc + A_TINT + 2, sw * q5.z * bw[2]);
+      atomicAdd(acc + A_TINTU, (q5.x * bw[0] + q5.y * bw[1] + q5.z * bw[2]) / (float)max(__float_as_int(q2.w), 1));   // brdf_reg
     }
   }
 }
@@ -1124,9 +1131,29 @@ __global__ void __launch_bounds__(128) k_shade_plain(const NmfScene s, const Pla
 struct FinishArgs {
   const float* rays; const float* tmin; const float* acc; const float* depth; const int* termk; const int* nvalid;
   const float* accum; int n; float focal; int model;
+  int chunk; float* stat4;
 };
 __global__ void k_finish0(const NmfScene s, const FinishArgs a, const NmfImages out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  {
+    // A19 (tensor_nerf.py:567-649): per-chunk sums behind ori_loss, diffuse_reg, brdf_reg and prediction_loss
+    const bool in = i < a.n;
+    const float* A = a.accum + (size_t)(in ? i : 0) * A_N;
+    float v[4] = {in ? A[A_ORI] : 0.f, in ? A[A_DIFF] + A[A_DIFF + 1] + A[A_DIFF + 2] : 0.f, in ? A[A_TINTU] : 0.f,
+                  in ? a.acc[i] : 0.f};
+    const int chunk = (in ? i : a.n - 1) / a.chunk;
+    const int chunk0 = __shfl_sync(FULL, chunk, 0);
+    if (__all_sync(FULL, chunk == chunk0)) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += __shfl_xor_sync(FULL, v[q], off);
+      if ((threadIdx.x & 31) == 0)
+        for (int q = 0; q < 4; ++q) atomicAdd(a.stat4 + 4 * chunk0 + q, v[q]);
+    } else if (in) {
+      for (int q = 0; q < 4; ++q) atomicAdd(a.stat4 + 4 * chunk + q, v[q]);
+    }
+  }
   if (i >= a.n) return;
   const float acc = a.acc[i];
   const float t = 1.0f - acc;
@@ -1171,6 +1198,8 @@ __global__ void k_export_counters(const WS w, const NmfCounters c, int model) {
     if (c.n_bounce_rays0) c.n_bounce_rays0[i] = w.ray_count0[i];
     if (c.n_bounce_rays1) c.n_bounce_rays1[i] = w.ray_count1[i];
     if (c.n_retrace) c.n_retrace[i] = w.n_sec[i];
+    if (c.stat4)
+      for (int q = 0; q < 4; ++q) c.stat4[4 * i + q] = w.stat4[4 * i + q];
   }
   if (i == 0) {
     if (c.n_shaded) { c.n_shaded[0] = w.n_surv[0]; c.n_shaded[1] = w.n_surv[1]; }
@@ -1369,7 +1398,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
     CKL();
     prof_mark(2, stream);
   }
-  FinishArgs fa = {rays, w.tmin0, w.acc0, w.depth0, w.termk0, w.nvalid0, w.accum0, n, rp->focal, s.model};
+  FinishArgs fa = {rays, w.tmin0, w.acc0, w.depth0, w.termk0, w.nvalid0, w.accum0, n, rp->focal, s.model, rp->chunk, w.stat4};
   k_finish0<<<(n + 127) / 128, 128, 0, stream>>>(s, fa, *out);
   CKL();
   if (counters) {
@@ -1400,7 +1429,7 @@ extern "C" int nmf_render_rays_host(const NmfScene* scene, const NmfRender* rp, 
 #define C2H(field, cnt) \
   if (counters_host->field && counters_dev->field) CK(cudaMemcpyAsync(counters_host->field, counters_dev->field, (cnt) * 4, cudaMemcpyDeviceToHost, stream));
     C2H(n_samples0, nc) C2H(n_samples1, nc) C2H(n_cand, nc) C2H(n_bounce_rays0, nc) C2H(n_bounce_rays1, nc) C2H(n_retrace, nc)
-    C2H(n_shaded, 2) C2H(error, 1)
+    C2H(n_shaded, 2) C2H(error, 1) C2H(stat4, 4 * nc)
 #undef C2H
   }
   return NMF_OK;
@@ -1659,6 +1688,64 @@ extern "C" int nmf_dense_alpha(const NmfScene* scene, int gx, int gy, int gz, fl
   if (!alpha || gx < 2 || gy < 2 || gz < 2) return NMF_E_ARG;
   const long long total = (long long)gx * gy * gz * 4;
   k_dense_alpha<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*scene, gx, gy, gz, alpha);
+  CKL();
+  return NMF_OK;
+}
+
+// ================================================================================================
+// Callers either side of the path
+// ================================================================================================
+// dataLoader/ray_utils.py:23-43 (get_ray_directions), dataLoader/blender.py:97-120,170-173 (normalise, get_rays):
+// the rays of one view are generated on the device from (pose, intrinsics) instead of being stored as (N,6) tensors
+struct RayGenArgs { float R[9], T[3]; int W; float fx, fy, cx, cy; const int* pixel_ids; int n; float* rays; };
+__global__ void k_generate_rays(const RayGenArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const int pix = a.pixel_ids ? a.pixel_ids[i] : i;
+  const float px = (float)(pix % a.W) + 0.5f, py = (float)(pix / a.W) + 0.5f;            // create_meshgrid + 0.5
+  const float dx = NMF_DIV(NMF_SUB(px, a.cx), a.fx), dy = NMF_DIV(NMF_SUB(py, a.cy), a.fy), dz = 1.0f;
+  const float nrm = sqrtf(NMF_ADD(NMF_ADD(NMF_MUL(dx, dx), NMF_MUL(dy, dy)), NMF_MUL(dz, dz)));   // blender.py:108-110
+  const float ux = NMF_DIV(dx, nrm), uy = NMF_DIV(dy, nrm), uz = NMF_DIV(dz, nrm);
+  float* o = a.rays + (size_t)i * 6;
+  o[0] = a.T[0]; o[1] = a.T[1]; o[2] = a.T[2];                                                   // ray_utils.py:84
+#pragma unroll
+  for (int r = 0; r < 3; ++r) o[3 + r] = ux * a.R[3 * r] + uy * a.R[3 * r + 1] + uz * a.R[3 * r + 2];   // directions @ c2w[:3,:3].T
+}
+extern "C" int nmf_generate_rays(const float* c2w_host, int H, int W, float fx, float fy, float cx, float cy, const int* pixel_ids,
+                                 int n, float* rays, void* stream) {
+  if (!c2w_host || !rays || H <= 0 || W <= 0 || n <= 0 || !(fx > 0.f) || !(fy > 0.f)) return NMF_E_ARG;
+  RayGenArgs a;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) a.R[3 * r + c] = c2w_host[4 * r + c];
+    a.T[r] = c2w_host[4 * r + 3];
+  }
+  a.W = W; a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.pixel_ids = pixel_ids; a.n = n; a.rays = rays;
+  k_generate_rays<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+  CKL();
+  return NMF_OK;
+}
+
+// renderer.py:399-401: squared error of the 8-bit quantised render against the ground truth, summed in fp64 on the
+// device (one 8-byte read-back per image instead of the image itself)
+__global__ void k_image_sq_error(const float* rgb, const float* gt, const int* pixel_ids, int n, double* out) {
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const size_t g = (size_t)(pixel_ids ? pixel_ids[i] : i) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float q = floorf(nmf_clampf(rgb[(size_t)i * 3 + c], 0.f, 1.f) * 255.0f) / 255.0f;
+      const float d = q - nmf_clampf(gt[g + c], 0.f, 1.f);
+      acc += (double)(d * d);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+extern "C" int nmf_image_sq_error(const float* rgb, const float* gt, const int* pixel_ids, int n, double* sum_sq, void* stream) {
+  if (!rgb || !gt || !sum_sq || n <= 0) return NMF_E_ARG;
+  CK(cudaMemsetAsync(sum_sq, 0, sizeof(double), (cudaStream_t)stream));
+  k_image_sq_error<<<sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(rgb, gt, pixel_ids, n, sum_sq);
   CKL();
   return NMF_OK;
 }

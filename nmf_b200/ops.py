@@ -119,6 +119,34 @@ def dense_alpha(scene, grid_size):
     return out
 
 
+def generate_rays(c2w, H, W, fx, fy=None, cx=None, cy=None, pixel_ids=None, device="cuda", out=None):
+    """(n,6) rays of one view generated on the device (dataLoader/ray_utils.py:23-89, blender.py:108-110,146).
+    c2w: 3x4 / 4x4 camera-to-world in the OpenCV convention; pixel_ids: optional int32 device tensor (render order)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.NmfError("nmf_b200 ops take CUDA tensors (there is no CPU path)")
+    m = torch.as_tensor(c2w, dtype=torch.float32).cpu()[:3, :4].contiguous()
+    n = H * W if pixel_ids is None else int(pixel_ids.shape[0])
+    if pixel_ids is not None and (pixel_ids.dtype != torch.int32 or not pixel_ids.is_cuda):
+        raise _lib.NmfError("pixel_ids must be an int32 CUDA tensor")
+    rays = torch.empty(n, 6, device=dev) if out is None else out
+    fy = fx if fy is None else fy
+    cx = W / 2 if cx is None else cx
+    cy = H / 2 if cy is None else cy
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().nmf_generate_rays(C.c_void_p(m.data_ptr()), H, W, float(fx), float(fy), float(cx), float(cy),
+                                                _p(pixel_ids), n, _p(rays), _stream()), "nmf_generate_rays")
+    return rays[:n]
+
+
+def image_sq_error(rgb, gt, pixel_ids=None):
+    """renderer.py:399-401 on the device: fp64 sum of squared errors of the 8-bit quantised render (a (1,) CUDA tensor)."""
+    r, g = _f32(rgb.reshape(-1, 3), rgb.device), _f32(gt.reshape(-1, 3), rgb.device)
+    out = torch.zeros(1, dtype=torch.float64, device=r.device)
+    _lib.check(_lib.lib().nmf_image_sq_error(_p(r), _p(g), _p(pixel_ids), r.shape[0], _p(out), _stream()), "nmf_image_sq_error")
+    return out
+
+
 class RenderBuffers:
     """Output images, counters and scratch for batches of up to `n_rays` rays (grow-only cache per scene)."""
 
@@ -135,8 +163,8 @@ class RenderBuffers:
         self.counters = {}
         self.c_counters = _lib.NmfCounters()
         for k in _lib.COUNTER_FIELDS:
-            n = 2 if k == "n_shaded" else (1 if k == "error" else self.n_chunks)
-            self.counters[k] = torch.zeros(n, dtype=torch.int32, device=dev)
+            n = 2 if k == "n_shaded" else (1 if k == "error" else (4 * self.n_chunks if k == "stat4" else self.n_chunks))
+            self.counters[k] = torch.zeros(n, dtype=torch.float32 if k == "stat4" else torch.int32, device=dev)
             setattr(self.c_counters, k, self.counters[k].data_ptr())
         nbytes = _lib.lib().nmf_workspace_bytes(scene.ref(), n_rays, chunk)
         if nbytes == 0:
@@ -182,7 +210,21 @@ def read_counters(buffers, n, chunk):
     out = {k: c[k][:nc].tolist() for k in ("n_samples0", "n_samples1", "n_cand", "n_bounce_rays0", "n_bounce_rays1", "n_retrace")}
     out["n_shaded"] = c["n_shaded"].tolist()
     out["n_samples"] = [[a, b] for a, b in zip(out["n_samples0"], out["n_samples1"])]
+    out["statistics"] = chunk_statistics(c["stat4"][:4 * nc].reshape(nc, 4), out["n_samples0"])
     return out
+
+
+def chunk_statistics(stat4, n_samples0, envmap_reg=None):
+    """A19 -- the regulariser inputs of TensorNeRF.forward (modules/tensor_nerf.py:567-649), one dict per chunk (= per
+    forward call of the reference), from the per-chunk sums the finish kernel leaves in NmfCounters.stat4."""
+    res = []
+    for (ori, diff, tint, acc), m in zip(stat4.tolist(), n_samples0):
+        d = dict(ori_loss=ori, diffuse_reg=diff / 3.0, brdf_reg=max(tint / (3.0 * m), 0.0) if m > 0 else 0.0,
+                 prediction_loss=2.0 * acc, distortion_loss=0.0)
+        if envmap_reg is not None:
+            d["envmap_reg"] = envmap_reg
+        res.append(d)
+    return res
 
 
 def profile_enable(on=True):

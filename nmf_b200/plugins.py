@@ -414,7 +414,7 @@ class IntegralEquirect(nn.Module):
         return torch.exp((self.brightness + self.mul * x).clip(max=20))
 
     def mean_color(self):
-        return self.activation_fn(self.bg_mat).reshape(3, -1).mean(dim=1)
+        return self.activation_fn(self.bg_mat).reshape(-1, 3).mean(dim=0)     # integral_equirect.py:286-287 (sic)
 
     def get_optparam_groups(self, lr_scale=1):
         return [{"params": [self.bg_mat], "lr": self.lr * lr_scale, "betas": self.betas},
@@ -517,7 +517,18 @@ class TensorNeRF(nn.Module):
                                   skip_eps=self.skip_eps, t_cut=self.t_cut, buffers=self._bufs)
         stats = dict(recur=0, whole_valid=torch.ones(n, dtype=torch.bool, device=rays.device),
                      n_samples=st["n_samples"], n_retrace=st["n_retrace"])
+        # A19 (modules/tensor_nerf.py:567-649): per-chunk regulariser inputs, one list entry per reference forward call
+        env_reg = self._envmap_reg()
+        for k in ("ori_loss", "diffuse_reg", "brdf_reg", "prediction_loss", "distortion_loss"):
+            stats[k] = [c[k] for c in st["statistics"]]
+        stats["envmap_reg"] = [env_reg] * len(st["statistics"])
         return ims, stats
+
+    def _envmap_reg(self):
+        """modules/tensor_nerf.py:606-610: (bg_module.mean_color().mean() - 0.05).clip(min=0)"""
+        if self.bg_module is None or not hasattr(self.bg_module, "mean_color"):
+            return 0.0
+        return float((self.bg_module.mean_color().mean() - 0.05).clip(min=0))
 
     @torch.no_grad()
     def forward(self, rays, focal, start_mipval=None, bg_col=None, stepmul=1, recur=0, override_near=None, output_alpha=None,
@@ -529,7 +540,8 @@ class TensorNeRF(nn.Module):
         ims, stats = self.render_chunks(rays, focal, chunk=rays.shape[0], ray_id0=self._calls * rays.shape[0],
                                         is_train=is_train, ndc_ray=ndc_ray)
         self._calls += 1
-        stats["n_samples"] = stats["n_samples"][0]
+        for k in ("n_samples", "ori_loss", "diffuse_reg", "brdf_reg", "prediction_loss", "distortion_loss", "envmap_reg"):
+            stats[k] = stats[k][0]
         return ims, stats
 
     @staticmethod

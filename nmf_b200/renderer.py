@@ -58,6 +58,7 @@ class HostRenderer:
         stats = {k: self.host_counters[k][:nc].tolist() for k in ("n_samples0", "n_samples1", "n_retrace")}
         stats["n_samples"] = [[a, b] for a, b in zip(stats["n_samples0"], stats["n_samples1"])]
         stats["whole_valid"] = torch.ones(n, dtype=torch.bool)
+        stats["statistics"] = ops.chunk_statistics(self.host_counters["stat4"][:4 * nc].reshape(nc, 4), stats["n_samples0"])
         return {k: v[:n] for k, v in self.host_images.items()}, stats
 
 
@@ -99,3 +100,42 @@ class BundleRender:
             v = v[inv]
             out[k] = v.reshape(self.H, self.W, *v.shape[1:])
         return out, stats
+
+
+@torch.no_grad()
+def evaluate_views(tensorf, poses, H, W, focal, gt_images=None, chunk=4096, shuffle=True, seed=0, keys=("rgb_map",)):
+    """Eval driver, the device-resident restatement of renderer.evaluate's render + PSNR loop (renderer.py:194-401) and
+    of evaluation / evaluation_path (:537-582), without its file output:
+
+      * rays are generated on the device from (pose, intrinsics) (nmf_generate_rays) -- no (N,6) ray tensors in host
+        memory, no H2D copy per view (SURVEY 8f row 4);
+      * pixels are rendered in a shuffled order like BundleRender (renderer.py:130-132) so that every chunk is a
+        random subset of the image, and un-shuffled on the device;
+      * PSNR (renderer.py:399-401: 8-bit quantised render vs clipped ground truth) is reduced on the device and read
+        back as ONE scalar per view; images stay on the device.
+
+    poses: iterable of 3x4 / 4x4 OpenCV-convention camera-to-world matrices; gt_images: optional (V,H,W,3) tensor.
+    Returns dict(images=[{key: (H,W,C) device tensor}], psnr=[float] or None, n_samples=[...])."""
+    dev = tensorf.get_device()
+    n = H * W
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    out_images, sq, n_samples = [], [], []
+    rays = torch.empty(n, 6, device=dev)
+    for v, pose in enumerate(poses):
+        perm = (torch.randperm(n, generator=gen) if shuffle else torch.arange(n)).to(device=dev, dtype=torch.int32)
+        ops.generate_rays(pose, H, W, focal, pixel_ids=perm, device=dev, out=rays)
+        ims, stats = tensorf.render_chunks(rays, focal, chunk=chunk, ray_id0=v * n)
+        n_samples.append(stats["n_samples"])
+        if gt_images is not None:
+            sq.append(ops.image_sq_error(ims["rgb_map"], gt_images[v].to(dev).reshape(-1, 3), pixel_ids=perm))
+        full = {}
+        for k in keys:
+            t = torch.empty_like(ims[k])
+            t[perm.long()] = ims[k]
+            full[k] = t.reshape(H, W, *t.shape[1:])
+        out_images.append(full)
+    psnr = None
+    if sq:
+        mse = torch.cat(sq).cpu() / (3.0 * n)                      # the only device -> host transfer of the loop
+        psnr = (-10.0 * torch.log10(mse)).tolist()
+    return dict(images=out_images, psnr=psnr, n_samples=n_samples)

@@ -117,16 +117,52 @@ def run_case(name, scene_name, G, bg_res, n_rays, crop, model_name, seed, write)
     return worst
 
 
+STAT_KEYS = ["ori_loss", "prediction_loss", "envmap_reg", "brdf_reg", "diffuse_reg", "distortion_loss"]
+
+
+def run_stats_case(name, write):
+    """A19: the reference forward without debug maps (is_train=False, draw_debug=False) returns the regulariser
+    inputs (modules/tensor_nerf.py:567-649).  Replays an existing fixture's scene and rays through the reference,
+    checks the oracle against it and stores the reference numbers in tests/golden/<name>_stats.pt."""
+    fix = torch.load(os.path.join(GOLDEN_DIR, f"{name}.pt"), weights_only=False)
+    meta = dict(aabb=fix["aabb"], near_far=fix["near_far"], grid_size=[fix["grid_size"]] * 3, bg_resolution=fix["bg_resolution"])
+    ref = load_scene_into_reference(fix["state"], meta, fix["model"])
+    assert torch.equal(ref.sampler.alphaMask.alpha_volume.reshape(-1).to(torch.uint8), fix["alpha_volume"].reshape(-1))
+    torch.manual_seed(fix["seed"])
+    with torch.no_grad():
+        ims, st = ref(fix["rays"], fix["focal"], is_train=False, ndc_ray=False, N_samples=-1, draw_debug=False)
+    hp = dict(model="microfacet" if fix["model"] == "microfacet_tensorf2" else "plain")
+    sc = nmf_oracle.Scene(fix["state"], fix["aabb"], fix["near_far"], meta["grid_size"], alpha_volume=fix["alpha_volume"].float(), **hp)
+    torch.manual_seed(fix["seed"])
+    oi, os_ = nmf_oracle.render_chunk(sc, fix["rays"], fix["focal"], keyed_rng.TorchRNG(), draw_debug=False)
+    out = {}
+    for k in STAT_KEYS:
+        a, b = float(st[k]), float(os_[k])
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (k, a, b)
+        out[k] = a
+    assert (ims["rgb_map"] - oi["rgb_map"]).abs().max() <= 2e-5
+    print(f"[{name}] statistics (reference == oracle):", {k: f"{v:.6g}" for k, v in out.items()})
+    if write:
+        torch.save(dict(name=name, ref_statistics=out, n_rays=int(fix["rays"].shape[0])), os.path.join(GOLDEN_DIR, f"{name}_stats.pt"))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--no-write", action="store_true")
+    ap.add_argument("--stats-only", action="store_true", help="only (re)generate the <name>_stats.pt fixtures")
     a = ap.parse_args()
     assert ref_harness.available(), "needs /root/reference"
     w = not a.no_write
+    if a.stats_only:
+        for name in ("microfacet_g40", "microfacet_g56_ship", "plain_g64"):
+            run_stats_case(name, w)
+        return
     run_case("microfacet_g40", "lego", 40, 32, 384, (330, 470, 330, 470), "microfacet_tensorf2", 20211200, w)
     run_case("microfacet_g56_ship", "ship", 56, 48, 256, (300, 500, 300, 500), "microfacet_tensorf2", 7, w)
     run_case("plain_g64", "lego", 64, 32, 4096, (368, 432, 368, 432), "tensorf", 20211200, w)
+    for name in ("microfacet_g40", "microfacet_g56_ship", "plain_g64"):
+        run_stats_case(name, w)
     if a.full:
         run_case("microfacet_g300_full", "lego", 300, 512, 4096, None, "microfacet_tensorf2", 20211200, False)
 

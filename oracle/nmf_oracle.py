@@ -731,6 +731,10 @@ def render_chunk(sc, rays, focal, rng, ray_keys=None, recur=0, start_mip=None, o
         images["cross_section"] = row_mask_sum(below[..., None] * ew * rgb.clip(min=0, max=1), valid)
         for k, v in debug.items():
             images[k] = row_mask_sum(v * ew, valid) + (1 - acc[..., None]) * bg
+    elif recur == 0:
+        stats.update(training_statistics(sc, pw, view[valid], normals, debug))
+        for k, v in debug.items():
+            images[k] = v
     if tonemap:
         rgb_map = srgb(rgb_map)
     images["rgb_map"] = rgb_map + (1 - acc[..., None]) * bg
@@ -740,6 +744,21 @@ def render_chunk(sc, rays, focal, rng, ray_keys=None, recur=0, start_mip=None, o
                    feat=feat if M > 0 else torch.empty(0, sc.basis.shape[0]), rgb=rgb)
         return images, stats, aux
     return images, stats
+
+
+def training_statistics(sc, aweight, view, world_normal, debug):
+    """A19: the regulariser inputs TensorNeRF.forward returns when it is not drawing debug maps
+    (modules/tensor_nerf.py:567-649; microfacet_tensorf2: no normal module => pred_norms = 0, geonorm_iters = -1,
+    align_pred_norms = True, distortion loss hard-coded to 0)."""
+    ndv2 = (-view.reshape(-1, 3) * world_normal.reshape(-1, 3)).sum(dim=-1)                     # :573-577
+    st = dict(ori_loss=(aweight * ndv2.clamp(max=0) ** 2).sum())                                 # :583
+    st["distortion_loss"] = torch.tensor(0.0)                                                    # :596
+    st["prediction_loss"] = (aweight * (2 * (1 - torch.zeros_like(aweight)))).sum()              # :598-602
+    mean_color = torch.exp((sc.brightness + sc.mul * sc.bg_mat).clip(max=20)).reshape(-1, 3).mean(dim=0)
+    st["envmap_reg"] = (mean_color.mean() - 0.05).clip(min=0).float()                            # :606-608
+    st["brdf_reg"] = debug["tint"].mean().clip(min=0) if "tint" in debug and debug["tint"].numel() else torch.tensor(0.0)
+    st["diffuse_reg"] = ((aweight.reshape(-1, 1) * debug["diffuse"]).sum() / 3) if "diffuse" in debug else torch.tensor(0.0)
+    return st
 
 
 def render_rays(sc, rays, focal, rng, chunk=4096, seed=0, ray_id0=0, keys=None):

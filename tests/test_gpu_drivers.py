@@ -1,0 +1,125 @@
+"""GPU: the callers either side of the render path: device ray generation, the
+device-resident eval driver with its PSNR reduction, checkpoint reload + environment swap (relight)."""
+import math
+
+import pytest
+import torch
+
+from conftest import load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from nmf_b200 import config
+    fix = load_fixture("microfacet_g40")
+    G = fix["grid_size"]
+    t, cfg = config.build_model([f"field.grid_size=[{G},{G},{G}]", "model.arch.bg_module.bg_resolution=32"],
+                                aabb=fix["aabb"], near_far=list(fix["near_far"]))
+    t.load_state_dict(fix["state"], strict=False)
+    t = t.cuda().eval()
+    t.sampler.update(t.rf, init=True)
+    t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
+    return fix, t, cfg
+
+
+def test_generate_rays_matches_the_loader_formulas(model):
+    """dataLoader/ray_utils.py:23-89 + blender.py:108-110,146 (restated in nmf_b200/synthetic.camera_rays with torch ops)."""
+    from nmf_b200 import ops, synthetic
+    poses = synthetic.hemisphere_poses(3, seed=1)
+    for H, W in ((800, 800), (37, 53)):
+        focal = synthetic.focal_for(W)
+        for pose in poses[:2]:
+            ref = synthetic.camera_rays(pose, H, W, focal)
+            c2w = torch.as_tensor(pose, dtype=torch.float32) @ torch.diag(torch.tensor([1.0, -1.0, -1.0, 1.0]))
+            got = ops.generate_rays(c2w, H, W, focal).cpu()
+            assert got.shape == ref.shape
+            assert torch.equal(got[:, :3], ref[:, :3])
+            assert (got[:, 3:] - ref[:, 3:]).abs().max() <= 2e-7        # sgemm vs explicit dot: last-bit differences
+            perm = torch.randperm(H * W, generator=torch.Generator().manual_seed(3))[: (H * W) // 3].to(torch.int32)
+            sub = ops.generate_rays(c2w, H, W, focal, pixel_ids=perm.cuda()).cpu()
+            assert torch.equal(sub, got[perm.long()])
+    with pytest.raises(Exception):
+        ops.generate_rays(c2w, 8, 8, focal, device="cpu")
+
+
+def test_image_sq_error_is_the_reference_metric(model):
+    from nmf_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    rgb = torch.rand(5000, 3, generator=g) * 1.2 - 0.1
+    gt = torch.rand(5000, 3, generator=g) * 1.2 - 0.1
+    ref = (((rgb.clip(0, 1) * 255).floor() / 255 - gt.clip(0, 1)).double() ** 2).sum()       # renderer.py:399-401
+    got = ops.image_sq_error(rgb.cuda(), gt.cuda()).cpu()[0]
+    assert abs(float(got) - float(ref)) <= 1e-9 * float(ref)
+    perm = torch.randperm(5000, generator=g)
+    got2 = ops.image_sq_error(rgb[perm].cuda(), gt.cuda(), pixel_ids=perm.to(torch.int32).cuda()).cpu()[0]   # render order
+    assert abs(float(got2) - float(ref)) <= 1e-9 * float(ref)
+
+
+def test_evaluate_views(model):
+    from nmf_b200 import renderer, synthetic
+    fix, t, _ = model
+    H = W = 24
+    focal = synthetic.focal_for(W)
+    poses = [torch.as_tensor(p, dtype=torch.float32) @ torch.diag(torch.tensor([1.0, -1.0, -1.0, 1.0]))
+             for p in synthetic.hemisphere_poses(2, seed=1)]
+    t.seed = 5
+    first = renderer.evaluate_views(t, poses, H, W, focal, chunk=96, keys=("rgb_map", "acc_map"))
+    assert first["psnr"] is None and len(first["images"]) == 2 and first["images"][0]["rgb_map"].shape == (H, W, 3)
+    assert first["images"][0]["rgb_map"].is_cuda and float(first["images"][0]["acc_map"].max()) > 0.5
+    # ground truth = the render shifted by a known amount: the PSNR must be the reference formula on the returned images
+    gt = torch.stack([im["rgb_map"] for im in first["images"]]).cpu() * 0.9 + 0.02
+    again = renderer.evaluate_views(t, poses, H, W, focal, gt_images=gt, chunk=96)
+    for v in range(2):
+        img = again["images"][v]["rgb_map"].cpu()
+        assert torch.allclose(img, first["images"][v]["rgb_map"].cpu(), atol=1e-6)          # keyed RNG: same render
+        mse = torch.mean(((img.clip(0, 1) * 255).floor() / 255 - gt[v].clip(0, 1)) ** 2)
+        assert abs(again["psnr"][v] - (-10.0 * math.log10(float(mse)))) < 1e-3
+    # the shuffle changes chunk membership (retrace selection), not the per-ray maps that do not depend on it
+    plain = renderer.evaluate_views(t, poses[:1], H, W, focal, chunk=96, shuffle=False, keys=("acc_map",))
+    assert torch.allclose(plain["images"][0]["acc_map"], first["images"][0]["acc_map"], atol=1e-6)
+
+
+def test_checkpoint_reload_and_env_swap(model, tmp_path):
+    from nmf_b200 import relight, renderer, synthetic
+    from nmf_b200.plugins import IntegralEquirect
+    fix, t, cfg = model
+    p = str(tmp_path / "scene.th")
+    t.save(p, cfg.model.arch)
+    t2 = relight.load_for_render(p, near_far=list(fix["near_far"]))
+    assert torch.equal(t2.sampler.alphaMask.alpha_volume.reshape(-1).cpu(), t.sampler.alphaMask.alpha_volume.reshape(-1).cpu())
+    # a fixed environment of a different resolution than the checkpoint's (train.py:96-131 hard-codes 512)
+    env = IntegralEquirect(bg_resolution=48, init_val=-0.6, activation="exp", mipbias=0.5)
+    with torch.no_grad():
+        env.bg_mat.add_(torch.randn(env.bg_mat.shape, generator=torch.Generator().manual_seed(1)) * 0.5)
+    bg_path = str(tmp_path / "env.th")
+    torch.save(env.state_dict(), bg_path)
+    relight.swap_env(t2, bg_path)
+    assert t2.bg_module.bg_resolution == 48 and float(t2.bg_module.mipbias) == 0.5
+    rays = fix["rays"][:128].cuda()
+    t.seed = t2.seed = 9
+    a, _ = t.render_chunks(rays, fix["focal"], chunk=128)
+    b, _ = t2.render_chunks(rays, fix["focal"], chunk=128)
+    assert torch.equal(a["surf_width"], b["surf_width"]) and torch.allclose(a["albedo"], b["albedo"], atol=1e-6)
+    assert (a["rgb_map"] - b["rgb_map"]).abs().max() > 1e-3          # new lighting
+    # same numbers as a scene built directly from the swapped state_dict
+    from nmf_b200 import ops
+    from nmf_b200.scene import DeviceScene
+    sd = {k: v for k, v in t.state_dict().items() if not k.startswith("bg_module.")}
+    sd.update({"bg_module." + k: v for k, v in env.state_dict().items()})
+    hp = t.model.hyper()
+    hp.update(distance_scale=t.rf.distance_scale, density_shift=t.rf.density_shift, step_ratio=t.rf.step_ratio)
+    dsc = DeviceScene(sd, t.rf.aabb, t.sampler.near_far, t.rf.grid_size.tolist(),
+                      alpha_volume=t.sampler.alphaMask.alpha_volume, device="cuda", **hp)
+    c, _ = ops.render_rays(dsc, rays, fix["focal"], chunk=128, seed=9)
+    assert torch.allclose(b["rgb_map"], c["rgb_map"], atol=1e-6)
+    # a two-job sweep on one rank
+    poses = [torch.as_tensor(q, dtype=torch.float32) @ torch.diag(torch.tensor([1.0, -1.0, -1.0, 1.0]))
+             for q in synthetic.hemisphere_poses(1, seed=1)]
+    res = relight.relight_sweep({"s": p}, {"e0": bg_path, "e1": env.state_dict()}, poses, 16, 16, synthetic.focal_for(16),
+                                near_far=list(fix["near_far"]), chunk=64)
+    assert set(res) == {("s", "e0"), ("s", "e1")}
+    assert torch.allclose(res[("s", "e0")]["images"][0]["rgb_map"], res[("s", "e1")]["images"][0]["rgb_map"], atol=1e-6)

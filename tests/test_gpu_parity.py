@@ -130,6 +130,25 @@ def compare_images(ims, ref, tol=FLOAT_TOL):
     return report, bad
 
 
+def test_training_statistics_match_oracle(case):
+    """A19: ori_loss / diffuse_reg / brdf_reg / prediction_loss of TensorNeRF.forward (modules/tensor_nerf.py:567-649),
+    per chunk, against the oracle's draw_debug=False forward on the same keyed random numbers."""
+    from nmf_b200 import ops
+    from oracle import keyed_rng as KR
+    from oracle import nmf_oracle as O
+    fix, osc, dsc = case
+    rays = fix["rays"]
+    n, chunk = rays.shape[0], 128
+    _, st = ops.render_rays(dsc, rays.cuda(), fix["focal"], chunk=chunk, seed=5, skip_eps=0.0, t_cut=0.0)
+    for c, got in enumerate(st["statistics"]):
+        r = rays[c * chunk:(c + 1) * chunk]
+        keys = KR.primary_ray_keys(5, np.arange(c * chunk, c * chunk + r.shape[0]))
+        _, ref = O.render_chunk(osc, r, fix["focal"], KR.KeyedRNG(), keys, draw_debug=False)
+        for k in ("ori_loss", "diffuse_reg", "brdf_reg", "prediction_loss"):
+            a, b = got[k], float(ref[k])
+            assert abs(a - b) <= 2e-3 * max(abs(b), 1e-3), (c, k, a, b)
+
+
 @pytest.mark.parametrize("skip", [False, True])
 def test_render_matches_oracle(case, skip):
     from nmf_b200 import ops

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     from nmf_b200 import _lib
     assert sorted(_lib.EXPORTED) == declared
     L.nmf_abi_version.restype = ctypes.c_int
-    assert L.nmf_abi_version() == 2
+    assert L.nmf_abi_version() == 3
 
 
 def test_struct_mirror_matches_header_size():
@@ -80,6 +80,14 @@ def test_plugins_keep_reference_state_dict_keys():
     t2, _ = config.build_model(["model=tensorf", "field.grid_size=[64,64,64]"], aabb=plain["aabb"], near_far=list(plain["near_far"]))
     res = t2.load_state_dict(plain["state"], strict=False)
     assert not res.unexpected_keys, res.unexpected_keys
+
+
+def test_relight_jobs_are_dealt_round_robin():
+    from nmf_b200 import relight
+    for n, world in ((18, 8), (3, 8), (7, 2)):
+        got = sorted(j for r in range(world) for j in relight.job_slice(n, r, world))
+        assert got == list(range(n))
+        assert max(len(relight.job_slice(n, r, world)) for r in range(world)) - min(len(relight.job_slice(n, r, world)) for r in range(world)) <= 1
 
 
 def test_shard_chunks_partition():
