@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--res", type=int, default=800)
     ap.add_argument("--chunk", type=int, default=4096)
     ap.add_argument("--scene", default="lego")
-    ap.add_argument("--cpu-chunks", type=int, default=3, help="chunks of the image the CPU baseline renders")
+    ap.add_argument("--cpu-chunks", type=int, default=16, help="chunks of the image the CPU baseline renders")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-eps", type=float, default=None)
     ap.add_argument("--t-cut", type=float, default=None)
@@ -105,6 +105,17 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_traffic.py from the capture named there); None when absent."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+        return d["kernels"].get(kernel), d.get("capture")
+    except Exception:
+        return None, None
 
 
 def oracle_chunks(state, meta, alpha_volume, rays, focal, chunk, n_chunks, seed, warm=1):
@@ -282,8 +293,24 @@ def main():
     fused_bytes = B_CAND * cand + (B_DENSITY + B_APP + B_NORMAL) * (M0 + M1) + B_ENV * (sum(stats["n_bounce_rays0"]) - n1 + sum(stats["n_bounce_rays1"])) + B_RAY * n
     fused_ms = sum(kernels[k]["ms"] for k in kernels)
     dom = max(("march0", "shade0"), key=lambda k: kernels[k]["ms"])
+    traffic, capture = ncu_traffic(f"k_{dom[:-1]}<0>")
+    n_bray = sum(stats["n_bounce_rays0"]) + sum(stats["n_bounce_rays1"])
+    mlp_ms = phase_acc["bounce0"] + phase_acc["bounce1"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1600.0)))
     roof = {"bound": "hbm", "kernel": f"k_{dom[:-1]}<0>", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": kernels[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "traffic_capture": capture, "peak_source": peak_src,
+            "note": "achieved = algorithmic bytes of SURVEY 8d (reference layouts, no reuse, every valid sample) / measured "
+                    "launch time; the factor planes are L2-resident (traffic << algorithmic bytes) and samples below the "
+                    "weight cut are not shaded, so frac > 1 is cache reuse + pruning, not an HBM rate",
+            "mlp": {"bound": "tensor", "kernel": "k_bounce<0>+k_bounce<1>", "flop_per_ray": 17152, "rays": n_bray,
+                    "achieved": 17152.0 * n_bray / max(mlp_ms, 1e-9) / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": 17152.0 * n_bray / max(mlp_ms, 1e-9) / 1e9 / tf_peak, "ms": mlp_ms,
+                    "note": "fp16 tcgen05 GEMMs of the 66-64-64-4 BRDF MLP; the kernels also sample GGX, encode and look up the environment"},
             "launch_ms": kernels[dom]["ms"], "algorithmic_bytes_per_launch": kernels[dom]["bytes"],
             "march_plus_query": {"ms": fused_ms, "algorithmic_bytes": (B_CAND * cand + (B_DENSITY + B_APP + B_NORMAL) * (M0 + M1)),
                                  "achieved": (B_CAND * cand + (B_DENSITY + B_APP + B_NORMAL) * (M0 + M1)) / max(fused_ms, 1e-9) / 1e6,

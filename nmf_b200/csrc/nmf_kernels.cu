@@ -385,18 +385,31 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
   float* s_feat = s_feat_all + warp * 32 * SHADE_FEAT_LD;
   for (int wbase = (blockIdx.x * 8 + warp) * 32; wbase < n; wbase += gridDim.x * 256) {
     // ---------------- gather phase ----------------
-#pragma unroll 1
-    for (int round = 0; round < 8; ++round) {
-      const int si = wbase + round * 4 + grp;
+    // Sample positions first, one lane per sample: the dependent chain survivor record -> ray -> position is paid
+    // once per 32 samples (coalesced) instead of once per round; the normalised position waits in the sample's
+    // feature row (the row is only overwritten by the contraction that follows the sample's own rounds).
+    {
+      const int si = wbase + lane;
       Surv sv; sv.ray = 0; sv.step = 0; sv.w = 0.f;
       if (si < n) sv = a.surv[si];
       const int ray = (int)sv.ray;
-      float o[3], d[3];
+      float o[3], d[3], p[3], xn[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) { o[i] = __ldg(a.rays + (size_t)ray * 6 + i); d[i] = __ldg(a.rays + (size_t)ray * 6 + 3 + i); }
-      float p[3], xn[3];
       nmf_step_pos(o, d, nmf_step_z(a.tmin[ray], s.stepsize, (int)sv.step), p);
       nmf_normalize_xyz(s, p, xn);
+      float* row = s_feat + lane * SHADE_FEAT_LD;
+      row[0] = xn[0]; row[1] = xn[1]; row[2] = xn[2];
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int round = 0; round < 8; ++round) {
+      const int si = wbase + round * 4 + grp;
+      float xn[3];
+      {
+        const float* row = s_feat + (round * 4 + grp) * SHADE_FEAT_LD;
+        xn[0] = row[0]; xn[1] = row[1]; xn[2] = row[2];
+      }
       const NmfTaps t = nmf_vm_taps(s, xn);
       // appearance coefficients: lanes 0..5 own 4 channels of each plane
       const int row = (round & 1) * 4 + grp;
