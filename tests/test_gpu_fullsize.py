@@ -1,0 +1,118 @@
+"""GPU: the bench workload at BASELINE.json's full size (model=microfacet_tensorf2, G=300, 800x800 = 640 000 rays,
+4096-ray chunks).  The oracle needs ~2 minutes per full image, so whole-image checks use size-independent properties
+(counter consistency, independence of ray order / sharding, linearity in the environment brightness) and the oracle
+itself is run on a sample of chunks."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+CHUNK = 4096
+
+
+@pytest.fixture(scope="module")
+def full():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from nmf_b200 import synthetic
+    from nmf_b200.scene import DeviceScene
+    state, meta = synthetic.make_scene("lego", grid_size=300, bg_resolution=512)
+    focal = synthetic.focal_for(800)
+    rays = synthetic.camera_rays(synthetic.hemisphere_poses(200, seed=1)[0], 800, 800, focal)
+    rays = rays[torch.randperm(rays.shape[0], generator=torch.Generator().manual_seed(20211200))].contiguous()
+    dsc = DeviceScene(state, meta["aabb"], meta["near_far"], meta["grid_size"], device="cuda:0")
+    alpha = dsc.update_alpha_mask()
+    return state, meta, focal, rays, dsc, alpha
+
+
+def test_whole_image_counters_are_consistent(full):
+    from nmf_b200 import ops
+    state, meta, focal, rays, dsc, alpha = full
+    ims, st = ops.render_rays(dsc, rays.cuda(), focal, chunk=CHUNK, seed=1)
+    n, nc = rays.shape[0], math.ceil(rays.shape[0] / CHUNK)
+    assert int(ims["surf_width"].sum()) == sum(st["n_samples0"])                  # per-ray counts vs per-chunk counters
+    sw = ims["surf_width"].cpu()
+    for c in (0, 1, nc - 1):
+        assert int(sw[c * CHUNK:(c + 1) * CHUNK].sum()) == st["n_samples0"][c]
+    assert st["n_retrace"] == [1000] * nc and all(0 < b <= dsc.hp["max_brdf_rays"][1] + 1024 for b in st["n_bounce_rays1"])
+    assert 0 < st["n_shaded"][0] <= sum(st["n_samples0"]) and 0 < st["n_shaded"][1] <= sum(st["n_samples1"])
+    for k, v in ims.items():
+        assert torch.isfinite(v.float()).all(), k
+    acc = ims["acc_map"]
+    assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-4
+    assert float(ims["rgb_map"].min()) >= 0.0 and float(ims["rgb_map"].max()) <= 2.0 + 1e-4
+    # A19: prediction_loss = 2 * sum(acc) per chunk; every statistic finite
+    for c in (0, nc - 1):
+        assert abs(st["statistics"][c]["prediction_loss"] - 2 * float(acc[c * CHUNK:(c + 1) * CHUNK].double().sum())) < 1e-2
+        assert all(math.isfinite(v) for v in st["statistics"][c].values())
+    # a second render of the same rays: identical up to the order of float atomics
+    again, _ = ops.render_rays(dsc, rays.cuda(), focal, chunk=CHUNK, seed=1)
+    assert torch.equal(again["surf_width"], ims["surf_width"])
+    assert (again["rgb_map"] - ims["rgb_map"]).abs().max() < 1e-4
+
+
+def test_sharding_and_ray_order_do_not_change_the_image(full):
+    from nmf_b200 import ops
+    from nmf_b200.distributed import shard_chunks
+    state, meta, focal, rays, dsc, alpha = full
+    sub = rays[:8 * CHUNK].cuda()
+    one, _ = ops.render_rays(dsc, sub, focal, chunk=CHUNK, seed=3)
+    one = {k: v.clone() for k, v in one.items()}
+    parts = []
+    for rank in range(3):                                  # 8 chunks over 3 "ranks": whole chunks, global ray ids
+        s0, s1 = shard_chunks(sub.shape[0], CHUNK, rank, 3)
+        p, _ = ops.render_rays(dsc, sub[s0:s1], focal, chunk=CHUNK, seed=3, ray_id0=s0)
+        parts.append({k: v.clone() for k, v in p.items()})
+    for k in one:
+        got = torch.cat([p[k] for p in parts])
+        if k == "surf_width":
+            assert torch.equal(got, one[k])
+        else:
+            assert (got.float() - one[k].float()).abs().max() < 2e-4, k
+    # reversing the rays inside a chunk keeps every per-ray quantity that does not depend on the retrace selection
+    rev, _ = ops.render_rays(dsc, sub[:CHUNK].flip(0), focal, chunk=CHUNK, seed=3)
+    # keyed numbers follow the global ray id, which flips with the order: compare the geometry-only maps
+    for k in ("acc_map", "depth", "world_normal", "albedo", "roughness"):
+        assert (rev[k].flip(0) - one[k][:CHUNK]).abs().max() < 1e-5, k
+    assert torch.equal(rev["surf_width"].flip(0), one["surf_width"][:CHUNK])
+
+
+def test_radiance_is_linear_in_the_environment_brightness(full):
+    from nmf_b200 import ops
+    from nmf_b200.scene import DeviceScene
+    state, meta, focal, rays, dsc, alpha = full
+    st2 = dict(state)
+    st2["bg_module.brightness"] = state["bg_module.brightness"] + math.log(2.0)
+    dsc2 = DeviceScene(st2, meta["aabb"], meta["near_far"], meta["grid_size"], alpha_volume=alpha, device="cuda:0")
+    sub = rays[:2 * CHUNK].cuda()
+    a, _ = ops.render_rays(dsc, sub, focal, chunk=CHUNK, seed=4)
+    a = {k: v.clone() for k, v in a.items()}
+    b, _ = ops.render_rays(dsc2, sub, focal, chunk=CHUNK, seed=4)
+    bgw = (1 - a["acc_map"])[:, None]                      # debug maps carry (1 - acc) * white
+    for k in ("spec", "diffuse"):
+        x, y = a[k] - bgw, b[k] - bgw
+        scale = float(x.abs().mean())
+        assert (y - 2 * x).abs().max() < 2e-3 * max(scale, 1e-3) + 1e-5, k
+    assert torch.equal(a["surf_width"], b["surf_width"]) and torch.allclose(a["albedo"], b["albedo"], atol=1e-6)
+
+
+def test_sampled_chunks_match_the_oracle(full):
+    from nmf_b200 import ops
+    from oracle import keyed_rng as KR
+    from oracle import nmf_oracle as O
+    from test_gpu_parity import compare_images
+    state, meta, focal, rays, dsc, alpha = full
+    osc = O.Scene(state, meta["aabb"], meta["near_far"], meta["grid_size"], alpha_volume=alpha.cpu().float())
+    ims, st = ops.render_rays(dsc, rays[:3 * CHUNK].cuda(), focal, chunk=CHUNK, seed=6, skip_eps=0.0, t_cut=0.0)
+    for c in (0, 2):
+        r = rays[c * CHUNK:(c + 1) * CHUNK]
+        keys = KR.primary_ray_keys(6, np.arange(c * CHUNK, (c + 1) * CHUNK))
+        ref, rst = O.render_chunk(osc, r, focal, KR.KeyedRNG(), keys)
+        assert st["n_samples0"][c] == rst["n_samples"][0]
+        assert abs(st["n_samples1"][c] - rst["n_samples"][1]) <= 0.005 * rst["n_samples"][1]
+        got = {k: v[c * CHUNK:(c + 1) * CHUNK] for k, v in ims.items()}
+        assert torch.equal(got["surf_width"].cpu(), ref["surf_width"])
+        report, bad = compare_images(got, ref)
+        assert not bad, (c, bad)
