@@ -35,7 +35,6 @@ struct __align__(16) BSample {
   float fresn[3]; uint32_t flags;
   uint64_t key; uint32_t chunk; uint32_t pad;
   float feat[24];
-  float rgbsum[4];              // level 0: sum over the sample's bounce rays of their combined radiance (k_incoming)
   // what GGX sampling and the ISH encodings need per SAMPLE, computed once in k_shade instead of once per bounce ray:
   // frame[0..17] = t, b, V_l, Vs, T1, T2 (nmf_ggx_frame), [18] = a, [19..20] = ISH scales s1, s2, [21..22] = the
   // per-sample Sobol offsets 0.25 * U (brdf_samplers/base.py:16-19)
@@ -71,6 +70,7 @@ struct WS {
   char* counters_base;
   // level 0
   float* tmin0; float* acc0; float* depth0; int* termk0; int* nvalid0; float* accum0;   // accum0 [n_rays][A_N]
+  float4* red0;     // [cap_bs0][2]: {w, count, ray, flags} and the sum of the sample's combined bounce radiance (k_incoming -> k_reduce0)
   Surv* surv0; BSample* bs0; BRay* brays0; uint32_t* owner0; float2* scu0;   // scu0: (retrace score, tie-break U) per ray
   // level 1
   float* rays1; float* mip1; uint64_t* key1; float* tmin1; float* acc1; int* nvalid1; float* accum1; float* rgb1;
@@ -122,6 +122,7 @@ static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base) {
   w.surv0 = (Surv*)take((size_t)w.cap_surv0 * sizeof(Surv));
   if (s->model == 0) {
     w.bs0 = (BSample*)take((size_t)w.cap_bs0 * sizeof(BSample));
+    w.red0 = (float4*)take((size_t)w.cap_bs0 * 2 * sizeof(float4));
     w.brays0 = (BRay*)take((size_t)nc * w.cap_rays0 * sizeof(BRay));
     w.owner0 = (uint32_t*)take((size_t)nc * w.cap_rays0 * 4);
     w.scu0 = (float2*)take((size_t)nc * w.cap_rays0 * sizeof(float2));
@@ -332,6 +333,7 @@ struct ShadeArgs {
   int* ray_count; int cap_rays; uint32_t* owner;
   const int* n_samples; const double* wsum;   // level 1 budget
   unsigned* error;
+  float4* red;              // level 0: per bounce sample {w, count, ray, flags | rgb sum}
 };
 
 // Two phases per warp, 32 surviving samples at a time:
@@ -579,7 +581,10 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       q[4] = make_float4(hs[3], hs[4], hs[5], __uint_as_float((uint32_t)roff));
       q[5] = make_float4(hs[6], hs[7], hs[8], __uint_as_float(xn[2] < 0.f ? 1u : 0u));
       b->key = skey; b->chunk = (uint32_t)chunk; b->pad = 0;
-      if (LEVEL == 0) *(float4*)b->rgbsum = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (LEVEL == 0) {
+        a.red[2 * slot] = make_float4(w, __int_as_float(count), __uint_as_float((uint32_t)ray), __uint_as_float(xn[2] < 0.f ? 1u : 0u));
+        a.red[2 * slot + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       // per-sample part of the GGX sampler and of the ISH encodings, shared by all bounce rays of the sample
       const NmfGGXFrame fr = nmf_ggx_frame(V, Nf, rough);
       float s1, s2;
@@ -947,8 +952,8 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
 // spec / tint debug maps go straight to the pixel accumulators, the combined radiance to the sample's rgbsum
 // ================================================================================================
 struct IncomingArgs {
-  BSample* bs; const BRay* brays; const uint32_t* owner; const int* ray_count; int cap_rays; const float* rgb1; int max_retrace;
-  float* accum; const int* tile_start; int n_chunks;
+  const BSample* bs; const BRay* brays; const uint32_t* owner; const int* ray_count; int cap_rays; const float* rgb1; int max_retrace;
+  float* accum; const int* tile_start; int n_chunks; float4* red;
 };
 __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, const IncomingArgs a) {
   const int n_tiles = a.tile_start[a.n_chunks];
@@ -965,7 +970,7 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
     const bool active = r < n;
     float comb[3] = {0.f, 0.f, 0.f}, inc[3] = {0.f, 0.f, 0.f}, bw[3] = {0.f, 0.f, 0.f};
     uint32_t key = 0xFFFFFFFFu;
-    BSample* b = a.bs;
+    const BSample* b = a.bs;
     if (active) {
       const BRay* o = a.brays + (size_t)chunk * a.cap_rays + r;
       const float4 q0 = *(const float4*)o->L, q1 = *(const float4*)o->bw;
@@ -993,14 +998,16 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
     seg_sum3(inc, seg, lane);
     seg_sum3(bw, seg, lane);
     if (active && seg.head) {
-      const float4 q0 = *(const float4*)b->pos, q2 = *(const float4*)b->N, q3 = *(const float4*)b->f0, q5 = *(const float4*)b->fresn;
-      const float sw = q0.w / (float)max(__float_as_int(q2.w), 1);
-      float* acc = a.accum + (size_t)__float_as_uint(q3.w) * A_N;
-      atomicAdd(b->rgbsum, comb[0]); atomicAdd(b->rgbsum + 1, comb[1]); atomicAdd(b->rgbsum + 2, comb[2]);
+      const float4 hdr = a.red[2 * (size_t)key], q5 = *(const float4*)b->fresn;      // {w, count, ray, flags}
+      const int cnt = max(__float_as_int(hdr.y), 1);
+      const float sw = hdr.x / (float)cnt;
+      float* acc = a.accum + (size_t)__float_as_uint(hdr.z) * A_N;
+      float* rs = (float*)(a.red + 2 * (size_t)key + 1);
+      atomicAdd(rs, comb[0]); atomicAdd(rs + 1, comb[1]); atomicAdd(rs + 2, comb[2]);
       atomicAdd(acc + A_SPEC, sw * inc[0]); atomicAdd(acc + A_SPEC + 1, sw * inc[1]); atomicAdd(acc + A_SPEC + 2, sw * inc[2]);
       atomicAdd(acc + A_TINT, sw * q5.x * bw[0]); atomicAdd(acc + A_TINT + 1, sw * q5.y * bw[1]);
       atomicAdd(acc + A_TINT + 2, sw * q5.z * bw[2]);
-      atomicAdd(acc + A_TINTU, (q5.x * bw[0] + q5.y * bw[1] + q5.z * bw[2]) / (float)max(__float_as_int(q2.w), 1));   // brdf_reg
+      atomicAdd(acc + A_TINTU, (q5.x * bw[0] + q5.y * bw[1] + q5.z * bw[2]) / (float)cnt);   // brdf_reg
     }
   }
 }
@@ -1009,15 +1016,14 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
 // k_reduce0: tensor_nerf.py:448-452,528 -- per bounce sample: mean radiance of its rays, weighted into the pixel
 // (and into the cross-section map, which clips the sample's colour first)
 // ================================================================================================
-struct ReduceArgs { const BSample* bs; const int* n_bs; int cap_bs; float* accum; };
+struct ReduceArgs { const float4* red; const int* n_bs; int cap_bs; float* accum; };
 __global__ void __launch_bounds__(256) k_reduce0(const ReduceArgs a) {
   const int n = min(*a.n_bs, a.cap_bs);
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-    const BSample* b = a.bs + i;
-    const float4 sum = *(const float4*)b->rgbsum;
-    const float inv = 1.0f / (float)b->count, w = b->w;
-    float* acc = a.accum + (size_t)b->ray * A_N;
-    const bool below = b->flags & 1u;
+    const float4 hdr = a.red[2 * (size_t)i], sum = a.red[2 * (size_t)i + 1];      // one 32-byte sector per sample
+    const float w = hdr.x, inv = 1.0f / (float)__float_as_int(hdr.y);
+    float* acc = a.accum + (size_t)__float_as_uint(hdr.z) * A_N;
+    const bool below = __float_as_uint(hdr.w) & 1u;
     const float rgb[3] = {sum.x * inv, sum.y * inv, sum.z * inv};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -1342,7 +1348,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
     h0.rays = rays; h0.tmin = w.tmin0; h0.seed = rp->seed; h0.ray_id0 = rp->ray_id0; h0.group = rp->chunk;
     h0.surv = w.surv0; h0.n_surv = w.n_surv; h0.cap_surv = w.cap_surv0; h0.accum = w.accum0;
     h0.bs = w.bs0; h0.n_bs = w.n_bs; h0.cap_bs = w.cap_bs0; h0.ray_count = w.ray_count0; h0.cap_rays = w.cap_rays0;
-    h0.owner = w.owner0; h0.error = w.error;
+    h0.owner = w.owner0; h0.error = w.error; h0.red = w.red0;
     k_shade<0><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h0);
     CKL();
     prof_mark(2, stream);
@@ -1391,11 +1397,11 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
       CKL();
       prof_mark(8, stream);
     }
-    IncomingArgs ia = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.rgb1, s.max_retrace, w.accum0, w.tile_start0, nc};
+    IncomingArgs ia = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.rgb1, s.max_retrace, w.accum0, w.tile_start0, nc, w.red0};
     k_incoming<<<sm_count() * 8, MLP_THREADS, 0, stream>>>(s, ia);
     CKL();
     prof_mark(9, stream);
-    ReduceArgs r0 = {w.bs0, w.n_bs, w.cap_bs0, w.accum0};
+    ReduceArgs r0 = {w.red0, w.n_bs, w.cap_bs0, w.accum0};
     k_reduce0<<<sm_count() * 4, 256, 0, stream>>>(r0);
     CKL();
     prof_mark(10, stream);

@@ -104,20 +104,28 @@ struct TcMlp {
 };
 
 // Called by all 128 threads once per CTA.  w0u / w1u / w2u: fp16 weights already in the canonical operand layout
-// (scene.py: [K/8][rows][8] halves, biases folded into column TC_ONE, K zero-padded to 80).
+// (scene.py: [K/8][rows][8] halves, biases folded into column TC_ONE, K zero-padded to 80), 16-byte aligned.
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tc_bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tc_mlp_init(TcMlp& c, void* sm_, const void* w0u, const void* w1u, const void* w2u) {
   char* sm = (char*)sm_;
   c.sm = sm;
-  c.phase = 0;
   const int tid = threadIdx.x;
-  for (int i = tid; i < TC_W_BYTES / 16; i += TC_ROWS) {
-    ((uint4*)(sm + TC_OFF_W0))[i] = __ldg((const uint4*)w0u + i);
-    ((uint4*)(sm + TC_OFF_W1))[i] = __ldg((const uint4*)w1u + i);
-  }
-  for (int i = tid; i < TC_W2_BYTES / 16; i += TC_ROWS) ((uint4*)(sm + TC_OFF_W2))[i] = __ldg((const uint4*)w2u + i);
+  const uint32_t bar = tc_smem_u32(sm + TC_OFF_BAR);
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(sm + TC_OFF_BAR)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the three weight tiles arrive by TMA (no register staging, written through the async proxy the MMAs read with);
+    // they complete phase 0 of the barrier that later counts the MMA commits
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * TC_W_BYTES + TC_W2_BYTES))
+                 : "memory");
+    tc_bulk_load(tc_smem_u32(sm + TC_OFF_W0), w0u, TC_W_BYTES, bar);
+    tc_bulk_load(tc_smem_u32(sm + TC_OFF_W1), w1u, TC_W_BYTES, bar);
+    tc_bulk_load(tc_smem_u32(sm + TC_OFF_W2), w2u, TC_W2_BYTES, bar);
   }
   if (tid < 32) {   // one warp allocates the accumulator columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(sm + TC_OFF_TMEM)),
@@ -125,10 +133,11 @@ __device__ __forceinline__ void tc_mlp_init(TcMlp& c, void* sm_, const void* w0u
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  tc_fence_async_smem();      // the weight tiles were written through the generic proxy
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();        // barrier initialised and TMEM address published before anyone waits / reads
   tc_fence_after();
+  tc_wait(bar, 0);        // weights have landed
+  c.phase = 1;
   c.tmem = *(volatile uint32_t*)(sm + TC_OFF_TMEM);
 }
 __device__ __forceinline__ void tc_mlp_free(TcMlp& c) {
