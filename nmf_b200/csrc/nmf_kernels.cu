@@ -597,8 +597,14 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       fq[4] = make_float4(fr.T2.y, fr.T2.z, fr.a, s1);
       fq[5] = make_float4(s2, 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_U), 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_V), 0.f);
       // appearance feature + noise (microfacet.py:297, keyed Box-Muller), one feature per trip of a rolled loop
+      const uint64_t nseed = nmf_noise_seed(skey);
 #pragma unroll 1
-      for (int i = 0; i < 24; ++i) fs[i] += s.anoise * nmf_normal(skey, NMF_STREAM_NOISE0 + i, NMF_STREAM_NOISE_B + i);
+      for (int i = 0; i < 12; ++i) {
+        float n0, n1;
+        nmf_noise_pair(nseed, (uint32_t)i, &n0, &n1);
+        fs[2 * i] += s.anoise * n0;
+        fs[2 * i + 1] += s.anoise * n1;
+      }
 #pragma unroll
       for (int i = 0; i < 6; ++i) *(float4*)(b->feat + 4 * i) = make_float4(fs[4 * i], fs[4 * i + 1], fs[4 * i + 2], fs[4 * i + 3]);
     }

@@ -58,6 +58,30 @@ NMF_HD float nmf_normal(uint64_t key, uint32_t sa, uint32_t sb) {
 #endif
 }
 
+// Appearance-feature noise (models/microfacet.py:297: 24 standard normals per shaded sample).  One 64-bit mix per sample
+// seeds two 32-bit counters; pair p (features 2p, 2p+1) hashes them with the murmur3 finaliser and uses BOTH outputs of
+// a Box-Muller transform -- a third of the integer work of 24 independent splitmix64 streams (oracle/keyed_rng.py).
+NMF_HD uint32_t nmf_fmix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+NMF_HD uint64_t nmf_noise_seed(uint64_t sample_key) { return nmf_mix64(sample_key, NMF_STREAM_NOISE0); }
+NMF_HD void nmf_noise_pair(uint64_t seed, uint32_t p, float* n0, float* n1) {
+  const uint32_t a = nmf_fmix32((uint32_t)seed + 0x9E3779B9u * (p + 1u));
+  const uint32_t b = nmf_fmix32((uint32_t)(seed >> 32) + 0x85EBCA6Bu * (p + 1u));
+  const float u1 = ((float)(a >> 8) + 1.0f) * 5.9604644775390625e-8f;      // (0, 1]
+  const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;               // [0, 1)
+  const float r = sqrtf(-2.0f * logf(u1));
+#ifdef __CUDA_ARCH__
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+#else
+  const float sn = sinf(6.2831855f * u2), cs = cosf(6.2831855f * u2);
+#endif
+  *n0 = r * cs;
+  *n1 = r * sn;
+}
+
 // ------------------------------------------------------------------------------------------------
 // small vector helpers
 // ------------------------------------------------------------------------------------------------

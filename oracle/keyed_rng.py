@@ -12,7 +12,7 @@ depend on data (valid-sample count M, bounce counts ...).  Two sources are provi
   uniforms without any shape-dependent stream alignment.  The hash is the splitmix64 finaliser.
 
 Stream ids (must match nmf_rng.cuh):
-    0..23   appearance-feature noise, one stream per feature dim  (models/microfacet.py:297)
+    0       seed of the appearance-feature noise (24 normals per sample: noise24)  (models/microfacet.py:297)
     32      bounce-count jitter U                                  (modules/pt_selectors.py:10,12)
     33, 34  per-sample Sobol offset (u, v)                         (brdf_samplers/base.py:17)
     35      retrace tie-break U (keyed by bounce-ray key)          (models/microfacet.py:506)
@@ -66,6 +66,37 @@ def normal(key, stream_a, stream_b):
     return torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(np.float32(2 * np.pi) * u2)
 
 
+def fmix32(x):
+    """murmur3 32-bit finaliser (numpy uint32 arithmetic wraps mod 2^32)."""
+    x = np.asarray(x).astype(np.uint32)
+    with np.errstate(over="ignore"):
+        x = x ^ (x >> np.uint32(16))
+        x = x * np.uint32(0x85EBCA6B)
+        x = x ^ (x >> np.uint32(13))
+        x = x * np.uint32(0xC2B2AE35)
+        x = x ^ (x >> np.uint32(16))
+    return x
+
+
+def noise24(sample_keys_):
+    """(n, 24) standard normals per sample key: one splitmix64 mix seeds two 32-bit counters, feature pair p uses both
+    outputs of a Box-Muller transform of (fmix32(lo + c1 (p+1)), fmix32(hi + c2 (p+1)))  (nmf_math.cuh: nmf_noise_pair)."""
+    seed = mix64(sample_keys_, STREAM_NOISE0)
+    lo = (seed & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    hi = (seed >> np.uint64(32)).astype(np.uint32)
+    cols = []
+    with np.errstate(over="ignore"):
+        for p in range(12):
+            a = fmix32(lo + np.uint32(0x9E3779B9) * np.uint32(p + 1))
+            b = fmix32(hi + np.uint32(0x85EBCA6B) * np.uint32(p + 1))
+            u1 = torch.from_numpy(((a >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * np.float32(2.0 ** -24))
+            u2 = torch.from_numpy((b >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24))
+            r = torch.sqrt(-2.0 * torch.log(u1))
+            ang = np.float32(2 * np.pi) * u2
+            cols += [r * torch.cos(ang), r * torch.sin(ang)]
+    return torch.stack(cols, dim=1)
+
+
 def primary_ray_keys(seed, ray_ids):
     return mix64(np.uint64(seed), _u64(ray_ids))
 
@@ -109,8 +140,8 @@ class KeyedRNG:
     keyed = True
 
     def app_noise(self, feat, skeys):
-        cols = [normal(skeys, STREAM_NOISE0 + d, STREAM_NOISE_B + d) for d in range(feat.shape[1])]
-        return torch.stack(cols, dim=1)
+        assert feat.shape[1] == 24
+        return noise24(skeys).reshape(feat.shape)
 
     def head_noise(self, diffuse, r):
         pass

@@ -16,6 +16,13 @@ void hc_normal(const uint64_t* key, uint32_t sa, uint32_t sb, int n, float* out)
   for (int i = 0; i < n; ++i) out[i] = nmf_normal(key[i], sa, sb);
 }
 
+void hc_noise24(const uint64_t* key, int n, float* out) {
+  for (int i = 0; i < n; ++i) {
+    const uint64_t seed = nmf_noise_seed(key[i]);
+    for (uint32_t p = 0; p < 12; ++p) nmf_noise_pair(seed, p, out + 24 * i + 2 * p, out + 24 * i + 2 * p + 1);
+  }
+}
+
 // AlphaGridSampler.sample (eval): dense validity + z
 void hc_sample_rays(const NmfScene* s, const float* rays, int n, float near_override, uint8_t* valid, float* z) {
   const int S = s->n_steps;

@@ -38,6 +38,13 @@ def test_keyed_rng(hostcheck):
     n = torch.zeros(1000)
     hostcheck.hc_normal(a.ctypes.data_as(C.c_void_p), C.c_uint32(3), C.c_uint32(67), 1000, ptr(n))
     assert torch.allclose(n, KR.normal(a, 3, 67), atol=2e-6)
+    nz = torch.zeros(1000, 24)
+    hostcheck.hc_noise24(a.ctypes.data_as(C.c_void_p), 1000, ptr(nz))
+    ref = KR.noise24(a)
+    assert torch.allclose(nz, ref, atol=3e-6)
+    assert abs(float(ref.mean())) < 0.02 and abs(float(ref.std()) - 1.0) < 0.02          # 24 000 standard normals
+    c = torch.corrcoef(ref.T)
+    assert float((c - torch.eye(24)).abs().max()) < 0.15                                   # no cross-feature structure
 
 
 @pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_g56_ship", "plain_g64"])
