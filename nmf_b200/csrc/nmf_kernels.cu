@@ -60,7 +60,7 @@ struct WS {
   int* n_samples1;    // [n_chunks]
   int* n_cand;        // [n_chunks]
   int* n_sec;         // [n_chunks]
-  float* score_sum;   // [n_chunks]
+  unsigned long long* score_sum;   // [n_chunks] sum of the retrace scores in 2^-32 fixed point (order-independent)
   double* wsum1;      // [n_chunks]
   unsigned* error;    // [1]
   float* stat4;       // [n_chunks][4] A19 statistics: sum of w*min(v.n,0)^2, of the diffuse map, of the sample tints, of acc
@@ -105,7 +105,7 @@ static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base) {
   w.n_samples1 = (int*)take(nc * sizeof(int));
   w.n_cand = (int*)take(nc * sizeof(int));
   w.n_sec = (int*)take(nc * sizeof(int));
-  w.score_sum = (float*)take(nc * sizeof(float));
+  w.score_sum = (unsigned long long*)take(nc * sizeof(unsigned long long));
   w.wsum1 = (double*)take(nc * sizeof(double));
   w.error = (unsigned*)take(sizeof(unsigned));
   w.stat4 = (float*)take((size_t)nc * 4 * sizeof(float));
@@ -725,7 +725,7 @@ __device__ __forceinline__ void seg_sum3(float (&v)[3], const Seg& g, int lane) 
 
 struct BounceArgs {
   const BSample* bs; BRay* brays; const uint32_t* owner; const int* ray_count; int cap_rays;
-  float* score_sum; float2* scu;     // level 0: retrace scores
+  unsigned long long* score_sum; float2* scu;     // level 0: retrace scores
   float* accum1;                     // level 1: per retraced ray rgb accumulators [n_rays1][4]
   const int* tile_start;    // [n_chunks + 1] exclusive prefix of the chunks' 128-ray tile counts (k_tile_prefix)
   int n_chunks;
@@ -825,7 +825,8 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) sc += __shfl_xor_sync(FULL, sc, off);
-      if ((threadIdx.x & 31) == 0 && sc != 0.f) atomicAdd(a.score_sum + chunk, sc);
+      // integer atomics: the chunk total (and with it the retrace selection) does not depend on arrival order
+      if ((threadIdx.x & 31) == 0 && sc > 0.f) atomicAdd(a.score_sum + chunk, (unsigned long long)((double)sc * 4294967296.0));
     } else {
       // no further retrace at this depth: every bounce ray reads the environment (microfacet.py:561); the mean over
       // the rays of a sample (microfacet.py:565-613) is a segmented warp reduction, weighted into the retraced ray's
@@ -861,7 +862,7 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
 // ================================================================================================
 struct SelectArgs {
   const BSample* bs; BRay* brays; const uint32_t* owner; float2* scu; const int* ray_count; int cap_rays;
-  const float* score_sum; int max_retrace; int* n_sec;
+  const unsigned long long* score_sum; int max_retrace; int* n_sec;
   float* rays1; float* mip1; uint64_t* key1;
 };
 
@@ -875,7 +876,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
   if (n_re == 0) return;
   BRay* region = a.brays + (size_t)chunk * a.cap_rays;
   float2* scu = a.scu + (size_t)chunk * a.cap_rays;
-  const float total = a.score_sum[chunk];
+  const float total = (float)((double)a.score_sum[chunk] * (1.0 / 4294967296.0));
   const int lane = threadIdx.x & 31;
   // pass 0: final score = cc / sum * n_re + U(ray key)   (microfacet.py:504-506); histogram of its top 11 bits.
   // The scores crowd into a handful of exponent bins, so equal bins of a warp are merged into one shared atomic.

@@ -47,10 +47,11 @@ def test_whole_image_counters_are_consistent(full):
     for c in (0, nc - 1):
         assert abs(st["statistics"][c]["prediction_loss"] - 2 * float(acc[c * CHUNK:(c + 1) * CHUNK].double().sum())) < 1e-2
         assert all(math.isfinite(v) for v in st["statistics"][c].values())
-    # a second render of the same rays: identical up to the order of float atomics
-    again, _ = ops.render_rays(dsc, rays.cuda(), focal, chunk=CHUNK, seed=1)
-    assert torch.equal(again["surf_width"], ims["surf_width"])
-    assert (again["rgb_map"] - ims["rgb_map"]).abs().max() < 1e-4
+    # a second render of the same rays: same selections (integer score totals), pixels equal up to float-atomic order
+    first = {k: v.clone() for k, v in ims.items()}
+    again, st2 = ops.render_rays(dsc, rays.cuda(), focal, chunk=CHUNK, seed=1)
+    assert torch.equal(again["surf_width"], first["surf_width"]) and st2["n_samples1"] == st["n_samples1"]
+    assert (again["rgb_map"] - first["rgb_map"]).abs().max() < 2e-5
 
 
 def test_sharding_and_ray_order_do_not_change_the_image(full):
