@@ -1341,7 +1341,11 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
   if (s.model == 0) {
     const bool tcm = s.mlp_mode == 0;
     const size_t mlp_smem = tcm ? (size_t)TC_SMEM_BYTES : MLP_SMEM_FLOATS * sizeof(float);
-    static bool attr_done = false;
+    // opt-in shared-memory sizes are a per-device function attribute: set them once per device of this process
+    static unsigned long long attr_done_mask = 0;
+    int dev_id = 0;
+    CK(cudaGetDevice(&dev_id));
+    const bool attr_done = (attr_done_mask >> (dev_id & 63)) & 1ull;
     if (!attr_done) {
       CK(cudaFuncSetAttribute(k_shade<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SHADE_SMEM_FLOATS * sizeof(float))));
       CK(cudaFuncSetAttribute(k_shade<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SHADE_SMEM_FLOATS * sizeof(float))));
@@ -1349,7 +1353,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
       CK(cudaFuncSetAttribute(k_bounce<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MLP_SMEM_FLOATS * sizeof(float))));
       CK(cudaFuncSetAttribute(k_bounce<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
       CK(cudaFuncSetAttribute(k_bounce<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-      attr_done = true;
+      attr_done_mask |= 1ull << (dev_id & 63);
     }
     ShadeArgs h0 = {};
     h0.rays = rays; h0.tmin = w.tmin0; h0.seed = rp->seed; h0.ray_id0 = rp->ray_id0; h0.group = rp->chunk;

@@ -218,3 +218,32 @@ def test_missing_and_empty_inputs(case):
     assert torch.equal(ims["surf_width"].cpu(), torch.zeros(7, dtype=torch.int64))
     assert torch.allclose(ims["rgb_map"], torch.ones(7, 3, device="cuda"))
     assert torch.equal(ims["termination_xyz"].cpu(), torch.zeros(7, 4))
+
+
+def test_render_call_is_cuda_graph_capturable(case):
+    """The C ABI promises a fixed launch sequence without host synchronisation (include/nmf_b200.h): capture one
+    nmf_render_rays call in a CUDA graph, replay it on new rays, compare with the eager call."""
+    from nmf_b200 import ops
+    fix, osc, dsc = case
+    rays = fix["rays"].cuda()
+    n = rays.shape[0]
+    bufs = ops.RenderBuffers(dsc, n, 128, ops.image_keys(dsc))
+    static_rays = rays.clone()
+    ops.render_rays(dsc, static_rays, fix["focal"], chunk=128, seed=2, buffers=bufs)          # warm-up (function attributes)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            ops.render_rays(dsc, static_rays, fix["focal"], chunk=128, seed=2, buffers=bufs, check_errors=False)
+    torch.cuda.current_stream().wait_stream(side)
+    static_rays.copy_(rays.flip(0))
+    graph.replay()
+    torch.cuda.synchronize()
+    got = {k: v.clone() for k, v in bufs.images.items()}
+    st = ops.read_counters(bufs, n, 128)
+    ref, st_ref = ops.render_rays(dsc, rays.flip(0).contiguous(), fix["focal"], chunk=128, seed=2)
+    assert st["n_samples"] == st_ref["n_samples"]
+    assert torch.equal(got["surf_width"][:n], ref["surf_width"])
+    assert (got["rgb_map"][:n] - ref["rgb_map"]).abs().max() < 2e-5
