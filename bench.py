@@ -326,7 +326,7 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": config_dict(a, n), "clocks": clk.summary(),
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
                     "ms_per_step": e2e_ms / a.steps},
-            "gpu_launches": 14 * a.steps, "roofline": roof,
+            "gpu_launches": 15 * a.steps, "roofline": roof,
             "samples": {"valid_primary": M0, "valid_secondary": M1, "candidates": cand, "shaded_primary": sh0,
                         "shaded_secondary": sh1, "bounce_rays0": sum(stats["n_bounce_rays0"]),
                         "bounce_rays1": sum(stats["n_bounce_rays1"]), "retraced": n1}}

@@ -41,7 +41,7 @@ struct __align__(16) BSample {
   float frame[24];
 };
 
-struct __align__(16) BRay {     // level-0 bounce ray (level-1 rays are reduced inside k_bounce<1> and never stored)
+struct __align__(16) BRay {     // bounce ray record handed from k_bounce to k_incoming
   float L[3]; float mip;
   float bw[3]; int slot;        // slot: index of the secondary ray that re-traces it, -1 = environment
 };
@@ -74,7 +74,7 @@ struct WS {
   Surv* surv0; BSample* bs0; BRay* brays0; uint32_t* owner0; float2* scu0;   // scu0: (retrace score, tie-break U) per ray
   // level 1
   float* rays1; float* mip1; uint64_t* key1; float* tmin1; float* acc1; int* nvalid1; float* accum1; float* rgb1;
-  Surv* surv1; BSample* bs1; uint32_t* owner1;
+  Surv* surv1; BSample* bs1; BRay* brays1; uint32_t* owner1;
   int n_chunks, n_rays1;
   int cap_surv0, cap_bs0, cap_rays0;   // cap_rays0: per chunk
   int cap_surv1, cap_bs1, cap_rays1;   // cap_rays1: per chunk
@@ -135,6 +135,7 @@ static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base) {
     w.rgb1 = (float*)take((size_t)w.n_rays1 * 4 * 4);
     w.surv1 = (Surv*)take((size_t)w.cap_surv1 * sizeof(Surv));
     w.bs1 = (BSample*)take((size_t)w.cap_bs1 * sizeof(BSample));
+    w.brays1 = (BRay*)take((size_t)nc * w.cap_rays1 * sizeof(BRay));
     w.owner1 = (uint32_t*)take((size_t)nc * w.cap_rays1 * 4);
   }
   w.total = off;
@@ -726,7 +727,6 @@ __device__ __forceinline__ void seg_sum3(float (&v)[3], const Seg& g, int lane) 
 struct BounceArgs {
   const BSample* bs; BRay* brays; const uint32_t* owner; const int* ray_count; int cap_rays;
   unsigned long long* score_sum; float2* scu;     // level 0: retrace scores
-  float* accum1;                     // level 1: per retraced ray rgb accumulators [n_rays1][4]
   const int* tile_start;    // [n_chunks + 1] exclusive prefix of the chunks' 128-ray tile counts (k_tile_prefix)
   int n_chunks;
 };
@@ -827,30 +827,13 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
       for (int off = 16; off > 0; off >>= 1) sc += __shfl_xor_sync(FULL, sc, off);
       // integer atomics: the chunk total (and with it the retrace selection) does not depend on arrival order
       if ((threadIdx.x & 31) == 0 && sc > 0.f) atomicAdd(a.score_sum + chunk, (unsigned long long)((double)sc * 4294967296.0));
-    } else {
-      // no further retrace at this depth: every bounce ray reads the environment (microfacet.py:561); the mean over
-      // the rays of a sample (microfacet.py:565-613) is a segmented warp reduction, weighted into the retraced ray's
-      // pixel (tensor_nerf.py:448-452) -- level-1 bounce rays never touch HBM
-      float comb[3] = {0.f, 0.f, 0.f};
-      if (active) {
-        float inc[3];
-        nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, g.L, mip, inc);
-        const float ch = fabsf(nmf_dot(V, g.H));
-        const float4 q3 = *(const float4*)b->f0, q4 = *(const float4*)b->diffuse;
-        const float F0 = nmf_fresnel(q3.x, ch), F1 = nmf_fresnel(q3.y, ch), F2 = nmf_fresnel(q3.z, ch);
-        comb[0] = F0 * inc[0] * bw[0] + (1.f - F0) * q4.x;                 // microfacet.py:585-600
-        comb[1] = F1 * inc[1] * bw[1] + (1.f - F1) * q4.y;
-        comb[2] = F2 * inc[2] * bw[2] + (1.f - F2) * q4.z;
-      }
-      const int lane = threadIdx.x & 31;
-      const uint32_t key = active ? slot : 0xFFFFFFFFu;
-      const Seg seg = seg_setup(key, lane);      // every lane takes part in the shuffles
-      seg_sum3(comb, seg, lane);
-      if (active && seg.head) {
-        const float sw = w / (float)count;
-        float* acc = a.accum1 + (size_t)b->ray * 4;
-        atomicAdd(acc, sw * comb[0]); atomicAdd(acc + 1, sw * comb[1]); atomicAdd(acc + 2, sw * comb[2]);
-      }
+    } else if (active) {
+      // no further retrace at this depth (microfacet.py:561): k_incoming<1> looks every ray up in the environment.
+      // (Doing the lookup here saved the 32-byte record but ran 15 % slower: this kernel sits at its register and
+      // shared-memory occupancy limit, the lookup kernel does not.)
+      BRay* o = region + r;
+      *(float4*)o->L = make_float4(g.L.x, g.L.y, g.L.z, mip);
+      *(float4*)o->bw = make_float4(bw[0], bw[1], bw[2], __int_as_float(-1));
     }
   }
   if (TC) tc_mlp_free(tc);
@@ -954,14 +937,16 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
 }
 
 // ================================================================================================
-// k_incoming (level 0): models/microfacet.py:549-613 -- incoming radiance of every primary bounce ray (re-traced
-// radiance or environment lookup), Fresnel mix, and the per-sample sums over the rays (segmented warp reduction):
-// spec / tint debug maps go straight to the pixel accumulators, the combined radiance to the sample's rgbsum
+// k_incoming: models/microfacet.py:549-613 -- incoming radiance of every bounce ray (level 0: re-traced radiance or
+// environment lookup; level 1: environment), Fresnel mix, and the per-sample sums over the rays as segmented warp
+// reductions.  Level 0: spec / tint debug maps go straight to the pixel accumulators, the combined radiance to the
+// sample's reduction record.  Level 1: the mean radiance of the sample is weighted straight into its retraced ray.
 // ================================================================================================
 struct IncomingArgs {
   const BSample* bs; const BRay* brays; const uint32_t* owner; const int* ray_count; int cap_rays; const float* rgb1; int max_retrace;
   float* accum; const int* tile_start; int n_chunks; float4* red;
 };
+template <int LEVEL>
 __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, const IncomingArgs a) {
   const int n_tiles = a.tile_start[a.n_chunks];
   const int lane = threadIdx.x & 31;
@@ -981,7 +966,7 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
     if (active) {
       const BRay* o = a.brays + (size_t)chunk * a.cap_rays + r;
       const float4 q0 = *(const float4*)o->L, q1 = *(const float4*)o->bw;
-      const int slot = __float_as_int(q1.w);
+      const int slot = LEVEL == 0 ? __float_as_int(q1.w) : -1;
       key = a.owner[(size_t)chunk * a.cap_rays + r];
       b = a.bs + key;
       const nmf_v3 L = nmf_mk3(q0.x, q0.y, q0.z);
@@ -1002,19 +987,29 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
     }
     const Seg seg = seg_setup(key, lane);        // every lane takes part in the shuffles
     seg_sum3(comb, seg, lane);
-    seg_sum3(inc, seg, lane);
-    seg_sum3(bw, seg, lane);
+    if (LEVEL == 0) {
+      seg_sum3(inc, seg, lane);
+      seg_sum3(bw, seg, lane);
+    }
     if (active && seg.head) {
-      const float4 hdr = a.red[2 * (size_t)key], q5 = *(const float4*)b->fresn;      // {w, count, ray, flags}
-      const int cnt = max(__float_as_int(hdr.y), 1);
-      const float sw = hdr.x / (float)cnt;
-      float* acc = a.accum + (size_t)__float_as_uint(hdr.z) * A_N;
-      float* rs = (float*)(a.red + 2 * (size_t)key + 1);
-      atomicAdd(rs, comb[0]); atomicAdd(rs + 1, comb[1]); atomicAdd(rs + 2, comb[2]);
-      atomicAdd(acc + A_SPEC, sw * inc[0]); atomicAdd(acc + A_SPEC + 1, sw * inc[1]); atomicAdd(acc + A_SPEC + 2, sw * inc[2]);
-      atomicAdd(acc + A_TINT, sw * q5.x * bw[0]); atomicAdd(acc + A_TINT + 1, sw * q5.y * bw[1]);
-      atomicAdd(acc + A_TINT + 2, sw * q5.z * bw[2]);
-      atomicAdd(acc + A_TINTU, (q5.x * bw[0] + q5.y * bw[1] + q5.z * bw[2]) / (float)cnt);   // brdf_reg
+      if (LEVEL == 0) {
+        const float4 hdr = a.red[2 * (size_t)key], q5 = *(const float4*)b->fresn;      // {w, count, ray, flags}
+        const int cnt = max(__float_as_int(hdr.y), 1);
+        const float sw = hdr.x / (float)cnt;
+        float* acc = a.accum + (size_t)__float_as_uint(hdr.z) * A_N;
+        float* rs = (float*)(a.red + 2 * (size_t)key + 1);
+        atomicAdd(rs, comb[0]); atomicAdd(rs + 1, comb[1]); atomicAdd(rs + 2, comb[2]);
+        atomicAdd(acc + A_SPEC, sw * inc[0]); atomicAdd(acc + A_SPEC + 1, sw * inc[1]); atomicAdd(acc + A_SPEC + 2, sw * inc[2]);
+        atomicAdd(acc + A_TINT, sw * q5.x * bw[0]); atomicAdd(acc + A_TINT + 1, sw * q5.y * bw[1]);
+        atomicAdd(acc + A_TINT + 2, sw * q5.z * bw[2]);
+        atomicAdd(acc + A_TINTU, (q5.x * bw[0] + q5.y * bw[1] + q5.z * bw[2]) / (float)cnt);   // brdf_reg
+      } else {
+        // tensor_nerf.py:448-452 at recur 1: sum_samples w * mean_rays(comb) into the retraced ray (its own index)
+        const float4 q0 = *(const float4*)b->pos, q2 = *(const float4*)b->N;
+        const float sw = q0.w / (float)max(__float_as_int(q2.w), 1);
+        float* acc = a.accum + (size_t)b->ray * 4;
+        atomicAdd(acc, sw * comb[0]); atomicAdd(acc + 1, sw * comb[1]); atomicAdd(acc + 2, sw * comb[2]);
+      }
     }
   }
 }
@@ -1368,7 +1363,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
     const int gb = sm_count() * (tcm ? 5 : 3);
     k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count0, w.cap_rays0, nc, w.tile_start0);
     CKL();
-    BounceArgs b0 = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.score_sum, w.scu0, nullptr, w.tile_start0, nc};
+    BounceArgs b0 = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.score_sum, w.scu0, w.tile_start0, nc};
     if (tcm) k_bounce<0, 1><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b0);
     else k_bounce<0, 0><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b0);
     CKL();
@@ -1398,9 +1393,12 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
       prof_mark(6, stream);
       k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count1, w.cap_rays1, nc, w.tile_start1);
       CKL();
-      BounceArgs b1 = {w.bs1, nullptr, w.owner1, w.ray_count1, w.cap_rays1, nullptr, nullptr, w.accum1, w.tile_start1, nc};
+      BounceArgs b1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr, nullptr, w.tile_start1, nc};
       if (tcm) k_bounce<1, 1><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b1);
       else k_bounce<1, 0><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b1);
+      CKL();
+      IncomingArgs i1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr, 0, w.accum1, w.tile_start1, nc, nullptr};
+      k_incoming<1><<<sm_count() * 8, MLP_THREADS, 0, stream>>>(s, i1);
       CKL();
       prof_mark(7, stream);
       k_finish1<<<(w.n_rays1 + 127) / 128, 128, 0, stream>>>(s, w.rays1, w.mip1, w.acc1, w.accum1, w.n_sec, s.max_retrace,
@@ -1409,7 +1407,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
       prof_mark(8, stream);
     }
     IncomingArgs ia = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.rgb1, s.max_retrace, w.accum0, w.tile_start0, nc, w.red0};
-    k_incoming<<<sm_count() * 8, MLP_THREADS, 0, stream>>>(s, ia);
+    k_incoming<0><<<sm_count() * 8, MLP_THREADS, 0, stream>>>(s, ia);
     CKL();
     prof_mark(9, stream);
     ReduceArgs r0 = {w.red0, w.n_bs, w.cap_bs0, w.accum0};
