@@ -1342,7 +1342,8 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
     g_march0 = resident_grid(k_march<0>, 256, 0); g_march1 = resident_grid(k_march<1>, 256, 0);
     g_inc0 = resident_grid(k_incoming<0>, MLP_THREADS, 0); g_inc1 = resident_grid(k_incoming<1>, MLP_THREADS, 0);
   }
-  k_march<0><<<min(g_march0, blocks_for(n, 8, 1 << 20)), 256, 0, stream>>>(s, m0);
+  // rays differ a lot in cost: several waves of small CTAs (a multiple of the resident count) balance better than one
+  k_march<0><<<min(4 * g_march0, blocks_for(n, 8, 1 << 20)), 256, 0, stream>>>(s, m0);
   CKL();
   prof_mark(1, stream);
 
@@ -1393,7 +1394,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
       m1.tmin = w.tmin1; m1.acc = w.acc1; m1.depth = nullptr; m1.termk = nullptr; m1.nvalid = w.nvalid1;
       m1.n_samples = w.n_samples1; m1.n_cand = w.n_cand; m1.wsum = w.wsum1;
       m1.surv = w.surv1; m1.n_surv = w.n_surv + 1; m1.cap_surv = w.cap_surv1; m1.error = w.error;
-      k_march<1><<<min(g_march1, blocks_for(w.n_rays1, 8, 1 << 20)), 256, 0, stream>>>(s, m1);
+      k_march<1><<<min(4 * g_march1, blocks_for(w.n_rays1, 8, 1 << 20)), 256, 0, stream>>>(s, m1);
       CKL();
       prof_mark(5, stream);
       ShadeArgs h1 = {};
