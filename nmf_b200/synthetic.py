@@ -101,32 +101,41 @@ def procedural_env_log_radiance(res, seed=0, base=-0.6):
 
 
 def make_scene(name="lego", grid_size=300, bg_resolution=512, n_density=16, n_app=24, app_dim=24,
-               amp=40.0, env="procedural", aabb_scale=1.0):
-    """Returns (state, meta). ``state`` uses reference checkpoint keys; ``meta`` holds aabb / near_far."""
+               amp=40.0, env="procedural", aabb_scale=1.0, full_density=False):
+    """Returns (state, meta). ``state`` uses reference checkpoint keys; ``meta`` holds aabb / near_far.
+    grid_size: an int (cubic) or (gx, gy, gz); full_density adds small random values to EVERY density factor (the
+    blobs only use plane 0 / line 0), so that all three plane/line pairs take part in density and normals."""
     seed = DATASET_SEED.get(name, 0)
     g = torch.Generator().manual_seed(seed)
-    G = int(grid_size)
+    gs = [int(grid_size)] * 3 if isinstance(grid_size, int) else [int(v) for v in grid_size]
     aabb = torch.tensor([[-1.5, -1.5, -1.5], [1.5, 1.5, 1.5]]) * aabb_scale
-    lin = torch.linspace(-1, 1, G)
+    lins = [torch.linspace(-1, 1, n) for n in gs]
+    mat, vec = [[0, 1], [0, 2], [1, 2]], [2, 1, 0]          # fields/tensoRF.py:40-41: plane p is (H = grid[mat1], W = grid[mat0])
     state = {}
-    dplanes = [torch.zeros(1, n_density, G, G) for _ in range(3)]
-    dlines = [torch.zeros(1, n_density, G, 1) for _ in range(3)]
+    dplanes = [torch.zeros(1, n_density, gs[mat[p][1]], gs[mat[p][0]]) for p in range(3)]
+    dlines = [torch.zeros(1, n_density, gs[vec[p]], 1) for p in range(3)]
     dplanes[0][0, 0] = -10.0
     dlines[0][0, 0] = 1.0
     for k, (kind, c, s) in enumerate(_blob_layout(seed)):
         if kind == "gauss":
-            fx, fy, fz = _gauss(lin, c[0], s), _gauss(lin, c[1], s), _gauss(lin, c[2], s)
+            fx, fy, fz = _gauss(lins[0], c[0], s), _gauss(lins[1], c[1], s), _gauss(lins[2], c[2], s)
         else:
-            fx, fy, fz = (_box(lin, c[0] - s, c[0] + s), _box(lin, c[1] - s, c[1] + s),
-                          _box(lin, c[2] - s, c[2] + s))
+            fx, fy, fz = (_box(lins[0], c[0] - s, c[0] + s), _box(lins[1], c[1] - s, c[1] + s),
+                          _box(lins[2], c[2] - s, c[2] + s))
         # plane 0 = (x -> W, y -> H), line 0 = z   (fields/tensoRF.py:40-41,161-179)
-        dplanes[0][0, k + 1] = amp * fy.view(G, 1) * fx.view(1, G)
+        dplanes[0][0, k + 1] = amp * fy.view(-1, 1) * fx.view(1, -1)
         dlines[0][0, k + 1, :, 0] = fz
     for i in range(3):
         state[f"rf.density_rf.app_plane.{i}"] = dplanes[i]
         state[f"rf.density_rf.app_line.{i}"] = dlines[i]
-        state[f"rf.app_rf.app_plane.{i}"] = 0.1 * torch.randn(1, n_app, G, G, generator=g)
-        state[f"rf.app_rf.app_line.{i}"] = 0.1 * torch.randn(1, n_app, G, 1, generator=g)
+        state[f"rf.app_rf.app_plane.{i}"] = 0.1 * torch.randn(1, n_app, gs[mat[i][1]], gs[mat[i][0]], generator=g)
+        state[f"rf.app_rf.app_line.{i}"] = 0.1 * torch.randn(1, n_app, gs[vec[i]], 1, generator=g)
+    if full_density:
+        for i in range(3):
+            # components 6..15 are unused by the blobs: products of O(0.6) factors bend the density of the blobs'
+            # surfaces (and their normals) through all three plane/line pairs without filling empty space
+            dplanes[i][0, 6:] = 0.6 * torch.randn(dplanes[i][0, 6:].shape, generator=g)
+            dlines[i][0, 6:] = 0.6 * torch.randn(dlines[i][0, 6:].shape, generator=g)
     state["rf.basis_mat.weight"] = _linear_default(app_dim, 3 * n_app, g)
     state["rf.dbasis_mat.weight"] = _linear_default(1, 3 * n_density, g)
     for head, od in (("diffuse", 3), ("tint", 3), ("f0", 3), ("roughness", 2)):
@@ -146,7 +155,7 @@ def make_scene(name="lego", grid_size=300, bg_resolution=512, n_density=16, n_ap
     state["bg_module.mipbias"] = torch.tensor(1.0, dtype=torch.float64)
     state["bg_module.brightness"] = torch.tensor(0.0, dtype=torch.float64)
     state["bg_module.mul"] = torch.tensor(1.0, dtype=torch.float64)
-    meta = dict(name=name, aabb=aabb, near_far=DATASET_NEAR_FAR.get(name, (2.0, 6.0)), grid_size=[G, G, G],
+    meta = dict(name=name, aabb=aabb, near_far=DATASET_NEAR_FAR.get(name, (2.0, 6.0)), grid_size=list(gs),
                 bg_resolution=bg_resolution)
     return state, meta
 

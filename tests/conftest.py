@@ -18,18 +18,23 @@ def load_fixture(name):
     return torch.load(os.path.join(GOLDEN, f"{name}.pt"), weights_only=False)
 
 
+def grid_of(fix):
+    g = fix["grid_size"]
+    return [g] * 3 if isinstance(g, int) else list(g)
+
+
 def oracle_scene(fix):
     """oracle.nmf_oracle.Scene of a golden fixture (test side only)."""
     from oracle import nmf_oracle
     model = "microfacet" if fix["model"] == "microfacet_tensorf2" else "plain"
-    return nmf_oracle.Scene(fix["state"], fix["aabb"], fix["near_far"], [fix["grid_size"]] * 3,
+    return nmf_oracle.Scene(fix["state"], fix["aabb"], fix["near_far"], grid_of(fix),
                             alpha_volume=fix["alpha_volume"].float(), model=model)
 
 
 def device_scene(fix, device, **kw):
     from nmf_b200.scene import DeviceScene
     model = "microfacet" if fix["model"] == "microfacet_tensorf2" else "plain"
-    return DeviceScene(fix["state"], fix["aabb"], fix["near_far"], [fix["grid_size"]] * 3,
+    return DeviceScene(fix["state"], fix["aabb"], fix["near_far"], grid_of(fix),
                        alpha_volume=fix["alpha_volume"], device=device, model=model, **kw)
 
 

@@ -98,7 +98,7 @@ def test_checkpoint_reload_and_env_swap(model, tmp_path):
     bg_path = str(tmp_path / "env.th")
     torch.save(env.state_dict(), bg_path)
     relight.swap_env(t2, bg_path)
-    assert t2.bg_module.bg_resolution == 48 and float(t2.bg_module.mipbias) == 0.5
+    assert t2.bg_module.bg_resolution == 48 and float(t2.bg_module.mipbias.detach()) == 0.5
     rays = fix["rays"][:128].cuda()
     t.seed = t2.seed = 9
     a, _ = t.render_chunks(rays, fix["focal"], chunk=128)

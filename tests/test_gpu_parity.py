@@ -23,7 +23,7 @@ def env():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(scope="module", params=["microfacet_g40", "microfacet_g56_ship"])
+@pytest.fixture(scope="module", params=["microfacet_g40", "microfacet_g56_ship", "microfacet_noncubic"])
 def case(request, env):
     from oracle import nmf_oracle as O
     fix = load_fixture(request.param)

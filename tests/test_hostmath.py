@@ -17,9 +17,9 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-@pytest.fixture(scope="module")
-def scenes():
-    fix = load_fixture("microfacet_g40")
+@pytest.fixture(scope="module", params=["microfacet_g40", "microfacet_noncubic"])
+def scenes(request):
+    fix = load_fixture(request.param)
     osc = oracle_scene(fix)
     dsc = device_scene(fix, "cpu", sh_conv=O.sh_irradiance_coeffs(osc))
     return fix, osc, dsc
@@ -47,7 +47,7 @@ def test_keyed_rng(hostcheck):
     assert float((c - torch.eye(24)).abs().max()) < 0.15                                   # no cross-feature structure
 
 
-@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_g56_ship", "plain_g64"])
+@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_g56_ship", "plain_g64", "microfacet_noncubic"])
 def test_sampler_mask_bit_exact(hostcheck, name):
     fix = load_fixture(name)
     osc = oracle_scene(fix)
@@ -69,13 +69,14 @@ def test_sampler_mask_bit_exact(hostcheck, name):
 def test_sampler_mask_on_lattice_points(hostcheck, scenes):
     """rays that run exactly along lattice planes (zero trilinear weights) and axis-parallel rays"""
     fix, osc, dsc = scenes
-    G = fix["grid_size"]
-    lin = torch.linspace(-1.5, 1.5, G)
+    from conftest import grid_of
+    gx, gy, gz = grid_of(fix)
+    lx, ly, lz = (torch.linspace(-1.5, 1.5, g) for g in (gx, gy, gz))
     rays = []
-    for i in range(0, G, 3):
-        rays.append([float(lin[i]), -4.0, float(lin[(i * 7) % G]), 0.0, 1.0, 0.0])
-        rays.append([-4.0, float(lin[i]), float(lin[(i * 5) % G]), 1.0, 0.0, 0.0])
-        rays.append([float(lin[i]), float(lin[(i * 3) % G]), 4.0, 0.0, 0.0, -1.0])
+    for i in range(0, min(gx, gy, gz), 3):
+        rays.append([float(lx[i]), -4.0, float(lz[(i * 7) % gz]), 0.0, 1.0, 0.0])
+        rays.append([-4.0, float(ly[i]), float(lz[(i * 5) % gz]), 1.0, 0.0, 0.0])
+        rays.append([float(lx[i]), float(ly[(i * 3) % gy]), 4.0, 0.0, 0.0, -1.0])
     rays = torch.tensor(rays)
     _, valid, z, _ = O.sample_rays(osc, rays, fix["focal"])
     v = torch.zeros(rays.shape[0], osc.n_samples, dtype=torch.uint8)
