@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NMF_ABI_VERSION 3
+#define NMF_ABI_VERSION 4
 
 #define NMF_OK 0
 #define NMF_E_ARG (-1)          /* null pointer / non-positive size                                   */
@@ -133,6 +133,8 @@ typedef struct NmfRender {
   float skip_eps;          /* shade a sample only if w >= skip_eps / n_valid(ray); 0 = shade every valid sample */
   float t_cut;             /* stop evaluating density once transmittance < t_cut; 0 = never */
   int white_bg;            /* 1: primary background is white (tensor_nerf.py:215,478) */
+  float cap_scale;         /* scales the capacities of the scratch lists (0 = 1.0).  A scene that overflows one of them
+                            * (NmfCounters.error) is re-rendered with a larger scale and nmf_workspace_bytes_scaled() */
 } NmfRender;
 
 /* outputs of one TensorNeRF.forward in eval mode (modules/tensor_nerf.py:448-566, 657-673); any pointer may be NULL */
@@ -180,8 +182,9 @@ int nmf_profile_enable(int on);
 int nmf_profile_read(float* ms, int n);
 const char* nmf_profile_phase_name(int i);
 
-/* Bytes of scratch nmf_render_rays needs for `n_rays` rays in chunks of `chunk`. */
+/* Bytes of scratch nmf_render_rays needs for `n_rays` rays in chunks of `chunk` (NmfRender.cap_scale = 1 / as given). */
 size_t nmf_workspace_bytes(const NmfScene* scene, int n_rays, int chunk);
+size_t nmf_workspace_bytes_scaled(const NmfScene* scene, int n_rays, int chunk, float cap_scale);
 
 /* The fused path: replaces renderer.chunk_renderer (renderer.py:56-106) + TensorNeRF.forward
  * (modules/tensor_nerf.py:210-674) in eval mode for all chunks of `rays` at once.

@@ -45,7 +45,7 @@ class NmfRender(C.Structure):
     _fields_ = [
         ("n_rays", C.c_int), ("chunk", C.c_int), ("focal", C.c_float),
         ("seed", C.c_uint64), ("ray_id0", C.c_uint64),
-        ("skip_eps", C.c_float), ("t_cut", C.c_float), ("white_bg", C.c_int),
+        ("skip_eps", C.c_float), ("t_cut", C.c_float), ("white_bg", C.c_int), ("cap_scale", C.c_float),
     ]
 
 
@@ -65,6 +65,10 @@ class NmfCounters(C.Structure):
 
 class NmfError(RuntimeError):
     pass
+
+
+class NmfOverflow(NmfError):
+    """A device-side scratch list was too small for the scene (NmfCounters.error): the render is incomplete."""
 
 
 _ERRORS = {-1: "NMF_E_ARG (null pointer or non-positive size)",
@@ -104,6 +108,7 @@ def lib():
         "nmf_profile_read": (I, [P, I]),
         "nmf_profile_phase_name": (C.c_char_p, [I]),
         "nmf_workspace_bytes": (C.c_size_t, [SP, I, I]),
+        "nmf_workspace_bytes_scaled": (C.c_size_t, [SP, I, I, F]),
         "nmf_render_rays": (I, [SP, RP, P, IP, CP, P, C.c_size_t, P]),
         "nmf_render_rays_host": (I, [SP, RP, P, P, IP, IP, CP, CP, P, C.c_size_t, P]),
         "nmf_sample_rays": (I, [SP, P, I, F, P, P, P, P]),
@@ -122,11 +127,11 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    assert L.nmf_abi_version() == 3, "libnmf_b200.so ABI mismatch: rebuild"
+    assert L.nmf_abi_version() == 4, "libnmf_b200.so ABI mismatch: rebuild"
     _lib = L
     return L
 
 
-EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_profile_phase_name", "nmf_workspace_bytes", "nmf_render_rays", "nmf_render_rays_host", "nmf_sample_rays",
+EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_profile_phase_name", "nmf_workspace_bytes", "nmf_workspace_bytes_scaled", "nmf_render_rays", "nmf_render_rays_host", "nmf_sample_rays",
             "nmf_vm_density", "nmf_vm_appfeature", "nmf_vm_normals", "nmf_env_lookup", "nmf_ggx_sample",
             "nmf_brdf_mlp", "nmf_material_heads", "nmf_dense_alpha", "nmf_generate_rays", "nmf_image_sq_error"]

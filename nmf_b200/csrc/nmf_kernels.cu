@@ -23,6 +23,7 @@
 #define NMF_BS0_PER_RAY 24         // bounce samples per primary ray (typical: 12)
 #define NMF_SURV1_PER_RAY 256      // per retraced ray
 #define NMF_BS1_PER_RAY 128
+#define NMF_NO_OWNER 0xFFFFFFFFu  // ray -> sample map entry of a ray whose sample could not be allocated (overflow)
 
 struct Surv { uint32_t ray; uint32_t step; float w; };
 
@@ -83,18 +84,20 @@ struct WS {
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base) {
+static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base, float cap_scale = 1.0f) {
+  const double cs = cap_scale > 0.f ? (double)cap_scale : 1.0;
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
   int nc = (n_rays + chunk - 1) / chunk;
   int maxre = s->model == 0 ? s->max_retrace : 0;
   w.n_chunks = nc;
   w.n_rays1 = nc * maxre;
-  w.cap_surv0 = n_rays * NMF_SURV0_PER_RAY;
-  w.cap_bs0 = n_rays * NMF_BS0_PER_RAY;
-  w.cap_rays0 = chunk * NMF_BRAY_CAP_PER_RAY;
-  w.cap_surv1 = w.n_rays1 * NMF_SURV1_PER_RAY;
-  w.cap_bs1 = w.n_rays1 * NMF_BS1_PER_RAY;
+  auto cap = [&](double items) { double v = items * cs; return (int)(v < 2.0e9 ? v : 2.0e9); };
+  w.cap_surv0 = cap((double)n_rays * NMF_SURV0_PER_RAY);
+  w.cap_bs0 = cap((double)n_rays * NMF_BS0_PER_RAY);
+  w.cap_rays0 = cap((double)chunk * NMF_BRAY_CAP_PER_RAY);
+  w.cap_surv1 = cap((double)w.n_rays1 * NMF_SURV1_PER_RAY);
+  w.cap_bs1 = cap((double)w.n_rays1 * NMF_BS1_PER_RAY);
   w.cap_rays1 = maxre > 0 ? s->max_brdf_rays1 + 1024 : 0;
   w.counters_base = take(0);
   w.n_surv = (int*)take(2 * sizeof(int));
@@ -527,8 +530,16 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       }
       if (count > 0) {
         slot = sbase + __popc(bm & lt);
-        if (slot >= a.cap_bs) { atomicOr(a.error, NMF_DEV_E_BSAMPLES); slot = -1; }
-        else if (roff + count > a.cap_rays) { atomicOr(a.error, NMF_DEV_E_BRAYS); slot = -1; }
+        if (slot >= a.cap_bs) {
+          atomicOr(a.error, NMF_DEV_E_BSAMPLES);
+          slot = -1;
+        } else if (roff + count > a.cap_rays) {
+          // the slot index is taken but its rays do not fit: leave an empty reduction record behind (every index
+          // below n_bs must be readable by k_reduce0) and drop the sample; the call reports the overflow
+          atomicOr(a.error, NMF_DEV_E_BRAYS);
+          if (LEVEL == 0) { a.red[2 * slot] = make_float4(0.f, 0.f, 0.f, 0.f); a.red[2 * slot + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+          slot = -1;
+        }
       }
     }
     BSample* b = a.bs + (slot >= 0 ? slot : 0);
@@ -609,15 +620,18 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
 #pragma unroll
       for (int i = 0; i < 6; ++i) *(float4*)(b->feat + 4 * i) = make_float4(fs[4 * i], fs[4 * i + 1], fs[4 * i + 2], fs[4 * i + 3]);
     }
-    // ray -> bounce-sample map of the allocated ranges, written by the whole warp
-    unsigned todo = __ballot_sync(FULL, slot >= 0);
+    // ray -> bounce-sample map of the allocated ranges, written by the whole warp.  A sample whose allocation failed
+    // (a list overflowed: the call reports an error) marks its rays with NMF_NO_OWNER so that no consumer follows a
+    // stale index.
+    unsigned todo = __ballot_sync(FULL, count > 0);
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const int c_cnt = __shfl_sync(FULL, count, src), c_slot = __shfl_sync(FULL, slot, src);
       const int c_roff = __shfl_sync(FULL, roff, src), c_chunk = __shfl_sync(FULL, chunk, src);
       uint32_t* ow = a.owner + (size_t)c_chunk * a.cap_rays + c_roff;
-      for (int j = lane; j < c_cnt; j += 32) ow[j] = (uint32_t)c_slot;
+      const int lim = min(c_cnt, a.cap_rays - c_roff);
+      for (int j = lane; j < lim; j += 32) ow[j] = c_slot >= 0 ? (uint32_t)c_slot : NMF_NO_OWNER;
     }
     __syncwarp();
   }
@@ -780,8 +794,10 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
     BRay* region = a.brays + (size_t)chunk * a.cap_rays;
     const uint32_t* owner = a.owner + (size_t)chunk * a.cap_rays;
     const int r = (tile - __ldg(a.tile_start + chunk)) * MLP_THREADS + threadIdx.x;
-    const bool active = r < n;
-    const uint32_t slot = active ? owner[r] : 0u;
+    uint32_t slot = r < n ? owner[r] : NMF_NO_OWNER;
+    const bool active = slot != NMF_NO_OWNER;
+    if (!active) slot = 0u;
+    if (LEVEL == 0 && r < n && !active) a.scu[(size_t)chunk * a.cap_rays + r] = make_float2(0.f, 0.f);
     const BSample* b = a.bs + slot;
     const int j = active ? r - (int)b->roff : 0;
     const float4 q0 = *(const float4*)b->pos, q1 = *(const float4*)b->V, q2 = *(const float4*)b->N;
@@ -920,7 +936,9 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
       const unsigned sl = atomicAdd(&sh_slot, 1u);
       if (sl < (unsigned)n_re) {
         BRay* o = region + r;
-        const BSample* b = a.bs + a.owner[(size_t)chunk * a.cap_rays + r];
+        const uint32_t own = a.owner[(size_t)chunk * a.cap_rays + r];
+        if (own == NMF_NO_OWNER) continue;                              // overflow case only
+        const BSample* b = a.bs + own;
         const float4 q = *(const float4*)o->L;
         const size_t gi = (size_t)chunk * a.max_retrace + sl;
         float* ry = a.rays1 + gi * 6;
@@ -959,15 +977,14 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
     const int chunk = lo;
     const int n = min(a.ray_count[chunk], a.cap_rays);
     const int r = (tile - __ldg(a.tile_start + chunk)) * MLP_THREADS + threadIdx.x;
-    const bool active = r < n;
+    uint32_t key = r < n ? a.owner[(size_t)chunk * a.cap_rays + r] : NMF_NO_OWNER;
+    const bool active = key != NMF_NO_OWNER;
     float comb[3] = {0.f, 0.f, 0.f}, inc[3] = {0.f, 0.f, 0.f}, bw[3] = {0.f, 0.f, 0.f};
-    uint32_t key = 0xFFFFFFFFu;
     const BSample* b = a.bs;
     if (active) {
       const BRay* o = a.brays + (size_t)chunk * a.cap_rays + r;
       const float4 q0 = *(const float4*)o->L, q1 = *(const float4*)o->bw;
       const int slot = LEVEL == 0 ? __float_as_int(q1.w) : -1;
-      key = a.owner[(size_t)chunk * a.cap_rays + r];
       b = a.bs + key;
       const nmf_v3 L = nmf_mk3(q0.x, q0.y, q0.z);
       if (slot >= 0) {
@@ -1023,6 +1040,7 @@ __global__ void __launch_bounds__(256) k_reduce0(const ReduceArgs a) {
   const int n = min(*a.n_bs, a.cap_bs);
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
     const float4 hdr = a.red[2 * (size_t)i], sum = a.red[2 * (size_t)i + 1];      // one 32-byte sector per sample
+    if (__float_as_int(hdr.y) <= 0) continue;                                       // dropped sample (overflow case only)
     const float w = hdr.x, inv = 1.0f / (float)__float_as_int(hdr.y);
     float* acc = a.accum + (size_t)__float_as_uint(hdr.z) * A_N;
     const bool below = __float_as_uint(hdr.w) & 1u;
@@ -1312,6 +1330,13 @@ extern "C" size_t nmf_workspace_bytes(const NmfScene* scene, int n_rays, int chu
   return w.total;
 }
 
+extern "C" size_t nmf_workspace_bytes_scaled(const NmfScene* scene, int n_rays, int chunk, float cap_scale) {
+  if (!scene || n_rays <= 0 || chunk <= 0) return 0;
+  WS w;
+  carve(w, scene, n_rays, chunk, nullptr, cap_scale);
+  return w.total;
+}
+
 extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const float* rays, const NmfImages* out,
                                const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream_) {
   int st = check_scene(scene);
@@ -1325,7 +1350,7 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
   if (s.model == 0 && s.max_retrace > 0 && s.max_brdf_rays1 <= 0) return NMF_E_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
   WS w;
-  carve(w, scene, rp->n_rays, rp->chunk, (char*)workspace);
+  carve(w, scene, rp->n_rays, rp->chunk, (char*)workspace, rp->cap_scale);
   if (w.total > workspace_bytes) return NMF_E_WORKSPACE;
   const int n = rp->n_rays, nc = w.n_chunks;
   CK(cudaMemsetAsync(w.counters_base, 0, w.counters_bytes, stream));

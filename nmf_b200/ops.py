@@ -150,9 +150,9 @@ def image_sq_error(rgb, gt, pixel_ids=None):
 class RenderBuffers:
     """Output images, counters and scratch for batches of up to `n_rays` rays (grow-only cache per scene)."""
 
-    def __init__(self, scene, n_rays, chunk, keys):
+    def __init__(self, scene, n_rays, chunk, keys, cap_scale=1.0):
         dev = scene.device
-        self.n_rays, self.chunk = n_rays, chunk
+        self.n_rays, self.chunk, self.cap_scale, self.keys = n_rays, chunk, float(cap_scale), list(keys)
         self.n_chunks = (n_rays + chunk - 1) // chunk
         self.images = {}
         self.c_images = _lib.NmfImages()
@@ -166,7 +166,7 @@ class RenderBuffers:
             n = 2 if k == "n_shaded" else (1 if k == "error" else (4 * self.n_chunks if k == "stat4" else self.n_chunks))
             self.counters[k] = torch.zeros(n, dtype=torch.float32 if k == "stat4" else torch.int32, device=dev)
             setattr(self.c_counters, k, self.counters[k].data_ptr())
-        nbytes = _lib.lib().nmf_workspace_bytes(scene.ref(), n_rays, chunk)
+        nbytes = _lib.lib().nmf_workspace_bytes_scaled(scene.ref(), n_rays, chunk, self.cap_scale)
         if nbytes == 0:
             raise _lib.NmfError("nmf_workspace_bytes: bad arguments")
         self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
@@ -187,16 +187,24 @@ def render_rays(scene, rays, focal, chunk=4096, seed=0, ray_id0=0, skip_eps=DEFA
     n = r.shape[0]
     if buffers is None or buffers.n_rays < n or buffers.chunk != chunk:
         buffers = RenderBuffers(scene, n, chunk, image_keys(scene))
-    rp = _lib.NmfRender(n_rays=n, chunk=chunk, focal=float(focal), seed=int(seed), ray_id0=int(ray_id0),
-                        skip_eps=float(skip_eps), t_cut=float(t_cut), white_bg=1)
-    st = _lib.lib().nmf_render_rays(scene.ref(), C.byref(rp), _p(r), C.byref(buffers.c_images), C.byref(buffers.c_counters),
-                                    C.c_void_p(buffers.ws_ptr), buffers.ws_bytes, _stream())
-    _lib.check(st, "nmf_render_rays")
-    images = {k: v[:n] for k, v in buffers.images.items()}
-    stats = dict(buffers=buffers)
-    if check_errors:
-        stats.update(read_counters(buffers, n, chunk))
-    return images, stats
+    while True:
+        rp = _lib.NmfRender(n_rays=n, chunk=chunk, focal=float(focal), seed=int(seed), ray_id0=int(ray_id0),
+                            skip_eps=float(skip_eps), t_cut=float(t_cut), white_bg=1, cap_scale=buffers.cap_scale)
+        st = _lib.lib().nmf_render_rays(scene.ref(), C.byref(rp), _p(r), C.byref(buffers.c_images), C.byref(buffers.c_counters),
+                                        C.c_void_p(buffers.ws_ptr), buffers.ws_bytes, _stream())
+        _lib.check(st, "nmf_render_rays")
+        images = {k: v[:n] for k, v in buffers.images.items()}
+        stats = dict(buffers=buffers)
+        if not check_errors:
+            return images, stats
+        try:
+            stats.update(read_counters(buffers, n, chunk))
+            return images, stats
+        except _lib.NmfOverflow:
+            # a scratch list was too small for this scene (results would be incomplete): grow and render again
+            if buffers.cap_scale >= 16:
+                raise
+            buffers = RenderBuffers(scene, max(n, buffers.n_rays), chunk, buffers.keys, cap_scale=buffers.cap_scale * 2)
 
 
 def read_counters(buffers, n, chunk):
@@ -206,7 +214,7 @@ def read_counters(buffers, n, chunk):
     err = int(c["error"][0])
     if err:
         msgs = [m for bit, m in _lib.DEV_ERRORS.items() if err & bit]
-        raise _lib.NmfError("nmf_render_rays: " + "; ".join(msgs) + " (render fewer rays per call)")
+        raise _lib.NmfOverflow("nmf_render_rays: " + "; ".join(msgs))
     out = {k: c[k][:nc].tolist() for k in ("n_samples0", "n_samples1", "n_cand", "n_bounce_rays0", "n_bounce_rays1", "n_retrace")}
     out["n_shaded"] = c["n_shaded"].tolist()
     out["n_samples"] = [[a, b] for a, b in zip(out["n_samples0"], out["n_samples1"])]

@@ -515,6 +515,7 @@ class TensorNeRF(nn.Module):
             self._bufs = ops.RenderBuffers(sc, n, chunk, ops.image_keys(sc))
         ims, st = ops.render_rays(sc, rays.to(self.get_device()), focal, chunk=chunk, seed=self.seed, ray_id0=ray_id0,
                                   skip_eps=self.skip_eps, t_cut=self.t_cut, buffers=self._bufs)
+        self._bufs = st["buffers"]            # grown if a scratch list overflowed
         stats = dict(recur=0, whole_valid=torch.ones(n, dtype=torch.bool, device=rays.device),
                      n_samples=st["n_samples"], n_retrace=st["n_retrace"])
         # A19 (modules/tensor_nerf.py:567-649): per-chunk regulariser inputs, one list entry per reference forward call

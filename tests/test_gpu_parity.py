@@ -247,3 +247,21 @@ def test_render_call_is_cuda_graph_capturable(case):
     assert st["n_samples"] == st_ref["n_samples"]
     assert torch.equal(got["surf_width"][:n], ref["surf_width"])
     assert (got["rgb_map"][:n] - ref["rgb_map"]).abs().max() < 2e-5
+
+
+def test_scratch_overflow_is_detected_and_buffers_regrow(case):
+    """Undersized scratch lists must never truncate a render silently: the device flags the overflow, the host
+    raises NmfOverflow, and ops.render_rays re-renders with larger lists."""
+    from nmf_b200 import _lib, ops
+    fix, osc, dsc = case
+    rays = fix["rays"].cuda()
+    n = rays.shape[0]
+    ref, _ = ops.render_rays(dsc, rays, fix["focal"], chunk=128, seed=8)
+    ref = {k: v.clone() for k, v in ref.items()}
+    small = ops.RenderBuffers(dsc, n, 128, ops.image_keys(dsc), cap_scale=0.02)
+    ops.render_rays(dsc, rays, fix["focal"], chunk=128, seed=8, buffers=small, check_errors=False)
+    with pytest.raises(_lib.NmfOverflow):
+        ops.read_counters(small, n, 128)
+    ims, st = ops.render_rays(dsc, rays, fix["focal"], chunk=128, seed=8, buffers=small)
+    assert st["buffers"].cap_scale > small.cap_scale
+    assert torch.equal(ims["surf_width"], ref["surf_width"]) and (ims["rgb_map"] - ref["rgb_map"]).abs().max() < 2e-5
