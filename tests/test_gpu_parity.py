@@ -265,3 +265,38 @@ def test_scratch_overflow_is_detected_and_buffers_regrow(case):
     ims, st = ops.render_rays(dsc, rays, fix["focal"], chunk=128, seed=8, buffers=small)
     assert st["buffers"].cap_scale > small.cap_scale
     assert torch.equal(ims["surf_width"], ref["surf_width"]) and (ims["rgb_map"] - ref["rgb_map"]).abs().max() < 2e-5
+
+
+HP_VARIANTS = {
+    "no_retrace": dict(max_retrace_rays=()),                                           # every bounce ray reads the environment
+    "few_rays": dict(rays_per_ray=32, max_retrace_rays=(50,), max_brdf_rays=(650000, 40000)),
+    "budget_exhausted": dict(rays_per_ray=64, max_retrace_rays=(200,), max_brdf_rays=(650000, 1500)),   # N <= 0 branch of pt_selectors.py:41-57
+    "biases": dict(diffuse_bias=0.3, roughness_bias=0.5, f0_bias=-1.0, brdf_bias=0.7, anoise=0.0),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(HP_VARIANTS))
+def test_hyper_parameter_variants_match_oracle(env, variant):
+    """The model hyper-parameters of configs/model/microfacet_tensorf2.yaml that change the control flow of the path
+    (retrace depth, bounce budgets, calibration biases) against the oracle with the same settings."""
+    from conftest import grid_of
+    from nmf_b200 import ops
+    from oracle import keyed_rng as KR
+    from oracle import nmf_oracle as O
+    hp = HP_VARIANTS[variant]
+    fix = load_fixture("microfacet_g56_ship")
+    osc = O.Scene(fix["state"], fix["aabb"], fix["near_far"], grid_of(fix), alpha_volume=fix["alpha_volume"].float(), **hp)
+    dsc = device_scene(fix, env, **hp)
+    rays = fix["rays"]
+    ims, st = ops.render_rays(dsc, rays.cuda(), fix["focal"], chunk=rays.shape[0], seed=4, skip_eps=0.0, t_cut=0.0)
+    ref, ns = O.render_rays(osc, rays, fix["focal"], KR.KeyedRNG(), chunk=rays.shape[0], seed=4)
+    assert st["n_samples"][0][0] == ns[0][0]
+    retrace = hp.get("max_retrace_rays", (1000,))
+    if len(retrace) == 0:
+        assert st["n_retrace"] == [0] and len(ns[0]) == 1
+    else:
+        assert st["n_retrace"][0] == min(retrace[0], st["n_bounce_rays0"][0])
+        assert abs(st["n_samples"][0][1] - ns[0][1]) <= max(2, 0.01 * ns[0][1])
+    assert torch.equal(ims["surf_width"].cpu(), ref["surf_width"])
+    report, bad = compare_images(ims, ref)
+    assert not bad, (variant, bad)
