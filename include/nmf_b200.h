@@ -192,8 +192,11 @@ size_t nmf_workspace_bytes_scaled(const NmfScene* scene, int n_rays, int chunk, 
 int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const float* rays, const NmfImages* out,
                     const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Same, with HOST buffers: copies `rays_host` in and every non-NULL image / counter out on `stream`
- * (the copies are asynchronous only if the host buffers are pinned).  `out_host` / `counters_host` hold HOST
+/* Same, with HOST buffers: copies `rays_host` in and every non-NULL image / counter out.  Maps are copied as soon as
+ * they are final -- geometry maps after the march, material maps after the shade -- on a library-owned copy stream
+ * that is ordered against `stream` with events only, so the transfers overlap the rest of the sequence; everything
+ * is complete when `stream` reaches the end of the call (the copies are asynchronous only if the host buffers are
+ * pinned).  One device per process.  `out_host` / `counters_host` hold HOST
  * pointers; `rays_dev`, `out_dev`, `counters_dev` are the device staging buffers of the same shapes. */
 int nmf_render_rays_host(const NmfScene* scene, const NmfRender* rp, const float* rays_host, float* rays_dev,
                          const NmfImages* out_host, const NmfImages* out_dev, const NmfCounters* counters_host,

@@ -1170,11 +1170,11 @@ __global__ void __launch_bounds__(128) k_shade_plain(const NmfScene s, const Pla
 struct FinishArgs {
   const float* rays; const float* tmin; const float* acc; const float* depth; const int* termk; const int* nvalid;
   const float* accum; int n; float focal; int model;
-  int chunk; float* stat4;
+  int chunk; float* stat4; int do_stats;
 };
 __global__ void k_finish0(const NmfScene s, const FinishArgs a, const NmfImages out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  {
+  if (a.do_stats) {
     // A19 (tensor_nerf.py:567-649): per-chunk sums behind ori_loss, diffuse_reg, brdf_reg and prediction_loss
     const bool in = i < a.n;
     const float* A = a.accum + (size_t)(in ? i : 0) * A_N;
@@ -1337,8 +1337,40 @@ extern "C" size_t nmf_workspace_bytes_scaled(const NmfScene* scene, int n_rays, 
   return w.total;
 }
 
-extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const float* rays, const NmfImages* out,
-                               const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream_) {
+// Host-buffer variant (nmf_render_rays_host): maps are copied to the host as soon as they are final, on a second stream,
+// while the rest of the sequence runs -- geometry maps after the march, material maps after the shade, radiance maps
+// at the end.  Stream order is kept with events only (no host synchronisation).
+struct StagedCopy {
+  const NmfImages* host;
+  cudaStream_t copy;
+  cudaEvent_t ready[2], done;
+};
+static void copy_map(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (dst && src) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+}
+static void copy_stage(const NmfImages* h, const NmfImages* d, int stage, size_t n, cudaStream_t st) {
+  if (stage == 0) {
+    copy_map(h->acc_map, d->acc_map, n * 4, st); copy_map(h->depth, d->depth, n * 4, st);
+    copy_map(h->surf_width, d->surf_width, n * 8, st); copy_map(h->termination_xyz, d->termination_xyz, n * 16, st);
+    copy_map(h->normal, d->normal, n * 12, st);
+  } else if (stage == 1) {
+    copy_map(h->world_normal, d->world_normal, n * 12, st); copy_map(h->albedo, d->albedo, n * 12, st);
+    copy_map(h->roughness, d->roughness, n * 12, st); copy_map(h->diffuse, d->diffuse, n * 12, st);
+  } else {
+    copy_map(h->rgb_map, d->rgb_map, n * 12, st); copy_map(h->spec, d->spec, n * 12, st);
+    copy_map(h->tint, d->tint, n * 12, st); copy_map(h->cross_section, d->cross_section, n * 12, st);
+  }
+}
+static NmfImages stage_images(const NmfImages& o, int stage) {
+  NmfImages r = {};
+  if (stage == 0) { r.acc_map = o.acc_map; r.depth = o.depth; r.surf_width = o.surf_width; r.termination_xyz = o.termination_xyz; r.normal = o.normal; }
+  else if (stage == 1) { r.world_normal = o.world_normal; r.albedo = o.albedo; r.roughness = o.roughness; r.diffuse = o.diffuse; }
+  else { r.rgb_map = o.rgb_map; r.spec = o.spec; r.tint = o.tint; r.cross_section = o.cross_section; }
+  return r;
+}
+
+static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* rays, const NmfImages* out,
+                       const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream_, const StagedCopy* sc) {
   int st = check_scene(scene);
   if (st) return st;
   if (!rp || !rays || !out || !workspace || rp->n_rays <= 0 || rp->chunk <= 0) return NMF_E_ARG;
@@ -1370,6 +1402,14 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
   // rays differ a lot in cost: several waves of small CTAs (a multiple of the resident count) balance better than one
   k_march<0><<<min(4 * g_march0, blocks_for(n, 8, 1 << 20)), 256, 0, stream>>>(s, m0);
   CKL();
+  FinishArgs fa = {rays, w.tmin0, w.acc0, w.depth0, w.termk0, w.nvalid0, w.accum0, n, rp->focal, s.model, rp->chunk, w.stat4, 0};
+  if (sc && s.model == 0) {
+    k_finish0<<<(n + 127) / 128, 128, 0, stream>>>(s, fa, stage_images(*out, 0));
+    CKL();
+    CK(cudaEventRecord(sc->ready[0], stream));
+    CK(cudaStreamWaitEvent(sc->copy, sc->ready[0], 0));
+    copy_stage(sc->host, out, 0, (size_t)n, sc->copy);
+  }
   prof_mark(1, stream);
 
   if (s.model == 0) {
@@ -1396,6 +1436,13 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
     h0.owner = w.owner0; h0.error = w.error; h0.red = w.red0;
     k_shade<0><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h0);
     CKL();
+    if (sc) {
+      k_finish0<<<(n + 127) / 128, 128, 0, stream>>>(s, fa, stage_images(*out, 1));
+      CKL();
+      CK(cudaEventRecord(sc->ready[1], stream));
+      CK(cudaStreamWaitEvent(sc->copy, sc->ready[1], 0));
+      copy_stage(sc->host, out, 1, (size_t)n, sc->copy);
+    }
     prof_mark(2, stream);
 
     // persistent grid over the flat tile list: 5 CTAs per SM with the fp16 operand tiles, 3 with the fp32 SIMT staging
@@ -1465,15 +1512,28 @@ extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const
     CKL();
     prof_mark(2, stream);
   }
-  FinishArgs fa = {rays, w.tmin0, w.acc0, w.depth0, w.termk0, w.nvalid0, w.accum0, n, rp->focal, s.model, rp->chunk, w.stat4};
-  k_finish0<<<(n + 127) / 128, 128, 0, stream>>>(s, fa, *out);
+  fa.do_stats = 1;
+  const bool staged = sc && s.model == 0;
+  k_finish0<<<(n + 127) / 128, 128, 0, stream>>>(s, fa, staged ? stage_images(*out, 2) : *out);
   CKL();
+  if (staged) {
+    copy_stage(sc->host, out, 2, (size_t)n, stream);            // the last maps go out on the main stream
+    CK(cudaEventRecord(sc->done, sc->copy));
+    CK(cudaStreamWaitEvent(stream, sc->done, 0));                // ... which also waits for the early copies
+  } else if (sc) {
+    for (int g = 0; g < 3; ++g) copy_stage(sc->host, out, g, (size_t)n, stream);
+  }
   if (counters) {
     k_export_counters<<<(nc + 127) / 128 > 0 ? (nc + 127) / 128 : 1, 128, 0, stream>>>(w, *counters, s.model);
     CKL();
   }
   prof_mark(11, stream);
   return NMF_OK;
+}
+
+extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const float* rays, const NmfImages* out,
+                               const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream_) {
+  return render_impl(scene, rp, rays, out, counters, workspace, workspace_bytes, stream_, nullptr);
 }
 
 extern "C" int nmf_render_rays_host(const NmfScene* scene, const NmfRender* rp, const float* rays_host, float* rays_dev,
@@ -1483,14 +1543,24 @@ extern "C" int nmf_render_rays_host(const NmfScene* scene, const NmfRender* rp, 
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t n = (size_t)rp->n_rays;
   CK(cudaMemcpyAsync(rays_dev, rays_host, n * 6 * sizeof(float), cudaMemcpyHostToDevice, stream));
-  int st = nmf_render_rays(scene, rp, rays_dev, out_dev, counters_dev, workspace, workspace_bytes, stream_);
+  // one copy stream and three events per process (created on first use; one host thread drives a device)
+  static StagedCopy sc = {};
+  static bool sc_made = false;
+  static int sc_dev = -1;
+  int cur_dev = 0;
+  CK(cudaGetDevice(&cur_dev));
+  if (sc_made && cur_dev != sc_dev) return NMF_E_UNSUPPORTED;     // one device per process (one process per GPU)
+  sc_dev = cur_dev;
+  if (!sc_made) {
+    CK(cudaStreamCreateWithFlags(&sc.copy, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&sc.ready[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sc.ready[1], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming));
+    sc_made = true;
+  }
+  sc.host = out_host;
+  int st = render_impl(scene, rp, rays_dev, out_dev, counters_dev, workspace, workspace_bytes, stream_, &sc);
   if (st) return st;
-#define D2H(field, elems, type) \
-  if (out_host->field && out_dev->field) CK(cudaMemcpyAsync(out_host->field, out_dev->field, n * (elems) * sizeof(type), cudaMemcpyDeviceToHost, stream));
-  D2H(rgb_map, 3, float) D2H(acc_map, 1, float) D2H(depth, 1, float) D2H(world_normal, 3, float) D2H(normal, 3, float)
-  D2H(termination_xyz, 4, float) D2H(surf_width, 1, int64_t) D2H(cross_section, 3, float) D2H(diffuse, 3, float)
-  D2H(tint, 3, float) D2H(roughness, 3, float) D2H(spec, 3, float) D2H(albedo, 3, float)
-#undef D2H
   if (counters_host && counters_dev) {
     const size_t nc = (n + rp->chunk - 1) / rp->chunk;
 #define C2H(field, cnt) \
