@@ -36,3 +36,50 @@ def render_sharded(render_fn, rays, chunk, rank=None, world=None, gather=True, g
         return None
     keys = next(p for p in parts if p).keys()
     return {k: torch.cat([p[k] for p in parts if p], dim=0) for k in keys}
+
+
+class FlatGradBucket:
+    """The one collective of ray-sharded training (BASELINE config #4): every rank renders its own
+    rays, back-propagates locally, then ONE all-reduce(SUM) over a single flat fp32 buffer that aliases every parameter's
+    `.grad` (~50 MB at G=300; NVSwitch reduces it in the fabric, so one launch-latency-sized bucket beats many).  The
+    loss normaliser becomes the global ray count via `scale`.  (The backward kernels that fill the gradients are the
+    next row of SURVEY 8f; this class is the communication half, tested with gloo on CPU and used as-is with NCCL.)"""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32 and p.dtype != torch.float64:
+                raise ValueError("FlatGradBucket handles floating-point parameters")
+            if p.dtype == torch.float32:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)      # autograd accumulates in place into the view
+            off += p.numel()
+        self._offsets = off
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce(self, scale=1.0, group=None):
+        """Sums the gradients of all ranks in one collective and multiplies by `scale` (e.g. 1 / global ray count)."""
+        import torch.distributed as dist
+        # float64 scalars of the reference (bg_module.mipbias / brightness / mul) are not views: stage them in and out
+        off = 0
+        for p in self.params:
+            if p.dtype == torch.float64 and p.grad is not None:
+                self.flat[off:off + p.numel()] = p.grad.reshape(-1).float()
+            off += p.numel()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        if scale != 1.0:
+            self.flat.mul_(scale)
+        off = 0
+        for p in self.params:
+            if p.dtype == torch.float64 and p.grad is not None:
+                p.grad.copy_(self.flat[off:off + p.numel()].view_as(p).double())
+            off += p.numel()
+        return self.flat

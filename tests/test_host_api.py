@@ -128,3 +128,35 @@ def test_sharded_render_equals_single(tmp_path):
     ids = torch.arange(n)
     assert torch.equal(out["rgb_map"], torch.stack([rays[:, 0], ids.float(), (ids // chunk).float()], -1))
     assert torch.equal(out["acc_map"], rays[:, 5] * 2)
+
+
+def _grad_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nmf_b200.distributed import FlatGradBucket
+    torch.manual_seed(0)
+    a = torch.nn.Parameter(torch.randn(5, 3))
+    b = torch.nn.Parameter(torch.randn(7))
+    c = torch.nn.Parameter(torch.tensor(0.5, dtype=torch.float64))        # like bg_module.mul
+    frozen = torch.nn.Parameter(torch.randn(2), requires_grad=False)
+    bucket = FlatGradBucket([a, b, c, frozen])
+    x = torch.full((3,), float(rank + 1))
+    loss = (a @ x).sum() + (b * (rank + 1)).sum() + c * (rank + 1) * 2          # local "per-shard" loss
+    bucket.zero()
+    loss.backward()
+    assert a.grad.data_ptr() == bucket.flat.data_ptr()                           # autograd wrote into the flat buffer
+    bucket.allreduce(scale=1.0 / world)
+    if rank == 0:
+        torch.save(dict(a=a.grad.clone(), b=b.grad.clone(), c=c.grad.clone(), n=bucket.flat.numel()), os.path.join(tmp, "g.pt"))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_bucket_allreduce(tmp_path):
+    """world_size-2 gloo run of the single gradient all-reduce of ray-sharded training."""
+    import torch.multiprocessing as mp
+    mp.spawn(_grad_worker, args=(2, 29631, str(tmp_path)), nprocs=2, join=True)
+    g = torch.load(os.path.join(str(tmp_path), "g.pt"))
+    assert g["n"] == 15 + 7 + 1
+    assert torch.allclose(g["a"], torch.full((5, 3), 1.5)) and torch.allclose(g["b"], torch.full((7,), 1.5))
+    assert abs(float(g["c"]) - 3.0) < 1e-12
