@@ -2,16 +2,21 @@
 //
 // One call of nmf_render_rays renders every chunk of a ray batch with a fixed sequence of launches (no host
 // synchronisation, CUDA-graph capturable).  Phases (DESIGN.md "Kernels"):
-//   k_march<0>    warp per ray: slab test, dense step enumeration, AABB + occupancy-bit test (bit-exact),
-//                 VM density gather (4 lanes per sample), transmittance scan, warp-compacted survivor list
-//   k_shade<0>    8 lanes per surviving sample: appearance gather + basis GEMV, smoothed-gradient normal,
-//                 material heads, SH irradiance, bounce count, debug-map accumulation, bounce-sample records
-//   k_bounce<0>   thread per bounce ray: Sobol + GGX VNDF sample, ISH encodings, BRDF MLP, retrace score
-//   k_select      CTA per chunk: radix-select of the top max_retrace scores -> secondary rays
-//   k_march<1> .. k_bounce<1> (environment lookup + per-sample mean fused), k_finish1: the retraced rays
-//   k_incoming    per primary bounce ray: retraced radiance or environment lookup, Fresnel mix, per-sample sums
-//   k_reduce0     per bounce sample: mean over its rays, composite into the pixel
-//   k_finish0     per ray: tonemap, background, auxiliary maps
+//   k_march<0>     warp per ray: slab test, dense step enumeration (four 32-step groups per occupancy round trip, exact
+//                  early exit past the box), AABB + occupancy-bit test (bit-exact), VM density gather (4 lanes per
+//                  sample), transmittance scan, warp-compacted survivor list
+//   k_shade<0>     per warp, 32 survivors: gather phase (8 lanes per sample: appearance taps, 3xTF32 mma.sync basis
+//                  contraction, smoothed-gradient normal) + shade phase (1 lane per sample: material heads, SH
+//                  irradiance, bounce count, debug maps, A19 sums, bounce-sample record incl. the per-sample GGX frame)
+//   k_tile_prefix  flat list of 128-ray tiles over the per-chunk bounce-ray regions
+//   k_bounce<0>    persistent CTAs, thread per bounce ray: Sobol + GGX VNDF sample, ISH encodings, BRDF MLP on
+//                  tcgen05 (fp16 operands, TMEM accumulators, TMA-staged weights), retrace score
+//   k_select       CTA per chunk: radix-select of the top max_retrace scores -> secondary rays
+//   k_march<1>, k_shade<1>, k_bounce<1>, k_incoming<1>, k_finish1: the retraced rays (recur = 1)
+//   k_incoming<0>  per primary bounce ray: retraced radiance or environment lookup, Fresnel mix, per-sample sums
+//   k_reduce0      per bounce sample: mean over its rays, composite into the pixel
+//   k_finish0      per ray: tonemap, background, auxiliary maps, per-chunk A19 statistics (in three stages when the
+//                  caller wants host buffers: maps leave for the host as soon as they are final)
 #include <cuda_runtime.h>
 
 #include "nmf_field.cuh"
