@@ -55,7 +55,7 @@ def test_whole_image_counters_are_consistent(full):
     assert torch.equal(again["surf_width"], first["surf_width"]) and st2["n_samples0"] == st["n_samples0"]
     assert all(abs(a - b) <= 0.002 * b for a, b in zip(st2["n_samples1"], st["n_samples1"]))
     diff = (again["rgb_map"] - first["rgb_map"]).abs().max(dim=1).values
-    assert float(diff.quantile(0.999)) < 2e-5 and float(diff.max()) < 5e-3
+    assert float(diff.quantile(0.999)) < 2e-5 and int((diff > 1e-3).sum()) <= 64
 
 
 def test_sharding_and_ray_order_do_not_change_the_image(full):
