@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NMF_ABI_VERSION 4
+#define NMF_ABI_VERSION 5
 
 #define NMF_OK 0
 #define NMF_E_ARG (-1)          /* null pointer / non-positive size                                   */
@@ -40,6 +40,7 @@ extern "C" {
 #define NMF_BRDF_IN 66          /* modules/brdf.py:96-120  24 + 2*(18+3)                               */
 #define NMF_BRDF_HID 64         /* configs/model/microfacet_tensorf2.yaml:93 hidden_w                  */
 #define NMF_MAX_STEPS 2048      /* dense steps per ray the march kernel keeps a bitmask for            */
+#define NMF_MAX_COARSE_WORDS 2048 /* coarse occupancy bit-field held in shared memory by k_march            */
 #define NMF_MAX_BOUNCE 400      /* modules/pt_selectors.py:39                                          */
 #define NMF_PLAIN_IN 135        /* modules/render_modules.py:201-235 with viewpe=2, feape=2            */
 #define NMF_PLAIN_HID 128       /* configs/model/tensorf.yaml featureC                                 */
@@ -71,6 +72,14 @@ typedef struct NmfScene {
   const uint32_t* occ_cell;
   int ow, oh, od, opitch;
   int has_occ;
+  /* conservative coarse occupancy, a pure accelerator that never changes a result (optional: occ_coarse may be NULL):
+   * flat bit (cz*och + cy)*ocw + cx is set iff a voxel with index in [8c-1, 8c+9] on every axis is set, i.e. iff the
+   * exact test can succeed for a sample whose cell index -- computed with one multiply, occ_scale = (size-1)/aabbSize,
+   * so possibly one cell off -- lands in coarse cell c.  At most NMF_MAX_COARSE_WORDS 32-bit words (it is held in
+   * shared memory by the march). */
+  const uint32_t* occ_coarse;
+  int ocw, och, ocd;
+  float occ_scale[3];
 
   /* density factors.  dval: [h][w][16] plane values; dpack: [h][w][val16 | dx16 | dy16] where dx/dy are the
    * smoothed-difference planes of modules/grid_sample_Cinf.py:218-242; lines: lval [n][16], lpack [n][4][val4,dy4] */

@@ -23,6 +23,7 @@ class NmfScene(C.Structure):
         ("plane_w", c_int3), ("plane_h", c_int3), ("line_n", c_int3),
         ("occ_vox", C.c_void_p), ("occ_cell", C.c_void_p),
         ("ow", C.c_int), ("oh", C.c_int), ("od", C.c_int), ("opitch", C.c_int), ("has_occ", C.c_int),
+        ("occ_coarse", C.c_void_p), ("ocw", C.c_int), ("och", C.c_int), ("ocd", C.c_int), ("occ_scale", c_float3),
         ("dval", c_ptr3), ("dpack", c_ptr3), ("lval", c_ptr3), ("lpack", c_ptr3),
         ("aval", c_ptr3), ("alval", c_ptr3), ("basis_t", C.c_void_p),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p),
@@ -127,7 +128,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    assert L.nmf_abi_version() == 4, "libnmf_b200.so ABI mismatch: rebuild"
+    assert L.nmf_abi_version() == 5, "libnmf_b200.so ABI mismatch: rebuild"
     _lib = L
     return L
 

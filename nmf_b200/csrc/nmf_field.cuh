@@ -35,6 +35,20 @@ NMF_HD void nmf_normalize_xyz(const NmfScene& s, const float* p, float* xn) {   
   xn[1] = nmf_norm_coord(p[1], s.aabb0[1], s.inv_aabb2[1]);
   xn[2] = nmf_norm_coord(p[2], s.aabb0[2], s.inv_aabb2[2]);
 }
+// Conservative coarse occupancy (NmfScene.occ_coarse, here already in shared memory): false => no voxel within one
+// cell of the sample's 8-cell block is set, so the exact trilinear test (nmf_occupied) is false.  The cell index comes
+// from one multiply (error ~1e-5 cells); the field is dilated by a whole voxel on each side, so a floor that lands one
+// cell off is still covered.
+NMF_HD bool nmf_occ_coarse(const NmfScene& s, const uint32_t* coarse, const float* p) {
+  int x = (int)((p[0] - s.aabb0[0]) * s.occ_scale[0]), y = (int)((p[1] - s.aabb0[1]) * s.occ_scale[1]);
+  int z = (int)((p[2] - s.aabb0[2]) * s.occ_scale[2]);
+  x = x < 0 ? 0 : (x >= s.ow ? s.ow - 1 : x);
+  y = y < 0 ? 0 : (y >= s.oh ? s.oh - 1 : y);
+  z = z < 0 ? 0 : (z >= s.od ? s.od - 1 : z);
+  const unsigned i = ((unsigned)(z >> 3) * (unsigned)s.och + (unsigned)(y >> 3)) * (unsigned)s.ocw + (unsigned)(x >> 3);
+  return (coarse[i >> 5] >> (i & 31)) & 1u;
+}
+
 NMF_HD NmfTaps nmf_vm_taps(const NmfScene& s, const float* xn) {                // tensoRF.py:161-179
   // every factor that is indexed by axis a has grid[a] texels along it (plane p: width grid[mat0(p)], height
   // grid[mat1(p)]; line p: grid[vec(p)]; checked by the host before any launch), so the nine bilinear set-ups of

@@ -168,6 +168,13 @@ struct MarchArgs {
 template <int LEVEL>
 __global__ void __launch_bounds__(256) k_march(const NmfScene s, const MarchArgs a) {
   __shared__ uint16_t s_list[8][NMF_MAX_STEPS];
+  __shared__ uint32_t s_coarse[NMF_MAX_COARSE_WORDS];
+  const bool use_coarse = s.has_occ && s.occ_coarse != nullptr;
+  if (use_coarse) {
+    const int nw = (s.ocw * s.och * s.ocd + 31) >> 5;
+    for (int i = threadIdx.x; i < nw; i += 256) s_coarse[i] = s.occ_coarse[i];
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int S = s.n_steps;
   const unsigned lt = (1u << lane) - 1u;
@@ -194,7 +201,8 @@ __global__ void __launch_bounds__(256) k_march(const NmfScene s, const MarchArgs
     int k0 = 0;
     for (; k0 < S && !done; k0 += 128) {
       uint32_t word[4];
-      int shift[4], state[4];                // 0 = outside the box, 1 = one cell bit decides, 2 = on a lattice plane, 3 = no occupancy grid
+      int shift[4], state[4];                // 0 = outside the box, 1 = one cell bit decides, 2 = on a lattice plane,
+                                             // 3 = no occupancy grid, 4 = in the box but in an empty coarse cell
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = k0 + 32 * j + lane;
@@ -205,7 +213,9 @@ __global__ void __launch_bounds__(256) k_march(const NmfScene s, const MarchArgs
           if (nmf_inside(p, s.aabb0, s.aabb1)) {
             ++cand;
             state[j] = 3;
-            if (s.has_occ) {
+            if (use_coarse && !nmf_occ_coarse(s, s_coarse, p)) {
+              state[j] = 4;                  // most of the box: no voxel near this cell, the exact test cannot succeed
+            } else if (s.has_occ) {
               float xn[3];
               long long wi;
               nmf_normalize_xyz(s, p, xn);
@@ -1291,6 +1301,10 @@ static int check_scene(const NmfScene* s) {
       s->line_n[1] != s->plane_h[0] || s->plane_h[2] != s->plane_h[1] || s->line_n[0] != s->plane_h[1])
     return NMF_E_UNSUPPORTED;
   if (s->has_occ && (!s->occ_vox || !s->occ_cell || (s->opitch & 31))) return NMF_E_ARG;
+  if (s->has_occ && s->occ_coarse &&
+      (s->ocw != (s->ow + 7) / 8 || s->och != (s->oh + 7) / 8 || s->ocd != (s->od + 7) / 8 ||
+       ((long long)s->ocw * s->och * s->ocd + 31) / 32 > NMF_MAX_COARSE_WORDS))
+    return NMF_E_ARG;
   return NMF_OK;
 }
 

@@ -233,7 +233,8 @@ class DeviceScene:
         if alpha_volume is None:
             s.has_occ = 0
             s.ow = s.oh = s.od = s.opitch = 0
-            s.occ_vox = s.occ_cell = None
+            s.occ_vox = s.occ_cell = s.occ_coarse = None
+            s.ocw = s.och = s.ocd = 0
             self.alpha_volume = None
             return
         vol = torch.as_tensor(alpha_volume).to(self.device)
@@ -246,6 +247,26 @@ class DeviceScene:
         self.keep["occ_vox"], self.keep["occ_cell"] = vox_bits, cell_bits
         s.occ_vox, s.occ_cell = vox_bits.data_ptr(), cell_bits.data_ptr()
         s.ow, s.oh, s.od, s.opitch, s.has_occ = W, H, D, pitch, 1
+        # conservative coarse field (8 fine cells per axis, dilated by one voxel): coarse cell c is set iff a voxel in
+        # [8c-1, 8c+9] is set on every axis; flat bit order, small enough for shared memory or left out
+        cdim = [(n + 7) // 8 for n in (W, H, D)]
+        s.occ_coarse, s.ocw, s.och, s.ocd = None, 0, 0, 0
+        if (cdim[0] * cdim[1] * cdim[2] + 31) // 32 <= 2048:
+            padr = [8 * c + 2 - n for c, n in zip(cdim, (W, H, D))]
+            padded = F.pad(vol.float()[None, None], (1, padr[0], 1, padr[1], 1, padr[2]))
+            coarse = (F.max_pool3d(padded, kernel_size=11, stride=8)[0, 0] > 0).reshape(-1)
+            assert coarse.numel() == cdim[0] * cdim[1] * cdim[2]
+            nw = (coarse.numel() + 31) // 32
+            bits = torch.zeros(nw * 32, dtype=torch.int64, device=vol.device)
+            bits[:coarse.numel()] = coarse.to(torch.int64)
+            words = (bits.view(nw, 32) << torch.arange(32, device=vol.device, dtype=torch.int64)).sum(dim=1)
+            words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).contiguous()
+            self.keep["occ_coarse"] = words
+            s.occ_coarse = words.data_ptr()
+            s.ocw, s.och, s.ocd = cdim
+            size = (self.aabb[1] - self.aabb[0]).cpu()
+            for i, n in enumerate((W, H, D)):
+                s.occ_scale[i] = float((n - 1) / float(size[i]))
         self.alpha_volume = vol
 
     def update_alpha_mask(self, grid_size=None):
