@@ -165,8 +165,15 @@ struct MarchArgs {
   Surv* surv; int* n_surv; int cap_surv; unsigned* error;
 };
 
+// The 8-corner occupancy test of a step that lies exactly on a lattice plane.  Rare (a handful per thousand rays), so it
+// is kept out of line: inlined four times it doubled the size of the march loop past the instruction cache.
+__device__ __noinline__ bool march_occupied_on_lattice(const uint32_t* vox, const uint32_t* cell, int ow, int oh, int od, int opitch,
+                                                       float xn0, float xn1, float xn2) {
+  return nmf_occupied(vox, cell, ow, oh, od, opitch, xn0, xn1, xn2);
+}
+
 template <int LEVEL>
-__global__ void __launch_bounds__(256) k_march(const NmfScene s, const MarchArgs a) {
+__global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchArgs a) {
   __shared__ uint16_t s_list[8][NMF_MAX_STEPS];
   __shared__ uint32_t s_coarse[NMF_MAX_COARSE_WORDS];
   const bool use_coarse = s.has_occ && s.occ_coarse != nullptr;
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(256) k_march(const NmfScene s, const MarchArgs
           float p[3], xn[3];
           nmf_step_pos(o, d, nmf_step_z(tmin, s.stepsize, k), p);
           nmf_normalize_xyz(s, p, xn);
-          ok = nmf_occupied(s.occ_vox, s.occ_cell, s.ow, s.oh, s.od, s.opitch, xn[0], xn[1], xn[2]);
+          ok = march_occupied_on_lattice(s.occ_vox, s.occ_cell, s.ow, s.oh, s.od, s.opitch, xn[0], xn[1], xn[2]);
         }
         const unsigned m = __ballot_sync(FULL, ok);
         if (ok) list[nv + __popc(m & lt)] = (uint16_t)k;
