@@ -804,19 +804,36 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
     xcol = sm + (MLP_SMEM_FLOATS - 66 * MLP_THREADS) + threadIdx.x;
   }
   const int n_tiles = a.tile_start[a.n_chunks];
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // chunk of this tile: last c with tile_start[c] <= tile
-    int lo = 0, hi = a.n_chunks;
+  // (chunk, ray index, owning bounce sample) of this thread in a tile; the NEXT tile's are looked up one iteration
+  // ahead and its sample record is prefetched, so that the dependent chain tile -> owner -> record is off the critical
+  // path of the tile that uses it
+  auto locate = [&](int tile, int& chunk, int& n, int& r, uint32_t& slot) {
+    int lo = 0, hi = a.n_chunks;                      // last c with tile_start[c] <= tile
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
       if (__ldg(a.tile_start + mid) <= tile) lo = mid; else hi = mid;
     }
-    const int chunk = lo;
-    const int n = min(a.ray_count[chunk], a.cap_rays);
+    chunk = lo;
+    n = min(a.ray_count[chunk], a.cap_rays);
+    r = (tile - __ldg(a.tile_start + chunk)) * MLP_THREADS + threadIdx.x;
+    slot = r < n ? a.owner[(size_t)chunk * a.cap_rays + r] : NMF_NO_OWNER;
+  };
+  int chunk = 0, n = 0, r = 0;
+  uint32_t slot = NMF_NO_OWNER;
+  if ((int)blockIdx.x < n_tiles) locate(blockIdx.x, chunk, n, r, slot);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int chunk_next = 0, n_next = 0, r_next = 0;
+    uint32_t slot_next = NMF_NO_OWNER;
+    if (tile + (int)gridDim.x < n_tiles) {
+      locate(tile + gridDim.x, chunk_next, n_next, r_next, slot_next);
+      if (slot_next != NMF_NO_OWNER) {
+        const char* rec = (const char*)(a.bs + slot_next);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 256));
+      }
+    }
     BRay* region = a.brays + (size_t)chunk * a.cap_rays;
-    const uint32_t* owner = a.owner + (size_t)chunk * a.cap_rays;
-    const int r = (tile - __ldg(a.tile_start + chunk)) * MLP_THREADS + threadIdx.x;
-    uint32_t slot = r < n ? owner[r] : NMF_NO_OWNER;
     const bool active = slot != NMF_NO_OWNER;
     if (!active) slot = 0u;
     if (LEVEL == 0 && r < n && !active) a.scu[(size_t)chunk * a.cap_rays + r] = make_float2(0.f, 0.f);
@@ -873,6 +890,7 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
       *(float4*)o->L = make_float4(g.L.x, g.L.y, g.L.z, mip);
       *(float4*)o->bw = make_float4(bw[0], bw[1], bw[2], __int_as_float(-1));
     }
+    chunk = chunk_next; n = n_next; r = r_next; slot = slot_next;
   }
   if (TC) tc_mlp_free(tc);
 }
