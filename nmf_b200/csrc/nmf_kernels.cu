@@ -28,6 +28,7 @@
 #define NMF_BS0_PER_RAY 24         // bounce samples per primary ray (typical: 12)
 #define NMF_SURV1_PER_RAY 256      // per retraced ray
 #define NMF_BS1_PER_RAY 128
+#define NMF_TIE_CAP 64            // exact score ties at a chunk's retrace threshold that are ordered by ray key
 #define NMF_NO_OWNER 0xFFFFFFFFu  // ray -> sample map entry of a ray whose sample could not be allocated (overflow)
 
 struct Surv { uint32_t ray; uint32_t step; float w; };
@@ -964,14 +965,44 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
     need = sh_need;
     __syncthreads();
   }
-  // prefix now holds the full 32-bit pattern of the threshold; `need` = how many rays equal to it are taken
-  if (threadIdx.x == 0) { sh_slot = 0; sh_eq = 0; }
+  // prefix now holds the full 32-bit pattern of the threshold; `need` = how many of the rays equal to it are taken.
+  // Scores are sums with a 24-bit uniform, so exact ties at the threshold do occur; they are broken by the rays' keys
+  // (a property of the ray, not of its position in the list), which keeps the selection reproducible run to run.
+  __shared__ unsigned long long tie_key[NMF_TIE_CAP];
+  __shared__ unsigned long long tie_cut;
+  if (threadIdx.x == 0) { sh_slot = 0; sh_eq = 0; tie_cut = ~0ull; }
   __syncthreads();
   const unsigned thr = prefix;
+  auto ray_key = [&](int r) -> unsigned long long {
+    const uint32_t own = a.owner[(size_t)chunk * a.cap_rays + r];
+    if (own == NMF_NO_OWNER) return ~0ull;
+    const BSample* b = a.bs + own;
+    return (unsigned long long)nmf_mix64(b->key, (uint64_t)(r - (int)b->roff) + NMF_STREAM_RAY0);
+  };
+  for (int r = threadIdx.x; r < n; r += 1024) {
+    if (__float_as_uint(scu[r].x) == thr) {
+      const unsigned e = atomicAdd(&sh_eq, 1u);
+      if (e < NMF_TIE_CAP) tie_key[e] = ray_key(r);
+    }
+  }
+  __syncthreads();
+  const unsigned n_tie = sh_eq;
+  const bool by_key = n_tie > need && n_tie <= NMF_TIE_CAP;      // otherwise all ties are taken, or (absurdly many) first come
+  if (by_key && threadIdx.x == 0) {
+    // the `need` smallest keys win: selection sort over a handful of entries
+    for (unsigned i = 0; i < need; ++i) {
+      unsigned m = i;
+      for (unsigned j = i + 1; j < n_tie; ++j) if (tie_key[j] < tie_key[m]) m = j;
+      const unsigned long long t = tie_key[i]; tie_key[i] = tie_key[m]; tie_key[m] = t;
+    }
+    tie_cut = tie_key[need - 1];
+  }
+  if (threadIdx.x == 0) sh_eq = 0;
+  __syncthreads();
   for (int r = threadIdx.x; r < n; r += 1024) {
     const unsigned bits = __float_as_uint(scu[r].x);
     bool take = bits > thr;
-    if (bits == thr) take = atomicAdd(&sh_eq, 1u) < need;
+    if (bits == thr) take = by_key ? ray_key(r) <= tie_cut : atomicAdd(&sh_eq, 1u) < need;
     if (take) {
       const unsigned sl = atomicAdd(&sh_slot, 1u);
       if (sl < (unsigned)n_re) {

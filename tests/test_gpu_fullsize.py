@@ -53,7 +53,7 @@ def test_whole_image_counters_are_consistent(full):
     first = {k: v.clone() for k, v in ims.items()}
     again, st2 = ops.render_rays(dsc, rays.cuda(), focal, chunk=CHUNK, seed=1)
     assert torch.equal(again["surf_width"], first["surf_width"]) and st2["n_samples0"] == st["n_samples0"]
-    assert all(abs(a - b) <= 0.002 * b for a, b in zip(st2["n_samples1"], st["n_samples1"]))
+    assert sum(a != b for a, b in zip(st2["n_samples1"], st["n_samples1"])) <= 1      # ties are broken by ray key
     diff = (again["rgb_map"] - first["rgb_map"]).abs().max(dim=1).values
     assert float(diff.quantile(0.999)) < 2e-5 and int((diff > 1e-3).sum()) <= 64
 
