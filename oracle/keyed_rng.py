@@ -30,6 +30,7 @@ STREAM_BOUNCE = 32
 STREAM_OFF_U = 33
 STREAM_OFF_V = 34
 STREAM_TIE = 35
+STREAM_JITTER = 36       # train-mode step jitter, keyed by (ray key, step)             (samplers/alphagrid.py:167-173)
 STREAM_NOISE_B = 64      # second uniform of the Box-Muller pair for noise dim d is stream 64 + d
 STREAM_RAY0 = 1000
 
@@ -113,6 +114,9 @@ class TorchRNG:
     """Reference-identical random streams (torch global generator, reference shapes and order)."""
     keyed = False
 
+    def jitter(self, B, S, ray_keys):
+        return torch.rand((B, S))                       # alphagrid.py:169
+
     def app_noise(self, feat, skeys):
         return torch.randn_like(feat)
 
@@ -138,6 +142,10 @@ class TorchRNG:
 
 class KeyedRNG:
     keyed = True
+
+    def jitter(self, B, S, ray_keys):
+        keys = sample_keys(np.repeat(_u64(ray_keys), S), np.tile(np.arange(S), B))
+        return uniform(keys, STREAM_JITTER).reshape(B, S)
 
     def app_noise(self, feat, skeys):
         assert feat.shape[1] == 24

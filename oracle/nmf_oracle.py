@@ -63,32 +63,45 @@ DEFAULT_HP = dict(
 class Scene:
     """Weights (reference state_dict key names) + the hyper-parameters the path reads."""
 
-    def __init__(self, state, aabb, near_far, grid_size, alpha_volume=None, **hp):
+    def __init__(self, state, aabb, near_far, grid_size, alpha_volume=None, requires_grad=False, **hp):
+        """requires_grad=True keeps every weight as an autograd leaf (``self.params``: reference state_dict key ->
+        leaf) so that ``render_chunk(..., is_train=True)`` can be back-propagated like the reference's training
+        forward (gradient oracle for SURVEY 8f row 1)."""
         self.hp = dict(DEFAULT_HP)
         self.hp.update(hp)
+        self.requires_grad = requires_grad
+        self.params = {}
+
+        def leaf(key, dtype=torch.float32):
+            t = state[key].detach().to(dtype).contiguous().clone()
+            if requires_grad:
+                t.requires_grad_(True)
+                self.params[key] = t
+            return t
+
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
         self.aabb = f32(torch.as_tensor(aabb))
         self.near_far = (float(near_far[0]), float(near_far[1]))
         self.grid_size = [int(g) for g in grid_size]
-        self.d_plane = [f32(state[f"rf.density_rf.app_plane.{i}"]) for i in range(3)]
-        self.d_line = [f32(state[f"rf.density_rf.app_line.{i}"]) for i in range(3)]
-        self.a_plane = [f32(state[f"rf.app_rf.app_plane.{i}"]) for i in range(3)]
-        self.a_line = [f32(state[f"rf.app_rf.app_line.{i}"]) for i in range(3)]
-        self.basis = f32(state["rf.basis_mat.weight"])
+        self.d_plane = [leaf(f"rf.density_rf.app_plane.{i}") for i in range(3)]
+        self.d_line = [leaf(f"rf.density_rf.app_line.{i}") for i in range(3)]
+        self.a_plane = [leaf(f"rf.app_rf.app_plane.{i}") for i in range(3)]
+        self.a_line = [leaf(f"rf.app_rf.app_line.{i}") for i in range(3)]
+        self.basis = leaf("rf.basis_mat.weight")
         if self.hp["model"] == "microfacet":
-            g = lambda k: f32(state[k])
+            g = lambda k: leaf(k) if "brdf_sampler" not in k else f32(state[k])
             self.heads = {h: (g(f"model.diffuse_module.{h}_mlp.0.weight"), g(f"model.diffuse_module.{h}_mlp.0.bias"))
                           for h in ("diffuse", "tint", "f0", "roughness")}
             self.brdf = [(g(f"model.brdf.mlp.{i}.weight"), g(f"model.brdf.mlp.{i}.bias")) for i in (0, 2, 4)]
             self.sobol = g("model.brdf_sampler.angs")
         else:
-            g = lambda k: f32(state[k])
+            g = lambda k: leaf(k)
             self.view_mlp = [(g(f"model.diffuse_module.mlp.{i}.weight"), g(f"model.diffuse_module.mlp.{i}.bias"))
                              for i in (0, 2, 4)]
-        self.bg_mat = f32(state["bg_module.bg_mat"])
-        self.mipbias = state["bg_module.mipbias"].detach().clone()        # 0-dim float64 parameter
-        self.brightness = state["bg_module.brightness"].detach().clone()
-        self.mul = state["bg_module.mul"].detach().clone()
+        self.bg_mat = leaf("bg_module.bg_mat")
+        self.mipbias = leaf("bg_module.mipbias", torch.float64)            # 0-dim float64 parameters
+        self.brightness = leaf("bg_module.brightness", torch.float64)
+        self.mul = leaf("bg_module.mul", torch.float64)
         # fields/tensor_base.py:56-62, 219-232
         self.aabb_size = self.aabb[1] - self.aabb[0]
         self.inv_aabb_size = 2.0 / self.aabb_size
@@ -114,10 +127,12 @@ def occupancy_lookup(sc, xyz):
     return vals > 0
 
 
-def sample_rays(sc, rays, focal, override_near=None):
-    """Eval-mode AlphaGridSampler.sample (alphagrid.py:131-207, 278-370).
+def sample_rays(sc, rays, focal, override_near=None, is_train=False, rng=None, ray_keys=None, max_samples=-1):
+    """AlphaGridSampler.sample (alphagrid.py:131-207, 278-370).
 
-    Returns xyzs (M,4), ray_valid (B,S) bool, z_vals (B,S), dists (B,S)."""
+    Returns xyzs (M,4), ray_valid (B,S) bool, z_vals (B,S), dists (B,S); in train mode also whole_valid (B) bool
+    (the rays kept by the dynamic batch truncation, :353-364) as a fifth value.
+    Train mode (cumrand = True, :167-173): z = t_min + cumsum(U * stepsize + stepsize / 2)."""
     o, d = rays[:, :3], rays[:, 3:6]
     near, far = sc.near_far
     if override_near is not None:
@@ -127,8 +142,12 @@ def sample_rays(sc, rays, focal, override_near=None):
     rate_a = (sc.aabb[1] - o) / vec
     rate_b = (sc.aabb[0] - o) / vec
     t_min = torch.minimum(rate_a, rate_b).amax(-1).clamp(min=near, max=far)
-    k = torch.arange(S)[None].float()
-    z = t_min[..., None] + sc.stepsize * k
+    if is_train:
+        steps = rng.jitter(rays.shape[0], S, ray_keys) * sc.stepsize + sc.stepsize / 2       # :169-172
+        z = t_min[..., None] + torch.cumsum(steps, dim=1)
+    else:
+        k = torch.arange(S)[None].float()
+        z = t_min[..., None] + sc.stepsize * k
     pts = o[..., None, :] + d[..., None, :] * z[..., None]
     outside = ((sc.aabb[0] > pts) | (pts > sc.aabb[1])).any(dim=-1)
     pts = torch.cat([pts, z.unsqueeze(-1) / focal], dim=-1)
@@ -139,7 +158,13 @@ def sample_rays(sc, rays, focal, override_near=None):
         inval[valid] |= ~occ
         valid = ~inval
     dists = torch.cat((z[:, 1:] - z[:, :-1], torch.zeros_like(z[:, :1])), dim=-1)
-    return pts[valid], valid, z, dists
+    if not is_train:
+        return pts[valid], valid, z, dists
+    whole = torch.ones(rays.shape[0], dtype=torch.bool)
+    if max_samples > 0 and valid.sum() > max_samples:                                        # :353-364
+        whole = torch.cumsum(valid.sum(dim=1), dim=0) < max_samples
+        valid, pts, z, dists = valid[whole], pts[whole], z[whole], dists[whole]
+    return pts[valid], valid, z, dists, whole
 
 
 # --------------------------------------------------------------------------------------------
@@ -151,6 +176,7 @@ def normalize_coord(sc, xyz):
 
 
 def _vm_grids(xn):
+    xn = xn.detach()                                   # tensoRF.py:182-183: the field is not differentiated w.r.t. positions
     planes = torch.stack([xn[..., list(m)] for m in MAT_MODE]).view(3, -1, 1, 2)
     lines = torch.stack([xn[..., v] for v in VEC_MODE])
     lines = torch.stack((torch.zeros_like(lines), lines), dim=-1).view(3, -1, 1, 2)
@@ -310,7 +336,8 @@ def ish18(v, rough):
 def env_tables(sc):
     """activation (exp) and SAT, integral_equirect.py:263-273, 431-433.  torch's CPU cumsum
     accumulates in float64 and rounds every prefix to float32."""
-    if sc._env is None:
+    stale = sc._env is not None and sc.requires_grad and torch.is_grad_enabled() and not sc._env[1].requires_grad
+    if sc._env is None or stale:                      # a table cached under no_grad cannot carry the gradient
         x = sc.brightness + sc.mul * sc.bg_mat
         act = torch.exp(x.clip(max=20))
         sat = torch.cumsum(torch.cumsum(act / 1000, dim=2), dim=3)
@@ -399,6 +426,22 @@ def env_mip_levels(sc, u, sa):
     return lw.clip(0, 7).float(), lh.clip(0, 7).float()
 
 
+class _Atan2Damped(torch.autograd.Function):
+    """modules/safemath.py:8-32: atan2 whose backward divides by (x^2 + y^2 + 1e-5), the gradient the reference
+    trains with (forward identical to torch.atan2)."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        ctx.save_for_backward(x, y)
+        return torch.atan2(x, y)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        den = x ** 2 + y ** 2 + 1e-5
+        return g * y / den, g * -x / den
+
+
 def env_lookup(sc, dirs, sa, rng=None):
     """IntegralEquirect.forward, integral_equirect.py:409-504."""
     if dirs.shape[0] == 0:
@@ -414,8 +457,8 @@ def env_lookup(sc, dirs, sa, rng=None):
     size = (offset / 2 * torch.tensor([w, h]).reshape(1, 1, 1, 2)).prod(dim=-1).reshape(-1, 1)
     a, b, c = dirs[:, 0:1], dirs[:, 1:2], dirs[:, 2:3]
     norm2d = torch.sqrt(a ** 2 + b ** 2)
-    phi = torch.atan2(b, a)
-    theta = torch.atan2(c, norm2d)
+    phi = _Atan2Damped.apply(b, a)
+    theta = _Atan2Damped.apply(c, norm2d)
     coords = torch.cat([(phi % (2 * math.pi) - math.pi) / math.pi, -theta / math.pi * 2], dim=1)
     x = coords.reshape(1, 1, -1, 2)
     bl = x - offset / 2
@@ -491,7 +534,7 @@ def ggx_sample(u1, u2, V, N, r, ray_mask):
     T1 = torch.where(Vs[..., 2:3] < 0.999, unit(torch.linalg.cross(Vs, z_up.unsqueeze(1), dim=-1)), x_up.unsqueeze(1))
     T2 = unit(torch.linalg.cross(T1, Vs, dim=-1))
     z = Vs[..., 2].reshape(-1, 1)
-    a = (1 / (1 + z).clip(min=1e-8)).clip(max=1e4)
+    a = (1 / (1 + z.detach()).clip(min=1e-8)).clip(max=1e4)                                  # ggx.py:116
     am = a.expand(u1.shape)[ray_mask]
     rm = rc.reshape(-1, 1).expand(u1.shape)[ray_mask]
     zm = z.expand(u1.shape)[ray_mask]
@@ -515,7 +558,8 @@ def ggx_sample(u1, u2, V, N, r, ray_mask):
     L = L * sign
     L_l = torch.matmul(cols.permute(0, 2, 1), L.unsqueeze(-1)).squeeze(-1)
     Vo_l = torch.matmul(cols.permute(0, 2, 1), Vo.unsqueeze(-1)).squeeze(-1)
-    logpdf = ggx_pdf(L_l, Vo_l, H_l, rm).clip(min=EPS).log().reshape(-1)
+    with torch.no_grad():                                                                      # ggx.py:218
+        logpdf = ggx_pdf(L_l, Vo_l, H_l, rm).clip(min=EPS).log().reshape(-1)
     return L, cols, logpdf
 
 
@@ -561,7 +605,10 @@ def srgb(img, noclip=False):
 # --------------------------------------------------------------------------------------------
 # A5 .. A16  per-sample shading                                      models/microfacet.py:271-673
 # --------------------------------------------------------------------------------------------
-def shade_microfacet(sc, xyz, feat, view, normals, weights, valid, recur, rng, ray_keys, trace, aux):
+def shade_microfacet(sc, xyz, feat, view, normals, weights, valid, recur, rng, ray_keys, trace, aux, is_train=False,
+                     detach_N=True):
+    """Microfacet.forward (models/microfacet.py:271-673).  The detach / no_grad points of the reference are kept so
+    that autograd through this function is the reference's gradient (they change nothing in the forward values)."""
     M = xyz.shape[0]
     rows, steps = torch.where(valid)
     skeys = KR.sample_keys(ray_keys[rows.numpy()], steps.numpy()) if rng.keyed else None
@@ -569,15 +616,17 @@ def shade_microfacet(sc, xyz, feat, view, normals, weights, valid, recur, rng, r
     nfeat = feat + noise * sc.hp["anoise"]
     albedo, tint, f0, r1 = material_heads(sc, feat)
     rng.head_noise(albedo, torch.empty(M, 2))
-    conv = sh_irradiance_coeffs(sc, rng if not rng.keyed else None)
-    E = (conv.reshape(1, -1, 3) * sh9(normals).reshape(M, -1, 1)).sum(dim=1)
+    with torch.no_grad():                                                                      # microfacet.py:305-315
+        conv = sh_irradiance_coeffs(sc, rng if not rng.keyed else None)
+        E = (conv.reshape(1, -1, 3) * sh9(normals).reshape(M, -1, 1)).sum(dim=1)
     diffuse = albedo * E
 
     dense_keys = None
     if rng.keyed and recur > 0:
         S = valid.shape[1]
         dense_keys = KR.sample_keys(np.repeat(ray_keys, S), np.tile(np.arange(S), valid.shape[0]))
-    kf = bounce_counts(sc, weights, valid, recur, rng, skeys, dense_keys)
+    with torch.no_grad():                                                                      # pt_selectors.py:5
+        kf = bounce_counts(sc, weights, valid, recur, rng, skeys, dense_keys)
     m = int(kf.max().clip(min=0, max=400).int()) if M > 0 else 0
     ray_mask_all = torch.arange(m).reshape(1, -1) < kf.reshape(-1, 1)
     bmask = ray_mask_all.sum(dim=-1) > 0
@@ -590,9 +639,13 @@ def shade_microfacet(sc, xyz, feat, view, normals, weights, valid, recur, rng, r
     if bmask.any() and ray_mask.any():
         ri, rj = torch.where(ray_mask)
         bN = normals[bmask]
+        if detach_N:                                                                           # microfacet.py:352-353
+            bN = bN.detach()
         bV = -view[bmask]
         bN = bN * (bV * bN).sum(dim=-1, keepdim=True).sign()
         rr = r1[bmask]
+        if is_train:
+            rr = rr.clip(min=sc.hp.get("min_rough", 0.0))                                        # microfacet.py:361-363
         nb = bN.shape[0]
         bkeys = skeys[bmask.numpy()] if rng.keyed else None
         off = rng.sobol_offset(nb, bkeys) * 0.25
@@ -611,7 +664,7 @@ def shade_microfacet(sc, xyz, feat, view, normals, weights, valid, recur, rng, r
         count = ray_mask.sum(dim=1)
         mip = -torch.log(count[ri].clip(min=1)) - lpdf
         brays = torch.cat([exyz + L * 5e-3, L], dim=-1)
-        bw = brdf_mlp(sc, efeat, half_l, diff_l, ea)
+        bw = brdf_mlp(sc, efeat, half_l.detach(), diff_l.detach(), ea.detach())                  # microfacet.py:461-472
         ray_count = (count + 1e-8)[..., None]
         rkeys = KR.bounce_ray_keys(bkeys[ri.numpy()], rj.numpy()) if rng.keyed else None
         R = brays.shape[0]
@@ -619,12 +672,13 @@ def shade_microfacet(sc, xyz, feat, view, normals, weights, valid, recur, rng, r
         retr = sc.hp["max_retrace_rays"]
         if len(retr) > recur:
             n_re = min(R, retr[recur])
-            per_sample = weights[valid][bmask].reshape(-1, 1) / ray_count
-            per_ray = bw.max(dim=-1, keepdim=True).values * ((eV * eN).sum(dim=-1, keepdim=True) > 0) * pdf
-            cc = per_ray.reshape(-1) * per_sample.expand(ray_mask.shape)[ri, rj]
-            cc = cc / cc.sum() * n_re
-            cc = cc + rng.tie_break(cc, rkeys)
-            order = cc.argsort()
+            with torch.no_grad():                                                              # microfacet.py:479
+                per_sample = weights[valid][bmask].reshape(-1, 1) / ray_count
+                per_ray = bw.max(dim=-1, keepdim=True).values * ((eV * eN).sum(dim=-1, keepdim=True) > 0) * pdf
+                cc = per_ray.reshape(-1) * per_sample.expand(ray_mask.shape)[ri, rj]
+                cc = cc / cc.sum() * n_re
+                cc = cc + rng.tie_break(cc, rkeys)
+                order = cc.argsort()
             cut = max(order.shape[0] - n_re, 0)
             re_idx, no_idx = order[cut:], order[:cut]
             aux["retrace_score"] = cc
@@ -669,11 +723,24 @@ def shade_plain(sc, feat, view):
 # TensorNeRF.forward (eval)                                          modules/tensor_nerf.py:210-674
 # --------------------------------------------------------------------------------------------
 def render_chunk(sc, rays, focal, rng, ray_keys=None, recur=0, start_mip=None, override_near=None,
-                 white_bg=True, tonemap=True, draw_debug=True, want_aux=False):
-    """One TensorNeRF.forward call in eval mode.  Returns (images, statistics[, aux])."""
-    B = rays.shape[0]
+                 white_bg=True, tonemap=True, draw_debug=True, want_aux=False, is_train=False, detach_N=True,
+                 max_samples=-1):
+    """One TensorNeRF.forward call (modules/tensor_nerf.py:210-674).  Returns (images, statistics[, aux]).
+    is_train=True is the training forward: jittered steps, dynamic batch truncation (statistics["whole_valid"]), no
+    debug maps (pass draw_debug=False like train.py:556-564); with a Scene built with requires_grad=True the result can
+    be back-propagated (detach_N mirrors Microfacet.detach_N, which train.py turns off after the first iterations)."""
+    if sc.requires_grad and recur == 0:
+        sc._deriv = sc._env = sc._sh = None          # cached tables belong to the previous autograd graph
     aux = {}
-    xyz, valid, z, dists = sample_rays(sc, rays, focal, override_near)
+    whole = torch.ones(rays.shape[0], dtype=torch.bool)
+    if is_train:
+        xyz, valid, z, dists, whole = sample_rays(sc, rays, focal, override_near, True, rng, ray_keys, max_samples)
+        rays = rays[whole]
+        if ray_keys is not None:
+            ray_keys = ray_keys[whole.numpy()]
+    else:
+        xyz, valid, z, dists = sample_rays(sc, rays, focal, override_near)
+    B = rays.shape[0]
     M = xyz.shape[0]
     S = valid.shape[1]
     n_samples = [M]
@@ -688,7 +755,8 @@ def render_chunk(sc, rays, focal, rng, ray_keys=None, recur=0, start_mip=None, o
     def trace(brays, mip, retrace, keys):
         if retrace:
             im, st = render_chunk(sc, brays, focal, rng, keys, recur + 1, mip.reshape(-1),
-                                  3 * sc.stepsize, white_bg=False, tonemap=False, draw_debug=False)
+                                  3 * sc.stepsize, white_bg=False, tonemap=False, draw_debug=False,
+                                  is_train=is_train, detach_N=detach_N, max_samples=max_samples)   # tensor_nerf.py:291-317
             n_samples.extend(st["n_samples"])
             return im["rgb_map"]
         return env_lookup(sc, brays[..., 3:6], mip.reshape(-1), rng)
@@ -698,7 +766,7 @@ def render_chunk(sc, rays, focal, rng, ray_keys=None, recur=0, start_mip=None, o
         if sc.hp["model"] == "microfacet":
             normals = vm_normals(sc, xyz)
             rgb, debug = shade_microfacet(sc, xyz, feat, view[valid], normals, weights, valid, recur, rng,
-                                          ray_keys, trace, aux)
+                                          ray_keys, trace, aux, is_train=is_train, detach_N=detach_N)
         else:
             rgb, debug = shade_plain(sc, feat, view[valid])
     else:
@@ -709,7 +777,7 @@ def render_chunk(sc, rays, focal, rng, ray_keys=None, recur=0, start_mip=None, o
     ew = pw[..., None]
     rgb_map = row_mask_sum(ew * rgb, valid)
     images = {}
-    stats = dict(recur=recur, whole_valid=torch.ones(B, dtype=torch.bool), n_samples=n_samples)
+    stats = dict(recur=recur, whole_valid=whole, n_samples=n_samples)
     if not white_bg:
         mipv = -100 * torch.ones(B, 1) if start_mip is None else start_mip
         bg = env_lookup(sc, view[:, 0, :], mipv, rng).reshape(-1, 3)
@@ -757,7 +825,8 @@ def training_statistics(sc, aweight, view, world_normal, debug):
     mean_color = torch.exp((sc.brightness + sc.mul * sc.bg_mat).clip(max=20)).reshape(-1, 3).mean(dim=0)
     st["envmap_reg"] = (mean_color.mean() - 0.05).clip(min=0).float()                            # :606-608
     st["brdf_reg"] = debug["tint"].mean().clip(min=0) if "tint" in debug and debug["tint"].numel() else torch.tensor(0.0)
-    st["diffuse_reg"] = ((aweight.reshape(-1, 1) * debug["diffuse"]).sum() / 3) if "diffuse" in debug else torch.tensor(0.0)
+    st["diffuse_reg"] = ((aweight.detach().reshape(-1, 1) * debug["diffuse"]).sum() / 3) if "diffuse" in debug \
+        else torch.tensor(0.0)                                                                   # :639-641
     return st
 
 

@@ -23,12 +23,12 @@ def grid_of(fix):
     return [g] * 3 if isinstance(g, int) else list(g)
 
 
-def oracle_scene(fix):
+def oracle_scene(fix, **kw):
     """oracle.nmf_oracle.Scene of a golden fixture (test side only)."""
     from oracle import nmf_oracle
     model = "microfacet" if fix["model"] == "microfacet_tensorf2" else "plain"
     return nmf_oracle.Scene(fix["state"], fix["aabb"], fix["near_far"], grid_of(fix),
-                            alpha_volume=fix["alpha_volume"].float(), model=model)
+                            alpha_volume=fix["alpha_volume"].float(), model=model, **kw)
 
 
 def device_scene(fix, device, **kw):
