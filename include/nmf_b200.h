@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NMF_ABI_VERSION 5
+#define NMF_ABI_VERSION 6
 
 #define NMF_OK 0
 #define NMF_E_ARG (-1)          /* null pointer / non-positive size                                   */
@@ -116,6 +116,8 @@ typedef struct NmfScene {
   const float* plain_w0t; const float* plain_b0;
   const float* plain_w1t; const float* plain_b1;
   const float* plain_w2t; const float* plain_b2;
+  /* the same weights as stored by the reference, (out, in) row-major: read by the training backward (nmf_train_plain) */
+  const float* plain_w0; const float* plain_w1;
 
   /* bounce budgets: models/microfacet.py:327-349, modules/pt_selectors.py:5-60 */
   int rays_per_ray;        /* 128 */
@@ -255,6 +257,65 @@ int nmf_generate_rays(const float* c2w_host, int H, int W, float fx, float fy, f
  * (floor(clip(rgb, 0, 1) * 255) / 255 - clip(gt, 0, 1))^2 in fp64 -> sum_sq[0] (device).  gt is indexed by
  * pixel_ids[i] when given (rgb is in render order, gt in image order).  PSNR = -10 log10(sum_sq / (3 n)). */
 int nmf_image_sq_error(const float* rgb, const float* gt, const int* pixel_ids, int n, double* sum_sq, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training slice, first model: model=tensorf (models/tensorf.py + MLPRender_Fea).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* AlphaGridSampler.sample with is_train=True (samplers/alphagrid.py:167-173, 353-364): jittered cumulative steps
+ * z = t_min + cumsum(U * stepsize + stepsize / 2) with U keyed by (seed, ray id, step) -- ray id = ray_ids[i] when
+ * given (device, uint64), else ray_id0 + i; the cumulative sum is exact in fp64 and rounded to fp32 per prefix (ATen's
+ * CPU cumsum), so z is bit-reproducible.  Outputs cover ALL n_rays rays: ray_valid (n, n_steps) uint8, z_vals
+ * (n, n_steps), n_valid (n); whole_valid (n) uint8 = rays kept by the dynamic batch truncation (all 1 unless
+ * max_samples > 0 and the batch holds more than max_samples valid samples; then cumsum(n_valid) < max_samples);
+ * n_kept (int[2]) = {kept rays (a prefix of the batch), valid samples of the kept rays}. */
+int nmf_sample_rays_train(const NmfScene* scene, const float* rays, int n_rays, float near_override, uint64_t seed,
+                          uint64_t ray_id0, const uint64_t* ray_ids, int max_samples, uint8_t* ray_valid, float* z_vals,
+                          int* n_valid, uint8_t* whole_valid, int* n_kept, void* stream);
+
+/* gradients of one training step, fp32, device, CHANNEL-LAST like the factors of NmfScene (the host permutes them
+ * back to the reference's (1,C,H,W) parameters); zeroed by nmf_train_plain before it accumulates */
+typedef struct NmfPlainGrads {
+  float* d_plane[3];       /* [h][w][16]  rf.density_rf.app_plane.p */
+  float* d_line[3];        /* [n][16]     rf.density_rf.app_line.p  */
+  float* a_plane[3];       /* [h][w][24]  rf.app_rf.app_plane.p     */
+  float* a_line[3];        /* [n][24]     rf.app_rf.app_line.p      */
+  float* basis_t;          /* [72][24]    rf.basis_mat.weight^T     */
+  float* w0t; float* b0;   /* [135][128], [128]  model.diffuse_module.mlp.0 (transposed weight) */
+  float* w1t; float* b1;   /* [128][128], [128]  mlp.2 */
+  float* w2t; float* b2;   /* [128][3],   [3]    mlp.4 */
+} NmfPlainGrads;
+
+typedef struct NmfTrain {
+  int n_rays;
+  float focal;
+  uint64_t seed, ray_id0;
+  const uint64_t* ray_ids; /* optional (device): global ray ids that key the jitter */
+  int max_samples;         /* AlphaGridSampler.max_samples (<= 0: no truncation) */
+  int cap_samples;         /* capacity of the per-sample scratch; more valid samples than this sets out->error */
+  float lambda_pred;       /* weight of statistics["prediction_loss"] = 2 * sum(acc) (tensor_nerf.py:598-602) */
+  int white_bg;            /* 1: white background (tensor_nerf.py:215,478) */
+} NmfTrain;
+
+typedef struct NmfTrainOut {
+  float* rgb_map;          /* (n,3) rows of the kept rays (a prefix), rest zero */
+  float* acc_map;          /* (n) */
+  uint8_t* whole_valid;    /* (n) statistics["whole_valid"] */
+  double* loss;            /* [2]: sum of squared clipped errors (train.py:597-601), sum of acc */
+  int* n_kept;             /* [2]: kept rays, valid samples (statistics["n_samples"][0]) */
+  unsigned* error;         /* [1]: NMF_DEV_E_SURVIVORS when cap_samples was too small (gradients are then invalid) */
+} NmfTrainOut;
+
+size_t nmf_train_workspace_bytes(const NmfScene* scene, int n_rays, int cap_samples);
+
+/* One training forward + backward of model=tensorf on a ray batch, fused on the device: TensorNeRF.forward
+ * (is_train=True; modules/tensor_nerf.py:210-674) -> models/tensorf.py:70-97 -> the photometric loss of
+ * train.py:576-611 (+ lambda_pred * prediction_loss), then the hand-written backward of every stage (compositing,
+ * softplus density, VM factors, basis_mat, positional encoding, the 135-128-128-3 MLP) into `grads`.
+ * rays (n,6), gt (n,3) device.  No autograd, no host synchronisation. */
+int nmf_train_plain(const NmfScene* scene, const NmfTrain* tp, const float* rays, const float* gt,
+                    const NmfPlainGrads* grads, const NmfTrainOut* out, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ class NmfScene(C.Structure):
         ("env_top", c_float3), ("env_bot", c_float3),
         ("plain_w0t", C.c_void_p), ("plain_b0", C.c_void_p), ("plain_w1t", C.c_void_p), ("plain_b1", C.c_void_p),
         ("plain_w2t", C.c_void_p), ("plain_b2", C.c_void_p),
+        ("plain_w0", C.c_void_p), ("plain_w1", C.c_void_p),
         ("rays_per_ray", C.c_int), ("max_brdf_rays1", C.c_int), ("max_retrace", C.c_int), ("model", C.c_int),
         ("brdf_w0u", C.c_void_p), ("brdf_w1u", C.c_void_p), ("brdf_w2u", C.c_void_p), ("mlp_mode", C.c_int),
     ]
@@ -48,6 +49,23 @@ class NmfRender(C.Structure):
         ("seed", C.c_uint64), ("ray_id0", C.c_uint64),
         ("skip_eps", C.c_float), ("t_cut", C.c_float), ("white_bg", C.c_int), ("cap_scale", C.c_float),
     ]
+
+
+class NmfPlainGrads(C.Structure):
+    _fields_ = [("d_plane", c_ptr3), ("d_line", c_ptr3), ("a_plane", c_ptr3), ("a_line", c_ptr3), ("basis_t", C.c_void_p),
+                ("w0t", C.c_void_p), ("b0", C.c_void_p), ("w1t", C.c_void_p), ("b1", C.c_void_p),
+                ("w2t", C.c_void_p), ("b2", C.c_void_p)]
+
+
+class NmfTrain(C.Structure):
+    _fields_ = [("n_rays", C.c_int), ("focal", C.c_float), ("seed", C.c_uint64), ("ray_id0", C.c_uint64),
+                ("ray_ids", C.c_void_p), ("max_samples", C.c_int), ("cap_samples", C.c_int),
+                ("lambda_pred", C.c_float), ("white_bg", C.c_int)]
+
+
+class NmfTrainOut(C.Structure):
+    _fields_ = [("rgb_map", C.c_void_p), ("acc_map", C.c_void_p), ("whole_valid", C.c_void_p), ("loss", C.c_void_p),
+                ("n_kept", C.c_void_p), ("error", C.c_void_p)]
 
 
 IMAGE_FIELDS = ["rgb_map", "acc_map", "depth", "world_normal", "normal", "termination_xyz", "surf_width",
@@ -123,16 +141,21 @@ def lib():
         "nmf_dense_alpha": (I, [SP, I, I, I, P, P]),
         "nmf_generate_rays": (I, [P, I, I, F, F, F, F, P, I, P, P]),
         "nmf_image_sq_error": (I, [P, P, P, I, P, P]),
+        "nmf_sample_rays_train": (I, [SP, P, I, F, C.c_uint64, C.c_uint64, P, I, P, P, P, P, P, P]),
+        "nmf_train_workspace_bytes": (C.c_size_t, [SP, I, I]),
+        "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
+                                C.c_size_t, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    assert L.nmf_abi_version() == 5, "libnmf_b200.so ABI mismatch: rebuild"
+    assert L.nmf_abi_version() == 6, "libnmf_b200.so ABI mismatch: rebuild"
     _lib = L
     return L
 
 
 EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_profile_phase_name", "nmf_workspace_bytes", "nmf_workspace_bytes_scaled", "nmf_render_rays", "nmf_render_rays_host", "nmf_sample_rays",
             "nmf_vm_density", "nmf_vm_appfeature", "nmf_vm_normals", "nmf_env_lookup", "nmf_ggx_sample",
-            "nmf_brdf_mlp", "nmf_material_heads", "nmf_dense_alpha", "nmf_generate_rays", "nmf_image_sq_error"]
+            "nmf_brdf_mlp", "nmf_material_heads", "nmf_dense_alpha", "nmf_generate_rays", "nmf_image_sq_error",
+            "nmf_sample_rays_train", "nmf_train_workspace_bytes", "nmf_train_plain"]

@@ -1,0 +1,602 @@
+// nmf_b200 -- training slice, first model: model=tensorf.
+//
+// nmf_sample_rays_train: AlphaGridSampler.sample(is_train=True) (samplers/alphagrid.py:131-207, 278-370).
+// nmf_train_plain: one fused forward + backward of TensorNeRF.forward(is_train=True) for model=tensorf and the
+// photometric loss of train.py:576-611, as a fixed sequence of launches (no autograd, no host synchronisation):
+//   k_train_sample     warp per ray: keyed jitter, exact fp64 warp scan of the step lengths, AABB + occupancy test
+//   k_train_prefix     one CTA: per-ray sample offsets and the dynamic batch truncation (whole_valid)
+//   k_train_density    warp per kept ray: ballot compaction of the valid steps, VM density, warp product scan of the
+//                      transmittance -> per-sample (ray, z, dist, f, alpha, T, w), per-ray acc
+//   k_train_mlp<0>     128 samples per CTA: appearance gather, basis, encoding, 135-128-128-3 MLP; rgb per sample,
+//                      w * rgb into the ray
+//   k_train_loss       per ray: tonemap, background, loss, dL/d(linear colour), dL/d(acc)
+//   k_train_mlp<1>     recomputes the tile's forward in shared memory ([feature][sample], stride 132) and walks back:
+//                      weight gradients are per-tile outer-product sums over the 128 samples (thread = output column,
+//                      rows broadcast from shared memory) flushed with coalesced REDs; activations' gradients in place;
+//                      encoding, basis_mat and the appearance factors (16-byte REDs into channel-last buffers)
+//   k_train_composite_bwd  warp per kept ray: reverse warp scan of dw * w, d sigma, softplus', density-factor REDs
+#include <cuda_runtime.h>
+
+#include "nmf_train.cuh"
+
+#define FULL 0xffffffffu
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+#define CKL() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
+#define TS 132              // shared-memory stride of one feature row: columns [k*TS + t] are conflict-free, rows are read
+                            // by their owner thread as 16-byte pieces (quarter-warp phases hit 8 x 4 distinct banks)
+#define TILE 128
+
+static int t_sms = 0;
+static int t_sm_count() {
+  if (!t_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&t_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (t_sms <= 0) t_sms = 148;
+  }
+  return t_sms;
+}
+static int t_check_scene(const NmfScene* s) {
+  if (!s) return NMF_E_ARG;
+  if (s->n_steps <= 0 || s->n_steps > NMF_MAX_STEPS) return NMF_E_UNSUPPORTED;
+  for (int p = 0; p < 3; ++p)
+    if (!s->dval[p] || !s->lval[p] || s->plane_w[p] < 2 || s->plane_h[p] < 2 || s->line_n[p] < 2) return NMF_E_ARG;
+  if (s->plane_w[1] != s->plane_w[0] || s->line_n[2] != s->plane_w[0] || s->plane_w[2] != s->plane_h[0] ||
+      s->line_n[1] != s->plane_h[0] || s->plane_h[2] != s->plane_h[1] || s->line_n[0] != s->plane_h[1])
+    return NMF_E_UNSUPPORTED;
+  if (s->has_occ && (!s->occ_vox || !s->occ_cell || (s->opitch & 31))) return NMF_E_ARG;
+  return NMF_OK;
+}
+
+// ================================================================================================
+// sampling (train)
+// ================================================================================================
+struct SampleArgs {
+  const float* rays; int n; float near_override; uint64_t seed, ray_id0; const uint64_t* ray_ids;
+  uint8_t* valid; float* z; int* n_valid;
+};
+__global__ void __launch_bounds__(256) k_train_sample(const NmfScene s, const SampleArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ray >= a.n) return;
+  float o[3], d[3];
+  for (int i = 0; i < 3; ++i) { o[i] = a.rays[(size_t)ray * 6 + i]; d[i] = a.rays[(size_t)ray * 6 + 3 + i]; }
+  const float tmin = nmf_ray_tmin(o, d, s.aabb0, s.aabb1, a.near_override >= 0.f ? a.near_override : s.near, s.far);
+  const uint64_t key = nmf_primary_key(a.seed, a.ray_ids ? a.ray_ids[ray] : a.ray_id0 + (uint64_t)ray);
+  double carry = 0.0;
+  int nv = 0;
+  for (int base = 0; base < s.n_steps; base += 32) {
+    const int k = base + lane;
+    // every partial sum of <= 2048 fp32 step lengths in [stepsize/2, 3 stepsize/2] is exact in fp64 (37 significant
+    // bits), so the scan order does not matter: prefix == ATen's sequential fp64 accumulation, rounded to fp32
+    double v = k < s.n_steps ? (double)nmf_jitter_step(key, k, s.stepsize) : 0.0;
+    for (int off = 1; off < 32; off <<= 1) {
+      const double u = __shfl_up_sync(FULL, v, off);
+      if (lane >= off) v += u;
+    }
+    v += carry;
+    carry = __shfl_sync(FULL, v, 31);
+    if (k < s.n_steps) {
+      const float z = NMF_ADD(tmin, (float)v);
+      float p[3];
+      nmf_step_pos(o, d, z, p);
+      bool ok = nmf_inside(p, s.aabb0, s.aabb1);
+      if (ok && s.has_occ) {
+        float xn[3];
+        nmf_normalize_xyz(s, p, xn);
+        ok = nmf_occupied(s.occ_vox, s.occ_cell, s.ow, s.oh, s.od, s.opitch, xn[0], xn[1], xn[2]);
+      }
+      a.valid[(size_t)ray * s.n_steps + k] = ok;
+      a.z[(size_t)ray * s.n_steps + k] = z;
+      nv += ok;
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) nv += __shfl_xor_sync(FULL, nv, off);
+  if (lane == 0) a.n_valid[ray] = nv;
+}
+
+// one CTA of 1024 threads: inclusive sums of n_valid -> whole_valid, offsets (alphagrid.py:353-364)
+__global__ void __launch_bounds__(1024) k_train_prefix(const int* n_valid, int n, int max_samples, int* offs, uint8_t* whole,
+                                                       int* n_kept) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int b = t * per, e = min(n, b + per);
+  long long sum = 0;
+  for (int i = b; i < e; ++i) sum += n_valid[i];
+  part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const long long v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  const long long total = part[1023];
+  const bool trunc = max_samples > 0 && total > (long long)max_samples;
+  long long run = t ? part[t - 1] : 0;
+  int last = -1;
+  long long last_incl = 0;
+  for (int i = b; i < e; ++i) {
+    const long long incl = run + n_valid[i];
+    const bool keep = !trunc || incl < (long long)max_samples;   // the inclusive sums are monotone: kept rays are a prefix
+    whole[i] = keep;
+    if (offs) offs[i] = (int)run;            // exclusive prefix (used for kept rays only)
+    if (keep) { last = i; last_incl = incl; }
+    run = incl;
+  }
+  if (last >= 0) {                           // n_kept is zeroed by the caller
+    atomicMax(n_kept, last + 1);
+    atomicMax(n_kept + 1, (int)last_incl);
+  }
+}
+
+extern "C" int nmf_sample_rays_train(const NmfScene* scene, const float* rays, int n_rays, float near_override, uint64_t seed,
+                                     uint64_t ray_id0, const uint64_t* ray_ids, int max_samples, uint8_t* ray_valid,
+                                     float* z_vals, int* n_valid, uint8_t* whole_valid, int* n_kept, void* stream) {
+  int st = t_check_scene(scene);
+  if (st) return st;
+  if (!rays || n_rays <= 0 || !ray_valid || !z_vals || !n_valid) return NMF_E_ARG;
+  cudaStream_t cs = (cudaStream_t)stream;
+  SampleArgs a{rays, n_rays, near_override, seed, ray_id0, ray_ids, ray_valid, z_vals, n_valid};
+  k_train_sample<<<(n_rays + 7) / 8, 256, 0, cs>>>(*scene, a);
+  CKL();
+  if (whole_valid && n_kept) {
+    CK(cudaMemsetAsync(n_kept, 0, 2 * sizeof(int), cs));
+    k_train_prefix<<<1, 1024, 0, cs>>>(n_valid, n_rays, max_samples, (int*)nullptr, whole_valid, n_kept);
+    CKL();
+  }
+  return NMF_OK;
+}
+
+// ================================================================================================
+// fused training step, model=tensorf
+// ================================================================================================
+struct TWS {
+  uint8_t* valid; float* z; int* n_valid; int* offs;
+  float* lin;     // [n][3] sum w * rgb  (zeroed)
+  float* acc;     // [n]
+  float* g_lin;   // [n][3]
+  float* g_acc;   // [n]
+  int* s_ray; float* s_z; float* s_dist; float* s_f; float* s_alpha; float* s_T; float* s_w; float* s_rgb; float* s_dw;
+  size_t zero_off, zero_bytes, total;
+};
+static size_t t_align(size_t x) { return (x + 255) & ~(size_t)255; }
+static void t_carve(TWS& w, const NmfScene* s, int n, int cap, char* base) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += t_align(bytes); return p; };
+  w.zero_off = off;
+  w.lin = (float*)take((size_t)n * 3 * 4);
+  w.acc = (float*)take((size_t)n * 4);
+  w.zero_bytes = off - w.zero_off;
+  w.valid = (uint8_t*)take((size_t)n * s->n_steps);
+  w.z = (float*)take((size_t)n * s->n_steps * 4);
+  w.n_valid = (int*)take((size_t)n * 4);
+  w.offs = (int*)take((size_t)n * 4);
+  w.g_lin = (float*)take((size_t)n * 3 * 4);
+  w.g_acc = (float*)take((size_t)n * 4);
+  w.s_ray = (int*)take((size_t)cap * 4);
+  w.s_z = (float*)take((size_t)cap * 4);
+  w.s_dist = (float*)take((size_t)cap * 4);
+  w.s_f = (float*)take((size_t)cap * 4);
+  w.s_alpha = (float*)take((size_t)cap * 4);
+  w.s_T = (float*)take((size_t)cap * 4);
+  w.s_w = (float*)take((size_t)cap * 4);
+  w.s_rgb = (float*)take((size_t)cap * 3 * 4);
+  w.s_dw = (float*)take((size_t)cap * 4);
+  w.total = off;
+}
+extern "C" size_t nmf_train_workspace_bytes(const NmfScene* scene, int n_rays, int cap_samples) {
+  if (!scene || n_rays <= 0 || cap_samples <= 0) return 0;
+  TWS w;
+  t_carve(w, scene, n_rays, cap_samples, nullptr);
+  return w.total;
+}
+
+// warp per kept ray: compaction + density + transmittance (tensor_nerf.py:19-35, 264-289, 366-369)
+struct DensityArgs { const float* rays; const int* n_kept; int cap; unsigned* error; };
+__global__ void __launch_bounds__(256) k_train_density(const NmfScene s, const DensityArgs a, const TWS w) {
+  const int lane = threadIdx.x & 31;
+  const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ray >= a.n_kept[0]) return;
+  if (a.n_kept[1] > a.cap) { if (ray == 0 && lane == 0) atomicOr(a.error, NMF_DEV_E_SURVIVORS); return; }
+  float o[3], d[3];
+  for (int i = 0; i < 3; ++i) { o[i] = a.rays[(size_t)ray * 6 + i]; d[i] = a.rays[(size_t)ray * 6 + 3 + i]; }
+  const uint8_t* valid = w.valid + (size_t)ray * s.n_steps;
+  const float* zs = w.z + (size_t)ray * s.n_steps;
+  int cnt = w.offs[ray];
+  float Tc = 1.0f, accsum = 0.f;
+  for (int base = 0; base < s.n_steps; base += 32) {
+    const int k = base + lane;
+    const bool ok = k < s.n_steps && valid[k];
+    const unsigned m = __ballot_sync(FULL, ok);
+    if (m == 0) continue;
+    float fac = 1.0f, alpha = 0.f, f = 0.f, z = 0.f, dist = 0.f;
+    if (ok) {
+      z = zs[k];
+      dist = k + 1 < s.n_steps ? NMF_SUB(zs[k + 1], z) : 0.f;           // alphagrid.py:343-345 (last = 0)
+      float p[3], xn[3];
+      nmf_step_pos(o, d, z, p);
+      nmf_normalize_xyz(s, p, xn);
+      const NmfTaps t = nmf_vm_taps(s, xn);
+      for (int g = 0; g < 4; ++g) f += nmf_density_group(s, t, g);
+      const float sigma = nmf_feature2density(f, s.density_shift);
+      dist = dist * s.distance_scale;
+      alpha = 1.0f - expf(-sigma * dist);
+      fac = 1.0f - alpha + 1e-10f;
+    }
+    float incl = fac;                        // inclusive product scan in step order (invalid lanes contribute 1)
+    for (int off = 1; off < 32; off <<= 1) {
+      const float u = __shfl_up_sync(FULL, incl, off);
+      if (lane >= off) incl *= u;
+    }
+    float excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float T = Tc * excl;
+    Tc *= __shfl_sync(FULL, incl, 31);
+    if (ok) {
+      const int i = cnt + __popc(m & ((1u << lane) - 1u));
+      const float wt = alpha * T;
+      w.s_ray[i] = ray; w.s_z[i] = z; w.s_dist[i] = dist; w.s_f[i] = f; w.s_alpha[i] = alpha; w.s_T[i] = T; w.s_w[i] = wt;
+      accsum += wt;
+    }
+    cnt += __popc(m);
+  }
+  for (int off = 16; off > 0; off >>= 1) accsum += __shfl_xor_sync(FULL, accsum, off);
+  if (lane == 0) w.acc[ray] = accsum;
+}
+
+// per ray: loss head
+struct LossArgs { const float* gt; const int* n_kept; int n; float lambda_pred; int white_bg; float* rgb_map; float* acc_map; double* loss; };
+__global__ void __launch_bounds__(256) k_train_loss(const LossArgs a, const TWS w) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  float lp = 0.f, la = 0.f;
+  if (ray < a.n) {
+    float map[3] = {0.f, 0.f, 0.f}, acc = 0.f;
+    if (ray < a.n_kept[0]) {
+      const float bg[3] = {a.white_bg ? 1.f : 0.f, a.white_bg ? 1.f : 0.f, a.white_bg ? 1.f : 0.f};
+      acc = w.acc[ray];
+      float gl[3], ga;
+      lp = nmf_train_loss_ray(w.lin + 3 * (size_t)ray, acc, bg, a.gt + 3 * (size_t)ray, a.lambda_pred, map, gl, &ga);
+      la = acc;
+      for (int c = 0; c < 3; ++c) w.g_lin[3 * (size_t)ray + c] = gl[c];
+      w.g_acc[ray] = ga;
+    }
+    if (a.rgb_map) for (int c = 0; c < 3; ++c) a.rgb_map[3 * (size_t)ray + c] = map[c];
+    if (a.acc_map) a.acc_map[ray] = acc;
+  }
+  for (int off = 16; off > 0; off >>= 1) { lp += __shfl_xor_sync(FULL, lp, off); la += __shfl_xor_sync(FULL, la, off); }
+  if ((threadIdx.x & 31) == 0 && (lp != 0.f || la != 0.f)) {
+    atomicAdd(a.loss, (double)lp);
+    atomicAdd(a.loss + 1, (double)la);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the MLP tile kernel.  Shared memory: X [135][TS], H1 [128][TS], H2 [128][TS], D2 [3][128]
+// ------------------------------------------------------------------------------------------------
+#define SM_X 0
+#define SM_H1 (135 * TS)
+#define SM_H2 (SM_H1 + 128 * TS)
+#define SM_D2 (SM_H2 + 128 * TS)
+#define SM_FLOATS (SM_D2 + 3 * 128)
+
+// out[t-th column of `dst`] = relu(b + W^T in) for 128 outputs in two halves of 64 register accumulators
+template <int K>
+__device__ __forceinline__ void tile_layer(const float* in, float* dst, const float* wt, const float* b, int t) {
+  for (int half = 0; half < 2; ++half) {
+    float h[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) h[i] = __ldg(b + half * 64 + i);
+    for (int k = 0; k < K; ++k) {
+      const float xv = in[k * TS + t];
+      const float4* wr = (const float4*)(wt + k * 128 + half * 64);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float4 wv = __ldg(wr + q);
+        h[4 * q] += xv * wv.x; h[4 * q + 1] += xv * wv.y; h[4 * q + 2] += xv * wv.z; h[4 * q + 3] += xv * wv.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 64; ++i) dst[(half * 64 + i) * TS + t] = fmaxf(h[i], 0.f);
+  }
+}
+// G[k][j = t] += sum_s A[k][s] * D[t][s] for k in [k0, k0 + NK): thread t owns output column t; A rows are broadcast
+template <int NK>
+__device__ __forceinline__ void tile_outer(const float* A, const float* D, float* G, int k0, int t) {
+  float acc[NK];
+#pragma unroll
+  for (int i = 0; i < NK; ++i) acc[i] = 0.f;
+  const float4* drow = (const float4*)(D + t * TS);
+  for (int q = 0; q < TILE / 4; ++q) {
+    const float4 dv = drow[q];
+#pragma unroll
+    for (int i = 0; i < NK; ++i) {
+      const float4 av = *(const float4*)(A + (k0 + i) * TS + 4 * q);
+      acc[i] += av.x * dv.x + av.y * dv.y + av.z * dv.z + av.w * dv.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NK; ++i) atomicAdd(G + (size_t)(k0 + i) * 128 + t, acc[i]);
+}
+// sum over the 128 samples of row `r` (read by one thread)
+__device__ __forceinline__ float tile_rowsum(const float* r) {
+  float b = 0.f;
+  for (int q = 0; q < TILE / 4; ++q) { const float4 v = ((const float4*)r)[q]; b += v.x + v.y + v.z + v.w; }
+  return b;
+}
+__device__ __forceinline__ float tile_rowdot(const float* r, const float* c) {
+  float b = 0.f;
+  for (int q = 0; q < TILE / 4; ++q) {
+    const float4 v = ((const float4*)r)[q], u = ((const float4*)c)[q];
+    b += v.x * u.x + v.y * u.y + v.z * u.z + v.w * u.w;
+  }
+  return b;
+}
+
+struct MlpArgs { const float* rays; const int* n_kept; int cap; NmfPlainGrads g; };
+template <int BWD>
+__global__ void __launch_bounds__(TILE, 1) k_train_mlp(const NmfScene s, const MlpArgs a, const TWS w) {
+  extern __shared__ __align__(16) float sm[];
+  float* X = sm + SM_X;
+  float* H1 = sm + SM_H1;
+  float* H2 = sm + SM_H2;
+  float* D2 = sm + SM_D2;
+  const int t = threadIdx.x;
+  const int M = min(a.n_kept[1], a.cap);
+  if (a.n_kept[1] > a.cap) return;
+  for (int tile = blockIdx.x * TILE; tile < M; tile += gridDim.x * TILE) {
+    const int si = tile + t;
+    const bool active = si < M;
+    int ray = 0;
+    float dv[3] = {0.f, 0.f, 0.f}, feat[24];
+    NmfTaps tp;
+    {
+      float o[3] = {0.f, 0.f, 0.f}, p[3], xn[3];
+      float z = 0.f;
+      if (active) {
+        ray = w.s_ray[si];
+        z = w.s_z[si];
+        for (int i = 0; i < 3; ++i) { o[i] = a.rays[(size_t)ray * 6 + i]; dv[i] = a.rays[(size_t)ray * 6 + 3 + i]; }
+      }
+      nmf_step_pos(o, dv, z, p);
+      nmf_normalize_xyz(s, p, xn);
+      tp = nmf_vm_taps(s, xn);
+    }
+    {
+      float coef[72];
+      nmf_app_coef(s, tp, coef);
+      for (int oo = 0; oo < 24; ++oo) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 72; ++j) acc += __ldg(s.basis_t + j * 24 + oo) * coef[j];
+        feat[oo] = active ? acc : 0.f;
+      }
+    }
+    nmf_plain_encode(feat, dv, X + t, TS);
+    tile_layer<135>(X, H1, s.plain_w0t, s.plain_b0, t);
+    tile_layer<128>(H1, H2, s.plain_w1t, s.plain_b1, t);
+    float o3[3] = {__ldg(s.plain_b2), __ldg(s.plain_b2 + 1), __ldg(s.plain_b2 + 2)};
+    for (int k = 0; k < 128; ++k) {
+      const float hv = H2[k * TS + t];
+      const float* w2 = s.plain_w2t + k * 3;
+      o3[0] += hv * __ldg(w2); o3[1] += hv * __ldg(w2 + 1); o3[2] += hv * __ldg(w2 + 2);
+    }
+    float rgb[3];
+    for (int c = 0; c < 3; ++c) rgb[c] = nmf_sigmoid(o3[c]);
+    if (!BWD) {
+      if (active) {
+        const float wt = w.s_w[si];
+        for (int c = 0; c < 3; ++c) {
+          w.s_rgb[3 * (size_t)si + c] = rgb[c];
+          atomicAdd(w.lin + 3 * (size_t)ray + c, wt * rgb[c]);
+        }
+      }
+      continue;                                   // forward: no cross-thread sharing of the tile buffers
+    }
+    // ---- backward ----
+    float dpre[3] = {0.f, 0.f, 0.f};
+    if (active) {
+      const float wt = w.s_w[si];
+      float dw = w.g_acc[ray];
+      for (int c = 0; c < 3; ++c) {
+        const float gl = w.g_lin[3 * (size_t)ray + c];
+        dw += gl * rgb[c];
+        dpre[c] = wt * gl * rgb[c] * (1.0f - rgb[c]);
+      }
+      w.s_dw[si] = dw;
+    }
+    for (int c = 0; c < 3; ++c) D2[c * 128 + t] = dpre[c];
+    __syncthreads();
+    {  // (a) dW2t[k = t][c], db2
+      const float* hrow = H2 + t * TS;
+      atomicAdd(a.g.w2t + t * 3, tile_rowdot(hrow, D2));
+      atomicAdd(a.g.w2t + t * 3 + 1, tile_rowdot(hrow, D2 + 128));
+      atomicAdd(a.g.w2t + t * 3 + 2, tile_rowdot(hrow, D2 + 256));
+      if (t < 3) atomicAdd(a.g.b2 + t, tile_rowsum(D2 + t * 128));
+    }
+    __syncthreads();
+    // (b) dh2 in place (own column)
+    for (int k = 0; k < 128; ++k) {
+      const float hv = H2[k * TS + t];
+      const float* w2 = s.plain_w2t + k * 3;
+      H2[k * TS + t] = hv > 0.f ? __ldg(w2) * dpre[0] + __ldg(w2 + 1) * dpre[1] + __ldg(w2 + 2) * dpre[2] : 0.f;
+    }
+    __syncthreads();
+    // (c) dW1t[k][j = t] += sum_s H1[k][s] dH2[t][s];  db1[t]
+    tile_outer<64>(H1, H2, a.g.w1t, 0, t);
+    tile_outer<64>(H1, H2, a.g.w1t, 64, t);
+    atomicAdd(a.g.b1 + t, tile_rowsum(H2 + t * TS));
+    __syncthreads();
+    // (d) dh1 in place (own column): dh1[k] = [h1[k] > 0] sum_j W1[j][k] dh2[j]
+    for (int half = 0; half < 2; ++half) {
+      float h[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) h[i] = 0.f;
+      for (int j = 0; j < 128; ++j) {
+        const float d2 = H2[j * TS + t];
+        const float4* wr = (const float4*)(s.plain_w1 + j * 128 + half * 64);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float4 wv = __ldg(wr + q);
+          h[4 * q] += d2 * wv.x; h[4 * q + 1] += d2 * wv.y; h[4 * q + 2] += d2 * wv.z; h[4 * q + 3] += d2 * wv.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        float* q = H1 + (half * 64 + i) * TS + t;
+        *q = *q > 0.f ? h[i] : 0.f;
+      }
+    }
+    __syncthreads();
+    // (e) dW0t[k][j = t] += sum_s X[k][s] dH1[t][s];  db0[t]
+    tile_outer<45>(X, H1, a.g.w0t, 0, t);
+    tile_outer<45>(X, H1, a.g.w0t, 45, t);
+    tile_outer<45>(X, H1, a.g.w0t, 90, t);
+    atomicAdd(a.g.b0 + t, tile_rowsum(H1 + t * TS));
+    // (f) dx (own column) for the feature rows and their encodings -> dfeat
+    float dfeat[24];
+    {
+      float dxa[24], dxs[48], dxc[48];
+#pragma unroll
+      for (int i = 0; i < 24; ++i) dxa[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 48; ++i) { dxs[i] = 0.f; dxc[i] = 0.f; }
+      for (int j = 0; j < 128; ++j) {
+        const float d1 = H1[j * TS + t];
+        const float* wr = s.plain_w0 + j * 135;
+#pragma unroll
+        for (int i = 0; i < 24; ++i) dxa[i] += d1 * __ldg(wr + i);
+#pragma unroll
+        for (int i = 0; i < 48; ++i) { dxs[i] += d1 * __ldg(wr + 27 + i); dxc[i] += d1 * __ldg(wr + 75 + i); }
+      }
+#pragma unroll
+      for (int oo = 0; oo < 24; ++oo)
+        dfeat[oo] = nmf_plain_encode_bwd(X + t, TS, oo, dxa[oo], dxs[2 * oo], dxs[2 * oo + 1], dxc[2 * oo], dxc[2 * oo + 1]);
+    }
+    __syncthreads();                              // every thread is done with X (e) before it is overwritten
+    for (int oo = 0; oo < 24; ++oo) X[oo * TS + t] = active ? dfeat[oo] : 0.f;
+    {
+      float coef[72];                             // gathered again (cheap next to the MLP) rather than kept live
+      nmf_app_coef(s, tp, coef);
+      for (int j = 0; j < 72; ++j) X[(24 + j) * TS + t] = active ? coef[j] : 0.f;
+    }
+    __syncthreads();
+    // (g) d basis_t[j][o] += sum_s coef_j[s] dfeat_o[s]
+    for (int idx = t; idx < 72 * 24; idx += TILE) {
+      atomicAdd(a.g.basis_t + idx, tile_rowdot(X + (24 + idx / 24) * TS, X + (idx % 24) * TS));
+    }
+    // (h) appearance factors (own sample)
+    if (active) {
+      float dcoef[72];
+      for (int j = 0; j < 72; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int oo = 0; oo < 24; ++oo) acc += __ldg(s.basis_t + j * 24 + oo) * dfeat[oo];
+        dcoef[j] = acc;
+      }
+      nmf_app_bwd(s, tp, dcoef, a.g.a_plane, a.g.a_line);
+    }
+    __syncthreads();                              // the next tile's forward overwrites X / H1 / H2
+  }
+}
+
+// warp per kept ray, samples walked from the last to the first
+struct CompArgs { const float* rays; const int* n_kept; int cap; NmfPlainGrads g; };
+__global__ void __launch_bounds__(256) k_train_composite_bwd(const NmfScene s, const CompArgs a, const TWS w) {
+  const int lane = threadIdx.x & 31;
+  const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ray >= a.n_kept[0] || a.n_kept[1] > a.cap) return;
+  const int b = w.offs[ray], n = w.n_valid[ray];
+  float o[3], d[3];
+  for (int i = 0; i < 3; ++i) { o[i] = a.rays[(size_t)ray * 6 + i]; d[i] = a.rays[(size_t)ray * 6 + 3 + i]; }
+  float carry = 0.f;                              // sum of dw_j w_j over the samples after the current group
+  for (int hi = n; hi > 0; hi -= 32) {
+    const int i = hi - 1 - lane;                  // lane 0 = last sample of the group
+    const bool ok = i >= 0;
+    const float dw = ok ? w.s_dw[b + i] : 0.f, wt = ok ? w.s_w[b + i] : 0.f;
+    float incl = dw * wt;                         // inclusive scan over lanes = over later samples
+    for (int off = 1; off < 32; off <<= 1) {
+      const float u = __shfl_up_sync(FULL, incl, off);
+      if (lane >= off) incl += u;
+    }
+    const float suffix = carry + incl - dw * wt;
+    carry += __shfl_sync(FULL, incl, 31);
+    if (ok) {
+      const float f = w.s_f[b + i];
+      const float dsigma = nmf_composite_bwd(dw, w.s_T[b + i], w.s_alpha[b + i], w.s_dist[b + i], suffix);
+      const float df = dsigma * nmf_feature2density_grad(f, s.density_shift);
+      if (df != 0.f) {
+        float p[3], xn[3];
+        nmf_step_pos(o, d, w.s_z[b + i], p);
+        nmf_normalize_xyz(s, p, xn);
+        const NmfTaps t = nmf_vm_taps(s, xn);
+        nmf_density_bwd(s, t, df, a.g.d_plane, a.g.d_line);
+      }
+    }
+  }
+}
+
+extern "C" int nmf_train_plain(const NmfScene* scene, const NmfTrain* tp, const float* rays, const float* gt,
+                               const NmfPlainGrads* grads, const NmfTrainOut* out, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  int st = t_check_scene(scene);
+  if (st) return st;
+  if (!tp || !rays || !gt || !grads || !out || !workspace || tp->n_rays <= 0 || tp->cap_samples <= 0) return NMF_E_ARG;
+  if (scene->model != 1 || !scene->plain_w0t || !scene->plain_w0 || !scene->plain_w1 || !scene->aval[0] || !scene->basis_t)
+    return NMF_E_UNSUPPORTED;
+  if (!out->loss || !out->n_kept || !out->error || !out->whole_valid) return NMF_E_ARG;
+  const int n = tp->n_rays, cap = tp->cap_samples;
+  TWS w;
+  t_carve(w, scene, n, cap, (char*)workspace);
+  if (workspace_bytes < w.total) return NMF_E_WORKSPACE;
+  cudaStream_t cs = (cudaStream_t)stream;
+  // zero: per-ray accumulators, outputs, gradients
+  CK(cudaMemsetAsync((char*)workspace + w.zero_off, 0, w.zero_bytes, cs));
+  CK(cudaMemsetAsync(out->loss, 0, 2 * sizeof(double), cs));
+  CK(cudaMemsetAsync(out->n_kept, 0, 2 * sizeof(int), cs));
+  CK(cudaMemsetAsync(out->error, 0, sizeof(unsigned), cs));
+  for (int p = 0; p < 3; ++p) {
+    const size_t hw = (size_t)scene->plane_h[p] * scene->plane_w[p];
+    if (!grads->d_plane[p] || !grads->d_line[p] || !grads->a_plane[p] || !grads->a_line[p]) return NMF_E_ARG;
+    CK(cudaMemsetAsync(grads->d_plane[p], 0, hw * 16 * 4, cs));
+    CK(cudaMemsetAsync(grads->a_plane[p], 0, hw * 24 * 4, cs));
+    CK(cudaMemsetAsync(grads->d_line[p], 0, (size_t)scene->line_n[p] * 16 * 4, cs));
+    CK(cudaMemsetAsync(grads->a_line[p], 0, (size_t)scene->line_n[p] * 24 * 4, cs));
+  }
+  if (!grads->basis_t || !grads->w0t || !grads->b0 || !grads->w1t || !grads->b1 || !grads->w2t || !grads->b2) return NMF_E_ARG;
+  CK(cudaMemsetAsync(grads->basis_t, 0, 72 * 24 * 4, cs));
+  CK(cudaMemsetAsync(grads->w0t, 0, 135 * 128 * 4, cs));
+  CK(cudaMemsetAsync(grads->b0, 0, 128 * 4, cs));
+  CK(cudaMemsetAsync(grads->w1t, 0, 128 * 128 * 4, cs));
+  CK(cudaMemsetAsync(grads->b1, 0, 128 * 4, cs));
+  CK(cudaMemsetAsync(grads->w2t, 0, 128 * 3 * 4, cs));
+  CK(cudaMemsetAsync(grads->b2, 0, 3 * 4, cs));
+
+  SampleArgs sa{rays, n, -1.0f, tp->seed, tp->ray_id0, tp->ray_ids, w.valid, w.z, w.n_valid};
+  const int warp_blocks = (n + 7) / 8;
+  k_train_sample<<<warp_blocks, 256, 0, cs>>>(*scene, sa);
+  CKL();
+  k_train_prefix<<<1, 1024, 0, cs>>>(w.n_valid, n, tp->max_samples, w.offs, out->whole_valid, out->n_kept);
+  CKL();
+  DensityArgs da{rays, out->n_kept, cap, out->error};
+  k_train_density<<<warp_blocks, 256, 0, cs>>>(*scene, da, w);
+  CKL();
+  const size_t smem = (size_t)SM_FLOATS * sizeof(float);
+  CK(cudaFuncSetAttribute(k_train_mlp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_train_mlp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int tiles = (cap + TILE - 1) / TILE;
+  const int grid = tiles < t_sm_count() ? tiles : t_sm_count();      // one resident CTA per SM (202 KB of shared memory)
+  MlpArgs ma{rays, out->n_kept, cap, *grads};
+  k_train_mlp<0><<<grid, TILE, smem, cs>>>(*scene, ma, w);
+  CKL();
+  LossArgs la{gt, out->n_kept, n, tp->lambda_pred, tp->white_bg, out->rgb_map, out->acc_map, out->loss};
+  k_train_loss<<<(n + 255) / 256, 256, 0, cs>>>(la, w);
+  CKL();
+  k_train_mlp<1><<<grid, TILE, smem, cs>>>(*scene, ma, w);
+  CKL();
+  CompArgs ca{rays, out->n_kept, cap, *grads};
+  k_train_composite_bwd<<<warp_blocks, 256, 0, cs>>>(*scene, ca, w);
+  CKL();
+  return NMF_OK;
+}

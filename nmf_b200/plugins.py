@@ -225,16 +225,28 @@ class AlphaGridSampler(nn.Module):
     @torch.no_grad()
     def sample(self, rays_chunk, focal, rf, override_near=None, is_train=False, dynamic_batch_size=True,
                override_alpha_thres=None, stepmul=1, ndc_ray=False, **args):
-        """samplers/alphagrid.py:278-370 (eval mode): xyzs (M,4), ray_valid (B,S), S, z_vals, dists, whole_valid"""
-        if is_train or ndc_ray:
-            raise NotImplementedError("AlphaGridSampler.sample: only the eval, non-NDC path is implemented")
+        """samplers/alphagrid.py:278-370: xyzs (M,4), ray_valid (b,S), S, z_vals (b,S), dists (b,S), whole_valid (B).
+        is_train=True: jittered cumulative steps keyed by (seed, ray id, step) -- keywords `seed`, `ray_id0` / `ray_ids` --
+        and, with dynamic_batch_size, the truncation to the rays whose cumulative sample count stays below max_samples."""
+        if ndc_ray:
+            raise NotImplementedError("AlphaGridSampler.sample: the NDC path is not implemented")
         sc = self._scene(rf)
         rays = rays_chunk[:, :6].contiguous()
-        ray_valid, z_vals, _ = ops.sample_rays(sc, rays, override_near)
+        whole_valid = torch.ones(rays.shape[0], dtype=torch.bool, device=rays.device)
+        if is_train:
+            from . import train
+            ray_valid, z_vals, _, whole, kept = train.sample_rays_train(
+                sc, rays, seed=args.get("seed", 0), ray_id0=args.get("ray_id0", 0), ray_ids=args.get("ray_ids"),
+                max_samples=self.max_samples if dynamic_batch_size else -1, override_near=override_near)
+            n = int(kept[0])                                   # the kept rays are a prefix of the batch
+            if n < rays.shape[0]:
+                whole_valid = whole
+                rays, ray_valid, z_vals = rays[:n], ray_valid[:n], z_vals[:n]
+        else:
+            ray_valid, z_vals, _ = ops.sample_rays(sc, rays, override_near)
         pts = rays[:, None, :3] + rays[:, None, 3:6] * z_vals[..., None]
         xyzs = torch.cat([pts, z_vals[..., None] / focal], dim=-1)[ray_valid]
         dists = torch.cat((z_vals[:, 1:] - z_vals[:, :-1], torch.zeros_like(z_vals[:, :1])), dim=-1)
-        whole_valid = torch.ones(rays.shape[0], dtype=torch.bool, device=rays.device)
         return xyzs, ray_valid, z_vals.shape[1], z_vals, dists, whole_valid
 
 
@@ -466,6 +478,7 @@ class TensorNeRF(nn.Module):
         self.near_far = list(near_far)
         self.skip_eps, self.t_cut, self.seed, self.mlp = ops.DEFAULT_SKIP_EPS, ops.DEFAULT_T_CUT, 20211200, "f16"
         self._scene, self._scene_key, self._bufs, self._calls = None, None, None, 0
+        self._train_bufs = None
 
     def get_device(self):
         return self.rf.units.device
@@ -524,6 +537,34 @@ class TensorNeRF(nn.Module):
             stats[k] = [c[k] for c in st["statistics"]]
         stats["envmap_reg"] = [env_reg] * len(st["statistics"])
         return ims, stats
+
+    def train_step(self, rays, gt, focal=1.0, ray_ids=None, lambda_pred=0.0):
+        """Forward + backward of one training iteration (train.py:540-700) in ONE fused device call (nmf_train_plain): the
+        training forward of modules/tensor_nerf.py:210-674 (jittered sampling, dynamic batch truncation), the photometric
+        loss of train.py:597-601 (+ lambda_pred * prediction_loss) and the hand-written backward.  Accumulates into the
+        `.grad` of every parameter (a SUM over rays; the caller divides by the batch size like train.py:709) and returns
+        (loss, statistics).  Covers model=tensorf; the microfacet backward is the rest of SURVEY 8f row 1."""
+        from . import train
+        sc = self.scene()
+        if sc.hp["model"] != "plain":
+            raise NotImplementedError("TensorNeRF.train_step: the fused backward covers model=tensorf (SURVEY 8f row 1)")
+        out = train.train_plain(sc, rays.to(self.get_device()), gt.to(self.get_device()), focal=focal,
+                                seed=self.seed + self._calls, ray_ids=ray_ids, max_samples=self.sampler.max_samples,
+                                lambda_pred=lambda_pred, buffers=self._train_bufs)
+        self._train_bufs = out["buffers"]
+        self._calls += 1
+        params = dict(self.named_parameters())
+        for k, g in out["grads"].reference_layout().items():
+            p = params[k]
+            if p.grad is None:
+                p.grad = g.view_as(p).clone()
+            else:
+                p.grad.add_(g.view_as(p))
+        stats = dict(recur=0, whole_valid=out["whole_valid"], n_samples=[out["n_samples"]],
+                     prediction_loss=2.0 * out["sum_acc"], ori_loss=0.0, diffuse_reg=0.0, brdf_reg=0.0, distortion_loss=0.0,
+                     envmap_reg=self._envmap_reg())
+        images = dict(rgb_map=out["rgb_map"][:out["n_rays"]], acc_map=out["acc_map"][:out["n_rays"]])
+        return out["loss_photo"] + lambda_pred * stats["prediction_loss"], images, stats
 
     def _envmap_reg(self):
         """modules/tensor_nerf.py:606-610: (bg_module.mean_color().mean() - 0.05).clip(min=0)"""

@@ -176,6 +176,8 @@ class DeviceScene:
                 w, b = f32(state[f"model.diffuse_module.mlp.{li}.weight"]), f32(state[f"model.diffuse_module.mlp.{li}.bias"])
                 self._ptr(s, f"plain_w{i}t", w.t().contiguous())
                 self._ptr(s, f"plain_b{i}", b)
+                if i < 2:
+                    self._ptr(s, f"plain_w{i}", w)       # (out, in) as stored: read by the training backward
             assert tuple(self.keep["plain_w0t"].shape) == (135, 128) and tuple(self.keep["plain_w2t"].shape) == (128, 3)
         for k in ("diffuse_mul", "diffuse_bias", "tint_bias", "f0_bias", "roughness_bias", "brdf_bias", "anoise"):
             setattr(s, k, float(self.hp[k]))

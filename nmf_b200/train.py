@@ -1,0 +1,197 @@
+"""Training slice, first model: ``model=tensorf`` (models/tensorf.py + MLPRender_Fea).
+
+``train_plain`` runs ONE fused forward + backward on the device (``nmf_train_plain``: hand-written CUDA for every stage,
+no autograd) and returns the loss terms and the gradient of every parameter under its reference state_dict key and in
+the reference's layout, so that the reference's optimiser loop (train.py:497-813: Adam over ``get_optparam_groups``)
+can consume it unchanged.  ``PlainTrainer`` is that loop for this model: ray batches, the step, ``torch.optim.Adam``
+(plumbing), re-packing of the updated factors, and -- when ``torch.distributed`` is initialised -- the single flat
+gradient all-reduce of ray-sharded training (distributed.FlatGradBucket).
+
+There is no CPU / PyTorch fallback: the step raises when libnmf_b200.so is missing or the tensors are not on a GPU.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .ops import _f32, _p, _stream
+
+PLAIN_PARAM_KEYS = ([f"rf.density_rf.app_plane.{p}" for p in range(3)] + [f"rf.density_rf.app_line.{p}" for p in range(3)] +
+                    [f"rf.app_rf.app_plane.{p}" for p in range(3)] + [f"rf.app_rf.app_line.{p}" for p in range(3)] +
+                    ["rf.basis_mat.weight"] +
+                    [f"model.diffuse_module.mlp.{i}.{w}" for i in (0, 2, 4) for w in ("weight", "bias")])
+
+
+class PlainGradBuffers:
+    """Channel-last gradient buffers of nmf_train_plain (struct NmfPlainGrads) for one scene geometry."""
+
+    def __init__(self, scene):
+        dev, s = scene.device, scene.c
+        self.t = {}
+        self.c = _lib.NmfPlainGrads()
+        z = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)
+        for p in range(3):
+            h, w, n = s.plane_h[p], s.plane_w[p], s.line_n[p]
+            for name, t, arr in ((f"d_plane{p}", z(h, w, 16), self.c.d_plane), (f"d_line{p}", z(n, 16), self.c.d_line),
+                                 (f"a_plane{p}", z(h, w, 24), self.c.a_plane), (f"a_line{p}", z(n, 24), self.c.a_line)):
+                self.t[name] = t
+                arr[p] = t.data_ptr()
+        for name, shape in (("basis_t", (72, 24)), ("w0t", (135, 128)), ("b0", (128,)), ("w1t", (128, 128)), ("b1", (128,)),
+                            ("w2t", (128, 3)), ("b2", (3,))):
+            self.t[name] = z(*shape)
+            setattr(self.c, name, self.t[name].data_ptr())
+
+    def zero_(self):
+        for t in self.t.values():
+            t.zero_()
+
+    def reference_layout(self):
+        """{reference state_dict key: gradient in the parameter's own shape}: planes (1,C,H,W), lines (1,C,N,1),
+        basis_mat (24,72), mlp weights (out,in)."""
+        g = {}
+        for p in range(3):
+            g[f"rf.density_rf.app_plane.{p}"] = self.t[f"d_plane{p}"].permute(2, 0, 1)[None].contiguous()
+            g[f"rf.density_rf.app_line.{p}"] = self.t[f"d_line{p}"].t()[None, :, :, None].contiguous()
+            g[f"rf.app_rf.app_plane.{p}"] = self.t[f"a_plane{p}"].permute(2, 0, 1)[None].contiguous()
+            g[f"rf.app_rf.app_line.{p}"] = self.t[f"a_line{p}"].t()[None, :, :, None].contiguous()
+        g["rf.basis_mat.weight"] = self.t["basis_t"].t().contiguous()
+        for i, li in enumerate((0, 2, 4)):
+            g[f"model.diffuse_module.mlp.{li}.weight"] = self.t[f"w{i}t"].t().contiguous()
+            g[f"model.diffuse_module.mlp.{li}.bias"] = self.t[f"b{i}"].clone()
+        return g
+
+
+class TrainBuffers:
+    """Outputs + scratch of nmf_train_plain for batches of up to n_rays rays and cap_samples valid samples."""
+
+    def __init__(self, scene, n_rays, cap_samples):
+        dev = scene.device
+        self.n_rays, self.cap_samples = int(n_rays), int(cap_samples)
+        self.rgb_map = torch.zeros(n_rays, 3, device=dev)
+        self.acc_map = torch.zeros(n_rays, device=dev)
+        self.whole_valid = torch.zeros(n_rays, dtype=torch.uint8, device=dev)
+        self.loss = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.n_kept = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.error = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.c = _lib.NmfTrainOut(rgb_map=self.rgb_map.data_ptr(), acc_map=self.acc_map.data_ptr(),
+                                  whole_valid=self.whole_valid.data_ptr(), loss=self.loss.data_ptr(),
+                                  n_kept=self.n_kept.data_ptr(), error=self.error.data_ptr())
+        self.grads = PlainGradBuffers(scene)
+        nbytes = _lib.lib().nmf_train_workspace_bytes(scene.ref(), self.n_rays, self.cap_samples)
+        if nbytes == 0:
+            raise _lib.NmfError("nmf_train_workspace_bytes: bad arguments")
+        self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        self.ws_ptr = self.workspace.data_ptr() + (-self.workspace.data_ptr()) % 256
+        self.ws_bytes = nbytes
+
+
+def sample_rays_train(scene, rays, seed=0, ray_id0=0, ray_ids=None, max_samples=-1, override_near=None):
+    """AlphaGridSampler.sample(is_train=True) (samplers/alphagrid.py:167-173, 353-364), for ALL rays of the batch:
+    (ray_valid (B,S) bool, z_vals (B,S), n_valid (B) int32, whole_valid (B) bool, (rays kept, samples kept))."""
+    r = _f32(rays[:, :6], scene.device)
+    B, S = r.shape[0], scene.n_steps
+    dev = r.device
+    valid = torch.empty(B, S, dtype=torch.uint8, device=dev)
+    z = torch.empty(B, S, device=dev)
+    nv = torch.empty(B, dtype=torch.int32, device=dev)
+    whole = torch.empty(B, dtype=torch.uint8, device=dev)
+    kept = torch.zeros(2, dtype=torch.int32, device=dev)
+    ids = None if ray_ids is None else ray_ids.to(device=dev, dtype=torch.int64).contiguous()
+    _lib.check(_lib.lib().nmf_sample_rays_train(scene.ref(), _p(r), B, -1.0 if override_near is None else float(override_near),
+                                                int(seed), int(ray_id0), _p(ids), int(max_samples), _p(valid), _p(z), _p(nv),
+                                                _p(whole), _p(kept), _stream()), "nmf_sample_rays_train")
+    return valid.bool(), z, nv, whole.bool(), kept
+
+
+def train_plain(scene, rays, gt, focal=1.0, seed=0, ray_id0=0, ray_ids=None, max_samples=-1, lambda_pred=0.0,
+                cap_samples=None, buffers=None, check_errors=True):
+    """One fused training forward + backward of model=tensorf (nmf_train_plain).  rays (B,>=6), gt (B,3) on the GPU.
+    Returns dict(loss_photo, sum_acc, n_rays, n_samples, whole_valid, rgb_map, acc_map, grads (channel-last buffers),
+    buffers).  With check_errors the call synchronises and regrows the per-sample scratch when it overflowed."""
+    if scene.hp["model"] != "plain":
+        raise _lib.NmfError("train_plain: the training slice covers model=tensorf (a 'plain' DeviceScene)")
+    r = _f32(rays[:, :6], scene.device)
+    g = _f32(gt.reshape(-1, 3), scene.device)
+    B = r.shape[0]
+    if g.shape[0] != B:
+        raise _lib.NmfError("train_plain: gt must hold one colour per ray")
+    ids = None if ray_ids is None else ray_ids.to(device=r.device, dtype=torch.int64).contiguous()
+    if cap_samples is None:
+        cap_samples = int(max_samples) if max_samples > 0 else 64 * B
+    while True:
+        if buffers is None or buffers.n_rays < B or buffers.cap_samples < cap_samples:
+            buffers = TrainBuffers(scene, B, cap_samples)
+        tp = _lib.NmfTrain(n_rays=B, focal=float(focal), seed=int(seed), ray_id0=int(ray_id0),
+                           ray_ids=None if ids is None else ids.data_ptr(), max_samples=int(max_samples),
+                           cap_samples=buffers.cap_samples, lambda_pred=float(lambda_pred), white_bg=1)
+        st = _lib.lib().nmf_train_plain(scene.ref(), C.byref(tp), _p(r), _p(g), C.byref(buffers.grads.c), C.byref(buffers.c),
+                                        C.c_void_p(buffers.ws_ptr), buffers.ws_bytes, _stream())
+        _lib.check(st, "nmf_train_plain")
+        out = dict(buffers=buffers, grads=buffers.grads, rgb_map=buffers.rgb_map[:B], acc_map=buffers.acc_map[:B],
+                   whole_valid=buffers.whole_valid[:B].bool(), loss=buffers.loss, n_kept=buffers.n_kept)
+        if not check_errors:
+            return out
+        kept = buffers.n_kept.tolist()                        # synchronises
+        if int(buffers.error.item()):
+            if kept[1] <= buffers.cap_samples:
+                raise _lib.NmfOverflow("nmf_train_plain: device error without an overflow")
+            cap_samples = int(kept[1] * 1.25) + 1024          # the per-sample scratch was too small: grow, step again
+            buffers = None
+            continue
+        loss = buffers.loss.tolist()
+        out.update(loss_photo=loss[0], sum_acc=loss[1], n_rays=kept[0], n_samples=kept[1])
+        return out
+
+
+class PlainTrainer:
+    """The optimiser loop of train.py:497-813 for model=tensorf: parameters are kept in the reference's layout and under
+    the reference's state_dict keys (a checkpoint loads / saves unchanged), every step is one nmf_train_plain call, the
+    update is torch.optim.Adam (train.py:301-303: betas (0.9, 0.99)), and the device scene is re-packed from the updated
+    parameters.  With torch.distributed initialised each rank trains on its own ray ids and the gradients are summed with
+    ONE all-reduce over a flat bucket before the update."""
+
+    def __init__(self, state, aabb, near_far, grid_size, alpha_volume=None, device="cuda", lr_grid=2e-2, lr_net=1e-3,
+                 max_samples=-1, lambda_pred=0.0, seed=0, **hp):
+        from .distributed import FlatGradBucket
+        from .scene import DeviceScene
+        self.device = torch.device(device)
+        self.meta = dict(aabb=aabb, near_far=near_far, grid_size=grid_size, hp=dict(hp, model="plain"))
+        self.alpha_volume = alpha_volume
+        self.state = {k: torch.as_tensor(v).detach().clone().to(self.device) for k, v in state.items()}
+        self.params = {k: torch.nn.Parameter(self.state[k].float()) for k in PLAIN_PARAM_KEYS}
+        grid = [self.params[k] for k in PLAIN_PARAM_KEYS if k.startswith("rf.") and "basis" not in k]
+        net = [self.params[k] for k in PLAIN_PARAM_KEYS if not (k.startswith("rf.") and "basis" not in k)]
+        self.optimizer = torch.optim.Adam([dict(params=grid, lr=lr_grid), dict(params=net, lr=lr_net)], betas=(0.9, 0.99))
+        self.bucket = FlatGradBucket(list(self.params.values()))
+        self.max_samples, self.lambda_pred, self.seed = max_samples, lambda_pred, seed
+        self.iteration = 0
+        self.buffers = None
+        self._DeviceScene = DeviceScene
+        self.repack()
+
+    def repack(self):
+        st = dict(self.state)
+        st.update({k: p.detach() for k, p in self.params.items()})
+        m = self.meta
+        self.scene = self._DeviceScene(st, m["aabb"], m["near_far"], m["grid_size"], alpha_volume=self.alpha_volume,
+                                       device=self.device, **m["hp"])
+
+    def step(self, rays, gt, ray_ids=None):
+        """One iteration on this rank's rays (train.py:540-760 without the regularisers that model=tensorf turns off)."""
+        import torch.distributed as dist
+        out = train_plain(self.scene, rays, gt, seed=self.seed + self.iteration, ray_ids=ray_ids,
+                          max_samples=self.max_samples, lambda_pred=self.lambda_pred, buffers=self.buffers)
+        self.buffers = out["buffers"]
+        grads = out["grads"].reference_layout()
+        tot = torch.tensor([float(out["n_rays"]), out["loss_photo"]], device=self.device, dtype=torch.float64)
+        for k, p in self.params.items():
+            p.grad.copy_(grads[k])                            # p.grad is a view into the flat bucket
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(tot)                              # global ray count = the loss normaliser
+        # one flat fp32 all-reduce (NCCL on GPUs), scaled by 1 / lbatch_size (train.py:709)
+        self.bucket.allreduce(scale=1.0 / max(float(tot[0]), 1.0))
+        self.optimizer.step()
+        self.repack()
+        self.iteration += 1
+        out["mse"] = float(tot[1]) / max(3.0 * float(tot[0]), 1.0)
+        return out

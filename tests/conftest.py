@@ -45,7 +45,8 @@ def hostcheck():
     d = os.path.join(ROOT, "tests", "hostcheck")
     so = os.path.join(d, "libnmf_hostcheck.so")
     srcs = [os.path.join(d, "hostcheck.cpp"), os.path.join(ROOT, "nmf_b200", "csrc", "nmf_math.cuh"),
-            os.path.join(ROOT, "nmf_b200", "csrc", "nmf_field.cuh"), os.path.join(ROOT, "include", "nmf_b200.h")]
+            os.path.join(ROOT, "nmf_b200", "csrc", "nmf_field.cuh"), os.path.join(ROOT, "nmf_b200", "csrc", "nmf_train.cuh"),
+            os.path.join(ROOT, "include", "nmf_b200.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, srcs[0]])
     return ctypes.CDLL(so)

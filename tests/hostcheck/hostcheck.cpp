@@ -2,7 +2,9 @@
 // nmf_field.cuh) for the host so that `pytest -m "not gpu"` can check it against the oracle without a GPU.
 // It is not part of the product and nothing under nmf_b200/ loads it.
 //   g++ -O2 -ffp-contract=off -shared -fPIC -o libnmf_hostcheck.so hostcheck.cpp
-#include "../../nmf_b200/csrc/nmf_field.cuh"
+#include <vector>
+
+#include "../../nmf_b200/csrc/nmf_train.cuh"
 
 extern "C" {
 
@@ -111,5 +113,159 @@ void hc_sh9(const float* v, int n, float* out) {
 }
 void hc_srgb(const float* x, int n, float* out) {
   for (int i = 0; i < n; ++i) out[i] = nmf_srgb(x[i]);
+}
+
+// ---- training slice (nmf_b200/csrc/nmf_train.cuh) ----
+// AlphaGridSampler.sample(is_train=True): z = t_min + cumsum(jittered steps); the fp64 sum is exact (see k_train_sample)
+void hc_sample_rays_train(const NmfScene* s, const float* rays, int n, float near_override, uint64_t seed, uint64_t ray_id0,
+                          const uint64_t* ray_ids, uint8_t* valid, float* z) {
+  const int S = s->n_steps;
+  const float near_ = near_override >= 0.f ? near_override : s->near;
+  for (int r = 0; r < n; ++r) {
+    const float* o = rays + 6 * r;
+    const float* d = o + 3;
+    const float tmin = nmf_ray_tmin(o, d, s->aabb0, s->aabb1, near_, s->far);
+    const uint64_t key = nmf_primary_key(seed, ray_ids ? ray_ids[r] : ray_id0 + (uint64_t)r);
+    double run = 0.0;
+    for (int k = 0; k < S; ++k) {
+      run += (double)nmf_jitter_step(key, k, s->stepsize);
+      const float zk = NMF_ADD(tmin, (float)run);
+      float p[3];
+      nmf_step_pos(o, d, zk, p);
+      bool ok = nmf_inside(p, s->aabb0, s->aabb1);
+      if (ok && s->has_occ) {
+        float xn[3];
+        nmf_normalize_xyz(*s, p, xn);
+        ok = nmf_occupied(s->occ_vox, s->occ_cell, s->ow, s->oh, s->od, s->opitch, xn[0], xn[1], xn[2]);
+      }
+      valid[(size_t)r * S + k] = ok;
+      z[(size_t)r * S + k] = zk;
+    }
+  }
+}
+
+// nmf_train_plain restated sequentially from the same per-element functions (the kernels' warp / tile choreography is
+// what `-m gpu` covers).  `g` buffers must be zeroed by the caller.
+void hc_train_plain(const NmfScene* s, const NmfTrain* tp, const float* rays, const float* gt, const NmfPlainGrads* g,
+                    float* rgb_map, float* acc_map, uint8_t* whole, double* loss, int* n_kept) {
+  const int n = tp->n_rays, S = s->n_steps;
+  std::vector<uint8_t> valid((size_t)n * S);
+  std::vector<float> z((size_t)n * S);
+  hc_sample_rays_train(s, rays, n, -1.0f, tp->seed, tp->ray_id0, tp->ray_ids, valid.data(), z.data());
+  std::vector<int> nv(n, 0);
+  long long total = 0;
+  for (int r = 0; r < n; ++r) { for (int k = 0; k < S; ++k) nv[r] += valid[(size_t)r * S + k]; total += nv[r]; }
+  const bool trunc = tp->max_samples > 0 && total > tp->max_samples;
+  long long run = 0;
+  int kept = 0, M = 0;
+  for (int r = 0; r < n; ++r) {
+    run += nv[r];
+    whole[r] = !trunc || run < tp->max_samples;
+    if (whole[r]) { kept = r + 1; M = (int)run; }
+  }
+  n_kept[0] = kept; n_kept[1] = M;
+  loss[0] = loss[1] = 0.0;
+  const float bg[3] = {tp->white_bg ? 1.f : 0.f, tp->white_bg ? 1.f : 0.f, tp->white_bg ? 1.f : 0.f};
+  struct Smp { float z, dist, f, alpha, T, w, rgb[3], x[135], h1[128], h2[128], dw; NmfTaps t; };
+  for (int r = 0; r < n; ++r) {
+    for (int c = 0; c < 3; ++c) rgb_map[3 * r + c] = 0.f;
+    acc_map[r] = 0.f;
+    if (r >= kept) continue;
+    const float* o = rays + 6 * r;
+    const float* d = o + 3;
+    std::vector<Smp> sm;
+    float T = 1.0f, acc = 0.f, lin[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < S; ++k) {
+      if (!valid[(size_t)r * S + k]) continue;
+      Smp q;
+      q.z = z[(size_t)r * S + k];
+      q.dist = (k + 1 < S ? NMF_SUB(z[(size_t)r * S + k + 1], q.z) : 0.f) * s->distance_scale;
+      float p[3], xn[3];
+      nmf_step_pos(o, d, q.z, p);
+      nmf_normalize_xyz(*s, p, xn);
+      q.t = nmf_vm_taps(*s, xn);
+      q.f = 0.f;
+      for (int gi = 0; gi < 4; ++gi) q.f += nmf_density_group(*s, q.t, gi);
+      q.alpha = 1.0f - expf(-nmf_feature2density(q.f, s->density_shift) * q.dist);
+      q.T = T;
+      q.w = q.alpha * T;
+      T *= 1.0f - q.alpha + 1e-10f;
+      acc += q.w;
+      // appearance + MLP forward
+      float coef[72], feat[24];
+      nmf_app_coef(*s, q.t, coef);
+      for (int oo = 0; oo < 24; ++oo) {
+        float a = 0.f;
+        for (int j = 0; j < 72; ++j) a += s->basis_t[j * 24 + oo] * coef[j];
+        feat[oo] = a;
+      }
+      nmf_plain_encode(feat, d, q.x, 1);
+      for (int j = 0; j < 128; ++j) {
+        float a = s->plain_b0[j];
+        for (int i = 0; i < 135; ++i) a += q.x[i] * s->plain_w0t[i * 128 + j];
+        q.h1[j] = fmaxf(a, 0.f);
+      }
+      for (int j = 0; j < 128; ++j) {
+        float a = s->plain_b1[j];
+        for (int i = 0; i < 128; ++i) a += q.h1[i] * s->plain_w1t[i * 128 + j];
+        q.h2[j] = fmaxf(a, 0.f);
+      }
+      for (int c = 0; c < 3; ++c) {
+        float a = s->plain_b2[c];
+        for (int i = 0; i < 128; ++i) a += q.h2[i] * s->plain_w2t[i * 3 + c];
+        q.rgb[c] = nmf_sigmoid(a);
+        lin[c] += q.w * q.rgb[c];
+      }
+      sm.push_back(q);
+    }
+    float gl[3], ga;
+    loss[0] += nmf_train_loss_ray(lin, acc, bg, gt + 3 * r, tp->lambda_pred, rgb_map + 3 * r, gl, &ga);
+    loss[1] += acc;
+    acc_map[r] = acc;
+    // backward: MLP, encoding, basis, appearance factors
+    for (Smp& q : sm) {
+      float dpre[3], dh2[128], dh1[128], dx[135], dfeat[24], coef[72], dcoef[72];
+      q.dw = ga;
+      for (int c = 0; c < 3; ++c) {
+        q.dw += gl[c] * q.rgb[c];
+        dpre[c] = q.w * gl[c] * q.rgb[c] * (1.0f - q.rgb[c]);
+        g->b2[c] += dpre[c];
+      }
+      for (int k = 0; k < 128; ++k) {
+        float a = 0.f;
+        for (int c = 0; c < 3; ++c) { g->w2t[k * 3 + c] += q.h2[k] * dpre[c]; a += s->plain_w2t[k * 3 + c] * dpre[c]; }
+        dh2[k] = q.h2[k] > 0.f ? a : 0.f;
+      }
+      for (int k = 0; k < 128; ++k) {
+        float a = 0.f;
+        for (int j = 0; j < 128; ++j) { g->w1t[k * 128 + j] += q.h1[k] * dh2[j]; a += s->plain_w1[j * 128 + k] * dh2[j]; }
+        dh1[k] = q.h1[k] > 0.f ? a : 0.f;
+      }
+      for (int j = 0; j < 128; ++j) { g->b1[j] += dh2[j]; g->b0[j] += dh1[j]; }
+      for (int i = 0; i < 135; ++i) {
+        float a = 0.f;
+        for (int j = 0; j < 128; ++j) { g->w0t[i * 128 + j] += q.x[i] * dh1[j]; a += s->plain_w0[j * 135 + i] * dh1[j]; }
+        dx[i] = a;
+      }
+      for (int oo = 0; oo < 24; ++oo)
+        dfeat[oo] = nmf_plain_encode_bwd(q.x, 1, oo, dx[oo], dx[27 + 2 * oo], dx[28 + 2 * oo], dx[75 + 2 * oo], dx[76 + 2 * oo]);
+      nmf_app_coef(*s, q.t, coef);
+      for (int j = 0; j < 72; ++j) {
+        float a = 0.f;
+        for (int oo = 0; oo < 24; ++oo) { g->basis_t[j * 24 + oo] += coef[j] * dfeat[oo]; a += s->basis_t[j * 24 + oo] * dfeat[oo]; }
+        dcoef[j] = a;
+      }
+      nmf_app_bwd(*s, q.t, dcoef, g->a_plane, g->a_line);
+    }
+    // backward: compositing and density factors
+    float suffix = 0.f;
+    for (int i = (int)sm.size() - 1; i >= 0; --i) {
+      const Smp& q = sm[i];
+      const float dsigma = nmf_composite_bwd(q.dw, q.T, q.alpha, q.dist, suffix);
+      suffix += q.dw * q.w;
+      const float df = dsigma * nmf_feature2density_grad(q.f, s->density_shift);
+      if (df != 0.f) nmf_density_bwd(*s, q.t, df, g->d_plane, g->d_line);
+    }
+  }
 }
 }

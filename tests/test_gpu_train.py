@@ -1,0 +1,185 @@
+"""GPU: the training slice (model=tensorf) through the C ABI against the oracle.
+
+The oracle's training forward AND its gradients are pinned to the unmodified reference (oracle/check_train.py,
+tests/test_oracle_golden.py::test_oracle_training_gradients_reproduce_reference); here the oracle consumes the keyed
+jitter (KeyedRNG) the kernels draw, so sampling is compared bit for bit and losses / gradients to a stated tolerance
+(2e-3 of each gradient's largest entry: fp32 atomics accumulate ~1e5 terms per entry in arbitrary order)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import device_scene, load_fixture, oracle_scene
+from test_hostmath import check_plain_grads, oracle_train_plain
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from nmf_b200 import _lib
+    _lib.lib()          # raises if the extension is missing: no fallback
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("name", ["plain_g64", "microfacet_g40", "microfacet_noncubic"])
+def test_train_sampler_bit_exact(env, name):
+    """A1/A2 in train mode: jittered cumulative steps, validity, per-ray counts, dynamic batch truncation"""
+    from nmf_b200 import train
+    from oracle import keyed_rng as KR
+    from oracle import nmf_oracle as O
+    fix = load_fixture(name)
+    osc, dsc = oracle_scene(fix), device_scene(fix, env)
+    rays = fix["rays"][:1024].contiguous()
+    ids = np.arange(500, 500 + rays.shape[0]).astype(np.uint64)
+    keys = KR.primary_ray_keys(7, ids)
+    _, valid, z, _, _ = O.sample_rays(osc, rays, fix["focal"], None, True, KR.KeyedRNG(), keys, -1)
+    total = int(valid.sum())
+    for max_samples in (-1, total // 2, total + 10):
+        v, zz, nv, whole, kept = train.sample_rays_train(dsc, rays.cuda(), seed=7, ray_id0=500, max_samples=max_samples)
+        assert torch.equal(zz.cpu(), z)
+        assert torch.equal(v.cpu(), valid)
+        assert torch.equal(nv.cpu().long(), valid.sum(1))
+        _, ov, _, _, owhole = O.sample_rays(osc, rays, fix["focal"], None, True, KR.KeyedRNG(), keys, max_samples)
+        assert torch.equal(whole.cpu(), owhole)
+        assert kept.tolist() == [int(owhole.sum()), int(ov.sum())]
+        if 0 < max_samples < total:
+            assert 0 < int(kept[0]) < rays.shape[0]
+    # explicit ray ids and a near override (the secondary-ray form of the call)
+    v2, z2, _, _, _ = train.sample_rays_train(dsc, rays.cuda(), seed=7, ray_ids=torch.from_numpy(ids.astype(np.int64)))
+    assert torch.equal(z2.cpu(), z) and torch.equal(v2.cpu(), valid)
+    near = 3 * float(osc.stepsize)
+    _, ovn, ozn, _, _ = O.sample_rays(osc, rays, fix["focal"], near, True, KR.KeyedRNG(), keys, -1)
+    v3, z3, _, _, _ = train.sample_rays_train(dsc, rays.cuda(), seed=7, ray_id0=500, override_near=near)
+    assert torch.equal(z3.cpu(), ozn) and torch.equal(v3.cpu(), ovn)
+
+
+def test_sampler_plugin_train_mode(env):
+    """AlphaGridSampler.sample(is_train=True) as TensorNeRF.forward calls it (tensor_nerf.py:237-255)"""
+    from nmf_b200 import config
+    from oracle import keyed_rng as KR
+    from oracle import nmf_oracle as O
+    fix = load_fixture("microfacet_g40")
+    G = fix["grid_size"]
+    t, _ = config.build_model([f"field.grid_size=[{G},{G},{G}]", "model.arch.bg_module.bg_resolution=32"],
+                              aabb=fix["aabb"], near_far=list(fix["near_far"]))
+    t.load_state_dict(fix["state"], strict=False)
+    t = t.cuda().eval()
+    t.sampler.update(t.rf, init=True)
+    t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
+    osc = oracle_scene(fix)
+    rays = fix["rays"][:512]
+    keys = KR.primary_ray_keys(3, np.arange(rays.shape[0]))
+    t.sampler.max_samples = 6000
+    oxyz, ovalid, oz, odists, owhole = O.sample_rays(osc, rays, fix["focal"], None, True, KR.KeyedRNG(), keys, 6000)
+    xyzs, ray_valid, S, z_vals, dists, whole = t.sampler.sample(rays.cuda(), fix["focal"], rf=t.rf, is_train=True, seed=3)
+    assert 0 < int(owhole.sum()) < rays.shape[0]
+    assert torch.equal(whole.cpu(), owhole) and torch.equal(ray_valid.cpu(), ovalid) and torch.equal(z_vals.cpu(), oz)
+    assert torch.equal(dists.cpu(), odists) and torch.equal(xyzs.cpu()[:, :3], oxyz[:, :3])
+
+
+@pytest.mark.parametrize("n,max_samples", [(256, -1), (256, 6000), (1000, -1)])
+def test_train_plain_matches_oracle_gradients(env, n, max_samples):
+    """nmf_train_plain: loss, images, whole_valid and the gradient of EVERY parameter against the oracle's autograd"""
+    from nmf_b200 import train
+    fix = load_fixture("plain_g64")
+    dsc = device_scene(fix, env)
+    rays = fix["rays"][:n].contiguous()
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
+    ids = np.arange(n).astype(np.uint64)
+    ref = oracle_train_plain(fix, rays, gt, 21, ids, max_samples, 0.001)
+    out = train.train_plain(dsc, rays.cuda(), gt.cuda(), focal=fix["focal"], seed=21, max_samples=max_samples,
+                            lambda_pred=0.001, cap_samples=4096)       # small on purpose: exercises the regrow path
+    assert torch.equal(out["whole_valid"].cpu(), ref["whole"])
+    assert out["n_rays"] == int(ref["whole"].sum()) and out["n_samples"] == ref["n_samples"]
+    if max_samples > 0:
+        assert 0 < out["n_rays"] < n
+    nk = out["n_rays"]
+    assert float((out["rgb_map"][:nk].cpu() - ref["rgb_map"]).abs().max()) < 2e-5
+    assert abs(out["loss_photo"] - ref["photo"]) <= 1e-4 * max(1.0, ref["photo"])
+    assert abs(out["sum_acc"] - ref["acc"]) <= 1e-4 * max(1.0, ref["acc"])
+    check_plain_grads(out["grads"].reference_layout(), ref["grads"])
+
+
+def test_train_plain_directional_derivative(env):
+    """size-independent property: <grad, v> equals the central finite difference of the loss along v (fixed jitter seed)"""
+    from nmf_b200 import train
+    from nmf_b200.scene import DeviceScene
+    from conftest import grid_of
+    fix = load_fixture("plain_g64")
+    n = 2048
+    rays = fix["rays"][:n].cuda()
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(9)).cuda()
+    state = {k: v.clone() for k, v in fix["state"].items()}
+
+    def scene_of(st):
+        return DeviceScene(st, fix["aabb"], fix["near_far"], grid_of(fix), alpha_volume=fix["alpha_volume"], device=env,
+                           model="plain")
+
+    def loss_of(st):
+        o = train.train_plain(scene_of(st), rays, gt, focal=fix["focal"], seed=4)
+        return o["loss_photo"], o
+
+    _, out = loss_of(state)
+    grads = {k: v.cpu().double() for k, v in out["grads"].reference_layout().items()}
+    g = torch.Generator().manual_seed(1)
+    for keys, eps in ((["model.diffuse_module.mlp.4.bias", "model.diffuse_module.mlp.2.weight"], 2e-3),
+                      (["rf.basis_mat.weight"], 2e-3),
+                      ([f"rf.app_rf.app_plane.{p}" for p in range(3)] + [f"rf.app_rf.app_line.{p}" for p in range(3)], 2e-3),
+                      ([f"rf.density_rf.app_plane.{p}" for p in range(3)], 5e-3)):
+        v = {k: torch.randn(state[k].shape, generator=g) for k in keys}
+        plus = dict(state); minus = dict(state)
+        for k in keys:
+            plus[k] = state[k] + eps * v[k]
+            minus[k] = state[k] - eps * v[k]
+        fd = (loss_of(plus)[0] - loss_of(minus)[0]) / (2 * eps)
+        an = sum(float((grads[k] * v[k].double()).sum()) for k in keys)
+        assert abs(fd - an) <= 3e-2 * max(abs(an), abs(fd)) + 1e-3, (keys[0], fd, an)
+
+
+def test_trainer_reduces_loss(env):
+    """the optimiser loop (train.PlainTrainer): perturbed weights are pulled back towards the images they came from"""
+    from conftest import grid_of
+    from nmf_b200 import ops, train
+    fix = load_fixture("plain_g64")
+    dsc = device_scene(fix, env)
+    n = 2048
+    rays = fix["rays"][:n].cuda()
+    target, _ = ops.render_rays(dsc, rays, fix["focal"], chunk=n, skip_eps=0.0, t_cut=0.0)
+    gt = target["rgb_map"].clone()
+    g = torch.Generator().manual_seed(2)
+    state = {k: v.clone() for k, v in fix["state"].items()}
+    for k in train.PLAIN_PARAM_KEYS:
+        if "app_" in k and "density" not in k or "mlp" in k:
+            state[k] = state[k] + 0.05 * state[k].abs().mean() * torch.randn(state[k].shape, generator=g)
+    tr = train.PlainTrainer(state, fix["aabb"], fix["near_far"], grid_of(fix), alpha_volume=fix["alpha_volume"], device=env,
+                            lr_grid=2e-2, lr_net=1e-3)
+    mse = [tr.step(rays, gt)["mse"] for _ in range(40)]
+    assert mse[-1] < 0.5 * mse[0], (mse[0], mse[-1])
+    assert all(np.isfinite(mse))
+
+
+def test_plugin_train_step_fills_grads(env):
+    """TensorNeRF.train_step for model=tensorf: gradients land on the plugin's parameters under the reference's names"""
+    from nmf_b200 import config
+    fix = load_fixture("plain_g64")
+    G = fix["grid_size"]
+    t, _ = config.build_model(["model=tensorf", f"field.grid_size=[{G},{G},{G}]"], aabb=fix["aabb"],
+                              near_far=list(fix["near_far"]))
+    missing = t.load_state_dict(fix["state"], strict=False)
+    t = t.cuda().train()
+    t.sampler.update(t.rf, init=True)
+    from nmf_b200.plugins import AlphaGridMask
+    t.sampler.alphaMask = AlphaGridMask(t.rf.aabb, fix["alpha_volume"].float().cuda()).cuda()
+    n = 512
+    rays, gt = fix["rays"][:n].cuda(), torch.rand(n, 3, generator=torch.Generator().manual_seed(5)).cuda()
+    loss, images, stats = t.train_step(rays, gt, focal=fix["focal"], lambda_pred=0.0)
+    assert np.isfinite(loss) and images["rgb_map"].shape == (n, 3) and stats["n_samples"][0] > 1000
+    params = dict(t.named_parameters())
+    from nmf_b200.train import PLAIN_PARAM_KEYS
+    for k in PLAIN_PARAM_KEYS:
+        assert params[k].grad is not None and params[k].grad.shape == params[k].shape, k
+        assert float(params[k].grad.abs().max()) > 0, k
+    with pytest.raises(NotImplementedError):
+        t.forward(rays, fix["focal"], is_train=True)

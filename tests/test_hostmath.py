@@ -160,3 +160,97 @@ def test_ggx_and_bases(hostcheck):
     y = torch.zeros(n)
     hostcheck.hc_srgb(ptr(x), n, ptr(y))
     assert torch.allclose(y, O.srgb(x, noclip=True), atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training slice: nmf_train.cuh on the host against the oracle (pinned to the reference's forward
+# AND gradients by tests/test_oracle_golden.py::test_oracle_training_gradients_reproduce_reference)
+# ---------------------------------------------------------------------------------------------------------------
+def u64ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("name", ["plain_g64", "microfacet_g40", "microfacet_noncubic"])
+def test_train_sampler_bit_exact(hostcheck, name):
+    """AlphaGridSampler.sample(is_train=True): jittered cumulative steps, validity mask, bit for bit"""
+    fix = load_fixture(name)
+    osc = oracle_scene(fix)
+    dsc = device_scene(fix, "cpu", sh_conv=torch.zeros(9, 3))
+    rays = fix["rays"][:384].contiguous()
+    ids = np.arange(1000, 1000 + rays.shape[0]).astype(np.uint64)
+    keys = KR.primary_ray_keys(11, ids)
+    _, valid, z, dists, whole = O.sample_rays(osc, rays, fix["focal"], None, True, KR.KeyedRNG(), keys, -1)
+    S = osc.n_samples
+    v = torch.zeros(rays.shape[0], S, dtype=torch.uint8)
+    zz = torch.zeros(rays.shape[0], S)
+    hostcheck.hc_sample_rays_train(dsc.ref(), ptr(rays), rays.shape[0], C.c_float(-1.0), C.c_uint64(11), C.c_uint64(1000),
+                                   None, ptr(v), ptr(zz))
+    assert torch.equal(zz, z)
+    assert torch.equal(v.bool(), valid)
+    assert valid.sum() > 1000 and bool(whole.all())
+    # the same ids passed explicitly
+    v2, z2 = torch.zeros_like(v), torch.zeros_like(zz)
+    hostcheck.hc_sample_rays_train(dsc.ref(), ptr(rays), rays.shape[0], C.c_float(-1.0), C.c_uint64(11), C.c_uint64(0),
+                                   u64ptr(ids), ptr(v2), ptr(z2))
+    assert torch.equal(z2, zz) and torch.equal(v2, v)
+
+
+def oracle_train_plain(fix, rays, gt, seed, ids, max_samples, lambda_pred):
+    """loss and gradients of the oracle's training forward (KeyedRNG jitter), reference state_dict keys"""
+    osc = oracle_scene(fix, requires_grad=True)
+    keys = KR.primary_ray_keys(seed, ids)
+    ims, st = O.render_chunk(osc, rays, fix["focal"], KR.KeyedRNG(), keys, draw_debug=False, is_train=True,
+                             max_samples=max_samples)
+    whole = st["whole_valid"]
+    rgb = ims["rgb_map"].clip(max=1)
+    photo = ((rgb.clip(0, 1) - gt[whole].clip(0, 1)) ** 2).sum()
+    loss = photo + lambda_pred * st["prediction_loss"]
+    loss.backward()
+    grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in osc.params.items()}
+    return dict(photo=float(photo.detach()), acc=float(ims["acc_map"].detach().sum()), whole=whole, n_samples=st["n_samples"][0],
+                rgb_map=ims["rgb_map"].detach(), grads=grads)
+
+
+def check_plain_grads(mine, ref, tol=2e-3):
+    bad = {}
+    for k, g in ref.items():
+        if k not in mine:
+            assert float(g.abs().max()) == 0.0 or k.startswith("bg_module"), k
+            continue
+        scale = float(g.abs().max()) + 1e-12
+        err = float((mine[k].cpu() - g).abs().max()) / scale
+        if not err <= tol:
+            bad[k] = err
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("max_samples", [-1, 2500])
+def test_train_plain_host_gradients(hostcheck, max_samples):
+    """the per-element forward + backward math of nmf_train_plain (host build) against the oracle's autograd"""
+    from nmf_b200 import _lib
+    from nmf_b200.train import PlainGradBuffers
+    fix = load_fixture("plain_g64")
+    dsc = device_scene(fix, "cpu")
+    n = 96
+    rays = fix["rays"][:n].contiguous()
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
+    ids = np.arange(n).astype(np.uint64)
+    ref = oracle_train_plain(fix, rays, gt, 21, ids, max_samples, 0.001)
+    gb = PlainGradBuffers(dsc)
+    tp = _lib.NmfTrain(n_rays=n, focal=float(fix["focal"]), seed=21, ray_id0=0, ray_ids=None, max_samples=max_samples,
+                       cap_samples=1 << 20, lambda_pred=0.001, white_bg=1)
+    rgb_map, acc_map = torch.zeros(n, 3), torch.zeros(n)
+    whole = torch.zeros(n, dtype=torch.uint8)
+    loss = torch.zeros(2, dtype=torch.float64)
+    kept = torch.zeros(2, dtype=torch.int32)
+    hostcheck.hc_train_plain(dsc.ref(), C.byref(tp), ptr(rays), ptr(gt), C.byref(gb.c), ptr(rgb_map), ptr(acc_map), ptr(whole),
+                             ptr(loss), ptr(kept))
+    assert torch.equal(whole.bool(), ref["whole"])
+    assert int(kept[0]) == int(ref["whole"].sum()) and int(kept[1]) == ref["n_samples"]
+    if max_samples > 0:
+        assert 0 < int(kept[0]) < n and int(kept[1]) < max_samples
+    nk = int(kept[0])
+    assert float((rgb_map[:nk] - ref["rgb_map"]).abs().max()) < 2e-5
+    assert abs(float(loss[0]) - ref["photo"]) <= 1e-4 * max(1.0, ref["photo"])
+    assert abs(float(loss[1]) - ref["acc"]) <= 1e-4 * max(1.0, ref["acc"])
+    check_plain_grads(gb.reference_layout(), ref["grads"])
