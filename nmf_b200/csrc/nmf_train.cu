@@ -10,9 +10,10 @@
 //   k_train_mlp<0>     128 samples per CTA: appearance gather, basis, encoding, 135-128-128-3 MLP; rgb per sample,
 //                      w * rgb into the ray
 //   k_train_loss       per ray: tonemap, background, loss, dL/d(linear colour), dL/d(acc)
-//   k_train_mlp<1>     recomputes the tile's forward in shared memory ([feature][sample], stride 132) and walks back:
-//                      weight gradients are per-tile outer-product sums over the 128 samples (thread = output column,
-//                      rows broadcast from shared memory) flushed with coalesced REDs; activations' gradients in place;
+//   k_train_mlp<1>     recomputes the tile's forward in shared memory ([feature][sample], stride 136) and walks back: the five
+//                      tile GEMMs (two layers, dW1, dH1, dW0, dX) on the tensor cores as 3xTF32 mma.sync,
+//                      weight gradients are per-tile contractions over the 128 samples flushed with REDs; activations'
+//                      gradients in place;
 //                      encoding, basis_mat and the appearance factors (16-byte REDs into channel-last buffers)
 //   k_train_composite_bwd  warp per kept ray: reverse warp scan of dw * w, d sigma, softplus', density-factor REDs
 #include <cuda_runtime.h>
@@ -22,8 +23,8 @@
 #define FULL 0xffffffffu
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 #define CKL() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
-#define TS 132              // shared-memory stride of one feature row: columns [k*TS + t] are conflict-free, rows are read
-                            // by their owner thread as 16-byte pieces (quarter-warp phases hit 8 x 4 distinct banks)
+#define TS 136              // shared-memory stride of one feature row (136 = 8 mod 32): columns [k*TS + t] and the mma B
+                            // fragments [(k0 + lane%4)*TS + n0 + lane/4] are bank-conflict-free; 16-byte aligned rows
 #define TILE 128
 
 static int t_sms = 0;
@@ -273,51 +274,76 @@ __global__ void __launch_bounds__(256) k_train_loss(const LossArgs a, const TWS 
 }
 
 // ------------------------------------------------------------------------------------------------
-// the MLP tile kernel.  Shared memory: X [135][TS], H1 [128][TS], H2 [128][TS], D2 [3][128]
+// the MLP tile kernel.  Shared memory: X [136][TS] (row 135 = 0: K padding), H1 [128][TS], H2 [128][TS], D2 [3][128].
+// The five tile GEMMs (two forward layers, dW1, dH1, dW0, dX) run on the tensor cores as 3xTF32 mma.sync.m16n8k8
+// (hi*hi + lo*hi + hi*lo: fp32-level accuracy, so the images and gradients stay within the parity tolerances); they
+// are true dense contractions over the 128 samples of the tile.  Everything per sample (gathers, encodings, the
+// 3-wide output layer, scatters) stays on the SIMT pipes, thread = sample = column.
 // ------------------------------------------------------------------------------------------------
 #define SM_X 0
-#define SM_H1 (135 * TS)
+#define SM_H1 (136 * TS)
 #define SM_H2 (SM_H1 + 128 * TS)
 #define SM_D2 (SM_H2 + 128 * TS)
 #define SM_FLOATS (SM_D2 + 3 * 128)
 
-// out[t-th column of `dst`] = relu(b + W^T in) for 128 outputs in two halves of 64 register accumulators
-template <int K>
-__device__ __forceinline__ void tile_layer(const float* in, float* dst, const float* wt, const float* b, int t) {
-  for (int half = 0; half < 2; ++half) {
-    float h[64];
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// One warp: acc[mt][nt] (16 x 8 tiles) += sum_k A(m, k) B(k, n), m in [0, 16 MT), n in [0, 8 NT), k in [0, 8 ksteps).
+// fa(m, k) / fb(k, n) fetch one element (global weights through the read-only path, or shared memory).
+// Fragment layout of m16n8k8: g = lane / 4, t = lane % 4; A: (g, t), (g+8, t), (g, t+4), (g+8, t+4); B: (t, g), (t+4, g);
+// C: (g, 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1).
+template <int MT, int NT, class FA, class FB>
+__device__ __forceinline__ void warp_gemm(float (&acc)[MT][NT][4], int ksteps, FA fa, FB fb, int lane) {
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) h[i] = __ldg(b + half * 64 + i);
-    for (int k = 0; k < K; ++k) {
-      const float xv = in[k * TS + t];
-      const float4* wr = (const float4*)(wt + k * 128 + half * 64);
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const float4 wv = __ldg(wr + q);
-        h[4 * q] += xv * wv.x; h[4 * q + 1] += xv * wv.y; h[4 * q + 2] += xv * wv.z; h[4 * q + 3] += xv * wv.w;
+    for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.f; acc[mt][nt][1] = 0.f; acc[mt][nt][2] = 0.f; acc[mt][nt][3] = 0.f; }
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const int k0 = 8 * ks;
+    uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      split_tf32(fa(16 * mt + g, k0 + t), ah[mt][0], al[mt][0]);
+      split_tf32(fa(16 * mt + g + 8, k0 + t), ah[mt][1], al[mt][1]);
+      split_tf32(fa(16 * mt + g, k0 + t + 4), ah[mt][2], al[mt][2]);
+      split_tf32(fa(16 * mt + g + 8, k0 + t + 4), ah[mt][3], al[mt][3]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      uint32_t bh0, bl0, bh1, bl1;
+      split_tf32(fb(k0 + t, 8 * nt + g), bh0, bl0);
+      split_tf32(fb(k0 + t + 4, 8 * nt + g), bh1, bl1);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        mma_tf32(acc[mt][nt], al[mt], bh0, bh1);
+        mma_tf32(acc[mt][nt], ah[mt], bl0, bl1);
+        mma_tf32(acc[mt][nt], ah[mt], bh0, bh1);
       }
     }
-#pragma unroll
-    for (int i = 0; i < 64; ++i) dst[(half * 64 + i) * TS + t] = fmaxf(h[i], 0.f);
   }
 }
-// G[k][j = t] += sum_s A[k][s] * D[t][s] for k in [k0, k0 + NK): thread t owns output column t; A rows are broadcast
-template <int NK>
-__device__ __forceinline__ void tile_outer(const float* A, const float* D, float* G, int k0, int t) {
-  float acc[NK];
+// visits every accumulator element of the warp: f(row, col, value)
+template <int MT, int NT, class F>
+__device__ __forceinline__ void warp_epilogue(float (&acc)[MT][NT][4], int lane, F f) {
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int i = 0; i < NK; ++i) acc[i] = 0.f;
-  const float4* drow = (const float4*)(D + t * TS);
-  for (int q = 0; q < TILE / 4; ++q) {
-    const float4 dv = drow[q];
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int i = 0; i < NK; ++i) {
-      const float4 av = *(const float4*)(A + (k0 + i) * TS + 4 * q);
-      acc[i] += av.x * dv.x + av.y * dv.y + av.z * dv.z + av.w * dv.w;
+    for (int nt = 0; nt < NT; ++nt) {
+      f(16 * mt + g, 8 * nt + 2 * t, acc[mt][nt][0]);
+      f(16 * mt + g, 8 * nt + 2 * t + 1, acc[mt][nt][1]);
+      f(16 * mt + g + 8, 8 * nt + 2 * t, acc[mt][nt][2]);
+      f(16 * mt + g + 8, 8 * nt + 2 * t + 1, acc[mt][nt][3]);
     }
-  }
-#pragma unroll
-  for (int i = 0; i < NK; ++i) atomicAdd(G + (size_t)(k0 + i) * 128 + t, acc[i]);
 }
 // sum over the 128 samples of row `r` (read by one thread)
 __device__ __forceinline__ float tile_rowsum(const float* r) {
@@ -342,17 +368,18 @@ __global__ void __launch_bounds__(TILE, 1) k_train_mlp(const NmfScene s, const M
   float* H1 = sm + SM_H1;
   float* H2 = sm + SM_H2;
   float* D2 = sm + SM_D2;
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, lane = t & 31, m0 = 32 * (t >> 5);     // warp `t >> 5` owns output rows m0 .. m0 + 31
   const int M = min(a.n_kept[1], a.cap);
   if (a.n_kept[1] > a.cap) return;
+  X[135 * TS + t] = 0.f;                                            // K padding row of the first layer
   for (int tile = blockIdx.x * TILE; tile < M; tile += gridDim.x * TILE) {
     const int si = tile + t;
     const bool active = si < M;
     int ray = 0;
-    float dv[3] = {0.f, 0.f, 0.f}, feat[24];
+    float dv[3] = {0.f, 0.f, 0.f};
     NmfTaps tp;
     {
-      float o[3] = {0.f, 0.f, 0.f}, p[3], xn[3];
+      float o[3] = {0.f, 0.f, 0.f}, p[3], xn[3], coef[72], feat[24];
       float z = 0.f;
       if (active) {
         ray = w.s_ray[si];
@@ -362,9 +389,6 @@ __global__ void __launch_bounds__(TILE, 1) k_train_mlp(const NmfScene s, const M
       nmf_step_pos(o, dv, z, p);
       nmf_normalize_xyz(s, p, xn);
       tp = nmf_vm_taps(s, xn);
-    }
-    {
-      float coef[72];
       nmf_app_coef(s, tp, coef);
       for (int oo = 0; oo < 24; ++oo) {
         float acc = 0.f;
@@ -372,10 +396,22 @@ __global__ void __launch_bounds__(TILE, 1) k_train_mlp(const NmfScene s, const M
         for (int j = 0; j < 72; ++j) acc += __ldg(s.basis_t + j * 24 + oo) * coef[j];
         feat[oo] = active ? acc : 0.f;
       }
+      nmf_plain_encode(feat, dv, X + t, TS);
     }
-    nmf_plain_encode(feat, dv, X + t, TS);
-    tile_layer<135>(X, H1, s.plain_w0t, s.plain_b0, t);
-    tile_layer<128>(H1, H2, s.plain_w1t, s.plain_b1, t);
+    __syncthreads();
+    float acc[2][16][4];
+    // layer 1: H1[j][n] = relu(b0[j] + sum_k W0[j][k] X[k][n])      (W0 as stored: (out, in), row stride 135)
+    warp_gemm<2, 16>(acc, 17,
+                     [&](int m, int k) { return k < 135 ? __ldg(s.plain_w0 + (m0 + m) * 135 + k) : 0.f; },
+                     [&](int k, int n) { return X[k * TS + n]; }, lane);
+    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { H1[(m0 + r) * TS + c] = fmaxf(v + __ldg(s.plain_b0 + m0 + r), 0.f); });
+    __syncthreads();
+    // layer 2
+    warp_gemm<2, 16>(acc, 16, [&](int m, int k) { return __ldg(s.plain_w1 + (m0 + m) * 128 + k); },
+                     [&](int k, int n) { return H1[k * TS + n]; }, lane);
+    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { H2[(m0 + r) * TS + c] = fmaxf(v + __ldg(s.plain_b1 + m0 + r), 0.f); });
+    __syncthreads();
+    // output layer (3 wide) per sample
     float o3[3] = {__ldg(s.plain_b2), __ldg(s.plain_b2 + 1), __ldg(s.plain_b2 + 2)};
     for (int k = 0; k < 128; ++k) {
       const float hv = H2[k * TS + t];
@@ -392,7 +428,7 @@ __global__ void __launch_bounds__(TILE, 1) k_train_mlp(const NmfScene s, const M
           atomicAdd(w.lin + 3 * (size_t)ray + c, wt * rgb[c]);
         }
       }
-      continue;                                   // forward: no cross-thread sharing of the tile buffers
+      continue;      // the next tile's writes to X / H1 / H2 are ordered behind this tile's reads by its own barriers
     }
     // ---- backward ----
     float dpre[3] = {0.f, 0.f, 0.f};
@@ -423,58 +459,36 @@ __global__ void __launch_bounds__(TILE, 1) k_train_mlp(const NmfScene s, const M
       H2[k * TS + t] = hv > 0.f ? __ldg(w2) * dpre[0] + __ldg(w2 + 1) * dpre[1] + __ldg(w2 + 2) * dpre[2] : 0.f;
     }
     __syncthreads();
-    // (c) dW1t[k][j = t] += sum_s H1[k][s] dH2[t][s];  db1[t]
-    tile_outer<64>(H1, H2, a.g.w1t, 0, t);
-    tile_outer<64>(H1, H2, a.g.w1t, 64, t);
+    // (c) dW1t[k][j] += sum_n H1[k][n] dH2[j][n]  (M = k, N = j, contraction over the tile's samples);  db1
+    warp_gemm<2, 16>(acc, 16, [&](int m, int k) { return H1[(m0 + m) * TS + k]; }, [&](int k, int n) { return H2[n * TS + k]; }, lane);
+    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { atomicAdd(a.g.w1t + (m0 + r) * 128 + c, v); });
     atomicAdd(a.g.b1 + t, tile_rowsum(H2 + t * TS));
     __syncthreads();
-    // (d) dh1 in place (own column): dh1[k] = [h1[k] > 0] sum_j W1[j][k] dh2[j]
-    for (int half = 0; half < 2; ++half) {
-      float h[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) h[i] = 0.f;
-      for (int j = 0; j < 128; ++j) {
-        const float d2 = H2[j * TS + t];
-        const float4* wr = (const float4*)(s.plain_w1 + j * 128 + half * 64);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float4 wv = __ldg(wr + q);
-          h[4 * q] += d2 * wv.x; h[4 * q + 1] += d2 * wv.y; h[4 * q + 2] += d2 * wv.z; h[4 * q + 3] += d2 * wv.w;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        float* q = H1 + (half * 64 + i) * TS + t;
-        *q = *q > 0.f ? h[i] : 0.f;
-      }
-    }
+    // (d) dH1[k][n] = [H1[k][n] > 0] sum_j W1[j][k] dH2[j][n], in place (every element has one owner)
+    warp_gemm<2, 16>(acc, 16, [&](int m, int k) { return __ldg(s.plain_w1t + (m0 + m) * 128 + k); },
+                     [&](int k, int n) { return H2[k * TS + n]; }, lane);
+    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { float* q = H1 + (m0 + r) * TS + c; *q = *q > 0.f ? v : 0.f; });
     __syncthreads();
-    // (e) dW0t[k][j = t] += sum_s X[k][s] dH1[t][s];  db0[t]
-    tile_outer<45>(X, H1, a.g.w0t, 0, t);
-    tile_outer<45>(X, H1, a.g.w0t, 45, t);
-    tile_outer<45>(X, H1, a.g.w0t, 90, t);
-    atomicAdd(a.g.b0 + t, tile_rowsum(H1 + t * TS));
-    // (f) dx (own column) for the feature rows and their encodings -> dfeat
-    float dfeat[24];
+    // (e) dW0t[i][j] += sum_n X[i][n] dH1[j][n]: rows 0..127 as above, rows 128..134 as one 16-row tile split over the warps' columns;  db0
+    warp_gemm<2, 16>(acc, 16, [&](int m, int k) { return X[(m0 + m) * TS + k]; }, [&](int k, int n) { return H1[n * TS + k]; }, lane);
+    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { atomicAdd(a.g.w0t + (m0 + r) * 128 + c, v); });
     {
-      float dxa[24], dxs[48], dxc[48];
-#pragma unroll
-      for (int i = 0; i < 24; ++i) dxa[i] = 0.f;
-#pragma unroll
-      for (int i = 0; i < 48; ++i) { dxs[i] = 0.f; dxc[i] = 0.f; }
-      for (int j = 0; j < 128; ++j) {
-        const float d1 = H1[j * TS + t];
-        const float* wr = s.plain_w0 + j * 135;
-#pragma unroll
-        for (int i = 0; i < 24; ++i) dxa[i] += d1 * __ldg(wr + i);
-#pragma unroll
-        for (int i = 0; i < 48; ++i) { dxs[i] += d1 * __ldg(wr + 27 + i); dxc[i] += d1 * __ldg(wr + 75 + i); }
-      }
-#pragma unroll
-      for (int oo = 0; oo < 24; ++oo)
-        dfeat[oo] = nmf_plain_encode_bwd(X + t, TS, oo, dxa[oo], dxs[2 * oo], dxs[2 * oo + 1], dxc[2 * oo], dxc[2 * oo + 1]);
+      float acc1[1][4][4];
+      warp_gemm<1, 4>(acc1, 16, [&](int m, int k) { return X[(128 + m) * TS + k]; }, [&](int k, int n) { return H1[(m0 + n) * TS + k]; }, lane);
+      warp_epilogue<1, 4>(acc1, lane, [&](int r, int c, float v) { if (r < 7) atomicAdd(a.g.w0t + (128 + r) * 128 + m0 + c, v); });
     }
-    __syncthreads();                              // every thread is done with X (e) before it is overwritten
+    atomicAdd(a.g.b0 + t, tile_rowsum(H1 + t * TS));
+    // (f) dX[i][n] = sum_j W0[j][i] dH1[j][n] for input rows 0..127 (features and their encodings are rows 0..122) -> H2
+    warp_gemm<2, 16>(acc, 16, [&](int m, int k) { return __ldg(s.plain_w0t + (m0 + m) * 128 + k); },
+                     [&](int k, int n) { return H1[k * TS + n]; }, lane);
+    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { H2[(m0 + r) * TS + c] = v; });
+    __syncthreads();
+    float dfeat[24];
+#pragma unroll
+    for (int oo = 0; oo < 24; ++oo)
+      dfeat[oo] = nmf_plain_encode_bwd(X + t, TS, oo, H2[oo * TS + t], H2[(27 + 2 * oo) * TS + t], H2[(28 + 2 * oo) * TS + t],
+                                       H2[(75 + 2 * oo) * TS + t], H2[(76 + 2 * oo) * TS + t]);
+    __syncthreads();                              // every thread is done with X before it is overwritten
     for (int oo = 0; oo < 24; ++oo) X[oo * TS + t] = active ? dfeat[oo] : 0.f;
     {
       float coef[72];                             // gathered again (cheap next to the MLP) rather than kept live
@@ -482,18 +496,17 @@ __global__ void __launch_bounds__(TILE, 1) k_train_mlp(const NmfScene s, const M
       for (int j = 0; j < 72; ++j) X[(24 + j) * TS + t] = active ? coef[j] : 0.f;
     }
     __syncthreads();
-    // (g) d basis_t[j][o] += sum_s coef_j[s] dfeat_o[s]
-    for (int idx = t; idx < 72 * 24; idx += TILE) {
+    // (g) d basis_t[j][o] += sum_n coef_j[n] dfeat_o[n]
+    for (int idx = t; idx < 72 * 24; idx += TILE)
       atomicAdd(a.g.basis_t + idx, tile_rowdot(X + (24 + idx / 24) * TS, X + (idx % 24) * TS));
-    }
     // (h) appearance factors (own sample)
     if (active) {
       float dcoef[72];
       for (int j = 0; j < 72; ++j) {
-        float acc = 0.f;
+        float accj = 0.f;
 #pragma unroll
-        for (int oo = 0; oo < 24; ++oo) acc += __ldg(s.basis_t + j * 24 + oo) * dfeat[oo];
-        dcoef[j] = acc;
+        for (int oo = 0; oo < 24; ++oo) accj += __ldg(s.basis_t + j * 24 + oo) * dfeat[oo];
+        dcoef[j] = accj;
       }
       nmf_app_bwd(s, tp, dcoef, a.g.a_plane, a.g.a_line);
     }

@@ -160,6 +160,17 @@ def make_scene(name="lego", grid_size=300, bg_resolution=512, n_density=16, n_ap
     return state, meta
 
 
+def plain_mlp_state(seed=0):
+    """MLPRender_Fea(viewpe=2, feape=2, featureC=128) weights for the model=tensorf plumbing case
+    (modules/render_modules.py:201-235: 135 -> 128 -> 128 -> 3, last bias zero)."""
+    g = torch.Generator().manual_seed(77 + seed)
+    st = {}
+    for li, (o, i) in zip((0, 2, 4), ((128, 135), (128, 128), (3, 128))):
+        st[f"model.diffuse_module.mlp.{li}.weight"] = _kaiming_uniform(o, i, g)
+        st[f"model.diffuse_module.mlp.{li}.bias"] = torch.zeros(o)
+    return st
+
+
 def hemisphere_poses(n=200, seed=1, radius=CAMERA_RADIUS):
     """n camera-to-world matrices (Blender/OpenGL convention) looking at the origin from the upper hemisphere."""
     rs = np.random.RandomState(seed)
