@@ -211,9 +211,13 @@ def oracle_train_plain(fix, rays, gt, seed, ids, max_samples, lambda_pred):
                 rgb_map=ims["rgb_map"].detach(), grads=grads)
 
 
-def check_plain_grads(mine, ref, tol=2e-3, tol_density=1e-2):
-    """max |g - g_ref| <= tol * max |g_ref| per parameter.  The density factors get 1e-2: their gradient divides by
-    (1 - alpha + 1e-10) (cumprod backward, tensor_nerf.py:19-35), which amplifies fp32 rounding on opaque surfaces."""
+def check_plain_grads(mine, ref, tol=5e-3, tol_density=1e-2):
+    """max |g - g_ref| <= tol * max |g_ref| per parameter.  Typical agreement is 1e-5 .. 1e-6 (tools/train_diag.py); the
+    tolerance is set by two discontinuities of the gradient itself: a ReLU whose pre-activation is within fp32 rounding
+    of zero takes the other branch on the GPU (the forward value does not change, that sample's gradient does by a finite
+    amount -- measured 2e-3 of the largest entry for one flipped unit in 17 000 samples), and the density factors'
+    gradient divides by (1 - alpha + 1e-10) (cumprod backward, tensor_nerf.py:19-35), which amplifies fp32 rounding on
+    opaque surfaces (run-to-run 5e-4 with unordered atomics)."""
     bad = {}
     for k, g in ref.items():
         if k not in mine:
