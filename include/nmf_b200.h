@@ -317,6 +317,11 @@ int nmf_train_plain(const NmfScene* scene, const NmfTrain* tp, const float* rays
                     const NmfPlainGrads* grads, const NmfTrainOut* out, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* Resolution schedule (fields/tensor_base.py:234-243 -> fields/tensoRF.py:208-227, 408-413): TensoRF.upsample is
+ * F.interpolate(mode="bilinear", align_corners=True) of every factor.  src (C,H,W) -> dst (C,H2,W2), both in the
+ * reference's own parameter layout (a line (1,C,N,1) is H = N, W = 1). */
+int nmf_upsample_bilinear(const float* src, int C, int H, int W, float* dst, int H2, int W2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

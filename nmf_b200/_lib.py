@@ -143,6 +143,7 @@ def lib():
         "nmf_image_sq_error": (I, [P, P, P, I, P, P]),
         "nmf_sample_rays_train": (I, [SP, P, I, F, C.c_uint64, C.c_uint64, P, I, P, P, P, P, P, P]),
         "nmf_train_workspace_bytes": (C.c_size_t, [SP, I, I]),
+        "nmf_upsample_bilinear": (I, [P, I, I, I, P, I, I, P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
                                 C.c_size_t, P]),
     }
@@ -158,4 +159,4 @@ def lib():
 EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_profile_phase_name", "nmf_workspace_bytes", "nmf_workspace_bytes_scaled", "nmf_render_rays", "nmf_render_rays_host", "nmf_sample_rays",
             "nmf_vm_density", "nmf_vm_appfeature", "nmf_vm_normals", "nmf_env_lookup", "nmf_ggx_sample",
             "nmf_brdf_mlp", "nmf_material_heads", "nmf_dense_alpha", "nmf_generate_rays", "nmf_image_sq_error",
-            "nmf_sample_rays_train", "nmf_train_workspace_bytes", "nmf_train_plain"]
+            "nmf_sample_rays_train", "nmf_train_workspace_bytes", "nmf_train_plain", "nmf_upsample_bilinear"]

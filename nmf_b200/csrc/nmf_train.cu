@@ -317,17 +317,29 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[MT][NT][4], int ksteps, F
       split_tf32(fa(16 * mt + g, k0 + t + 4), ah[mt][2], al[mt][2]);
       split_tf32(fa(16 * mt + g + 8, k0 + t + 4), ah[mt][3], al[mt][3]);
     }
+    // B fragments four column tiles at a time; the three passes (lo*hi, hi*lo, hi*hi) each sweep all 4 x MT accumulator
+    // tiles, so that dependent MMAs on one accumulator are 4 * MT instructions apart (4 warps per SM: the ILP has to
+    // come from inside the warp)
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      uint32_t bh0, bl0, bh1, bl1;
-      split_tf32(fb(k0 + t, 8 * nt + g), bh0, bl0);
-      split_tf32(fb(k0 + t + 4, 8 * nt + g), bh1, bl1);
+    for (int n4 = 0; n4 < NT; n4 += 4) {
+      uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        mma_tf32(acc[mt][nt], al[mt], bh0, bh1);
-        mma_tf32(acc[mt][nt], ah[mt], bl0, bl1);
-        mma_tf32(acc[mt][nt], ah[mt], bh0, bh1);
+      for (int q = 0; q < 4; ++q) {
+        split_tf32(fb(k0 + t, 8 * (n4 + q) + g), bh[q][0], bl[q][0]);
+        split_tf32(fb(k0 + t + 4, 8 * (n4 + q) + g), bh[q][1], bl[q][1]);
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][n4 + q], al[mt], bh[q][0], bh[q][1]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][n4 + q], ah[mt], bl[q][0], bl[q][1]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][n4 + q], ah[mt], bh[q][0], bh[q][1]);
     }
   }
 }
@@ -610,6 +622,32 @@ extern "C" int nmf_train_plain(const NmfScene* scene, const NmfTrain* tp, const 
   CKL();
   CompArgs ca{rays, out->n_kept, cap, *grads};
   k_train_composite_bwd<<<warp_blocks, 256, 0, cs>>>(*scene, ca, w);
+  CKL();
+  return NMF_OK;
+}
+
+// ================================================================================================
+// resolution schedule: TensoRF.upsample (fields/tensoRF.py:208-227) = F.interpolate(bilinear, align_corners=True)
+// of every plane (1,C,H,W) and line (1,C,N,1), in the reference's own parameter layout
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_upsample(const float* src, int C, int H, int W, float* dst, int H2, int W2) {
+  const size_t n = (size_t)C * H2 * W2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W2), y = (int)((i / W2) % H2), c = (int)(i / ((size_t)W2 * H2));
+    int x0, x1, y0, y1;
+    float wx0, wx1, hy0, hy1;
+    nmf_resize_tap(x, W, W2, &x0, &x1, &wx0, &wx1);
+    nmf_resize_tap(y, H, H2, &y0, &y1, &hy0, &hy1);
+    dst[i] = nmf_resize_pixel(src + (size_t)c * H * W, W, y0, y1, hy0, hy1, x0, x1, wx0, wx1);
+  }
+}
+extern "C" int nmf_upsample_bilinear(const float* src, int C, int H, int W, float* dst, int H2, int W2, void* stream) {
+  if (!src || !dst || C <= 0 || H <= 0 || W <= 0 || H2 <= 0 || W2 <= 0) return NMF_E_ARG;
+  const size_t n = (size_t)C * H2 * W2;
+  size_t blocks = (n + 255) / 256;
+  const size_t cap = (size_t)t_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  k_upsample<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, C, H, W, dst, H2, W2);
   CKL();
   return NMF_OK;
 }

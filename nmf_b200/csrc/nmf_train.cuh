@@ -137,3 +137,23 @@ NMF_HD float nmf_composite_bwd(float dw, float T, float alpha, float dist, float
   const float dalpha = dw * T - suffix / (1.0f - alpha + 1e-10f);
   return dalpha * dist * (1.0f - alpha);
 }
+
+// F.interpolate(mode="bilinear", align_corners=True) source tap for output index `o` (fields/tensoRF.py:208-227 ->
+// ATen UpSample.h: scale = (in - 1) / (out - 1) in fp32, src = scale * o, i0 = min(floor(src), in - 1),
+// lambda1 = clamp(src - i0, 0, 1), i1 = i0 + (i0 < in - 1))
+NMF_HD void nmf_resize_tap(int o, int in, int out, int* i0, int* i1, float* l0, float* l1) {
+  if (in == out) { *i0 = *i1 = o; *l0 = 1.0f; *l1 = 0.0f; return; }
+  const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.0f;
+  const float src = NMF_MUL(scale, (float)o);
+  int a = (int)floorf(src);
+  if (a > in - 1) a = in - 1;
+  *i0 = a;
+  *i1 = a + (a < in - 1 ? 1 : 0);
+  *l1 = fminf(fmaxf(NMF_SUB(src, (float)a), 0.0f), 1.0f);
+  *l0 = NMF_SUB(1.0f, *l1);
+}
+NMF_HD float nmf_resize_pixel(const float* plane, int W, int y0, int y1, float hy0, float hy1, int x0, int x1, float wx0, float wx1) {
+  const float top = NMF_ADD(NMF_MUL(wx0, plane[(size_t)y0 * W + x0]), NMF_MUL(wx1, plane[(size_t)y0 * W + x1]));
+  const float bot = NMF_ADD(NMF_MUL(wx0, plane[(size_t)y1 * W + x0]), NMF_MUL(wx1, plane[(size_t)y1 * W + x1]));
+  return NMF_ADD(NMF_MUL(hy0, top), NMF_MUL(hy1, bot));
+}

@@ -119,6 +119,19 @@ def dense_alpha(scene, grid_size):
     return out
 
 
+def upsample_bilinear(src, size):
+    """F.interpolate(src, size, mode="bilinear", align_corners=True) for a (1,C,H,W) factor (fields/tensoRF.py:208-227)."""
+    x = _f32(src, src.device)
+    if x.dim() != 4 or x.shape[0] != 1:
+        raise _lib.NmfError("upsample_bilinear takes a (1,C,H,W) tensor")
+    _, Cn, H, W = x.shape
+    H2, W2 = int(size[0]), int(size[1])
+    out = torch.empty(1, Cn, H2, W2, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().nmf_upsample_bilinear(_p(x), Cn, H, W, _p(out), H2, W2, _stream()), "nmf_upsample_bilinear")
+    return out
+
+
 def generate_rays(c2w, H, W, fx, fy=None, cx=None, cy=None, pixel_ids=None, device="cuda", out=None):
     """(n,6) rays of one view generated on the device (dataLoader/ray_utils.py:23-89, blender.py:108-110,146).
     c2w: 3x4 / 4x4 camera-to-world in the OpenCV convention; pixel_ids: optional int32 device tensor (render order)."""

@@ -120,7 +120,26 @@ class TensorVMSplit(nn.Module):
         return g
 
     def check_schedule(self, iter, batch_mul):
-        return False      # resolution upsampling belongs to the training loop
+        """fields/tensor_base.py:234-243: at the iterations of upsamp_list the factors are resampled to the next
+        resolution of N_voxel_list; True tells the caller to rebuild the optimiser (train.py:806-809)."""
+        upsamp_list = [i * batch_mul for i in self.upsamp_list]
+        if iter in upsamp_list:
+            self.upsample_volume_grid(_n_to_reso(self.N_voxel_list[upsamp_list.index(iter)], self.aabb))
+            return True
+        return False
+
+    @torch.no_grad()
+    def upsample_volume_grid(self, res_target):
+        """fields/tensoRF.py:208-227, 408-413: every plane (grid[mat1], grid[mat0]) and line (grid[vec]) through the
+        CUDA bilinear resize (nmf_upsample_bilinear = F.interpolate(align_corners=True)), then update_stepSize."""
+        res = [int(r) for r in res_target]
+        mat, vec = [[0, 1], [0, 2], [1, 2]], [2, 1, 0]
+        for rf in (self.app_rf, self.density_rf):
+            for i in range(3):
+                rf.app_plane[i] = nn.Parameter(ops.upsample_bilinear(rf.app_plane[i].data, (res[mat[i][1]], res[mat[i][0]])))
+                rf.app_line[i] = nn.Parameter(ops.upsample_bilinear(rf.app_line[i].data, (res[vec[i]], 1)))
+        self.update_stepSize(res)
+        self._scene = None
 
     def normalize_coord(self, xyz_sampled):
         coords = (xyz_sampled[..., :3] - self.aabb[0]) * self.invaabbSize - 1

@@ -159,15 +159,45 @@ class PlainTrainer:
         self.alpha_volume = alpha_volume
         self.state = {k: torch.as_tensor(v).detach().clone().to(self.device) for k, v in state.items()}
         self.params = {k: torch.nn.Parameter(self.state[k].float()) for k in PLAIN_PARAM_KEYS}
-        grid = [self.params[k] for k in PLAIN_PARAM_KEYS if k.startswith("rf.") and "basis" not in k]
-        net = [self.params[k] for k in PLAIN_PARAM_KEYS if not (k.startswith("rf.") and "basis" not in k)]
-        self.optimizer = torch.optim.Adam([dict(params=grid, lr=lr_grid), dict(params=net, lr=lr_net)], betas=(0.9, 0.99))
-        self.bucket = FlatGradBucket(list(self.params.values()))
+        self.lr_grid, self.lr_net = lr_grid, lr_net
+        self._FlatGradBucket = FlatGradBucket
         self.max_samples, self.lambda_pred, self.seed = max_samples, lambda_pred, seed
         self.iteration = 0
         self.buffers = None
         self._DeviceScene = DeviceScene
+        self._make_optimizer()
         self.repack()
+
+    def _make_optimizer(self):
+        grid = [self.params[k] for k in PLAIN_PARAM_KEYS if k.startswith("rf.") and "basis" not in k]
+        net = [self.params[k] for k in PLAIN_PARAM_KEYS if not (k.startswith("rf.") and "basis" not in k)]
+        self.optimizer = torch.optim.Adam([dict(params=grid, lr=self.lr_grid), dict(params=net, lr=self.lr_net)],
+                                          betas=(0.9, 0.99))
+        self.bucket = self._FlatGradBucket(list(self.params.values()))
+
+    def upsample(self, grid_size):
+        """Resolution schedule (fields/tensor_base.py:234-243, fields/tensoRF.py:208-227, 408-413; train.py:806-809): the
+        factors are resampled on the device (nmf_upsample_bilinear), the occupancy grid is rebuilt at the new resolution
+        (samplers/alphagrid.py:249-276) and the optimiser is re-created, as the reference does when check_schedule fires."""
+        from . import ops
+        res = [int(g) for g in grid_size]
+        mat, vec = [[0, 1], [0, 2], [1, 2]], [2, 1, 0]
+        new = {}
+        for k, p in self.params.items():
+            if ".app_plane." in k:
+                i = int(k[-1])
+                new[k] = torch.nn.Parameter(ops.upsample_bilinear(p.data, (res[mat[i][1]], res[mat[i][0]])))
+            elif ".app_line." in k:
+                new[k] = torch.nn.Parameter(ops.upsample_bilinear(p.data, (res[vec[int(k[-1])]], 1)))
+            else:
+                new[k] = torch.nn.Parameter(p.data.clone())
+        self.params = new
+        self.meta["grid_size"] = res
+        self.alpha_volume = None
+        self.buffers = None
+        self._make_optimizer()
+        self.repack()
+        self.alpha_volume = self.scene.update_alpha_mask(res)
 
     def repack(self):
         st = dict(self.state)

@@ -268,4 +268,16 @@ void hc_train_plain(const NmfScene* s, const NmfTrain* tp, const float* rays, co
     }
   }
 }
+
+void hc_upsample(const float* src, int C, int H, int W, float* dst, int H2, int W2) {
+  for (int c = 0; c < C; ++c)
+    for (int y = 0; y < H2; ++y)
+      for (int x = 0; x < W2; ++x) {
+        int x0, x1, y0, y1;
+        float wx0, wx1, hy0, hy1;
+        nmf_resize_tap(x, W, W2, &x0, &x1, &wx0, &wx1);
+        nmf_resize_tap(y, H, H2, &y0, &y1, &hy0, &hy1);
+        dst[((size_t)c * H2 + y) * W2 + x] = nmf_resize_pixel(src + (size_t)c * H * W, W, y0, y1, hy0, hy1, x0, x1, wx0, wx1);
+      }
+}
 }

@@ -233,3 +233,38 @@ def test_ray_sharded_training_two_gpus(env, tmp_path):
     worst = torch.load(out)
     # Adam normalises the step: parameters move by ~lr per iteration, a last-bit gradient difference moves them by << lr
     assert max(worst.values()) < 2e-4, worst
+
+
+def test_upsample_schedule(env):
+    """resolution schedule: nmf_upsample_bilinear == F.interpolate(align_corners=True); the plugin's check_schedule and the
+    trainer's upsample keep rendering the same scene at the new resolution (fields/tensoRF.py:208-227, 408-413)"""
+    from conftest import grid_of
+    from nmf_b200 import config, ops, train
+    g = torch.Generator().manual_seed(0)
+    for shape, size in (((1, 16, 40, 40), (56, 56)), ((1, 24, 36, 48), (42, 77)), ((1, 16, 40, 1), (93, 1)), ((1, 24, 300, 300), (300, 300))):
+        src = torch.randn(shape, generator=g)
+        ref = torch.nn.functional.interpolate(src, size=size, mode="bilinear", align_corners=True)
+        out = ops.upsample_bilinear(src.cuda(), size).cpu()
+        assert float((out - ref).abs().max()) <= 4e-7 * float(src.abs().max())
+    fix = load_fixture("plain_g64")
+    n = 1024
+    rays = fix["rays"][:n].cuda()
+    tr = train.PlainTrainer(fix["state"], fix["aabb"], fix["near_far"], grid_of(fix), alpha_volume=fix["alpha_volume"], device=env)
+    before = ops.render_rays(tr.scene, rays, fix["focal"], chunk=n)[0]["rgb_map"].clone()
+    tr.upsample([96, 96, 96])
+    assert tuple(tr.params["rf.app_rf.app_plane.0"].shape) == (1, 24, 96, 96) and tr.scene.n_steps > 219
+    after = ops.render_rays(tr.scene, rays, fix["focal"], chunk=n)[0]["rgb_map"]
+    assert float((after - before).abs().mean()) < 5e-2          # same scene, resampled factors and finer steps
+    gt = before
+    mse = [tr.step(rays, gt)["mse"] for _ in range(10)]        # the re-created optimiser keeps training
+    assert np.isfinite(mse).all() and mse[-1] <= mse[0]
+    # plugin slot: TensorVMSplit.check_schedule fires on upsamp_list and returns True (train.py:806-809)
+    t, _ = config.build_model(["model=tensorf", "field.grid_size=[64,64,64]", "field.upsamp_list=[5]", "field.N_voxel_final=884736"],
+                              aabb=fix["aabb"], near_far=list(fix["near_far"]))
+    t = t.cuda()
+    assert t.rf.check_schedule(4, 1) is False and t.rf.check_schedule(5, 1) is True
+    from nmf_b200.plugins import _n_to_reso
+    res = _n_to_reso(t.rf.N_voxel_list[0], t.rf.aabb.cpu())
+    assert 95 <= res[0] <= 96 and t.rf.grid_size.tolist() == res
+    assert tuple(t.rf.app_rf.app_plane[0].shape) == (1, 24, res[1], res[0])
+    assert tuple(t.rf.density_rf.app_line[0].shape) == (1, 16, res[2], 1)

@@ -260,3 +260,14 @@ def test_train_plain_host_gradients(hostcheck, max_samples):
     assert abs(float(loss[0]) - ref["photo"]) <= 1e-4 * max(1.0, ref["photo"])
     assert abs(float(loss[1]) - ref["acc"]) <= 1e-4 * max(1.0, ref["acc"])
     check_plain_grads(gb.reference_layout(), ref["grads"])
+
+
+@pytest.mark.parametrize("shape,size", [((16, 40, 40), (56, 56)), ((24, 36, 48), (42, 77)), ((16, 40, 1), (93, 1)),
+                                        ((3, 17, 9), (17, 9)), ((2, 300, 1), (128, 1))])
+def test_upsample_matches_interpolate(hostcheck, shape, size):
+    """TensoRF.upsample (fields/tensoRF.py:208-227): F.interpolate(bilinear, align_corners=True), tap indices exact"""
+    src = torch.randn(shape, generator=torch.Generator().manual_seed(0))
+    ref = torch.nn.functional.interpolate(src[None], size=size, mode="bilinear", align_corners=True)[0]
+    out = torch.zeros(shape[0], *size)
+    hostcheck.hc_upsample(ptr(src), shape[0], shape[1], shape[2], ptr(out), size[0], size[1])
+    assert float((out - ref).abs().max()) <= 4e-7 * float(src.abs().max())
