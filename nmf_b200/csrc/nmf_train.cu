@@ -26,6 +26,7 @@
 #define TS 136              // shared-memory stride of one feature row (136 = 8 mod 32): columns [k*TS + t] and the mma B
                             // fragments [(k0 + lane%4)*TS + n0 + lane/4] are bank-conflict-free; 16-byte aligned rows
 #define TILE 128
+#define MLP_T 256           // threads of the MLP tile kernel (8 warps: two per scheduler)
 
 static int t_sms = 0;
 static int t_sm_count() {
@@ -286,10 +287,12 @@ __global__ void __launch_bounds__(256) k_train_loss(const LossArgs a, const TWS 
 #define SM_D2 (SM_H2 + 128 * TS)
 #define SM_FLOATS (SM_D2 + 3 * 128)
 
+// x = hi + lo with hi = x truncated to TF32's 10 explicit mantissa bits (one LOP) and lo = x - hi, exact in fp32; the
+// tensor core reads only the TF32 bits of lo, so x is represented to ~2^-21 relative (cvt.rna costs ~6 ALU instructions
+// per element on this target and made the GEMM loops issue-bound)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -320,24 +323,25 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[MT][NT][4], int ksteps, F
     // B fragments four column tiles at a time; the three passes (lo*hi, hi*lo, hi*hi) each sweep all 4 x MT accumulator
     // tiles, so that dependent MMAs on one accumulator are 4 * MT instructions apart (4 warps per SM: the ILP has to
     // come from inside the warp)
+    constexpr int NG = NT < 4 ? NT : 4;
 #pragma unroll
-    for (int n4 = 0; n4 < NT; n4 += 4) {
-      uint32_t bh[4][2], bl[4][2];
+    for (int n4 = 0; n4 < NT; n4 += NG) {
+      uint32_t bh[NG][2], bl[NG][2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < NG; ++q) {
         split_tf32(fb(k0 + t, 8 * (n4 + q) + g), bh[q][0], bl[q][0]);
         split_tf32(fb(k0 + t + 4, 8 * (n4 + q) + g), bh[q][1], bl[q][1]);
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < NG; ++q)
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][n4 + q], al[mt], bh[q][0], bh[q][1]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < NG; ++q)
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][n4 + q], ah[mt], bl[q][0], bl[q][1]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < NG; ++q)
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][n4 + q], ah[mt], bh[q][0], bh[q][1]);
     }
@@ -374,23 +378,26 @@ __device__ __forceinline__ float tile_rowdot(const float* r, const float* c) {
 
 struct MlpArgs { const float* rays; const int* n_kept; int cap; NmfPlainGrads g; };
 template <int BWD>
-__global__ void __launch_bounds__(TILE, 1) k_train_mlp(const NmfScene s, const MlpArgs a, const TWS w) {
+__global__ void __launch_bounds__(MLP_T, 1) k_train_mlp(const NmfScene s, const MlpArgs a, const TWS w) {
   extern __shared__ __align__(16) float sm[];
   float* X = sm + SM_X;
   float* H1 = sm + SM_H1;
   float* H2 = sm + SM_H2;
   float* D2 = sm + SM_D2;
-  const int t = threadIdx.x, lane = t & 31, m0 = 32 * (t >> 5);     // warp `t >> 5` owns output rows m0 .. m0 + 31
+  // 8 warps: warp w owns the 32 x 64 output block (rows m0 .. m0+31, columns n0 .. n0+63) of every tile GEMM; the
+  // per-sample phases run on the first 128 threads (thread = sample = column)
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, m0 = 32 * (wid & 3), n0 = 64 * (wid >> 2);
+  const bool lead = t < TILE;
   const int M = min(a.n_kept[1], a.cap);
   if (a.n_kept[1] > a.cap) return;
-  X[135 * TS + t] = 0.f;                                            // K padding row of the first layer
+  if (lead) X[135 * TS + t] = 0.f;                                  // K padding row of the first layer
   for (int tile = blockIdx.x * TILE; tile < M; tile += gridDim.x * TILE) {
     const int si = tile + t;
-    const bool active = si < M;
+    const bool active = lead && si < M;
     int ray = 0;
     float dv[3] = {0.f, 0.f, 0.f};
     NmfTaps tp;
-    {
+    if (lead) {
       float o[3] = {0.f, 0.f, 0.f}, p[3], xn[3], coef[72], feat[24];
       float z = 0.f;
       if (active) {
@@ -411,21 +418,21 @@ __global__ void __launch_bounds__(TILE, 1) k_train_mlp(const NmfScene s, const M
       nmf_plain_encode(feat, dv, X + t, TS);
     }
     __syncthreads();
-    float acc[2][16][4];
+    float acc[2][8][4];
     // layer 1: H1[j][n] = relu(b0[j] + sum_k W0[j][k] X[k][n])      (W0 as stored: (out, in), row stride 135)
-    warp_gemm<2, 16>(acc, 17,
+    warp_gemm<2, 8>(acc, 17,
                      [&](int m, int k) { return k < 135 ? __ldg(s.plain_w0 + (m0 + m) * 135 + k) : 0.f; },
-                     [&](int k, int n) { return X[k * TS + n]; }, lane);
-    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { H1[(m0 + r) * TS + c] = fmaxf(v + __ldg(s.plain_b0 + m0 + r), 0.f); });
+                     [&](int k, int n) { return X[k * TS + n0 + n]; }, lane);
+    warp_epilogue<2, 8>(acc, lane, [&](int r, int c, float v) { H1[(m0 + r) * TS + n0 + c] = fmaxf(v + __ldg(s.plain_b0 + m0 + r), 0.f); });
     __syncthreads();
     // layer 2
-    warp_gemm<2, 16>(acc, 16, [&](int m, int k) { return __ldg(s.plain_w1 + (m0 + m) * 128 + k); },
-                     [&](int k, int n) { return H1[k * TS + n]; }, lane);
-    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { H2[(m0 + r) * TS + c] = fmaxf(v + __ldg(s.plain_b1 + m0 + r), 0.f); });
+    warp_gemm<2, 8>(acc, 16, [&](int m, int k) { return __ldg(s.plain_w1 + (m0 + m) * 128 + k); },
+                     [&](int k, int n) { return H1[k * TS + n0 + n]; }, lane);
+    warp_epilogue<2, 8>(acc, lane, [&](int r, int c, float v) { H2[(m0 + r) * TS + n0 + c] = fmaxf(v + __ldg(s.plain_b1 + m0 + r), 0.f); });
     __syncthreads();
     // output layer (3 wide) per sample
     float o3[3] = {__ldg(s.plain_b2), __ldg(s.plain_b2 + 1), __ldg(s.plain_b2 + 2)};
-    for (int k = 0; k < 128; ++k) {
+    if (lead) for (int k = 0; k < 128; ++k) {
       const float hv = H2[k * TS + t];
       const float* w2 = s.plain_w2t + k * 3;
       o3[0] += hv * __ldg(w2); o3[1] += hv * __ldg(w2 + 1); o3[2] += hv * __ldg(w2 + 2);
@@ -454,9 +461,9 @@ __global__ void __launch_bounds__(TILE, 1) k_train_mlp(const NmfScene s, const M
       }
       w.s_dw[si] = dw;
     }
-    for (int c = 0; c < 3; ++c) D2[c * 128 + t] = dpre[c];
+    if (lead) for (int c = 0; c < 3; ++c) D2[c * 128 + t] = dpre[c];
     __syncthreads();
-    {  // (a) dW2t[k = t][c], db2
+    if (lead) {  // (a) dW2t[k = t][c], db2
       const float* hrow = H2 + t * TS;
       atomicAdd(a.g.w2t + t * 3, tile_rowdot(hrow, D2));
       atomicAdd(a.g.w2t + t * 3 + 1, tile_rowdot(hrow, D2 + 128));
@@ -465,51 +472,53 @@ __global__ void __launch_bounds__(TILE, 1) k_train_mlp(const NmfScene s, const M
     }
     __syncthreads();
     // (b) dh2 in place (own column)
-    for (int k = 0; k < 128; ++k) {
+    if (lead) for (int k = 0; k < 128; ++k) {
       const float hv = H2[k * TS + t];
       const float* w2 = s.plain_w2t + k * 3;
       H2[k * TS + t] = hv > 0.f ? __ldg(w2) * dpre[0] + __ldg(w2 + 1) * dpre[1] + __ldg(w2 + 2) * dpre[2] : 0.f;
     }
     __syncthreads();
     // (c) dW1t[k][j] += sum_n H1[k][n] dH2[j][n]  (M = k, N = j, contraction over the tile's samples);  db1
-    warp_gemm<2, 16>(acc, 16, [&](int m, int k) { return H1[(m0 + m) * TS + k]; }, [&](int k, int n) { return H2[n * TS + k]; }, lane);
-    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { atomicAdd(a.g.w1t + (m0 + r) * 128 + c, v); });
-    atomicAdd(a.g.b1 + t, tile_rowsum(H2 + t * TS));
+    warp_gemm<2, 8>(acc, 16, [&](int m, int k) { return H1[(m0 + m) * TS + k]; }, [&](int k, int n) { return H2[(n0 + n) * TS + k]; }, lane);
+    warp_epilogue<2, 8>(acc, lane, [&](int r, int c, float v) { atomicAdd(a.g.w1t + (m0 + r) * 128 + n0 + c, v); });
+    if (lead) atomicAdd(a.g.b1 + t, tile_rowsum(H2 + t * TS));
     __syncthreads();
     // (d) dH1[k][n] = [H1[k][n] > 0] sum_j W1[j][k] dH2[j][n], in place (every element has one owner)
-    warp_gemm<2, 16>(acc, 16, [&](int m, int k) { return __ldg(s.plain_w1t + (m0 + m) * 128 + k); },
-                     [&](int k, int n) { return H2[k * TS + n]; }, lane);
-    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { float* q = H1 + (m0 + r) * TS + c; *q = *q > 0.f ? v : 0.f; });
+    warp_gemm<2, 8>(acc, 16, [&](int m, int k) { return __ldg(s.plain_w1t + (m0 + m) * 128 + k); },
+                     [&](int k, int n) { return H2[k * TS + n0 + n]; }, lane);
+    warp_epilogue<2, 8>(acc, lane, [&](int r, int c, float v) { float* q = H1 + (m0 + r) * TS + n0 + c; *q = *q > 0.f ? v : 0.f; });
     __syncthreads();
     // (e) dW0t[i][j] += sum_n X[i][n] dH1[j][n]: rows 0..127 as above, rows 128..134 as one 16-row tile split over the warps' columns;  db0
-    warp_gemm<2, 16>(acc, 16, [&](int m, int k) { return X[(m0 + m) * TS + k]; }, [&](int k, int n) { return H1[n * TS + k]; }, lane);
-    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { atomicAdd(a.g.w0t + (m0 + r) * 128 + c, v); });
+    warp_gemm<2, 8>(acc, 16, [&](int m, int k) { return X[(m0 + m) * TS + k]; }, [&](int k, int n) { return H1[(n0 + n) * TS + k]; }, lane);
+    warp_epilogue<2, 8>(acc, lane, [&](int r, int c, float v) { atomicAdd(a.g.w0t + (m0 + r) * 128 + n0 + c, v); });
     {
-      float acc1[1][4][4];
-      warp_gemm<1, 4>(acc1, 16, [&](int m, int k) { return X[(128 + m) * TS + k]; }, [&](int k, int n) { return H1[(m0 + n) * TS + k]; }, lane);
-      warp_epilogue<1, 4>(acc1, lane, [&](int r, int c, float v) { if (r < 7) atomicAdd(a.g.w0t + (128 + r) * 128 + m0 + c, v); });
+      float acc1[1][2][4];
+      warp_gemm<1, 2>(acc1, 16, [&](int m, int k) { return X[(128 + m) * TS + k]; }, [&](int k, int n) { return H1[(16 * wid + n) * TS + k]; }, lane);
+      warp_epilogue<1, 2>(acc1, lane, [&](int r, int c, float v) { if (r < 7) atomicAdd(a.g.w0t + (128 + r) * 128 + 16 * wid + c, v); });
     }
-    atomicAdd(a.g.b0 + t, tile_rowsum(H1 + t * TS));
+    if (lead) atomicAdd(a.g.b0 + t, tile_rowsum(H1 + t * TS));
     // (f) dX[i][n] = sum_j W0[j][i] dH1[j][n] for input rows 0..127 (features and their encodings are rows 0..122) -> H2
-    warp_gemm<2, 16>(acc, 16, [&](int m, int k) { return __ldg(s.plain_w0t + (m0 + m) * 128 + k); },
-                     [&](int k, int n) { return H1[k * TS + n]; }, lane);
-    warp_epilogue<2, 16>(acc, lane, [&](int r, int c, float v) { H2[(m0 + r) * TS + c] = v; });
+    warp_gemm<2, 8>(acc, 16, [&](int m, int k) { return __ldg(s.plain_w0t + (m0 + m) * 128 + k); },
+                     [&](int k, int n) { return H1[k * TS + n0 + n]; }, lane);
+    warp_epilogue<2, 8>(acc, lane, [&](int r, int c, float v) { H2[(m0 + r) * TS + n0 + c] = v; });
     __syncthreads();
     float dfeat[24];
+    if (lead) {
 #pragma unroll
-    for (int oo = 0; oo < 24; ++oo)
-      dfeat[oo] = nmf_plain_encode_bwd(X + t, TS, oo, H2[oo * TS + t], H2[(27 + 2 * oo) * TS + t], H2[(28 + 2 * oo) * TS + t],
-                                       H2[(75 + 2 * oo) * TS + t], H2[(76 + 2 * oo) * TS + t]);
+      for (int oo = 0; oo < 24; ++oo)
+        dfeat[oo] = nmf_plain_encode_bwd(X + t, TS, oo, H2[oo * TS + t], H2[(27 + 2 * oo) * TS + t], H2[(28 + 2 * oo) * TS + t],
+                                         H2[(75 + 2 * oo) * TS + t], H2[(76 + 2 * oo) * TS + t]);
+    }
     __syncthreads();                              // every thread is done with X before it is overwritten
-    for (int oo = 0; oo < 24; ++oo) X[oo * TS + t] = active ? dfeat[oo] : 0.f;
-    {
+    if (lead) {
+      for (int oo = 0; oo < 24; ++oo) X[oo * TS + t] = active ? dfeat[oo] : 0.f;
       float coef[72];                             // gathered again (cheap next to the MLP) rather than kept live
       nmf_app_coef(s, tp, coef);
       for (int j = 0; j < 72; ++j) X[(24 + j) * TS + t] = active ? coef[j] : 0.f;
     }
     __syncthreads();
     // (g) d basis_t[j][o] += sum_n coef_j[n] dfeat_o[n]
-    for (int idx = t; idx < 72 * 24; idx += TILE)
+    for (int idx = t; idx < 72 * 24; idx += MLP_T)
       atomicAdd(a.g.basis_t + idx, tile_rowdot(X + (24 + idx / 24) * TS, X + (idx % 24) * TS));
     // (h) appearance factors (own sample)
     if (active) {
@@ -613,12 +622,12 @@ extern "C" int nmf_train_plain(const NmfScene* scene, const NmfTrain* tp, const 
   int tiles = (cap + TILE - 1) / TILE;
   const int grid = tiles < t_sm_count() ? tiles : t_sm_count();      // one resident CTA per SM (202 KB of shared memory)
   MlpArgs ma{rays, out->n_kept, cap, *grads};
-  k_train_mlp<0><<<grid, TILE, smem, cs>>>(*scene, ma, w);
+  k_train_mlp<0><<<grid, MLP_T, smem, cs>>>(*scene, ma, w);
   CKL();
   LossArgs la{gt, out->n_kept, n, tp->lambda_pred, tp->white_bg, out->rgb_map, out->acc_map, out->loss};
   k_train_loss<<<(n + 255) / 256, 256, 0, cs>>>(la, w);
   CKL();
-  k_train_mlp<1><<<grid, TILE, smem, cs>>>(*scene, ma, w);
+  k_train_mlp<1><<<grid, MLP_T, smem, cs>>>(*scene, ma, w);
   CKL();
   CompArgs ca{rays, out->n_kept, cap, *grads};
   k_train_composite_bwd<<<warp_blocks, 256, 0, cs>>>(*scene, ca, w);

@@ -255,9 +255,9 @@ def test_upsample_schedule(env):
     assert tuple(tr.params["rf.app_rf.app_plane.0"].shape) == (1, 24, 96, 96) and tr.scene.n_steps > 219
     after = ops.render_rays(tr.scene, rays, fix["focal"], chunk=n)[0]["rgb_map"]
     assert float((after - before).abs().mean()) < 5e-2          # same scene, resampled factors and finer steps
-    gt = before
-    mse = [tr.step(rays, gt)["mse"] for _ in range(10)]        # the re-created optimiser keeps training
-    assert np.isfinite(mse).all() and mse[-1] <= mse[0]
+    gt = 0.7 * before                                          # a target the scene has to move towards
+    mse = [tr.step(rays, gt)["mse"] for _ in range(15)]        # the re-created optimiser keeps training
+    assert np.isfinite(mse).all() and mse[-1] < 0.8 * mse[0], (mse[0], mse[-1])
     # plugin slot: TensorVMSplit.check_schedule fires on upsamp_list and returns True (train.py:806-809)
     t, _ = config.build_model(["model=tensorf", "field.grid_size=[64,64,64]", "field.upsamp_list=[5]", "field.N_voxel_final=884736"],
                               aabb=fix["aabb"], near_far=list(fix["near_far"]))
