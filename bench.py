@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--scene", default="lego")
     ap.add_argument("--cpu-chunks", type=int, default=16, help="chunks of the image the CPU baseline renders")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra train_step entry (training slice, SURVEY 8f row 1)")
     ap.add_argument("--skip-eps", type=float, default=None)
     ap.add_argument("--t-cut", type=float, default=None)
     return ap.parse_args()
@@ -340,6 +341,13 @@ def main():
                                 "sample": f"{a.cpu_chunks} chunks of {a.chunk} rays of the same image ({t_tot:.1f} s) after 1 warm-up chunk; "
                                           "oracle = CPU restatement of the reference's PyTorch path (torch CPU ops, all cores)"}
         line["psnr_vs_oracle_db"] = (10 * math.log10(1.0 / mse)) if mse > 0 else 99.0
+    # ---- extra, outside the timed region and not part of `value`: the fused training step of the model=tensorf slice ----
+    if not a.no_train and not a.no_cpu and world == 1:
+        try:
+            from nmf_b200 import train
+            line["train_step"] = train.benchmark_plain(a.grid, 4096, steps=10, iters=0, device=f"cuda:{torch.cuda.current_device()}")
+        except Exception as e:                      # never lets the extra entry take the bench line down
+            line["train_step"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

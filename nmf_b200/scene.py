@@ -113,35 +113,8 @@ class DeviceScene:
         self.aabb = aabb
         self.near_far = (float(near_far[0]), float(near_far[1]))
 
-        kx, ky = derivative_stencils()
-        kx, ky = kx.to(dev), ky.to(dev)
-        conv = lambda img, k: F.conv2d(img.permute(1, 0, 2, 3), k, stride=1, padding=(2, 2)).permute(1, 0, 2, 3)
-        for p in range(3):
-            dp = f32(state[f"rf.density_rf.app_plane.{p}"])
-            dl = f32(state[f"rf.density_rf.app_line.{p}"])
-            ap = f32(state[f"rf.app_rf.app_plane.{p}"])
-            al = f32(state[f"rf.app_rf.app_line.{p}"])
-            if dp.shape[1] != 16 or ap.shape[1] != 24:
-                raise _lib.NmfError("kernels are compiled for density_n_comp=16, appearance_n_comp=24")
-            H, W = dp.shape[2], dp.shape[3]
-            N = dl.shape[2]
-            s.plane_w[p], s.plane_h[p], s.line_n[p] = W, H, N
-            dval = dp[0].permute(1, 2, 0).contiguous()                                   # (H,W,16)
-            pdx, pdy = conv(dp, kx)[0].permute(1, 2, 0), conv(dp, ky)[0].permute(1, 2, 0)
-            dpack = torch.cat([dval, pdx, pdy], dim=2).contiguous()                      # (H,W,48): [val16 | dx16 | dy16]
-            lval = dl[0, :, :, 0].permute(1, 0).contiguous()                             # (N,16)
-            ldy = conv(dl, ky)[0, :, :, 0].permute(1, 0)
-            lpack = torch.stack([lval.view(N, 4, 4), ldy.reshape(N, 4, 4)], dim=2).reshape(N, 4, 8).contiguous()
-            aval = ap[0].permute(1, 2, 0).contiguous()                                   # (H,W,24)
-            alval = al[0, :, :, 0].permute(1, 0).contiguous()                            # (N,24)
-            for name, t, arr in (("dval", dval, s.dval), ("dpack", dpack, s.dpack), ("lval", lval, s.lval),
-                                 ("lpack", lpack, s.lpack), ("aval", aval, s.aval), ("alval", alval, s.alval)):
-                self.keep[f"{name}{p}"] = t
-                arr[p] = t.data_ptr()
-        basis = f32(state["rf.basis_mat.weight"])
-        if tuple(basis.shape) != (24, 72):
-            raise _lib.NmfError("kernels are compiled for app_dim=24")
-        self._ptr(s, "basis_t", basis.t().contiguous())
+        self.c = s
+        self._pack_factors(state)
 
         model = self.hp["model"]          # "microfacet" | "plain" | "field" (factors only: plugin-slot field queries)
         s.model = 0 if model == "microfacet" else 1
@@ -172,13 +145,7 @@ class DeviceScene:
             assert sob.shape[0] >= 400 and sob.shape[1] == 2
             self._ptr(s, "sobol", sob)
         elif model == "plain":
-            for i, li in enumerate((0, 2, 4)):
-                w, b = f32(state[f"model.diffuse_module.mlp.{li}.weight"]), f32(state[f"model.diffuse_module.mlp.{li}.bias"])
-                self._ptr(s, f"plain_w{i}t", w.t().contiguous())
-                self._ptr(s, f"plain_b{i}", b)
-                if i < 2:
-                    self._ptr(s, f"plain_w{i}", w)       # (out, in) as stored: read by the training backward
-            assert tuple(self.keep["plain_w0t"].shape) == (135, 128) and tuple(self.keep["plain_w2t"].shape) == (128, 3)
+            self._pack_plain_mlp(state)
         for k in ("diffuse_mul", "diffuse_bias", "tint_bias", "f0_bias", "roughness_bias", "brdf_bias", "anoise"):
             setattr(s, k, float(self.hp[k]))
         s.rays_per_ray = int(self.hp["rays_per_ray"])
@@ -189,6 +156,79 @@ class DeviceScene:
         self.set_alpha_volume(alpha_volume)
         if "bg_module.bg_mat" in state:
             self._set_env(state, sh_conv)
+
+    def _put(self, name, t, arr=None, index=None):
+        """Keeps `t` under `name`; an existing buffer of the same shape is overwritten in place (its device pointer, which
+        NmfScene holds, stays valid), otherwise the pointer is (re)set."""
+        old = self.keep.get(name)
+        if old is not None and old.shape == t.shape and old.dtype == t.dtype:
+            old.copy_(t)
+            return old
+        t = t.contiguous()
+        self.keep[name] = t
+        if arr is not None:
+            arr[index] = t.data_ptr()
+        else:
+            setattr(self.c, name, t.data_ptr())
+        return t
+
+    def _pack_factors(self, state, derivatives=True):
+        """Reference-layout factors (1,C,H,W) / (1,C,N,1) -> the channel-last buffers of DESIGN.md section 2."""
+        s, dev = self.c, self.device
+        f32 = lambda t: torch.as_tensor(t).detach().to(device=dev, dtype=torch.float32).contiguous()
+        if derivatives:
+            kx, ky = derivative_stencils()
+            kx, ky = kx.to(dev), ky.to(dev)
+            conv = lambda img, k: F.conv2d(img.permute(1, 0, 2, 3), k, stride=1, padding=(2, 2)).permute(1, 0, 2, 3)
+        for p in range(3):
+            dp = f32(state[f"rf.density_rf.app_plane.{p}"])
+            dl = f32(state[f"rf.density_rf.app_line.{p}"])
+            ap = f32(state[f"rf.app_rf.app_plane.{p}"])
+            al = f32(state[f"rf.app_rf.app_line.{p}"])
+            if dp.shape[1] != 16 or ap.shape[1] != 24:
+                raise _lib.NmfError("kernels are compiled for density_n_comp=16, appearance_n_comp=24")
+            H, W = dp.shape[2], dp.shape[3]
+            N = dl.shape[2]
+            s.plane_w[p], s.plane_h[p], s.line_n[p] = W, H, N
+            dval = dp[0].permute(1, 2, 0)                                                # (H,W,16)
+            lval = dl[0, :, :, 0].permute(1, 0)                                          # (N,16)
+            packed = [("dval", dval, s.dval), ("lval", lval, s.lval),
+                      ("aval", ap[0].permute(1, 2, 0), s.aval),                          # (H,W,24)
+                      ("alval", al[0, :, :, 0].permute(1, 0), s.alval)]                  # (N,24)
+            if derivatives:
+                pdx, pdy = conv(dp, kx)[0].permute(1, 2, 0), conv(dp, ky)[0].permute(1, 2, 0)
+                ldy = conv(dl, ky)[0, :, :, 0].permute(1, 0)
+                packed += [("dpack", torch.cat([dval, pdx, pdy], dim=2), s.dpack),      # (H,W,48): [val16 | dx16 | dy16]
+                           ("lpack", torch.stack([lval.reshape(N, 4, 4), ldy.reshape(N, 4, 4)], dim=2).reshape(N, 4, 8), s.lpack)]
+            else:
+                for name, arr in (("dpack", s.dpack), ("lpack", s.lpack)):              # stale derivative planes: drop them
+                    self.keep.pop(f"{name}{p}", None)
+                    arr[p] = None
+            for name, t, arr in packed:
+                self._put(f"{name}{p}", t, arr, p)
+        basis = f32(state["rf.basis_mat.weight"])
+        if tuple(basis.shape) != (24, 72):
+            raise _lib.NmfError("kernels are compiled for app_dim=24")
+        self._put("basis_t", basis.t())
+
+    def _pack_plain_mlp(self, state):
+        f32 = lambda t: torch.as_tensor(t).detach().to(device=self.device, dtype=torch.float32).contiguous()
+        for i, li in enumerate((0, 2, 4)):
+            w, b = f32(state[f"model.diffuse_module.mlp.{li}.weight"]), f32(state[f"model.diffuse_module.mlp.{li}.bias"])
+            self._put(f"plain_w{i}t", w.t())
+            self._put(f"plain_b{i}", b)
+            if i < 2:
+                self._put(f"plain_w{i}", w)              # (out, in) as stored: read by the training backward
+        assert tuple(self.keep["plain_w0t"].shape) == (135, 128) and tuple(self.keep["plain_w2t"].shape) == (128, 3)
+
+    def refresh_plain(self, state):
+        """After an optimiser step of model=tensorf: re-packs the factors and the view MLP IN PLACE (same buffers, same
+        NmfScene pointers; no derivative planes -- this model has no normals -- and the occupancy is left alone, as the
+        reference only rebuilds it on its schedule, samplers/alphagrid.py:188-199)."""
+        if self.hp["model"] != "plain":
+            raise _lib.NmfError("refresh_plain: model=tensorf scenes only")
+        self._pack_factors(state, derivatives=False)
+        self._pack_plain_mlp(state)
 
     @classmethod
     def env_only(cls, bg_mat, mipbias=1.0, brightness=0.0, mul=1.0, device="cuda"):

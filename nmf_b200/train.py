@@ -199,12 +199,17 @@ class PlainTrainer:
         self.repack()
         self.alpha_volume = self.scene.update_alpha_mask(res)
 
-    def repack(self):
+    def repack(self, rebuild=True):
+        """rebuild=True: a new DeviceScene (construction, resolution change); False: the updated parameters are packed
+        into the existing buffers in place (every optimiser step)."""
         st = dict(self.state)
         st.update({k: p.detach() for k, p in self.params.items()})
         m = self.meta
-        self.scene = self._DeviceScene(st, m["aabb"], m["near_far"], m["grid_size"], alpha_volume=self.alpha_volume,
-                                       device=self.device, **m["hp"])
+        if rebuild or getattr(self, "scene", None) is None:
+            self.scene = self._DeviceScene(st, m["aabb"], m["near_far"], m["grid_size"], alpha_volume=self.alpha_volume,
+                                           device=self.device, **m["hp"])
+        else:
+            self.scene.refresh_plain(st)
 
     def step(self, rays, gt, ray_ids=None):
         """One iteration on this rank's rays (train.py:540-760 without the regularisers that model=tensorf turns off)."""
@@ -221,7 +226,57 @@ class PlainTrainer:
         # one flat fp32 all-reduce (NCCL on GPUs), scaled by 1 / lbatch_size (train.py:709)
         self.bucket.allreduce(scale=1.0 / max(float(tot[0]), 1.0))
         self.optimizer.step()
-        self.repack()
+        self.repack(rebuild=False)
         self.iteration += 1
         out["mse"] = float(tot[1]) / max(3.0 * float(tot[0]), 1.0)
         return out
+
+
+def benchmark_plain(grid=300, n_rays=4096, steps=20, iters=60, device="cuda:0"):
+    """Times nmf_train_plain (CUDA events, `steps` steps after 3 warm-ups) and a short PlainTrainer loop (`iters` Adam
+    iterations, wall clock around a synchronised loop) on the synthetic lego scene at grid^3.  Used by bench.py
+    (`train_step` entry of the JSON line) and tools/train_bench.py."""
+    import time
+    from . import ops, synthetic
+    from .scene import DeviceScene
+    dev = torch.device(device)
+    state, meta = synthetic.make_scene("lego", grid_size=grid, bg_resolution=32)
+    state.update(synthetic.plain_mlp_state(0))
+    sc = DeviceScene(state, meta["aabb"], meta["near_far"], meta["grid_size"], device=dev, model="plain")
+    vol = sc.update_alpha_mask()
+    H = W = 800
+    focal = synthetic.focal_for(W)
+    pose = synthetic.hemisphere_poses(4)[1]
+    pix = torch.randperm(H * W, generator=torch.Generator().manual_seed(0))[:n_rays]
+    rays = synthetic.camera_rays(pose, H, W, focal)[pix].contiguous().to(dev)
+    gt = ops.render_rays(sc, rays, focal, chunk=n_rays, skip_eps=0.0, t_cut=0.0)[0]["rgb_map"].clone()
+    out = train_plain(sc, rays, gt, focal=focal, seed=1)
+    bufs = out["buffers"]
+    for _ in range(3):
+        train_plain(sc, rays, gt, focal=focal, seed=1, buffers=bufs, check_errors=False)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(steps):
+        train_plain(sc, rays, gt, focal=focal, seed=1, buffers=bufs, check_errors=False)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / max(steps, 1)
+    res = dict(what="nmf_train_plain forward+backward, model=tensorf (SURVEY 8f row 1)", grid=grid, rays=n_rays,
+               n_samples=out["n_samples"], ms_per_step=ms, rays_per_s=n_rays / ms * 1e3,
+               samples_per_s=out["n_samples"] / ms * 1e3, gpu_launches_per_step=7)
+    if iters > 0:
+        g = torch.Generator().manual_seed(2)
+        st2 = {k: v.clone() for k, v in state.items()}
+        for k in PLAIN_PARAM_KEYS:
+            if ("app_rf" in k) or ("mlp" in k):
+                st2[k] = st2[k] + 0.05 * st2[k].abs().mean() * torch.randn(st2[k].shape, generator=g)
+        tr = PlainTrainer(st2, meta["aabb"], meta["near_far"], meta["grid_size"], alpha_volume=vol, device=dev)
+        mse = [tr.step(rays, gt)["mse"] for _ in range(3)]
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        mse += [tr.step(rays, gt)["mse"] for _ in range(iters - 3)]
+        torch.cuda.synchronize(dev)
+        res.update(loop_iters=iters, loop_ms_per_iter=(time.perf_counter() - t0) / max(iters - 3, 1) * 1e3,
+                   loop_mse_first=mse[0], loop_mse_last=mse[-1])
+    return res
