@@ -195,6 +195,18 @@ def test_train_sampler_bit_exact(hostcheck, name):
     assert torch.equal(z2, zz) and torch.equal(v2, v)
 
 
+def plain_variant(name):
+    """a golden fixture's field (factors, occupancy, rays) under the model=tensorf view MLP: turns the microfacet
+    fixtures -- non-cubic grids, density in all three plane/line pairs -- into training cases"""
+    from nmf_b200 import synthetic
+    fix = dict(load_fixture(name))
+    if fix["model"] != "tensorf":
+        fix["state"] = dict(fix["state"])
+        fix["state"].update(synthetic.plain_mlp_state(3))
+        fix["model"] = "tensorf"
+    return fix
+
+
 def oracle_train_plain(fix, rays, gt, seed, ids, max_samples, lambda_pred):
     """loss and gradients of the oracle's training forward (KeyedRNG jitter), reference state_dict keys"""
     osc = oracle_scene(fix, requires_grad=True)
@@ -230,12 +242,12 @@ def check_plain_grads(mine, ref, tol=5e-3, tol_density=1e-2):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("max_samples", [-1, 2500])
-def test_train_plain_host_gradients(hostcheck, max_samples):
+@pytest.mark.parametrize("name,max_samples", [("plain_g64", -1), ("plain_g64", 2500), ("microfacet_noncubic", -1)])
+def test_train_plain_host_gradients(hostcheck, name, max_samples):
     """the per-element forward + backward math of nmf_train_plain (host build) against the oracle's autograd"""
     from nmf_b200 import _lib
     from nmf_b200.train import PlainGradBuffers
-    fix = load_fixture("plain_g64")
+    fix = plain_variant(name)
     dsc = device_scene(fix, "cpu")
     n = 96
     rays = fix["rays"][:n].contiguous()
