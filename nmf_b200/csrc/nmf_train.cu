@@ -97,42 +97,6 @@ __global__ void __launch_bounds__(256) k_train_sample(const NmfScene s, const Sa
   if (lane == 0) a.n_valid[ray] = nv;
 }
 
-// one CTA of 1024 threads: inclusive sums of n_valid -> whole_valid, offsets (alphagrid.py:353-364)
-__global__ void __launch_bounds__(1024) k_train_prefix(const int* n_valid, int n, int max_samples, int* offs, uint8_t* whole,
-                                                       int* n_kept) {
-  __shared__ long long part[1024];
-  const int t = threadIdx.x;
-  const int per = (n + 1023) / 1024;
-  const int b = t * per, e = min(n, b + per);
-  long long sum = 0;
-  for (int i = b; i < e; ++i) sum += n_valid[i];
-  part[t] = sum;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const long long v = t >= off ? part[t - off] : 0;
-    __syncthreads();
-    part[t] += v;
-    __syncthreads();
-  }
-  const long long total = part[1023];
-  const bool trunc = max_samples > 0 && total > (long long)max_samples;
-  long long run = t ? part[t - 1] : 0;
-  int last = -1;
-  long long last_incl = 0;
-  for (int i = b; i < e; ++i) {
-    const long long incl = run + n_valid[i];
-    const bool keep = !trunc || incl < (long long)max_samples;   // the inclusive sums are monotone: kept rays are a prefix
-    whole[i] = keep;
-    if (offs) offs[i] = (int)run;            // exclusive prefix (used for kept rays only)
-    if (keep) { last = i; last_incl = incl; }
-    run = incl;
-  }
-  if (last >= 0) {                           // n_kept is zeroed by the caller
-    atomicMax(n_kept, last + 1);
-    atomicMax(n_kept + 1, (int)last_incl);
-  }
-}
-
 extern "C" int nmf_sample_rays_train(const NmfScene* scene, const float* rays, int n_rays, float near_override, uint64_t seed,
                                      uint64_t ray_id0, const uint64_t* ray_ids, int max_samples, uint8_t* ray_valid,
                                      float* z_vals, int* n_valid, uint8_t* whole_valid, int* n_kept, void* stream) {

@@ -157,3 +157,60 @@ NMF_HD float nmf_resize_pixel(const float* plane, int W, int y0, int y1, float h
   const float bot = NMF_ADD(NMF_MUL(wx0, plane[(size_t)y1 * W + x0]), NMF_MUL(wx1, plane[(size_t)y1 * W + x1]));
   return NMF_ADD(NMF_MUL(hy0, top), NMF_MUL(hy1, bot));
 }
+
+#ifdef __CUDACC__
+// One warp writes the jittered distances of a ray: z_k = tmin + fp32(sum_{j<=k} step_j).  Every partial sum of <= 2048
+// fp32 step lengths in [stepsize/2, 3 stepsize/2] is exact in fp64 (37 significant bits), so the scan order does not
+// matter: the prefix equals ATen's sequential fp64 accumulation (CPU cumsum), rounded to fp32 per element.
+__device__ __forceinline__ void nmf_warp_jitter_z(uint64_t key, float tmin, float stepsize, int S, float* zrow, int lane) {
+  double carry = 0.0;
+  for (int base = 0; base < S; base += 32) {
+    const int k = base + lane;
+    double v = k < S ? (double)nmf_jitter_step(key, k, stepsize) : 0.0;
+    for (int off = 1; off < 32; off <<= 1) {
+      const double u = __shfl_up_sync(0xffffffffu, v, off);
+      if (lane >= off) v += u;
+    }
+    v += carry;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+    if (k < S) zrow[k] = NMF_ADD(tmin, (float)v);
+  }
+}
+
+// one CTA of 1024 threads: inclusive sums of n_valid -> whole_valid, offsets, kept counts (alphagrid.py:353-364).
+// n_kept[0..1] must be zero on entry.
+static __global__ void __launch_bounds__(1024) k_train_prefix(const int* n_valid, int n, int max_samples, int* offs, uint8_t* whole,
+                                                              int* n_kept) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int b = t * per, e = min(n, b + per);
+  long long sum = 0;
+  for (int i = b; i < e; ++i) sum += n_valid[i];
+  part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const long long v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  const long long total = part[1023];
+  const bool trunc = max_samples > 0 && total > (long long)max_samples;
+  long long run = t ? part[t - 1] : 0;
+  int last = -1;
+  long long last_incl = 0;
+  for (int i = b; i < e; ++i) {
+    const long long incl = run + n_valid[i];
+    const bool keep = !trunc || incl < (long long)max_samples;   // the inclusive sums are monotone: kept rays are a prefix
+    whole[i] = keep;
+    if (offs) offs[i] = (int)run;            // exclusive prefix (used for kept rays only)
+    if (keep) { last = i; last_incl = incl; }
+    run = incl;
+  }
+  if (last >= 0) {
+    atomicMax(n_kept, last + 1);
+    atomicMax(n_kept + 1, (int)last_incl);
+  }
+}
+#endif
