@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NMF_ABI_VERSION 6
+#define NMF_ABI_VERSION 7
 
 #define NMF_OK 0
 #define NMF_E_ARG (-1)          /* null pointer / non-positive size                                   */
@@ -268,7 +268,7 @@ int nmf_image_sq_error(const float* rgb, const float* gt, const int* pixel_ids, 
  * CPU cumsum), so z is bit-reproducible.  Outputs cover ALL n_rays rays: ray_valid (n, n_steps) uint8, z_vals
  * (n, n_steps), n_valid (n); whole_valid (n) uint8 = rays kept by the dynamic batch truncation (all 1 unless
  * max_samples > 0 and the batch holds more than max_samples valid samples; then cumsum(n_valid) < max_samples);
- * n_kept (int[2]) = {kept rays (a prefix of the batch), valid samples of the kept rays}. */
+ * n_kept (int[2]) = {kept rays (a prefix of the batch), valid samples of the kept rays}.  ray_valid may be NULL. */
 int nmf_sample_rays_train(const NmfScene* scene, const float* rays, int n_rays, float near_override, uint64_t seed,
                           uint64_t ray_id0, const uint64_t* ray_ids, int max_samples, uint8_t* ray_valid, float* z_vals,
                           int* n_valid, uint8_t* whole_valid, int* n_kept, void* stream);
@@ -316,6 +316,26 @@ size_t nmf_train_workspace_bytes(const NmfScene* scene, int n_rays, int cap_samp
 int nmf_train_plain(const NmfScene* scene, const NmfTrain* tp, const float* rays, const float* gt,
                     const NmfPlainGrads* grads, const NmfTrainOut* out, void* workspace, size_t workspace_bytes,
                     void* stream);
+
+/* Training FORWARD of the microfacet model: TensorNeRF.forward(is_train=True, draw_debug=False)
+ * (modules/tensor_nerf.py:210-674 with models/microfacet.py:271-673) through the fused render kernels --
+ * jittered cumulative distances at recur 0 and in the re-traced rays (samplers/alphagrid.py:167-173; the recursion
+ * passes is_train on, tensor_nerf.py:303), the dynamic batch truncation at recur 0 only (alphagrid.py:353-364; the
+ * recursion runs with dynamic_batch_size=False, tensor_nerf.py:299), the bounce roughness clipped from below
+ * (microfacet.py:361-363).  Loss-side quantities come back as in eval mode: rgb_map / acc_map rows of the kept rays
+ * (a prefix of the batch: rows >= n_kept[0] are background), NmfCounters.stat4 = the A19 regulariser sums,
+ * n_samples0 / n_samples1 = statistics["n_samples"].  The batch is ONE forward call: rp->n_rays <= rp->chunk.
+ * The jitter is keyed by (rp->seed, rp->ray_id0 + i, step).  Forward only: the microfacet backward is not built. */
+typedef struct NmfRenderTrain {
+  int max_samples;         /* AlphaGridSampler.max_samples (<= 0: no truncation) */
+  float min_rough;         /* Microfacet.min_rough */
+  uint8_t* whole_valid;    /* (n) out, device: statistics["whole_valid"] */
+  int* n_kept;             /* [2] out, device: kept rays, valid primary samples of the kept rays */
+} NmfRenderTrain;
+size_t nmf_render_train_workspace_bytes(const NmfScene* scene, int n_rays, float cap_scale);
+int nmf_render_rays_train(const NmfScene* scene, const NmfRender* rp, const NmfRenderTrain* tr, const float* rays,
+                          const NmfImages* out, const NmfCounters* counters, void* workspace, size_t workspace_bytes,
+                          void* stream);
 
 /* Resolution schedule (fields/tensor_base.py:234-243 -> fields/tensoRF.py:208-227, 408-413): TensoRF.upsample is
  * F.interpolate(mode="bilinear", align_corners=True) of every factor.  src (C,H,W) -> dst (C,H2,W2), both in the

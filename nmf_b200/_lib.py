@@ -68,6 +68,10 @@ class NmfTrainOut(C.Structure):
                 ("n_kept", C.c_void_p), ("error", C.c_void_p)]
 
 
+class NmfRenderTrain(C.Structure):
+    _fields_ = [("max_samples", C.c_int), ("min_rough", C.c_float), ("whole_valid", C.c_void_p), ("n_kept", C.c_void_p)]
+
+
 IMAGE_FIELDS = ["rgb_map", "acc_map", "depth", "world_normal", "normal", "termination_xyz", "surf_width",
                 "cross_section", "diffuse", "tint", "roughness", "spec", "albedo"]
 COUNTER_FIELDS = ["n_samples0", "n_samples1", "n_cand", "n_bounce_rays0", "n_bounce_rays1", "n_retrace",
@@ -144,6 +148,8 @@ def lib():
         "nmf_sample_rays_train": (I, [SP, P, I, F, C.c_uint64, C.c_uint64, P, I, P, P, P, P, P, P]),
         "nmf_train_workspace_bytes": (C.c_size_t, [SP, I, I]),
         "nmf_upsample_bilinear": (I, [P, I, I, I, P, I, I, P]),
+        "nmf_render_train_workspace_bytes": (C.c_size_t, [SP, I, F]),
+        "nmf_render_rays_train": (I, [SP, RP, C.POINTER(NmfRenderTrain), P, IP, CP, P, C.c_size_t, P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
                                 C.c_size_t, P]),
     }
@@ -151,7 +157,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    assert L.nmf_abi_version() == 6, "libnmf_b200.so ABI mismatch: rebuild"
+    assert L.nmf_abi_version() == 7, "libnmf_b200.so ABI mismatch: rebuild"
     _lib = L
     return L
 
@@ -159,4 +165,5 @@ def lib():
 EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_profile_phase_name", "nmf_workspace_bytes", "nmf_workspace_bytes_scaled", "nmf_render_rays", "nmf_render_rays_host", "nmf_sample_rays",
             "nmf_vm_density", "nmf_vm_appfeature", "nmf_vm_normals", "nmf_env_lookup", "nmf_ggx_sample",
             "nmf_brdf_mlp", "nmf_material_heads", "nmf_dense_alpha", "nmf_generate_rays", "nmf_image_sq_error",
-            "nmf_sample_rays_train", "nmf_train_workspace_bytes", "nmf_train_plain", "nmf_upsample_bilinear"]
+            "nmf_sample_rays_train", "nmf_train_workspace_bytes", "nmf_train_plain", "nmf_upsample_bilinear",
+            "nmf_render_train_workspace_bytes", "nmf_render_rays_train"]

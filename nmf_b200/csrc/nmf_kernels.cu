@@ -21,6 +21,7 @@
 
 #include "nmf_field.cuh"
 #include "nmf_mlp_tc.cuh"
+#include "nmf_train.cuh"   // train mode: jittered distances, dynamic batch truncation
 
 #define FULL 0xffffffffu
 #define NMF_BRAY_CAP_PER_RAY 160   // bounce rays per primary ray a chunk region can hold (typical: 57)
@@ -82,6 +83,8 @@ struct WS {
   // level 1
   float* rays1; float* mip1; uint64_t* key1; float* tmin1; float* acc1; int* nvalid1; float* accum1; float* rgb1;
   Surv* surv1; BSample* bs1; BRay* brays1; uint32_t* owner1;
+  // train mode (nmf_render_rays_train): jittered distances per dense step, dynamic batch truncation
+  float* zvals0; float* zvals1; uint8_t* whole0; int* n_kept;
   int n_chunks, n_rays1;
   int cap_surv0, cap_bs0, cap_rays0;   // cap_rays0: per chunk
   int cap_surv1, cap_bs1, cap_rays1;   // cap_rays1: per chunk
@@ -90,7 +93,7 @@ struct WS {
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base, float cap_scale = 1.0f) {
+static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base, float cap_scale = 1.0f, bool train = false) {
   const double cs = cap_scale > 0.f ? (double)cap_scale : 1.0;
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
@@ -147,6 +150,13 @@ static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base, f
     w.brays1 = (BRay*)take((size_t)nc * w.cap_rays1 * sizeof(BRay));
     w.owner1 = (uint32_t*)take((size_t)nc * w.cap_rays1 * 4);
   }
+  w.zvals0 = w.zvals1 = nullptr; w.whole0 = nullptr; w.n_kept = nullptr;
+  if (train) {
+    w.zvals0 = (float*)take((size_t)n_rays * s->n_steps * 4);
+    w.zvals1 = (float*)take((size_t)w.n_rays1 * s->n_steps * 4);
+    w.whole0 = (uint8_t*)take((size_t)n_rays);
+    w.n_kept = (int*)take(2 * sizeof(int));
+  }
   w.total = off;
 }
 
@@ -164,6 +174,8 @@ struct MarchArgs {
   float* tmin; float* acc; float* depth; int* termk; int* nvalid;
   int* n_samples; int* n_cand; double* wsum;
   Surv* surv; int* n_surv; int cap_surv; unsigned* error;
+  float* zvals;            // train mode: (n, n_steps) jittered distances (level 0: read, level 1: written here)
+  const uint8_t* whole;    // train mode, level 0: rays kept by the dynamic batch truncation
 };
 
 // The 8-corner occupancy test of a step that lies exactly on a lattice plane.  Rare (a handful per thousand rays), so it
@@ -173,7 +185,11 @@ __device__ __noinline__ bool march_occupied_on_lattice(const uint32_t* vox, cons
   return nmf_occupied(vox, cell, ow, oh, od, opitch, xn0, xn1, xn2);
 }
 
-template <int LEVEL>
+// TRAIN = 1 (TensorNeRF.forward(is_train=True), alphagrid.py:167-173): the distance of dense step k is read from the
+// ray's row of jittered cumulative distances instead of tmin + stepsize * k.  Level 0 rows come from k_train_sample (the
+// dynamic batch truncation sits between the sampling and the march); level 1 rows are written here (the recursion runs
+// with dynamic_batch_size=False, tensor_nerf.py:299).  The distances are still increasing in k, so the exit test holds.
+template <int LEVEL, int TRAIN>
 __global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchArgs a) {
   __shared__ uint16_t s_list[8][NMF_MAX_STEPS];
   __shared__ uint32_t s_coarse[NMF_MAX_COARSE_WORDS];
@@ -190,6 +206,10 @@ __global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchA
   for (int ray = blockIdx.x * 8 + warp; ray < a.n; ray += gridDim.x * 8) {
     const int chunk = ray / a.group;
     if (LEVEL == 1 && (ray - chunk * a.group) >= a.n_active[chunk]) continue;
+    if (TRAIN && LEVEL == 0 && !a.whole[ray]) {      // alphagrid.py:359-364: the ray is dropped from the batch
+      if (lane == 0) { a.tmin[ray] = 0.f; a.acc[ray] = 0.f; a.nvalid[ray] = 0; a.depth[ray] = 0.f; a.termk[ray] = -1; }
+      continue;
+    }
     float o[3], d[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) { o[i] = __ldg(a.rays + (size_t)ray * 6 + i); d[i] = __ldg(a.rays + (size_t)ray * 6 + 3 + i); }
@@ -197,6 +217,12 @@ __global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchA
     const float tmin = nmf_ray_tmin(o, d, s.aabb0, s.aabb1, near_, s.far);
     uint64_t key = 0;
     if (LEVEL == 1) key = a.keys[ray];
+    float* zrow = TRAIN ? a.zvals + (size_t)ray * S : nullptr;
+    if (TRAIN && LEVEL == 1) {
+      nmf_warp_jitter_z(key, tmin, s.stepsize, S, zrow, lane);
+      __syncwarp();
+    }
+#define MARCH_Z(k_) (TRAIN ? zrow[k_] : nmf_step_z(tmin, s.stepsize, (k_)))
     // ---- pass A: enumerate the dense steps, keep those inside the box and in an occupied cell ----
     // Each coordinate of p_k = o + d * (tmin + step * k) is monotone in k also in fp32 (mul and add are monotone), so
     // the in-box steps are one contiguous range: after the first out-of-box step that follows an in-box one, every
@@ -217,7 +243,7 @@ __global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchA
         state[j] = 0; word[j] = 0; shift[j] = 0;
         if (k < S) {
           float p[3];
-          nmf_step_pos(o, d, nmf_step_z(tmin, s.stepsize, k), p);
+          nmf_step_pos(o, d, MARCH_Z(k), p);
           if (nmf_inside(p, s.aabb0, s.aabb1)) {
             ++cand;
             state[j] = 3;
@@ -244,7 +270,7 @@ __global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchA
         bool ok = state[j] == 3 || (state[j] == 1 && ((word[j] >> shift[j]) & 1u));
         if (state[j] == 2) {                 // rare: a sample exactly on a lattice plane takes the 8-corner path
           float p[3], xn[3];
-          nmf_step_pos(o, d, nmf_step_z(tmin, s.stepsize, k), p);
+          nmf_step_pos(o, d, MARCH_Z(k), p);
           nmf_normalize_xyz(s, p, xn);
           ok = march_occupied_on_lattice(s.occ_vox, s.occ_cell, s.ow, s.oh, s.od, s.opitch, xn[0], xn[1], xn[2]);
         }
@@ -271,7 +297,7 @@ __global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchA
       const int j = j0 + sj;
       const bool active = j < nv;
       const int k = active ? (int)list[j] : 0;
-      const float z = nmf_step_z(tmin, s.stepsize, k);
+      const float z = MARCH_Z(k);
       float p[3], xn[3];
       nmf_step_pos(o, d, z, p);
       nmf_normalize_xyz(s, p, xn);
@@ -280,7 +306,7 @@ __global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchA
       f += __shfl_xor_sync(FULL, f, 1);
       f += __shfl_xor_sync(FULL, f, 2);
       const float sigma = active ? nmf_feature2density(f, s.density_shift) : 0.f;
-      const float z1 = (k + 1 < S) ? nmf_step_z(tmin, s.stepsize, k + 1) : z;       // alphagrid.py:348-350
+      const float z1 = (k + 1 < S) ? MARCH_Z(k + 1) : z;                            // alphagrid.py:348-350
       const float dist = NMF_SUB(z1, z) * s.distance_scale;
       const float alpha = 1.0f - expf(-sigma * dist);                                // tensor_nerf.py:25
       float incl = (1.0f - alpha) + 1e-10f;                                          // :28
@@ -343,6 +369,7 @@ __global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchA
     }
     __syncwarp();
   }
+#undef MARCH_Z
 }
 
 // ================================================================================================
@@ -361,6 +388,8 @@ struct ShadeArgs {
   const int* n_samples; const double* wsum;   // level 1 budget
   unsigned* error;
   float4* red;              // level 0: per bounce sample {w, count, ray, flags | rgb sum}
+  const float* zvals; int n_steps;   // train mode: jittered distances (n, n_steps)
+  float min_rough;          // train mode: Microfacet.min_rough (models/microfacet.py:361-363)
 };
 
 // Two phases per warp, 32 surviving samples at a time:
@@ -387,7 +416,7 @@ __device__ __forceinline__ void shade_mma(float (&c)[4], uint32_t a0, uint32_t a
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
 }
-template <int LEVEL>
+template <int LEVEL, int TRAIN>
 __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeArgs a) {
   extern __shared__ __align__(16) float shade_sm[];
   uint32_t* s_bhi = (uint32_t*)shade_sm;                 // [72][24] TF32 high part of basis_t
@@ -425,7 +454,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       float o[3], d[3], p[3], xn[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) { o[i] = __ldg(a.rays + (size_t)ray * 6 + i); d[i] = __ldg(a.rays + (size_t)ray * 6 + 3 + i); }
-      nmf_step_pos(o, d, nmf_step_z(a.tmin[ray], s.stepsize, (int)sv.step), p);
+      nmf_step_pos(o, d, TRAIN ? a.zvals[(size_t)ray * a.n_steps + sv.step] : nmf_step_z(a.tmin[ray], s.stepsize, (int)sv.step), p);
       nmf_normalize_xyz(s, p, xn);
       float* row = s_feat + lane * SHADE_FEAT_LD;
       row[0] = xn[0]; row[1] = xn[1]; row[2] = xn[2];
@@ -502,7 +531,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
     float o[3], d[3], p[3], xn[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) { o[i] = __ldg(a.rays + (size_t)ray * 6 + i); d[i] = __ldg(a.rays + (size_t)ray * 6 + 3 + i); }
-    nmf_step_pos(o, d, nmf_step_z(a.tmin[ray], s.stepsize, k), p);
+    nmf_step_pos(o, d, TRAIN ? a.zvals[(size_t)ray * a.n_steps + k] : nmf_step_z(a.tmin[ray], s.stepsize, k), p);
     nmf_normalize_xyz(s, p, xn);
     float* fs = s_feat + lane * SHADE_FEAT_LD;
     float* hs = s_coef + lane * 9;         // per-channel head results, parked in the (now idle) coefficient staging rows
@@ -610,7 +639,8 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       const nmf_v3 Nf = nmf_mk3(nrm.x * sgn, nrm.y * sgn, nrm.z * sgn);
       float4* q = (float4*)b;
       q[0] = make_float4(p[0], p[1], p[2], w);
-      q[1] = make_float4(V.x, V.y, V.z, rough);
+      const float rough_b = TRAIN ? fmaxf(rough, a.min_rough) : rough;     // microfacet.py:361-363 (bounce rays only)
+      q[1] = make_float4(V.x, V.y, V.z, rough_b);
       q[2] = make_float4(Nf.x, Nf.y, Nf.z, __int_as_float(count));
       q[3] = make_float4(hs[0], hs[1], hs[2], __uint_as_float((uint32_t)ray));
       q[4] = make_float4(hs[3], hs[4], hs[5], __uint_as_float((uint32_t)roff));
@@ -621,9 +651,9 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
         a.red[2 * slot + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       // per-sample part of the GGX sampler and of the ISH encodings, shared by all bounce rays of the sample
-      const NmfGGXFrame fr = nmf_ggx_frame(V, Nf, rough);
+      const NmfGGXFrame fr = nmf_ggx_frame(V, Nf, rough_b);
       float s1, s2;
-      nmf_ish_scales(rough, &s1, &s2);
+      nmf_ish_scales(rough_b, &s1, &s2);
       float4* fq = (float4*)b->frame;
       fq[0] = make_float4(fr.t.x, fr.t.y, fr.t.z, fr.b.x);
       fq[1] = make_float4(fr.b.y, fr.b.z, fr.V_l.x, fr.V_l.y);
@@ -1242,6 +1272,7 @@ struct FinishArgs {
   const float* rays; const float* tmin; const float* acc; const float* depth; const int* termk; const int* nvalid;
   const float* accum; int n; float focal; int model;
   int chunk; float* stat4; int do_stats;
+  const float* zvals; int n_steps;    // train mode: jittered distances
 };
 __global__ void k_finish0(const NmfScene s, const FinishArgs a, const NmfImages out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1277,7 +1308,7 @@ __global__ void k_finish0(const NmfScene s, const FinishArgs a, const NmfImages 
     if (k >= 0) {
       float o[3], d[3];
       for (int c = 0; c < 3; ++c) { o[c] = a.rays[(size_t)i * 6 + c]; d[c] = a.rays[(size_t)i * 6 + 3 + c]; }
-      const float z = nmf_step_z(a.tmin[i], s.stepsize, k);
+      const float z = a.zvals ? a.zvals[(size_t)i * a.n_steps + k] : nmf_step_z(a.tmin[i], s.stepsize, k);
       nmf_step_pos(o, d, z, v);
       v[3] = z / a.focal;                                               // alphagrid.py:200
     }
@@ -1445,7 +1476,8 @@ static NmfImages stage_images(const NmfImages& o, int stage) {
 }
 
 static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* rays, const NmfImages* out,
-                       const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream_, const StagedCopy* sc) {
+                       const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream_, const StagedCopy* sc,
+                       const NmfRenderTrain* tr = nullptr) {
   int st = check_scene(scene);
   if (st) return st;
   if (!rp || !rays || !out || !workspace || rp->n_rays <= 0 || rp->chunk <= 0) return NMF_E_ARG;
@@ -1457,7 +1489,8 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
   if (s.model == 0 && s.max_retrace > 0 && s.max_brdf_rays1 <= 0) return NMF_E_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
   WS w;
-  carve(w, scene, rp->n_rays, rp->chunk, (char*)workspace, rp->cap_scale);
+  if (tr && (s.model != 0 || rp->n_rays > rp->chunk || !tr->whole_valid || !tr->n_kept)) return NMF_E_UNSUPPORTED;
+  carve(w, scene, rp->n_rays, rp->chunk, (char*)workspace, rp->cap_scale, tr != nullptr);
   if (w.total > workspace_bytes) return NMF_E_WORKSPACE;
   const int n = rp->n_rays, nc = w.n_chunks;
   CK(cudaMemsetAsync(w.counters_base, 0, w.counters_bytes, stream));
@@ -1469,15 +1502,25 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
   m0.tmin = w.tmin0; m0.acc = w.acc0; m0.depth = w.depth0; m0.termk = w.termk0; m0.nvalid = w.nvalid0;
   m0.n_samples = w.n_samples0; m0.n_cand = w.n_cand; m0.wsum = nullptr;
   m0.surv = w.surv0; m0.n_surv = w.n_surv; m0.cap_surv = w.cap_surv0; m0.error = w.error;
+  m0.zvals = w.zvals0; m0.whole = tr ? tr->whole_valid : nullptr;
   static int g_march0 = 0, g_march1 = 0, g_inc0 = 0, g_inc1 = 0;
   if (!g_march0) {
-    g_march0 = resident_grid(k_march<0>, 256, 0); g_march1 = resident_grid(k_march<1>, 256, 0);
+    g_march0 = resident_grid(k_march<0, 0>, 256, 0); g_march1 = resident_grid(k_march<1, 0>, 256, 0);
     g_inc0 = resident_grid(k_incoming<0>, MLP_THREADS, 0); g_inc1 = resident_grid(k_incoming<1>, MLP_THREADS, 0);
   }
   // rays differ a lot in cost: several waves of small CTAs (a multiple of the resident count) balance better than one
-  k_march<0><<<min(4 * g_march0, blocks_for(n, 8, 1 << 20)), 256, 0, stream>>>(s, m0);
+  if (tr) {
+    // alphagrid.py:167-207 + 353-364: jittered distances and per-ray counts of the whole batch, then the truncation
+    st = nmf_sample_rays_train(scene, rays, n, -1.0f, rp->seed, rp->ray_id0, nullptr, tr->max_samples, nullptr, w.zvals0,
+                               w.nvalid0, tr->whole_valid, tr->n_kept, stream_);
+    if (st) return st;
+    k_march<0, 1><<<min(4 * g_march0, blocks_for(n, 8, 1 << 20)), 256, 0, stream>>>(s, m0);
+  } else {
+    k_march<0, 0><<<min(4 * g_march0, blocks_for(n, 8, 1 << 20)), 256, 0, stream>>>(s, m0);
+  }
   CKL();
-  FinishArgs fa = {rays, w.tmin0, w.acc0, w.depth0, w.termk0, w.nvalid0, w.accum0, n, rp->focal, s.model, rp->chunk, w.stat4, 0};
+  FinishArgs fa = {rays, w.tmin0, w.acc0, w.depth0, w.termk0, w.nvalid0, w.accum0, n, rp->focal, s.model, rp->chunk, w.stat4, 0,
+                   w.zvals0, s.n_steps};
   if (sc && s.model == 0) {
     k_finish0<<<(n + 127) / 128, 128, 0, stream>>>(s, fa, stage_images(*out, 0));
     CKL();
@@ -1496,8 +1539,10 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
     CK(cudaGetDevice(&dev_id));
     const bool attr_done = (attr_done_mask >> (dev_id & 63)) & 1ull;
     if (!attr_done) {
-      CK(cudaFuncSetAttribute(k_shade<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SHADE_SMEM_FLOATS * sizeof(float))));
-      CK(cudaFuncSetAttribute(k_shade<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SHADE_SMEM_FLOATS * sizeof(float))));
+      CK(cudaFuncSetAttribute(k_shade<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SHADE_SMEM_FLOATS * sizeof(float))));
+      CK(cudaFuncSetAttribute(k_shade<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SHADE_SMEM_FLOATS * sizeof(float))));
+      CK(cudaFuncSetAttribute(k_shade<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SHADE_SMEM_FLOATS * sizeof(float))));
+      CK(cudaFuncSetAttribute(k_shade<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SHADE_SMEM_FLOATS * sizeof(float))));
       CK(cudaFuncSetAttribute(k_bounce<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MLP_SMEM_FLOATS * sizeof(float))));
       CK(cudaFuncSetAttribute(k_bounce<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MLP_SMEM_FLOATS * sizeof(float))));
       CK(cudaFuncSetAttribute(k_bounce<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
@@ -1509,7 +1554,9 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
     h0.surv = w.surv0; h0.n_surv = w.n_surv; h0.cap_surv = w.cap_surv0; h0.accum = w.accum0;
     h0.bs = w.bs0; h0.n_bs = w.n_bs; h0.cap_bs = w.cap_bs0; h0.ray_count = w.ray_count0; h0.cap_rays = w.cap_rays0;
     h0.owner = w.owner0; h0.error = w.error; h0.red = w.red0;
-    k_shade<0><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h0);
+    h0.zvals = w.zvals0; h0.n_steps = s.n_steps; h0.min_rough = tr ? tr->min_rough : 0.f;
+    if (tr) k_shade<0, 1><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h0);
+    else k_shade<0, 0><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h0);
     CKL();
     if (sc) {
       k_finish0<<<(n + 127) / 128, 128, 0, stream>>>(s, fa, stage_images(*out, 1));
@@ -1541,7 +1588,9 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
       m1.tmin = w.tmin1; m1.acc = w.acc1; m1.depth = nullptr; m1.termk = nullptr; m1.nvalid = w.nvalid1;
       m1.n_samples = w.n_samples1; m1.n_cand = w.n_cand; m1.wsum = w.wsum1;
       m1.surv = w.surv1; m1.n_surv = w.n_surv + 1; m1.cap_surv = w.cap_surv1; m1.error = w.error;
-      k_march<1><<<min(4 * g_march1, blocks_for(w.n_rays1, 8, 1 << 20)), 256, 0, stream>>>(s, m1);
+      m1.zvals = w.zvals1;
+      if (tr) k_march<1, 1><<<min(4 * g_march1, blocks_for(w.n_rays1, 8, 1 << 20)), 256, 0, stream>>>(s, m1);
+      else k_march<1, 0><<<min(4 * g_march1, blocks_for(w.n_rays1, 8, 1 << 20)), 256, 0, stream>>>(s, m1);
       CKL();
       prof_mark(5, stream);
       ShadeArgs h1 = {};
@@ -1549,7 +1598,9 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
       h1.surv = w.surv1; h1.n_surv = w.n_surv + 1; h1.cap_surv = w.cap_surv1; h1.accum = nullptr;
       h1.bs = w.bs1; h1.n_bs = w.n_bs + 1; h1.cap_bs = w.cap_bs1; h1.ray_count = w.ray_count1; h1.cap_rays = w.cap_rays1;
       h1.owner = w.owner1; h1.n_samples = w.n_samples1; h1.wsum = w.wsum1; h1.error = w.error;
-      k_shade<1><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h1);
+      h1.zvals = w.zvals1; h1.n_steps = s.n_steps; h1.min_rough = tr ? tr->min_rough : 0.f;
+      if (tr) k_shade<1, 1><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h1);
+      else k_shade<1, 0><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h1);
       CKL();
       prof_mark(6, stream);
       k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count1, w.cap_rays1, nc, w.tile_start1);
@@ -1609,6 +1660,20 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
 extern "C" int nmf_render_rays(const NmfScene* scene, const NmfRender* rp, const float* rays, const NmfImages* out,
                                const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream_) {
   return render_impl(scene, rp, rays, out, counters, workspace, workspace_bytes, stream_, nullptr);
+}
+
+extern "C" size_t nmf_render_train_workspace_bytes(const NmfScene* scene, int n_rays, float cap_scale) {
+  if (!scene || n_rays <= 0) return 0;
+  WS w;
+  carve(w, scene, n_rays, n_rays, nullptr, cap_scale, true);
+  return w.total;
+}
+
+extern "C" int nmf_render_rays_train(const NmfScene* scene, const NmfRender* rp, const NmfRenderTrain* tr, const float* rays,
+                                     const NmfImages* out, const NmfCounters* counters, void* workspace,
+                                     size_t workspace_bytes, void* stream_) {
+  if (!tr) return NMF_E_ARG;
+  return render_impl(scene, rp, rays, out, counters, workspace, workspace_bytes, stream_, nullptr, tr);
 }
 
 extern "C" int nmf_render_rays_host(const NmfScene* scene, const NmfRender* rp, const float* rays_host, float* rays_dev,

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_train_sample(const NmfScene s, const Sa
         nmf_normalize_xyz(s, p, xn);
         ok = nmf_occupied(s.occ_vox, s.occ_cell, s.ow, s.oh, s.od, s.opitch, xn[0], xn[1], xn[2]);
       }
-      a.valid[(size_t)ray * s.n_steps + k] = ok;
+      if (a.valid) a.valid[(size_t)ray * s.n_steps + k] = ok;
       a.z[(size_t)ray * s.n_steps + k] = z;
       nv += ok;
     }
@@ -102,7 +102,7 @@ extern "C" int nmf_sample_rays_train(const NmfScene* scene, const float* rays, i
                                      float* z_vals, int* n_valid, uint8_t* whole_valid, int* n_kept, void* stream) {
   int st = t_check_scene(scene);
   if (st) return st;
-  if (!rays || n_rays <= 0 || !ray_valid || !z_vals || !n_valid) return NMF_E_ARG;
+  if (!rays || n_rays <= 0 || !z_vals || !n_valid) return NMF_E_ARG;     // ray_valid is optional
   cudaStream_t cs = (cudaStream_t)stream;
   SampleArgs a{rays, n_rays, near_override, seed, ray_id0, ray_ids, ray_valid, z_vals, n_valid};
   k_train_sample<<<(n_rays + 7) / 8, 256, 0, cs>>>(*scene, a);

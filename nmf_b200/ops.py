@@ -163,8 +163,9 @@ def image_sq_error(rgb, gt, pixel_ids=None):
 class RenderBuffers:
     """Output images, counters and scratch for batches of up to `n_rays` rays (grow-only cache per scene)."""
 
-    def __init__(self, scene, n_rays, chunk, keys, cap_scale=1.0):
+    def __init__(self, scene, n_rays, chunk, keys, cap_scale=1.0, train=False):
         dev = scene.device
+        self.train = train
         self.n_rays, self.chunk, self.cap_scale, self.keys = n_rays, chunk, float(cap_scale), list(keys)
         self.n_chunks = (n_rays + chunk - 1) // chunk
         self.images = {}
@@ -179,7 +180,12 @@ class RenderBuffers:
             n = 2 if k == "n_shaded" else (1 if k == "error" else (4 * self.n_chunks if k == "stat4" else self.n_chunks))
             self.counters[k] = torch.zeros(n, dtype=torch.float32 if k == "stat4" else torch.int32, device=dev)
             setattr(self.c_counters, k, self.counters[k].data_ptr())
-        nbytes = _lib.lib().nmf_workspace_bytes_scaled(scene.ref(), n_rays, chunk, self.cap_scale)
+        if train:     # one forward call per batch (chunk = n_rays) + the train-mode distance rows
+            nbytes = _lib.lib().nmf_render_train_workspace_bytes(scene.ref(), n_rays, self.cap_scale)
+            self.whole_valid = torch.zeros(n_rays, dtype=torch.uint8, device=dev)
+            self.n_kept = torch.zeros(2, dtype=torch.int32, device=dev)
+        else:
+            nbytes = _lib.lib().nmf_workspace_bytes_scaled(scene.ref(), n_rays, chunk, self.cap_scale)
         if nbytes == 0:
             raise _lib.NmfError("nmf_workspace_bytes: bad arguments")
         self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
@@ -218,6 +224,43 @@ def render_rays(scene, rays, focal, chunk=4096, seed=0, ray_id0=0, skip_eps=DEFA
             if buffers.cap_scale >= 16:
                 raise
             buffers = RenderBuffers(scene, max(n, buffers.n_rays), chunk, buffers.keys, cap_scale=buffers.cap_scale * 2)
+
+
+TRAIN_KEYS = ["rgb_map", "acc_map"]
+
+
+def render_rays_train(scene, rays, focal, seed=0, ray_id0=0, max_samples=-1, min_rough=0.0, skip_eps=0.0, t_cut=0.0,
+                      buffers=None):
+    """TensorNeRF.forward(is_train=True, draw_debug=False) of the microfacet model for ONE ray batch
+    (nmf_render_rays_train; forward only).  Returns (images, stats): images = rgb_map / acc_map rows of the kept rays,
+    stats = dict(whole_valid (n) bool, n_kept, n_samples=[M0, M1], statistics=A19 dict, counters...)."""
+    r = _f32(rays[:, :6], scene.device)
+    n = r.shape[0]
+    if n == 0:
+        raise _lib.NmfError("render_rays_train: empty ray batch")
+    if buffers is None or not getattr(buffers, "train", False) or buffers.n_rays != n:
+        buffers = RenderBuffers(scene, n, n, TRAIN_KEYS, cap_scale=2.0, train=True)
+    while True:
+        rp = _lib.NmfRender(n_rays=n, chunk=n, focal=float(focal), seed=int(seed), ray_id0=int(ray_id0),
+                            skip_eps=float(skip_eps), t_cut=float(t_cut), white_bg=1, cap_scale=buffers.cap_scale)
+        tr = _lib.NmfRenderTrain(max_samples=int(max_samples), min_rough=float(min_rough),
+                                 whole_valid=buffers.whole_valid.data_ptr(), n_kept=buffers.n_kept.data_ptr())
+        st = _lib.lib().nmf_render_rays_train(scene.ref(), C.byref(rp), C.byref(tr), _p(r), C.byref(buffers.c_images),
+                                              C.byref(buffers.c_counters), C.c_void_p(buffers.ws_ptr), buffers.ws_bytes,
+                                              _stream())
+        _lib.check(st, "nmf_render_rays_train")
+        try:
+            stats = read_counters(buffers, n, n)
+        except _lib.NmfOverflow:
+            if buffers.cap_scale >= 32:
+                raise
+            buffers = RenderBuffers(scene, n, n, TRAIN_KEYS, cap_scale=buffers.cap_scale * 2, train=True)
+            continue
+        kept, m0 = buffers.n_kept.tolist()
+        stats.update(buffers=buffers, whole_valid=buffers.whole_valid[:n].bool(), n_kept=kept,
+                     n_samples=stats["n_samples"][0], statistics=stats["statistics"][0])
+        assert stats["n_samples"][0] == m0, "kept-sample count of the truncation and of the march disagree"
+        return {k: v[:kept] for k, v in buffers.images.items()}, stats
 
 
 def read_counters(buffers, n, chunk):

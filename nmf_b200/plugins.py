@@ -15,8 +15,9 @@ by the sm_100a kernels behind the C ABI (nmf_b200/ops.py).  Reference classes mi
     IntegralEquirect      modules/integral_equirect.py:176-504
     SRGBTonemap           modules/tonemap.py:38-49
 
-Scope: eval-mode forward (the hot path of BASELINE.json).  Training (`is_train=True`: jittered steps, dynamic batch
-truncation, losses, backward) is a "next" row of SURVEY section 8f and raises NotImplementedError here.
+Scope: eval-mode forward (the hot path of BASELINE.json); the training FORWARD (`is_train=True`: jittered steps,
+dynamic batch truncation, A19 statistics) for both models; forward + backward (`TensorNeRF.train_step`) for
+model=tensorf.  The microfacet backward is not built: `train_step` raises for it.
 """
 import math
 
@@ -363,7 +364,8 @@ class Microfacet(nn.Module):
                  max_brdf_rays=(650000, 450000), max_retrace_rays=(1000,), target_num_samples=(1000000,),
                  percent_bright=0.0, min_rough_start=0.0, min_rough_decay=0.999, conserve_energy=True,
                  russian_roulette=False, start_std=0.0, std_decay=1.0, cold_start_bg_iters=0, detach_N_iters=0,
-                 no_emitters=True, diffuse_mixing_mode="fresnel", freeze=False, visibility_module=None, **kwargs):
+                 no_emitters=True, diffuse_mixing_mode="fresnel", freeze=False, visibility_module=None,
+                 std_decay_interval=10, **kwargs):
         super().__init__()
         if diffuse_mixing_mode != "fresnel" or not no_emitters or visibility_module is not None or russian_roulette or percent_bright:
             raise _lib.NmfError("Microfacet: kernels implement diffuse_mixing_mode=fresnel, no_emitters, no visibility module")
@@ -373,6 +375,10 @@ class Microfacet(nn.Module):
         self.anoise, self.rays_per_ray, self.test_rays_per_ray = anoise, rays_per_ray, test_rays_per_ray
         self.max_brdf_rays, self.max_retrace_rays = list(max_brdf_rays), list(max_retrace_rays)
         self.target_num_samples = list(target_num_samples)
+        # training schedule state (models/microfacet.py:53-58, 70-71)
+        self.min_rough, self.min_rough_decay = min_rough_start, min_rough_decay
+        self.std, self.std_decay, self.std_decay_interval = start_std, std_decay, std_decay_interval
+        self.detach_N_iters, self.detach_N = detach_N_iters, True
         self.outputs = {"diffuse": 3, "roughness": 1, "tint": 3, "spec": 3}
         self.needs_normals = lambda recur: True
 
@@ -384,6 +390,13 @@ class Microfacet(nn.Module):
                     tint_bias=d.tint_bias, f0_bias=0.0, brdf_bias=b.bias)
 
     def check_schedule(self, iter, batch_mul, **kw):
+        """models/microfacet.py:112-121"""
+        if iter % 10 == 0:
+            self.min_rough *= self.min_rough_decay
+        if iter > batch_mul * self.detach_N_iters:
+            self.detach_N = False
+        if iter % self.std_decay_interval == 0:
+            self.std *= self.std_decay
         return False
 
     def get_optparam_groups(self, lr_scale=1):
@@ -498,6 +511,7 @@ class TensorNeRF(nn.Module):
         self.skip_eps, self.t_cut, self.seed, self.mlp = ops.DEFAULT_SKIP_EPS, ops.DEFAULT_T_CUT, 20211200, "f16"
         self._scene, self._scene_key, self._bufs, self._calls = None, None, None, 0
         self._train_bufs = None
+        self._render_train_bufs = None
 
     def get_device(self):
         return self.rf.units.device
@@ -537,8 +551,11 @@ class TensorNeRF(nn.Module):
     def render_chunks(self, rays, focal, chunk=4096, ray_id0=0, is_train=False, ndc_ray=False, N_samples=-1, **kw):
         """All chunks of `rays` in one asynchronous launch sequence (the B200-first replacement of the per-chunk host
         loop of renderer.py:72-104).  Returns (images, statistics) with the keys of TensorNeRF.forward."""
-        if is_train or ndc_ray:
-            raise NotImplementedError("TensorNeRF: only the eval, non-NDC render path is implemented (SURVEY 8f)")
+        if ndc_ray:
+            raise NotImplementedError("TensorNeRF: only the non-NDC render path is implemented")
+        if is_train:
+            raise NotImplementedError("TensorNeRF.render_chunks is the eval driver; the training forward is one batch per "
+                                      "call: TensorNeRF.forward(is_train=True)")
         sc = self.scene()
         n = rays.shape[0]
         if self._bufs is not None and (self._bufs.n_rays < n or self._bufs.chunk != chunk):
@@ -585,11 +602,36 @@ class TensorNeRF(nn.Module):
         images = dict(rgb_map=out["rgb_map"][:out["n_rays"]], acc_map=out["acc_map"][:out["n_rays"]])
         return out["loss_photo"] + lambda_pred * stats["prediction_loss"], images, stats
 
+    @torch.no_grad()
+    def forward_train(self, rays, focal, ray_id0=None):
+        """TensorNeRF.forward(is_train=True, draw_debug=False) (modules/tensor_nerf.py:210-674) of the microfacet model
+        for one ray batch, through nmf_render_rays_train: jittered steps (also in the re-traced rays), the dynamic batch
+        truncation (statistics["whole_valid"], rows of the kept rays only), min_rough, the A19 regulariser inputs.
+        Forward only -- no autograd graph is built and the microfacet backward kernels do not exist yet."""
+        sc = self.scene()
+        if sc.hp["model"] != "microfacet":
+            raise NotImplementedError("forward_train: model=tensorf trains through TensorNeRF.train_step")
+        if self.model.std != 0:
+            raise NotImplementedError("Microfacet.std != 0 (material-head noise, render_modules.py:556-558) is not built")
+        if self.model.rays_per_ray != self.model.test_rays_per_ray:
+            raise NotImplementedError("rays_per_ray != test_rays_per_ray")
+        n = rays.shape[0]
+        ims, st = ops.render_rays_train(sc, rays.to(self.get_device()), focal, seed=self.seed,
+                                        ray_id0=self._calls * n if ray_id0 is None else ray_id0,
+                                        max_samples=self.sampler.max_samples, min_rough=self.model.min_rough,
+                                        buffers=self._render_train_bufs)
+        self._render_train_bufs = st["buffers"]
+        self._calls += 1
+        stats = dict(recur=0, whole_valid=st["whole_valid"].to(rays.device), n_samples=list(st["n_samples"]),
+                     n_retrace=st["n_retrace"][0], envmap_reg=self._envmap_reg())
+        stats.update(st["statistics"])
+        return ims, stats
+
     def _envmap_reg(self):
         """modules/tensor_nerf.py:606-610: (bg_module.mean_color().mean() - 0.05).clip(min=0)"""
         if self.bg_module is None or not hasattr(self.bg_module, "mean_color"):
             return 0.0
-        return float((self.bg_module.mean_color().mean() - 0.05).clip(min=0))
+        return float((self.bg_module.mean_color().detach().mean() - 0.05).clip(min=0))
 
     @torch.no_grad()
     def forward(self, rays, focal, start_mipval=None, bg_col=None, stepmul=1, recur=0, override_near=None, output_alpha=None,
@@ -598,6 +640,10 @@ class TensorNeRF(nn.Module):
         """modules/tensor_nerf.py:210-674 for one chunk in eval mode (recur=0: the recursion runs on the device)."""
         if recur != 0 or start_mipval is not None or override_near is not None or not tonemap:
             raise NotImplementedError("TensorNeRF.forward: secondary-ray renders are issued by the kernels themselves")
+        if is_train:
+            if ndc_ray:
+                raise NotImplementedError("TensorNeRF: only the non-NDC render path is implemented")
+            return self.forward_train(rays, focal)
         ims, stats = self.render_chunks(rays, focal, chunk=rays.shape[0], ray_id0=self._calls * rays.shape[0],
                                         is_train=is_train, ndc_ray=ndc_ray)
         self._calls += 1

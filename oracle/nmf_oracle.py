@@ -756,7 +756,8 @@ def render_chunk(sc, rays, focal, rng, ray_keys=None, recur=0, start_mip=None, o
         if retrace:
             im, st = render_chunk(sc, brays, focal, rng, keys, recur + 1, mip.reshape(-1),
                                   3 * sc.stepsize, white_bg=False, tonemap=False, draw_debug=False,
-                                  is_train=is_train, detach_N=detach_N, max_samples=max_samples)   # tensor_nerf.py:291-317
+                                  is_train=is_train, detach_N=detach_N, max_samples=-1)   # tensor_nerf.py:291-317
+            # (dynamic_batch_size=False in the recursion, tensor_nerf.py:299: re-traced rays are never truncated)
             n_samples.extend(st["n_samples"])
             return im["rgb_map"]
         return env_lookup(sc, brays[..., 3:6], mip.reshape(-1), rng)

@@ -80,7 +80,7 @@ def test_sampler_plugin_train_mode(env):
 
 
 @pytest.mark.parametrize("name,n,max_samples", [("plain_g64", 256, -1), ("plain_g64", 256, 6000), ("plain_g64", 1000, -1),
-                                                ("microfacet_noncubic", 300, -1), ("microfacet_g40", 300, 5000)])
+                                                ("microfacet_noncubic", 256, -1), ("microfacet_g40", 300, 5000)])
 def test_train_plain_matches_oracle_gradients(env, name, n, max_samples):
     """nmf_train_plain: loss, images, whole_valid and the gradient of EVERY parameter against the oracle's autograd
     (plain_g64: the model=tensorf fixture; the microfacet fixtures' fields -- non-cubic grid, density in all three
@@ -271,3 +271,79 @@ def test_upsample_schedule(env):
     assert 95 <= res[0] <= 96 and t.rf.grid_size.tolist() == res
     assert tuple(t.rf.app_rf.app_plane[0].shape) == (1, 24, res[1], res[0])
     assert tuple(t.rf.density_rf.app_line[0].shape) == (1, 16, res[2], 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# microfacet model: the training FORWARD through the fused render kernels (nmf_render_rays_train)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n,frac,min_rough", [("microfacet_g40", 384, None, 0.0), ("microfacet_g40", 384, 0.5, 0.2),
+                                                   ("microfacet_noncubic", 256, None, 0.0),
+                                                   ("microfacet_g56_ship", 256, 0.6, 0.05)])
+def test_microfacet_train_forward_matches_oracle(env, name, n, frac, min_rough):
+    """TensorNeRF.forward(is_train=True, draw_debug=False) of the microfacet model: jittered steps at recur 0 and in the
+    re-traced rays, dynamic batch truncation at recur 0 only, min_rough, A19 statistics -- against the oracle's
+    training forward (pinned to the unmodified reference by oracle/check_train.py) on the same keyed random numbers.
+    whole_valid / kept counts / primary sample count: bit-exact; maps and statistics: tolerances of the eval tests."""
+    from nmf_b200 import ops
+    from oracle import keyed_rng as KR
+    from oracle import nmf_oracle as O
+    from test_gpu_parity import FLOAT_TOL, compare_images
+    fix = load_fixture(name)
+    osc, dsc = oracle_scene(fix, min_rough=min_rough), device_scene(fix, env)
+    rays = fix["rays"][:n].contiguous()
+    seed, id0 = 13, 2000
+    keys = KR.primary_ray_keys(seed, np.arange(id0, id0 + n))
+    _, valid, _, _, _ = O.sample_rays(osc, rays, fix["focal"], None, True, KR.KeyedRNG(), keys, -1)
+    ms = -1 if frac is None else int(int(valid.sum()) * frac)
+    ref, rst = O.render_chunk(osc, rays, fix["focal"], KR.KeyedRNG(), keys, draw_debug=False, is_train=True, max_samples=ms)
+    ims, st = ops.render_rays_train(dsc, rays.cuda(), fix["focal"], seed=seed, ray_id0=id0, max_samples=ms,
+                                    min_rough=min_rough)
+    assert torch.equal(st["whole_valid"].cpu(), rst["whole_valid"])
+    kept = int(rst["whole_valid"].sum())
+    assert st["n_kept"] == kept and (frac is None or 0 < kept < n)
+    assert st["n_samples"][0] == rst["n_samples"][0]
+    m1 = rst["n_samples"][1] if len(rst["n_samples"]) > 1 else 0
+    assert abs(st["n_samples"][1] - m1) <= max(8, 0.002 * m1), (st["n_samples"], rst["n_samples"])
+    assert ims["rgb_map"].shape == (kept, 3) and ims["acc_map"].shape == (kept,)
+    report, bad = compare_images(ims, ref, {k: FLOAT_TOL[k] for k in ("rgb_map", "acc_map")})
+    print(report)
+    assert not bad, bad
+    for k in ("ori_loss", "diffuse_reg", "brdf_reg", "prediction_loss"):
+        a, b = st["statistics"][k], float(rst[k])
+        assert abs(a - b) <= 2e-3 * max(abs(b), 1e-3), (k, a, b)
+    # the jitter is keyed: the same call again gives the same truncation and the same geometry, another seed does not
+    ims2, st2 = ops.render_rays_train(dsc, rays.cuda(), fix["focal"], seed=seed, ray_id0=id0, max_samples=ms,
+                                      min_rough=min_rough)
+    assert torch.equal(ims2["acc_map"], ims["acc_map"]) and st2["n_samples"][0] == st["n_samples"][0]
+    _, st3 = ops.render_rays_train(dsc, rays.cuda(), fix["focal"], seed=seed + 1, ray_id0=id0, max_samples=-1)
+    assert st3["n_samples"][0] != st["n_samples"][0] or frac is not None
+
+
+def test_microfacet_train_forward_plugin(env):
+    """TensorNeRF.forward(is_train=True) of the plugin mirror: kept rows, statistics keys of tensor_nerf.py:567-649,
+    and the eval forward of the same module is untouched by it."""
+    from nmf_b200 import config
+    fix = load_fixture("microfacet_g40")
+    G = fix["grid_size"]
+    t, _ = config.build_model([f"field.grid_size=[{G},{G},{G}]", "model.arch.bg_module.bg_resolution=32"],
+                              aabb=fix["aabb"], near_far=list(fix["near_far"]))
+    t.load_state_dict(fix["state"], strict=False)
+    t = t.cuda().eval()
+    t.sampler.update(t.rf, init=True)
+    t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
+    rays = fix["rays"][:256].cuda()
+    ev, _ = t(rays, fix["focal"])
+    ev = ev["rgb_map"].clone()
+    t.sampler.max_samples = 4000
+    ims, st = t(rays, fix["focal"], is_train=True, draw_debug=False)
+    kept = int(st["whole_valid"].sum())
+    assert 0 < kept < 256 and ims["rgb_map"].shape == (kept, 3)
+    assert st["n_samples"][0] < 4000 and len(st["n_samples"]) == 2
+    for k in ("ori_loss", "diffuse_reg", "brdf_reg", "prediction_loss", "envmap_reg"):
+        assert np.isfinite(st[k])
+    assert abs(st["prediction_loss"] - 2 * float(ims["acc_map"].sum())) < 1e-3 * max(1.0, st["prediction_loss"])
+    t._calls = 0
+    ev2, _ = t(rays, fix["focal"])
+    assert torch.allclose(ev2["rgb_map"], ev, atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        t.train_step(rays, torch.zeros(256, 3).cuda())
