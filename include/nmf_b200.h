@@ -337,6 +337,27 @@ int nmf_render_rays_train(const NmfScene* scene, const NmfRender* rp, const NmfR
                           const NmfImages* out, const NmfCounters* counters, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* ---- optimiser step on the device (the update half of train.py:497-813) ----
+ * All three stream their tensors once; `sum_abs` / `sq_norm` are device fp64 accumulators the caller zeroes. */
+
+/* TensorVMSplit.density_L1 (fields/tensoRF.py:332-340) for one factor: sum_abs += sum |param|, and when grad != NULL
+ * grad += coef * sign(param) with coef = L1_reg_weight / numel (train.py:675-678: the mean over the factor). */
+int nmf_l1_reg(const float* param, size_t n, float coef, float* grad, double* sum_abs, void* stream);
+/* sq_norm += sum grad^2 in fp64: the total norm torch.nn.utils.clip_grad_norm_ (train.py:752-753) needs */
+int nmf_grad_sq_norm(const float* grad, size_t n, double* sq_norm, void* stream);
+/* One torch.optim.Adam update (train.py:443-457, 754; amsgrad off, L2 weight_decay) of one parameter segment, fused
+ * with the loss normalisation and the gradient clipping: g = grad * grad_scale * min(1, max_norm / (grad_scale *
+ * sqrt(*sq_norm) + 1e-6)).  sq_norm (device) may be NULL (no clipping); step >= 1 is the update count of this
+ * optimiser instance (bias correction); lr already includes the LambdaLR factor (train.py:458-466). */
+typedef struct NmfAdam {
+  float lr, beta1, beta2, eps, weight_decay;
+  int step;
+  float grad_scale;        /* 1 / lbatch_size (train.py:709) */
+  float max_norm;          /* params.clip_grad; <= 0: off */
+} NmfAdam;
+int nmf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const NmfAdam* adam,
+                  const double* sq_norm, void* stream);
+
 /* Resolution schedule (fields/tensor_base.py:234-243 -> fields/tensoRF.py:208-227, 408-413): TensoRF.upsample is
  * F.interpolate(mode="bilinear", align_corners=True) of every factor.  src (C,H,W) -> dst (C,H2,W2), both in the
  * reference's own parameter layout (a line (1,C,N,1) is H = N, W = 1). */

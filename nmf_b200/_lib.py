@@ -68,6 +68,11 @@ class NmfTrainOut(C.Structure):
                 ("n_kept", C.c_void_p), ("error", C.c_void_p)]
 
 
+class NmfAdam(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("step", C.c_int), ("grad_scale", C.c_float), ("max_norm", C.c_float)]
+
+
 class NmfRenderTrain(C.Structure):
     _fields_ = [("max_samples", C.c_int), ("min_rough", C.c_float), ("whole_valid", C.c_void_p), ("n_kept", C.c_void_p)]
 
@@ -148,6 +153,9 @@ def lib():
         "nmf_sample_rays_train": (I, [SP, P, I, F, C.c_uint64, C.c_uint64, P, I, P, P, P, P, P, P]),
         "nmf_train_workspace_bytes": (C.c_size_t, [SP, I, I]),
         "nmf_upsample_bilinear": (I, [P, I, I, I, P, I, I, P]),
+        "nmf_l1_reg": (I, [P, C.c_size_t, F, P, P, P]),
+        "nmf_grad_sq_norm": (I, [P, C.c_size_t, P, P]),
+        "nmf_adam_step": (I, [P, P, P, P, C.c_size_t, C.POINTER(NmfAdam), P, P]),
         "nmf_render_train_workspace_bytes": (C.c_size_t, [SP, I, F]),
         "nmf_render_rays_train": (I, [SP, RP, C.POINTER(NmfRenderTrain), P, IP, CP, P, C.c_size_t, P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
@@ -166,4 +174,4 @@ EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_pr
             "nmf_vm_density", "nmf_vm_appfeature", "nmf_vm_normals", "nmf_env_lookup", "nmf_ggx_sample",
             "nmf_brdf_mlp", "nmf_material_heads", "nmf_dense_alpha", "nmf_generate_rays", "nmf_image_sq_error",
             "nmf_sample_rays_train", "nmf_train_workspace_bytes", "nmf_train_plain", "nmf_upsample_bilinear",
-            "nmf_render_train_workspace_bytes", "nmf_render_rays_train"]
+            "nmf_render_train_workspace_bytes", "nmf_render_rays_train", "nmf_l1_reg", "nmf_grad_sq_norm", "nmf_adam_step"]

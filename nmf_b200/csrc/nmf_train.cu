@@ -624,3 +624,105 @@ extern "C" int nmf_upsample_bilinear(const float* src, int C, int H, int W, floa
   CKL();
   return NMF_OK;
 }
+
+
+// ================================================================================================
+// optimiser step on the device (train.py:443-467 Adam + LambdaLR, :675-678 density L1, :752-754 clip + step)
+// ================================================================================================
+// Every kernel streams its tensors once (grid-stride, 16-byte accesses when the segment is aligned): HBM-bound.
+__global__ void __launch_bounds__(256) k_l1_reg(const float* __restrict__ p, size_t n, float coef, float* __restrict__ g,
+                                                double* sum_abs) {
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = p[i];
+    acc += (double)fabsf(v);
+    if (g) g[i] += nmf_l1_grad(v, coef);
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && sum_abs) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += part[i];
+    atomicAdd(sum_abs, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sq_norm(const float* __restrict__ g, size_t n, double* out) {
+  double acc = 0.0;
+  const size_t n4 = ((uintptr_t)g & 15) == 0 ? n / 4 : 0;
+  const float4* g4 = (const float4*)g;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = g4[i];
+    acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    acc += (double)g[i] * g[i];
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += part[i];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, size_t n, const NmfAdamScalars h, const double* sq_norm) {
+  const float gmul = h.grad_scale * (sq_norm ? nmf_clip_coef(*sq_norm, h.grad_scale, h.max_norm) : 1.0f);
+  const bool al = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+  const size_t n4 = al ? n / 4 : 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 P = ((float4*)p)[i], M = ((float4*)m)[i], V = ((float4*)v)[i];
+    const float4 G = ((const float4*)g)[i];
+    nmf_adam_elem(&P.x, G.x, &M.x, &V.x, h, gmul);
+    nmf_adam_elem(&P.y, G.y, &M.y, &V.y, h, gmul);
+    nmf_adam_elem(&P.z, G.z, &M.z, &V.z, h, gmul);
+    nmf_adam_elem(&P.w, G.w, &M.w, &V.w, h, gmul);
+    ((float4*)p)[i] = P; ((float4*)m)[i] = M; ((float4*)v)[i] = V;
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    nmf_adam_elem(p + i, g[i], m + i, v + i, h, gmul);
+}
+
+static int stream_grid(size_t n, int per_thread) {
+  const size_t blocks = (n + (size_t)256 * per_thread - 1) / ((size_t)256 * per_thread);
+  const size_t cap = (size_t)t_sm_count() * 8;          // one resident wave of 256-thread CTAs
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+extern "C" int nmf_l1_reg(const float* param, size_t n, float coef, float* grad, double* sum_abs, void* stream) {
+  if (!param || n == 0) return NMF_E_ARG;
+  k_l1_reg<<<stream_grid(n, 4), 256, 0, (cudaStream_t)stream>>>(param, n, coef, grad, sum_abs);
+  CKL();
+  return NMF_OK;
+}
+
+extern "C" int nmf_grad_sq_norm(const float* grad, size_t n, double* sq_norm, void* stream) {
+  if (!grad || !sq_norm || n == 0) return NMF_E_ARG;
+  k_sq_norm<<<stream_grid(n, 8), 256, 0, (cudaStream_t)stream>>>(grad, n, sq_norm);
+  CKL();
+  return NMF_OK;
+}
+
+extern "C" int nmf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const NmfAdam* a,
+                             const double* sq_norm, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !a || n == 0 || a->step < 1) return NMF_E_ARG;
+  NmfAdamScalars h;
+  const double b1 = a->beta1, b2 = a->beta2;
+  h.one_minus_b1 = (float)(1.0 - b1);
+  h.b2 = (float)b2;
+  h.one_minus_b2 = (float)(1.0 - b2);
+  h.eps = a->eps;
+  h.weight_decay = a->weight_decay;
+  h.step_size = (float)((double)a->lr / (1.0 - pow(b1, (double)a->step)));
+  h.bc2_sqrt = (float)sqrt(1.0 - pow(b2, (double)a->step));
+  h.grad_scale = a->grad_scale;
+  h.max_norm = a->max_norm;
+  k_adam<<<stream_grid(n, 8), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, h, sq_norm);
+  CKL();
+  return NMF_OK;
+}

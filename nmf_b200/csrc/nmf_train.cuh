@@ -158,6 +158,38 @@ NMF_HD float nmf_resize_pixel(const float* plane, int W, int y0, int y1, float h
   return NMF_ADD(NMF_MUL(hy0, top), NMF_MUL(hy1, bot));
 }
 
+// ---- optimiser step (train.py:443-467, 675-678, 752-754) ----
+// Hyper-parameters of one fused update, prepared on the host in double like torch does for its Python scalars.
+struct NmfAdamScalars {
+  float one_minus_b1, b2, one_minus_b2, eps, weight_decay;
+  float step_size;         // lr / (1 - beta1^t)
+  float bc2_sqrt;          // sqrt(1 - beta2^t)
+  float grad_scale;        // 1 / lbatch_size (train.py:709: total_loss / lbatch_size)
+  float max_norm;          // params.clip_grad (<= 0: no clipping)
+};
+// torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (total_norm + 1e-6)); the norm is of the SCALED gradient
+NMF_HD float nmf_clip_coef(double sq_norm, float grad_scale, float max_norm) {
+  if (!(max_norm > 0.f)) return 1.0f;
+  const float total = grad_scale * (float)sqrt(sq_norm);
+  const float c = max_norm / (total + 1e-6f);
+  return c < 1.0f ? c : 1.0f;
+}
+// torch.optim.Adam, one element (torch/optim/adam.py _single_tensor_adam, amsgrad=False): L2 weight decay added to the
+// gradient, exp_avg.lerp_(g, 1 - b1), exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2),
+// denom = sqrt(exp_avg_sq) / sqrt(bias_correction2) + eps, param.addcdiv_(exp_avg, denom, -step_size)
+NMF_HD void nmf_adam_elem(float* p, float g, float* m, float* v, const NmfAdamScalars& h, float gmul) {
+  g = NMF_MUL(g, gmul);
+  if (h.weight_decay != 0.f) g = NMF_ADD(g, NMF_MUL(h.weight_decay, *p));
+  const float m1 = NMF_ADD(*m, NMF_MUL(NMF_SUB(g, *m), h.one_minus_b1));
+  const float v1 = NMF_ADD(NMF_MUL(*v, h.b2), NMF_MUL(h.one_minus_b2, NMF_MUL(g, g)));
+  const float denom = NMF_ADD(sqrtf(v1) / h.bc2_sqrt, h.eps);
+  *p = NMF_SUB(*p, NMF_MUL(h.step_size, m1 / denom));
+  *m = m1;
+  *v = v1;
+}
+// d/dp of weight * mean|p| (TensorVMSplit.density_L1, fields/tensoRF.py:332-340): coef = weight / numel
+NMF_HD float nmf_l1_grad(float p, float coef) { return p > 0.f ? coef : (p < 0.f ? -coef : 0.f); }
+
 #ifdef __CUDACC__
 // One warp writes the jittered distances of a ray: z_k = tmin + fp32(sum_{j<=k} step_j).  Every partial sum of <= 2048
 // fp32 step lengths in [stepsize/2, 3 stepsize/2] is exact in fp64 (37 significant bits), so the scan order does not

@@ -3,13 +3,17 @@
 ``train_plain`` runs ONE fused forward + backward on the device (``nmf_train_plain``: hand-written CUDA for every stage,
 no autograd) and returns the loss terms and the gradient of every parameter under its reference state_dict key and in
 the reference's layout, so that the reference's optimiser loop (train.py:497-813: Adam over ``get_optparam_groups``)
-can consume it unchanged.  ``PlainTrainer`` is that loop for this model: ray batches, the step, ``torch.optim.Adam``
-(plumbing), re-packing of the updated factors, and -- when ``torch.distributed`` is initialised -- the single flat
-gradient all-reduce of ray-sharded training (distributed.FlatGradBucket).
+can consume it unchanged.  ``PlainTrainer`` is that loop for this model: ``fit`` mirrors train.py:497-813 (ray-id
+sampler, adaptive batch controller with gradient accumulation, density L1, gradient clipping, Adam + LambdaLR decay,
+the resolution / occupancy schedule with optimiser re-creation); the update itself is ``FusedAdam`` -- clip + weight
+decay + Adam in one pass over each parameter (``nmf_adam_step``), no torch.optim -- followed by the in-place re-packing
+of the updated factors, and -- when ``torch.distributed`` is initialised -- the single flat gradient all-reduce of
+ray-sharded training (distributed.FlatGradBucket).
 
 There is no CPU / PyTorch fallback: the step raises when libnmf_b200.so is missing or the tensors are not on a GPU.
 """
 import ctypes as C
+import math
 
 import torch
 
@@ -143,6 +147,102 @@ def train_plain(scene, rays, gt, focal=1.0, seed=0, ray_id0=0, ray_ids=None, max
         return out
 
 
+# configs/model/tensorf.yaml:69-111 (`params:`), the values train.py reads for model=tensorf
+REFERENCE_PARAMS = dict(L1_weight_initial=8e-5, clip_grad=10.0, weight_decay=1e-6, eps=1e-15, betas=(0.9, 0.99),
+                        starting_batch_size=100, min_batch_size=4096, max_batch_size=32000, target_num_samples=400000,
+                        n_iters=30000, batch_size=4096, lr_init=1.0, lr_final=1e-3, lr_delay_mult=0.1, lr_delay_steps=100)
+
+
+def learning_rate_decay(step, lr_init=1.0, lr_final=1e-3, max_steps=30000, lr_delay_steps=0, lr_delay_mult=1.0, **_):
+    """utils.learning_rate_decay / log_lerp (utils.py:318-359): the LambdaLR factor of train.py:458-466."""
+    if lr_delay_steps > 0:
+        delay = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0.0), 1.0))
+    else:
+        delay = 1.0
+    t = min(max(step / max_steps, 0.0), 1.0)
+    return delay * math.exp(t * (math.log(lr_final) - math.log(lr_init)) + math.log(lr_init))
+
+
+class FusedAdam:
+    """torch.optim.Adam + lr_scheduler.LambdaLR + clip_grad_norm_ as the reference composes them (train.py:443-467,
+    752-755), as device updates: one nmf_grad_sq_norm over the flat gradient buffer, then one nmf_adam_step per parameter
+    that applies loss normalisation, clip coefficient, L2 weight decay and the Adam update in a single pass (the clip
+    coefficient is read from device memory: no host synchronisation).  `groups`: [{"params": [...], "lr": base_lr}]."""
+
+    def __init__(self, groups, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0, clip_grad=None, lr_lambda=None, flat_grad=None):
+        self.groups = [dict(params=list(g["params"]), lr=float(g["lr"])) for g in groups]
+        self.betas, self.eps, self.weight_decay = (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        self.clip_grad = float(clip_grad) if clip_grad is not None and clip_grad > 0 else 0.0
+        self.lr_lambda, self.flat_grad = lr_lambda, flat_grad
+        self.state = {}
+        ps = [p for g in self.groups for p in g["params"]]
+        if not ps:
+            raise ValueError("FusedAdam: no parameters")
+        for p in ps:
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.NmfError("FusedAdam takes contiguous fp32 CUDA parameters (there is no CPU path)")
+            self.state[id(p)] = (torch.zeros_like(p), torch.zeros_like(p))       # exp_avg, exp_avg_sq
+        self.device = ps[0].device
+        self.sq_norm = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.t = 0            # updates done by this instance = scheduler epoch (both restart when it is re-created)
+
+    def lr_factor(self):
+        return float(self.lr_lambda(self.t)) if self.lr_lambda is not None else 1.0
+
+    def step(self, grad_scale=1.0):
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            st = _stream()
+            clip = self.clip_grad > 0
+            if clip:
+                self.sq_norm.zero_()
+                if self.flat_grad is not None:
+                    _lib.check(L.nmf_grad_sq_norm(_p(self.flat_grad), self.flat_grad.numel(), _p(self.sq_norm), st), "nmf_grad_sq_norm")
+                else:
+                    for g in self.groups:
+                        for p in g["params"]:
+                            if p.grad is not None:
+                                _lib.check(L.nmf_grad_sq_norm(_p(p.grad), p.numel(), _p(self.sq_norm), st), "nmf_grad_sq_norm")
+            lam = self.lr_factor()                      # LambdaLR: update k (1-based) runs at base_lr * lambda(k - 1)
+            self.t += 1
+            for g in self.groups:
+                a = _lib.NmfAdam(lr=g["lr"] * lam, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                                 weight_decay=self.weight_decay, step=self.t, grad_scale=float(grad_scale),
+                                 max_norm=self.clip_grad)
+                for p in g["params"]:
+                    if p.grad is None:
+                        continue
+                    m, v = self.state[id(p)]
+                    _lib.check(L.nmf_adam_step(_p(p.data), _p(p.grad), _p(m), _p(v), p.numel(), C.byref(a),
+                                               _p(self.sq_norm) if clip else None, st), "nmf_adam_step")
+
+
+def l1_reg(param, weight, grad=None, sum_abs=None):
+    """weight * mean|param| (one term of TensorVMSplit.density_L1, fields/tensoRF.py:332-340): accumulates the value's
+    numerator into `sum_abs` (fp64 device scalar) and d/dparam into `grad`."""
+    with torch.cuda.device(param.device):
+        _lib.check(_lib.lib().nmf_l1_reg(_p(param), param.numel(), float(weight) / param.numel(), _p(grad), _p(sum_abs), _stream()),
+                   "nmf_l1_reg")
+
+
+class RayIdSampler:
+    """train.SimpleSampler (train.py:36-51): epochs of a device-side random permutation of the ray ids."""
+
+    def __init__(self, total, batch, device, seed=0):
+        self.total, self.batch, self.curr, self.ids = total, batch, total, None
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(seed)
+        self.device = device
+
+    def nextids(self, batch=None):
+        batch = self.batch if batch is None else batch
+        self.curr += batch
+        if self.curr + batch > self.total or self.ids is None:
+            self.ids = torch.randperm(self.total, dtype=torch.long, device=self.device, generator=self.gen)
+            self.curr = 0
+        return self.ids[self.curr:self.curr + batch]
+
+
 class PlainTrainer:
     """The optimiser loop of train.py:497-813 for model=tensorf: parameters are kept in the reference's layout and under
     the reference's state_dict keys (a checkpoint loads / saves unchanged), every step is one nmf_train_plain call, the
@@ -151,7 +251,9 @@ class PlainTrainer:
     ONE all-reduce over a flat bucket before the update."""
 
     def __init__(self, state, aabb, near_far, grid_size, alpha_volume=None, device="cuda", lr_grid=2e-2, lr_net=1e-3,
-                 max_samples=-1, lambda_pred=0.0, seed=0, **hp):
+                 max_samples=-1, lambda_pred=0.0, seed=0, params=None, **hp):
+        """params: the `params:` block of the model config (REFERENCE_PARAMS = configs/model/tensorf.yaml); None keeps
+        a bare Adam (torch defaults, no L1 / clipping / decay), which is what the gradient tests want."""
         from .distributed import FlatGradBucket
         from .scene import DeviceScene
         self.device = torch.device(device)
@@ -162,7 +264,11 @@ class PlainTrainer:
         self.lr_grid, self.lr_net = lr_grid, lr_net
         self._FlatGradBucket = FlatGradBucket
         self.max_samples, self.lambda_pred, self.seed = max_samples, lambda_pred, seed
+        self.hparams = None if params is None else dict(REFERENCE_PARAMS, **params)
+        self.l1_weight = 0.0 if params is None else float(self.hparams["L1_weight_initial"])
+        self.l1_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.iteration = 0
+        self._calls = 0
         self.buffers = None
         self._DeviceScene = DeviceScene
         self._make_optimizer()
@@ -171,14 +277,22 @@ class PlainTrainer:
     def _make_optimizer(self):
         grid = [self.params[k] for k in PLAIN_PARAM_KEYS if k.startswith("rf.") and "basis" not in k]
         net = [self.params[k] for k in PLAIN_PARAM_KEYS if not (k.startswith("rf.") and "basis" not in k)]
-        self.optimizer = torch.optim.Adam([dict(params=grid, lr=self.lr_grid), dict(params=net, lr=self.lr_net)],
-                                          betas=(0.9, 0.99))
         self.bucket = self._FlatGradBucket(list(self.params.values()))
+        groups = [dict(params=grid, lr=self.lr_grid), dict(params=net, lr=self.lr_net)]
+        if self.hparams is None:
+            self.optimizer = FusedAdam(groups, betas=(0.9, 0.99), flat_grad=self.bucket.flat)
+        else:
+            h = self.hparams
+            lam = lambda step: learning_rate_decay(step, max_steps=h["n_iters"], **h)      # train.py:458-466
+            self.optimizer = FusedAdam(groups, betas=h["betas"], eps=h["eps"], weight_decay=h["weight_decay"],
+                                       clip_grad=h["clip_grad"], lr_lambda=lam, flat_grad=self.bucket.flat)
 
-    def upsample(self, grid_size):
+    def upsample(self, grid_size, rebuild_occupancy=True):
         """Resolution schedule (fields/tensor_base.py:234-243, fields/tensoRF.py:208-227, 408-413; train.py:806-809): the
-        factors are resampled on the device (nmf_upsample_bilinear), the occupancy grid is rebuilt at the new resolution
-        (samplers/alphagrid.py:249-276) and the optimiser is re-created, as the reference does when check_schedule fires."""
+        factors are resampled on the device (nmf_upsample_bilinear) and the optimiser is re-created, as the reference does
+        when check_schedule fires.  rebuild_occupancy=True also rebuilds the occupancy grid at the new resolution
+        (samplers/alphagrid.py:249-276); the reference loop does that on its own schedule (`update_list`), so `fit`
+        passes False and keeps the current volume."""
         from . import ops
         res = [int(g) for g in grid_size]
         mat, vec = [[0, 1], [0, 2], [1, 2]], [2, 1, 0]
@@ -193,11 +307,13 @@ class PlainTrainer:
                 new[k] = torch.nn.Parameter(p.data.clone())
         self.params = new
         self.meta["grid_size"] = res
-        self.alpha_volume = None
+        if rebuild_occupancy:
+            self.alpha_volume = None
         self.buffers = None
         self._make_optimizer()
         self.repack()
-        self.alpha_volume = self.scene.update_alpha_mask(res)
+        if rebuild_occupancy:
+            self.alpha_volume = self.scene.update_alpha_mask(res)
 
     def repack(self, rebuild=True):
         """rebuild=True: a new DeviceScene (construction, resolution change); False: the updated parameters are packed
@@ -211,25 +327,105 @@ class PlainTrainer:
         else:
             self.scene.refresh_plain(st)
 
-    def step(self, rays, gt, ray_ids=None):
-        """One iteration on this rank's rays (train.py:540-760 without the regularisers that model=tensorf turns off)."""
+    def accumulate(self, rays, gt, ray_ids=None, first=True):
+        """Forward + backward of one ray sub-batch (the body of the `while num_remaining > 0` loop, train.py:509-712):
+        gradients are SUMS over rays, added into the flat bucket (first=True overwrites = optimizer.zero_grad), plus the
+        density L1 term the reference adds to every sub-batch's loss (train.py:675-678)."""
         import torch.distributed as dist
-        out = train_plain(self.scene, rays, gt, seed=self.seed + self.iteration, ray_ids=ray_ids,
+        out = train_plain(self.scene, rays, gt, seed=self.seed + self._calls, ray_ids=ray_ids,
                           max_samples=self.max_samples, lambda_pred=self.lambda_pred, buffers=self.buffers)
+        self._calls += 1
         self.buffers = out["buffers"]
         grads = out["grads"].reference_layout()
-        tot = torch.tensor([float(out["n_rays"]), out["loss_photo"]], device=self.device, dtype=torch.float64)
-        for k, p in self.params.items():
-            p.grad.copy_(grads[k])                            # p.grad is a view into the flat bucket
+        for k, p in self.params.items():                      # p.grad is a view into the flat bucket
+            if first:
+                p.grad.copy_(grads[k])
+            else:
+                p.grad.add_(grads[k])
+        if self.l1_weight > 0:
+            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            self.l1_sum.zero_()
+            for k, p in self.params.items():
+                if ".density_rf." in k:                       # every rank adds its share: the all-reduce sums them
+                    l1_reg(p.data, self.l1_weight / world, p.grad, self.l1_sum)
+        return out
+
+    def apply(self, n_rays_local, loss_local=0.0, normaliser=None):
+        """clip_grad_norm_ + optimizer.step() + scheduler.step() (train.py:752-755) on the accumulated gradients, after
+        the ONE flat all-reduce of ray-sharded training; the loss normaliser 1 / lbatch_size (train.py:709) is applied
+        inside the fused update.  normaliser=None: the global number of kept rays."""
+        import torch.distributed as dist
+        tot = torch.tensor([float(n_rays_local), float(loss_local)], device=self.device, dtype=torch.float64)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(tot)                              # global ray count = the loss normaliser
-        # one flat fp32 all-reduce (NCCL on GPUs), scaled by 1 / lbatch_size (train.py:709)
-        self.bucket.allreduce(scale=1.0 / max(float(tot[0]), 1.0))
-        self.optimizer.step()
+        self.bucket.allreduce(scale=1.0)                      # one flat fp32 all-reduce (NCCL on GPUs)
+        norm = float(tot[0]) if normaliser is None else float(normaliser)
+        self.optimizer.step(grad_scale=1.0 / max(norm, 1.0))
         self.repack(rebuild=False)
         self.iteration += 1
-        out["mse"] = float(tot[1]) / max(3.0 * float(tot[0]), 1.0)
+        return float(tot[0]), float(tot[1])
+
+    def step(self, rays, gt, ray_ids=None):
+        """One iteration on this rank's rays: one sub-batch, normalised by the global number of kept rays."""
+        out = self.accumulate(rays, gt, ray_ids=ray_ids, first=True)
+        n, loss = self.apply(out["n_rays"], out["loss_photo"])
+        out["mse"] = loss / max(3.0 * n, 1.0)
         return out
+
+    def check_schedule(self, iteration, upsamp_list=(), n_voxel_list=(), update_list=()):
+        """TensorNeRF.check_schedule (modules/tensor_nerf.py:177-195) for this model: the sampler's occupancy update
+        first (samplers/alphagrid.py:91-94, at the field's CURRENT resolution), then the field's upsampling
+        (fields/tensor_base.py:234-243).  True = the optimiser (and its LambdaLR) was re-created (train.py:806-809)."""
+        from .plugins import _n_to_reso
+        if iteration in update_list:
+            self.alpha_volume = self.scene.update_alpha_mask(self.meta["grid_size"])
+        if iteration in upsamp_list:
+            aabb = torch.as_tensor(self.meta["aabb"]).float().cpu()
+            self.upsample(_n_to_reso(n_voxel_list[list(upsamp_list).index(iteration)], aabb), rebuild_occupancy=False)
+            return True
+        return False
+
+    def fit(self, allrays, allrgbs, n_iters=None, upsamp_list=(), n_voxel_list=(), update_list=(), callback=None):
+        """The optimiser loop of train.py:497-813 for model=tensorf on device-resident rays (N,6) / colours (N,3|4):
+        per iteration, sub-batches of `num_rays` rays are accumulated until `lbatch_size` rays were seen; `num_rays`
+        follows the valid-sample count (train.py:616-626: target_num_samples per sub-batch); the gradients are
+        normalised by lbatch_size, clipped and applied; schedule events re-create the optimiser and reset the controller.
+        Needs `params` (REFERENCE_PARAMS).  Returns the per-iteration history."""
+        if self.hparams is None:
+            raise _lib.NmfError("PlainTrainer.fit needs the `params` block (train.REFERENCE_PARAMS)")
+        h = self.hparams
+        n_iters = h["n_iters"] if n_iters is None else n_iters
+        allrays, allrgbs = allrays.to(self.device), allrgbs.to(self.device)
+        sampler = RayIdSampler(allrays.shape[0], h["batch_size"], self.device, seed=self.seed)
+        num_rays, prev = h["starting_batch_size"], None
+        history = []
+        for it in range(n_iters):
+            lbatch = min(h["min_batch_size"] if num_rays < h["min_batch_size"] else num_rays, h["max_batch_size"])
+            remaining, first, kept, loss, samples, subs = lbatch, True, 0, 0.0, 0, 0
+            while remaining > 0:
+                ln = min(num_rays, remaining)
+                remaining -= ln
+                ids = sampler.nextids(ln)
+                rgba = allrgbs[ids]
+                if rgba.shape[-1] == 4:                      # train.py:527-531, bg_col = white
+                    rgba = rgba[:, :3] * rgba[:, 3:] + (1 - rgba[:, 3:])
+                out = self.accumulate(allrays[ids], rgba, ray_ids=ids, first=first)
+                first = False
+                kept, loss, samples, subs = kept + out["n_rays"], loss + out["loss_photo"], samples + out["n_samples"], subs + 1
+                ratio = out["n_rays"] / max(out["n_samples"], 1)                       # train.py:616-626
+                prev = ratio if prev is None else min(0.1 * ratio + 0.9 * prev, ratio)
+                num_rays = int(prev * h["target_num_samples"] + 1)
+            self.apply(kept, loss, normaliser=lbatch)
+            rec = dict(iteration=it, lbatch_size=lbatch, sub_batches=subs, kept_rays=kept, n_samples=samples,
+                       mse=loss / max(3.0 * kept, 1.0), next_num_rays=num_rays, lr_factor=self.optimizer.lr_factor(),
+                       grid=list(self.meta["grid_size"]))
+            if self.check_schedule(it, upsamp_list, n_voxel_list, update_list):
+                num_rays, prev = h["starting_batch_size"], None                         # train.py:810-812
+                rec["reinit"] = True
+            history.append(rec)
+            if callback is not None:
+                callback(rec)
+        return history
 
 
 def benchmark_plain(grid=300, n_rays=4096, steps=20, iters=60, device="cuda:0"):

@@ -269,6 +269,26 @@ void hc_train_plain(const NmfScene* s, const NmfTrain* tp, const float* rays, co
   }
 }
 
+// optimiser step (nmf_adam_step / nmf_l1_reg on the host)
+void hc_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps, float wd, int step,
+             float grad_scale, float max_norm) {
+  NmfAdamScalars h;
+  h.one_minus_b1 = (float)(1.0 - (double)b1); h.b2 = b2; h.one_minus_b2 = (float)(1.0 - (double)b2); h.eps = eps;
+  h.weight_decay = wd;
+  h.step_size = (float)((double)lr / (1.0 - pow((double)b1, (double)step)));
+  h.bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)step));
+  h.grad_scale = grad_scale; h.max_norm = max_norm;
+  double sq = 0.0;
+  for (int i = 0; i < n; ++i) sq += (double)g[i] * g[i];
+  const float gmul = grad_scale * nmf_clip_coef(sq, grad_scale, max_norm);
+  for (int i = 0; i < n; ++i) nmf_adam_elem(p + i, g[i], m + i, v + i, h, gmul);
+}
+double hc_l1(const float* p, int n, float coef, float* g) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) { s += fabs((double)p[i]); g[i] += nmf_l1_grad(p[i], coef); }
+  return s;
+}
+
 void hc_upsample(const float* src, int C, int H, int W, float* dst, int H2, int W2) {
   for (int c = 0; c < C; ++c)
     for (int y = 0; y < H2; ++y)

@@ -347,3 +347,133 @@ def test_microfacet_train_forward_plugin(env):
     assert torch.allclose(ev2["rgb_map"], ev, atol=1e-5)
     with pytest.raises(NotImplementedError):
         t.train_step(rays, torch.zeros(256, 3).cuda())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the optimiser loop of train.py:443-467, 497-813 on the device
+# ---------------------------------------------------------------------------------------------------------------
+def test_fused_adam_matches_torch_optim(env):
+    """FusedAdam (nmf_grad_sq_norm + nmf_adam_step: loss normalisation, clip_grad_norm_, L2 weight decay, Adam, LambdaLR
+    in one pass per parameter) against torch.optim.Adam + lr_scheduler.LambdaLR + clip_grad_norm_ on the same gradients;
+    odd sizes exercise the unaligned tails."""
+    from nmf_b200 import train
+    from nmf_b200.distributed import FlatGradBucket
+    g = torch.Generator().manual_seed(0)
+    shapes = [(1, 16, 37, 41), (1, 16, 37, 1), (3,), (127, 5), (1000003,)]
+    mine = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in mine]
+    lam = lambda step: train.learning_rate_decay(step, max_steps=50, **train.REFERENCE_PARAMS)
+    bucket = FlatGradBucket(mine)
+    opt = train.FusedAdam([dict(params=mine[:2], lr=2e-2), dict(params=mine[2:], lr=1e-3)], betas=(0.9, 0.99), eps=1e-15,
+                          weight_decay=1e-6, clip_grad=10.0, lr_lambda=lam, flat_grad=bucket.flat)
+    topt = torch.optim.Adam([dict(params=ref[:2], lr=2e-2), dict(params=ref[2:], lr=1e-3)], betas=(0.9, 0.99), eps=1e-15,
+                            weight_decay=1e-6)
+    sched = torch.optim.lr_scheduler.LambdaLR(topt, lam)
+    scale = 1.0 / 4096
+    for step in range(6):
+        mag = 3000.0 if step % 2 == 0 else 1.0            # clipped / not clipped
+        for p, r in zip(mine, ref):
+            gr = (torch.randn(p.shape, generator=g) * mag).cuda()
+            p.grad.copy_(gr)
+            r.grad = gr * scale
+        torch.nn.utils.clip_grad_norm_(ref, 10.0)
+        topt.step()
+        sched.step()
+        opt.step(grad_scale=scale)
+        for p, r in zip(mine, ref):
+            assert torch.allclose(p.detach(), r.detach(), rtol=2e-5, atol=2e-7), (step, p.shape, (p - r).abs().max())
+    # without a flat buffer / clipping / schedule: plain Adam with torch's defaults
+    a = torch.nn.Parameter(torch.randn(999, generator=g).cuda())
+    b = torch.nn.Parameter(a.detach().clone())
+    o1, o2 = train.FusedAdam([dict(params=[a], lr=1e-3)]), torch.optim.Adam([b], lr=1e-3, betas=(0.9, 0.99))
+    for _ in range(3):
+        a.grad = torch.randn(999, generator=g).cuda()
+        b.grad = a.grad.clone()
+        o1.step()
+        o2.step()
+    assert torch.allclose(a.detach(), b.detach(), rtol=2e-5, atol=2e-7)
+    with pytest.raises(Exception):
+        train.FusedAdam([dict(params=[torch.nn.Parameter(torch.zeros(3))], lr=1e-3)])     # CPU tensors: no fallback
+
+
+def test_l1_reg_kernel(env):
+    from nmf_b200 import train
+    g = torch.Generator().manual_seed(1)
+    p = torch.randn(1, 16, 33, 29, generator=g).cuda()
+    p.view(-1)[::7] = 0.0
+    q = p.clone().requires_grad_(True)
+    (8e-5 * q.abs().mean()).backward()
+    grad = torch.zeros_like(p)
+    total = torch.zeros(1, dtype=torch.float64, device="cuda")
+    train.l1_reg(p, 8e-5, grad, total)
+    train.l1_reg(p, 8e-5, grad, total)
+    assert torch.allclose(grad, 2 * q.grad, rtol=1e-6, atol=1e-14)
+    assert abs(float(total) - 2 * float(p.double().abs().sum())) < 1e-9 * float(total)
+
+
+def test_fit_loop_matches_the_reference_loop_on_the_oracle(env):
+    """PlainTrainer.fit (train.py:497-813: ray-id sampler, adaptive batch controller with gradient accumulation, density
+    L1, 1/lbatch_size, clip_grad_norm_, Adam(weight_decay, eps) + LambdaLR) against the same loop written with the oracle's
+    autograd and torch.optim on the CPU.  The controller's decisions (sub-batch sizes, kept rays, sample counts) are
+    integer work and must be identical; parameters agree to the tolerance below (Adam's update is ~ lr * sign(g) in the
+    first steps, so an element whose gradient is rounding noise around zero may move the other way: a quantile is
+    bounded, not the maximum)."""
+    from nmf_b200 import train
+    from conftest import grid_of
+    from test_hostmath import oracle_train_plain
+    fix = load_fixture("plain_g64")
+    hp = dict(starting_batch_size=48, min_batch_size=160, max_batch_size=256, target_num_samples=2500, batch_size=64,
+              n_iters=4)
+    n_iters, seed, ms = 4, 17, 3000
+    allrays = fix["rays"][:1024].contiguous()
+    allrgbs = torch.rand(allrays.shape[0], 3, generator=torch.Generator().manual_seed(2))
+    tr = train.PlainTrainer(fix["state"], fix["aabb"], fix["near_far"], grid_of(fix), alpha_volume=fix["alpha_volume"],
+                            device=env, max_samples=ms, seed=seed, params=hp)
+    hist = tr.fit(allrays, allrgbs, n_iters=n_iters)
+    assert any(h["sub_batches"] > 1 for h in hist) and all(h["kept_rays"] <= h["lbatch_size"] for h in hist)
+
+    # ---- the same loop on the CPU: oracle forward + autograd, torch.optim.Adam, LambdaLR, clip_grad_norm_ ----
+    H = dict(train.REFERENCE_PARAMS, **hp)
+    state = {k: v.clone() for k, v in fix["state"].items()}
+    params = {k: torch.nn.Parameter(state[k].float().clone()) for k in train.PLAIN_PARAM_KEYS}
+    grid = [params[k] for k in train.PLAIN_PARAM_KEYS if k.startswith("rf.") and "basis" not in k]
+    net = [params[k] for k in train.PLAIN_PARAM_KEYS if not (k.startswith("rf.") and "basis" not in k)]
+    opt = torch.optim.Adam([dict(params=grid, lr=2e-2), dict(params=net, lr=1e-3)], betas=H["betas"], eps=H["eps"],
+                           weight_decay=H["weight_decay"])
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: train.learning_rate_decay(s, max_steps=H["n_iters"], **H))
+    sampler = train.RayIdSampler(allrays.shape[0], H["batch_size"], env, seed=seed)
+    num_rays, prev, calls = H["starting_batch_size"], None, 0
+    for it in range(n_iters):
+        opt.zero_grad(set_to_none=True)
+        lbatch = min(H["min_batch_size"] if num_rays < H["min_batch_size"] else num_rays, H["max_batch_size"])
+        remaining, kept, samples, subs = lbatch, 0, 0, 0
+        while remaining > 0:
+            ln = min(num_rays, remaining)
+            remaining -= ln
+            ids = sampler.nextids(ln).cpu()
+            cur = dict(fix, state=dict(state, **{k: p.detach().clone() for k, p in params.items()}))
+            ref = oracle_train_plain(cur, allrays[ids], allrgbs[ids], seed + calls, ids.numpy().astype(np.uint64), ms, 0.0)
+            calls += 1
+            for k, p in params.items():
+                gk = ref["grads"][k].reshape(p.shape).clone()
+                if ".density_rf." in k:
+                    gk += H["L1_weight_initial"] * torch.sign(p.detach()) / p.numel()
+                p.grad = gk / lbatch if p.grad is None else p.grad + gk / lbatch
+            nk = int(ref["whole"].sum())
+            kept, samples, subs = kept + nk, samples + ref["n_samples"], subs + 1
+            ratio = nk / max(ref["n_samples"], 1)
+            prev = ratio if prev is None else min(0.1 * ratio + 0.9 * prev, ratio)
+            num_rays = int(prev * H["target_num_samples"] + 1)
+        torch.nn.utils.clip_grad_norm_(list(params.values()), H["clip_grad"])
+        opt.step()
+        sched.step()
+        h = hist[it]
+        assert (h["lbatch_size"], h["sub_batches"], h["kept_rays"], h["n_samples"], h["next_num_rays"]) == \
+            (lbatch, subs, kept, samples, num_rays), (it, h)
+    n_moved = 0
+    for k, p in params.items():
+        d = (tr.params[k].detach().cpu() - p.detach()).abs().reshape(-1)
+        n_moved += int(float((p.detach() - state[k].float()).abs().max()) > 0)   # all-zero factors with zero gradient stay put
+        q = float(d.quantile(0.999)) if d.numel() < 10_000_000 else float(d.max())
+        assert q <= 2e-4 and float(d.mean()) <= 2e-5, (k, q, float(d.mean()), float(d.max()))
+    assert n_moved >= 12

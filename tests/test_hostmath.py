@@ -283,3 +283,59 @@ def test_upsample_matches_interpolate(hostcheck, shape, size):
     out = torch.zeros(shape[0], *size)
     hostcheck.hc_upsample(ptr(src), shape[0], shape[1], shape[2], ptr(out), size[0], size[1])
     assert float((out - ref).abs().max()) <= 4e-7 * float(src.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# optimiser step (nmf_adam_step / nmf_l1_reg per-element math on the host) against torch's own implementations
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wd,eps,clip,scale", [(0.0, 1e-8, 0.0, 1.0), (1e-6, 1e-15, 10.0, 1.0 / 4096), (1e-2, 1e-15, 0.5, 1.0)])
+def test_adam_host_matches_torch(hostcheck, wd, eps, clip, scale):
+    """train.py:443-467, 752-755: clip_grad_norm_ + Adam(weight_decay) over several updates with a changing learning rate"""
+    g = torch.Generator().manual_seed(3)
+    n = 5003
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=0.02, betas=(0.9, 0.99), eps=eps, weight_decay=wd)
+    p, m, v = p0.clone(), torch.zeros(n), torch.zeros(n)
+    for step in range(1, 8):
+        grad = torch.randn(n, generator=g) * (50.0 if step % 2 else 1e-3) / scale
+        lr = 0.02 * (0.5 + 0.1 * step)
+        ref.grad = grad * scale
+        if clip > 0:
+            torch.nn.utils.clip_grad_norm_([ref], clip)
+        for gr in opt.param_groups:
+            gr["lr"] = lr
+        opt.step()
+        hostcheck.hc_adam(ptr(p), ptr(grad), ptr(m), ptr(v), n, C.c_float(lr), C.c_float(0.9), C.c_float(0.99), C.c_float(eps),
+                          C.c_float(wd), step, C.c_float(scale), C.c_float(clip))
+        assert torch.allclose(p, ref.detach(), rtol=2e-6, atol=2e-7), (step, (p - ref.detach()).abs().max())
+    st = opt.state[ref]
+    assert torch.allclose(m, st["exp_avg"], rtol=1e-5, atol=1e-6 * float(m.abs().max()))
+    assert torch.allclose(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-6 * float(v.abs().max()))
+
+
+def test_l1_host_matches_autograd(hostcheck):
+    """fields/tensoRF.py:332-340 density_L1 term: weight * mean|p| and its gradient"""
+    g = torch.Generator().manual_seed(4)
+    p = torch.randn(1, 16, 9, 7, generator=g)
+    p.view(-1)[::5] = 0.0
+    q = p.clone().requires_grad_(True)
+    (8e-5 * q.abs().mean()).backward()
+    grad = torch.zeros_like(p)
+    hostcheck.hc_l1.restype = C.c_double
+    s = hostcheck.hc_l1(ptr(p), p.numel(), C.c_float(8e-5 / p.numel()), ptr(grad))
+    assert abs(s - float(p.abs().sum())) < 1e-6 * float(p.abs().sum())
+    assert torch.allclose(grad, q.grad, rtol=1e-6, atol=1e-14)
+    hostcheck.hc_l1(ptr(p), p.numel(), C.c_float(8e-5 / p.numel()), ptr(grad))        # accumulates
+    assert torch.allclose(grad, 2 * q.grad, rtol=1e-6, atol=1e-14)
+
+
+def test_learning_rate_decay_is_the_reference_formula():
+    """utils.py:318-359 (log_lerp with the reverse-cosine delay), configs/model/tensorf.yaml:108-111"""
+    from nmf_b200 import train
+    for step in (0, 1, 50, 100, 101, 15000, 30000, 40000):
+        delay = 0.1 + 0.9 * np.sin(0.5 * np.pi * np.clip(step / 100, 0, 1))
+        want = delay * np.exp(np.clip(step / 30000, 0, 1) * (np.log(1e-3) - np.log(1.0)) + np.log(1.0))
+        got = train.learning_rate_decay(step, max_steps=30000, **train.REFERENCE_PARAMS)
+        assert abs(got - want) < 1e-12
+    assert train.learning_rate_decay(7, lr_init=2.0, lr_final=2.0, max_steps=10) == pytest.approx(2.0)
