@@ -174,20 +174,43 @@ class FusedAdam:
         self.betas, self.eps, self.weight_decay = (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.clip_grad = float(clip_grad) if clip_grad is not None and clip_grad > 0 else 0.0
         self.lr_lambda, self.flat_grad = lr_lambda, flat_grad
-        self.state = {}
         ps = [p for g in self.groups for p in g["params"]]
         if not ps:
             raise ValueError("FusedAdam: no parameters")
         for p in ps:
             if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                 raise _lib.NmfError("FusedAdam takes contiguous fp32 CUDA parameters (there is no CPU path)")
-            self.state[id(p)] = (torch.zeros_like(p), torch.zeros_like(p))       # exp_avg, exp_avg_sq
         self.device = ps[0].device
+        # Parameters (and their gradients) that sit back to back in memory -- views of one flat buffer, as PlainTrainer
+        # allocates them -- are updated by ONE launch per run: the step is launch-bound otherwise (19 small tensors).
+        self.state = {}                                   # id(param) -> (exp_avg, exp_avg_sq) views
+        for g in self.groups:
+            runs = []
+            for p in g["params"]:
+                last = runs[-1][-1] if runs else None
+                if (last is not None and p.grad is not None and last.grad is not None
+                        and p.data_ptr() == last.data_ptr() + 4 * last.numel()
+                        and p.grad.data_ptr() == last.grad.data_ptr() + 4 * last.numel()):
+                    runs[-1].append(p)
+                else:
+                    runs.append([p])
+            g["runs"] = []
+            for run in runs:
+                n = sum(q.numel() for q in run)
+                m, v = torch.zeros(n, device=self.device), torch.zeros(n, device=self.device)
+                off = 0
+                for q in run:
+                    self.state[id(q)] = (m[off:off + q.numel()].view_as(q), v[off:off + q.numel()].view_as(q))
+                    off += q.numel()
+                g["runs"].append((run, n, m, v))
         self.sq_norm = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.t = 0            # updates done by this instance = scheduler epoch (both restart when it is re-created)
 
     def lr_factor(self):
         return float(self.lr_lambda(self.t)) if self.lr_lambda is not None else 1.0
+
+    def n_launches(self):
+        return sum(len(g["runs"]) for g in self.groups) + (1 if self.clip_grad > 0 else 0)
 
     def step(self, grad_scale=1.0):
         L = _lib.lib()
@@ -209,11 +232,10 @@ class FusedAdam:
                 a = _lib.NmfAdam(lr=g["lr"] * lam, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
                                  weight_decay=self.weight_decay, step=self.t, grad_scale=float(grad_scale),
                                  max_norm=self.clip_grad)
-                for p in g["params"]:
-                    if p.grad is None:
+                for run, n, m, v in g["runs"]:
+                    if run[0].grad is None:
                         continue
-                    m, v = self.state[id(p)]
-                    _lib.check(L.nmf_adam_step(_p(p.data), _p(p.grad), _p(m), _p(v), p.numel(), C.byref(a),
+                    _lib.check(L.nmf_adam_step(_p(run[0].data), _p(run[0].grad), _p(m), _p(v), n, C.byref(a),
                                                _p(self.sq_norm) if clip else None, st), "nmf_adam_step")
 
 
@@ -260,7 +282,7 @@ class PlainTrainer:
         self.meta = dict(aabb=aabb, near_far=near_far, grid_size=grid_size, hp=dict(hp, model="plain"))
         self.alpha_volume = alpha_volume
         self.state = {k: torch.as_tensor(v).detach().clone().to(self.device) for k, v in state.items()}
-        self.params = {k: torch.nn.Parameter(self.state[k].float()) for k in PLAIN_PARAM_KEYS}
+        self.params = self._flat_params({k: self.state[k].float() for k in PLAIN_PARAM_KEYS})
         self.lr_grid, self.lr_net = lr_grid, lr_net
         self._FlatGradBucket = FlatGradBucket
         self.max_samples, self.lambda_pred, self.seed = max_samples, lambda_pred, seed
@@ -274,10 +296,29 @@ class PlainTrainer:
         self._make_optimizer()
         self.repack()
 
+    @staticmethod
+    def _is_grid(k):
+        return k.startswith("rf.") and "basis" not in k
+
+    def _flat_params(self, tensors):
+        """Every parameter is a view of ONE flat fp32 buffer, the factor (grid) group first, then the network group --
+        the same order as the flat gradient bucket, so that an optimiser group is one contiguous segment."""
+        order = [k for k in PLAIN_PARAM_KEYS if self._is_grid(k)] + [k for k in PLAIN_PARAM_KEYS if not self._is_grid(k)]
+        flat = torch.empty(sum(tensors[k].numel() for k in order), dtype=torch.float32, device=self.device)
+        out, off = {}, 0
+        for k in order:
+            t = tensors[k]
+            view = flat[off:off + t.numel()].view(t.shape)
+            view.copy_(t)
+            out[k] = torch.nn.Parameter(view)
+            off += t.numel()
+        self.flat_params = flat
+        return out
+
     def _make_optimizer(self):
-        grid = [self.params[k] for k in PLAIN_PARAM_KEYS if k.startswith("rf.") and "basis" not in k]
-        net = [self.params[k] for k in PLAIN_PARAM_KEYS if not (k.startswith("rf.") and "basis" not in k)]
-        self.bucket = self._FlatGradBucket(list(self.params.values()))
+        grid = [p for k, p in self.params.items() if self._is_grid(k)]
+        net = [p for k, p in self.params.items() if not self._is_grid(k)]
+        self.bucket = self._FlatGradBucket(grid + net)
         groups = [dict(params=grid, lr=self.lr_grid), dict(params=net, lr=self.lr_net)]
         if self.hparams is None:
             self.optimizer = FusedAdam(groups, betas=(0.9, 0.99), flat_grad=self.bucket.flat)
@@ -300,12 +341,12 @@ class PlainTrainer:
         for k, p in self.params.items():
             if ".app_plane." in k:
                 i = int(k[-1])
-                new[k] = torch.nn.Parameter(ops.upsample_bilinear(p.data, (res[mat[i][1]], res[mat[i][0]])))
+                new[k] = ops.upsample_bilinear(p.data, (res[mat[i][1]], res[mat[i][0]]))
             elif ".app_line." in k:
-                new[k] = torch.nn.Parameter(ops.upsample_bilinear(p.data, (res[vec[int(k[-1])]], 1)))
+                new[k] = ops.upsample_bilinear(p.data, (res[vec[int(k[-1])]], 1))
             else:
-                new[k] = torch.nn.Parameter(p.data.clone())
-        self.params = new
+                new[k] = p.data
+        self.params = self._flat_params(new)
         self.meta["grid_size"] = res
         if rebuild_occupancy:
             self.alpha_volume = None
@@ -475,4 +516,80 @@ def benchmark_plain(grid=300, n_rays=4096, steps=20, iters=60, device="cuda:0"):
         torch.cuda.synchronize(dev)
         res.update(loop_iters=iters, loop_ms_per_iter=(time.perf_counter() - t0) / max(iters - 3, 1) * 1e3,
                    loop_mse_first=mse[0], loop_mse_last=mse[-1])
+        res["optimizer"] = benchmark_optimizer(tr, steps)
     return res
+
+
+def benchmark_optimizer(tr, steps=20):
+    """The update half of an iteration at the trainer's resolution, CUDA-event timed: FusedAdam with the reference's
+    settings (clip_grad_norm_ + weight decay + Adam: one norm pass over the flat gradient + one pass per parameter)
+    next to torch.optim.Adam + clip_grad_norm_ on copies of the same tensors.  HBM-bound: algorithmic bytes per
+    parameter element = 4 (norm) + 16 read + 12 written (p, g, m, v -> p, m, v)."""
+    dev = tr.device
+    from .distributed import FlatGradBucket
+    flat = tr.flat_params.clone()                # same layout as the trainer: views of one flat buffer, groups contiguous
+    ps, off = [], 0
+    for p in tr.params.values():
+        ps.append(torch.nn.Parameter(flat[off:off + p.numel()].view(p.shape)))
+        off += p.numel()
+    bucket = FlatGradBucket(ps)
+    bucket.flat.normal_(generator=None)
+    h = REFERENCE_PARAMS
+    opt = FusedAdam([dict(params=ps, lr=2e-2)], betas=h["betas"], eps=h["eps"], weight_decay=h["weight_decay"],
+                    clip_grad=h["clip_grad"], flat_grad=bucket.flat)
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    for r, p in zip(ref, ps):
+        r.grad = p.grad.detach().clone()
+    topt = torch.optim.Adam(ref, lr=2e-2, betas=h["betas"], eps=h["eps"], weight_decay=h["weight_decay"])
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / max(steps, 1)
+
+    def torch_step():
+        torch.nn.utils.clip_grad_norm_(ref, h["clip_grad"])
+        topt.step()
+
+    n = bucket.flat.numel()
+    ms = timed(lambda: opt.step(grad_scale=1.0 / 4096))
+    ms_torch = timed(torch_step)
+    return dict(n_params=n, fused_ms=ms, fused_launches=opt.n_launches(), torch_ms=ms_torch, algorithmic_bytes=32 * n,
+                fused_GBps=32 * n / ms / 1e6)
+
+
+def benchmark_microfacet_forward(grid=300, n_rays=4096, steps=20, device="cuda:0"):
+    """Times nmf_render_rays_train (TensorNeRF.forward(is_train=True) of microfacet_tensorf2: jittered steps, dynamic
+    batch truncation at max_samples = 200000, one retrace level) for one training batch of the synthetic lego scene."""
+    from . import ops, synthetic
+    from .scene import DeviceScene
+    dev = torch.device(device)
+    state, meta = synthetic.make_scene("lego", grid_size=grid)
+    sc = DeviceScene(state, meta["aabb"], meta["near_far"], meta["grid_size"], device=dev, model="microfacet")
+    sc.update_alpha_mask()
+    H = W = 800
+    focal = synthetic.focal_for(W)
+    pose = synthetic.hemisphere_poses(4)[1]
+    pix = torch.randperm(H * W, generator=torch.Generator().manual_seed(0))[:n_rays]
+    rays = synthetic.camera_rays(pose, H, W, focal)[pix].contiguous().to(dev)
+    ims, st = ops.render_rays_train(sc, rays, focal, seed=1, max_samples=200000)
+    bufs = st["buffers"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for i in range(steps):
+        ops.render_rays_train(sc, rays, focal, seed=2 + i, max_samples=200000, buffers=bufs)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / max(steps, 1)
+    return dict(what="nmf_render_rays_train: microfacet training forward (SURVEY 8f row 1, forward half)", grid=grid, rays=n_rays,
+                kept_rays=st["n_kept"], n_samples=st["n_samples"], n_retrace=st["n_retrace"][0],
+                n_bounce_rays=[st["n_bounce_rays0"][0], st["n_bounce_rays1"][0]], ms_per_step=ms,
+                kept_rays_per_s=st["n_kept"] / ms * 1e3, note="includes the counter read-back (one host sync per step)")

@@ -360,7 +360,33 @@ def test_fused_adam_matches_torch_optim(env):
     from nmf_b200.distributed import FlatGradBucket
     g = torch.Generator().manual_seed(0)
     shapes = [(1, 16, 37, 41), (1, 16, 37, 1), (3,), (127, 5), (1000003,)]
-    mine = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    _fused_adam_case(shapes, g, flat=False)
+    _fused_adam_case(shapes, g, flat=True)
+    # without a flat buffer / clipping / schedule: plain Adam with torch's defaults
+    a = torch.nn.Parameter(torch.randn(999, generator=g).cuda())
+    b = torch.nn.Parameter(a.detach().clone())
+    o1, o2 = train.FusedAdam([dict(params=[a], lr=1e-3)]), torch.optim.Adam([b], lr=1e-3, betas=(0.9, 0.99))
+    for _ in range(3):
+        a.grad = torch.randn(999, generator=g).cuda()
+        b.grad = a.grad.clone()
+        o1.step()
+        o2.step()
+    assert torch.allclose(a.detach(), b.detach(), rtol=2e-5, atol=2e-7)
+    with pytest.raises(Exception):
+        train.FusedAdam([dict(params=[torch.nn.Parameter(torch.zeros(3))], lr=1e-3)])     # CPU tensors: no fallback
+
+
+def _fused_adam_case(shapes, g, flat):
+    """flat=True: the parameters are views of one buffer (PlainTrainer's layout): one launch per optimiser group"""
+    from nmf_b200 import train
+    from nmf_b200.distributed import FlatGradBucket
+    vals = [torch.randn(s, generator=g).cuda() for s in shapes]
+    if flat:
+        buf = torch.cat([v.reshape(-1) for v in vals])
+        offs = np.cumsum([0] + [v.numel() for v in vals])
+        mine = [torch.nn.Parameter(buf[offs[i]:offs[i + 1]].view(shapes[i])) for i in range(len(shapes))]
+    else:
+        mine = [torch.nn.Parameter(v) for v in vals]
     ref = [torch.nn.Parameter(p.detach().clone()) for p in mine]
     lam = lambda step: train.learning_rate_decay(step, max_steps=50, **train.REFERENCE_PARAMS)
     bucket = FlatGradBucket(mine)
@@ -382,18 +408,9 @@ def test_fused_adam_matches_torch_optim(env):
         opt.step(grad_scale=scale)
         for p, r in zip(mine, ref):
             assert torch.allclose(p.detach(), r.detach(), rtol=2e-5, atol=2e-7), (step, p.shape, (p - r).abs().max())
-    # without a flat buffer / clipping / schedule: plain Adam with torch's defaults
-    a = torch.nn.Parameter(torch.randn(999, generator=g).cuda())
-    b = torch.nn.Parameter(a.detach().clone())
-    o1, o2 = train.FusedAdam([dict(params=[a], lr=1e-3)]), torch.optim.Adam([b], lr=1e-3, betas=(0.9, 0.99))
-    for _ in range(3):
-        a.grad = torch.randn(999, generator=g).cuda()
-        b.grad = a.grad.clone()
-        o1.step()
-        o2.step()
-    assert torch.allclose(a.detach(), b.detach(), rtol=2e-5, atol=2e-7)
-    with pytest.raises(Exception):
-        train.FusedAdam([dict(params=[torch.nn.Parameter(torch.zeros(3))], lr=1e-3)])     # CPU tensors: no fallback
+    assert opt.n_launches() == (3 if flat else 1 + len(shapes))
+    st = topt.state[ref[0]]
+    assert torch.allclose(opt.state[id(mine[0])][0], st["exp_avg"], rtol=1e-4, atol=1e-6 * float(st["exp_avg"].abs().max()))
 
 
 def test_l1_reg_kernel(env):
@@ -477,3 +494,30 @@ def test_fit_loop_matches_the_reference_loop_on_the_oracle(env):
         q = float(d.quantile(0.999)) if d.numel() < 10_000_000 else float(d.max())
         assert q <= 2e-4 and float(d.mean()) <= 2e-5, (k, q, float(d.mean()), float(d.max()))
     assert n_moved >= 12
+
+
+def test_fit_schedule_events(env):
+    """TensorNeRF.check_schedule inside the loop (modules/tensor_nerf.py:177-195, train.py:806-812): the occupancy update
+    of `update_list` runs at the field's current resolution, the upsampling of `upsamp_list` re-creates the optimiser
+    (Adam moments and the LambdaLR delay restart) and resets the batch controller; training continues afterwards."""
+    from nmf_b200 import train
+    from nmf_b200.plugins import _n_to_reso
+    from conftest import grid_of
+    fix = load_fixture("plain_g64")
+    hp = dict(starting_batch_size=64, min_batch_size=128, max_batch_size=256, target_num_samples=4000, batch_size=128)
+    allrays = fix["rays"][:2048].contiguous()
+    tr0 = train.PlainTrainer(fix["state"], fix["aabb"], fix["near_far"], grid_of(fix), alpha_volume=fix["alpha_volume"], device=env)
+    from nmf_b200 import ops
+    gt = ops.render_rays(tr0.scene, allrays.cuda(), fix["focal"], chunk=2048, skip_eps=0.0, t_cut=0.0)[0]["rgb_map"].clone()
+    tr = train.PlainTrainer(fix["state"], fix["aabb"], fix["near_far"], grid_of(fix), alpha_volume=fix["alpha_volume"],
+                            device=env, max_samples=50000, seed=3, params=hp)
+    n_vox = [80 ** 3]
+    hist = tr.fit(allrays, gt, n_iters=8, upsamp_list=[3], n_voxel_list=n_vox, update_list=[2, 5])
+    want = _n_to_reso(n_vox[0], torch.as_tensor(fix["aabb"]).float())
+    assert [h.get("reinit", False) for h in hist] == [False, False, False, True, False, False, False, False]
+    assert hist[3]["grid"] == grid_of(fix) and hist[4]["grid"] == want and tr.meta["grid_size"] == want
+    assert hist[3]["next_num_rays"] != hp["starting_batch_size"] and hist[4]["lbatch_size"] == hp["min_batch_size"]
+    assert tr.optimizer.t == 4 and abs(hist[4]["lr_factor"] - train.learning_rate_decay(1, max_steps=30000, **train.REFERENCE_PARAMS)) < 1e-9
+    assert tr.params["rf.density_rf.app_plane.0"].shape[-2:] == (want[1], want[0])
+    assert tuple(tr.alpha_volume.shape) == (want[2], want[1], want[0])          # rebuilt at iteration 5, new resolution
+    assert all(np.isfinite(h["mse"]) for h in hist) and hist[-1]["mse"] < 1e-2

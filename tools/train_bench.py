@@ -19,3 +19,4 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=60)
     a = ap.parse_args()
     print(json.dumps(train.benchmark_plain(a.grid, a.rays, a.steps, a.iters)))
+    print(json.dumps(train.benchmark_microfacet_forward(a.grid, a.rays, a.steps)))
