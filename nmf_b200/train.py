@@ -49,20 +49,25 @@ class PlainGradBuffers:
         for t in self.t.values():
             t.zero_()
 
-    def reference_layout(self):
+    def reference_views(self):
         """{reference state_dict key: gradient in the parameter's own shape}: planes (1,C,H,W), lines (1,C,N,1),
-        basis_mat (24,72), mlp weights (out,in)."""
+        basis_mat (24,72), mlp weights (out,in) -- strided VIEWS of the channel-last buffers (no copy: the trainer adds
+        them straight into the flat gradient bucket, one pass)."""
         g = {}
         for p in range(3):
-            g[f"rf.density_rf.app_plane.{p}"] = self.t[f"d_plane{p}"].permute(2, 0, 1)[None].contiguous()
-            g[f"rf.density_rf.app_line.{p}"] = self.t[f"d_line{p}"].t()[None, :, :, None].contiguous()
-            g[f"rf.app_rf.app_plane.{p}"] = self.t[f"a_plane{p}"].permute(2, 0, 1)[None].contiguous()
-            g[f"rf.app_rf.app_line.{p}"] = self.t[f"a_line{p}"].t()[None, :, :, None].contiguous()
-        g["rf.basis_mat.weight"] = self.t["basis_t"].t().contiguous()
+            g[f"rf.density_rf.app_plane.{p}"] = self.t[f"d_plane{p}"].permute(2, 0, 1)[None]
+            g[f"rf.density_rf.app_line.{p}"] = self.t[f"d_line{p}"].t()[None, :, :, None]
+            g[f"rf.app_rf.app_plane.{p}"] = self.t[f"a_plane{p}"].permute(2, 0, 1)[None]
+            g[f"rf.app_rf.app_line.{p}"] = self.t[f"a_line{p}"].t()[None, :, :, None]
+        g["rf.basis_mat.weight"] = self.t["basis_t"].t()
         for i, li in enumerate((0, 2, 4)):
-            g[f"model.diffuse_module.mlp.{li}.weight"] = self.t[f"w{i}t"].t().contiguous()
-            g[f"model.diffuse_module.mlp.{li}.bias"] = self.t[f"b{i}"].clone()
+            g[f"model.diffuse_module.mlp.{li}.weight"] = self.t[f"w{i}t"].t()
+            g[f"model.diffuse_module.mlp.{li}.bias"] = self.t[f"b{i}"]
         return g
+
+    def reference_layout(self):
+        """reference_views(), materialised (contiguous copies that outlive the next step)."""
+        return {k: v.contiguous().clone() if v.is_contiguous() else v.contiguous() for k, v in self.reference_views().items()}
 
 
 class TrainBuffers:
@@ -377,7 +382,7 @@ class PlainTrainer:
                           max_samples=self.max_samples, lambda_pred=self.lambda_pred, buffers=self.buffers)
         self._calls += 1
         self.buffers = out["buffers"]
-        grads = out["grads"].reference_layout()
+        grads = out["grads"].reference_views()
         for k, p in self.params.items():                      # p.grad is a view into the flat bucket
             if first:
                 p.grad.copy_(grads[k])
