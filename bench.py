@@ -345,7 +345,9 @@ def main():
     if not a.no_train and not a.no_cpu and world == 1:
         try:
             from nmf_b200 import train
-            line["train_step"] = train.benchmark_plain(a.grid, 4096, steps=10, iters=0, device=f"cuda:{torch.cuda.current_device()}")
+            dev_s = f"cuda:{torch.cuda.current_device()}"
+            line["train_step"] = train.benchmark_plain(a.grid, 4096, steps=10, iters=8, device=dev_s)
+            line["train_forward_microfacet"] = train.benchmark_microfacet_forward(a.grid, 4096, steps=10, device=dev_s)
         except Exception as e:                      # never lets the extra entry take the bench line down
             line["train_step"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     print(json.dumps(line), flush=True)

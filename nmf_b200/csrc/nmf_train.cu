@@ -10,8 +10,8 @@
 //   k_train_mlp<0>     128 samples per CTA: appearance gather, basis, encoding, 135-128-128-3 MLP; rgb per sample,
 //                      w * rgb into the ray
 //   k_train_loss       per ray: tonemap, background, loss, dL/d(linear colour), dL/d(acc)
-//   k_train_mlp<1>     recomputes the tile's forward in shared memory ([feature][sample], stride 136) and walks back: the five
-//                      tile GEMMs (two layers, dW1, dH1, dW0, dX) on the tensor cores as 3xTF32 mma.sync,
+//   k_train_mlp<1>     reloads the tile's forward activations ([feature][sample], stride 136; kept by k_train_mlp<0>) and walks
+//                      back: the four tile GEMMs (dW1, dH1, dW0, dX) on the tensor cores as 3xTF32 mma.sync,
 //                      weight gradients are per-tile contractions over the 128 samples flushed with REDs; activations'
 //                      gradients in place;
 //                      encoding, basis_mat and the appearance factors (16-byte REDs into channel-last buffers)
@@ -125,6 +125,9 @@ struct TWS {
   float* g_lin;   // [n][3]
   float* g_acc;   // [n]
   int* s_ray; float* s_z; float* s_dist; float* s_f; float* s_alpha; float* s_T; float* s_w; float* s_rgb; float* s_dw;
+  // activations of the forward tiles, kept for the backward pass: per 128-sample tile [row][128] floats -- the encoded
+  // input X (135 rows) and the two hidden layers after ReLU (128 rows each); 1564 B per sample, written once, read once
+  float* act_x; float* act_h1; float* act_h2;
   size_t zero_off, zero_bytes, total;
 };
 static size_t t_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -150,6 +153,10 @@ static void t_carve(TWS& w, const NmfScene* s, int n, int cap, char* base) {
   w.s_w = (float*)take((size_t)cap * 4);
   w.s_rgb = (float*)take((size_t)cap * 3 * 4);
   w.s_dw = (float*)take((size_t)cap * 4);
+  const size_t tiles = ((size_t)cap + 127) / 128;
+  w.act_x = (float*)take(tiles * 135 * 128 * 4);
+  w.act_h1 = (float*)take(tiles * 128 * 128 * 4);
+  w.act_h2 = (float*)take(tiles * 128 * 128 * 4);
   w.total = off;
 }
 extern "C" size_t nmf_train_workspace_bytes(const NmfScene* scene, int n_rays, int cap_samples) {
@@ -340,6 +347,20 @@ __device__ __forceinline__ float tile_rowdot(const float* r, const float* c) {
   return b;
 }
 
+// shared-memory tile ([row][TS]) <-> global tile ([row][128]), 16-byte accesses by all threads of the CTA
+__device__ __forceinline__ void tile_store(float* g, const float* sm_rows, int rows, int t) {
+  for (int i = t; i < rows * 32; i += MLP_T) {
+    const int r = i >> 5, c4 = (i & 31) * 4;
+    __stcs((float4*)(g + (size_t)r * 128 + c4), *(const float4*)(sm_rows + r * TS + c4));      // streamed: read once, later
+  }
+}
+__device__ __forceinline__ void tile_load(float* sm_rows, const float* g, int rows, int t) {
+  for (int i = t; i < rows * 32; i += MLP_T) {
+    const int r = i >> 5, c4 = (i & 31) * 4;
+    *(float4*)(sm_rows + r * TS + c4) = __ldcs((const float4*)(g + (size_t)r * 128 + c4));
+  }
+}
+
 struct MlpArgs { const float* rays; const int* n_kept; int cap; NmfPlainGrads g; };
 template <int BWD>
 __global__ void __launch_bounds__(MLP_T, 1) k_train_mlp(const NmfScene s, const MlpArgs a, const TWS w) {
@@ -361,8 +382,10 @@ __global__ void __launch_bounds__(MLP_T, 1) k_train_mlp(const NmfScene s, const 
     int ray = 0;
     float dv[3] = {0.f, 0.f, 0.f};
     NmfTaps tp;
+    const size_t tile_id = (size_t)(tile / TILE);
+    float rgb[3] = {0.f, 0.f, 0.f};
     if (lead) {
-      float o[3] = {0.f, 0.f, 0.f}, p[3], xn[3], coef[72], feat[24];
+      float o[3] = {0.f, 0.f, 0.f}, p[3], xn[3];
       float z = 0.f;
       if (active) {
         ray = w.s_ray[si];
@@ -372,37 +395,52 @@ __global__ void __launch_bounds__(MLP_T, 1) k_train_mlp(const NmfScene s, const 
       nmf_step_pos(o, dv, z, p);
       nmf_normalize_xyz(s, p, xn);
       tp = nmf_vm_taps(s, xn);
-      nmf_app_coef(s, tp, coef);
-      for (int oo = 0; oo < 24; ++oo) {
-        float acc = 0.f;
+      if (!BWD) {
+        float coef[72], feat[24];
+        nmf_app_coef(s, tp, coef);
+        for (int oo = 0; oo < 24; ++oo) {
+          float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 72; ++j) acc += __ldg(s.basis_t + j * 24 + oo) * coef[j];
-        feat[oo] = active ? acc : 0.f;
+          for (int j = 0; j < 72; ++j) acc += __ldg(s.basis_t + j * 24 + oo) * coef[j];
+          feat[oo] = active ? acc : 0.f;
+        }
+        nmf_plain_encode(feat, dv, X + t, TS);
       }
-      nmf_plain_encode(feat, dv, X + t, TS);
     }
-    __syncthreads();
     float acc[2][8][4];
-    // layer 1: H1[j][n] = relu(b0[j] + sum_k W0[j][k] X[k][n])      (W0 as stored: (out, in), row stride 135)
-    warp_gemm<2, 8>(acc, 17,
-                     [&](int m, int k) { return k < 135 ? __ldg(s.plain_w0 + (m0 + m) * 135 + k) : 0.f; },
-                     [&](int k, int n) { return X[k * TS + n0 + n]; }, lane);
-    warp_epilogue<2, 8>(acc, lane, [&](int r, int c, float v) { H1[(m0 + r) * TS + n0 + c] = fmaxf(v + __ldg(s.plain_b0 + m0 + r), 0.f); });
-    __syncthreads();
-    // layer 2
-    warp_gemm<2, 8>(acc, 16, [&](int m, int k) { return __ldg(s.plain_w1 + (m0 + m) * 128 + k); },
-                     [&](int k, int n) { return H1[k * TS + n0 + n]; }, lane);
-    warp_epilogue<2, 8>(acc, lane, [&](int r, int c, float v) { H2[(m0 + r) * TS + n0 + c] = fmaxf(v + __ldg(s.plain_b1 + m0 + r), 0.f); });
-    __syncthreads();
-    // output layer (3 wide) per sample
-    float o3[3] = {__ldg(s.plain_b2), __ldg(s.plain_b2 + 1), __ldg(s.plain_b2 + 2)};
-    if (lead) for (int k = 0; k < 128; ++k) {
-      const float hv = H2[k * TS + t];
-      const float* w2 = s.plain_w2t + k * 3;
-      o3[0] += hv * __ldg(w2); o3[1] += hv * __ldg(w2 + 1); o3[2] += hv * __ldg(w2 + 2);
+    if (BWD) {
+      // the forward pass kept this tile's activations (1564 B per sample through HBM instead of recomputing the
+      // gather, the encoding and both 128-wide layers: a third of the backward pass's MMA work)
+      tile_load(X, w.act_x + tile_id * 135 * 128, 135, t);
+      tile_load(H1, w.act_h1 + tile_id * 128 * 128, 128, t);
+      tile_load(H2, w.act_h2 + tile_id * 128 * 128, 128, t);
+      if (active) for (int c = 0; c < 3; ++c) rgb[c] = w.s_rgb[3 * (size_t)si + c];
+      __syncthreads();
+    } else {
+      __syncthreads();
+      tile_store(w.act_x + tile_id * 135 * 128, X, 135, t);
+      // layer 1: H1[j][n] = relu(b0[j] + sum_k W0[j][k] X[k][n])      (W0 as stored: (out, in), row stride 135)
+      warp_gemm<2, 8>(acc, 17,
+                       [&](int m, int k) { return k < 135 ? __ldg(s.plain_w0 + (m0 + m) * 135 + k) : 0.f; },
+                       [&](int k, int n) { return X[k * TS + n0 + n]; }, lane);
+      warp_epilogue<2, 8>(acc, lane, [&](int r, int c, float v) { H1[(m0 + r) * TS + n0 + c] = fmaxf(v + __ldg(s.plain_b0 + m0 + r), 0.f); });
+      __syncthreads();
+      tile_store(w.act_h1 + tile_id * 128 * 128, H1, 128, t);
+      // layer 2
+      warp_gemm<2, 8>(acc, 16, [&](int m, int k) { return __ldg(s.plain_w1 + (m0 + m) * 128 + k); },
+                       [&](int k, int n) { return H1[k * TS + n0 + n]; }, lane);
+      warp_epilogue<2, 8>(acc, lane, [&](int r, int c, float v) { H2[(m0 + r) * TS + n0 + c] = fmaxf(v + __ldg(s.plain_b1 + m0 + r), 0.f); });
+      __syncthreads();
+      tile_store(w.act_h2 + tile_id * 128 * 128, H2, 128, t);
+      // output layer (3 wide) per sample
+      float o3[3] = {__ldg(s.plain_b2), __ldg(s.plain_b2 + 1), __ldg(s.plain_b2 + 2)};
+      if (lead) for (int k = 0; k < 128; ++k) {
+        const float hv = H2[k * TS + t];
+        const float* w2 = s.plain_w2t + k * 3;
+        o3[0] += hv * __ldg(w2); o3[1] += hv * __ldg(w2 + 1); o3[2] += hv * __ldg(w2 + 2);
+      }
+      for (int c = 0; c < 3; ++c) rgb[c] = nmf_sigmoid(o3[c]);
     }
-    float rgb[3];
-    for (int c = 0; c < 3; ++c) rgb[c] = nmf_sigmoid(o3[c]);
     if (!BWD) {
       if (active) {
         const float wt = w.s_w[si];
