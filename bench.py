@@ -169,7 +169,7 @@ def run_reference(a):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def reference_alpha_volume(state, meta):
@@ -195,8 +195,31 @@ def config_dict(a, n_rays):
                   "through HBM every step, factor planes (78 MB) compete with it for the 126 MB L2"}
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Rank 0 must print exactly ONE JSON line: everything else that writes to fd 1 during the run (the NCCL version
+    banner, library chatter) is sent to stderr; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     a = parse()
+    _claim_stdout()
     if a.impl == "reference":
         return run_reference(a)
     rank = int(os.environ.get("RANK", "0"))
@@ -350,7 +373,7 @@ def main():
             line["train_forward_microfacet"] = train.benchmark_microfacet_forward(a.grid, 4096, steps=10, device=dev_s)
         except Exception as e:                      # never lets the extra entry take the bench line down
             line["train_step"] = {"error": f"{type(e).__name__}: {e}"[:200]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
