@@ -344,7 +344,9 @@ def main():
             "per_kernel": {k: {"ms": round(d["ms"], 4), "GBps_algorithmic": round(d["gbs"], 1),
                                "GBps_touched": (round(d["touched"] / (d["ms"] * 1e-3) / 1e9, 1) if d["touched"] and d["ms"] > 0 else None)}
                            for k, d in kernels.items()},
-            "phase_ms": {k: round(v, 4) for k, v in phase_acc.items()}}
+            "phase_ms": {k: round(v, 4) for k, v in phase_acc.items()},
+            "phase_note": "CUDA-event phase times averaged over the e2e (host-buffer) steps: same kernels as the device-resident "
+                          "steps; 'finish' there also holds the last staged device-to-host copies (k_finish0 itself: ~40 us)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_dict(a, n), "clocks": clk.summary(),

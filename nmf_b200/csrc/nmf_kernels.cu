@@ -462,7 +462,6 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
     __syncwarp();
 #pragma unroll 1
     for (int round = 0; round < 8; ++round) {
-      const int si = wbase + round * 4 + grp;
       float xn[3];
       {
         const float* row = s_feat + (round * 4 + grp) * SHADE_FEAT_LD;
@@ -1017,6 +1016,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
   }
   __syncthreads();
   const unsigned n_tie = sh_eq;
+  __syncthreads();            // every thread holds the tie count before thread 0 reuses the counter below (racecheck)
   const bool by_key = n_tie > need && n_tie <= NMF_TIE_CAP;      // otherwise all ties are taken, or (absurdly many) first come
   if (by_key && threadIdx.x == 0) {
     // the `need` smallest keys win: selection sort over a handful of entries
@@ -1089,7 +1089,7 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
       b = a.bs + key;
       const nmf_v3 L = nmf_mk3(q0.x, q0.y, q0.z);
       if (slot >= 0) {
-        const float* src = a.rgb1 + ((size_t)chunk * a.max_retrace + slot) * 4;
+        const float* src = a.rgb1 + ((size_t)chunk * (size_t)a.max_retrace + (size_t)slot) * 4;
         inc[0] = src[0]; inc[1] = src[1]; inc[2] = src[2];
       } else {
         nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, L, q0.w, inc);
