@@ -98,6 +98,42 @@ def compose(overrides=(), config_dir=CONFIG_DIR, config_name="default"):
     return cfg
 
 
+def expand_multirun(overrides):
+    """hydra `-m` (README.md:10-17 of the reference: `python train.py -m dataset=ficus,helmet,toaster`): every override
+    whose value is a top-level comma list sweeps over its items; the jobs are the cartesian product, run sequentially,
+    in hydra's order (the last sweep varies fastest).  Bracketed values (`a=[1,2]`) are lists, not sweeps."""
+    import itertools
+    axes = []
+    for o in overrides:
+        k, v = o.split("=", 1)
+        items, depth, cur = [], 0, ""
+        for ch in v:
+            if ch in "[{(":
+                depth += 1
+            elif ch in "]})":
+                depth -= 1
+            if ch == "," and depth == 0:
+                items.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        items.append(cur)
+        axes.append([f"{k}={it}" for it in items])
+    return [list(job) for job in itertools.product(*axes)]
+
+
+def save(cfg, path):
+    """OmegaConf.save(config=cfg, f=path) (train.py:485): the composed run config as YAML, loadable by load_yaml."""
+    def plain(node):
+        if isinstance(node, dict):
+            return {k: plain(v) for k, v in node.items()}
+        if isinstance(node, (list, tuple)):
+            return [plain(v) for v in node]
+        return node
+    with open(path, "w") as f:
+        yaml.safe_dump(plain(cfg), f, sort_keys=False)
+
+
 def _resolve(name):
     name = TARGETS.get(name, name)
     mod, _, attr = name.rpartition(".")

@@ -63,6 +63,23 @@ def test_config_compose_and_overrides():
     assert cfg.model.arch.rf._target_ == "fields.tensoRF.TensorVMSplit"       # rf <- field splice (train.py:911)
 
 
+def test_config_multirun_and_save(tmp_path):
+    """hydra -m sweeps (sequential jobs, last sweep fastest) and OmegaConf.save of the run config (train.py:485)"""
+    from nmf_b200 import config
+    jobs = config.expand_multirun(["dataset=ficus,helmet,toaster", "model.arch.model.anoise=0.1", "field.grid_size=[64,64,64]",
+                                   "model.arch.bg_module.bg_resolution=32,64"])
+    assert len(jobs) == 6 and jobs[0] == ["dataset=ficus", "model.arch.model.anoise=0.1", "field.grid_size=[64,64,64]",
+                                          "model.arch.bg_module.bg_resolution=32"]
+    assert jobs[1][3] == "model.arch.bg_module.bg_resolution=64" and jobs[2][0] == "dataset=helmet"
+    cfgs = [config.compose(j) for j in jobs]
+    assert cfgs[2].dataset.near_far == [3, 5] and cfgs[5].model.arch.bg_module.bg_resolution == 64
+    assert cfgs[3].model.arch.rf.grid_size == [64, 64, 64]
+    path = tmp_path / "config.yaml"
+    config.save(cfgs[2], str(path))
+    back = config.load_yaml(str(path))
+    assert back == cfgs[2] and back.model.arch.rf.lr == 2e-2 and back.model.arch.normal_module is None
+
+
 def test_plugins_keep_reference_state_dict_keys():
     from nmf_b200 import config
     fix = load_fixture("microfacet_g40")
