@@ -235,9 +235,10 @@ int nmf_ggx_sample(const float* u, const float* V, const float* N, const float* 
 /* MLPBRDF.forward (modules/brdf.py:177-261): feat (n,24), half_local (n,3), diff_local (n,3), rough (n) -> (n,3) */
 int nmf_brdf_mlp(const NmfScene* scene, const float* feat, const float* half_local, const float* diff_local,
                  const float* rough, int n, float* out, void* stream);
-/* RandHydraMLPDiffuse.forward (modules/render_modules.py:519-574): feat (n,24) -> albedo, tint, f0 (n,3), r1 (n) */
+/* RandHydraMLPDiffuse.forward (modules/render_modules.py:519-574): feat (n,24) -> albedo, tint, f0 (n,3), r1 (n) and,
+ * when r2 != NULL, the second roughness channel r2 (n) (the render path sets r2 = r1, models/microfacet.py:360) */
 int nmf_material_heads(const NmfScene* scene, const float* feat, int n, float* albedo, float* tint, float* f0,
-                       float* r1, void* stream);
+                       float* r1, float* r2, void* stream);
 /* occupancy rebuild, alpha stage of AlphaGridSampler.getDenseAlpha (samplers/alphagrid.py:209-247):
  * alpha[z][y][x] = 1 - exp(-sigma(lattice point) * stepsize) on a (gz,gy,gx) lattice spanning the aabb */
 int nmf_dense_alpha(const NmfScene* scene, int gx, int gy, int gz, float* alpha, void* stream);

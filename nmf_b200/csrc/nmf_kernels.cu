@@ -1907,7 +1907,7 @@ extern "C" int nmf_brdf_mlp(const NmfScene* scene, const float* feat, const floa
   CKL();
   return NMF_OK;
 }
-__global__ void k_heads(const NmfScene s, const float* feat, int n, float* albedo, float* tint, float* f0, float* r1) {
+__global__ void k_heads(const NmfScene s, const float* feat, int n, float* albedo, float* tint, float* f0, float* r1, float* r2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float lin[11];
@@ -1922,11 +1922,12 @@ __global__ void k_heads(const NmfScene s, const float* feat, int n, float* albed
     f0[3 * i + c] = nmf_sigmoid(lin[6 + c] + s.f0_bias);
   }
   r1[i] = nmf_clampf(nmf_sigmoid(lin[9] + s.roughness_bias) / 2.0f, 1e-2f, 1.0f);
+  if (r2) r2[i] = nmf_clampf(nmf_sigmoid(lin[10] + s.roughness_bias) / 2.0f, 1e-2f, 1.0f);   // render_modules.py:557-560
 }
 extern "C" int nmf_material_heads(const NmfScene* scene, const float* feat, int n, float* albedo, float* tint, float* f0,
-                                  float* r1, void* stream) {
+                                  float* r1, float* r2, void* stream) {
   if (!scene || !scene->head_w || !feat || !albedo || !tint || !f0 || !r1 || n <= 0) return NMF_E_ARG;
-  k_heads<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*scene, feat, n, albedo, tint, f0, r1);
+  k_heads<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*scene, feat, n, albedo, tint, f0, r1, r2);
   CKL();
   return NMF_OK;
 }

@@ -101,15 +101,18 @@ def brdf_mlp(scene, feat, half_local, diff_local, rough):
     return out
 
 
-def material_heads(scene, feat):
+def material_heads(scene, feat, with_r2=False):
+    """RandHydraMLPDiffuse.forward (render_modules.py:519-574): (albedo, tint, f0 (n,3), r1 (n)[, r2 (n)])."""
     f = _f32(feat, scene.device)
     n = f.shape[0]
     a, t, f0 = (torch.empty(n, 3, device=f.device) for _ in range(3))
     r1 = torch.empty(n, device=f.device)
+    r2 = torch.empty(n, device=f.device) if with_r2 else None
     if n:
-        _lib.check(_lib.lib().nmf_material_heads(scene.ref(), _p(f), n, _p(a), _p(t), _p(f0), _p(r1), _stream()),
-                   "nmf_material_heads")
-    return a, t, f0, r1
+        with torch.cuda.device(f.device):
+            _lib.check(_lib.lib().nmf_material_heads(scene.ref(), _p(f), n, _p(a), _p(t), _p(f0), _p(r1), _p(r2), _stream()),
+                       "nmf_material_heads")
+    return (a, t, f0, r1, r2) if with_r2 else (a, t, f0, r1)
 
 
 def dense_alpha(scene, grid_size):

@@ -150,7 +150,8 @@ class TensorVMSplit(nn.Module):
         return {prefix + k: v for k, v in self.state_dict().items()}
 
     def _param_key(self):
-        return tuple(p._version for p in self.parameters()) + (tuple(self.grid_size.tolist()), str(self.get_device()))
+        return tuple(p._version for p in self.parameters()) + (tuple(self.grid_size.tolist()), str(self.get_device()),
+                                                               float(self.density_shift), float(self.distance_scale))
 
     def scene(self):
         """DeviceScene holding only the factors (field-only plugin calls); rebuilt when a parameter changed."""
@@ -319,7 +320,9 @@ class MLPBRDF(nn.Module):
         if not (feape == 0 and dotpe < 0 and activation == "sigmoid" and not mul_LdotN and hidden_w == 64 and num_layers == 3
                 and v_encoder is None and n_encoder is None and l_encoder is None):
             raise _lib.NmfError("MLPBRDF: kernels implement the microfacet_tensorf2 configuration (66 -> 64 -> 64 -> 4, sigmoid)")
-        self.in_channels, self.bias, self.lr, self.init_val = in_channels, bias, lr, 0.5
+        self.in_channels, self.bias, self.lr, self.init_val = in_channels, bias, lr, 0.25      # modules/brdf.py:119
+        self.activation_name = activation
+        self._scene, self._scene_key = None, None
         self.h_encoder, self.d_encoder = h_encoder, d_encoder
         self.in_mlpC = in_channels + 2 * (18 + 3)
         self.mlp = nn.Sequential(nn.Linear(self.in_mlpC, 64), nn.ReLU(inplace=True), nn.Linear(64, 64), nn.ReLU(inplace=True),
@@ -329,6 +332,36 @@ class MLPBRDF(nn.Module):
                 nn.init.kaiming_uniform_(m.weight, nonlinearity="relu")
                 nn.init.zeros_(m.bias)
 
+    def _own_scene(self):
+        """A device scene that only carries this MLP (nmf_brdf_mlp), rebuilt when a weight or the bias changed."""
+        dev = self.mlp[0].weight.device
+        key = (tuple(p._version for p in self.parameters()), float(self.bias), str(dev))
+        if self._scene is None or key != self._scene_key:
+            st = {f"model.brdf.{k}": v for k, v in self.state_dict().items()}
+            self._scene = DeviceScene.shading_only(st, device=dev, heads=False, brdf=True, brdf_bias=float(self.bias))
+            self._scene_key = key
+        return self._scene
+
+    @torch.no_grad()
+    def forward(self, V, L, N, H, local_v, half_vec, diff_vec, efeatures, eax, eay=None):
+        """modules/brdf.py:177-261 in the microfacet_tensorf2 configuration: the MLP sees [feature, ISH(half_vec),
+        half_vec, ISH(diff_vec), diff_vec] (V, L, N, H, local_v only feed options that are off) -> (n,3) BRDF weight."""
+        return ops.brdf_mlp(self._own_scene(), efeatures, half_vec.reshape(-1, 3), diff_vec.reshape(-1, 3), eax.reshape(-1))
+
+    @torch.no_grad()
+    def calibrate(self, efeatures, bg_brightness):
+        """modules/brdf.py:141-176: shifts `bias` so that the mean BRDF weight over random directions is
+        init_val / bg_brightness (inverse-sigmoid domain)."""
+        n, dev = efeatures.shape[0], efeatures.device
+        unit = lambda v: v / (v ** 2).sum(-1, keepdim=True).clip(min=torch.finfo(torch.float32).eps).sqrt()
+        rand_vecs = lambda: unit(2 * torch.rand((n, 3), device=dev) - 1)
+        L, norms = rand_vecs(), rand_vecs()
+        norms = (L * norms).sum(dim=-1, keepdim=True) * norms
+        weight = self(rand_vecs(), L, norms, rand_vecs(), rand_vecs(), rand_vecs(), rand_vecs(), efeatures,
+                      torch.rand(n, device=dev), torch.rand(n, device=dev))
+        target = self.init_val / float(bg_brightness)
+        self.bias += math.log(target / (1 - target)) - float((weight / (1 - weight)).log().mean())
+
 
 class RandHydraMLPDiffuse(nn.Module):
     def __init__(self, in_channels, pospe=-1, feape=0, roughness_view_encoder=None, roughness_cfg=None, hidden_w=64,
@@ -337,13 +370,45 @@ class RandHydraMLPDiffuse(nn.Module):
         super().__init__()
         if num_layers != 1 or pospe >= 0 or feape > 0 or roughness_view_encoder is not None:
             raise _lib.NmfError("RandHydraMLPDiffuse: kernels implement single-Linear heads on the raw feature (num_layers=1)")
-        self.in_channels, self.lr = in_channels, lr
+        self.in_channels, self.lr, self.start_roughness = in_channels, lr, start_roughness
         self.tint_bias, self.diffuse_bias, self.diffuse_mul, self.roughness_bias = tint_bias, diffuse_bias, diffuse_mul, roughness_bias
+        self.f0_bias = kwargs.get("f0_bias", 0)
+        self._scene, self._scene_key = None, None
         for name, od in (("diffuse", 3), ("tint", 3), ("f0", 3), ("roughness", 2)):
             lin = nn.Linear(in_channels, od)
             nn.init.xavier_uniform_(lin.weight)
             nn.init.zeros_(lin.bias)
             setattr(self, f"{name}_mlp", nn.Sequential(lin))
+
+    def _own_scene(self):
+        dev = self.diffuse_mlp[0].weight.device
+        biases = dict(diffuse_bias=float(self.diffuse_bias), diffuse_mul=float(self.diffuse_mul), tint_bias=float(self.tint_bias),
+                      roughness_bias=float(self.roughness_bias), f0_bias=float(self.f0_bias))
+        key = (tuple(p._version for p in self.parameters()), tuple(biases.values()), str(dev))
+        if self._scene is None or key != self._scene_key:
+            st = {f"model.diffuse_module.{k}": v for k, v in self.state_dict().items()}
+            self._scene = DeviceScene.shading_only(st, device=dev, heads=True, brdf=False, **biases)
+            self._scene_key = key
+        return self._scene
+
+    @torch.no_grad()
+    def forward(self, pts, viewdirs, features, std=0, **kwargs):
+        """modules/render_modules.py:519-574 (nmf_material_heads): (diffuse, tint, dict(diffuse, r1, r2, f0, tint))."""
+        if std != 0:
+            raise NotImplementedError("RandHydraMLPDiffuse: std != 0 (material noise) is not built")
+        a, t, f0, r1, r2 = ops.material_heads(self._own_scene(), features, with_r2=True)
+        return a, t, dict(diffuse=a, r1=r1.reshape(-1, 1), r2=r2.reshape(-1, 1), f0=f0, tint=t)
+
+    @torch.no_grad()
+    def calibrate(self, mean_brightness, conserve_energy, *args, **kwargs):
+        """modules/render_modules.py:632-642: moves diffuse_bias / roughness_bias so that the mean albedo is
+        (0.5 or 0.25) / mean_brightness and the mean roughness is start_roughness (inverse-sigmoid domain)."""
+        inv = lambda x: (x / (1 - x)).log() if torch.is_tensor(x) else math.log(x / (1 - x))
+        diffuse, tint, extra = self(*args, **kwargs)
+        v = (0.25 if not conserve_energy else 0.5) / float(mean_brightness)
+        self.diffuse_bias += inv(v) - float(inv(diffuse).mean())
+        rough = (extra["r1"] + extra["r2"]) / 2 / 2
+        self.roughness_bias += inv(self.start_roughness) - float(inv(rough).mean())
 
 
 class MLPRender_Fea(nn.Module):
@@ -355,6 +420,9 @@ class MLPRender_Fea(nn.Module):
         self.mlp = nn.Sequential(nn.Linear(in_mlpC, featureC), nn.ReLU(inplace=True), nn.Linear(featureC, featureC),
                                  nn.ReLU(inplace=True), nn.Linear(featureC, 3))
         nn.init.constant_(self.mlp[-1].bias, 0)
+
+    def calibrate(self, *args):
+        return              # modules/render_modules.py:222-223
 
 
 class Microfacet(nn.Module):
@@ -374,6 +442,8 @@ class Microfacet(nn.Module):
         self.diffuse_module = diffuse_module(in_channels=app_dim)
         self.anoise, self.rays_per_ray, self.test_rays_per_ray = anoise, rays_per_ray, test_rays_per_ray
         self.max_brdf_rays, self.max_retrace_rays = list(max_brdf_rays), list(max_retrace_rays)
+        self.start_max_retrace_rays = list(max_retrace_rays)
+        self.mean_ratios, self.ratio_list, self.conserve_energy = None, None, conserve_energy
         self.target_num_samples = list(target_num_samples)
         # training schedule state (models/microfacet.py:53-58, 70-71)
         self.min_rough, self.min_rough_decay = min_rough_start, min_rough_decay
@@ -387,7 +457,7 @@ class Microfacet(nn.Module):
         return dict(model="microfacet", anoise=self.anoise, rays_per_ray=self.test_rays_per_ray,
                     max_brdf_rays=tuple(self.max_brdf_rays), max_retrace_rays=tuple(self.max_retrace_rays),
                     diffuse_bias=d.diffuse_bias, diffuse_mul=d.diffuse_mul, roughness_bias=d.roughness_bias,
-                    tint_bias=d.tint_bias, f0_bias=0.0, brdf_bias=b.bias)
+                    tint_bias=d.tint_bias, f0_bias=getattr(d, "f0_bias", 0.0), brdf_bias=b.bias)
 
     def check_schedule(self, iter, batch_mul, **kw):
         """models/microfacet.py:112-121"""
@@ -403,8 +473,38 @@ class Microfacet(nn.Module):
         return [{"params": self.diffuse_module.parameters(), "lr": self.diffuse_module.lr * lr_scale},
                 {"params": self.brdf.parameters(), "lr": self.brdf.lr * lr_scale}]
 
+    def reset_counter(self):
+        """models/microfacet.py:236-239"""
+        self.max_retrace_rays = list(self.start_max_retrace_rays)
+        self.mean_ratios = None
+        self.ratio_list = None
+
     def update_n_samples(self, n_samples):
-        pass   # the adaptive retrace controller is part of the training loop (train.py:627)
+        """models/microfacet.py:241-268, the adaptive retrace controller fed by statistics["n_samples"][1:] (train.py:627):
+        max_retrace_rays[i] follows target_num_samples[i] * min(recent rays-per-sample ratios), capped by max_brdf_rays."""
+        if len(n_samples) != len(self.max_retrace_rays):
+            return
+        ratios = [(n_rays / n_sample) if n_sample > 0 else 1e-3 for n_rays, n_sample in zip(self.max_retrace_rays, n_samples)]
+        if self.ratio_list is None:
+            self.ratio_list = [[r, 1e-3] if r is not None else [] for r in ratios]
+        else:
+            self.ratio_list = [[r for r in ([ratio] + rlist) if r is not None][:20] for ratio, rlist in zip(ratios, self.ratio_list)]
+        self.mean_ratios = [min(rlist) if len(rlist) > 0 else None for rlist in self.ratio_list]
+        self.max_retrace_rays = [min(int(target * ratio + 1), maxv) if ratio is not None else prev
+                                 for target, ratio, maxv, prev in zip(self.target_num_samples, self.mean_ratios,
+                                                                      self.max_brdf_rays[:-1], self.max_retrace_rays)]
+
+    def calibrate(self, args, xyz, feat, bg_brightness, save_config=True):
+        """models/microfacet.py:79-96 (train.py:437): bias calibration of the material heads and the BRDF MLP against the
+        environment's mean brightness; the new biases are written back into the run config."""
+        unit = lambda v: v / (v ** 2).sum(-1, keepdim=True).clip(min=torch.finfo(torch.float32).eps).sqrt()
+        self.diffuse_module.calibrate(bg_brightness, self.conserve_energy, xyz, unit(torch.rand_like(xyz[:, :3])), feat)
+        self.brdf.calibrate(feat, bg_brightness)
+        if save_config and args is not None:
+            args.model.arch.model.brdf.bias = self.brdf.bias
+            args.model.arch.model.diffuse_module.diffuse_bias = self.diffuse_module.diffuse_bias
+            args.model.arch.model.diffuse_module.roughness_bias = self.diffuse_module.roughness_bias
+        return args
 
     def forward(self, *a, **kw):
         raise NotImplementedError("Microfacet.forward runs inside the fused kernels: call TensorNeRF.forward / render_chunks")
@@ -431,6 +531,12 @@ class PlainTensoRF(nn.Module):
 
     def update_n_samples(self, n_samples):
         pass
+
+    def reset_counter(self):
+        pass
+
+    def calibrate(self, args, *fargs, **kwargs):
+        return args          # models/tensorf.py:22-23
 
 
 class IntegralEquirect(nn.Module):
@@ -538,13 +644,20 @@ class TensorNeRF(nn.Module):
         vol = None if self.sampler.alphaMask is None else self.sampler.alphaMask.alpha_volume
         key = (tuple(p._version for p in self.parameters()), id(vol), str(self.get_device()), self.mlp,
                tuple(self.rf.grid_size.tolist()))
-        if self._scene is None or key != self._scene_key:
-            hp = self.model.hyper()
-            hp.update(distance_scale=self.rf.distance_scale, density_shift=self.rf.density_shift, step_ratio=self.rf.step_ratio,
-                      mlp=self.mlp)
+        hp = self.model.hyper()
+        hp.update(distance_scale=self.rf.distance_scale, density_shift=self.rf.density_shift, step_ratio=self.rf.step_ratio,
+                  mlp=self.mlp)
+        norm = lambda v: tuple(v) if isinstance(v, (list, tuple)) else v
+        hkey = tuple(sorted((k, norm(v)) for k, v in hp.items()))
+        fixed = ("distance_scale", "density_shift", "step_ratio", "mlp", "model")     # baked into packed tensors / step count
+        if self._scene is None or key != self._scene_key or any(self._scene.hp.get(k) != hp[k] for k in fixed):
             self._scene = DeviceScene(self.state_dict(), self.rf.aabb, self.sampler.near_far, self.rf.grid_size.tolist(),
                                       alpha_volume=vol, device=self.get_device(), **hp)
-            self._scene_key, self._bufs = key, None
+            self._scene_key, self._hyper_key, self._bufs, self._render_train_bufs = key, hkey, None, None
+        elif hkey != getattr(self, "_hyper_key", None):
+            # calibrated biases / controller-moved ray budgets: scalar fields only, scratch sizes may change
+            self._scene.update_hyper(**{k: v for k, v in hp.items() if k not in fixed})
+            self._hyper_key, self._bufs, self._render_train_bufs = hkey, None, None
         return self._scene
 
     @torch.no_grad()

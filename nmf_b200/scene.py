@@ -119,12 +119,39 @@ class DeviceScene:
         model = self.hp["model"]          # "microfacet" | "plain" | "field" (factors only: plugin-slot field queries)
         s.model = 0 if model == "microfacet" else 1
         if model == "microfacet":
-            g = lambda k: f32(state[k])
+            self._pack_shading(state)
+        elif model == "plain":
+            self._pack_plain_mlp(state)
+        self.c = s
+        self.update_hyper()
+
+        self.set_alpha_volume(alpha_volume)
+        if "bg_module.bg_mat" in state:
+            self._set_env(state, sh_conv)
+
+    def update_hyper(self, **hp):
+        """(Re)sets the scalar hyper-parameters NmfScene carries -- the calibrated biases (models/microfacet.py:79-96) and
+        the ray budgets the adaptive controller moves (models/microfacet.py:241-268) -- without re-packing any tensor.
+        Scratch buffers sized for another max_retrace_rays must be re-created by the caller."""
+        self.hp.update(hp)
+        s = self.c
+        for k in ("diffuse_mul", "diffuse_bias", "tint_bias", "f0_bias", "roughness_bias", "brdf_bias", "anoise"):
+            setattr(s, k, float(self.hp[k]))
+        s.rays_per_ray = int(self.hp["rays_per_ray"])
+        s.max_brdf_rays1 = int(self.hp["max_brdf_rays"][1]) if len(self.hp["max_brdf_rays"]) > 1 else 0
+        s.max_retrace = int(self.hp["max_retrace_rays"][0]) if len(self.hp["max_retrace_rays"]) > 0 else 0
+
+    def _pack_shading(self, state, heads=True, brdf=True):
+        """Material heads (render_modules.py:519-574) and the BRDF MLP (modules/brdf.py:177-261) + the Sobol table."""
+        dev, s = self.device, self.c
+        g = lambda k: torch.as_tensor(state[k]).detach().to(device=dev, dtype=torch.float32).contiguous()
+        if heads:
             hw = torch.cat([g(f"model.diffuse_module.{h}_mlp.0.weight") for h in ("diffuse", "tint", "f0", "roughness")])
             hb = torch.cat([g(f"model.diffuse_module.{h}_mlp.0.bias") for h in ("diffuse", "tint", "f0", "roughness")])
             assert tuple(hw.shape) == (11, 24), hw.shape
             self._ptr(s, "head_w", hw.contiguous())
             self._ptr(s, "head_b", hb.contiguous())
+        if brdf:
             for i, li in enumerate((0, 2, 4)):
                 w, b = g(f"model.brdf.mlp.{li}.weight"), g(f"model.brdf.mlp.{li}.bias")
                 self._ptr(s, f"brdf_w{i}t", w.t().contiguous())
@@ -141,21 +168,25 @@ class DeviceScene:
             if self.hp.get("mlp", "f16") not in ("f16", "fp32"):
                 raise _lib.NmfError("mlp must be 'f16' (tcgen05, fp16 operands / fp32 accumulate) or 'fp32' (SIMT)")
             s.mlp_mode = 0 if self.hp.get("mlp", "f16") == "f16" else 1
-            sob = g("model.brdf_sampler.angs")
-            assert sob.shape[0] >= 400 and sob.shape[1] == 2
-            self._ptr(s, "sobol", sob)
-        elif model == "plain":
-            self._pack_plain_mlp(state)
-        for k in ("diffuse_mul", "diffuse_bias", "tint_bias", "f0_bias", "roughness_bias", "brdf_bias", "anoise"):
-            setattr(s, k, float(self.hp[k]))
-        s.rays_per_ray = int(self.hp["rays_per_ray"])
-        s.max_brdf_rays1 = int(self.hp["max_brdf_rays"][1]) if len(self.hp["max_brdf_rays"]) > 1 else 0
-        s.max_retrace = int(self.hp["max_retrace_rays"][0]) if len(self.hp["max_retrace_rays"]) > 0 else 0
+            if "model.brdf_sampler.angs" in state:
+                sob = g("model.brdf_sampler.angs")
+                assert sob.shape[0] >= 400 and sob.shape[1] == 2
+                self._ptr(s, "sobol", sob)
 
-        self.c = s
-        self.set_alpha_volume(alpha_volume)
-        if "bg_module.bg_mat" in state:
-            self._set_env(state, sh_conv)
+    @classmethod
+    def shading_only(cls, state, device="cuda", heads=True, brdf=True, **hp):
+        """A scene that only carries the material heads and / or the BRDF MLP (the diffuse_module / brdf plugins used on
+        their own: nmf_material_heads, nmf_brdf_mlp).  `state`: reference keys (model.diffuse_module.*, model.brdf.*)."""
+        self = cls.__new__(cls)
+        self.hp = dict(DEFAULT_HP, model="shading")
+        self.hp.update(hp)
+        self.device = torch.device(device)
+        self.keep = {}
+        self.c = _lib.NmfScene()
+        self._pack_shading(state, heads=heads, brdf=brdf)
+        for k in ("diffuse_mul", "diffuse_bias", "tint_bias", "f0_bias", "roughness_bias", "brdf_bias", "anoise"):
+            setattr(self.c, k, float(self.hp[k]))
+        return self
 
     def _put(self, name, t, arr=None, index=None):
         """Keeps `t` under `name`; an existing buffer of the same shape is overwritten in place (its device pointer, which

@@ -168,6 +168,31 @@ def learning_rate_decay(step, lr_init=1.0, lr_final=1e-3, max_steps=30000, lr_de
     return delay * math.exp(t * (math.log(lr_final) - math.log(lr_init)) + math.log(lr_init))
 
 
+@torch.no_grad()
+def calibrate_start(tensorf, args=None, start_density=5e-3, n_density=20000, n_model=100000, generator=None):
+    """The initial calibration of a training run (train.py:403-437, `args.ckpt is None`, num_pretrain = 0):
+      * `rf.calibrate`: density_shift += log(target_sigma) - log(mean density of 20000 random points), with
+        target_sigma = -log(1 - start_density) / (stepsize * distance_scale)            (train.py:403-418)
+      * `model.calibrate(args, xyz, feat, bg_brightness)` on 100000 random points       (train.py:428-437)
+    Field queries and material / BRDF evaluations run on the device through the plugin slots; returns `args`."""
+    dev = tensorf.get_device()
+    rf = tensorf.rf
+    rand = lambda *shape: torch.rand(*shape, device=dev, generator=generator)
+    if getattr(rf, "calibrate", False):
+        xyz = (rand(n_density, 3) * 2 - 1) * rf.aabb[1].reshape(1, 3)
+        sigma_feat = rf.compute_densityfeature(xyz)
+        target_sigma = -math.log(1 - start_density) / (float(tensorf.sampler.stepsize) * rf.distance_scale)
+        rf.density_shift += math.log(target_sigma) - math.log(float(sigma_feat.mean()))
+        if args is not None:
+            args.field.density_shift = rf.density_shift
+    tensorf.sampler.update(rf, init=True)
+    xyz = rand(n_model, 4) * 2 - 1
+    xyz[:, 3] *= 0
+    feat = rf.compute_appfeature(xyz)
+    bg_brightness = tensorf.bg_module.mean_color().detach().mean()
+    return tensorf.model.calibrate(args, xyz, feat, bg_brightness)
+
+
 class FusedAdam:
     """torch.optim.Adam + lr_scheduler.LambdaLR + clip_grad_norm_ as the reference composes them (train.py:443-467,
     752-755), as device updates: one nmf_grad_sq_norm over the flat gradient buffer, then one nmf_adam_step per parameter

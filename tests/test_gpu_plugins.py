@@ -138,3 +138,94 @@ def test_checkpoint_round_trip(model, tmp_path):
     a, _ = t.render_chunks(rays, fix["focal"], chunk=64)
     b, _ = t2.render_chunks(rays, fix["focal"], chunk=64)
     assert torch.allclose(a["rgb_map"], b["rgb_map"], atol=1e-5) and torch.equal(a["surf_width"], b["surf_width"])
+
+
+def test_shading_sub_plugins_and_calibration(model):
+    """model.brdf(...) / model.diffuse_module(...) as free-standing plugin calls (modules/brdf.py:177-261,
+    render_modules.py:519-574) against the oracle, and the start-of-training calibration (train.py:403-437,
+    models/microfacet.py:79-96, render_modules.py:632-642, brdf.py:141-176): after it the mean albedo / roughness / BRDF
+    weight sit at their targets and the fused render picks the new biases up without re-packing the factors."""
+    import math
+    from nmf_b200 import config, train
+    from oracle import nmf_oracle as O
+    fix, osc, _ = model
+    G = fix["grid_size"]                       # its own module instance: the calibration changes biases and budgets
+    t, _ = config.build_model([f"field.grid_size=[{G},{G},{G}]", "model.arch.bg_module.bg_resolution=32"],
+                              aabb=fix["aabb"], near_far=list(fix["near_far"]))
+    t.load_state_dict(fix["state"], strict=False)
+    t = t.cuda().eval()
+    t.sampler.update(t.rf, init=True)
+    t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
+    g = torch.Generator().manual_seed(0)
+    n = 4000
+    feat = (torch.randn(n, 24, generator=g) * 0.3).cuda()
+    a, tint, ex = t.model.diffuse_module(None, None, feat)
+    ra, rt, rf0, rr = O.material_heads(osc, feat.cpu())
+    assert torch.allclose(a.cpu(), ra, atol=2e-6) and torch.allclose(tint.cpu(), rt, atol=2e-6)
+    assert torch.allclose(ex["f0"].cpu(), rf0, atol=2e-6) and torch.allclose(ex["r1"].cpu(), rr[:, :1], atol=2e-6)
+    w = t.model.diffuse_module.roughness_mlp[0]
+    r2 = (torch.sigmoid(feat @ w.weight[1] + w.bias[1] + t.model.diffuse_module.roughness_bias) / 2).clip(1e-2, 1)
+    assert torch.allclose(ex["r2"].reshape(-1), r2, atol=2e-6)
+    unit = lambda v: v / v.norm(dim=-1, keepdim=True)
+    half_l, diff_l = unit(torch.randn(n, 3, generator=g)), unit(torch.randn(n, 3, generator=g))
+    rough = torch.rand(n, generator=g) * 0.49 + 0.01
+    bw = t.model.brdf(None, None, None, None, None, half_l.cuda(), diff_l.cuda(), feat, rough.cuda(), rough.cuda())
+    ref = O.brdf_mlp(osc, feat.cpu(), half_l, diff_l, rough.reshape(-1, 1))
+    assert (bw.cpu() - ref).abs().max() < 1e-3 and (bw.cpu() - ref).abs().mean() < 1e-4
+    # ---- calibration ----
+    rays = fix["rays"][:128].cuda()
+    before, _ = t(rays, fix["focal"])
+    before = before["rgb_map"].clone()
+    t._calls = 0
+    sc0 = t.scene()
+    args = config.compose([])
+    shift0 = t.rf.density_shift
+    t.rf.calibrate = True
+    args = train.calibrate_start(t, args, start_density=5e-3, generator=torch.Generator(device="cuda").manual_seed(1))
+    assert args.model.arch.model.brdf.bias == t.model.brdf.bias and args.field.density_shift == t.rf.density_shift
+    assert t.rf.density_shift != shift0
+    xyz = (torch.rand(20000, 3, device="cuda") * 2 - 1) * t.rf.aabb[1].reshape(1, 3)
+    sig = t.rf.compute_densityfeature(xyz)
+    alpha = 1 - torch.exp(-sig.mean() * float(t.sampler.stepsize) * t.rf.distance_scale)
+    assert abs(float(alpha) - 5e-3) < 5e-4                        # mean density at the start_density target
+    bright = float(t.bg_module.mean_color().mean())
+    feat2 = t.rf.compute_appfeature(torch.cat([torch.rand(50000, 3, device="cuda") * 2 - 1, torch.zeros(50000, 1, device="cuda")], 1))
+    a2, _, ex2 = t.model.diffuse_module(None, None, feat2)
+    inv = lambda x: (x / (1 - x)).log()
+    target = min(0.5 / bright, 0.999)
+    assert abs(float(inv(a2.clip(1e-6, 1 - 1e-6)).mean()) - math.log(target / (1 - target))) < 0.05
+    assert abs(float(inv((ex2["r1"] + ex2["r2"]) / 4).mean()) - math.log(0.35 / 0.65)) < 0.05
+    after, _ = t(rays, fix["focal"])
+    assert not torch.allclose(after["rgb_map"], before, atol=1e-3)      # new biases and density shift reach the kernels
+    # the adaptive retrace controller (models/microfacet.py:241-268) moves the budget; the scene only patches scalars
+    sc1 = t.scene()
+    t.model.update_n_samples([20000])
+    assert t.model.max_retrace_rays != [1000]
+    sc2 = t.scene()
+    assert sc2 is sc1 and sc2.c.max_retrace == t.model.max_retrace_rays[0]
+    ims, st = t(rays, fix["focal"])
+    nre = st["n_retrace"][0] if isinstance(st["n_retrace"], (list, tuple)) else st["n_retrace"]
+    assert nre <= t.model.max_retrace_rays[0]
+    t.model.reset_counter()
+    assert t.model.max_retrace_rays == [1000] and t.scene().c.max_retrace == 1000
+
+
+def test_calibrate_matches_reference_biases(model):
+    """RandHydraMLPDiffuse.calibrate / MLPBRDF.calibrate against the biases the unmodified reference arrives at on the same
+    weights and features (tests/golden/controller.pt; the BRDF calibration draws random directions on both sides, so it
+    is compared as a Monte-Carlo estimate)."""
+    from nmf_b200 import plugins
+    gold = load_fixture("controller")
+    h = gold["heads_calibrate"]
+    d = plugins.RandHydraMLPDiffuse(in_channels=24, diffuse_bias=h["diffuse_bias0"], roughness_bias=h["roughness_bias0"]).cuda()
+    d.load_state_dict(h["state"])
+    d.calibrate(torch.tensor(h["brightness"]), True, h["xyz"].cuda(), None, h["feat"].cuda())
+    assert abs(d.diffuse_bias - h["diffuse_bias"]) < 2e-4 and abs(d.roughness_bias - h["roughness_bias"]) < 2e-4
+    b = gold["brdf_calibrate"]
+    brdf = plugins.MLPBRDF(in_channels=24, h_encoder=plugins.ListISH([0, 1, 2, 4]), d_encoder=plugins.ListISH([0, 1, 2, 4]),
+                           bias=b["bias0"]).cuda()
+    brdf.load_state_dict(b["state"])
+    assert brdf.init_val == b["init_val"]
+    torch.manual_seed(3)
+    brdf.calibrate(h["feat"].cuda(), torch.tensor(h["brightness"]))
+    assert abs(brdf.bias - b["bias"]) < 0.05, (brdf.bias, b["bias"])

@@ -178,3 +178,24 @@ def test_flat_gradient_bucket_allreduce(tmp_path):
     assert g["n"] == 15 + 7 + 1
     assert torch.allclose(g["a"], torch.full((5, 3), 1.5)) and torch.allclose(g["b"], torch.full((7,), 1.5))
     assert abs(float(g["c"]) - 3.0) < 1e-12
+
+
+def test_microfacet_training_state_matches_reference():
+    """Host-side training state of the model slot against vectors recorded from the unmodified reference
+    (oracle/make_golden_controller.py): the adaptive retrace controller (models/microfacet.py:236-268) and the
+    min_rough / std / detach_N schedule (models/microfacet.py:112-121)."""
+    from nmf_b200 import config
+    gold = load_fixture("controller")
+    t, _ = config.build_model(["field.grid_size=[16,16,16]", "model.arch.bg_module.bg_resolution=16"])
+    m = t.model
+    for n, want in zip(gold["controller"]["inputs"], gold["controller"]["max_retrace_rays"]):
+        m.update_n_samples(n)
+        assert m.max_retrace_rays == want, (n, m.max_retrace_rays, want)
+    m.update_n_samples([1, 2])                      # wrong length: ignored, as in the reference
+    assert m.max_retrace_rays == gold["controller"]["max_retrace_rays"][-1]
+    m.reset_counter()
+    assert m.max_retrace_rays == gold["after_reset"] and m.ratio_list is None
+    m.min_rough, m.min_rough_decay, m.std, m.std_decay, m.detach_N_iters, m.detach_N = 0.3, 0.9, 0.2, 0.5, 25, True
+    for it, (mr, std, dn) in enumerate(gold["schedule"]):
+        m.check_schedule(it, 1)
+        assert abs(m.min_rough - mr) < 1e-12 and abs(m.std - std) < 1e-12 and m.detach_N == dn, it
