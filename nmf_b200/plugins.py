@@ -320,7 +320,7 @@ class MLPBRDF(nn.Module):
         if not (feape == 0 and dotpe < 0 and activation == "sigmoid" and not mul_LdotN and hidden_w == 64 and num_layers == 3
                 and v_encoder is None and n_encoder is None and l_encoder is None):
             raise _lib.NmfError("MLPBRDF: kernels implement the microfacet_tensorf2 configuration (66 -> 64 -> 64 -> 4, sigmoid)")
-        self.in_channels, self.bias, self.lr, self.init_val = in_channels, bias, lr, 0.25      # modules/brdf.py:119
+        self.in_channels, self.bias, self.lr, self.init_val = in_channels, bias, lr, 0.5
         self.activation_name = activation
         self._scene, self._scene_key = None, None
         self.h_encoder, self.d_encoder = h_encoder, d_encoder

@@ -181,20 +181,25 @@ def test_shading_sub_plugins_and_calibration(model):
     args = config.compose([])
     shift0 = t.rf.density_shift
     t.rf.calibrate = True
+    # train.py:403-418: density_shift += log(target_sigma) - log(mean density of 20000 random points) (the reference's
+    # formula "assumes exponential activation": with softplus it moves towards the target, it does not land on it)
+    g1 = torch.Generator(device="cuda").manual_seed(1)
+    xyz = (torch.rand(20000, 3, device="cuda", generator=g1) * 2 - 1) * t.rf.aabb[1].reshape(1, 3)
+    sigma0 = float(t.rf.compute_densityfeature(xyz).mean())
+    target_sigma = -math.log(1 - 5e-3) / (float(t.sampler.stepsize) * t.rf.distance_scale)
     args = train.calibrate_start(t, args, start_density=5e-3, generator=torch.Generator(device="cuda").manual_seed(1))
     assert args.model.arch.model.brdf.bias == t.model.brdf.bias and args.field.density_shift == t.rf.density_shift
-    assert t.rf.density_shift != shift0
-    xyz = (torch.rand(20000, 3, device="cuda") * 2 - 1) * t.rf.aabb[1].reshape(1, 3)
-    sig = t.rf.compute_densityfeature(xyz)
-    alpha = 1 - torch.exp(-sig.mean() * float(t.sampler.stepsize) * t.rf.distance_scale)
-    assert abs(float(alpha) - 5e-3) < 5e-4                        # mean density at the start_density target
-    bright = float(t.bg_module.mean_color().mean())
+    assert abs(t.rf.density_shift - (shift0 + math.log(target_sigma) - math.log(sigma0))) < 1e-5
+    assert float(t.rf.compute_densityfeature(xyz).mean()) < sigma0        # the shifted field is thinner, as intended
+    bright = float(t.bg_module.mean_color().detach().mean())
     feat2 = t.rf.compute_appfeature(torch.cat([torch.rand(50000, 3, device="cuda") * 2 - 1, torch.zeros(50000, 1, device="cuda")], 1))
     a2, _, ex2 = t.model.diffuse_module(None, None, feat2)
     inv = lambda x: (x / (1 - x)).log()
     target = min(0.5 / bright, 0.999)
     assert abs(float(inv(a2.clip(1e-6, 1 - 1e-6)).mean()) - math.log(target / (1 - target))) < 0.05
-    assert abs(float(inv((ex2["r1"] + ex2["r2"]) / 4).mean()) - math.log(0.35 / 0.65)) < 0.05
+    # (the roughness bias takes the reference's single additive step, render_modules.py:640-642, which is exact only in
+    # the logit domain of the un-halved value: its result is pinned by test_calibrate_matches_reference_biases)
+    assert t.model.diffuse_module.roughness_bias != -1
     after, _ = t(rays, fix["focal"])
     assert not torch.allclose(after["rgb_map"], before, atol=1e-3)      # new biases and density shift reach the kernels
     # the adaptive retrace controller (models/microfacet.py:241-268) moves the budget; the scene only patches scalars
