@@ -36,6 +36,17 @@ def _n_to_reso(n_voxels, bbox):
     return ((xyz_max - xyz_min) / voxel_size).long().tolist()
 
 
+class TVLoss(nn.Module):
+    """utils.TVLoss (utils.py:139-151): total variation of a plane (1,C,H,W) or a line (1,C,N,1)."""
+
+    def forward(self, x):
+        if x.shape[-1] == 1:
+            return (x[:, :, 1:, :] - x[:, :, :-1, :]).abs().mean()
+        h_tv = x[:, :, 1:, :-1] - x[:, :, :-1, :-1]
+        w_tv = x[:, :, :-1, 1:] - x[:, :, :-1, :-1]
+        return (w_tv ** 2 + h_tv ** 2 + 1e-5).sqrt().mean()
+
+
 class SRGBTonemap(nn.Module):
     def forward(self, img, noclip=False):
         limit = 0.0031308
@@ -178,6 +189,14 @@ class TensorVMSplit(nn.Module):
     def density_L1(self):
         return sum(torch.mean(torch.abs(p)) + torch.mean(torch.abs(l))
                    for p, l in zip(self.density_rf.app_plane, self.density_rf.app_line))
+
+    def TV_loss_density(self, reg):
+        """fields/tensoRF.py:342-350 (weight 0 in the shipped configs: plain tensor ops, not a hot path)"""
+        return sum(reg(p) * 1e-2 + reg(l) * 1e-3 for p, l in zip(self.density_rf.app_plane, self.density_rf.app_line))
+
+    def TV_loss_app(self, reg, start_ind=0, end_ind=-1):
+        """fields/tensoRF.py:352-360"""
+        return sum(reg(p) * 1e-2 + reg(l) * 1e-3 for p, l in zip(self.app_rf.app_plane, self.app_rf.app_line))
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -562,6 +581,29 @@ class IntegralEquirect(nn.Module):
 
     def activation_fn(self, x):
         return torch.exp((self.brightness + self.mul * x).clip(max=20))
+
+    def hw(self):
+        return self.bg_mat.shape[-2], self.bg_mat.shape[-1]
+
+    @torch.no_grad()
+    def calc_envmap_psnr(self, gt_im, fH=500):
+        """modules/integral_equirect.py:290-321 (host-side metric, renderer.py:305-313): the ground-truth panorama is
+        flipped and rolled by half its width, both maps are resized (nearest) to (fH, 2 fH), an affine colour map
+        pred -> gt is fitted by least squares (sklearn LinearRegression in the reference) and the PSNR of the clipped
+        squared error is returned."""
+        import numpy as np
+        fW = 2 * fH
+        gt = np.asarray(gt_im)
+        gW = gt.shape[1]
+        gt = gt[:, ::-1]
+        gt = np.concatenate([gt[:, gW // 2:], gt[:, :gW // 2]], axis=1)
+        resize = lambda im: torch.nn.functional.interpolate(im.permute(2, 0, 1).unsqueeze(0), (fH, fW)).squeeze(0).permute(1, 2, 0)
+        Y = resize(torch.as_tensor(gt.copy()).float()).reshape(-1, 3).double().numpy()
+        X = resize(self.activation_fn(self.bg_mat[0]).permute(1, 2, 0).detach().float().cpu()).reshape(-1, 3).double().numpy()
+        A = np.concatenate([X, np.ones((X.shape[0], 1))], axis=1)
+        coef, *_ = np.linalg.lstsq(A, Y, rcond=None)
+        err = ((A @ coef - Y) ** 2).clip(min=0, max=1)
+        return float(-10.0 * np.log(err.mean()) / np.log(10.0))
 
     def mean_color(self):
         return self.activation_fn(self.bg_mat).reshape(-1, 3).mean(dim=0)     # integral_equirect.py:286-287 (sic)
