@@ -467,7 +467,12 @@ class PlainTrainer:
         h = self.hparams
         n_iters = h["n_iters"] if n_iters is None else n_iters
         allrays, allrgbs = allrays.to(self.device), allrgbs.to(self.device)
-        sampler = RayIdSampler(allrays.shape[0], h["batch_size"], self.device, seed=self.seed)
+        import torch.distributed as dist
+        on = dist.is_available() and dist.is_initialized()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+        # ray-sharded training: every rank draws its own ray ids (seed + rank) and runs the same number of
+        # iterations; the loss normaliser is the global lbatch_size
+        sampler = RayIdSampler(allrays.shape[0], h["batch_size"], self.device, seed=self.seed + 1000003 * rank)
         num_rays, prev = h["starting_batch_size"], None
         history = []
         for it in range(n_iters):
@@ -486,7 +491,7 @@ class PlainTrainer:
                 ratio = out["n_rays"] / max(out["n_samples"], 1)                       # train.py:616-626
                 prev = ratio if prev is None else min(0.1 * ratio + 0.9 * prev, ratio)
                 num_rays = int(prev * h["target_num_samples"] + 1)
-            self.apply(kept, loss, normaliser=lbatch)
+            self.apply(kept, loss, normaliser=lbatch * world)
             rec = dict(iteration=it, lbatch_size=lbatch, sub_batches=subs, kept_rays=kept, n_samples=samples,
                        mse=loss / max(3.0 * kept, 1.0), next_num_rays=num_rays, lr_factor=self.optimizer.lr_factor(),
                        grid=list(self.meta["grid_size"]))
