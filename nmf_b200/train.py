@@ -424,13 +424,15 @@ class PlainTrainer:
     def apply(self, n_rays_local, loss_local=0.0, normaliser=None):
         """clip_grad_norm_ + optimizer.step() + scheduler.step() (train.py:752-755) on the accumulated gradients, after
         the ONE flat all-reduce of ray-sharded training; the loss normaliser 1 / lbatch_size (train.py:709) is applied
-        inside the fused update.  normaliser=None: the global number of kept rays."""
+        inside the fused update.  normaliser: this rank's lbatch_size (summed over the ranks); None: the global number of
+        kept rays."""
         import torch.distributed as dist
-        tot = torch.tensor([float(n_rays_local), float(loss_local)], device=self.device, dtype=torch.float64)
+        tot = torch.tensor([float(n_rays_local), float(loss_local), float(normaliser or 0.0)], device=self.device,
+                           dtype=torch.float64)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(tot)                              # global ray count = the loss normaliser
+            dist.all_reduce(tot)                              # global ray count / global lbatch_size = the loss normaliser
         self.bucket.allreduce(scale=1.0)                      # one flat fp32 all-reduce (NCCL on GPUs)
-        norm = float(tot[0]) if normaliser is None else float(normaliser)
+        norm = float(tot[0]) if normaliser is None else float(tot[2])
         self.optimizer.step(grad_scale=1.0 / max(norm, 1.0))
         self.repack(rebuild=False)
         self.iteration += 1
@@ -491,7 +493,7 @@ class PlainTrainer:
                 ratio = out["n_rays"] / max(out["n_samples"], 1)                       # train.py:616-626
                 prev = ratio if prev is None else min(0.1 * ratio + 0.9 * prev, ratio)
                 num_rays = int(prev * h["target_num_samples"] + 1)
-            self.apply(kept, loss, normaliser=lbatch * world)
+            self.apply(kept, loss, normaliser=lbatch)          # summed over the ranks inside
             rec = dict(iteration=it, lbatch_size=lbatch, sub_batches=subs, kept_rays=kept, n_samples=samples,
                        mse=loss / max(3.0 * kept, 1.0), next_num_rays=num_rays, lr_factor=self.optimizer.lr_factor(),
                        grid=list(self.meta["grid_size"]))
