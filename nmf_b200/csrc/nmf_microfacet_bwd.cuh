@@ -1,0 +1,138 @@
+// Per-element backward math of the MICROFACET model (remainder) -- first stage:
+// the pieces whose gradient can be stated per bounce ray / per sample, compiled for the host (tests/hostcheck) and checked
+// against the oracle's autograd (= the reference's gradient, oracle/check_train.py) in the CPU suite.  No kernel
+// includes this header yet: the reverse-pass kernels that will call it are the next step, this file fixes their math.
+//
+//   nmf_ggx_sample_dr     d L / d roughness and d H / d roughness of the GGX VNDF sample (brdf_samplers/ggx.py:61-226):
+//                         forward-mode (dual-number) restatement of nmf_ggx_frame + nmf_ggx_sample_f.  The reference
+//                         detaches `a = 1 / (1 + Vs.z)` (ggx.py:116) and evaluates the pdf under no_grad (ggx.py:218),
+//                         so the mip level of the environment lookup carries NO roughness gradient.
+//   nmf_fresnel_mix_bwd   comb = F * L_in * brdf + (1 - F) * diffuse, F = R0 + (1 - R0) (1 - |v.h|)^5
+//                         (models/microfacet.py:565-613)
+//   nmf_heads_bwd         the sigmoid material heads on the 24-d feature with their clip gates
+//                         (modules/render_modules.py:553-560)
+#pragma once
+#include "nmf_math.cuh"
+
+// ---- minimal forward-mode AD: value + derivative w.r.t. ONE scalar (the sample's roughness) ----
+struct NmfDual { float v, d; };
+NMF_HD NmfDual nmf_dk(float c) { NmfDual r; r.v = c; r.d = 0.f; return r; }
+NMF_HD NmfDual nmf_dmk(float v, float d) { NmfDual r; r.v = v; r.d = d; return r; }
+NMF_HD NmfDual operator+(NmfDual a, NmfDual b) { return nmf_dmk(a.v + b.v, a.d + b.d); }
+NMF_HD NmfDual operator-(NmfDual a, NmfDual b) { return nmf_dmk(a.v - b.v, a.d - b.d); }
+NMF_HD NmfDual operator*(NmfDual a, NmfDual b) { return nmf_dmk(a.v * b.v, a.d * b.v + a.v * b.d); }
+NMF_HD NmfDual operator/(NmfDual a, NmfDual b) { return nmf_dmk(a.v / b.v, (a.d * b.v - a.v * b.d) / (b.v * b.v)); }
+NMF_HD NmfDual operator*(float a, NmfDual b) { return nmf_dmk(a * b.v, a * b.d); }
+NMF_HD NmfDual operator*(NmfDual a, float b) { return nmf_dmk(a.v * b, a.d * b); }
+// sqrt(max(x, floor)): torch.clip passes no gradient below the floor
+NMF_HD NmfDual nmf_dsqrt_floor(NmfDual x, float floor_) {
+  if (x.v > floor_) { const float s = sqrtf(x.v); return nmf_dmk(s, x.d / (2.0f * s)); }
+  return nmf_dk(sqrtf(floor_));
+}
+struct NmfDual3 { NmfDual x, y, z; };
+NMF_HD NmfDual3 nmf_d3(NmfDual x, NmfDual y, NmfDual z) { NmfDual3 r; r.x = x; r.y = y; r.z = z; return r; }
+NMF_HD NmfDual3 nmf_d3k(nmf_v3 v) { return nmf_d3(nmf_dk(v.x), nmf_dk(v.y), nmf_dk(v.z)); }
+NMF_HD NmfDual nmf_ddot(NmfDual3 a, NmfDual3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+NMF_HD NmfDual3 nmf_dcross(NmfDual3 a, NmfDual3 b) {
+  return nmf_d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+NMF_HD NmfDual3 nmf_dscale(NmfDual3 a, NmfDual s) { return nmf_d3(a.x * s, a.y * s, a.z * s); }
+NMF_HD NmfDual3 nmf_dadd(NmfDual3 a, NmfDual3 b) { return nmf_d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+NMF_HD NmfDual3 nmf_dunit(NmfDual3 v) {                      // v / sqrt(max(|v|^2, eps))  (nmf_unit)
+  const NmfDual n = nmf_dsqrt_floor(nmf_ddot(v, v), NMF_EPS);
+  return nmf_d3(v.x / n, v.y / n, v.z / n);
+}
+
+struct NmfGGXdr {
+  nmf_v3 L, dL;        // outgoing direction and d L / d roughness
+  nmf_v3 H, dH;        // normalize((V + L) / 2) (models/microfacet.py:388) and its derivative
+};
+// V: unit vector to the viewer, N: normal flipped to V's side and DETACHED (Microfacet.detach_N, microfacet.py:352-353;
+// with detach_N off the normal's own gradient is a separate path), r: roughness of the sample (r2 = r1).
+NMF_HD NmfGGXdr nmf_ggx_sample_dr(float u1, float u2, nmf_v3 V, nmf_v3 N, float r_) {
+  const NmfDual r = nmf_dmk(r_, 1.0f);
+  const nmf_v3 up = (fabsf(N.z) < 0.999f) ? nmf_mk3(0.f, 0.f, 1.f) : nmf_mk3(-1.f, 0.f, 0.f);
+  const nmf_v3 t = nmf_unit(nmf_cross(up, N));
+  const nmf_v3 b = nmf_unit(nmf_cross(N, t));
+  const nmf_v3 V_l = nmf_mk3(nmf_dot(t, V), nmf_dot(b, V), nmf_dot(N, V));
+  const NmfDual3 Vs = nmf_dunit(nmf_d3(r * V_l.x, r * V_l.y, nmf_dk(V_l.z)));
+  const NmfDual3 zup = nmf_d3k(nmf_mk3(0.f, 0.f, 1.f));
+  const NmfDual3 T1 = (Vs.z.v < 0.999f) ? nmf_dunit(nmf_dcross(Vs, zup)) : nmf_d3k(nmf_mk3(-1.f, 0.f, 0.f));
+  const NmfDual3 T2 = nmf_dunit(nmf_dcross(T1, Vs));
+  const float a = fminf(1.0f / fmaxf(1.0f + Vs.z.v, 1e-8f), 1e4f);          // detached (ggx.py:116)
+  const float rad = sqrtf(u1);
+  const bool lo = u2 < a;
+  const float phi = lo ? (u2 / a * NMF_PI) : ((u2 - a) / (1.0f - a) * NMF_PI + NMF_PI);
+  const float pm = fmodf(phi, 100.0f * NMF_PI);
+  const NmfDual P1 = nmf_dk(rad * cosf(pm));
+  const NmfDual P2 = lo ? nmf_dk(rad * sinf(pm)) : (rad * sinf(pm)) * Vs.z;
+  const NmfDual c = nmf_dsqrt_floor(nmf_dk(1.0f) - P1 * P1 - P2 * P2, NMF_EPS);
+  const NmfDual3 Ns = nmf_dadd(nmf_dadd(nmf_dscale(T1, P1), nmf_dscale(T2, P2)), nmf_dscale(Vs, c));
+  const NmfDual3 H_l = nmf_dunit(nmf_d3(Ns.x * r, Ns.y * r, Ns.z));
+  const NmfDual3 Hs = nmf_dadd(nmf_dadd(nmf_dscale(nmf_d3k(t), H_l.x), nmf_dscale(nmf_d3k(b), H_l.y)), nmf_dscale(nmf_d3k(N), H_l.z));
+  const NmfDual3 Vd = nmf_d3k(V);
+  const NmfDual vh = nmf_ddot(Vd, Hs);
+  NmfDual3 L = nmf_dunit(nmf_d3(2.0f * vh * Hs.x - Vd.x, 2.0f * vh * Hs.y - Vd.y, 2.0f * vh * Hs.z - Vd.z));
+  if (!(L.x.v * N.x + L.y.v * N.y + L.z.v * N.z > 0.0f)) L = nmf_dscale(L, nmf_dk(-1.0f));
+  const NmfDual3 H2 = nmf_dunit(nmf_d3((Vd.x + L.x) * 0.5f, (Vd.y + L.y) * 0.5f, (Vd.z + L.z) * 0.5f));
+  NmfGGXdr o;
+  o.L = nmf_mk3(L.x.v, L.y.v, L.z.v);
+  o.dL = nmf_mk3(L.x.d, L.y.d, L.z.d);
+  o.H = nmf_mk3(H2.x.v, H2.y.v, H2.z.v);
+  o.dH = nmf_mk3(H2.x.d, H2.y.d, H2.z.d);
+  return o;
+}
+
+// comb_c = F_c * inc_c * bw_c + (1 - F_c) * diff_c,  F_c = R0_c + (1 - R0_c) * m^5,  m = clip(1 - cost, 0, 1),
+// cost = |v . h|  (models/microfacet.py:584-600).  g = d loss / d comb.  Returns d loss / d cost.
+NMF_HD float nmf_fresnel_mix_bwd(const float* R0, float cost, const float* inc, const float* bw, const float* diff, const float* g,
+                                 float* dR0, float* dinc, float* dbw, float* ddiff) {
+  const float m = nmf_clampf(1.0f - cost, 0.0f, 1.0f);
+  const float m2 = m * m, m5 = m2 * m2 * m, m4 = m2 * m2;
+  const bool open = (1.0f - cost) >= 0.0f && (1.0f - cost) <= 1.0f;       // torch.clip passes the gradient on the closed interval
+  float dcost = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    const float F = R0[c] + (1.0f - R0[c]) * m5;
+    const float dF = g[c] * (inc[c] * bw[c] - diff[c]);
+    dR0[c] = dF * (1.0f - m5);
+    dinc[c] = g[c] * F * bw[c];
+    dbw[c] = g[c] * F * inc[c];
+    ddiff[c] = g[c] * (1.0f - F);
+    if (open) dcost -= dF * (1.0f - R0[c]) * 5.0f * m4;
+  }
+  return dcost;
+}
+
+// Material heads (render_modules.py:553-560) on one sample: albedo_c = clip(sigmoid(mul * lin_c + bias_d), 0, 1),
+// f0_c = sigmoid(lin_{6+c} + bias_f), r = clip(sigmoid(lin_9 + bias_r) / 2, 1e-2, 1) with lin = W feat + b
+// (W rows: diffuse 0..2, tint 3..5, f0 6..8, roughness 9..10).  Upstream: g_albedo[3], g_f0[3], g_rough.
+// Accumulates dW (11 x 24), db (11) and writes dfeat (24).  The tint head and r2 feed nothing on this path.
+NMF_HD void nmf_heads_bwd(const float* feat, const float* W, const float* b, float diffuse_mul, float diffuse_bias, float f0_bias,
+                          float roughness_bias, const float* g_albedo, const float* g_f0, float g_rough, float* dW, float* db,
+                          float* dfeat) {
+  float dlin[11];
+  for (int h = 0; h < 11; ++h) dlin[h] = 0.f;
+  float lin[11];
+  for (int h = 0; h < 11; ++h) {
+    float v = b[h];
+    for (int k = 0; k < 24; ++k) v += W[h * 24 + k] * feat[k];
+    lin[h] = v;
+  }
+  for (int c = 0; c < 3; ++c) {
+    const float sa = nmf_sigmoid(diffuse_mul * lin[c] + diffuse_bias);
+    dlin[c] = (sa >= 0.f && sa <= 1.f) ? g_albedo[c] * sa * (1.0f - sa) * diffuse_mul : 0.f;
+    const float sf = nmf_sigmoid(lin[6 + c] + f0_bias);
+    dlin[6 + c] = g_f0[c] * sf * (1.0f - sf);
+  }
+  const float sr = nmf_sigmoid(lin[9] + roughness_bias);
+  dlin[9] = (sr / 2.0f >= 1e-2f && sr / 2.0f <= 1.0f) ? g_rough * 0.5f * sr * (1.0f - sr) : 0.f;
+  for (int k = 0; k < 24; ++k) dfeat[k] = 0.f;
+  for (int h = 0; h < 11; ++h) {
+    if (dlin[h] == 0.f) continue;
+    db[h] += dlin[h];
+    for (int k = 0; k < 24; ++k) {
+      dW[h * 24 + k] += dlin[h] * feat[k];
+      dfeat[k] += dlin[h] * W[h * 24 + k];
+    }
+  }
+}

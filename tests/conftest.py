@@ -46,6 +46,7 @@ def hostcheck():
     so = os.path.join(d, "libnmf_hostcheck.so")
     srcs = [os.path.join(d, "hostcheck.cpp"), os.path.join(ROOT, "nmf_b200", "csrc", "nmf_math.cuh"),
             os.path.join(ROOT, "nmf_b200", "csrc", "nmf_field.cuh"), os.path.join(ROOT, "nmf_b200", "csrc", "nmf_train.cuh"),
+            os.path.join(ROOT, "nmf_b200", "csrc", "nmf_microfacet_bwd.cuh"),
             os.path.join(ROOT, "include", "nmf_b200.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, srcs[0]])

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "../../nmf_b200/csrc/nmf_train.cuh"
+#include "../../nmf_b200/csrc/nmf_microfacet_bwd.cuh"
 
 extern "C" {
 
@@ -287,6 +288,31 @@ double hc_l1(const float* p, int n, float coef, float* g) {
   double s = 0.0;
   for (int i = 0; i < n; ++i) { s += fabs((double)p[i]); g[i] += nmf_l1_grad(p[i], coef); }
   return s;
+}
+
+// microfacet backward, first stage (csrc/nmf_microfacet_bwd.cuh)
+void hc_ggx_dr(const float* u, const float* V, const float* N, const float* r, int n, float* L, float* dL, float* H, float* dH) {
+  for (int i = 0; i < n; ++i) {
+    const NmfGGXdr g = nmf_ggx_sample_dr(u[2 * i], u[2 * i + 1], nmf_mk3(V[3 * i], V[3 * i + 1], V[3 * i + 2]),
+                                         nmf_mk3(N[3 * i], N[3 * i + 1], N[3 * i + 2]), r[i]);
+    L[3 * i] = g.L.x; L[3 * i + 1] = g.L.y; L[3 * i + 2] = g.L.z;
+    dL[3 * i] = g.dL.x; dL[3 * i + 1] = g.dL.y; dL[3 * i + 2] = g.dL.z;
+    H[3 * i] = g.H.x; H[3 * i + 1] = g.H.y; H[3 * i + 2] = g.H.z;
+    dH[3 * i] = g.dH.x; dH[3 * i + 1] = g.dH.y; dH[3 * i + 2] = g.dH.z;
+  }
+}
+void hc_fresnel_mix_bwd(const float* R0, const float* cost, const float* inc, const float* bw, const float* diff, const float* g, int n,
+                        float* dR0, float* dinc, float* dbw, float* ddiff, float* dcost) {
+  for (int i = 0; i < n; ++i)
+    dcost[i] = nmf_fresnel_mix_bwd(R0 + 3 * i, cost[i], inc + 3 * i, bw + 3 * i, diff + 3 * i, g + 3 * i, dR0 + 3 * i, dinc + 3 * i,
+                                   dbw + 3 * i, ddiff + 3 * i);
+}
+void hc_heads_bwd(const float* feat, const float* W, const float* b, float diffuse_mul, float diffuse_bias, float f0_bias,
+                  float roughness_bias, const float* g_albedo, const float* g_f0, const float* g_rough, int n, float* dW, float* db,
+                  float* dfeat) {
+  for (int i = 0; i < n; ++i)
+    nmf_heads_bwd(feat + 24 * i, W, b, diffuse_mul, diffuse_bias, f0_bias, roughness_bias, g_albedo + 3 * i, g_f0 + 3 * i, g_rough[i],
+                  dW, db, dfeat + 24 * i);
 }
 
 void hc_upsample(const float* src, int C, int H, int W, float* dst, int H2, int W2) {

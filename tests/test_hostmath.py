@@ -339,3 +339,92 @@ def test_learning_rate_decay_is_the_reference_formula():
         got = train.learning_rate_decay(step, max_steps=30000, **train.REFERENCE_PARAMS)
         assert abs(got - want) < 1e-12
     assert train.learning_rate_decay(7, lr_init=2.0, lr_final=2.0, max_steps=10) == pytest.approx(2.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# microfacet backward, first stage (csrc/nmf_microfacet_bwd.cuh) against the oracle's autograd
+# ---------------------------------------------------------------------------------------------------------------
+def _ggx_inputs(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    N = O.unit(torch.randn(n, 3, generator=g))
+    N[:4] = torch.tensor([[0.0, 0.0, 1.0], [0.0, 0.0, -1.0], [0.02, 0.0, 0.9998], [1.0, 0.0, 0.0]])   # frame switch at |n_z| >= 0.999
+    V = O.unit(torch.randn(n, 3, generator=g))
+    V = torch.where((V * N).sum(-1, keepdim=True) < 0, -V, V)            # the shaded normal faces the viewer (microfacet.py:354-356)
+    r = torch.rand(n, 1, generator=g) * 0.49 + 0.01
+    r[:8] = 0.01                                                           # roughness at its clip
+    u = torch.rand(n, 2, generator=g)
+    return u, V, N, r
+
+
+def test_ggx_roughness_derivative_matches_autograd(hostcheck):
+    """d L / d roughness and d H / d roughness of the GGX VNDF sample (brdf_samplers/ggx.py:61-226 with its detach points)
+    as forward-mode arithmetic, against torch autograd through the oracle's ggx_sample (one bounce ray per row)."""
+    n = 4000
+    u, V, N, r = _ggx_inputs(n, 7)
+    rr = r.clone().requires_grad_(True)
+    L, cols, _ = O.ggx_sample(u[:, :1], u[:, 1:], V, N, rr, torch.ones(n, 1, dtype=torch.bool))
+    H = O.unit((V + L) / 2)
+    want_dL = torch.stack([torch.autograd.grad(L[:, c].sum(), rr, retain_graph=True)[0].reshape(-1) for c in range(3)], dim=1)
+    want_dH = torch.stack([torch.autograd.grad(H[:, c].sum(), rr, retain_graph=True)[0].reshape(-1) for c in range(3)], dim=1)
+    oL, odL, oH, odH = (torch.zeros(n, 3) for _ in range(4))
+    hostcheck.hc_ggx_dr(ptr(u.contiguous()), ptr(V.contiguous()), ptr(N.contiguous()), ptr(r.reshape(-1).contiguous()), n,
+                        ptr(oL), ptr(odL), ptr(oH), ptr(odH))
+    assert (oL - L.detach()).abs().max() < 2e-5 and (oH - H.detach()).abs().max() < 2e-5
+    # derivatives are O(1 / roughness): relative tolerance on the vector, a handful of samples sit on a branch
+    # (u2 at the disk split, L on the horizon) where fp32 rounding picks the other side
+    for got, want in ((odL, want_dL), (odH, want_dH)):
+        err = (got - want).norm(dim=1) / (want.norm(dim=1) + 1e-2)
+        assert (err < 2e-3).float().mean() > 0.995, float((err < 2e-3).float().mean())
+        assert float(err.median()) < 1e-5
+    assert float(want_dL.norm(dim=1).median()) > 0.1               # the derivative is not trivially zero
+
+
+def test_fresnel_mix_backward_matches_autograd(hostcheck):
+    """models/microfacet.py:584-600: comb = F L_in brdf + (1 - F) diffuse with F = R0 + (1 - R0) clip(1 - |v.h|, 0, 1)^5"""
+    g = torch.Generator().manual_seed(2)
+    n = 3000
+    leaf = lambda *s: torch.rand(*s, generator=g).requires_grad_(True)
+    R0, inc, bw, diff, cost = leaf(n, 3), leaf(n, 3), leaf(n, 3), leaf(n, 3), leaf(n, 1)
+    with torch.no_grad():
+        cost[:5] = torch.tensor([[0.0], [1.0], [1e-8], [0.5], [0.999]])
+    up = torch.randn(n, 3, generator=g)
+    fres = R0 + (1 - R0) * (1 - cost).clip(min=0, max=1) ** 5
+    comb = fres * inc * bw + (1 - fres) * diff
+    (comb * up).sum().backward()
+    outs = [torch.zeros(n, 3) for _ in range(4)] + [torch.zeros(n)]
+    c = lambda t: t.detach().contiguous()
+    hostcheck.hc_fresnel_mix_bwd(ptr(c(R0)), ptr(c(cost).reshape(-1)), ptr(c(inc)), ptr(c(bw)), ptr(c(diff)), ptr(up.contiguous()), n,
+                                 *[ptr(o) for o in outs])
+    for got, leaf_t in zip(outs, (R0, inc, bw, diff, cost)):
+        assert torch.allclose(got.reshape(-1), leaf_t.grad.reshape(-1), rtol=1e-5, atol=1e-6)
+
+
+def test_material_heads_backward_matches_autograd(hostcheck, scenes):
+    """modules/render_modules.py:553-560 through the oracle's material_heads on a scene with autograd leaves: gradients of the
+    three heads the path uses w.r.t. their weights, biases and the feature"""
+    fix = load_fixture("microfacet_g40")
+    osc = oracle_scene(fix, requires_grad=True)
+    g = torch.Generator().manual_seed(3)
+    n = 500
+    feat = (torch.randn(n, 24, generator=g) * 0.5).requires_grad_(True)
+    feat.data[:3] *= 30                                             # drives the roughness head into its clip
+    albedo, tint, f0, r1 = O.material_heads(osc, feat)
+    ga, gf, gr = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g), torch.randn(n, 1, generator=g)
+    ((albedo * ga).sum() + (f0 * gf).sum() + (r1 * gr).sum()).backward()
+    names = ("diffuse", "tint", "f0", "roughness")
+    W = torch.cat([fix["state"][f"model.diffuse_module.{h}_mlp.0.weight"] for h in names]).float().contiguous()
+    b = torch.cat([fix["state"][f"model.diffuse_module.{h}_mlp.0.bias"] for h in names]).float().contiguous()
+    dW, db, dfeat = torch.zeros(11, 24), torch.zeros(11), torch.zeros(n, 24)
+    hp = osc.hp
+    hostcheck.hc_heads_bwd(ptr(feat.detach().contiguous()), ptr(W), ptr(b), C.c_float(hp["diffuse_mul"]), C.c_float(hp["diffuse_bias"]),
+                           C.c_float(hp["f0_bias"]), C.c_float(hp["roughness_bias"]), ptr(ga.contiguous()), ptr(gf.contiguous()),
+                           ptr(gr.reshape(-1).contiguous()), n, ptr(dW), ptr(db), ptr(dfeat))
+    assert torch.allclose(dfeat, feat.grad, rtol=1e-4, atol=1e-6)
+    rows = {"diffuse": slice(0, 3), "tint": slice(3, 6), "f0": slice(6, 9), "roughness": slice(9, 11)}
+    for h in names:
+        gw = osc.params[f"model.diffuse_module.{h}_mlp.0.weight"].grad
+        gb = osc.params[f"model.diffuse_module.{h}_mlp.0.bias"].grad
+        gw = torch.zeros_like(W[rows[h]]) if gw is None else gw
+        gb = torch.zeros_like(b[rows[h]]) if gb is None else gb
+        assert torch.allclose(dW[rows[h]], gw, rtol=1e-4, atol=1e-5 * max(1.0, float(gw.abs().max()))), h
+        assert torch.allclose(db[rows[h]], gb, rtol=1e-4, atol=1e-5 * max(1.0, float(gb.abs().max()))), h
