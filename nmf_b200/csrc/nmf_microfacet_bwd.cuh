@@ -11,8 +11,11 @@
 //                         (models/microfacet.py:565-613)
 //   nmf_heads_bwd         the sigmoid material heads on the 24-d feature with their clip gates
 //                         (modules/render_modules.py:553-560)
+//   nmf_env_lookup1_bwd_map  gradient of an environment lookup w.r.t. the map: scatter into a SAT-shaped image with the
+//                         forward's own box walk (modules/integral_equirect.py:409-504); the adjoint of the double
+//                         cumsum and the activation chain are whole-map passes (stated in the test)
 #pragma once
-#include "nmf_math.cuh"
+#include "nmf_train.cuh"
 
 // ---- minimal forward-mode AD: value + derivative w.r.t. ONE scalar (the sample's roughness) ----
 struct NmfDual { float v, d; };
@@ -135,4 +138,56 @@ NMF_HD void nmf_heads_bwd(const float* feat, const float* W, const float* b, flo
       dfeat[k] += dlin[h] * W[h * 24 + k];
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Environment lookup, gradient w.r.t. the map (modules/integral_equirect.py:263-273, 409-504).
+//   forward:  act = exp(min(brightness + mul * bg_mat, 20)),  SAT = cumsum_y cumsum_x (act / 1000),
+//             rgb = 1000 * sum_boxes sign * bilinear(SAT, corner) / size        (pole rows: the mean of act's first / last row)
+//   backward: (1) every lookup scatters g * sign * w_bilinear / size into a SAT-shaped gradient image -- the SAME box walk
+//                 as the forward (nmf_env_integrate) with a scattering tap; pole lookups add g to the row-mean gradient;
+//             (2) d act = reverse cumsum over x and y of that image (the 1/1000 and the 1000 cancel), + row-mean terms;
+//             (3) d bg_mat = d act * act * mul where the clip is open, d brightness = sum d act * act, d mul = sum d act * act * bg.
+// Step (1) is per bounce ray (atomics into an 8 MB image on the device), steps (2) / (3) are two prefix-sum passes and an
+// elementwise pass over the 512 x 1024 map per optimiser step.
+// ------------------------------------------------------------------------------------------------
+struct NmfSatScatterTap {
+  float* gsat; int h, w;          // channel-last gradient image [h][w][4] (zeroed by the caller)
+  float gs[3];                    // upstream gradient * 1 / size of the lookup's box
+  NMF_HD void operator()(float px, float py, float sign, float* acc) const {
+    (void)acc;
+    px = nmf_clampf(px, -1.0f, 1.0f);
+    py = nmf_clampf(py, -1.0f, 1.0f);
+    float ix = (px + 1.0f) * 0.5f * (float)(w - 1), iy = (py + 1.0f) * 0.5f * (float)(h - 1);
+    float fx = floorf(ix), fy = floorf(iy);
+    int x0 = (int)fx, y0 = (int)fy;
+    float tx = ix - fx, ty = iy - fy;
+    int x1 = x0 + 1 < w ? x0 + 1 : x0, y1 = y0 + 1 < h ? y0 + 1 : y0;
+    const float wgt[4] = {(1.0f - tx) * (1.0f - ty), tx * (1.0f - ty), (1.0f - tx) * ty, tx * ty};
+    const size_t idx[4] = {(size_t)y0 * w + x0, (size_t)y0 * w + x1, (size_t)y1 * w + x0, (size_t)y1 * w + x1};
+    for (int q = 0; q < 4; ++q) {
+      if (wgt[q] == 0.f) continue;
+      for (int k = 0; k < 3; ++k) {
+#ifdef __CUDA_ARCH__
+        atomicAdd(gsat + idx[q] * 4 + k, sign * wgt[q] * gs[k]);
+#else
+        gsat[idx[q] * 4 + k] += sign * wgt[q] * gs[k];
+#endif
+      }
+    }
+  }
+};
+// one lookup: g = d loss / d rgb.  g_top / g_bot (3 floats each) collect the pole-row terms.
+NMF_HD void nmf_env_lookup1_bwd_map(float* gsat, int h, int w, float mipbias, nmf_v3 dir, float sa, const float* g, float* g_top,
+                                    float* g_bot) {
+  const NmfEnvBox bx = nmf_env_box(dir, sa, h, w, mipbias);
+  const float cutoff = 1.0f - 2.0f / (float)h * 3.0f;
+  if (bx.cy < -cutoff) { for (int k = 0; k < 3; ++k) NMF_ATOMIC_ADD(g_top + k, g[k]); return; }
+  if (bx.cy > cutoff) { for (int k = 0; k < 3; ++k) NMF_ATOMIC_ADD(g_bot + k, g[k]); return; }
+  NmfSatScatterTap tap;
+  tap.gsat = gsat; tap.h = h; tap.w = w;
+  const float inv_size = 1.0f / bx.size;
+  for (int k = 0; k < 3; ++k) tap.gs[k] = g[k] * inv_size;
+  float unused[3];
+  nmf_env_integrate(tap, bx, unused);
 }

@@ -315,6 +315,12 @@ void hc_heads_bwd(const float* feat, const float* W, const float* b, float diffu
                   dW, db, dfeat + 24 * i);
 }
 
+void hc_env_bwd_map(int h, int w, float mipbias, const float* dirs, const float* sa, const float* g, int n, float* gsat, float* g_top,
+                    float* g_bot) {
+  for (int i = 0; i < n; ++i)
+    nmf_env_lookup1_bwd_map(gsat, h, w, mipbias, nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), sa[i], g + 3 * i, g_top, g_bot);
+}
+
 void hc_upsample(const float* src, int C, int H, int W, float* dst, int H2, int W2) {
   for (int c = 0; c < C; ++c)
     for (int y = 0; y < H2; ++y)
