@@ -14,6 +14,7 @@
 //   nmf_env_lookup1_bwd_map  gradient of an environment lookup w.r.t. the map: scatter into a SAT-shaped image with the
 //                         forward's own box walk (modules/integral_equirect.py:409-504); the adjoint of the double
 //                         cumsum and the activation chain are whole-map passes (stated in the test)
+//   nmf_env_lookup1_d     directional derivative of a lookup along a tangent of the direction (d L / d roughness), forward-mode
 #pragma once
 #include "nmf_train.cuh"
 
@@ -190,4 +191,110 @@ NMF_HD void nmf_env_lookup1_bwd_map(float* gsat, int h, int w, float mipbias, nm
   for (int k = 0; k < 3; ++k) tap.gs[k] = g[k] * inv_size;
   float unused[3];
   nmf_env_integrate(tap, bx, unused);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Environment lookup, DIRECTIONAL derivative along a tangent of the direction (the bounce direction moves with the
+// roughness: tangent = d L / d roughness from nmf_ggx_sample_dr; the mip level `sa` carries no gradient, see above).
+// Forward-mode restatement of nmf_env_box + nmf_env_integrate + NmfSatTap with the reference's gradient conventions:
+// _Atan2Damped (modules/safemath.py:8-32: backward divides by x^2 + y^2 + 1e-5), torch.clip gates (closed interval),
+// grid_sample's bilinear coordinate gradient, constants where the reference assigns constants (wrap / pole pieces).
+// ------------------------------------------------------------------------------------------------
+NMF_HD NmfDual nmf_dclamp(NmfDual x, float lo, float hi) {
+  if (x.v < lo) return nmf_dk(lo);
+  if (x.v > hi) return nmf_dk(hi);
+  return x;
+}
+NMF_HD NmfDual nmf_dmax_floor(NmfDual x, float floor_) { return x.v >= floor_ ? x : nmf_dk(floor_); }
+NMF_HD NmfDual nmf_dlog(NmfDual x) { return nmf_dmk(logf(x.v), x.d / x.v); }
+NMF_HD NmfDual nmf_dexp2(NmfDual x) { const float e = exp2f(x.v); return nmf_dmk(e, 0.6931471805599453f * e * x.d); }
+NMF_HD NmfDual nmf_datan2_damped(NmfDual y, NmfDual x) {      // atan2(y, x); d = (x dy - y dx) / (x^2 + y^2 + 1e-5)
+  return nmf_dmk(atan2f(y.v, x.v), (x.v * y.d - y.v * x.d) / (x.v * x.v + y.v * y.v + 1e-5f));
+}
+struct NmfEnvBoxD { NmfDual cx, cy, sw, sh, size; };
+NMF_HD NmfEnvBoxD nmf_env_box_d(NmfDual3 u, float sa, int h, int w, float mipbias) {
+  NmfEnvBoxD bx;
+  const NmfDual cosv = nmf_dsqrt_floor(nmf_dk(1.0f) - u.z * u.z, NMF_EPS);
+  const NmfDual d = nmf_dk((float)(h * w)) / nmf_dmax_floor((float)(2.0 * 3.14159265358979323846 * 3.14159265358979323846) * cosv, NMF_EPS);
+  const float es = expf(sa);
+  const NmfDual area = nmf_dmk(expf(logf(d.v / 2.0f) + sa), 0.5f * es * d.d);
+  const NmfDual hh = nmf_dmax_floor(nmf_dsqrt_floor(area, NMF_EPS) * cosv, NMF_EPS);
+  const NmfDual ww = area / hh;
+  const float ln2 = 0.6931471805599453f;
+  const NmfDual lw = nmf_dclamp(nmf_dlog(ww) * (1.0f / ln2) + nmf_dk(mipbias), 0.0f, 7.0f);
+  const NmfDual lh = nmf_dclamp(nmf_dlog(hh) * (1.0f / ln2) + nmf_dk(mipbias), 0.0f, 7.0f);
+  bx.sw = nmf_dexp2(lw) * (1.0f / (float)h / 2.0f);
+  bx.sh = nmf_dexp2(lh) * (1.0f / (float)h);
+  bx.size = (bx.sw * (0.5f * (float)w)) * (bx.sh * (0.5f * (float)h));
+  const NmfDual n2 = u.x * u.x + u.y * u.y;
+  const float n2s = sqrtf(n2.v);
+  const NmfDual norm2d = nmf_dmk(n2s, n2s > 0.f ? n2.d / (2.0f * n2s) : 0.f);
+  const NmfDual phi = nmf_datan2_damped(u.y, u.x);
+  const NmfDual theta = nmf_datan2_damped(u.z, norm2d);
+  const float twopi = 6.2831855f;
+  const float pm = phi.v - twopi * floorf(phi.v / twopi);
+  bx.cx = nmf_dmk((pm - 3.1415927f) / 3.1415927f, phi.d / 3.1415927f);
+  bx.cy = nmf_dmk(-theta.v / 3.1415927f * 2.0f, -theta.d / 3.1415927f * 2.0f);
+  return bx;
+}
+// bilinear tap of the channel-last SAT at clip(p, -1, 1) with its derivative along (px.d, py.d)
+NMF_HD void nmf_sat_tap_d(const float* sat, int h, int w, NmfDual px, NmfDual py, float sign, NmfDual* acc) {
+  px = nmf_dclamp(px, -1.0f, 1.0f);
+  py = nmf_dclamp(py, -1.0f, 1.0f);
+  const NmfDual ix = (px + nmf_dk(1.0f)) * (0.5f * (float)(w - 1)), iy = (py + nmf_dk(1.0f)) * (0.5f * (float)(h - 1));
+  const float fx = floorf(ix.v), fy = floorf(iy.v);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const NmfDual tx = nmf_dmk(ix.v - fx, ix.d), ty = nmf_dmk(iy.v - fy, iy.d);
+  const int x1 = x0 + 1 < w ? x0 + 1 : x0, y1 = y0 + 1 < h ? y0 + 1 : y0;
+  const NmfDual one = nmf_dk(1.0f);
+  const NmfDual w00 = (one - tx) * (one - ty), w10 = tx * (one - ty), w01 = (one - tx) * ty, w11 = tx * ty;
+  const float* a = sat + ((size_t)y0 * w + x0) * 4; const float* b = sat + ((size_t)y0 * w + x1) * 4;
+  const float* c = sat + ((size_t)y1 * w + x0) * 4; const float* d = sat + ((size_t)y1 * w + x1) * 4;
+  for (int k = 0; k < 3; ++k) acc[k] = acc[k] + sign * (w00 * a[k] + w10 * b[k] + w01 * c[k] + w11 * d[k]);
+}
+NMF_HD void nmf_env_box1_d(const float* sat, int h, int w, NmfDual x0, NmfDual y0, NmfDual x1, NmfDual y1, NmfDual inv_size,
+                           NmfDual* out) {
+  NmfDual acc[3] = {nmf_dk(0.f), nmf_dk(0.f), nmf_dk(0.f)};
+  nmf_sat_tap_d(sat, h, w, x1, y1, 1.0f, acc);
+  nmf_sat_tap_d(sat, h, w, x0, y0, 1.0f, acc);
+  nmf_sat_tap_d(sat, h, w, x0, y1, -1.0f, acc);
+  nmf_sat_tap_d(sat, h, w, x1, y0, -1.0f, acc);
+  for (int k = 0; k < 3; ++k) out[k] = out[k] + acc[k] * inv_size;
+}
+// rgb[k] = value, drgb[k] = derivative along the tangent carried by `dir`
+NMF_HD void nmf_env_lookup1_d(const float* sat, int h, int w, float mipbias, const float* top, const float* bot, NmfDual3 dir,
+                              float sa, float* rgb, float* drgb) {
+  const NmfEnvBoxD bx = nmf_env_box_d(dir, sa, h, w, mipbias);
+  const float cutoff = 1.0f - 2.0f / (float)h * 3.0f;
+  if (bx.cy.v > cutoff) { for (int k = 0; k < 3; ++k) { rgb[k] = bot[k]; drgb[k] = 0.f; } return; }
+  if (bx.cy.v < -cutoff) { for (int k = 0; k < 3; ++k) { rgb[k] = top[k]; drgb[k] = 0.f; } return; }
+  const NmfDual hx = bx.sw * 0.5f, hy = bx.sh * 0.5f;
+  const NmfDual bx0 = bx.cx - hx, by0 = bx.cy - hy, bx1 = bx.cx + hx, by1 = bx.cy + hy;
+  const NmfDual inv_size = nmf_dk(1.0f) / bx.size;
+  const NmfDual rot = nmf_dk(bx0.v > 0.0f ? -1.0f : 1.0f);
+  NmfDual out[3] = {nmf_dk(0.f), nmf_dk(0.f), nmf_dk(0.f)};
+  for (int part = 0; part < 3; ++part) {
+    NmfDual x0 = bx0, x1 = bx1, y0 = by0, y1 = by1;
+    if (part == 1) {
+      if (!(by1.v > 1.0f)) continue;
+      const NmfDual over = nmf_dclamp(by1 - nmf_dk(1.0f), 0.0f, 0.5f);
+      x0 = bx0 + rot; x1 = bx1 + rot; y0 = nmf_dk(1.0f) - over; y1 = nmf_dk(1.0f);
+    } else if (part == 2) {
+      if (!(by0.v < -1.0f)) continue;
+      const NmfDual over = nmf_dclamp(nmf_dk(-1.0f) - by0, 0.0f, 0.5f);
+      x0 = bx0 + rot; x1 = bx1 + rot; y0 = nmf_dk(-1.0f); y1 = nmf_dk(-1.0f) + over;
+    }
+    for (int wrap = 0; wrap < 3; ++wrap) {
+      NmfDual u0 = x0, u1 = x1;
+      if (wrap == 1) {
+        if (!(x1.v > 1.0f)) continue;
+        u0 = nmf_dk(-1.0f); u1 = x1 - nmf_dk(2.0f);
+      } else if (wrap == 2) {
+        if (!(x0.v < -1.0f)) continue;
+        u0 = x0 + nmf_dk(2.0f); u1 = nmf_dk(1.0f);
+      }
+      nmf_env_box1_d(sat, h, w, u0, y0, u1, y1, inv_size, out);
+    }
+  }
+  for (int k = 0; k < 3; ++k) { rgb[k] = out[k].v * 1000.0f; drgb[k] = out[k].d * 1000.0f; }
 }

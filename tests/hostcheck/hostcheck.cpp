@@ -321,6 +321,14 @@ void hc_env_bwd_map(int h, int w, float mipbias, const float* dirs, const float*
     nmf_env_lookup1_bwd_map(gsat, h, w, mipbias, nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), sa[i], g + 3 * i, g_top, g_bot);
 }
 
+void hc_env_lookup_d(const NmfScene* s, const float* dirs, const float* tangent, const float* mip, int n, float* rgb, float* drgb) {
+  for (int i = 0; i < n; ++i) {
+    const NmfDual3 d = nmf_d3(nmf_dmk(dirs[3 * i], tangent[3 * i]), nmf_dmk(dirs[3 * i + 1], tangent[3 * i + 1]),
+                              nmf_dmk(dirs[3 * i + 2], tangent[3 * i + 2]));
+    nmf_env_lookup1_d(s->env_sat, s->env_h, s->env_w, s->env_mipbias, s->env_top, s->env_bot, d, mip[i], rgb + 3 * i, drgb + 3 * i);
+  }
+}
+
 void hc_upsample(const float* src, int C, int H, int W, float* dst, int H2, int W2) {
   for (int c = 0; c < C; ++c)
     for (int y = 0; y < H2; ++y)

@@ -464,3 +464,41 @@ def test_env_map_gradient_matches_autograd(hostcheck):
     assert scale > 0
     err = (got.float() - want).abs()
     assert float(err.max()) < 2e-3 * scale and float(err.mean()) < 2e-5 * scale, (float(err.max()) / scale, float(err.mean()) / scale)
+
+
+def test_env_direction_derivative_matches_autograd(hostcheck, scenes):
+    """Directional derivative of an environment lookup along a tangent of the direction (how the bounce radiance moves with
+    the roughness through L): forward-mode restatement (nmf_env_lookup1_d) against J^T products of torch autograd through
+    the oracle's env_lookup, with the reference's damped atan2 gradient, clip gates and grid_sample coordinate gradient."""
+    fix, osc, dsc = scenes
+    g = torch.Generator().manual_seed(6)
+    n = 6000
+    d = O.unit(torch.randn(n, 3, generator=g))
+    d[:6] = torch.tensor([[0, 0, 1.0], [0, 0, -1.0], [-1.0, 1e-4, 0.0], [-1.0, -1e-4, 0.0], [1.0, 0, 0], [0, 1.0, 0]])
+    d[6:200, 2] = d[6:200, 2].sign() * 0.97
+    d = O.unit(d)
+    mip = torch.rand(n, generator=g) * 14 - 10
+    tangent = torch.randn(n, 3, generator=g)
+    dd = d.clone().requires_grad_(True)
+    ref = O.env_lookup(osc, dd, mip)
+    want = torch.stack([(torch.autograd.grad(ref[:, c].sum(), dd, retain_graph=True)[0] * tangent).sum(-1) for c in range(3)], dim=1)
+    rgb, drgb = torch.zeros(n, 3), torch.zeros(n, 3)
+    hostcheck.hc_env_lookup_d(dsc.ref(), ptr(d.contiguous()), ptr(tangent.contiguous()), ptr(mip), n, ptr(rgb), ptr(drgb))
+    out = torch.zeros(n, 3)
+    hostcheck.hc_env_lookup(dsc.ref(), ptr(d.contiguous()), ptr(mip), n, ptr(out))
+    verr = (rgb - out).abs() / (out.abs() + 1e-2)                  # same values as the forward tap walk, up to the rounding of a
+    assert verr.max() < 5e-2 and verr.mean() < 2e-4, (verr.max(), verr.mean())   # differently ordered fp32 evaluation (sub-pixel boxes)
+    # The derivative is a difference of SAT slopes divided by the box size: for sub-pixel boxes (mip level 0) the fp32 SAT
+    # differences cancel catastrophically on BOTH sides (SURVEY section 7, hard part 4: ~5e-3 absolute noise on O(1) radiance),
+    # so the comparison is global (relative L2) plus per lookup for boxes of more than a texel.  The oracle's own gradient
+    # is NaN exactly at the poles (sqrt at 0); the restatement gives 0 there (pole rows are constants).
+    ok = ~torch.isnan(want).any(1)
+    assert int((~ok).sum()) <= 2 and bool(torch.isfinite(drgb).all())
+    lw, lh = O.env_mip_levels(osc, d, mip)
+    big = ok & ((lw >= 1.5) | (lh >= 1.5))
+    rel = lambda sel: float((want[sel] - drgb[sel]).norm() / want[sel].norm())
+    assert rel(ok) < 2e-3 and rel(big) < 5e-4, (rel(ok), rel(big))
+    scale = want.abs().max(dim=1).values + 1e-2 * ref.detach().abs().max(dim=1).values + 1e-3
+    err = ((drgb - want).abs().max(dim=1).values / scale)[big]
+    assert (err < 2e-2).float().mean() > 0.97 and float(err.median()) < 1e-4, (float((err < 2e-2).float().mean()), float(err.median()))
+    assert float(want[ok].abs().median()) > 1e-4
