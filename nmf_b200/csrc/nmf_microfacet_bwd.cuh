@@ -298,3 +298,88 @@ NMF_HD void nmf_env_lookup1_d(const float* sat, int h, int w, float mipbias, con
   }
   for (int k = 0; k < 3; ++k) { rgb[k] = out[k].v * 1000.0f; drgb[k] = out[k].d * 1000.0f; }
 }
+
+// ------------------------------------------------------------------------------------------------
+// BRDF MLP (modules/brdf.py:177-261), one row: x = [feat(24) | ISH(h)(18) | h(3) | ISH(d)(18) | d(3)] -> 64 ReLU -> 64 ReLU -> 4,
+// bw = sigmoid(out[:3] + bias).  Weights transposed as in NmfScene (w0t [66][64], w1t [64][64], w2t [64][4]).
+// Backward of g = d loss / d bw: accumulates the weight / bias gradients (same layouts) and returns d x[0..23]
+// (the encodings and the roughness reach the MLP detached: models/microfacet.py:461-472).
+// ------------------------------------------------------------------------------------------------
+NMF_HD void nmf_brdf_input(const float* feat, nmf_v3 half_l, nmf_v3 diff_l, float rough, float* x) {
+  for (int i = 0; i < 24; ++i) x[i] = feat[i];
+  nmf_ish18(half_l, rough, x + 24);
+  x[42] = half_l.x; x[43] = half_l.y; x[44] = half_l.z;
+  nmf_ish18(diff_l, rough, x + 45);
+  x[63] = diff_l.x; x[64] = diff_l.y; x[65] = diff_l.z;
+}
+NMF_HD void nmf_brdf_row_fwd_bwd(const float* x, const float* w0t, const float* b0, const float* w1t, const float* b1, const float* w2t,
+                                 const float* b2, float brdf_bias, const float* g, float* bw, float* dw0t, float* db0, float* dw1t,
+                                 float* db1, float* dw2t, float* db2, float* dfeat) {
+  float h1[64], h2[64], o[4];
+  for (int j = 0; j < 64; ++j) { float v = b0[j]; for (int k = 0; k < 66; ++k) v += x[k] * w0t[k * 64 + j]; h1[j] = fmaxf(v, 0.f); }
+  for (int j = 0; j < 64; ++j) { float v = b1[j]; for (int k = 0; k < 64; ++k) v += h1[k] * w1t[k * 64 + j]; h2[j] = fmaxf(v, 0.f); }
+  for (int j = 0; j < 4; ++j) { float v = b2[j]; for (int k = 0; k < 64; ++k) v += h2[k] * w2t[k * 4 + j]; o[j] = v; }
+  float dout[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < 3; ++c) { bw[c] = nmf_sigmoid(o[c] + brdf_bias); if (g) dout[c] = g[c] * bw[c] * (1.0f - bw[c]); }
+  if (!g) return;
+  float dh2[64], dh1[64];
+  for (int k = 0; k < 64; ++k) {
+    float v = 0.f;
+    for (int j = 0; j < 3; ++j) { NMF_ATOMIC_ADD(dw2t + k * 4 + j, h2[k] * dout[j]); v += w2t[k * 4 + j] * dout[j]; }
+    dh2[k] = h2[k] > 0.f ? v : 0.f;
+  }
+  for (int j = 0; j < 3; ++j) NMF_ATOMIC_ADD(db2 + j, dout[j]);
+  for (int k = 0; k < 64; ++k) {
+    float v = 0.f;
+    for (int j = 0; j < 64; ++j) { NMF_ATOMIC_ADD(dw1t + k * 64 + j, h1[k] * dh2[j]); v += w1t[k * 64 + j] * dh2[j]; }
+    dh1[k] = h1[k] > 0.f ? v : 0.f;
+  }
+  for (int j = 0; j < 64; ++j) NMF_ATOMIC_ADD(db1 + j, dh2[j]);
+  for (int k = 0; k < 66; ++k) {
+    float v = 0.f;
+    for (int j = 0; j < 64; ++j) { NMF_ATOMIC_ADD(dw0t + k * 64 + j, x[k] * dh1[j]); v += w0t[k * 64 + j] * dh1[j]; }
+    if (k < 24) dfeat[k] += v;
+  }
+  for (int j = 0; j < 64; ++j) NMF_ATOMIC_ADD(db0 + j, dh1[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One bounce sample with m environment rays (no re-trace), models/microfacet.py:352-613: the reverse pass composed from
+// the pieces above.  reflect = mean_j [ F_j inc_j bw_j + (1 - F_j) diffuse ];  g = d loss / d reflect.
+// Outputs: d R0 (3), d diffuse (3), d roughness (through L: Fresnel angle and environment direction), d feat (24, the
+// noisy feature the BRDF MLP sees), BRDF weight gradients, environment-map scatter.
+// ------------------------------------------------------------------------------------------------
+struct NmfBrdfGrads { float* w0t; float* b0; float* w1t; float* b1; float* w2t; float* b2; };
+NMF_HD void nmf_bounce_sample_bwd(const NmfScene& s, const float* nfeat, nmf_v3 V, nmf_v3 N, const float* R0, const float* diffuse,
+                                  float rough, const float* u, int m, const float* g, float* dR0, float* ddiffuse, float* drough,
+                                  float* dfeat, NmfBrdfGrads bg, float* gsat, float* g_top, float* g_bot) {
+  const float inv_m = 1.0f / (float)m;
+  float gm[3] = {g[0] * inv_m, g[1] * inv_m, g[2] * inv_m};
+  for (int c = 0; c < 3; ++c) { dR0[c] = 0.f; ddiffuse[c] = 0.f; }
+  for (int k = 0; k < 24; ++k) dfeat[k] = 0.f;
+  float dr = 0.f;
+  for (int j = 0; j < m; ++j) {
+    const float u1 = u[2 * j], u2 = u[2 * j + 1];
+    const NmfGGX fw = nmf_ggx_sample(u1, u2, V, N, rough);             // half_l / diff_l / logpdf as the forward draws them
+    const NmfGGXdr dg = nmf_ggx_sample_dr(u1, u2, V, N, rough);
+    const float mip = -logf((float)m) - fw.logpdf;                     // models/microfacet.py:445-448 (no gradient)
+    float x[66], bw[3], inc[3], dinc_dr[3];
+    nmf_brdf_input(nfeat, fw.half_l, fw.diff_l, rough, x);
+    const NmfDual3 Ld = nmf_d3(nmf_dmk(dg.L.x, dg.dL.x), nmf_dmk(dg.L.y, dg.dL.y), nmf_dmk(dg.L.z, dg.dL.z));
+    nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, Ld, mip, inc, dinc_dr);
+    // forward value of the BRDF weight first (g = NULL), then the mix backward, then the MLP backward with d bw
+    nmf_brdf_row_fwd_bwd(x, s.brdf_w0t, s.brdf_b0, s.brdf_w1t, s.brdf_b1, s.brdf_w2t, s.brdf_b2, s.brdf_bias, nullptr, bw, nullptr,
+                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    const float vh = nmf_dot(V, dg.H);
+    const float cost = fabsf(vh);
+    float a_R0[3], a_inc[3], a_bw[3], a_diff[3];
+    const float dcost = nmf_fresnel_mix_bwd(R0, cost, inc, bw, diffuse, gm, a_R0, a_inc, a_bw, a_diff);
+    for (int c = 0; c < 3; ++c) { dR0[c] += a_R0[c]; ddiffuse[c] += a_diff[c]; dr += a_inc[c] * dinc_dr[c]; }
+    dr += dcost * (vh > 0.f ? 1.0f : (vh < 0.f ? -1.0f : 0.f)) * nmf_dot(V, dg.dH);
+    float bw2[3];
+    nmf_brdf_row_fwd_bwd(x, s.brdf_w0t, s.brdf_b0, s.brdf_w1t, s.brdf_b1, s.brdf_w2t, s.brdf_b2, s.brdf_bias, a_bw, bw2, bg.w0t, bg.b0,
+                         bg.w1t, bg.b1, bg.w2t, bg.b2, dfeat);
+    nmf_env_lookup1_bwd_map(gsat, s.env_h, s.env_w, s.env_mipbias, dg.L, mip, a_inc, g_top, g_bot);
+  }
+  *drough = dr;
+}

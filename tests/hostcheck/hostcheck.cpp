@@ -329,6 +329,18 @@ void hc_env_lookup_d(const NmfScene* s, const float* dirs, const float* tangent,
   }
 }
 
+// n bounce samples with m rays each: the composed reverse pass of one shading level without re-trace
+void hc_bounce_samples_bwd(const NmfScene* s, const float* nfeat, const float* V, const float* N, const float* R0, const float* diffuse,
+                           const float* rough, const float* u, int n, int m, const float* g, float* dR0, float* ddiffuse, float* drough,
+                           float* dfeat, float* dw0t, float* db0, float* dw1t, float* db1, float* dw2t, float* db2, float* gsat,
+                           float* g_top, float* g_bot) {
+  NmfBrdfGrads bg{dw0t, db0, dw1t, db1, dw2t, db2};
+  for (int i = 0; i < n; ++i)
+    nmf_bounce_sample_bwd(*s, nfeat + 24 * i, nmf_mk3(V[3 * i], V[3 * i + 1], V[3 * i + 2]), nmf_mk3(N[3 * i], N[3 * i + 1], N[3 * i + 2]),
+                          R0 + 3 * i, diffuse + 3 * i, rough[i], u + (size_t)2 * m * i, m, g + 3 * i, dR0 + 3 * i, ddiffuse + 3 * i,
+                          drough + i, dfeat + 24 * i, bg, gsat, g_top, g_bot);
+}
+
 void hc_upsample(const float* src, int C, int H, int W, float* dst, int H2, int W2) {
   for (int c = 0; c < C; ++c)
     for (int y = 0; y < H2; ++y)
