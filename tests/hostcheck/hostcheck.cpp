@@ -270,6 +270,153 @@ void hc_train_plain(const NmfScene* s, const NmfTrain* tp, const float* rays, co
   }
 }
 
+// Training forward + backward of the MICROFACET model on the host for the case without re-trace (max_retrace_rays = ())
+// and detach_N = True: TensorNeRF.forward(is_train=True) -> Microfacet.forward -> photometric loss, then the reverse pass
+// composed from csrc/nmf_microfacet_bwd.cuh and the compositing / VM-factor backward of the model=tensorf slice.
+// Reference for the reverse-pass kernels of DESIGN.md section 9 (checked against the oracle's autograd of render_chunk).
+void hc_train_microfacet(const NmfScene* s, const NmfTrain* tp, const float* rays, const float* gt, const NmfPlainGrads* g,
+                         float* d_head_w, float* d_head_b, float* dw0t, float* db0, float* dw1t, float* db1, float* dw2t, float* db2,
+                         float* gsat, float* g_top, float* g_bot, float* rgb_map, float* acc_map, double* loss, int* n_samples) {
+  const int n = tp->n_rays, S = s->n_steps;
+  std::vector<uint8_t> valid((size_t)n * S);
+  std::vector<float> z((size_t)n * S);
+  hc_sample_rays_train(s, rays, n, -1.0f, tp->seed, tp->ray_id0, tp->ray_ids, valid.data(), z.data());
+  loss[0] = loss[1] = 0.0;
+  *n_samples = 0;
+  const float bg[3] = {1.f, 1.f, 1.f};
+  NmfBrdfGrads bgr{dw0t, db0, dw1t, db1, dw2t, db2};
+  struct Smp { float z, dist, f, alpha, T, w, dw; NmfTaps t; float feat[24], nfeat[24], albedo[3], f0[3], rough, E[3], refl[3];
+               nmf_v3 V, Nf; int count; uint64_t skey; };
+  for (int r = 0; r < n; ++r) {
+    const float* o = rays + 6 * r;
+    const float* d = o + 3;
+    const uint64_t rkey = nmf_primary_key(tp->seed, tp->ray_ids ? tp->ray_ids[r] : tp->ray_id0 + (uint64_t)r);
+    std::vector<Smp> sm;
+    float T = 1.0f, acc = 0.f, lin[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < S; ++k) {
+      if (!valid[(size_t)r * S + k]) continue;
+      Smp q;
+      q.z = z[(size_t)r * S + k];
+      q.dist = (k + 1 < S ? NMF_SUB(z[(size_t)r * S + k + 1], q.z) : 0.f) * s->distance_scale;
+      float p[3], xn[3];
+      nmf_step_pos(o, d, q.z, p);
+      nmf_normalize_xyz(*s, p, xn);
+      q.t = nmf_vm_taps(*s, xn);
+      q.f = 0.f;
+      for (int gi = 0; gi < 4; ++gi) q.f += nmf_density_group(*s, q.t, gi);
+      q.alpha = 1.0f - expf(-nmf_feature2density(q.f, s->density_shift) * q.dist);
+      q.T = T;
+      q.w = q.alpha * T;
+      T *= 1.0f - q.alpha + 1e-10f;
+      acc += q.w;
+      // appearance feature, normal, heads, irradiance
+      float coef[72];
+      nmf_app_coef(*s, q.t, coef);
+      for (int oo = 0; oo < 24; ++oo) {
+        float a = 0.f;
+        for (int j = 0; j < 72; ++j) a += s->basis_t[j * 24 + oo] * coef[j];
+        q.feat[oo] = a;
+      }
+      float grad[3] = {0.f, 0.f, 0.f};
+      for (int l = 0; l < 8; ++l) nmf_normal_lane(*s, q.t, l, grad);
+      const nmf_v3 nrm = nmf_normal_from_grad(*s, grad);
+      float lin11[11];
+      for (int h = 0; h < 11; ++h) {
+        float v = s->head_b[h];
+        for (int i = 0; i < 24; ++i) v += s->head_w[h * 24 + i] * q.feat[i];
+        lin11[h] = v;
+      }
+      float sh[9];
+      nmf_sh9(nrm, sh);
+      for (int c = 0; c < 3; ++c) {
+        q.albedo[c] = nmf_clampf(nmf_sigmoid(s->diffuse_mul * lin11[c] + s->diffuse_bias), 0.f, 1.f);
+        q.f0[c] = nmf_sigmoid(lin11[6 + c] + s->f0_bias);
+        float e = 0.f;
+        for (int i = 0; i < 9; ++i) e += s->sh_conv[i * 3 + c] * sh[i];
+        q.E[c] = e;
+        q.refl[c] = 0.f;
+      }
+      q.rough = nmf_clampf(nmf_sigmoid(lin11[9] + s->roughness_bias) / 2.0f, 1e-2f, 1.0f);
+      q.V = nmf_mk3(-d[0], -d[1], -d[2]);
+      const float vn = nmf_dot(q.V, nrm);
+      const float sgn = vn > 0.f ? 1.f : (vn < 0.f ? -1.f : 0.f);
+      q.Nf = nmf_mk3(nrm.x * sgn, nrm.y * sgn, nrm.z * sgn);
+      q.skey = nmf_mix64(rkey, (uint64_t)k);
+      const float kf = floorf(q.w * (float)s->rays_per_ray + nmf_uniform(q.skey, NMF_STREAM_BOUNCE) - 0.5f);     // pt_selectors.py:20-40
+      q.count = (int)nmf_clampf(kf, 0.f, (float)NMF_MAX_BOUNCE);
+      const uint64_t nseed = nmf_noise_seed(q.skey);
+      for (uint32_t pp = 0; pp < 12; ++pp) {
+        float n0, n1;
+        nmf_noise_pair(nseed, pp, &n0, &n1);
+        q.nfeat[2 * pp] = q.feat[2 * pp] + s->anoise * n0;
+        q.nfeat[2 * pp + 1] = q.feat[2 * pp + 1] + s->anoise * n1;
+      }
+      // forward shading of the bounce rays (the reverse pass below recomputes them)
+      if (q.count > 0) {
+        const float offu = 0.25f * nmf_uniform(q.skey, NMF_STREAM_OFF_U), offv = 0.25f * nmf_uniform(q.skey, NMF_STREAM_OFF_V);
+        for (int j = 0; j < q.count; ++j) {
+          const float u1 = nmf_wrap01(s->sobol[2 * j] + offu), u2 = nmf_wrap01(s->sobol[2 * j + 1] + offv);
+          const NmfGGX fw = nmf_ggx_sample(u1, u2, q.V, q.Nf, q.rough);
+          const float mip = -logf((float)q.count) - fw.logpdf;
+          float x[66], bw[3], inc[3];
+          nmf_brdf_input(q.nfeat, fw.half_l, fw.diff_l, q.rough, x);
+          nmf_brdf_row_fwd_bwd(x, s->brdf_w0t, s->brdf_b0, s->brdf_w1t, s->brdf_b1, s->brdf_w2t, s->brdf_b2, s->brdf_bias, nullptr, bw,
+                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+          nmf_env_lookup1(s->env_sat, s->env_h, s->env_w, s->env_mipbias, s->env_top, s->env_bot, fw.L, mip, inc);
+          const float cost = fabsf(nmf_dot(q.V, fw.H));
+          for (int c = 0; c < 3; ++c) {
+            const float F = nmf_fresnel(q.f0[c], cost);
+            q.refl[c] += (F * inc[c] * bw[c] + (1.0f - F) * q.albedo[c] * q.E[c]) / (float)q.count;
+          }
+        }
+      }
+      for (int c = 0; c < 3; ++c) lin[c] += q.w * q.refl[c];
+      sm.push_back(q);
+    }
+    *n_samples += (int)sm.size();
+    float gl[3], ga;
+    loss[0] += nmf_train_loss_ray(lin, acc, bg, gt + 3 * r, tp->lambda_pred, rgb_map + 3 * r, gl, &ga);
+    loss[1] += acc;
+    acc_map[r] = acc;
+    // ---- reverse pass ----
+    for (Smp& q : sm) {
+      q.dw = ga;
+      for (int c = 0; c < 3; ++c) q.dw += gl[c] * q.refl[c];
+      if (q.count == 0) continue;
+      const float offu = 0.25f * nmf_uniform(q.skey, NMF_STREAM_OFF_U), offv = 0.25f * nmf_uniform(q.skey, NMF_STREAM_OFF_V);
+      std::vector<float> u(2 * (size_t)q.count);
+      for (int j = 0; j < q.count; ++j) { u[2 * j] = nmf_wrap01(s->sobol[2 * j] + offu); u[2 * j + 1] = nmf_wrap01(s->sobol[2 * j + 1] + offv); }
+      float diffuse[3], gre[3], dR0[3], ddiff[3], drough, dnfeat[24], dfeat_h[24], g_alb[3];
+      for (int c = 0; c < 3; ++c) { diffuse[c] = q.albedo[c] * q.E[c]; gre[c] = q.w * gl[c]; }
+      nmf_bounce_sample_bwd(*s, q.nfeat, q.V, q.Nf, q.f0, diffuse, q.rough, u.data(), q.count, gre, dR0, ddiff, &drough, dnfeat, bgr,
+                            gsat, g_top, g_bot);
+      for (int c = 0; c < 3; ++c) g_alb[c] = ddiff[c] * q.E[c];                       // diffuse = albedo * E, E under no_grad
+      nmf_heads_bwd(q.feat, s->head_w, s->head_b, s->diffuse_mul, s->diffuse_bias, s->f0_bias, s->roughness_bias, g_alb, dR0, drough,
+                    d_head_w, d_head_b, dfeat_h);
+      float coef[72], dcoef[72];
+      nmf_app_coef(*s, q.t, coef);
+      for (int j = 0; j < 72; ++j) {
+        float a = 0.f;
+        for (int oo = 0; oo < 24; ++oo) {
+          const float df = dnfeat[oo] + dfeat_h[oo];
+          g->basis_t[j * 24 + oo] += coef[j] * df;
+          a += s->basis_t[j * 24 + oo] * df;
+        }
+        dcoef[j] = a;
+      }
+      nmf_app_bwd(*s, q.t, dcoef, g->a_plane, g->a_line);
+    }
+    float suffix = 0.f;
+    for (int i = (int)sm.size() - 1; i >= 0; --i) {
+      const Smp& q = sm[i];
+      const float dsigma = nmf_composite_bwd(q.dw, q.T, q.alpha, q.dist, suffix);
+      suffix += q.dw * q.w;
+      const float df = dsigma * nmf_feature2density_grad(q.f, s->density_shift);
+      if (df != 0.f) nmf_density_bwd(*s, q.t, df, g->d_plane, g->d_line);
+    }
+  }
+}
+
 // optimiser step (nmf_adam_step / nmf_l1_reg on the host)
 void hc_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps, float wd, int step,
              float grad_scale, float max_norm) {

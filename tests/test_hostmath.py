@@ -565,3 +565,72 @@ def test_bounce_sample_backward_matches_autograd(hostcheck):
         x = (osc.brightness + osc.mul * osc.bg_mat)[0].double()
         got_bg = (dact * torch.exp(x.clip(max=20)) * float(osc.mul.detach()) * (x <= 20)).float()
     assert rel(got_bg, P["bg_module.bg_mat"].grad[0]) < 1e-4, rel(got_bg, P["bg_module.bg_mat"].grad[0])             # measured 2e-6
+
+
+@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_noncubic"])
+def test_train_microfacet_host_gradients(hostcheck, name):
+    """The reverse pass of the MICROFACET training forward, composed on the host for one shading level (no re-trace,
+    detach_N on): loss and the gradient of EVERY parameter against autograd through the oracle's render_chunk(is_train=True)
+    -- which oracle/check_train.py pins to the unmodified reference -- on the same keyed random numbers."""
+    from nmf_b200 import _lib
+    from nmf_b200.train import PlainGradBuffers
+    fix = load_fixture(name)
+    hp = dict(max_retrace_rays=())
+    osc = oracle_scene(fix, requires_grad=True, **hp)
+    dsc = device_scene(fix, "cpu", sh_conv=O.sh_irradiance_coeffs(oracle_scene(fix)), **hp)
+    n, seed = 64, 21
+    rays = fix["rays"][:n].contiguous()
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
+    ids = np.arange(n).astype(np.uint64)
+    keys = KR.primary_ray_keys(seed, ids)
+    ims, st = O.render_chunk(osc, rays, fix["focal"], KR.KeyedRNG(), keys, draw_debug=False, is_train=True, detach_N=True)
+    assert len(st["n_samples"]) == 1                               # no re-traced level
+    photo = ((ims["rgb_map"].clip(0, 1) - gt.clip(0, 1)) ** 2).sum()
+    photo.backward()
+    P = osc.params
+    gb = PlainGradBuffers(dsc)
+    tp = _lib.NmfTrain(n_rays=n, focal=float(fix["focal"]), seed=seed, ray_id0=0, ray_ids=None, max_samples=-1, cap_samples=1 << 20,
+                       lambda_pred=0.0, white_bg=1)
+    z = lambda *s: torch.zeros(*s)
+    dhw, dhb = z(11, 24), z(11)
+    dw0t, db0, dw1t, db1, dw2t, db2 = z(66, 64), z(64), z(64, 64), z(64), z(64, 4), z(4)
+    h, w = osc.bg_mat.shape[-2:]
+    gsat, g_top, g_bot = z(h, w, 4), z(3), z(3)
+    rgb_map, acc_map = z(n, 3), z(n)
+    loss = torch.zeros(2, dtype=torch.float64)
+    ns = torch.zeros(1, dtype=torch.int32)
+    hostcheck.hc_train_microfacet(dsc.ref(), C.byref(tp), ptr(rays), ptr(gt), C.byref(gb.c), ptr(dhw), ptr(dhb), ptr(dw0t), ptr(db0),
+                                  ptr(dw1t), ptr(db1), ptr(dw2t), ptr(db2), ptr(gsat), ptr(g_top), ptr(g_bot), ptr(rgb_map),
+                                  ptr(acc_map), ptr(loss), ptr(ns))
+    assert int(ns[0]) == st["n_samples"][0]
+    assert float((rgb_map - ims["rgb_map"].detach()).abs().max()) < 2e-4
+    assert abs(float(loss[0]) - float(photo.detach())) <= 1e-4 * max(1.0, float(photo.detach()))
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
+    got = dict(gb.reference_layout())
+    names = ("diffuse", "tint", "f0", "roughness")
+    rows = {"diffuse": slice(0, 3), "tint": slice(3, 6), "f0": slice(6, 9), "roughness": slice(9, 11)}
+    for hname in names:
+        got[f"model.diffuse_module.{hname}_mlp.0.weight"] = dhw[rows[hname]]
+        got[f"model.diffuse_module.{hname}_mlp.0.bias"] = dhb[rows[hname]]
+    for i, (wt, b) in zip((0, 2, 4), ((dw0t, db0), (dw1t, db1), (dw2t, db2))):
+        got[f"model.brdf.mlp.{i}.weight"] = wt.t()
+        got[f"model.brdf.mlp.{i}.bias"] = b
+    gs = gsat[..., :3].permute(2, 0, 1).double()
+    dact = gs.flip(1).cumsum(1).flip(1).flip(2).cumsum(2).flip(2)
+    dact[:, 0, :] += g_top.double()[:, None] / w
+    dact[:, -1, :] += g_bot.double()[:, None] / w
+    with torch.no_grad():
+        x = (osc.brightness + osc.mul * osc.bg_mat)[0].double()
+        got["bg_module.bg_mat"] = (dact * torch.exp(x.clip(max=20)) * float(osc.mul.detach()) * (x <= 20)).float()[None]
+    report, checked = {}, 0
+    for k, p in P.items():
+        if p.grad is None or float(p.grad.abs().max()) == 0.0 or k not in got:
+            if k in got and p.grad is not None:
+                assert float(got[k].abs().max()) < 1e-6 * max(1.0, float(p.grad.abs().max())), k
+            continue
+        report[k] = rel(got[k].reshape(p.grad.shape), p.grad)
+        checked += 1
+    print(report)
+    assert checked >= 20, checked
+    bad = {k: v for k, v in report.items() if v > (2e-2 if "density_rf" in k else 5e-3)}
+    assert not bad, bad
