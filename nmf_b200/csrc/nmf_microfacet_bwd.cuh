@@ -51,15 +51,16 @@ struct NmfGGXdr {
   nmf_v3 L, dL;        // outgoing direction and d L / d roughness
   nmf_v3 H, dH;        // normalize((V + L) / 2) (models/microfacet.py:388) and its derivative
 };
-// V: unit vector to the viewer, N: normal flipped to V's side and DETACHED (Microfacet.detach_N, microfacet.py:352-353;
-// with detach_N off the normal's own gradient is a separate path), r: roughness of the sample (r2 = r1).
-NMF_HD NmfGGXdr nmf_ggx_sample_dr(float u1, float u2, nmf_v3 V, nmf_v3 N, float r_) {
-  const NmfDual r = nmf_dmk(r_, 1.0f);
-  const nmf_v3 up = (fabsf(N.z) < 0.999f) ? nmf_mk3(0.f, 0.f, 1.f) : nmf_mk3(-1.f, 0.f, 0.f);
-  const nmf_v3 t = nmf_unit(nmf_cross(up, N));
-  const nmf_v3 b = nmf_unit(nmf_cross(N, t));
-  const nmf_v3 V_l = nmf_mk3(nmf_dot(t, V), nmf_dot(b, V), nmf_dot(N, V));
-  const NmfDual3 Vs = nmf_dunit(nmf_d3(r * V_l.x, r * V_l.y, nmf_dk(V_l.z)));
+// V: unit vector to the viewer, N: normal flipped to V's side, r: roughness of the sample (r2 = r1).  N and r carry ONE
+// tangent: seed r = (r, 1), N constant for d / d roughness (N is detached while Microfacet.detach_N is on,
+// microfacet.py:352-353); seed N = (N, e_c), r constant for the c-th column of d / d N once detach_N is off.
+NMF_HD NmfGGXdr nmf_ggx_sample_dual(float u1, float u2, nmf_v3 V, NmfDual3 N, NmfDual r) {
+  const NmfDual3 up = nmf_d3k((fabsf(N.z.v) < 0.999f) ? nmf_mk3(0.f, 0.f, 1.f) : nmf_mk3(-1.f, 0.f, 0.f));
+  const NmfDual3 t = nmf_dunit(nmf_dcross(up, N));
+  const NmfDual3 b = nmf_dunit(nmf_dcross(N, t));
+  const NmfDual3 Vd = nmf_d3k(V);
+  const NmfDual3 V_l = nmf_d3(nmf_ddot(t, Vd), nmf_ddot(b, Vd), nmf_ddot(N, Vd));
+  const NmfDual3 Vs = nmf_dunit(nmf_d3(r * V_l.x, r * V_l.y, V_l.z));
   const NmfDual3 zup = nmf_d3k(nmf_mk3(0.f, 0.f, 1.f));
   const NmfDual3 T1 = (Vs.z.v < 0.999f) ? nmf_dunit(nmf_dcross(Vs, zup)) : nmf_d3k(nmf_mk3(-1.f, 0.f, 0.f));
   const NmfDual3 T2 = nmf_dunit(nmf_dcross(T1, Vs));
@@ -73,11 +74,10 @@ NMF_HD NmfGGXdr nmf_ggx_sample_dr(float u1, float u2, nmf_v3 V, nmf_v3 N, float 
   const NmfDual c = nmf_dsqrt_floor(nmf_dk(1.0f) - P1 * P1 - P2 * P2, NMF_EPS);
   const NmfDual3 Ns = nmf_dadd(nmf_dadd(nmf_dscale(T1, P1), nmf_dscale(T2, P2)), nmf_dscale(Vs, c));
   const NmfDual3 H_l = nmf_dunit(nmf_d3(Ns.x * r, Ns.y * r, Ns.z));
-  const NmfDual3 Hs = nmf_dadd(nmf_dadd(nmf_dscale(nmf_d3k(t), H_l.x), nmf_dscale(nmf_d3k(b), H_l.y)), nmf_dscale(nmf_d3k(N), H_l.z));
-  const NmfDual3 Vd = nmf_d3k(V);
+  const NmfDual3 Hs = nmf_dadd(nmf_dadd(nmf_dscale(t, H_l.x), nmf_dscale(b, H_l.y)), nmf_dscale(N, H_l.z));
   const NmfDual vh = nmf_ddot(Vd, Hs);
   NmfDual3 L = nmf_dunit(nmf_d3(2.0f * vh * Hs.x - Vd.x, 2.0f * vh * Hs.y - Vd.y, 2.0f * vh * Hs.z - Vd.z));
-  if (!(L.x.v * N.x + L.y.v * N.y + L.z.v * N.z > 0.0f)) L = nmf_dscale(L, nmf_dk(-1.0f));
+  if (!(L.x.v * N.x.v + L.y.v * N.y.v + L.z.v * N.z.v > 0.0f)) L = nmf_dscale(L, nmf_dk(-1.0f));
   const NmfDual3 H2 = nmf_dunit(nmf_d3((Vd.x + L.x) * 0.5f, (Vd.y + L.y) * 0.5f, (Vd.z + L.z) * 0.5f));
   NmfGGXdr o;
   o.L = nmf_mk3(L.x.v, L.y.v, L.z.v);
@@ -85,6 +85,15 @@ NMF_HD NmfGGXdr nmf_ggx_sample_dr(float u1, float u2, nmf_v3 V, nmf_v3 N, float 
   o.H = nmf_mk3(H2.x.v, H2.y.v, H2.z.v);
   o.dH = nmf_mk3(H2.x.d, H2.y.d, H2.z.d);
   return o;
+}
+NMF_HD NmfGGXdr nmf_ggx_sample_dr(float u1, float u2, nmf_v3 V, nmf_v3 N, float r) {
+  return nmf_ggx_sample_dual(u1, u2, V, nmf_d3k(N), nmf_dmk(r, 1.0f));
+}
+// c-th column of d / d N (c = 0, 1, 2)
+NMF_HD NmfGGXdr nmf_ggx_sample_dN(float u1, float u2, nmf_v3 V, nmf_v3 N, float r, int c) {
+  NmfDual3 Nd = nmf_d3k(N);
+  if (c == 0) Nd.x.d = 1.0f; else if (c == 1) Nd.y.d = 1.0f; else Nd.z.d = 1.0f;
+  return nmf_ggx_sample_dual(u1, u2, V, Nd, nmf_dk(r));
 }
 
 // comb_c = F_c * inc_c * bw_c + (1 - F_c) * diff_c,  F_c = R0_c + (1 - R0_c) * m^5,  m = clip(1 - cost, 0, 1),
@@ -352,12 +361,13 @@ NMF_HD void nmf_brdf_row_fwd_bwd(const float* x, const float* w0t, const float* 
 struct NmfBrdfGrads { float* w0t; float* b0; float* w1t; float* b1; float* w2t; float* b2; };
 NMF_HD void nmf_bounce_sample_bwd(const NmfScene& s, const float* nfeat, nmf_v3 V, nmf_v3 N, const float* R0, const float* diffuse,
                                   float rough, const float* u, int m, const float* g, float* dR0, float* ddiffuse, float* drough,
-                                  float* dfeat, NmfBrdfGrads bg, float* gsat, float* g_top, float* g_bot) {
+                                  float* dfeat, NmfBrdfGrads bg, float* gsat, float* g_top, float* g_bot, float* dN = nullptr) {
   const float inv_m = 1.0f / (float)m;
   float gm[3] = {g[0] * inv_m, g[1] * inv_m, g[2] * inv_m};
   for (int c = 0; c < 3; ++c) { dR0[c] = 0.f; ddiffuse[c] = 0.f; }
   for (int k = 0; k < 24; ++k) dfeat[k] = 0.f;
   float dr = 0.f;
+  if (dN) dN[0] = dN[1] = dN[2] = 0.f;
   for (int j = 0; j < m; ++j) {
     const float u1 = u[2 * j], u2 = u[2 * j + 1];
     const NmfGGX fw = nmf_ggx_sample(u1, u2, V, N, rough);             // half_l / diff_l / logpdf as the forward draws them
@@ -375,7 +385,19 @@ NMF_HD void nmf_bounce_sample_bwd(const NmfScene& s, const float* nfeat, nmf_v3 
     float a_R0[3], a_inc[3], a_bw[3], a_diff[3];
     const float dcost = nmf_fresnel_mix_bwd(R0, cost, inc, bw, diffuse, gm, a_R0, a_inc, a_bw, a_diff);
     for (int c = 0; c < 3; ++c) { dR0[c] += a_R0[c]; ddiffuse[c] += a_diff[c]; dr += a_inc[c] * dinc_dr[c]; }
-    dr += dcost * (vh > 0.f ? 1.0f : (vh < 0.f ? -1.0f : 0.f)) * nmf_dot(V, dg.dH);
+    const float svh = vh > 0.f ? 1.0f : (vh < 0.f ? -1.0f : 0.f);
+    dr += dcost * svh * nmf_dot(V, dg.dH);
+    if (dN) {                                  // detach_N off: the same two paths (environment direction, Fresnel angle) per column of N
+      for (int c = 0; c < 3; ++c) {
+        const NmfGGXdr dn = nmf_ggx_sample_dN(u1, u2, V, N, rough, c);
+        const NmfDual3 Ln = nmf_d3(nmf_dmk(dn.L.x, dn.dL.x), nmf_dmk(dn.L.y, dn.dL.y), nmf_dmk(dn.L.z, dn.dL.z));
+        float inc_n[3], dinc_dn[3];
+        nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, Ln, mip, inc_n, dinc_dn);
+        float acc = dcost * svh * nmf_dot(V, dn.dH);
+        for (int k = 0; k < 3; ++k) acc += a_inc[k] * dinc_dn[k];
+        dN[c] += acc;
+      }
+    }
     float bw2[3];
     nmf_brdf_row_fwd_bwd(x, s.brdf_w0t, s.brdf_b0, s.brdf_w1t, s.brdf_b1, s.brdf_w2t, s.brdf_b2, s.brdf_bias, a_bw, bw2, bg.w0t, bg.b0,
                          bg.w1t, bg.b1, bg.w2t, bg.b2, dfeat);

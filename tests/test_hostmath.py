@@ -634,3 +634,27 @@ def test_train_microfacet_host_gradients(hostcheck, name):
     assert checked >= 20, checked
     bad = {k: v for k, v in report.items() if v > (2e-2 if "density_rf" in k else 5e-3)}
     assert not bad, bad
+
+
+def test_ggx_normal_derivative_matches_autograd(hostcheck):
+    """d L / d N (the path that opens when Microfacet.detach_N goes off, microfacet.py:352-353): three forward-mode passes,
+    one per column, against torch autograd through the oracle's ggx_sample (the tangent frame, the stretched view vector
+    and the reflection all move with N)."""
+    n = 3000
+    u, V, N, r = _ggx_inputs(n, 9)
+    N = N.clone()
+    N[:4] = O.unit(torch.tensor([[0.3, 0.1, 0.9], [0.0, 0.6, -0.8], [0.5, 0.5, 0.7], [1.0, 0.2, 0.1]]))   # away from the frame switch
+    V = torch.where((V * N).sum(-1, keepdim=True) < 0, -V, V)
+    NN = N.clone().requires_grad_(True)
+    L, _, _ = O.ggx_sample(u[:, :1], u[:, 1:], V, NN, r, torch.ones(n, 1, dtype=torch.bool))
+    J = torch.stack([torch.autograd.grad(L[:, a].sum(), NN, retain_graph=True)[0] for a in range(3)], dim=1)   # (n, out a, in c)
+    worst = []
+    for c in range(3):
+        dL, dH = torch.zeros(n, 3), torch.zeros(n, 3)
+        hostcheck.hc_ggx_dN(ptr(u.contiguous()), ptr(V.contiguous()), ptr(N.contiguous()), ptr(r.reshape(-1).contiguous()), n, c,
+                            ptr(dL), ptr(dH))
+        want = J[:, :, c]
+        err = (dL - want).norm(dim=1) / (want.norm(dim=1) + 1e-2)
+        worst.append(float((err < 2e-3).float().mean()))
+        assert float(err.median()) < 1e-5
+    assert min(worst) > 0.99, worst
