@@ -15,6 +15,10 @@
 //                         forward's own box walk (modules/integral_equirect.py:409-504); the adjoint of the double
 //                         cumsum and the activation chain are whole-map passes (stated in the test)
 //   nmf_env_lookup1_d     directional derivative of a lookup along a tangent of the direction (d L / d roughness), forward-mode
+//   nmf_brdf_row_fwd_bwd  the 66-64-64-4 BRDF MLP, one row;  nmf_bounce_sample_bwd  the composed reverse pass of a bounce sample
+//   nmf_normal_vec_bwd / nmf_normal_bwd  the normal path that opens with detach_N off (scatter into dpack / lpack-shaped images)
+// tests/hostcheck hc_train_microfacet composes all of it into the training reverse pass of one shading level; its gradients
+// equal the oracle's for every parameter (tests/test_hostmath.py::test_train_microfacet_host_gradients).
 #pragma once
 #include "nmf_train.cuh"
 
@@ -404,4 +408,52 @@ NMF_HD void nmf_bounce_sample_bwd(const NmfScene& s, const float* nfeat, nmf_v3 
     nmf_env_lookup1_bwd_map(gsat, s.env_h, s.env_w, s.env_mipbias, dg.L, mip, a_inc, g_top, g_bot);
   }
   *drough = dr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Normals (fields/tensor_base.py:107-129 with the smoothed-difference planes of modules/grid_sample_Cinf.py:218-281), the
+// path that opens when detach_N goes off:  grad[mat0] += sum_c line_c * plane_dx_c,  grad[mat1] += sum_c line_c * plane_dy_c,
+// grad[vec] += sum_c plane_c * line_dy_c  (all bilinear taps),  n = normalize(-grad * invaabbSize).
+// nmf_normal_vec_bwd: d n -> d grad.   nmf_normal_bwd: d grad -> scatter into gradient images laid out like dpack
+// ([h][w][val16 | dx16 | dy16]) and lpack ([n][4][val4 | dy4]); the dx / dy parts still have to go through the adjoint of
+// the 5x5 stencil convolution (a whole-plane pass per step) to reach the density planes / lines.
+// ------------------------------------------------------------------------------------------------
+NMF_HD void nmf_normal_vec_bwd(const NmfScene& s, const float* grad, const float* dn, float* dgrad) {
+  float v[3], n2 = 0.f;
+  for (int c = 0; c < 3; ++c) { v[c] = -(grad[c] * s.inv_aabb2[c]); n2 += v[c] * v[c]; }
+  if (!(n2 > NMF_EPS)) { dgrad[0] = dgrad[1] = dgrad[2] = 0.f; return; }
+  const float len = sqrtf(n2);
+  float nd = 0.f;
+  for (int c = 0; c < 3; ++c) nd += (v[c] / len) * dn[c];
+  for (int c = 0; c < 3; ++c) dgrad[c] = -s.inv_aabb2[c] * (dn[c] - (v[c] / len) * nd) / len;
+}
+NMF_HD void nmf_normal_bwd(const NmfScene& s, const NmfTaps& t, const float* dgrad, float* const* gpack, float* const* glpack) {
+  for (int p = 0; p < 3; ++p) {
+    const int w = s.plane_w[p];
+    const NmfLerp& lx = t.px[p]; const NmfLerp& ly = t.py[p]; const NmfLerp& ll = t.pl[p];
+    const float g0 = dgrad[NMF_MAT0(p)], g1 = dgrad[NMF_MAT1(p)], gv = dgrad[NMF_VEC(p)];
+    const size_t tex[4] = {(size_t)ly.i0 * w + lx.i0, (size_t)ly.i0 * w + lx.i1, (size_t)ly.i1 * w + lx.i0, (size_t)ly.i1 * w + lx.i1};
+    const float tw[4] = {ly.w0 * lx.w0, ly.w0 * lx.w1, ly.w1 * lx.w0, ly.w1 * lx.w1};
+    for (int c = 0; c < 16; ++c) {
+      const int lo = (c >> 2) * 8 + (c & 3);              // lpack: [texel][group][val4 | dy4]
+      float pc = 0.f, dpx = 0.f, dpy = 0.f;
+      for (int q = 0; q < 4; ++q) {
+        if (tw[q] == 0.f) continue;
+        const float* e = s.dpack[p] + tex[q] * 48;
+        pc += tw[q] * e[c]; dpx += tw[q] * e[16 + c]; dpy += tw[q] * e[32 + c];
+      }
+      const float* a0 = s.lpack[p] + (size_t)ll.i0 * 32;
+      const float* a1 = s.lpack[p] + (size_t)ll.i1 * 32;
+      const float lc = (ll.w0 != 0.f ? ll.w0 * a0[lo] : 0.f) + (ll.w1 != 0.f ? ll.w1 * a1[lo] : 0.f);
+      const float dly = (ll.w0 != 0.f ? ll.w0 * a0[lo + 4] : 0.f) + (ll.w1 != 0.f ? ll.w1 * a1[lo + 4] : 0.f);
+      const float d_lc = g0 * dpx + g1 * dpy, d_dpx = g0 * lc, d_dpy = g1 * lc, d_pc = gv * dly, d_dly = gv * pc;
+      for (int q = 0; q < 4; ++q) {
+        if (tw[q] == 0.f) continue;
+        float* e = gpack[p] + tex[q] * 48;
+        NMF_ATOMIC_ADD(e + c, tw[q] * d_pc); NMF_ATOMIC_ADD(e + 16 + c, tw[q] * d_dpx); NMF_ATOMIC_ADD(e + 32 + c, tw[q] * d_dpy);
+      }
+      if (ll.w0 != 0.f) { NMF_ATOMIC_ADD(glpack[p] + (size_t)ll.i0 * 32 + lo, ll.w0 * d_lc); NMF_ATOMIC_ADD(glpack[p] + (size_t)ll.i0 * 32 + lo + 4, ll.w0 * d_dly); }
+      if (ll.w1 != 0.f) { NMF_ATOMIC_ADD(glpack[p] + (size_t)ll.i1 * 32 + lo, ll.w1 * d_lc); NMF_ATOMIC_ADD(glpack[p] + (size_t)ll.i1 * 32 + lo + 4, ll.w1 * d_dly); }
+    }
+  }
 }

@@ -276,7 +276,8 @@ void hc_train_plain(const NmfScene* s, const NmfTrain* tp, const float* rays, co
 // Reference for the reverse-pass kernels of DESIGN.md section 9 (checked against the oracle's autograd of render_chunk).
 void hc_train_microfacet(const NmfScene* s, const NmfTrain* tp, const float* rays, const float* gt, const NmfPlainGrads* g,
                          float* d_head_w, float* d_head_b, float* dw0t, float* db0, float* dw1t, float* db1, float* dw2t, float* db2,
-                         float* gsat, float* g_top, float* g_bot, float* rgb_map, float* acc_map, double* loss, int* n_samples) {
+                         float* gsat, float* g_top, float* g_bot, float* rgb_map, float* acc_map, double* loss, int* n_samples,
+                         int detach_N, float* const* gpack, float* const* glpack) {
   const int n = tp->n_rays, S = s->n_steps;
   std::vector<uint8_t> valid((size_t)n * S);
   std::vector<float> z((size_t)n * S);
@@ -286,7 +287,7 @@ void hc_train_microfacet(const NmfScene* s, const NmfTrain* tp, const float* ray
   const float bg[3] = {1.f, 1.f, 1.f};
   NmfBrdfGrads bgr{dw0t, db0, dw1t, db1, dw2t, db2};
   struct Smp { float z, dist, f, alpha, T, w, dw; NmfTaps t; float feat[24], nfeat[24], albedo[3], f0[3], rough, E[3], refl[3];
-               nmf_v3 V, Nf; int count; uint64_t skey; };
+               nmf_v3 V, Nf; int count; uint64_t skey; float ngrad[3], sgn; };
   for (int r = 0; r < n; ++r) {
     const float* o = rays + 6 * r;
     const float* d = o + 3;
@@ -341,6 +342,8 @@ void hc_train_microfacet(const NmfScene* s, const NmfTrain* tp, const float* ray
       const float vn = nmf_dot(q.V, nrm);
       const float sgn = vn > 0.f ? 1.f : (vn < 0.f ? -1.f : 0.f);
       q.Nf = nmf_mk3(nrm.x * sgn, nrm.y * sgn, nrm.z * sgn);
+      q.sgn = sgn;
+      for (int c = 0; c < 3; ++c) q.ngrad[c] = grad[c];
       q.skey = nmf_mix64(rkey, (uint64_t)k);
       const float kf = floorf(q.w * (float)s->rays_per_ray + nmf_uniform(q.skey, NMF_STREAM_BOUNCE) - 0.5f);     // pt_selectors.py:20-40
       q.count = (int)nmf_clampf(kf, 0.f, (float)NMF_MAX_BOUNCE);
@@ -388,8 +391,14 @@ void hc_train_microfacet(const NmfScene* s, const NmfTrain* tp, const float* ray
       for (int j = 0; j < q.count; ++j) { u[2 * j] = nmf_wrap01(s->sobol[2 * j] + offu); u[2 * j + 1] = nmf_wrap01(s->sobol[2 * j + 1] + offv); }
       float diffuse[3], gre[3], dR0[3], ddiff[3], drough, dnfeat[24], dfeat_h[24], g_alb[3];
       for (int c = 0; c < 3; ++c) { diffuse[c] = q.albedo[c] * q.E[c]; gre[c] = q.w * gl[c]; }
+      float dNf[3];
       nmf_bounce_sample_bwd(*s, q.nfeat, q.V, q.Nf, q.f0, diffuse, q.rough, u.data(), q.count, gre, dR0, ddiff, &drough, dnfeat, bgr,
-                            gsat, g_top, g_bot);
+                            gsat, g_top, g_bot, detach_N ? nullptr : dNf);
+      if (!detach_N) {                             // normal path: d Nf -> d n (sign flip) -> d grad -> derivative-plane scatter
+        float dn[3] = {q.sgn * dNf[0], q.sgn * dNf[1], q.sgn * dNf[2]}, dgrad[3];
+        nmf_normal_vec_bwd(*s, q.ngrad, dn, dgrad);
+        nmf_normal_bwd(*s, q.t, dgrad, gpack, glpack);
+      }
       for (int c = 0; c < 3; ++c) g_alb[c] = ddiff[c] * q.E[c];                       // diffuse = albedo * E, E under no_grad
       nmf_heads_bwd(q.feat, s->head_w, s->head_b, s->diffuse_mul, s->diffuse_bias, s->f0_bias, s->roughness_bias, g_alb, dR0, drough,
                     d_head_w, d_head_b, dfeat_h);

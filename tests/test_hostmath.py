@@ -567,11 +567,15 @@ def test_bounce_sample_backward_matches_autograd(hostcheck):
     assert rel(got_bg, P["bg_module.bg_mat"].grad[0]) < 1e-4, rel(got_bg, P["bg_module.bg_mat"].grad[0])             # measured 2e-6
 
 
-@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_noncubic"])
-def test_train_microfacet_host_gradients(hostcheck, name):
-    """The reverse pass of the MICROFACET training forward, composed on the host for one shading level (no re-trace,
-    detach_N on): loss and the gradient of EVERY parameter against autograd through the oracle's render_chunk(is_train=True)
-    -- which oracle/check_train.py pins to the unmodified reference -- on the same keyed random numbers."""
+@pytest.mark.parametrize("name,detach_N", [("microfacet_g40", True), ("microfacet_noncubic", True), ("microfacet_g40", False),
+                                           ("microfacet_noncubic", False)])
+def test_train_microfacet_host_gradients(hostcheck, name, detach_N):
+    """The reverse pass of the MICROFACET training forward, composed on the host for one shading level (no re-trace), with
+    Microfacet.detach_N on (first iteration) and off (every later one: the bounce direction also moves with the normal, whose
+    gradient reaches the density factors through the smoothed-difference planes): loss and the gradient of EVERY parameter
+    against autograd through the oracle's render_chunk(is_train=True) -- which oracle/check_train.py pins to the unmodified
+    reference -- on the same keyed random numbers."""
+    import torch.nn.functional as Fn
     from nmf_b200 import _lib
     from nmf_b200.train import PlainGradBuffers
     fix = load_fixture(name)
@@ -583,7 +587,7 @@ def test_train_microfacet_host_gradients(hostcheck, name):
     gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
     ids = np.arange(n).astype(np.uint64)
     keys = KR.primary_ray_keys(seed, ids)
-    ims, st = O.render_chunk(osc, rays, fix["focal"], KR.KeyedRNG(), keys, draw_debug=False, is_train=True, detach_N=True)
+    ims, st = O.render_chunk(osc, rays, fix["focal"], KR.KeyedRNG(), keys, draw_debug=False, is_train=True, detach_N=detach_N)
     assert len(st["n_samples"]) == 1                               # no re-traced level
     photo = ((ims["rgb_map"].clip(0, 1) - gt.clip(0, 1)) ** 2).sum()
     photo.backward()
@@ -599,14 +603,37 @@ def test_train_microfacet_host_gradients(hostcheck, name):
     rgb_map, acc_map = z(n, 3), z(n)
     loss = torch.zeros(2, dtype=torch.float64)
     ns = torch.zeros(1, dtype=torch.int32)
+    gpack = [torch.zeros_like(dsc.keep[f"dpack{p}"]) for p in range(3)]          # gradient images laid out like dpack / lpack
+    glpack = [torch.zeros_like(dsc.keep[f"lpack{p}"]) for p in range(3)]
+    parr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
     hostcheck.hc_train_microfacet(dsc.ref(), C.byref(tp), ptr(rays), ptr(gt), C.byref(gb.c), ptr(dhw), ptr(dhb), ptr(dw0t), ptr(db0),
                                   ptr(dw1t), ptr(db1), ptr(dw2t), ptr(db2), ptr(gsat), ptr(g_top), ptr(g_bot), ptr(rgb_map),
-                                  ptr(acc_map), ptr(loss), ptr(ns))
+                                  ptr(acc_map), ptr(loss), ptr(ns), int(detach_N), parr(gpack), parr(glpack))
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
     assert int(ns[0]) == st["n_samples"][0]
     assert float((rgb_map - ims["rgb_map"].detach()).abs().max()) < 2e-4
     assert abs(float(loss[0]) - float(photo.detach())) <= 1e-4 * max(1.0, float(photo.detach()))
-    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
     got = dict(gb.reference_layout())
+    if not detach_N:
+        # normal path: value parts add directly, dx / dy parts go through the adjoint of the 5x5 stencil convolution
+        kx, ky = O.derivative_stencils()
+        conv = lambda img, k: Fn.conv2d(img.permute(1, 0, 2, 3), k, stride=1, padding=(2, 2)).permute(1, 0, 2, 3)
+
+        def adjoint(shape, k, gimg):
+            xz = torch.zeros(shape, requires_grad=True)
+            return torch.autograd.grad(conv(xz, k), xz, gimg)[0]
+        assert any(float(t.abs().max()) > 0 for t in gpack)
+        direct_only = rel(got["rf.density_rf.app_plane.0"], P["rf.density_rf.app_plane.0"].grad)
+        assert direct_only > 5e-3, direct_only               # the normal path is a material part of this gradient
+        for p in range(3):
+            gp = gpack[p].reshape(gpack[p].shape[0], gpack[p].shape[1], 48)
+            img = lambda sl: gp[..., sl].permute(2, 0, 1)[None].contiguous()
+            key = f"rf.density_rf.app_plane.{p}"
+            got[key] = got[key] + img(slice(0, 16)) + adjoint(got[key].shape, kx, img(slice(16, 32))) + adjoint(got[key].shape, ky, img(slice(32, 48)))
+            gl = glpack[p].reshape(-1, 4, 8)
+            lin_img = lambda sl: gl[:, :, sl].reshape(-1, 16).t()[None, :, :, None].contiguous()
+            key = f"rf.density_rf.app_line.{p}"
+            got[key] = got[key] + lin_img(slice(0, 4)) + adjoint(got[key].shape, ky, lin_img(slice(4, 8)))
     names = ("diffuse", "tint", "f0", "roughness")
     rows = {"diffuse": slice(0, 3), "tint": slice(3, 6), "f0": slice(6, 9), "roughness": slice(9, 11)}
     for hname in names:
