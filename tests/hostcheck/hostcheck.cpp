@@ -277,17 +277,17 @@ void hc_train_plain(const NmfScene* s, const NmfTrain* tp, const float* rays, co
 void hc_train_microfacet(const NmfScene* s, const NmfTrain* tp, const float* rays, const float* gt, const NmfPlainGrads* g,
                          float* d_head_w, float* d_head_b, float* dw0t, float* db0, float* dw1t, float* db1, float* dw2t, float* db2,
                          float* gsat, float* g_top, float* g_bot, float* rgb_map, float* acc_map, double* loss, int* n_samples,
-                         int detach_N, float* const* gpack, float* const* glpack) {
+                         int detach_N, float* const* gpack, float* const* glpack, float lambda_ori) {
   const int n = tp->n_rays, S = s->n_steps;
   std::vector<uint8_t> valid((size_t)n * S);
   std::vector<float> z((size_t)n * S);
   hc_sample_rays_train(s, rays, n, -1.0f, tp->seed, tp->ray_id0, tp->ray_ids, valid.data(), z.data());
-  loss[0] = loss[1] = 0.0;
+  loss[0] = loss[1] = loss[2] = 0.0;
   *n_samples = 0;
   const float bg[3] = {1.f, 1.f, 1.f};
   NmfBrdfGrads bgr{dw0t, db0, dw1t, db1, dw2t, db2};
   struct Smp { float z, dist, f, alpha, T, w, dw; NmfTaps t; float feat[24], nfeat[24], albedo[3], f0[3], rough, E[3], refl[3];
-               nmf_v3 V, Nf; int count; uint64_t skey; float ngrad[3], sgn; };
+               nmf_v3 V, Nf; int count; uint64_t skey; float ngrad[3], sgn, vn; };
   for (int r = 0; r < n; ++r) {
     const float* o = rays + 6 * r;
     const float* d = o + 3;
@@ -343,7 +343,9 @@ void hc_train_microfacet(const NmfScene* s, const NmfTrain* tp, const float* ray
       const float sgn = vn > 0.f ? 1.f : (vn < 0.f ? -1.f : 0.f);
       q.Nf = nmf_mk3(nrm.x * sgn, nrm.y * sgn, nrm.z * sgn);
       q.sgn = sgn;
+      q.vn = vn;
       for (int c = 0; c < 3; ++c) q.ngrad[c] = grad[c];
+      if (vn < 0.f) loss[2] += (double)(q.w * vn * vn);                    // ori_loss (tensor_nerf.py:573-583)
       q.skey = nmf_mix64(rkey, (uint64_t)k);
       const float kf = floorf(q.w * (float)s->rays_per_ray + nmf_uniform(q.skey, NMF_STREAM_BOUNCE) - 0.5f);     // pt_selectors.py:20-40
       q.count = (int)nmf_clampf(kf, 0.f, (float)NMF_MAX_BOUNCE);
@@ -385,6 +387,13 @@ void hc_train_microfacet(const NmfScene* s, const NmfTrain* tp, const float* ray
     for (Smp& q : sm) {
       q.dw = ga;
       for (int c = 0; c < 3; ++c) q.dw += gl[c] * q.refl[c];
+      if (lambda_ori != 0.f && q.vn < 0.f) {       // ori_lambda * sum w min(v.n, 0)^2: to the weight and, through the normal, to the density factors
+        q.dw += lambda_ori * q.vn * q.vn;
+        const float k2 = lambda_ori * q.w * 2.0f * q.vn;
+        float dn[3] = {k2 * q.V.x, k2 * q.V.y, k2 * q.V.z}, dgrad[3];
+        nmf_normal_vec_bwd(*s, q.ngrad, dn, dgrad);
+        nmf_normal_bwd(*s, q.t, dgrad, gpack, glpack);
+      }
       if (q.count == 0) continue;
       const float offu = 0.25f * nmf_uniform(q.skey, NMF_STREAM_OFF_U), offv = 0.25f * nmf_uniform(q.skey, NMF_STREAM_OFF_V);
       std::vector<float> u(2 * (size_t)q.count);
@@ -503,6 +512,28 @@ void hc_bounce_samples_bwd(const NmfScene* s, const float* nfeat, const float* V
     nmf_bounce_sample_bwd(*s, nfeat + 24 * i, nmf_mk3(V[3 * i], V[3 * i + 1], V[3 * i + 2]), nmf_mk3(N[3 * i], N[3 * i + 1], N[3 * i + 2]),
                           R0 + 3 * i, diffuse + 3 * i, rough[i], u + (size_t)2 * m * i, m, g + 3 * i, dR0 + 3 * i, ddiffuse + 3 * i,
                           drough + i, dfeat + 24 * i, bg, gsat, g_top, g_bot);
+}
+
+// ori_loss = sum w * min(v.n, 0)^2 at given points: value and the normal-path scatter (tensor_nerf.py:573-583)
+double hc_ori_loss_bwd(const NmfScene* s, const float* xyz, const float* V, const float* w, int n, float* const* gpack,
+                       float* const* glpack) {
+  double total = 0.0;
+  for (int i = 0; i < n; ++i) {
+    float xn[3];
+    nmf_normalize_xyz(*s, xyz + 4 * (size_t)i, xn);
+    const NmfTaps t = nmf_vm_taps(*s, xn);
+    float grad[3] = {0.f, 0.f, 0.f};
+    for (int l = 0; l < 8; ++l) nmf_normal_lane(*s, t, l, grad);
+    const nmf_v3 nn = nmf_normal_from_grad(*s, grad);
+    const float vn = V[3 * i] * nn.x + V[3 * i + 1] * nn.y + V[3 * i + 2] * nn.z;
+    if (!(vn < 0.f)) continue;
+    total += (double)(w[i] * vn * vn);
+    const float k2 = w[i] * 2.0f * vn;
+    float dn[3] = {k2 * V[3 * i], k2 * V[3 * i + 1], k2 * V[3 * i + 2]}, dgrad[3];
+    nmf_normal_vec_bwd(*s, grad, dn, dgrad);
+    nmf_normal_bwd(*s, t, dgrad, gpack, glpack);
+  }
+  return total;
 }
 
 void hc_upsample(const float* src, int C, int H, int W, float* dst, int H2, int W2) {

@@ -590,41 +590,49 @@ def test_train_microfacet_host_gradients(hostcheck, name, detach_N):
     ims, st = O.render_chunk(osc, rays, fix["focal"], KR.KeyedRNG(), keys, draw_debug=False, is_train=True, detach_N=detach_N)
     assert len(st["n_samples"]) == 1                               # no re-traced level
     photo = ((ims["rgb_map"].clip(0, 1) - gt.clip(0, 1)) ** 2).sum()
-    photo.backward()
+    # the loss of configs/model/microfacet_tensorf2.yaml:192-218: photometric + pred_lambda * prediction_loss + ori_lambda * ori_loss
+    lam_pred, lam_ori = 3e-4, 0.1
+    # (ori_loss is 0 on these clean fixtures -- every weighted normal faces the viewer; its gradient path is exercised on its
+    # own in test_ori_loss_normal_path_matches_autograd)
+    (photo + lam_pred * st["prediction_loss"] + lam_ori * st["ori_loss"]).backward()
     P = osc.params
     gb = PlainGradBuffers(dsc)
     tp = _lib.NmfTrain(n_rays=n, focal=float(fix["focal"]), seed=seed, ray_id0=0, ray_ids=None, max_samples=-1, cap_samples=1 << 20,
-                       lambda_pred=0.0, white_bg=1)
+                       lambda_pred=lam_pred, white_bg=1)
     z = lambda *s: torch.zeros(*s)
     dhw, dhb = z(11, 24), z(11)
     dw0t, db0, dw1t, db1, dw2t, db2 = z(66, 64), z(64), z(64, 64), z(64), z(64, 4), z(4)
     h, w = osc.bg_mat.shape[-2:]
     gsat, g_top, g_bot = z(h, w, 4), z(3), z(3)
     rgb_map, acc_map = z(n, 3), z(n)
-    loss = torch.zeros(2, dtype=torch.float64)
+    loss = torch.zeros(3, dtype=torch.float64)
     ns = torch.zeros(1, dtype=torch.int32)
     gpack = [torch.zeros_like(dsc.keep[f"dpack{p}"]) for p in range(3)]          # gradient images laid out like dpack / lpack
     glpack = [torch.zeros_like(dsc.keep[f"lpack{p}"]) for p in range(3)]
     parr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
     hostcheck.hc_train_microfacet(dsc.ref(), C.byref(tp), ptr(rays), ptr(gt), C.byref(gb.c), ptr(dhw), ptr(dhb), ptr(dw0t), ptr(db0),
                                   ptr(dw1t), ptr(db1), ptr(dw2t), ptr(db2), ptr(gsat), ptr(g_top), ptr(g_bot), ptr(rgb_map),
-                                  ptr(acc_map), ptr(loss), ptr(ns), int(detach_N), parr(gpack), parr(glpack))
+                                  ptr(acc_map), ptr(loss), ptr(ns), int(detach_N), parr(gpack), parr(glpack), C.c_float(lam_ori))
     rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
     assert int(ns[0]) == st["n_samples"][0]
     assert float((rgb_map - ims["rgb_map"].detach()).abs().max()) < 2e-4
     assert abs(float(loss[0]) - float(photo.detach())) <= 1e-4 * max(1.0, float(photo.detach()))
+    assert abs(float(loss[1]) * 2 - float(st["prediction_loss"].detach())) <= 1e-4 * float(st["prediction_loss"].detach())
+    assert abs(float(loss[2]) - float(st["ori_loss"].detach())) <= 1e-3 * float(st["ori_loss"].detach()) + 1e-12
     got = dict(gb.reference_layout())
-    if not detach_N:
-        # normal path: value parts add directly, dx / dy parts go through the adjoint of the 5x5 stencil convolution
+    if True:
+        # normal path (ori_loss always; the bounce direction once detach_N is off): value parts add directly, dx / dy parts
+        # go through the adjoint of the 5x5 stencil convolution
         kx, ky = O.derivative_stencils()
         conv = lambda img, k: Fn.conv2d(img.permute(1, 0, 2, 3), k, stride=1, padding=(2, 2)).permute(1, 0, 2, 3)
 
         def adjoint(shape, k, gimg):
             xz = torch.zeros(shape, requires_grad=True)
             return torch.autograd.grad(conv(xz, k), xz, gimg)[0]
-        assert any(float(t.abs().max()) > 0 for t in gpack)
-        direct_only = rel(got["rf.density_rf.app_plane.0"], P["rf.density_rf.app_plane.0"].grad)
-        assert direct_only > 5e-3, direct_only               # the normal path is a material part of this gradient
+        if not detach_N:
+            assert any(float(t.abs().max()) > 0 for t in gpack)
+            direct_only = rel(got["rf.density_rf.app_plane.0"], P["rf.density_rf.app_plane.0"].grad)
+            assert direct_only > 5e-3, direct_only           # the normal path is a material part of this gradient
         for p in range(3):
             gp = gpack[p].reshape(gpack[p].shape[0], gpack[p].shape[1], 48)
             img = lambda sl: gp[..., sl].permute(2, 0, 1)[None].contiguous()
@@ -685,3 +693,49 @@ def test_ggx_normal_derivative_matches_autograd(hostcheck):
         worst.append(float((err < 2e-3).float().mean()))
         assert float(err.median()) < 1e-5
     assert min(worst) > 0.99, worst
+
+
+@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_noncubic"])
+def test_ori_loss_normal_path_matches_autograd(hostcheck, name):
+    """ori_loss = sum w * min(v.n, 0)^2 (modules/tensor_nerf.py:573-583, ori_lambda = 0.1 in microfacet_tensorf2.yaml) sends a
+    gradient through the normal into the density factors: normalisation backward, scatter into dpack / lpack-shaped images,
+    adjoint of the 5x5 stencil -- against autograd through the oracle's vm_normals at random points and view directions."""
+    import torch.nn.functional as Fn
+    fix = load_fixture(name)
+    osc = oracle_scene(fix, requires_grad=True)
+    dsc = device_scene(fix, "cpu", sh_conv=O.sh_irradiance_coeffs(oracle_scene(fix)))
+    g = torch.Generator().manual_seed(12)
+    n = 3000
+    lo, hi = osc.aabb[0], osc.aabb[1]
+    xyz = torch.cat([lo + (hi - lo) * (0.1 + 0.8 * torch.rand(n, 3, generator=g)), torch.zeros(n, 1)], dim=1)
+    V = O.unit(torch.randn(n, 3, generator=g))
+    wgt = torch.rand(n, generator=g)
+    nrm = O.vm_normals(osc, xyz)
+    vn = (V * nrm).sum(-1)
+    loss = (wgt * vn.clamp(max=0) ** 2).sum()
+    assert float(loss.detach()) > 0
+    loss.backward()
+    gpack = [torch.zeros_like(dsc.keep[f"dpack{p}"]) for p in range(3)]
+    glpack = [torch.zeros_like(dsc.keep[f"lpack{p}"]) for p in range(3)]
+    parr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
+    hostcheck.hc_ori_loss_bwd.restype = C.c_double
+    val = hostcheck.hc_ori_loss_bwd(dsc.ref(), ptr(xyz.contiguous()), ptr(V.contiguous()), ptr(wgt.contiguous()), n, parr(gpack), parr(glpack))
+    assert abs(val - float(loss.detach())) <= 1e-4 * float(loss.detach())
+    kx, ky = O.derivative_stencils()
+    conv = lambda img, k: Fn.conv2d(img.permute(1, 0, 2, 3), k, stride=1, padding=(2, 2)).permute(1, 0, 2, 3)
+
+    def adjoint(shape, k, gimg):
+        xz = torch.zeros(shape, requires_grad=True)
+        return torch.autograd.grad(conv(xz, k), xz, gimg)[0]
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
+    for p in range(3):
+        want_p, want_l = osc.params[f"rf.density_rf.app_plane.{p}"].grad, osc.params[f"rf.density_rf.app_line.{p}"].grad
+        gp = gpack[p].reshape(gpack[p].shape[0], gpack[p].shape[1], 48)
+        img = lambda sl: gp[..., sl].permute(2, 0, 1)[None].contiguous()
+        got_p = img(slice(0, 16)) + adjoint(want_p.shape, kx, img(slice(16, 32))) + adjoint(want_p.shape, ky, img(slice(32, 48)))
+        gl = glpack[p].reshape(-1, 4, 8)
+        lin_img = lambda sl: gl[:, :, sl].reshape(-1, 16).t()[None, :, :, None].contiguous()
+        got_l = lin_img(slice(0, 4)) + adjoint(want_l.shape, ky, lin_img(slice(4, 8)))
+        if float(want_p.abs().max()) > 0:
+            assert rel(got_p, want_p) < 2e-3, (p, rel(got_p, want_p))
+            assert rel(got_l, want_l) < 2e-3, (p, rel(got_l, want_l))
