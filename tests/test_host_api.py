@@ -231,3 +231,18 @@ def test_regulariser_and_env_metric_surface():
     noisy = gt + 0.2 * np.random.RandomState(0).randn(*gt.shape)
     p2 = bg.calc_envmap_psnr(noisy, fH=16)
     assert 10 < p2 < 20                                                                      # sigma 0.2 -> ~14 dB
+
+
+def test_training_params_block_reaches_the_trainer():
+    """cfg.model.params (the `params:` block train.py reads) composes with the model group, parses its floats the OmegaConf
+    way, and carries the values the optimiser loop uses (train.REFERENCE_PARAMS for model=tensorf)."""
+    from nmf_b200 import config, train
+    p = config.compose(["model=tensorf"]).model.params
+    for k, v in train.REFERENCE_PARAMS.items():
+        got = p[k]
+        assert (list(got) == list(v)) if isinstance(v, (tuple, list)) else (float(got) == float(v)), (k, got, v)
+    assert isinstance(p.eps, float) and p.eps == 1e-15 and p.lr is None and p.clip_grad == 10
+    m = config.compose(["model.params.ori_lambda=0.05"]).model.params
+    assert m.ori_lambda == 0.05 and m.pred_lambda == 3e-4 and m.clip_grad is None and m.target_num_samples == 200000
+    h = dict(train.REFERENCE_PARAMS, **{k: p[k] for k in train.REFERENCE_PARAMS})
+    assert abs(train.learning_rate_decay(50, max_steps=h["n_iters"], **h) - train.learning_rate_decay(50, max_steps=30000, **train.REFERENCE_PARAMS)) < 1e-15
