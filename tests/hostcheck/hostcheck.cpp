@@ -284,6 +284,18 @@ void hc_train_microfacet(const NmfScene* s, const NmfTrain* tp, const float* ray
   hc_sample_rays_train(s, rays, n, -1.0f, tp->seed, tp->ray_id0, tp->ray_ids, valid.data(), z.data());
   loss[0] = loss[1] = loss[2] = 0.0;
   *n_samples = 0;
+  // dynamic batch truncation (alphagrid.py:353-364): rays kept = the prefix whose inclusive sample count stays below max_samples
+  int kept = n;
+  if (tp->max_samples > 0) {
+    long long total = 0, run = 0;
+    std::vector<int> nv(n, 0);
+    for (int r = 0; r < n; ++r) { for (int k = 0; k < S; ++k) nv[r] += valid[(size_t)r * S + k]; total += nv[r]; }
+    if (total > tp->max_samples) {
+      kept = 0;
+      for (int r = 0; r < n; ++r) { run += nv[r]; if (run < tp->max_samples) kept = r + 1; }
+    }
+  }
+  n_samples[1] = kept;
   const float bg[3] = {1.f, 1.f, 1.f};
   NmfBrdfGrads bgr{dw0t, db0, dw1t, db1, dw2t, db2};
   struct Smp { float z, dist, f, alpha, T, w, dw; NmfTaps t; float feat[24], nfeat[24], albedo[3], f0[3], rough, E[3], refl[3];
@@ -292,6 +304,7 @@ void hc_train_microfacet(const NmfScene* s, const NmfTrain* tp, const float* ray
     const float* o = rays + 6 * r;
     const float* d = o + 3;
     const uint64_t rkey = nmf_primary_key(tp->seed, tp->ray_ids ? tp->ray_ids[r] : tp->ray_id0 + (uint64_t)r);
+    if (r >= kept) { for (int c = 0; c < 3; ++c) rgb_map[3 * r + c] = 0.f; acc_map[r] = 0.f; continue; }
     std::vector<Smp> sm;
     float T = 1.0f, acc = 0.f, lin[3] = {0.f, 0.f, 0.f};
     for (int k = 0; k < S; ++k) {

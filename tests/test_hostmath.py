@@ -567,9 +567,9 @@ def test_bounce_sample_backward_matches_autograd(hostcheck):
     assert rel(got_bg, P["bg_module.bg_mat"].grad[0]) < 1e-4, rel(got_bg, P["bg_module.bg_mat"].grad[0])             # measured 2e-6
 
 
-@pytest.mark.parametrize("name,detach_N", [("microfacet_g40", True), ("microfacet_noncubic", True), ("microfacet_g40", False),
-                                           ("microfacet_noncubic", False)])
-def test_train_microfacet_host_gradients(hostcheck, name, detach_N):
+@pytest.mark.parametrize("name,detach_N,max_samples", [("microfacet_g40", True, -1), ("microfacet_noncubic", True, -1),
+                                                       ("microfacet_g40", False, -1), ("microfacet_noncubic", False, 2500)])
+def test_train_microfacet_host_gradients(hostcheck, name, detach_N, max_samples):
     """The reverse pass of the MICROFACET training forward, composed on the host for one shading level (no re-trace), with
     Microfacet.detach_N on (first iteration) and off (every later one: the bounce direction also moves with the normal, whose
     gradient reaches the density factors through the smoothed-difference planes): loss and the gradient of EVERY parameter
@@ -587,9 +587,13 @@ def test_train_microfacet_host_gradients(hostcheck, name, detach_N):
     gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
     ids = np.arange(n).astype(np.uint64)
     keys = KR.primary_ray_keys(seed, ids)
-    ims, st = O.render_chunk(osc, rays, fix["focal"], KR.KeyedRNG(), keys, draw_debug=False, is_train=True, detach_N=detach_N)
+    ims, st = O.render_chunk(osc, rays, fix["focal"], KR.KeyedRNG(), keys, draw_debug=False, is_train=True, detach_N=detach_N,
+                             max_samples=max_samples)
     assert len(st["n_samples"]) == 1                               # no re-traced level
-    photo = ((ims["rgb_map"].clip(0, 1) - gt.clip(0, 1)) ** 2).sum()
+    whole = st["whole_valid"]
+    nk = int(whole.sum())
+    assert (max_samples < 0 and nk == n) or (0 < nk < n)           # dynamic batch truncation (alphagrid.py:353-364)
+    photo = ((ims["rgb_map"].clip(0, 1) - gt[whole].clip(0, 1)) ** 2).sum()
     # the loss of configs/model/microfacet_tensorf2.yaml:192-218: photometric + pred_lambda * prediction_loss + ori_lambda * ori_loss
     lam_pred, lam_ori = 3e-4, 0.1
     # (ori_loss is 0 on these clean fixtures -- every weighted normal faces the viewer; its gradient path is exercised on its
@@ -597,8 +601,8 @@ def test_train_microfacet_host_gradients(hostcheck, name, detach_N):
     (photo + lam_pred * st["prediction_loss"] + lam_ori * st["ori_loss"]).backward()
     P = osc.params
     gb = PlainGradBuffers(dsc)
-    tp = _lib.NmfTrain(n_rays=n, focal=float(fix["focal"]), seed=seed, ray_id0=0, ray_ids=None, max_samples=-1, cap_samples=1 << 20,
-                       lambda_pred=lam_pred, white_bg=1)
+    tp = _lib.NmfTrain(n_rays=n, focal=float(fix["focal"]), seed=seed, ray_id0=0, ray_ids=None, max_samples=max_samples,
+                       cap_samples=1 << 20, lambda_pred=lam_pred, white_bg=1)
     z = lambda *s: torch.zeros(*s)
     dhw, dhb = z(11, 24), z(11)
     dw0t, db0, dw1t, db1, dw2t, db2 = z(66, 64), z(64), z(64, 64), z(64), z(64, 4), z(4)
@@ -606,7 +610,7 @@ def test_train_microfacet_host_gradients(hostcheck, name, detach_N):
     gsat, g_top, g_bot = z(h, w, 4), z(3), z(3)
     rgb_map, acc_map = z(n, 3), z(n)
     loss = torch.zeros(3, dtype=torch.float64)
-    ns = torch.zeros(1, dtype=torch.int32)
+    ns = torch.zeros(2, dtype=torch.int32)
     gpack = [torch.zeros_like(dsc.keep[f"dpack{p}"]) for p in range(3)]          # gradient images laid out like dpack / lpack
     glpack = [torch.zeros_like(dsc.keep[f"lpack{p}"]) for p in range(3)]
     parr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
@@ -614,8 +618,8 @@ def test_train_microfacet_host_gradients(hostcheck, name, detach_N):
                                   ptr(dw1t), ptr(db1), ptr(dw2t), ptr(db2), ptr(gsat), ptr(g_top), ptr(g_bot), ptr(rgb_map),
                                   ptr(acc_map), ptr(loss), ptr(ns), int(detach_N), parr(gpack), parr(glpack), C.c_float(lam_ori))
     rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
-    assert int(ns[0]) == st["n_samples"][0]
-    assert float((rgb_map - ims["rgb_map"].detach()).abs().max()) < 2e-4
+    assert int(ns[0]) == st["n_samples"][0] and int(ns[1]) == nk
+    assert float((rgb_map[:nk] - ims["rgb_map"].detach()).abs().max()) < 2e-4
     assert abs(float(loss[0]) - float(photo.detach())) <= 1e-4 * max(1.0, float(photo.detach()))
     assert abs(float(loss[1]) * 2 - float(st["prediction_loss"].detach())) <= 1e-4 * float(st["prediction_loss"].detach())
     assert abs(float(loss[2]) - float(st["ori_loss"].detach())) <= 1e-3 * float(st["ori_loss"].detach()) + 1e-12
