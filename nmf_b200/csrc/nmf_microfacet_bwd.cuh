@@ -457,3 +457,36 @@ NMF_HD void nmf_normal_bwd(const NmfScene& s, const NmfTaps& t, const float* dgr
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Finishing pass of the normal path: the gradient images scattered by nmf_normal_bwd hold d loss / d (value | dx | dy) per
+// texel; the dx / dy planes are cross-correlations of the density plane with the 5x5 smoothed-difference stencils
+// (grid_sample_Cinf.py:218-242, zero padding 2), so the plane gradient is  val + K_x^T * g_dx + K_y^T * g_dy  -- one texel
+// and one channel per call (a whole-plane, HBM-streaming pass per optimiser step: 25 taps x 2 images).  Output layout =
+// NmfPlainGrads.d_plane / d_line (channel-last), so the reverse-pass kernels can add it to the compositing path's gradient.
+// ------------------------------------------------------------------------------------------------
+NMF_HD float nmf_plane_grad_finish(const float* gpack, int h, int w, const float* kx25, const float* ky25, int y, int x, int c) {
+  float acc = gpack[((size_t)y * w + x) * 48 + c];
+  for (int i = 0; i < 5; ++i) {
+    const int yy = y - i + 2;
+    if (yy < 0 || yy >= h) continue;
+    for (int j = 0; j < 5; ++j) {
+      const int xx = x - j + 2;
+      if (xx < 0 || xx >= w) continue;
+      const float* e = gpack + ((size_t)yy * w + xx) * 48;
+      acc += kx25[i * 5 + j] * e[16 + c] + ky25[i * 5 + j] * e[32 + c];
+    }
+  }
+  return acc;
+}
+// lines are (N, 1) images: only the centre column of the stencil meets data
+NMF_HD float nmf_line_grad_finish(const float* glpack, int n, const float* ky25, int i, int c) {
+  const int lo = (c >> 2) * 8 + (c & 3);
+  float acc = glpack[(size_t)i * 32 + lo];
+  for (int r = 0; r < 5; ++r) {
+    const int ii = i - r + 2;
+    if (ii < 0 || ii >= n) continue;
+    acc += ky25[r * 5 + 2] * glpack[(size_t)ii * 32 + lo + 4];
+  }
+  return acc;
+}

@@ -549,6 +549,15 @@ double hc_ori_loss_bwd(const NmfScene* s, const float* xyz, const float* V, cons
   return total;
 }
 
+void hc_normal_grad_finish(const float* gpack, int h, int w, const float* glpack, int n, const float* kx25, const float* ky25,
+                           float* d_plane, float* d_line) {
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x)
+      for (int c = 0; c < 16; ++c) d_plane[((size_t)y * w + x) * 16 + c] += nmf_plane_grad_finish(gpack, h, w, kx25, ky25, y, x, c);
+  for (int i = 0; i < n; ++i)
+    for (int c = 0; c < 16; ++c) d_line[(size_t)i * 16 + c] += nmf_line_grad_finish(glpack, n, ky25, i, c);
+}
+
 void hc_upsample(const float* src, int C, int H, int W, float* dst, int H2, int W2) {
   for (int c = 0; c < C; ++c)
     for (int y = 0; y < H2; ++y)

@@ -743,3 +743,11 @@ def test_ori_loss_normal_path_matches_autograd(hostcheck, name):
         if float(want_p.abs().max()) > 0:
             assert rel(got_p, want_p) < 2e-3, (p, rel(got_p, want_p))
             assert rel(got_l, want_l) < 2e-3, (p, rel(got_l, want_l))
+        # the finishing pass as the reverse-pass kernels will run it (nmf_plane_grad_finish / nmf_line_grad_finish: stencil
+        # adjoint per texel, channel-last output added to the d_plane / d_line buffers) equals the autograd adjoint
+        H_, W_ = gp.shape[:2]
+        fin_p, fin_l = torch.zeros(H_, W_, 16), torch.zeros(gl.shape[0], 16)
+        hostcheck.hc_normal_grad_finish(ptr(gpack[p]), H_, W_, ptr(glpack[p]), gl.shape[0], ptr(kx.reshape(-1).contiguous()),
+                                        ptr(ky.reshape(-1).contiguous()), ptr(fin_p), ptr(fin_l))
+        assert torch.allclose(fin_p.permute(2, 0, 1)[None], got_p, rtol=1e-4, atol=1e-6 * float(got_p.abs().max()) + 1e-12)
+        assert torch.allclose(fin_l.t()[None, :, :, None], got_l, rtol=1e-4, atol=1e-6 * float(got_l.abs().max()) + 1e-12)
