@@ -490,3 +490,26 @@ NMF_HD float nmf_line_grad_finish(const float* glpack, int n, const float* ky25,
   }
   return acc;
 }
+
+// Finishing pass of the environment-map gradient: reverse prefix sums of the scattered SAT gradient over x and y (the adjoint
+// of integral_equirect.py:271-273's double cumsum), the pole-row means, then the exp activation with its clip at 20
+// (integral_equirect.py:263-270).  Sequential reference of what is two scan passes + one elementwise pass on the device.
+// gsat: [h][w][4] (overwritten with d act), bg: (3, h, w) parameter, out: (3, h, w) gradient (accumulated).
+inline void nmf_env_map_grad_finish(float* gsat, int h, int w, const float* g_top, const float* g_bot, const float* bg, float brightness,
+                                    float mul, float* out) {
+  for (int y = 0; y < h; ++y)
+    for (int x = w - 2; x >= 0; --x)
+      for (int k = 0; k < 3; ++k) gsat[((size_t)y * w + x) * 4 + k] += gsat[((size_t)y * w + x + 1) * 4 + k];
+  for (int y = h - 2; y >= 0; --y)
+    for (int x = 0; x < w; ++x)
+      for (int k = 0; k < 3; ++k) gsat[((size_t)y * w + x) * 4 + k] += gsat[((size_t)(y + 1) * w + x) * 4 + k];
+  for (int k = 0; k < 3; ++k)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        float d = gsat[((size_t)y * w + x) * 4 + k];
+        if (y == 0) d += g_top[k] / (float)w;
+        if (y == h - 1) d += g_bot[k] / (float)w;
+        const float pre = brightness + mul * bg[((size_t)k * h + y) * w + x];
+        if (pre <= 20.0f) out[((size_t)k * h + y) * w + x] += d * expf(pre) * mul;
+      }
+}

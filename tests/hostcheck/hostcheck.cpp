@@ -558,6 +558,11 @@ void hc_normal_grad_finish(const float* gpack, int h, int w, const float* glpack
     for (int c = 0; c < 16; ++c) d_line[(size_t)i * 16 + c] += nmf_line_grad_finish(glpack, n, ky25, i, c);
 }
 
+void hc_env_map_grad_finish(float* gsat, int h, int w, const float* g_top, const float* g_bot, const float* bg, float brightness,
+                            float mul, float* out) {
+  nmf_env_map_grad_finish(gsat, h, w, g_top, g_bot, bg, brightness, mul, out);
+}
+
 void hc_upsample(const float* src, int C, int H, int W, float* dst, int H2, int W2) {
   for (int c = 0; c < C; ++c)
     for (int y = 0; y < H2; ++y)

@@ -464,6 +464,12 @@ def test_env_map_gradient_matches_autograd(hostcheck):
     assert scale > 0
     err = (got.float() - want).abs()
     assert float(err.max()) < 2e-3 * scale and float(err.mean()) < 2e-5 * scale, (float(err.max()) / scale, float(err.mean()) / scale)
+    # the same finishing pass as the reverse-pass kernels will run it (fp32, in place)
+    fin = torch.zeros(3, h, w)
+    hostcheck.hc_env_map_grad_finish(ptr(gsat), h, w, ptr(g_top), ptr(g_bot), ptr(osc.bg_mat.detach()[0].contiguous()),
+                                     C.c_float(float(osc.brightness.detach())), C.c_float(float(osc.mul.detach())), ptr(fin))
+    err = (fin - want).abs()
+    assert float(err.max()) < 2e-3 * scale and float(err.mean()) < 2e-5 * scale, (float(err.max()) / scale, float(err.mean()) / scale)
 
 
 def test_env_direction_derivative_matches_autograd(hostcheck, scenes):
