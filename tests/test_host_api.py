@@ -246,3 +246,18 @@ def test_training_params_block_reaches_the_trainer():
     assert m.ori_lambda == 0.05 and m.pred_lambda == 3e-4 and m.clip_grad is None and m.target_num_samples == 200000
     h = dict(train.REFERENCE_PARAMS, **{k: p[k] for k in train.REFERENCE_PARAMS})
     assert abs(train.learning_rate_decay(50, max_steps=h["n_iters"], **h) - train.learning_rate_decay(50, max_steps=30000, **train.REFERENCE_PARAMS)) < 1e-15
+
+
+def test_backward_header_compiles_for_the_device(tmp_path):
+    """csrc/nmf_microfacet_bwd.cuh is host-checked math that the reverse-pass kernels will call: it must compile as sm_100a
+    device code (nvcc cross-compiles without a GPU)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    src = os.path.join(ROOT, "tests", "hostcheck", "bwd_device_probe.cu")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "--expt-relaxed-constexpr",
+                        "-I", os.path.join(ROOT, "nmf_b200", "csrc"), "-I", os.path.join(ROOT, "include"), "-c", src,
+                        "-o", str(tmp_path / "probe.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
