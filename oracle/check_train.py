@@ -38,7 +38,9 @@ def probes(g, n=16):
     return idx, flat[idx].clone()
 
 
-def run(name, detach_N, write):
+def run(name, detach_N, write, retrace=True):
+    """retrace=False: Microfacet.max_retrace_rays = [] -- one shading level, every bounce ray goes to the environment
+    (microfacet.py:475-476 `else` branch); the configuration the host-composed reverse pass of DESIGN.md section 9 covers."""
     fix = torch.load(os.path.join(make_golden.GOLDEN_DIR, f"{name}.pt"), weights_only=False)
     gsz = fix["grid_size"]
     grid = [gsz] * 3 if isinstance(gsz, int) else list(gsz)
@@ -47,6 +49,8 @@ def run(name, detach_N, write):
     ref.train()
     if hasattr(ref.model, "detach_N"):
         ref.model.detach_N = detach_N
+    if not retrace:
+        ref.model.max_retrace_rays = []
     rays, focal, seed = fix["rays"], fix["focal"], fix["seed"]
     target = torch.rand(rays.shape[0], 3, generator=torch.Generator().manual_seed(99))
     torch.manual_seed(seed)
@@ -57,13 +61,13 @@ def run(name, detach_N, write):
 
     model = "microfacet" if fix["model"] == "microfacet_tensorf2" else "plain"
     sc = nmf_oracle.Scene(fix["state"], fix["aabb"], fix["near_far"], grid, alpha_volume=fix["alpha_volume"].float(),
-                          requires_grad=True, model=model)
+                          requires_grad=True, model=model, **({} if retrace else dict(max_retrace_rays=())))
     torch.manual_seed(seed)
     oi, os_ = nmf_oracle.render_chunk(sc, rays, focal, keyed_rng.TorchRNG(), draw_debug=False, is_train=True,
                                       detach_N=detach_N, max_samples=ref.sampler.max_samples)
     oloss = training_loss(oi, os_, target)
     oloss.backward()
-    print(f"[{name} detach_N={detach_N}] loss ref {float(loss):.6f} oracle {float(oloss):.6f}  n_samples {st['n_samples']} {os_['n_samples']}")
+    print(f"[{name} detach_N={detach_N} retrace={retrace}] loss ref {float(loss):.6f} oracle {float(oloss):.6f}  n_samples {st['n_samples']} {os_['n_samples']}")
     assert list(st["n_samples"]) == list(os_["n_samples"])
     assert (ims["rgb_map"] - oi["rgb_map"]).abs().max() < 2e-5
     worst = {}
@@ -80,11 +84,11 @@ def run(name, detach_N, write):
     print("   max |grad_ref - grad_oracle| / max |grad_ref| :", {k.split(".", 1)[1] if "." in k else k: f"{v:.1e}" for k, v in worst.items()})
     assert not bad, bad
     if write:
-        out = dict(name=name, detach_N=detach_N, loss=float(loss), target_seed=99, stat_weights=STAT_W,
+        out = dict(name=name, detach_N=detach_N, retrace=retrace, loss=float(loss), target_seed=99, stat_weights=STAT_W,
                    max_samples=int(ref.sampler.max_samples),
                    statistics={k: float(torch.as_tensor(st[k]).sum()) for k in STAT_W},
                    grads={k: dict(norm=float(g.norm()), max=float(g.abs().max()), probes=probes(g)) for k, g in ref_grads.items() if k in sc.params})
-        path = os.path.join(make_golden.GOLDEN_DIR, f"{name}_train{'_dN' if detach_N else ''}.pt")
+        path = os.path.join(make_golden.GOLDEN_DIR, f"{name}_train{'' if retrace else '_noretrace'}{'_dN' if detach_N else ''}.pt")
         torch.save(out, path)
         print("   wrote", path)
 
@@ -92,7 +96,12 @@ def run(name, detach_N, write):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--write", action="store_true")
+    ap.add_argument("--only-noretrace", action="store_true")
     a = ap.parse_args()
+    for dn in (True, False):
+        run("microfacet_g40", dn, a.write, retrace=False)
+    if a.only_noretrace:
+        sys.exit(0)
     for nm in ("microfacet_g40", "microfacet_noncubic"):
         for dn in (True, False):
             run(nm, dn, a.write)
