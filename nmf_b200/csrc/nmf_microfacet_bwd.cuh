@@ -58,11 +58,10 @@ struct NmfGGXdr {
 // V: unit vector to the viewer, N: normal flipped to V's side, r: roughness of the sample (r2 = r1).  N and r carry ONE
 // tangent: seed r = (r, 1), N constant for d / d roughness (N is detached while Microfacet.detach_N is on,
 // microfacet.py:352-353); seed N = (N, e_c), r constant for the c-th column of d / d N once detach_N is off.
-NMF_HD NmfGGXdr nmf_ggx_sample_dual(float u1, float u2, nmf_v3 V, NmfDual3 N, NmfDual r) {
+NMF_HD NmfGGXdr nmf_ggx_sample_dual3(float u1, float u2, NmfDual3 Vd, NmfDual3 N, NmfDual r) {
   const NmfDual3 up = nmf_d3k((fabsf(N.z.v) < 0.999f) ? nmf_mk3(0.f, 0.f, 1.f) : nmf_mk3(-1.f, 0.f, 0.f));
   const NmfDual3 t = nmf_dunit(nmf_dcross(up, N));
   const NmfDual3 b = nmf_dunit(nmf_dcross(N, t));
-  const NmfDual3 Vd = nmf_d3k(V);
   const NmfDual3 V_l = nmf_d3(nmf_ddot(t, Vd), nmf_ddot(b, Vd), nmf_ddot(N, Vd));
   const NmfDual3 Vs = nmf_dunit(nmf_d3(r * V_l.x, r * V_l.y, V_l.z));
   const NmfDual3 zup = nmf_d3k(nmf_mk3(0.f, 0.f, 1.f));
@@ -89,6 +88,16 @@ NMF_HD NmfGGXdr nmf_ggx_sample_dual(float u1, float u2, nmf_v3 V, NmfDual3 N, Nm
   o.H = nmf_mk3(H2.x.v, H2.y.v, H2.z.v);
   o.dH = nmf_mk3(H2.x.d, H2.y.d, H2.z.d);
   return o;
+}
+NMF_HD NmfGGXdr nmf_ggx_sample_dual(float u1, float u2, nmf_v3 V, NmfDual3 N, NmfDual r) {
+  return nmf_ggx_sample_dual3(u1, u2, nmf_d3k(V), N, r);
+}
+// c-th column of d / d V: the tangent a RE-TRACED ray's shading sees (its view vector is minus the parent's bounce direction,
+// which moves with the parent's roughness / normal; positions are detached in the field, tensoRF.py:182-183)
+NMF_HD NmfGGXdr nmf_ggx_sample_dV(float u1, float u2, nmf_v3 V, nmf_v3 N, float r, int c) {
+  NmfDual3 Vd = nmf_d3k(V);
+  if (c == 0) Vd.x.d = 1.0f; else if (c == 1) Vd.y.d = 1.0f; else Vd.z.d = 1.0f;
+  return nmf_ggx_sample_dual3(u1, u2, Vd, nmf_d3k(N), nmf_dk(r));
 }
 NMF_HD NmfGGXdr nmf_ggx_sample_dr(float u1, float u2, nmf_v3 V, nmf_v3 N, float r) {
   return nmf_ggx_sample_dual(u1, u2, V, nmf_d3k(N), nmf_dmk(r, 1.0f));

@@ -487,6 +487,14 @@ void hc_ggx_dN(const float* u, const float* V, const float* N, const float* r, i
     dH[3 * i] = g.dH.x; dH[3 * i + 1] = g.dH.y; dH[3 * i + 2] = g.dH.z;
   }
 }
+void hc_ggx_dV(const float* u, const float* V, const float* N, const float* r, int n, int c, float* dL, float* dH) {
+  for (int i = 0; i < n; ++i) {
+    const NmfGGXdr g = nmf_ggx_sample_dV(u[2 * i], u[2 * i + 1], nmf_mk3(V[3 * i], V[3 * i + 1], V[3 * i + 2]),
+                                         nmf_mk3(N[3 * i], N[3 * i + 1], N[3 * i + 2]), r[i], c);
+    dL[3 * i] = g.dL.x; dL[3 * i + 1] = g.dL.y; dL[3 * i + 2] = g.dL.z;
+    dH[3 * i] = g.dH.x; dH[3 * i + 1] = g.dH.y; dH[3 * i + 2] = g.dH.z;
+  }
+}
 void hc_fresnel_mix_bwd(const float* R0, const float* cost, const float* inc, const float* bw, const float* diff, const float* g, int n,
                         float* dR0, float* dinc, float* dbw, float* ddiff, float* dcost) {
   for (int i = 0; i < n; ++i)

@@ -757,3 +757,26 @@ def test_ori_loss_normal_path_matches_autograd(hostcheck, name):
                                         ptr(ky.reshape(-1).contiguous()), ptr(fin_p), ptr(fin_l))
         assert torch.allclose(fin_p.permute(2, 0, 1)[None], got_p, rtol=1e-4, atol=1e-6 * float(got_p.abs().max()) + 1e-12)
         assert torch.allclose(fin_l.t()[None, :, :, None], got_l, rtol=1e-4, atol=1e-6 * float(got_l.abs().max()) + 1e-12)
+
+
+def test_ggx_view_derivative_matches_autograd(hostcheck):
+    """d L / d V and d H / d V: the tangent the shading of a RE-TRACED ray sees (its view vector is minus the parent's bounce
+    direction; sample positions are detached in the field, so this is the only way the secondary radiance moves with the
+    parent's roughness) -- three forward-mode passes against torch autograd through the oracle's ggx_sample."""
+    n = 3000
+    u, V, N, r = _ggx_inputs(n, 15)
+    N = N.clone()
+    N[:4] = O.unit(torch.tensor([[0.3, 0.1, 0.9], [0.0, 0.6, -0.8], [0.5, 0.5, 0.7], [1.0, 0.2, 0.1]]))
+    V = torch.where((V * N).sum(-1, keepdim=True) < 0, -V, V)
+    VV = V.clone().requires_grad_(True)
+    L, _, _ = O.ggx_sample(u[:, :1], u[:, 1:], VV, N, r, torch.ones(n, 1, dtype=torch.bool))
+    H = O.unit((VV + L) / 2)
+    JL = torch.stack([torch.autograd.grad(L[:, a].sum(), VV, retain_graph=True)[0] for a in range(3)], dim=1)
+    JH = torch.stack([torch.autograd.grad(H[:, a].sum(), VV, retain_graph=True)[0] for a in range(3)], dim=1)
+    for c in range(3):
+        dL, dH = torch.zeros(n, 3), torch.zeros(n, 3)
+        hostcheck.hc_ggx_dV(ptr(u.contiguous()), ptr(V.contiguous()), ptr(N.contiguous()), ptr(r.reshape(-1).contiguous()), n, c,
+                            ptr(dL), ptr(dH))
+        for got, want in ((dL, JL[:, :, c]), (dH, JH[:, :, c])):
+            err = (got - want).norm(dim=1) / (want.norm(dim=1) + 1e-2)
+            assert (err < 2e-3).float().mean() > 0.99 and float(err.median()) < 1e-5, (c, float((err < 2e-3).float().mean()))
