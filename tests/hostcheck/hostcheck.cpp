@@ -571,6 +571,15 @@ void hc_env_map_grad_finish(float* gsat, int h, int w, const float* g_top, const
   nmf_env_map_grad_finish(gsat, h, w, g_top, g_bot, bg, brightness, mul, out);
 }
 
+void hc_bounce_samples_tangent(const NmfScene* s, const float* nfeat, const float* V, const float* dV, const float* N, const float* R0,
+                               const float* diffuse, const float* rough, const float* u, int n, int m, float* refl, float* drefl) {
+  for (int i = 0; i < n; ++i) {
+    const NmfDual3 Vd = nmf_d3(nmf_dmk(V[3 * i], dV[3 * i]), nmf_dmk(V[3 * i + 1], dV[3 * i + 1]), nmf_dmk(V[3 * i + 2], dV[3 * i + 2]));
+    nmf_bounce_sample_tangent(*s, nfeat + 24 * i, Vd, nmf_mk3(N[3 * i], N[3 * i + 1], N[3 * i + 2]), R0 + 3 * i, diffuse + 3 * i, rough[i],
+                              u + (size_t)2 * m * i, m, refl + 3 * i, drefl + 3 * i);
+  }
+}
+
 void hc_upsample(const float* src, int C, int H, int W, float* dst, int H2, int W2) {
   for (int c = 0; c < C; ++c)
     for (int y = 0; y < H2; ++y)

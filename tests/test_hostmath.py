@@ -780,3 +780,45 @@ def test_ggx_view_derivative_matches_autograd(hostcheck):
         for got, want in ((dL, JL[:, :, c]), (dH, JH[:, :, c])):
             err = (got - want).norm(dim=1) / (want.norm(dim=1) + 1e-2)
             assert (err < 2e-3).float().mean() > 0.99 and float(err.median()) < 1e-5, (c, float((err < 2e-3).float().mean()))
+
+
+def test_bounce_sample_view_tangent_matches_autograd(hostcheck):
+    """d reflect / d V along a tangent (nmf_bounce_sample_tangent): how the radiance a re-traced ray returns moves with the
+    parent's bounce direction -- against J^T products of torch autograd through the oracle's functions wired as in
+    shade_microfacet (BRDF encodings detached, mip without gradient)."""
+    import math as _m
+    fix = load_fixture("microfacet_g40")
+    osc = oracle_scene(fix)
+    dsc = device_scene(fix, "cpu", sh_conv=O.sh_irradiance_coeffs(osc))
+    n, m = 300, 5
+    g = torch.Generator().manual_seed(16)
+    N = O.unit(torch.randn(n, 3, generator=g))
+    V = O.unit(torch.randn(n, 3, generator=g))
+    V = torch.where((V * N).sum(-1, keepdim=True) < 0, -V, V)
+    nfeat = torch.randn(n, 24, generator=g) * 0.3
+    R0, diffuse = torch.rand(n, 3, generator=g), torch.rand(n, 3, generator=g)
+    rr = torch.rand(n, 1, generator=g) * 0.4 + 0.08
+    u = torch.rand(n, m, 2, generator=g)
+    tangent = torch.randn(n, 3, generator=g)
+    VV = V.clone().requires_grad_(True)
+    L, cols, lpdf = O.ggx_sample(u[..., 0], u[..., 1], VV, N, rr, torch.ones(n, m, dtype=torch.bool))
+    ri = torch.arange(n).repeat_interleave(m)
+    eV = VV[ri]
+    H = O.unit((eV + L) / 2)
+    to_local = cols.permute(0, 2, 1)
+    diff_l = torch.matmul(to_local, L.unsqueeze(-1)).squeeze(-1)
+    half_l = torch.matmul(to_local, H.unsqueeze(-1)).squeeze(-1)
+    mip = -_m.log(m) - lpdf
+    bw = O.brdf_mlp(osc, nfeat[ri], half_l.detach(), diff_l.detach(), rr.expand(n, m).reshape(-1))
+    inc = O.env_lookup(osc, L, mip)
+    cost = (-eV * H).sum(dim=-1, keepdim=True).abs()
+    fres = R0[ri] + (1 - R0[ri]) * (1 - cost).clip(min=0, max=1) ** 5
+    reflect = (fres * inc * bw + (1 - fres) * diffuse[ri]).reshape(n, m, 3).mean(dim=1)
+    want = torch.stack([(torch.autograd.grad(reflect[:, c].sum(), VV, retain_graph=True)[0] * tangent).sum(-1) for c in range(3)], dim=1)
+    refl, drefl = torch.zeros(n, 3), torch.zeros(n, 3)
+    c_ = lambda t: t.detach().contiguous()
+    hostcheck.hc_bounce_samples_tangent(dsc.ref(), ptr(c_(nfeat)), ptr(c_(V)), ptr(c_(tangent)), ptr(c_(N)), ptr(c_(R0)), ptr(c_(diffuse)),
+                                        ptr(c_(rr).reshape(-1)), ptr(u.contiguous()), n, m, ptr(refl), ptr(drefl))
+    assert torch.allclose(refl, reflect.detach(), rtol=1e-3, atol=1e-3)
+    rel = float((drefl - want).norm() / want.norm())
+    assert rel < 2e-3, rel
