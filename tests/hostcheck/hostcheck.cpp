@@ -592,3 +592,313 @@ void hc_upsample(const float* src, int C, int H, int W, float* dst, int H2, int 
       }
 }
 }
+// Training forward + backward of the microfacet model with ONE re-traced level where EVERY bounce ray is re-traced
+// (max_retrace_rays[0] >= number of bounce rays: no selection), on the host.
+extern "C" void hc_train_microfacet_retrace(const NmfScene* s, const NmfTrain* tp, const float* rays, const float* gt, const NmfPlainGrads* g,
+                                 float* d_head_w, float* d_head_b, float* dw0t, float* db0, float* dw1t, float* db1, float* dw2t, float* db2,
+                                 float* gsat, float* g_top, float* g_bot, float* rgb_map, double* loss, int* n_samples, int detach_N,
+                                 float* const* gpack, float* const* glpack) {
+  const int n = tp->n_rays, S = s->n_steps;
+  NmfBrdfGrads bgr{dw0t, db0, dw1t, db1, dw2t, db2};
+  struct Smp { float z, dist, f, alpha, T, w, dw; NmfTaps t; float pos[3]; float feat[24], nfeat[24], albedo[3], f0[3], rough, E[3], refl[3];
+               nmf_v3 V, Nf; int count; uint64_t skey; float ngrad[3], sgn; int ray0; };
+  struct Sec { float o[3], d[3]; uint64_t key; float mip; std::vector<Smp> sm; float acc; double usum; float lin[3], bg[3], rgb[3]; };
+  // ---- shared: march one ray (level 0: eval-key by (seed, id); level 1: key given) and shade heads; counts are set by the caller ----
+  auto march = [&](const float* o, const float* d, uint64_t rkey, float near_, std::vector<Smp>& sm, float& acc, double* usum) {
+    const float tmin = nmf_ray_tmin(o, d, s->aabb0, s->aabb1, near_, s->far);
+    std::vector<float> z(S);
+    std::vector<uint8_t> ok(S);
+    double run = 0.0;
+    for (int k = 0; k < S; ++k) {
+      run += (double)nmf_jitter_step(rkey, k, s->stepsize);
+      z[k] = NMF_ADD(tmin, (float)run);
+      float p[3];
+      nmf_step_pos(o, d, z[k], p);
+      bool v = nmf_inside(p, s->aabb0, s->aabb1);
+      if (v && s->has_occ) {
+        float xn[3];
+        nmf_normalize_xyz(*s, p, xn);
+        v = nmf_occupied(s->occ_vox, s->occ_cell, s->ow, s->oh, s->od, s->opitch, xn[0], xn[1], xn[2]);
+      }
+      ok[k] = v;
+      if (usum) *usum += (double)nmf_uniform(nmf_mix64(rkey, (uint64_t)k), NMF_STREAM_BOUNCE);
+    }
+    float T = 1.0f;
+    acc = 0.f;
+    for (int k = 0; k < S; ++k) {
+      if (!ok[k]) continue;
+      Smp q;
+      q.z = z[k];
+      q.dist = (k + 1 < S ? NMF_SUB(z[k + 1], q.z) : 0.f) * s->distance_scale;
+      float xn[3];
+      nmf_step_pos(o, d, q.z, q.pos);
+      nmf_normalize_xyz(*s, q.pos, xn);
+      q.t = nmf_vm_taps(*s, xn);
+      q.f = 0.f;
+      for (int gi = 0; gi < 4; ++gi) q.f += nmf_density_group(*s, q.t, gi);
+      q.alpha = 1.0f - expf(-nmf_feature2density(q.f, s->density_shift) * q.dist);
+      q.T = T;
+      q.w = q.alpha * T;
+      T *= 1.0f - q.alpha + 1e-10f;
+      acc += q.w;
+      float coef[72];
+      nmf_app_coef(*s, q.t, coef);
+      for (int oo = 0; oo < 24; ++oo) {
+        float a = 0.f;
+        for (int j = 0; j < 72; ++j) a += s->basis_t[j * 24 + oo] * coef[j];
+        q.feat[oo] = a;
+      }
+      float grad[3] = {0.f, 0.f, 0.f};
+      for (int l = 0; l < 8; ++l) nmf_normal_lane(*s, q.t, l, grad);
+      const nmf_v3 nrm = nmf_normal_from_grad(*s, grad);
+      float lin11[11];
+      for (int h = 0; h < 11; ++h) {
+        float v = s->head_b[h];
+        for (int i = 0; i < 24; ++i) v += s->head_w[h * 24 + i] * q.feat[i];
+        lin11[h] = v;
+      }
+      float sh[9];
+      nmf_sh9(nrm, sh);
+      for (int c = 0; c < 3; ++c) {
+        q.albedo[c] = nmf_clampf(nmf_sigmoid(s->diffuse_mul * lin11[c] + s->diffuse_bias), 0.f, 1.f);
+        q.f0[c] = nmf_sigmoid(lin11[6 + c] + s->f0_bias);
+        float e = 0.f;
+        for (int i = 0; i < 9; ++i) e += s->sh_conv[i * 3 + c] * sh[i];
+        q.E[c] = e;
+        q.refl[c] = 0.f;
+      }
+      q.rough = nmf_clampf(nmf_sigmoid(lin11[9] + s->roughness_bias) / 2.0f, 1e-2f, 1.0f);
+      q.V = nmf_mk3(-d[0], -d[1], -d[2]);
+      const float vn = nmf_dot(q.V, nrm);
+      q.sgn = vn > 0.f ? 1.f : (vn < 0.f ? -1.f : 0.f);
+      q.Nf = nmf_mk3(nrm.x * q.sgn, nrm.y * q.sgn, nrm.z * q.sgn);
+      for (int c = 0; c < 3; ++c) q.ngrad[c] = grad[c];
+      q.skey = nmf_mix64(rkey, (uint64_t)k);
+      const uint64_t nseed = nmf_noise_seed(q.skey);
+      for (uint32_t pp = 0; pp < 12; ++pp) {
+        float n0, n1;
+        nmf_noise_pair(nseed, pp, &n0, &n1);
+        q.nfeat[2 * pp] = q.feat[2 * pp] + s->anoise * n0;
+        q.nfeat[2 * pp + 1] = q.feat[2 * pp + 1] + s->anoise * n1;
+      }
+      q.count = 0; q.ray0 = -1; q.dw = 0.f;
+      sm.push_back(q);
+    }
+  };
+  auto sample_u = [&](const Smp& q, std::vector<float>& u) {
+    const float offu = 0.25f * nmf_uniform(q.skey, NMF_STREAM_OFF_U), offv = 0.25f * nmf_uniform(q.skey, NMF_STREAM_OFF_V);
+    u.resize(2 * (size_t)q.count);
+    for (int j = 0; j < q.count; ++j) { u[2 * j] = nmf_wrap01(s->sobol[2 * j] + offu); u[2 * j + 1] = nmf_wrap01(s->sobol[2 * j + 1] + offv); }
+  };
+  // ---- level 0 ----
+  std::vector<std::vector<Smp>> L0(n);
+  std::vector<float> acc0(n);
+  std::vector<Sec> secs;
+  for (int r = 0; r < n; ++r) {
+    const uint64_t rkey = nmf_primary_key(tp->seed, tp->ray_id0 + (uint64_t)r);
+    march(rays + 6 * r, rays + 6 * r + 3, rkey, s->near, L0[r], acc0[r], nullptr);
+    for (Smp& q : L0[r]) {
+      const float kf = floorf(q.w * (float)s->rays_per_ray + nmf_uniform(q.skey, NMF_STREAM_BOUNCE) - 0.5f);
+      q.count = (int)nmf_clampf(kf, 0.f, (float)NMF_MAX_BOUNCE);
+      if (q.count == 0) continue;
+      q.ray0 = (int)secs.size();
+      std::vector<float> u;
+      sample_u(q, u);
+      for (int j = 0; j < q.count; ++j) {
+        const NmfGGX fw = nmf_ggx_sample(u[2 * j], u[2 * j + 1], q.V, q.Nf, q.rough);
+        Sec sc;
+        sc.o[0] = q.pos[0] + fw.L.x * 5e-3f; sc.o[1] = q.pos[1] + fw.L.y * 5e-3f; sc.o[2] = q.pos[2] + fw.L.z * 5e-3f;
+        sc.d[0] = fw.L.x; sc.d[1] = fw.L.y; sc.d[2] = fw.L.z;
+        sc.key = nmf_mix64(q.skey, (uint64_t)j + NMF_STREAM_RAY0);
+        sc.mip = -logf((float)q.count) - fw.logpdf;
+        sc.usum = 0.0;
+        secs.push_back(sc);
+      }
+    }
+  }
+  // ---- level 1: march, chunk totals, budgeted counts, shading ----
+  long long n1 = 0;
+  double wsum = 0.0;
+  for (Sec& sc : secs) {
+    march(sc.o, sc.d, sc.key, NMF_MUL(3.0f, s->stepsize), sc.sm, sc.acc, &sc.usum);
+    n1 += (long long)sc.sm.size();
+    wsum += (double)sc.acc + 1e-3 * sc.usum;
+  }
+  n_samples[0] = 0;
+  for (int r = 0; r < n; ++r) n_samples[0] += (int)L0[r].size();
+  n_samples[1] = (int)n1;
+  const float wsumf = fmaxf((float)wsum, 1e-3f);
+  const int budget = s->max_brdf_rays1;
+  const int Nb = budget - (int)n1;
+  auto shade_fwd = [&](Smp& q) {        // all rays to the environment
+    for (int c = 0; c < 3; ++c) q.refl[c] = 0.f;
+    if (q.count == 0) return;
+    std::vector<float> u;
+    sample_u(q, u);
+    for (int j = 0; j < q.count; ++j) {
+      const NmfGGX fw = nmf_ggx_sample(u[2 * j], u[2 * j + 1], q.V, q.Nf, q.rough);
+      const float mip = -logf((float)q.count) - fw.logpdf;
+      float x[66], bw[3], inc[3];
+      nmf_brdf_input(q.nfeat, fw.half_l, fw.diff_l, q.rough, x);
+      nmf_brdf_row_fwd_bwd(x, s->brdf_w0t, s->brdf_b0, s->brdf_w1t, s->brdf_b1, s->brdf_w2t, s->brdf_b2, s->brdf_bias, nullptr, bw,
+                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+      nmf_env_lookup1(s->env_sat, s->env_h, s->env_w, s->env_mipbias, s->env_top, s->env_bot, fw.L, mip, inc);
+      const float cost = fabsf(nmf_dot(q.V, fw.H));
+      for (int c = 0; c < 3; ++c) {
+        const float F = nmf_fresnel(q.f0[c], cost);
+        q.refl[c] += (F * inc[c] * bw[c] + (1.0f - F) * q.albedo[c] * q.E[c]) / (float)q.count;
+      }
+    }
+  };
+  for (Sec& sc : secs) {
+    for (int c = 0; c < 3; ++c) sc.lin[c] = 0.f;
+    for (Smp& q : sc.sm) {
+      const float U = nmf_uniform(q.skey, NMF_STREAM_BOUNCE);
+      const float wj = q.w + 1e-3f * U;
+      const float kf = Nb > 0 ? floorf(wj / wsumf * (float)Nb + 1.0f) : floorf(wj / wsumf * (float)budget + 0.5f);
+      q.count = (int)nmf_clampf(kf, 0.f, (float)NMF_MAX_BOUNCE);
+      shade_fwd(q);
+      for (int c = 0; c < 3; ++c) sc.lin[c] += q.w * q.refl[c];
+    }
+    nmf_env_lookup1(s->env_sat, s->env_h, s->env_w, s->env_mipbias, s->env_top, s->env_bot, nmf_mk3(sc.d[0], sc.d[1], sc.d[2]), sc.mip, sc.bg);
+    for (int c = 0; c < 3; ++c) sc.rgb[c] = sc.lin[c] + (1.0f - sc.acc) * sc.bg[c];
+  }
+  // ---- level 0 reflect + loss + reverse ----
+  loss[0] = loss[1] = 0.0;
+  const float bgw[3] = {1.f, 1.f, 1.f};
+  // reverse of one sample's shading given d loss / d reflect (gre): level-independent part (heads, BRDF, features, normals)
+  auto factors_bwd = [&](const Smp& q, const float* dnfeat, const float* dR0, const float* ddiff, float drough, const float* dNf) {
+    float g_alb[3], dfeat_h[24];
+    for (int c = 0; c < 3; ++c) g_alb[c] = ddiff[c] * q.E[c];
+    nmf_heads_bwd(q.feat, s->head_w, s->head_b, s->diffuse_mul, s->diffuse_bias, s->f0_bias, s->roughness_bias, g_alb, dR0, drough,
+                  d_head_w, d_head_b, dfeat_h);
+    float coef[72], dcoef[72];
+    nmf_app_coef(*s, q.t, coef);
+    for (int j = 0; j < 72; ++j) {
+      float a = 0.f;
+      for (int oo = 0; oo < 24; ++oo) {
+        const float df = dnfeat[oo] + dfeat_h[oo];
+        g->basis_t[j * 24 + oo] += coef[j] * df;
+        a += s->basis_t[j * 24 + oo] * df;
+      }
+      dcoef[j] = a;
+    }
+    nmf_app_bwd(*s, q.t, dcoef, g->a_plane, g->a_line);
+    if (dNf) {
+      float dn[3] = {q.sgn * dNf[0], q.sgn * dNf[1], q.sgn * dNf[2]}, dgrad[3];
+      nmf_normal_vec_bwd(*s, q.ngrad, dn, dgrad);
+      nmf_normal_bwd(*s, q.t, dgrad, gpack, glpack);
+    }
+  };
+  auto composite_bwd = [&](std::vector<Smp>& sm) {
+    float suffix = 0.f;
+    for (int i = (int)sm.size() - 1; i >= 0; --i) {
+      const Smp& q = sm[i];
+      const float dsigma = nmf_composite_bwd(q.dw, q.T, q.alpha, q.dist, suffix);
+      suffix += q.dw * q.w;
+      const float df = dsigma * nmf_feature2density_grad(q.f, s->density_shift);
+      if (df != 0.f) nmf_density_bwd(*s, q.t, df, g->d_plane, g->d_line);
+    }
+  };
+  // tangent of a secondary ray's radiance along a tangent dL of its direction (V1 = -d1; background lookup)
+  auto sec_tangent = [&](const Sec& sc, nmf_v3 dL, float* out) {
+    out[0] = out[1] = out[2] = 0.f;
+    const NmfDual3 Vd = nmf_d3(nmf_dmk(-sc.d[0], -dL.x), nmf_dmk(-sc.d[1], -dL.y), nmf_dmk(-sc.d[2], -dL.z));
+    for (const Smp& q : sc.sm) {
+      if (q.count == 0) continue;
+      std::vector<float> u;
+      sample_u(q, u);
+      float diffuse[3], refl[3], drefl[3];
+      for (int c = 0; c < 3; ++c) diffuse[c] = q.albedo[c] * q.E[c];
+      nmf_bounce_sample_tangent(*s, q.nfeat, Vd, q.Nf, q.f0, diffuse, q.rough, u.data(), q.count, refl, drefl);
+      for (int c = 0; c < 3; ++c) out[c] += q.w * drefl[c];
+    }
+    const NmfDual3 Dd = nmf_d3(nmf_dmk(sc.d[0], dL.x), nmf_dmk(sc.d[1], dL.y), nmf_dmk(sc.d[2], dL.z));
+    float bgv[3], dbg[3];
+    nmf_env_lookup1_d(s->env_sat, s->env_h, s->env_w, s->env_mipbias, s->env_top, s->env_bot, Dd, sc.mip, bgv, dbg);
+    for (int c = 0; c < 3; ++c) out[c] += (1.0f - sc.acc) * dbg[c];
+  };
+  for (int r = 0; r < n; ++r) {
+    float lin[3] = {0.f, 0.f, 0.f};
+    std::vector<std::vector<float>> bws(L0[r].size());
+    for (size_t si = 0; si < L0[r].size(); ++si) {
+      Smp& q = L0[r][si];
+      if (q.count == 0) continue;
+      std::vector<float> u;
+      sample_u(q, u);
+      bws[si].resize(3 * (size_t)q.count);
+      for (int j = 0; j < q.count; ++j) {
+        const NmfGGX fw = nmf_ggx_sample(u[2 * j], u[2 * j + 1], q.V, q.Nf, q.rough);
+        float x[66];
+        nmf_brdf_input(q.nfeat, fw.half_l, fw.diff_l, q.rough, x);
+        nmf_brdf_row_fwd_bwd(x, s->brdf_w0t, s->brdf_b0, s->brdf_w1t, s->brdf_b1, s->brdf_w2t, s->brdf_b2, s->brdf_bias, nullptr,
+                             &bws[si][3 * j], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        const float cost = fabsf(nmf_dot(q.V, fw.H));
+        const Sec& sc = secs[q.ray0 + j];
+        for (int c = 0; c < 3; ++c) {
+          const float F = nmf_fresnel(q.f0[c], cost);
+          q.refl[c] += (F * sc.rgb[c] * bws[si][3 * j + c] + (1.0f - F) * q.albedo[c] * q.E[c]) / (float)q.count;
+        }
+      }
+      for (int c = 0; c < 3; ++c) lin[c] += q.w * q.refl[c];
+    }
+    float gl[3], ga;
+    loss[0] += nmf_train_loss_ray(lin, acc0[r], bgw, gt + 3 * r, tp->lambda_pred, rgb_map + 3 * r, gl, &ga);
+    loss[1] += acc0[r];
+    for (size_t si = 0; si < L0[r].size(); ++si) {
+      Smp& q = L0[r][si];
+      q.dw = ga;
+      for (int c = 0; c < 3; ++c) q.dw += gl[c] * q.refl[c];
+      if (q.count == 0) continue;
+      std::vector<float> u;
+      sample_u(q, u);
+      float diffuse[3], gm[3], dR0[3] = {0.f, 0.f, 0.f}, ddiff[3] = {0.f, 0.f, 0.f}, dnfeat[24], dNf[3] = {0.f, 0.f, 0.f};
+      float dr = 0.f;
+      for (int k = 0; k < 24; ++k) dnfeat[k] = 0.f;
+      for (int c = 0; c < 3; ++c) { diffuse[c] = q.albedo[c] * q.E[c]; gm[c] = q.w * gl[c] / (float)q.count; }
+      for (int j = 0; j < q.count; ++j) {
+        Sec& sc = secs[q.ray0 + j];
+        const float u1 = u[2 * j], u2 = u[2 * j + 1];
+        const NmfGGX fw = nmf_ggx_sample(u1, u2, q.V, q.Nf, q.rough);
+        const NmfGGXdr dg = nmf_ggx_sample_dr(u1, u2, q.V, q.Nf, q.rough);
+        const float vh = nmf_dot(q.V, dg.H), cost = fabsf(vh), svh = vh > 0.f ? 1.f : (vh < 0.f ? -1.f : 0.f);
+        float a_R0[3], a_inc[3], a_bw[3], a_diff[3];
+        const float dcost = nmf_fresnel_mix_bwd(q.f0, cost, sc.rgb, &bws[si][3 * j], diffuse, gm, a_R0, a_inc, a_bw, a_diff);
+        for (int c = 0; c < 3; ++c) { dR0[c] += a_R0[c]; ddiff[c] += a_diff[c]; }
+        float tang[3];
+        sec_tangent(sc, dg.dL, tang);
+        dr += dcost * svh * nmf_dot(q.V, dg.dH) + a_inc[0] * tang[0] + a_inc[1] * tang[1] + a_inc[2] * tang[2];
+        if (!detach_N)
+          for (int c = 0; c < 3; ++c) {
+            const NmfGGXdr dn = nmf_ggx_sample_dN(u1, u2, q.V, q.Nf, q.rough, c);
+            sec_tangent(sc, dn.dL, tang);
+            dNf[c] += dcost * svh * nmf_dot(q.V, dn.dH) + a_inc[0] * tang[0] + a_inc[1] * tang[1] + a_inc[2] * tang[2];
+          }
+        float x[66], bw2[3];
+        nmf_brdf_input(q.nfeat, fw.half_l, fw.diff_l, q.rough, x);
+        nmf_brdf_row_fwd_bwd(x, s->brdf_w0t, s->brdf_b0, s->brdf_w1t, s->brdf_b1, s->brdf_w2t, s->brdf_b2, s->brdf_bias, a_bw, bw2, bgr.w0t,
+                             bgr.b0, bgr.w1t, bgr.b1, bgr.w2t, bgr.b2, dnfeat);
+        // ---- level-1 reverse with the linear upstream a_inc on this secondary ray's radiance ----
+        float gbg = 0.f;
+        for (int c = 0; c < 3; ++c) gbg += a_inc[c] * sc.bg[c];
+        float gbg3[3] = {(1.0f - sc.acc) * a_inc[0], (1.0f - sc.acc) * a_inc[1], (1.0f - sc.acc) * a_inc[2]};
+        nmf_env_lookup1_bwd_map(gsat, s->env_h, s->env_w, s->env_mipbias, nmf_mk3(sc.d[0], sc.d[1], sc.d[2]), sc.mip, gbg3, g_top, g_bot);
+        for (Smp& q1 : sc.sm) {
+          q1.dw = -gbg;
+          for (int c = 0; c < 3; ++c) q1.dw += a_inc[c] * q1.refl[c];
+          if (q1.count == 0) continue;
+          std::vector<float> u1v;
+          sample_u(q1, u1v);
+          float diffuse1[3], gre1[3], dR01[3], ddiff1[3], drough1, dnfeat1[24], dNf1[3];
+          for (int c = 0; c < 3; ++c) { diffuse1[c] = q1.albedo[c] * q1.E[c]; gre1[c] = q1.w * a_inc[c]; }
+          nmf_bounce_sample_bwd(*s, q1.nfeat, q1.V, q1.Nf, q1.f0, diffuse1, q1.rough, u1v.data(), q1.count, gre1, dR01, ddiff1, &drough1,
+                                dnfeat1, bgr, gsat, g_top, g_bot, detach_N ? nullptr : dNf1);
+          factors_bwd(q1, dnfeat1, dR01, ddiff1, drough1, detach_N ? nullptr : dNf1);
+        }
+        composite_bwd(sc.sm);
+      }
+      factors_bwd(q, dnfeat, dR0, ddiff, dr, detach_N ? nullptr : dNf);
+    }
+    composite_bwd(L0[r]);
+  }
+}

@@ -822,3 +822,79 @@ def test_bounce_sample_view_tangent_matches_autograd(hostcheck):
     assert torch.allclose(refl, reflect.detach(), rtol=1e-3, atol=1e-3)
     rel = float((drefl - want).norm() / want.norm())
     assert rel < 2e-3, rel
+
+
+@pytest.mark.parametrize("name,detach_N", [("microfacet_g40", True), ("microfacet_g40", False), ("microfacet_noncubic", False)])
+def test_train_microfacet_retrace_host_gradients(hostcheck, name, detach_N):
+    """The reverse pass of the microfacet training forward WITH its re-traced level, composed on the host (tests/hostcheck
+    hc_train_microfacet_retrace): every bounce ray of the primary samples is re-traced (max_retrace_rays above their number, so
+    the top-k selection is the identity), the secondary rays are marched with their own jitter, shaded with the budgeted
+    bounce counts of recur = 1 (pt_selectors.py), composited over the environment; the reverse pass sends each parent ray's
+    d L_in into its secondary ray (parameters of both levels) and brings the secondary radiance's dependence on the parent's
+    bounce direction back as a tangent (view vector of the level-1 shading + background lookup; positions are detached,
+    tensoRF.py:182-183).  Loss, sample counts of both levels and the gradient of EVERY parameter against autograd through
+    the oracle's render_chunk(is_train=True), detach_N on and off."""
+    import torch.nn.functional as Fn
+    from nmf_b200 import _lib
+    from nmf_b200.train import PlainGradBuffers
+    fix = load_fixture(name)
+    hp = dict(max_retrace_rays=(100000,), max_brdf_rays=(650000, 20000))
+    osc = oracle_scene(fix, requires_grad=True, **hp)
+    dsc = device_scene(fix, "cpu", sh_conv=O.sh_irradiance_coeffs(oracle_scene(fix)), **hp)
+    n, seed = 12, 21
+    rays = fix["rays"][40:40+n].contiguous()
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
+    keys = KR.primary_ray_keys(seed, np.arange(n).astype(np.uint64))
+    ims, st = O.render_chunk(osc, rays, fix["focal"], KR.KeyedRNG(), keys, draw_debug=False, is_train=True, detach_N=detach_N)
+    photo = ((ims["rgb_map"].clip(0, 1) - gt.clip(0, 1)) ** 2).sum()
+    photo.backward()
+    P = osc.params
+    gb = PlainGradBuffers(dsc)
+    tp = _lib.NmfTrain(n_rays=n, focal=float(fix["focal"]), seed=seed, ray_id0=0, ray_ids=None, max_samples=-1, cap_samples=1 << 20, lambda_pred=0.0, white_bg=1)
+    z = lambda *s: torch.zeros(*s)
+    dhw, dhb = z(11, 24), z(11)
+    dw0t, db0, dw1t, db1, dw2t, db2 = z(66, 64), z(64), z(64, 64), z(64), z(64, 4), z(4)
+    h, w = osc.bg_mat.shape[-2:]
+    gsat, g_top, g_bot = z(h, w, 4), z(3), z(3)
+    rgb_map = z(n, 3)
+    loss = torch.zeros(3, dtype=torch.float64)
+    ns = torch.zeros(2, dtype=torch.int32)
+    gpack = [torch.zeros_like(dsc.keep[f"dpack{p}"]) for p in range(3)]
+    glpack = [torch.zeros_like(dsc.keep[f"lpack{p}"]) for p in range(3)]
+    parr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
+    hostcheck.hc_train_microfacet_retrace(dsc.ref(), C.byref(tp), ptr(rays), ptr(gt), C.byref(gb.c), ptr(dhw), ptr(dhb), ptr(dw0t), ptr(db0), ptr(dw1t), ptr(db1),
+                                   ptr(dw2t), ptr(db2), ptr(gsat), ptr(g_top), ptr(g_bot), ptr(rgb_map), ptr(loss), ptr(ns), int(detach_N), parr(gpack), parr(glpack))
+    assert ns.tolist() == list(st["n_samples"]) and len(st["n_samples"]) == 2 and ns[1] > 1000      # both levels, sample counts identical
+    assert float((rgb_map - ims["rgb_map"].detach()).abs().max()) < 2e-4
+    assert abs(float(loss[0]) - float(photo.detach())) <= 1e-4 * max(1.0, float(photo.detach()))
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
+    got = dict(gb.reference_layout())
+    kx, ky = O.derivative_stencils()
+    conv = lambda img, k: Fn.conv2d(img.permute(1, 0, 2, 3), k, stride=1, padding=(2, 2)).permute(1, 0, 2, 3)
+    def adjoint(shape, k, gimg):
+        xz = torch.zeros(shape, requires_grad=True)
+        return torch.autograd.grad(conv(xz, k), xz, gimg)[0]
+    for p in range(3):
+        gp = gpack[p].reshape(gpack[p].shape[0], gpack[p].shape[1], 48)
+        img = lambda sl: gp[..., sl].permute(2, 0, 1)[None].contiguous()
+        key = f"rf.density_rf.app_plane.{p}"
+        got[key] = got[key] + img(slice(0, 16)) + adjoint(got[key].shape, kx, img(slice(16, 32))) + adjoint(got[key].shape, ky, img(slice(32, 48)))
+        gl = glpack[p].reshape(-1, 4, 8)
+        lin_img = lambda sl: gl[:, :, sl].reshape(-1, 16).t()[None, :, :, None].contiguous()
+        key = f"rf.density_rf.app_line.{p}"
+        got[key] = got[key] + lin_img(slice(0, 4)) + adjoint(got[key].shape, ky, lin_img(slice(4, 8)))
+    names = ("diffuse", "tint", "f0", "roughness")
+    rows = {"diffuse": slice(0, 3), "tint": slice(3, 6), "f0": slice(6, 9), "roughness": slice(9, 11)}
+    for hname in names:
+        got[f"model.diffuse_module.{hname}_mlp.0.weight"] = dhw[rows[hname]]
+        got[f"model.diffuse_module.{hname}_mlp.0.bias"] = dhb[rows[hname]]
+    for i, (wt, b) in zip((0, 2, 4), ((dw0t, db0), (dw1t, db1), (dw2t, db2))):
+        got[f"model.brdf.mlp.{i}.weight"] = wt.t(); got[f"model.brdf.mlp.{i}.bias"] = b
+    fin = torch.zeros(3, h, w)
+    hostcheck.hc_env_map_grad_finish(ptr(gsat), h, w, ptr(g_top), ptr(g_bot), ptr(osc.bg_mat.detach()[0].contiguous()), C.c_float(float(osc.brightness.detach())), C.c_float(float(osc.mul.detach())), ptr(fin))
+    got["bg_module.bg_mat"] = fin[None]
+    report = {k: rel(got[k].reshape(p.grad.shape), p.grad) for k, p in P.items()
+              if p.grad is not None and float(p.grad.abs().max()) > 0.0 and k in got}
+    assert len(report) >= 20, len(report)
+    bad = {k: v for k, v in report.items() if v > (2e-2 if "density_rf" in k else 5e-3)}
+    assert not bad, bad
