@@ -1,7 +1,8 @@
-// Per-element backward math of the MICROFACET model (remainder) -- first stage:
-// the pieces whose gradient can be stated per bounce ray / per sample, compiled for the host (tests/hostcheck) and checked
-// against the oracle's autograd (= the reference's gradient, oracle/check_train.py) in the CPU suite.  No kernel
-// includes this header yet: the reverse-pass kernels that will call it are the next step, this file fixes their math.
+// Per-element backward math of the MICROFACET model (remainder): every piece of the
+// reverse pass stated per bounce ray / per sample / per texel, compiled for the host (tests/hostcheck) and checked against
+// the oracle's autograd (= the reference's gradient, oracle/check_train.py) in the CPU suite -- piece by piece and composed
+// into the whole two-level training reverse pass (hc_train_microfacet, hc_train_microfacet_retrace).  No kernel includes
+// this header yet: the reverse-pass kernels that will call it are the next step, this file fixes their math.
 //
 //   nmf_ggx_sample_dr     d L / d roughness and d H / d roughness of the GGX VNDF sample (brdf_samplers/ggx.py:61-226):
 //                         forward-mode (dual-number) restatement of nmf_ggx_frame + nmf_ggx_sample_f.  The reference
