@@ -359,6 +359,19 @@ typedef struct NmfAdam {
 int nmf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const NmfAdam* adam,
                   const double* sq_norm, void* stream);
 
+/* Reverse pass of IntegralEquirect lookups w.r.t. the map (modules/integral_equirect.py:263-273 activation_fn / calc_sat,
+ * 409-504 forward, under autograd) -- the environment stage of the microfacet backward.
+ * Step 1, per batch of lookups: dirs (n,3), mip (n), g (n,3) = d loss / d rgb are scattered with the forward's own box
+ * walk into gsat = [h][w][4] floats followed by 8 floats (pole-row terms: top rgb, pad, bottom rgb, pad); the caller
+ * zeroes gsat (h*w*4 + 8 floats) before the first batch of an optimiser step; batches accumulate. */
+int nmf_env_lookup_bwd_scatter(const NmfScene* scene, const float* dirs, const float* mip, const float* g, int n,
+                               float* gsat, void* stream);
+/* Step 2, once per optimiser step: adjoint of the double cumsum (two reverse prefix sums, gsat is overwritten), the
+ * pole-row means and the clipped exp activation: d_bg_mat (3,h,w) += ..., and when not NULL d_brightness[0] += ...,
+ * d_mul[0] += ... (device scalars).  bg_mat is the (3,h,w) parameter, brightness / mul its scalar parameters. */
+int nmf_env_lookup_bwd_finish(float* gsat, int h, int w, const float* bg_mat, float brightness, float mul,
+                              float* d_bg_mat, float* d_brightness, float* d_mul, void* stream);
+
 /* Resolution schedule (fields/tensor_base.py:234-243 -> fields/tensoRF.py:208-227, 408-413): TensoRF.upsample is
  * F.interpolate(mode="bilinear", align_corners=True) of every factor.  src (C,H,W) -> dst (C,H2,W2), both in the
  * reference's own parameter layout (a line (1,C,N,1) is H = N, W = 1). */

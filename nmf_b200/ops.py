@@ -40,6 +40,39 @@ def env_lookup(scene, dirs, mip):
     return out
 
 
+class EnvMapGrad:
+    """Reverse pass of IntegralEquirect lookups w.r.t. the map (modules/integral_equirect.py:263-273, 409-504 under
+    autograd): `scatter` once per batch of lookups (accumulates), `finish` once per optimiser step.
+    nmf_env_lookup_bwd_scatter / nmf_env_lookup_bwd_finish (csrc/nmf_env_bwd.cu)."""
+
+    def __init__(self, scene):
+        self.scene = scene
+        self.h, self.w = int(scene.c.env_h), int(scene.c.env_w)
+        self.gsat = torch.zeros(self.h * self.w * 4 + 8, device=scene.device)
+
+    def zero(self):
+        self.gsat.zero_()
+
+    def scatter(self, dirs, mip, g):
+        d = _f32(dirs.reshape(-1, 3), self.scene.device)
+        m = _f32(mip.reshape(-1), self.scene.device)
+        u = _f32(g.reshape(-1, 3), self.scene.device)
+        if not (d.shape[0] == m.shape[0] == u.shape[0]):
+            raise _lib.NmfError("EnvMapGrad.scatter: dirs / mip / g disagree on the number of lookups")
+        _lib.check(_lib.lib().nmf_env_lookup_bwd_scatter(self.scene.ref(), _p(d), _p(m), _p(u), d.shape[0], _p(self.gsat), _stream()),
+                   "nmf_env_lookup_bwd_scatter")
+
+    def finish(self, bg_mat, brightness, mul):
+        """-> (d bg_mat (1,3,h,w), d brightness, d mul); consumes (and re-zeroes) the accumulated scatter image."""
+        bg = _f32(bg_mat.reshape(3, self.h, self.w), self.scene.device)
+        d_bg = torch.zeros_like(bg)
+        d_sc = torch.zeros(2, device=bg.device)
+        _lib.check(_lib.lib().nmf_env_lookup_bwd_finish(_p(self.gsat), self.h, self.w, _p(bg), float(brightness), float(mul), _p(d_bg),
+                                                        _p(d_sc[0:1]), _p(d_sc[1:2]), _stream()), "nmf_env_lookup_bwd_finish")
+        self.zero()
+        return d_bg.reshape(1, 3, self.h, self.w), d_sc[0], d_sc[1]
+
+
 def vm_density(scene, xyz, activate=True):
     x = _f32(xyz, scene.device)
     out = torch.empty(x.shape[0], device=x.device)

@@ -570,7 +570,7 @@ class IntegralEquirect(nn.Module):
         self.register_parameter("mul", nn.Parameter(torch.tensor(1.0, dtype=float)))
         self.mipnoise, self.lr, self.mul_lr, self.mipbias_lr, self.brightness_lr = mipnoise, lr, mul_lr, mipbias_lr, brightness_lr
         self.betas, self.mul_betas = list(betas), list(mul_betas)
-        self._scene, self._key = None, None
+        self._scene, self._key, self._grad_acc = None, None, None
 
     @property
     def bg_resolution(self):
@@ -625,6 +625,29 @@ class IntegralEquirect(nn.Module):
     def forward(self, viewdirs, saSample, max_level=None):
         """integral_equirect.py:409-504"""
         return ops.env_lookup(self.scene(), viewdirs, saSample)
+
+    @torch.no_grad()
+    def accumulate_grad(self, viewdirs, saSample, grad_rgb):
+        """Reverse pass of `forward` w.r.t. the map for one batch of lookups (what autograd does to the reference's module:
+        integral_equirect.py:263-273, 409-504).  grad_rgb (n,3) = d loss / d forward(viewdirs, saSample).  Batches
+        accumulate on the device until `finish_grad`."""
+        sc = self.scene()
+        if self._grad_acc is None or self._grad_acc.scene is not sc:
+            self._grad_acc = ops.EnvMapGrad(sc)
+        self._grad_acc.scatter(viewdirs, saSample, grad_rgb)
+
+    @torch.no_grad()
+    def finish_grad(self):
+        """Once per optimiser step: adds the accumulated gradient to bg_mat.grad / brightness.grad / mul.grad (created when
+        absent, like autograd's accumulation).  NOT produced here: d mipbias (the reference differentiates the box size
+        w.r.t. the bias, integral_equirect.py:373-397; that is the box-geometry derivative of DESIGN.md section 9, whose
+        forward-mode math is nmf_env_lookup1_d) -- mipbias.grad is left untouched."""
+        if self._grad_acc is None:
+            return
+        d_bg, d_br, d_mul = self._grad_acc.finish(self.bg_mat, self.brightness, self.mul)
+        for p, g in ((self.bg_mat, d_bg), (self.brightness, d_br), (self.mul, d_mul)):
+            g = g.to(p.dtype).reshape(p.shape)
+            p.grad = g if p.grad is None else p.grad + g
 
     @torch.no_grad()
     def get_spherical_harmonics(self, G, mipval=-5):

@@ -1,0 +1,113 @@
+"""GPU parity of the environment-map reverse pass (csrc/nmf_env_bwd.cu: nmf_env_lookup_bwd_scatter / _finish) against
+torch autograd through the oracle's env_lookup (= the reference's IntegralEquirect under autograd,
+modules/integral_equirect.py:263-273, 409-504).  Floating point: the stated tolerances are relative to the largest entry of
+the reference gradient (fp32 atomics + fp32 prefix sums over 512 x 1024 against the oracle's fp64 SAT).
+
+This file sorts last on purpose: these are the newest kernels (first stage of DESIGN.md section 9 on the device).
+"""
+import pytest
+import torch
+
+from conftest import device_scene, load_fixture, oracle_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from nmf_b200 import _lib
+    _lib.lib()          # raises if the extension is missing: no fallback
+    return torch.device("cuda:0")
+
+
+def _lookups(n, seed):
+    from oracle import nmf_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    d = O.unit(torch.randn(n, 3, generator=g))
+    d[:6] = torch.tensor([[0, 0, 1.0], [0, 0, -1.0], [-1.0, 1e-4, 0.0], [-1.0, -1e-4, 0.0], [1.0, 0, 0], [0, 1.0, 0]])
+    d[6:200, 2] = d[6:200, 2].sign() * 0.97                        # near the poles: overhang boxes
+    d = O.unit(d)
+    sa = torch.rand(n, generator=g) * 14 - 10                      # every mip level
+    up = torch.randn(n, 3, generator=g)
+    return d, sa, up
+
+
+@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_g56_ship", "fullsize_512x1024"])
+def test_env_map_gradient_on_device(env, name):
+    from nmf_b200 import ops
+    from oracle import nmf_oracle as O
+    if name == "fullsize_512x1024":                                # the map size of configs/model/microfacet_tensorf2.yaml
+        fix = load_fixture("microfacet_g40")
+        fix["state"]["bg_module.bg_mat"] = torch.randn(1, 3, 512, 1024, generator=torch.Generator().manual_seed(11)) * 0.7 - 0.5
+    else:
+        fix = load_fixture(name)
+    osc = oracle_scene(fix, requires_grad=True)
+    dsc = device_scene(fix, env)
+    n = 40000
+    d, sa, up = _lookups(n, 4)
+    (O.env_lookup(osc, d, sa) * up).sum().backward()
+    want = osc.params["bg_module.bg_mat"].grad.float()             # (1,3,h,w)
+    acc = ops.EnvMapGrad(dsc)
+    half = n // 2                                                  # two batches accumulate into one optimiser step
+    acc.scatter(d[:half].cuda(), sa[:half].cuda(), up[:half].cuda())
+    acc.scatter(d[half:].cuda(), sa[half:].cuda(), up[half:].cuda())
+    d_bg, d_br, d_mul = acc.finish(osc.bg_mat.detach().cuda(), float(osc.brightness.detach()), float(osc.mul.detach()))
+    torch.cuda.synchronize()
+    assert d_bg.shape == want.shape
+    scale = float(want.abs().max())
+    assert scale > 0
+    err = (d_bg.cpu() - want).abs()
+    assert float(err.max()) < 5e-3 * scale and float(err.mean()) < 5e-5 * scale, (float(err.max()) / scale, float(err.mean()) / scale)
+    for got, key in ((d_br, "bg_module.brightness"), (d_mul, "bg_module.mul")):
+        ref = osc.params[key].grad
+        if ref is not None:
+            assert abs(float(got) - float(ref)) < 2e-3 * max(1.0, abs(float(ref))), (key, float(got), float(ref))
+    assert float(acc.gsat.abs().sum()) == 0.0                      # finish() leaves the accumulator ready for the next step
+
+
+def test_env_map_gradient_is_linear_and_skips_zero_upstream(env):
+    """Size-independent properties: the reverse pass is linear in the upstream gradient, and lookups with a zero upstream
+    leave the map gradient untouched."""
+    from nmf_b200 import ops
+    fix = load_fixture("microfacet_g40")
+    dsc = device_scene(fix, env)
+    st = fix["state"]
+    bg, br, mul = st["bg_module.bg_mat"].cuda(), float(st["bg_module.brightness"]), float(st["bg_module.mul"])
+    d, sa, up = _lookups(20000, 9)
+    acc = ops.EnvMapGrad(dsc)
+    acc.scatter(d.cuda(), sa.cuda(), up.cuda())
+    g1, _, _ = acc.finish(bg, br, mul)
+    acc.scatter(d.cuda(), sa.cuda(), (2.0 * up).cuda())
+    acc.scatter(d.cuda(), sa.cuda(), torch.zeros_like(up).cuda())
+    g2, _, _ = acc.finish(bg, br, mul)
+    scale = float(g1.abs().max())
+    assert scale > 0
+    assert float((g2 - 2.0 * g1).abs().max()) < 2e-3 * scale
+
+
+def test_plugin_accumulates_into_parameter_grads(env):
+    """The hydra slot (plugins.IntegralEquirect): accumulate_grad per batch + finish_grad per optimiser step leave in
+    bg_mat.grad / brightness.grad / mul.grad what autograd leaves in the reference's module."""
+    from nmf_b200 import plugins
+    from oracle import nmf_oracle as O
+    fix = load_fixture("microfacet_g40")
+    osc = oracle_scene(fix, requires_grad=True)
+    sd = {k[len("bg_module."):]: v for k, v in fix["state"].items() if k.startswith("bg_module.")}
+    bg = plugins.IntegralEquirect(bg_resolution=sd["bg_mat"].shape[2], init_val=0.0, activation="exp")
+    bg.load_state_dict(sd)
+    bg = bg.to(env)
+    d, sa, up = _lookups(10000, 5)
+    (O.env_lookup(osc, d, sa) * up).sum().backward()
+    for rep in range(2):                                           # a second step accumulates like autograd does
+        bg.accumulate_grad(d.cuda(), sa.cuda(), up.cuda())
+        bg.finish_grad()
+        want = (rep + 1) * osc.params["bg_module.bg_mat"].grad.float()
+        scale = float(want.abs().max())
+        err = (bg.bg_mat.grad.cpu() - want).abs()
+        assert float(err.max()) < 5e-3 * scale and float(err.mean()) < 5e-5 * scale
+        for p, key in ((bg.brightness, "bg_module.brightness"), (bg.mul, "bg_module.mul")):
+            ref = (rep + 1) * float(osc.params[key].grad)
+            assert p.grad.dtype == p.dtype and abs(float(p.grad) - ref) < 2e-3 * max(1.0, abs(ref)), key
+    assert bg.mipbias.grad is None

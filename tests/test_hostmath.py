@@ -430,12 +430,15 @@ def test_material_heads_backward_matches_autograd(hostcheck, scenes):
         assert torch.allclose(db[rows[h]], gb, rtol=1e-4, atol=1e-5 * max(1.0, float(gb.abs().max()))), h
 
 
-def test_env_map_gradient_matches_autograd(hostcheck):
+@pytest.mark.parametrize("full_size", [False, True])
+def test_env_map_gradient_matches_autograd(hostcheck, full_size):
     """d loss / d bg_mat of IntegralEquirect lookups (modules/integral_equirect.py:263-273, 409-504): per-lookup scatter with
     the forward's own box walk (nmf_env_lookup1_bwd_map), then the adjoint of the double cumsum and the exp activation as
     whole-map passes -- against torch autograd through the oracle's env_lookup (boxes of every mip level, wrap-around at
     the seam, pole overhangs, pole rows)."""
     fix = load_fixture("microfacet_g40")
+    if full_size:                                                  # the 512 x 1024 map of configs/model/microfacet_tensorf2.yaml
+        fix["state"]["bg_module.bg_mat"] = torch.randn(1, 3, 512, 1024, generator=torch.Generator().manual_seed(11)) * 0.7 - 0.5
     osc = oracle_scene(fix, requires_grad=True)
     g = torch.Generator().manual_seed(4)
     n = 20000
