@@ -372,6 +372,23 @@ int nmf_env_lookup_bwd_scatter(const NmfScene* scene, const float* dirs, const f
 int nmf_env_lookup_bwd_finish(float* gsat, int h, int w, const float* bg_mat, float brightness, float mul,
                               float* d_bg_mat, float* d_brightness, float* d_mul, void* stream);
 
+/* Reverse pass of TensorBase.compute_normals (fields/tensor_base.py:107-129 -> modules/grid_sample_Cinf.py:109-281 under
+ * autograd) w.r.t. the density planes / lines -- the normal stage of the microfacet backward (detach_N off) and of ori_loss.
+ * Gradient images are laid out like the scene's derivative-packed factors and zeroed by the caller before the first batch
+ * of an optimiser step: gpack[p] = [h][w][48] (d value | d dx | d dy), glpack[p] = [n][4][8] (val4 | dy4). */
+typedef struct NmfNormalGrads {
+  float* gpack[3];
+  float* glpack[3];
+} NmfNormalGrads;
+/* Step 1, per batch: xyz (n, stride), d_normals (n,3) = d loss / d compute_normals(xyz); batches accumulate. */
+int nmf_vm_normals_bwd_scatter(const NmfScene* scene, const float* xyz, int n, int stride, const float* d_normals,
+                               const NmfNormalGrads* imgs, void* stream);
+/* Step 2, once per optimiser step: adjoint of the 5x5 smoothed-difference stencils kx25 / ky25 (device, row-major 5x5;
+ * grid_sample_Cinf.py:218-242) -> d_plane[p] [h][w][16] += ..., d_line[p] [n][16] += ... (channel-last, the layout of
+ * NmfPlainGrads.d_plane / d_line). */
+int nmf_vm_normals_bwd_finish(const NmfScene* scene, const NmfNormalGrads* imgs, const float* kx25, const float* ky25,
+                              float* const* d_plane, float* const* d_line, void* stream);
+
 /* Resolution schedule (fields/tensor_base.py:234-243 -> fields/tensoRF.py:208-227, 408-413): TensoRF.upsample is
  * F.interpolate(mode="bilinear", align_corners=True) of every factor.  src (C,H,W) -> dst (C,H2,W2), both in the
  * reference's own parameter layout (a line (1,C,N,1) is H = N, W = 1). */

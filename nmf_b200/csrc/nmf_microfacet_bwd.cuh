@@ -501,6 +501,21 @@ NMF_HD float nmf_line_grad_finish(const float* glpack, int n, const float* ky25,
   return acc;
 }
 
+// Reverse pass of TensorBase.compute_normals (fields/tensor_base.py:107-129) for ONE sample: recomputes the smoothed-difference
+// gradient of the density feature at p (the forward's own taps), sends d n through the normalisation and scatters into the
+// gradient images.  Shared by k_normals_bwd_scatter (csrc/nmf_normals_bwd.cu) and tests/hostcheck.
+NMF_HD void nmf_normals_bwd_sample(const NmfScene& s, const float* p, const float* dn, float* const* gpack, float* const* glpack) {
+  if (dn[0] == 0.f && dn[1] == 0.f && dn[2] == 0.f) return;
+  float xn[3];
+  nmf_normalize_xyz(s, p, xn);
+  const NmfTaps t = nmf_vm_taps(s, xn);
+  float grad[3] = {0.f, 0.f, 0.f}, dgrad[3];
+  for (int l = 0; l < 8; ++l) nmf_normal_lane(s, t, l, grad);
+  nmf_normal_vec_bwd(s, grad, dn, dgrad);
+  if (dgrad[0] == 0.f && dgrad[1] == 0.f && dgrad[2] == 0.f) return;
+  nmf_normal_bwd(s, t, dgrad, gpack, glpack);
+}
+
 // Finishing pass of the environment-map gradient: reverse prefix sums of the scattered SAT gradient over x and y (the adjoint
 // of integral_equirect.py:271-273's double cumsum), the pole-row means, then the exp activation with its clip at 20
 // (integral_equirect.py:263-270).  Sequential reference of what is two scan passes + one elementwise pass on the device.

@@ -73,6 +73,52 @@ class EnvMapGrad:
         return d_bg.reshape(1, 3, self.h, self.w), d_sc[0], d_sc[1]
 
 
+class NormalsGrad:
+    """Reverse pass of TensorBase.compute_normals w.r.t. the density factors (fields/tensor_base.py:107-129 ->
+    modules/grid_sample_Cinf.py:109-281 under autograd): `scatter` once per batch of samples (accumulates), `finish` once per
+    optimiser step.  nmf_vm_normals_bwd_scatter / nmf_vm_normals_bwd_finish (csrc/nmf_normals_bwd.cu)."""
+
+    def __init__(self, scene):
+        from .scene import derivative_stencils
+        self.scene = scene
+        if "dpack0" not in scene.keep:
+            raise _lib.NmfError("NormalsGrad: the scene holds no derivative planes (model without normals)")
+        self.gpack = [torch.zeros_like(scene.keep[f"dpack{p}"]) for p in range(3)]
+        self.glpack = [torch.zeros_like(scene.keep[f"lpack{p}"]) for p in range(3)]
+        self.c = _lib.NmfNormalGrads()
+        for p in range(3):
+            self.c.gpack[p] = self.gpack[p].data_ptr()
+            self.c.glpack[p] = self.glpack[p].data_ptr()
+        kx, ky = derivative_stencils()
+        self.kx = kx.reshape(25).to(device=scene.device, dtype=torch.float32).contiguous()
+        self.ky = ky.reshape(25).to(device=scene.device, dtype=torch.float32).contiguous()
+
+    def zero(self):
+        for t in self.gpack + self.glpack:
+            t.zero_()
+
+    def scatter(self, xyz, d_normals):
+        x = _f32(xyz, self.scene.device)
+        g = _f32(d_normals.reshape(-1, 3), self.scene.device)
+        if x.dim() != 2 or x.shape[1] < 3 or x.shape[0] != g.shape[0]:
+            raise _lib.NmfError("NormalsGrad.scatter: xyz (n, >=3) and d_normals (n, 3) expected")
+        _lib.check(_lib.lib().nmf_vm_normals_bwd_scatter(self.scene.ref(), _p(x), x.shape[0], x.shape[1], _p(g), C.byref(self.c),
+                                                         _stream()), "nmf_vm_normals_bwd_scatter")
+
+    def finish(self):
+        """-> ([d app_plane.p (1,16,H,W)], [d app_line.p (1,16,N,1)]) of rf.density_rf, in the reference's parameter layout;
+        consumes (and re-zeroes) the accumulated images."""
+        d_plane = [torch.zeros(g.shape[0], g.shape[1], 16, device=g.device) for g in self.gpack]
+        d_line = [torch.zeros(g.shape[0], 16, device=g.device) for g in self.glpack]
+        pp = (C.c_void_p * 3)(*[t.data_ptr() for t in d_plane])
+        lp = (C.c_void_p * 3)(*[t.data_ptr() for t in d_line])
+        _lib.check(_lib.lib().nmf_vm_normals_bwd_finish(self.scene.ref(), C.byref(self.c), _p(self.kx), _p(self.ky), pp, lp, _stream()),
+                   "nmf_vm_normals_bwd_finish")
+        self.zero()
+        return ([t.permute(2, 0, 1)[None].contiguous() for t in d_plane],
+                [t.t()[None, :, :, None].contiguous() for t in d_line])
+
+
 def vm_density(scene, xyz, activate=True):
     x = _f32(xyz, scene.device)
     out = torch.empty(x.shape[0], device=x.device)

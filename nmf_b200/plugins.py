@@ -183,6 +183,30 @@ class TensorVMSplit(nn.Module):
     def compute_normals(self, xyz_sampled):
         return ops.vm_normals(self.scene(), xyz_sampled)
 
+    @torch.no_grad()
+    def accumulate_normals_grad(self, xyz_sampled, grad_normals):
+        """Reverse pass of `compute_normals` for one batch (what autograd does through tensor_base.py:107-129 and
+        grid_sample_Cinf.py:109-281): grad_normals (n,3) = d loss / d compute_normals(xyz_sampled).  Batches accumulate on
+        the device until `finish_normals_grad`."""
+        sc = self.scene()
+        acc = getattr(self, "_normals_acc", None)
+        if acc is None or acc.scene is not sc:
+            acc = self._normals_acc = ops.NormalsGrad(sc)
+        acc.scatter(xyz_sampled, grad_normals)
+
+    @torch.no_grad()
+    def finish_normals_grad(self):
+        """Once per optimiser step: adjoint of the smoothed-difference stencil, added to density_rf.app_plane[p].grad /
+        app_line[p].grad (created when absent, like autograd's accumulation)."""
+        acc = getattr(self, "_normals_acc", None)
+        if acc is None:
+            return
+        d_plane, d_line = acc.finish()
+        for params, grads in ((self.density_rf.app_plane, d_plane), (self.density_rf.app_line, d_line)):
+            for prm, g in zip(params, grads):
+                g = g.to(prm.dtype)
+                prm.grad = g if prm.grad is None else prm.grad + g
+
     def feature2density(self, density_features):
         return torch.nn.functional.softplus(density_features.clamp(-15, 1e3) + self.density_shift)
 

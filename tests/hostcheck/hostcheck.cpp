@@ -557,6 +557,10 @@ double hc_ori_loss_bwd(const NmfScene* s, const float* xyz, const float* V, cons
   return total;
 }
 
+void hc_normals_bwd(const NmfScene* s, const float* xyz, int stride, const float* dn, int n, float* const* gpack, float* const* glpack) {
+  for (int i = 0; i < n; ++i) nmf_normals_bwd_sample(*s, xyz + (size_t)stride * i, dn + 3 * (size_t)i, gpack, glpack);
+}
+
 void hc_normal_grad_finish(const float* gpack, int h, int w, const float* glpack, int n, const float* kx25, const float* ky25,
                            float* d_plane, float* d_line) {
   for (int y = 0; y < h; ++y)

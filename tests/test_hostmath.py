@@ -762,6 +762,43 @@ def test_ori_loss_normal_path_matches_autograd(hostcheck, name):
         assert torch.allclose(fin_l.t()[None, :, :, None], got_l, rtol=1e-4, atol=1e-6 * float(got_l.abs().max()) + 1e-12)
 
 
+@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_noncubic"])
+def test_normals_reverse_pass_matches_autograd(hostcheck, name):
+    """nmf_normals_bwd_sample + the stencil adjoint -- the per-sample body of k_normals_bwd_scatter and the per-texel body of
+    k_normals_bwd_planes / _lines (csrc/nmf_normals_bwd.cu) -- against autograd through the oracle's vm_normals
+    (fields/tensor_base.py:107-129) for an arbitrary upstream d loss / d normal."""
+    from nmf_b200.scene import derivative_stencils
+    fix = load_fixture(name)
+    osc = oracle_scene(fix, requires_grad=True)
+    dsc = device_scene(fix, "cpu", sh_conv=O.sh_irradiance_coeffs(oracle_scene(fix)))
+    g = torch.Generator().manual_seed(21)
+    n = 6000
+    lo, hi = osc.aabb[0], osc.aabb[1]
+    xyz = torch.cat([lo + (hi - lo) * (0.05 + 0.9 * torch.rand(n, 3, generator=g)), torch.zeros(n, 1)], dim=1).contiguous()
+    up = torch.randn(n, 3, generator=g)
+    up[::7] = 0                                                    # samples without upstream are skipped
+    (O.vm_normals(osc, xyz) * up).sum().backward()
+    gpack = [torch.zeros_like(dsc.keep[f"dpack{p}"]) for p in range(3)]
+    glpack = [torch.zeros_like(dsc.keep[f"lpack{p}"]) for p in range(3)]
+    parr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
+    hostcheck.hc_normals_bwd(dsc.ref(), ptr(xyz), 4, ptr(up), n, parr(gpack), parr(glpack))
+    kx, ky = derivative_stencils()
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
+    seen = 0
+    for p in range(3):
+        H_, W_, N_ = gpack[p].shape[0], gpack[p].shape[1], glpack[p].shape[0]
+        fin_p, fin_l = torch.zeros(H_, W_, 16), torch.zeros(N_, 16)
+        hostcheck.hc_normal_grad_finish(ptr(gpack[p]), H_, W_, ptr(glpack[p]), N_, ptr(kx.reshape(-1).contiguous()),
+                                        ptr(ky.reshape(-1).contiguous()), ptr(fin_p), ptr(fin_l))
+        want_p, want_l = osc.params[f"rf.density_rf.app_plane.{p}"].grad, osc.params[f"rf.density_rf.app_line.{p}"].grad
+        if float(want_p.abs().max()) > 0:
+            seen += 1
+            assert rel(fin_p.permute(2, 0, 1)[None], want_p) < 1e-4 and rel(fin_l.t()[None, :, :, None], want_l) < 1e-4, p
+        else:
+            assert float(fin_p.abs().max()) == 0 and float(fin_l.abs().max()) == 0
+    assert seen > 0
+
+
 def test_ggx_view_derivative_matches_autograd(hostcheck):
     """d L / d V and d H / d V: the tangent the shading of a RE-TRACED ray sees (its view vector is minus the parent's bounce
     direction; sample positions are detached in the field, so this is the only way the secondary radiance moves with the
