@@ -372,6 +372,11 @@ int nmf_env_lookup_bwd_scatter(const NmfScene* scene, const float* dirs, const f
 int nmf_env_lookup_bwd_finish(float* gsat, int h, int w, const float* bg_mat, float brightness, float mul,
                               float* d_bg_mat, float* d_brightness, float* d_mul, void* stream);
 
+/* d loss / d IntegralEquirect.mipbias of a batch of lookups (the box size moves with the bias: sa2mip,
+ * integral_equirect.py:373-397): d_mipbias[0] (device float) += sum_i g_i . d rgb_i / d mipbias. */
+int nmf_env_lookup_bwd_mipbias(const NmfScene* scene, const float* dirs, const float* mip, const float* g, int n,
+                               float* d_mipbias, void* stream);
+
 /* Reverse pass of TensorBase.compute_normals (fields/tensor_base.py:107-129 -> modules/grid_sample_Cinf.py:109-281 under
  * autograd) w.r.t. the density planes / lines -- the normal stage of the microfacet backward (detach_N off) and of ori_loss.
  * Gradient images are laid out like the scene's derivative-packed factors and zeroed by the caller before the first batch
@@ -388,6 +393,13 @@ int nmf_vm_normals_bwd_scatter(const NmfScene* scene, const float* xyz, int n, i
  * NmfPlainGrads.d_plane / d_line). */
 int nmf_vm_normals_bwd_finish(const NmfScene* scene, const NmfNormalGrads* imgs, const float* kx25, const float* ky25,
                               float* const* d_plane, float* const* d_line, void* stream);
+
+/* Reverse pass of RandHydraMLPDiffuse.forward (modules/render_modules.py:519-574 under autograd): feat (n,24) and the
+ * upstream gradients g_albedo (n,3) (= d loss / d diffuse), g_f0 (n,3), g_rough (n) (= d loss / d r1)
+ * -> d_head_w [11][24] += ..., d_head_b [11] += ... (rows as NmfScene.head_w: diffuse 3, tint 3 (always zero: the tint
+ * head feeds nothing on this path), f0 3, roughness 2), d_feat (n,24) written. */
+int nmf_material_heads_bwd(const NmfScene* scene, const float* feat, const float* g_albedo, const float* g_f0,
+                           const float* g_rough, int n, float* d_head_w, float* d_head_b, float* d_feat, void* stream);
 
 /* Resolution schedule (fields/tensor_base.py:234-243 -> fields/tensoRF.py:208-227, 408-413): TensoRF.upsample is
  * F.interpolate(mode="bilinear", align_corners=True) of every factor.  src (C,H,W) -> dst (C,H2,W2), both in the

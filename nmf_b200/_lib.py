@@ -162,8 +162,10 @@ def lib():
         "nmf_adam_step": (I, [P, P, P, P, C.c_size_t, C.POINTER(NmfAdam), P, P]),
         "nmf_env_lookup_bwd_scatter": (I, [SP, P, P, P, I, P, P]),
         "nmf_env_lookup_bwd_finish": (I, [P, I, I, P, F, F, P, P, P, P]),
+        "nmf_env_lookup_bwd_mipbias": (I, [SP, P, P, P, I, P, P]),
         "nmf_vm_normals_bwd_scatter": (I, [SP, P, I, I, P, C.POINTER(NmfNormalGrads), P]),
         "nmf_vm_normals_bwd_finish": (I, [SP, C.POINTER(NmfNormalGrads), P, P, P, P, P]),
+        "nmf_material_heads_bwd": (I, [SP, P, P, P, P, I, P, P, P, P]),
         "nmf_render_train_workspace_bytes": (C.c_size_t, [SP, I, F]),
         "nmf_render_rays_train": (I, [SP, RP, C.POINTER(NmfRenderTrain), P, IP, CP, P, C.c_size_t, P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
@@ -183,5 +185,5 @@ EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_pr
             "nmf_brdf_mlp", "nmf_material_heads", "nmf_dense_alpha", "nmf_generate_rays", "nmf_image_sq_error",
             "nmf_sample_rays_train", "nmf_train_workspace_bytes", "nmf_train_plain", "nmf_upsample_bilinear",
             "nmf_render_train_workspace_bytes", "nmf_render_rays_train", "nmf_l1_reg", "nmf_grad_sq_norm", "nmf_adam_step",
-            "nmf_env_lookup_bwd_scatter", "nmf_env_lookup_bwd_finish", "nmf_vm_normals_bwd_scatter",
-            "nmf_vm_normals_bwd_finish"]
+            "nmf_env_lookup_bwd_scatter", "nmf_env_lookup_bwd_finish", "nmf_env_lookup_bwd_mipbias", "nmf_vm_normals_bwd_scatter",
+            "nmf_vm_normals_bwd_finish", "nmf_material_heads_bwd"]

@@ -98,6 +98,34 @@ __global__ void k_env_bwd_finish(const float* __restrict__ gsat, int h, int w, c
   }
 }
 
+// d loss / d mipbias: per lookup the forward-mode pass nmf_env_lookup1_dmipbias (unit tangent on the bias: the box size moves,
+// the taps' bilinear weights and 1 / size with it), dotted with the upstream; warp sum, one atomic per warp.
+__global__ void k_env_bwd_mipbias(const NmfScene s, const float* __restrict__ dirs, const float* __restrict__ mip,
+                                  const float* __restrict__ g, int n, float* d_mipbias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  if (i < n) {
+    const float gi[3] = {g[3 * i], g[3 * i + 1], g[3 * i + 2]};
+    if (gi[0] != 0.f || gi[1] != 0.f || gi[2] != 0.f) {
+      float rgb[3], d[3];
+      nmf_env_lookup1_dmipbias(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot,
+                               nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), mip[i], rgb, d);
+      acc = gi[0] * d[0] + gi[1] * d[1] + gi[2] * d[2];
+    }
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(d_mipbias, acc);
+}
+
+extern "C" int nmf_env_lookup_bwd_mipbias(const NmfScene* scene, const float* dirs, const float* mip, const float* g, int n,
+                                          float* d_mipbias, void* stream) {
+  if (!scene || !scene->env_sat || !dirs || !mip || !g || !d_mipbias || n < 0) return NMF_E_ARG;
+  if (n == 0) return NMF_OK;
+  k_env_bwd_mipbias<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*scene, dirs, mip, g, n, d_mipbias);
+  CKL();
+  return NMF_OK;
+}
+
 extern "C" int nmf_env_lookup_bwd_scatter(const NmfScene* scene, const float* dirs, const float* mip, const float* g, int n,
                                           float* gsat, void* stream) {
   if (!scene || !dirs || !mip || !g || !gsat || n < 0 || scene->env_h <= 0 || scene->env_w <= 0) return NMF_E_ARG;

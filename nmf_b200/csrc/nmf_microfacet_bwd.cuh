@@ -1,8 +1,8 @@
 // Per-element backward math of the MICROFACET model (remainder): every piece of the
 // reverse pass stated per bounce ray / per sample / per texel, compiled for the host (tests/hostcheck) and checked against
 // the oracle's autograd (= the reference's gradient, oracle/check_train.py) in the CPU suite -- piece by piece and composed
-// into the whole two-level training reverse pass (hc_train_microfacet, hc_train_microfacet_retrace).  No kernel includes
-// this header yet: the reverse-pass kernels that will call it are the next step, this file fixes their math.
+// into the whole two-level training reverse pass (hc_train_microfacet, hc_train_microfacet_retrace).  The first kernels that
+// include it: csrc/nmf_env_bwd.cu (map / mipbias gradient), csrc/nmf_normals_bwd.cu, csrc/nmf_shade_bwd.cu (material heads).
 //
 //   nmf_ggx_sample_dr     d L / d roughness and d H / d roughness of the GGX VNDF sample (brdf_samplers/ggx.py:61-226):
 //                         forward-mode (dual-number) restatement of nmf_ggx_frame + nmf_ggx_sample_f.  The reference
@@ -134,10 +134,9 @@ NMF_HD float nmf_fresnel_mix_bwd(const float* R0, float cost, const float* inc, 
 // f0_c = sigmoid(lin_{6+c} + bias_f), r = clip(sigmoid(lin_9 + bias_r) / 2, 1e-2, 1) with lin = W feat + b
 // (W rows: diffuse 0..2, tint 3..5, f0 6..8, roughness 9..10).  Upstream: g_albedo[3], g_f0[3], g_rough.
 // Accumulates dW (11 x 24), db (11) and writes dfeat (24).  The tint head and r2 feed nothing on this path.
-NMF_HD void nmf_heads_bwd(const float* feat, const float* W, const float* b, float diffuse_mul, float diffuse_bias, float f0_bias,
-                          float roughness_bias, const float* g_albedo, const float* g_f0, float g_rough, float* dW, float* db,
-                          float* dfeat) {
-  float dlin[11];
+// d loss / d lin (the 11 pre-activations) of one sample; shared by nmf_heads_bwd and k_heads_bwd (csrc/nmf_shade_bwd.cu)
+NMF_HD void nmf_heads_dlin(const float* feat, const float* W, const float* b, float diffuse_mul, float diffuse_bias, float f0_bias,
+                           float roughness_bias, const float* g_albedo, const float* g_f0, float g_rough, float* dlin) {
   for (int h = 0; h < 11; ++h) dlin[h] = 0.f;
   float lin[11];
   for (int h = 0; h < 11; ++h) {
@@ -153,6 +152,12 @@ NMF_HD void nmf_heads_bwd(const float* feat, const float* W, const float* b, flo
   }
   const float sr = nmf_sigmoid(lin[9] + roughness_bias);
   dlin[9] = (sr / 2.0f >= 1e-2f && sr / 2.0f <= 1.0f) ? g_rough * 0.5f * sr * (1.0f - sr) : 0.f;
+}
+NMF_HD void nmf_heads_bwd(const float* feat, const float* W, const float* b, float diffuse_mul, float diffuse_bias, float f0_bias,
+                          float roughness_bias, const float* g_albedo, const float* g_f0, float g_rough, float* dW, float* db,
+                          float* dfeat) {
+  float dlin[11];
+  nmf_heads_dlin(feat, W, b, diffuse_mul, diffuse_bias, f0_bias, roughness_bias, g_albedo, g_f0, g_rough, dlin);
   for (int k = 0; k < 24; ++k) dfeat[k] = 0.f;
   for (int h = 0; h < 11; ++h) {
     if (dlin[h] == 0.f) continue;
@@ -235,7 +240,7 @@ NMF_HD NmfDual nmf_datan2_damped(NmfDual y, NmfDual x) {      // atan2(y, x); d 
   return nmf_dmk(atan2f(y.v, x.v), (x.v * y.d - y.v * x.d) / (x.v * x.v + y.v * y.v + 1e-5f));
 }
 struct NmfEnvBoxD { NmfDual cx, cy, sw, sh, size; };
-NMF_HD NmfEnvBoxD nmf_env_box_d(NmfDual3 u, float sa, int h, int w, float mipbias) {
+NMF_HD NmfEnvBoxD nmf_env_box_d(NmfDual3 u, float sa, int h, int w, NmfDual mipbias) {   // the tangent may sit on the bias too
   NmfEnvBoxD bx;
   const NmfDual cosv = nmf_dsqrt_floor(nmf_dk(1.0f) - u.z * u.z, NMF_EPS);
   const NmfDual d = nmf_dk((float)(h * w)) / nmf_dmax_floor((float)(2.0 * 3.14159265358979323846 * 3.14159265358979323846) * cosv, NMF_EPS);
@@ -244,8 +249,8 @@ NMF_HD NmfEnvBoxD nmf_env_box_d(NmfDual3 u, float sa, int h, int w, float mipbia
   const NmfDual hh = nmf_dmax_floor(nmf_dsqrt_floor(area, NMF_EPS) * cosv, NMF_EPS);
   const NmfDual ww = area / hh;
   const float ln2 = 0.6931471805599453f;
-  const NmfDual lw = nmf_dclamp(nmf_dlog(ww) * (1.0f / ln2) + nmf_dk(mipbias), 0.0f, 7.0f);
-  const NmfDual lh = nmf_dclamp(nmf_dlog(hh) * (1.0f / ln2) + nmf_dk(mipbias), 0.0f, 7.0f);
+  const NmfDual lw = nmf_dclamp(nmf_dlog(ww) * (1.0f / ln2) + mipbias, 0.0f, 7.0f);
+  const NmfDual lh = nmf_dclamp(nmf_dlog(hh) * (1.0f / ln2) + mipbias, 0.0f, 7.0f);
   bx.sw = nmf_dexp2(lw) * (1.0f / (float)h / 2.0f);
   bx.sh = nmf_dexp2(lh) * (1.0f / (float)h);
   bx.size = (bx.sw * (0.5f * (float)w)) * (bx.sh * (0.5f * (float)h));
@@ -285,8 +290,8 @@ NMF_HD void nmf_env_box1_d(const float* sat, int h, int w, NmfDual x0, NmfDual y
   for (int k = 0; k < 3; ++k) out[k] = out[k] + acc[k] * inv_size;
 }
 // rgb[k] = value, drgb[k] = derivative along the tangent carried by `dir`
-NMF_HD void nmf_env_lookup1_d(const float* sat, int h, int w, float mipbias, const float* top, const float* bot, NmfDual3 dir,
-                              float sa, float* rgb, float* drgb) {
+NMF_HD void nmf_env_lookup1_dm(const float* sat, int h, int w, NmfDual mipbias, const float* top, const float* bot, NmfDual3 dir,
+                               float sa, float* rgb, float* drgb) {
   const NmfEnvBoxD bx = nmf_env_box_d(dir, sa, h, w, mipbias);
   const float cutoff = 1.0f - 2.0f / (float)h * 3.0f;
   if (bx.cy.v > cutoff) { for (int k = 0; k < 3; ++k) { rgb[k] = bot[k]; drgb[k] = 0.f; } return; }
@@ -320,6 +325,16 @@ NMF_HD void nmf_env_lookup1_d(const float* sat, int h, int w, float mipbias, con
     }
   }
   for (int k = 0; k < 3; ++k) { rgb[k] = out[k].v * 1000.0f; drgb[k] = out[k].d * 1000.0f; }
+}
+NMF_HD void nmf_env_lookup1_d(const float* sat, int h, int w, float mipbias, const float* top, const float* bot, NmfDual3 dir,
+                              float sa, float* rgb, float* drgb) {
+  nmf_env_lookup1_dm(sat, h, w, nmf_dk(mipbias), top, bot, dir, sa, rgb, drgb);
+}
+// d rgb / d mipbias of one lookup (IntegralEquirect.mipbias is a parameter: the box size moves with it, sa2mip
+// integral_equirect.py:373-397): the same forward-mode pass with the unit tangent on the bias and none on the direction.
+NMF_HD void nmf_env_lookup1_dmipbias(const float* sat, int h, int w, float mipbias, const float* top, const float* bot, nmf_v3 dir,
+                                     float sa, float* rgb, float* drgb) {
+  nmf_env_lookup1_dm(sat, h, w, nmf_dmk(mipbias, 1.0f), top, bot, nmf_d3k(dir), sa, rgb, drgb);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -49,9 +49,11 @@ class EnvMapGrad:
         self.scene = scene
         self.h, self.w = int(scene.c.env_h), int(scene.c.env_w)
         self.gsat = torch.zeros(self.h * self.w * 4 + 8, device=scene.device)
+        self.d_mipbias = torch.zeros(1, device=scene.device)
 
     def zero(self):
         self.gsat.zero_()
+        self.d_mipbias.zero_()
 
     def scatter(self, dirs, mip, g):
         d = _f32(dirs.reshape(-1, 3), self.scene.device)
@@ -59,18 +61,24 @@ class EnvMapGrad:
         u = _f32(g.reshape(-1, 3), self.scene.device)
         if not (d.shape[0] == m.shape[0] == u.shape[0]):
             raise _lib.NmfError("EnvMapGrad.scatter: dirs / mip / g disagree on the number of lookups")
-        _lib.check(_lib.lib().nmf_env_lookup_bwd_scatter(self.scene.ref(), _p(d), _p(m), _p(u), d.shape[0], _p(self.gsat), _stream()),
-                   "nmf_env_lookup_bwd_scatter")
+        with torch.cuda.device(d.device):
+            _lib.check(_lib.lib().nmf_env_lookup_bwd_scatter(self.scene.ref(), _p(d), _p(m), _p(u), d.shape[0], _p(self.gsat),
+                                                             _stream()), "nmf_env_lookup_bwd_scatter")
+            _lib.check(_lib.lib().nmf_env_lookup_bwd_mipbias(self.scene.ref(), _p(d), _p(m), _p(u), d.shape[0], _p(self.d_mipbias),
+                                                             _stream()), "nmf_env_lookup_bwd_mipbias")
 
     def finish(self, bg_mat, brightness, mul):
-        """-> (d bg_mat (1,3,h,w), d brightness, d mul); consumes (and re-zeroes) the accumulated scatter image."""
+        """-> (d bg_mat (1,3,h,w), d brightness, d mul, d mipbias); consumes (and re-zeroes) the accumulated scatter image."""
         bg = _f32(bg_mat.reshape(3, self.h, self.w), self.scene.device)
         d_bg = torch.zeros_like(bg)
         d_sc = torch.zeros(2, device=bg.device)
-        _lib.check(_lib.lib().nmf_env_lookup_bwd_finish(_p(self.gsat), self.h, self.w, _p(bg), float(brightness), float(mul), _p(d_bg),
-                                                        _p(d_sc[0:1]), _p(d_sc[1:2]), _stream()), "nmf_env_lookup_bwd_finish")
+        with torch.cuda.device(bg.device):
+            _lib.check(_lib.lib().nmf_env_lookup_bwd_finish(_p(self.gsat), self.h, self.w, _p(bg), float(brightness), float(mul),
+                                                            _p(d_bg), _p(d_sc[0:1]), _p(d_sc[1:2]), _stream()),
+                       "nmf_env_lookup_bwd_finish")
+        d_mb = self.d_mipbias[0].clone()
         self.zero()
-        return d_bg.reshape(1, 3, self.h, self.w), d_sc[0], d_sc[1]
+        return d_bg.reshape(1, 3, self.h, self.w), d_sc[0], d_sc[1], d_mb
 
 
 class NormalsGrad:
@@ -102,8 +110,9 @@ class NormalsGrad:
         g = _f32(d_normals.reshape(-1, 3), self.scene.device)
         if x.dim() != 2 or x.shape[1] < 3 or x.shape[0] != g.shape[0]:
             raise _lib.NmfError("NormalsGrad.scatter: xyz (n, >=3) and d_normals (n, 3) expected")
-        _lib.check(_lib.lib().nmf_vm_normals_bwd_scatter(self.scene.ref(), _p(x), x.shape[0], x.shape[1], _p(g), C.byref(self.c),
-                                                         _stream()), "nmf_vm_normals_bwd_scatter")
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().nmf_vm_normals_bwd_scatter(self.scene.ref(), _p(x), x.shape[0], x.shape[1], _p(g), C.byref(self.c),
+                                                             _stream()), "nmf_vm_normals_bwd_scatter")
 
     def finish(self):
         """-> ([d app_plane.p (1,16,H,W)], [d app_line.p (1,16,N,1)]) of rf.density_rf, in the reference's parameter layout;
@@ -112,8 +121,9 @@ class NormalsGrad:
         d_line = [torch.zeros(g.shape[0], 16, device=g.device) for g in self.glpack]
         pp = (C.c_void_p * 3)(*[t.data_ptr() for t in d_plane])
         lp = (C.c_void_p * 3)(*[t.data_ptr() for t in d_line])
-        _lib.check(_lib.lib().nmf_vm_normals_bwd_finish(self.scene.ref(), C.byref(self.c), _p(self.kx), _p(self.ky), pp, lp, _stream()),
-                   "nmf_vm_normals_bwd_finish")
+        with torch.cuda.device(self.kx.device):
+            _lib.check(_lib.lib().nmf_vm_normals_bwd_finish(self.scene.ref(), C.byref(self.c), _p(self.kx), _p(self.ky), pp, lp,
+                                                            _stream()), "nmf_vm_normals_bwd_finish")
         self.zero()
         return ([t.permute(2, 0, 1)[None].contiguous() for t in d_plane],
                 [t.t()[None, :, :, None].contiguous() for t in d_line])
@@ -192,6 +202,26 @@ def material_heads(scene, feat, with_r2=False):
             _lib.check(_lib.lib().nmf_material_heads(scene.ref(), _p(f), n, _p(a), _p(t), _p(f0), _p(r1), _p(r2), _stream()),
                        "nmf_material_heads")
     return (a, t, f0, r1, r2) if with_r2 else (a, t, f0, r1)
+
+
+def material_heads_bwd(scene, feat, g_albedo, g_f0, g_rough, d_head_w=None, d_head_b=None):
+    """Reverse pass of RandHydraMLPDiffuse.forward (render_modules.py:519-574 under autograd): -> (d_head_w (11,24),
+    d_head_b (11), d_feat (n,24)); d_head_w / d_head_b accumulate into the given buffers (rows: diffuse 3, tint 3, f0 3,
+    roughness 2)."""
+    f = _f32(feat, scene.device)
+    n = f.shape[0]
+    ga, gf = _f32(g_albedo.reshape(-1, 3), scene.device), _f32(g_f0.reshape(-1, 3), scene.device)
+    gr = _f32(g_rough.reshape(-1), scene.device)
+    if f.dim() != 2 or f.shape[1] != 24 or not (ga.shape[0] == gf.shape[0] == gr.shape[0] == n):
+        raise _lib.NmfError("material_heads_bwd: feat (n,24), g_albedo (n,3), g_f0 (n,3), g_rough (n) expected")
+    dw = torch.zeros(11, 24, device=f.device) if d_head_w is None else d_head_w
+    db = torch.zeros(11, device=f.device) if d_head_b is None else d_head_b
+    d_feat = torch.empty_like(f)
+    if n:
+        with torch.cuda.device(f.device):
+            _lib.check(_lib.lib().nmf_material_heads_bwd(scene.ref(), _p(f), _p(ga), _p(gf), _p(gr), n, _p(dw), _p(db), _p(d_feat),
+                                                         _stream()), "nmf_material_heads_bwd")
+    return dw, db, d_feat
 
 
 def dense_alpha(scene, grid_size):

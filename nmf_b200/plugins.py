@@ -663,13 +663,12 @@ class IntegralEquirect(nn.Module):
     @torch.no_grad()
     def finish_grad(self):
         """Once per optimiser step: adds the accumulated gradient to bg_mat.grad / brightness.grad / mul.grad (created when
-        absent, like autograd's accumulation).  NOT produced here: d mipbias (the reference differentiates the box size
-        w.r.t. the bias, integral_equirect.py:373-397; that is the box-geometry derivative of DESIGN.md section 9, whose
-        forward-mode math is nmf_env_lookup1_d) -- mipbias.grad is left untouched."""
+        absent, like autograd's accumulation): bg_mat, brightness, mul and mipbias (the box size moves with the bias,
+        integral_equirect.py:373-397: nmf_env_lookup_bwd_mipbias)."""
         if self._grad_acc is None:
             return
-        d_bg, d_br, d_mul = self._grad_acc.finish(self.bg_mat, self.brightness, self.mul)
-        for p, g in ((self.bg_mat, d_bg), (self.brightness, d_br), (self.mul, d_mul)):
+        d_bg, d_br, d_mul, d_mb = self._grad_acc.finish(self.bg_mat, self.brightness, self.mul)
+        for p, g in ((self.bg_mat, d_bg), (self.brightness, d_br), (self.mul, d_mul), (self.mipbias, d_mb)):
             g = g.to(p.dtype).reshape(p.shape)
             p.grad = g if p.grad is None else p.grad + g
 

@@ -515,6 +515,17 @@ void hc_env_bwd_map(int h, int w, float mipbias, const float* dirs, const float*
     nmf_env_lookup1_bwd_map(gsat, h, w, mipbias, nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), sa[i], g + 3 * i, g_top, g_bot);
 }
 
+double hc_env_mipbias_grad(const NmfScene* s, const float* dirs, const float* mip, const float* g, int n) {
+  double acc = 0.0;
+  for (int i = 0; i < n; ++i) {
+    float rgb[3], d[3];
+    nmf_env_lookup1_dmipbias(s->env_sat, s->env_h, s->env_w, s->env_mipbias, s->env_top, s->env_bot,
+                             nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), mip[i], rgb, d);
+    acc += (double)(g[3 * i] * d[0] + g[3 * i + 1] * d[1] + g[3 * i + 2] * d[2]);
+  }
+  return acc;
+}
+
 void hc_env_lookup_d(const NmfScene* s, const float* dirs, const float* tangent, const float* mip, int n, float* rgb, float* drgb) {
   for (int i = 0; i < n; ++i) {
     const NmfDual3 d = nmf_d3(nmf_dmk(dirs[3 * i], tangent[3 * i]), nmf_dmk(dirs[3 * i + 1], tangent[3 * i + 1]),

@@ -475,6 +475,28 @@ def test_env_map_gradient_matches_autograd(hostcheck, full_size):
     assert float(err.max()) < 2e-3 * scale and float(err.mean()) < 2e-5 * scale, (float(err.max()) / scale, float(err.mean()) / scale)
 
 
+@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_g56_ship"])
+def test_env_mipbias_gradient_matches_autograd(hostcheck, name):
+    """d loss / d IntegralEquirect.mipbias (the box size moves with the bias, integral_equirect.py:373-397): the forward-mode
+    pass with the unit tangent on the bias (nmf_env_lookup1_dmipbias, the per-lookup body of k_env_bwd_mipbias) against
+    autograd through the oracle's env_lookup; tolerance 2e-3 relative (measured: <= 5e-4)."""
+    fix = load_fixture(name)
+    dsc = device_scene(fix, "cpu", sh_conv=O.sh_irradiance_coeffs(oracle_scene(fix)))
+    g = torch.Generator().manual_seed(4)
+    n = 20000
+    d = O.unit(torch.randn(n, 3, generator=g))
+    d[6:200, 2] = d[6:200, 2].sign() * 0.97
+    d = O.unit(d).contiguous()
+    sa = (torch.rand(n, generator=g) * 14 - 10).contiguous()
+    hostcheck.hc_env_mipbias_grad.restype = C.c_double
+    for up in (torch.randn(n, 3, generator=g).abs().contiguous(), torch.randn(n, 3, generator=g).contiguous()):
+        osc = oracle_scene(fix, requires_grad=True)                # the scene caches the SAT's graph: one backward per scene
+        (O.env_lookup(osc, d, sa) * up).sum().backward()
+        want = float(osc.params["bg_module.mipbias"].grad.detach())
+        got = hostcheck.hc_env_mipbias_grad(dsc.ref(), ptr(d), ptr(sa), ptr(up), n)
+        assert abs(got - want) < 2e-3 * abs(want), (got, want)
+
+
 def test_env_direction_derivative_matches_autograd(hostcheck, scenes):
     """Directional derivative of an environment lookup along a tangent of the direction (how the bounce radiance moves with
     the roughness through L): forward-mode restatement (nmf_env_lookup1_d) against J^T products of torch autograd through
