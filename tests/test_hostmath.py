@@ -784,7 +784,7 @@ def test_ori_loss_normal_path_matches_autograd(hostcheck, name):
         assert torch.allclose(fin_l.t()[None, :, :, None], got_l, rtol=1e-4, atol=1e-6 * float(got_l.abs().max()) + 1e-12)
 
 
-@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_noncubic"])
+@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_g56_ship", "microfacet_noncubic"])
 def test_normals_reverse_pass_matches_autograd(hostcheck, name):
     """nmf_normals_bwd_sample + the stencil adjoint -- the per-sample body of k_normals_bwd_scatter and the per-texel body of
     k_normals_bwd_planes / _lines (csrc/nmf_normals_bwd.cu) -- against autograd through the oracle's vm_normals
@@ -799,6 +799,10 @@ def test_normals_reverse_pass_matches_autograd(hostcheck, name):
     xyz = torch.cat([lo + (hi - lo) * (0.05 + 0.9 * torch.rand(n, 3, generator=g)), torch.zeros(n, 1)], dim=1).contiguous()
     up = torch.randn(n, 3, generator=g)
     up[::7] = 0                                                    # samples without upstream are skipped
+    with torch.no_grad():                                          # upstream only where there is density (see the GPU test)
+        sig = O.feature2density(osc, O.density_feature(osc, xyz))
+    up[sig <= 1e-2] = 0
+    assert int((up.abs().sum(1) > 0).sum()) > 500
     (O.vm_normals(osc, xyz) * up).sum().backward()
     gpack = [torch.zeros_like(dsc.keep[f"dpack{p}"]) for p in range(3)]
     glpack = [torch.zeros_like(dsc.keep[f"lpack{p}"]) for p in range(3)]
