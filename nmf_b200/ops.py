@@ -70,10 +70,11 @@ class EnvMapGrad:
     def finish(self, bg_mat, brightness, mul):
         """-> (d bg_mat (1,3,h,w), d brightness, d mul, d mipbias); consumes (and re-zeroes) the accumulated scatter image."""
         bg = _f32(bg_mat.reshape(3, self.h, self.w), self.scene.device)
+        brightness, mul = (float(v.detach()) if torch.is_tensor(v) else float(v) for v in (brightness, mul))
         d_bg = torch.zeros_like(bg)
         d_sc = torch.zeros(2, device=bg.device)
         with torch.cuda.device(bg.device):
-            _lib.check(_lib.lib().nmf_env_lookup_bwd_finish(_p(self.gsat), self.h, self.w, _p(bg), float(brightness), float(mul),
+            _lib.check(_lib.lib().nmf_env_lookup_bwd_finish(_p(self.gsat), self.h, self.w, _p(bg), brightness, mul,
                                                             _p(d_bg), _p(d_sc[0:1]), _p(d_sc[1:2]), _stream()),
                        "nmf_env_lookup_bwd_finish")
         d_mb = self.d_mipbias[0].clone()
