@@ -1,5 +1,5 @@
 #!/bin/bash
-# First GPU call of the next round: gate the reverse-pass kernels written after round 1's GPU minutes were spent (they sort last
+# First GPU call of the next round: gate the reverse-pass kernels written in round 1's last GPU seconds (they sort last
 # in the suite), time them, and capture them once with ncu.  Everything else in the suite is the established parity set.
 set -x
 mkdir -p gpurun_out
