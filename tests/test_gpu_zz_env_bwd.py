@@ -213,3 +213,16 @@ def test_material_heads_gradient_on_device(env, n):
         assert torch.allclose(db[rows[h]].cpu(), gb, rtol=1e-4, atol=1e-5 * max(1.0, float(gb.abs().max()))), h
     assert torch.allclose(dW2, 2 * dW, rtol=1e-4, atol=1e-5 * max(1.0, float(dW.abs().max())))       # buffers accumulate
     assert torch.allclose(db2, 2 * db, rtol=1e-4, atol=1e-5 * max(1.0, float(db.abs().max())))
+
+
+def test_standalone_device_check(env):
+    """tests/hostcheck/devcheck (built by __graft_entry__.build): the reverse-pass kernels against their host restatements on
+    random inputs, straight through the C ABI without Python -- the check that first ran them on a B200
+    (profiles/r01_h_devcheck_reverse_kernels.log)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck", "devcheck")
+    if not os.path.exists(exe):
+        pytest.skip("tests/hostcheck/devcheck not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "devcheck PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-500:]
