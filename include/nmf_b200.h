@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NMF_ABI_VERSION 7
+#define NMF_ABI_VERSION 8
 
 #define NMF_OK 0
 #define NMF_E_ARG (-1)          /* null pointer / non-positive size                                   */
@@ -49,6 +49,7 @@ extern "C" {
 #define NMF_DEV_E_SURVIVORS 1u  /* surviving-sample list overflowed                                    */
 #define NMF_DEV_E_BSAMPLES 2u   /* bounce-sample list overflowed                                       */
 #define NMF_DEV_E_BRAYS 4u      /* a chunk's bounce-ray region overflowed                              */
+#define NMF_DEV_E_VSAMPLES 8u   /* train mode: the valid-sample list kept for the reverse pass overflowed */
 
 /* ------------------------------------------------------------------------------------------------
  * Scene: every weight the path reads, in the layouts the kernels gather from (DESIGN.md "HBM layout").
@@ -400,6 +401,50 @@ int nmf_vm_normals_bwd_finish(const NmfScene* scene, const NmfNormalGrads* imgs,
  * head feeds nothing on this path), f0 3, roughness 2), d_feat (n,24) written. */
 int nmf_material_heads_bwd(const NmfScene* scene, const float* feat, const float* g_albedo, const float* g_f0,
                            const float* g_rough, int n, float* d_head_w, float* d_head_b, float* d_feat, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Training step of the MICROFACET model (configs #3 / #4): forward + loss + reverse pass.
+ * Replaces, for model=microfacet_tensorf2, what train.py:540-712 does with autograd: TensorNeRF.forward(is_train=True)
+ * (modules/tensor_nerf.py:210-674 -> models/microfacet.py:271-673 -> brdf_samplers/ggx.py:61-226, modules/brdf.py:177-261,
+ * modules/render_modules.py:519-574, modules/integral_equirect.py:409-504, fields/tensor_base.py:107-129 with
+ * create_graph=True, one re-traced level), the loss  sum (clip(rgb) - clip(gt))^2 + lambda_pred * prediction_loss +
+ * lambda_ori * ori_loss  (train.py:586-657 with the lambdas of configs/model/microfacet_tensorf2.yaml:205-218; the other
+ * regularisers have weight 0 there), and total_loss.backward().
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct NmfMicrofacetGrads {   /* device, fp32; every field ACCUMULATES: the caller zeroes once per optimiser step */
+  float* d_plane[3];       /* [h][w][16]  rf.density_rf.app_plane.p   (channel-last, like NmfPlainGrads)              */
+  float* d_line[3];        /* [n][16]     rf.density_rf.app_line.p                                                     */
+  float* a_plane[3];       /* [h][w][24]  rf.app_rf.app_plane.p                                                        */
+  float* a_line[3];        /* [n][24]     rf.app_rf.app_line.p                                                         */
+  float* basis_t;          /* [72][24]    rf.basis_mat.weight^T                                                        */
+  float* head_w;           /* [11][24]    model.diffuse_module.{diffuse,tint,f0,roughness}_mlp.0.weight (rows 3|3|3|2)  */
+  float* head_b;           /* [11]                                                                                     */
+  float* w0t; float* b0;   /* [66][64], [64]  model.brdf.mlp.0 (transposed weight)                                     */
+  float* w1t; float* b1;   /* [64][64], [64]  model.brdf.mlp.2                                                         */
+  float* w2t; float* b2;   /* [64][4],  [4]   model.brdf.mlp.4                                                         */
+  float* gsat;             /* [env_h][env_w][4] + 8: scatter image of the environment lookups; nmf_env_lookup_bwd_finish
+                            * turns it into d bg_mat / d brightness / d mul once per optimiser step                    */
+  float* d_mipbias;        /* [1]  bg_module.mipbias                                                                   */
+  NmfNormalGrads normals;  /* derivative-plane gradient images of the normal path; nmf_vm_normals_bwd_finish adds their
+                            * stencil adjoint to d_plane / d_line once per optimiser step                              */
+} NmfMicrofacetGrads;
+
+typedef struct NmfMicrofacetTrain {
+  float lambda_pred;       /* params.pred_lambda (3e-4): weight of prediction_loss = 2 sum(acc) (no normal module)     */
+  float lambda_ori;        /* params.ori_lambda (0.1): weight of ori_loss = sum w min(v.n, 0)^2                        */
+  int detach_N;            /* Microfacet.detach_N (models/microfacet.py:117-118, 352-353)                              */
+  double* loss;            /* [3] out, device: photometric sum, sum of acc (prediction_loss / 2), ori_loss             */
+} NmfMicrofacetTrain;
+
+/* One forward + backward of a ray batch (rp->n_rays <= rp->chunk, as nmf_render_rays_train; rp->skip_eps / t_cut are
+ * ignored: the reference shades every sample of positive weight).  rays (n,6), gt (n,3) device: gt row i belongs to ray i
+ * (the kept rays are a prefix).  out / counters / tr as in nmf_render_rays_train (rgb_map and acc_map rows of the kept
+ * rays, whole_valid, n_kept, n_samples, the A19 sums).  workspace: nmf_render_train_workspace_bytes().  Asynchronous on
+ * `stream`; device-side list overflows are reported in NmfCounters.error (gradients are then incomplete: grow and repeat). */
+int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp, const NmfRenderTrain* tr, const NmfMicrofacetTrain* tp,
+                         const float* rays, const float* gt, const NmfMicrofacetGrads* grads, const NmfImages* out,
+                         const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Resolution schedule (fields/tensor_base.py:234-243 -> fields/tensoRF.py:208-227, 408-413): TensoRF.upsample is
  * F.interpolate(mode="bilinear", align_corners=True) of every factor.  src (C,H,W) -> dst (C,H2,W2), both in the

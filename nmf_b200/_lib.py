@@ -61,6 +61,18 @@ class NmfNormalGrads(C.Structure):
     _fields_ = [("gpack", c_ptr3), ("glpack", c_ptr3)]
 
 
+class NmfMicrofacetGrads(C.Structure):
+    _fields_ = [("d_plane", c_ptr3), ("d_line", c_ptr3), ("a_plane", c_ptr3), ("a_line", c_ptr3), ("basis_t", C.c_void_p),
+                ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+                ("w0t", C.c_void_p), ("b0", C.c_void_p), ("w1t", C.c_void_p), ("b1", C.c_void_p),
+                ("w2t", C.c_void_p), ("b2", C.c_void_p), ("gsat", C.c_void_p), ("d_mipbias", C.c_void_p),
+                ("normals", NmfNormalGrads)]
+
+
+class NmfMicrofacetTrain(C.Structure):
+    _fields_ = [("lambda_pred", C.c_float), ("lambda_ori", C.c_float), ("detach_N", C.c_int), ("loss", C.c_void_p)]
+
+
 class NmfTrain(C.Structure):
     _fields_ = [("n_rays", C.c_int), ("focal", C.c_float), ("seed", C.c_uint64), ("ray_id0", C.c_uint64),
                 ("ray_ids", C.c_void_p), ("max_samples", C.c_int), ("cap_samples", C.c_int),
@@ -108,7 +120,7 @@ _ERRORS = {-1: "NMF_E_ARG (null pointer or non-positive size)",
            -3: "NMF_E_WORKSPACE (workspace too small)"}
 N_PHASES = 11
 DEV_ERRORS = {1: "surviving-sample list overflowed", 2: "bounce-sample list overflowed",
-              4: "a chunk's bounce-ray region overflowed"}
+              4: "a chunk's bounce-ray region overflowed", 8: "the valid-sample list of the reverse pass overflowed"}
 
 
 def check(status, what):
@@ -168,6 +180,8 @@ def lib():
         "nmf_material_heads_bwd": (I, [SP, P, P, P, P, I, P, P, P, P]),
         "nmf_render_train_workspace_bytes": (C.c_size_t, [SP, I, F]),
         "nmf_render_rays_train": (I, [SP, RP, C.POINTER(NmfRenderTrain), P, IP, CP, P, C.c_size_t, P]),
+        "nmf_train_microfacet": (I, [SP, RP, C.POINTER(NmfRenderTrain), C.POINTER(NmfMicrofacetTrain), P, P,
+                                     C.POINTER(NmfMicrofacetGrads), IP, CP, P, C.c_size_t, P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
                                 C.c_size_t, P]),
     }
@@ -175,7 +189,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    assert L.nmf_abi_version() == 7, "libnmf_b200.so ABI mismatch: rebuild"
+    assert L.nmf_abi_version() == 8, "libnmf_b200.so ABI mismatch: rebuild"
     _lib = L
     return L
 
@@ -186,4 +200,4 @@ EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_pr
             "nmf_sample_rays_train", "nmf_train_workspace_bytes", "nmf_train_plain", "nmf_upsample_bilinear",
             "nmf_render_train_workspace_bytes", "nmf_render_rays_train", "nmf_l1_reg", "nmf_grad_sq_norm", "nmf_adam_step",
             "nmf_env_lookup_bwd_scatter", "nmf_env_lookup_bwd_finish", "nmf_env_lookup_bwd_mipbias", "nmf_vm_normals_bwd_scatter",
-            "nmf_vm_normals_bwd_finish", "nmf_material_heads_bwd"]
+            "nmf_vm_normals_bwd_finish", "nmf_material_heads_bwd", "nmf_train_microfacet"]

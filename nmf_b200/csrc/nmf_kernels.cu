@@ -23,142 +23,7 @@
 #include "nmf_mlp_tc.cuh"
 #include "nmf_train.cuh"   // train mode: jittered distances, dynamic batch truncation
 
-#define FULL 0xffffffffu
-#define NMF_BRAY_CAP_PER_RAY 160   // bounce rays per primary ray a chunk region can hold (typical: 57)
-#define NMF_SURV0_PER_RAY 64       // surviving samples per primary ray (typical: 10-20)
-#define NMF_BS0_PER_RAY 24         // bounce samples per primary ray (typical: 12)
-#define NMF_SURV1_PER_RAY 256      // per retraced ray
-#define NMF_BS1_PER_RAY 128
-#define NMF_TIE_CAP 64            // exact score ties at a chunk's retrace threshold that are ordered by ray key
-#define NMF_NO_OWNER 0xFFFFFFFFu  // ray -> sample map entry of a ray whose sample could not be allocated (overflow)
-
-struct Surv { uint32_t ray; uint32_t step; float w; };
-
-struct __align__(16) BSample {
-  float pos[3]; float w;
-  float V[3]; float rough;
-  float N[3]; int count;
-  float f0[3]; uint32_t ray;
-  float diffuse[3]; uint32_t roff;
-  float fresn[3]; uint32_t flags;
-  uint64_t key; uint32_t chunk; uint32_t pad;
-  float feat[24];
-  // what GGX sampling and the ISH encodings need per SAMPLE, computed once in k_shade instead of once per bounce ray:
-  // frame[0..17] = t, b, V_l, Vs, T1, T2 (nmf_ggx_frame), [18] = a, [19..20] = ISH scales s1, s2, [21..22] = the
-  // per-sample Sobol offsets 0.25 * U (brdf_samplers/base.py:16-19)
-  float frame[24];
-};
-
-struct __align__(16) BRay {     // bounce ray record handed from k_bounce to k_incoming
-  float L[3]; float mip;
-  float bw[3]; int slot;        // slot: index of the secondary ray that re-traces it, -1 = environment
-};
-
-// per-ray accumulators of level 0 (floats)
-// A_ORI / A_TINTU feed the A19 statistics: sum w * min(v.n, 0)^2 and the UNWEIGHTED sum of the per-sample tint
-enum { A_RGB = 0, A_WN = 3, A_CROSS = 6, A_DIFF = 9, A_TINT = 12, A_SPEC = 15, A_ALB = 18, A_ROUGH = 21, A_ORI = 22, A_TINTU = 23, A_N = 24 };
-
-struct WS {
-  // counters (zeroed every call)
-  int* n_surv;        // [2]
-  int* n_bs;          // [2]
-  int* ray_count0;    // [n_chunks]
-  int* ray_count1;    // [n_chunks]
-  int* n_samples0;    // [n_chunks]
-  int* n_samples1;    // [n_chunks]
-  int* n_cand;        // [n_chunks]
-  int* n_sec;         // [n_chunks]
-  unsigned long long* score_sum;   // [n_chunks] sum of the retrace scores in 2^-32 fixed point (order-independent)
-  double* wsum1;      // [n_chunks]
-  unsigned* error;    // [1]
-  float* stat4;       // [n_chunks][4] A19 statistics: sum of w*min(v.n,0)^2, of the diffuse map, of the sample tints, of acc
-  int* tile_start0;   // [n_chunks + 1]
-  int* tile_start1;   // [n_chunks + 1]
-  size_t counters_bytes;
-  char* counters_base;
-  // level 0
-  float* tmin0; float* acc0; float* depth0; int* termk0; int* nvalid0; float* accum0;   // accum0 [n_rays][A_N]
-  float4* red0;     // [cap_bs0][2]: {w, count, ray, flags} and the sum of the sample's combined bounce radiance (k_incoming -> k_reduce0)
-  Surv* surv0; BSample* bs0; BRay* brays0; uint32_t* owner0; float2* scu0;   // scu0: (retrace score, tie-break U) per ray
-  // level 1
-  float* rays1; float* mip1; uint64_t* key1; float* tmin1; float* acc1; int* nvalid1; float* accum1; float* rgb1;
-  Surv* surv1; BSample* bs1; BRay* brays1; uint32_t* owner1;
-  // train mode (nmf_render_rays_train): jittered distances per dense step, dynamic batch truncation
-  float* zvals0; float* zvals1; uint8_t* whole0; int* n_kept;
-  int n_chunks, n_rays1;
-  int cap_surv0, cap_bs0, cap_rays0;   // cap_rays0: per chunk
-  int cap_surv1, cap_bs1, cap_rays1;   // cap_rays1: per chunk
-  size_t total;
-};
-
-static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
-
-static void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base, float cap_scale = 1.0f, bool train = false) {
-  const double cs = cap_scale > 0.f ? (double)cap_scale : 1.0;
-  size_t off = 0;
-  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
-  int nc = (n_rays + chunk - 1) / chunk;
-  int maxre = s->model == 0 ? s->max_retrace : 0;
-  w.n_chunks = nc;
-  w.n_rays1 = nc * maxre;
-  auto cap = [&](double items) { double v = items * cs; return (int)(v < 2.0e9 ? v : 2.0e9); };
-  w.cap_surv0 = cap((double)n_rays * NMF_SURV0_PER_RAY);
-  w.cap_bs0 = cap((double)n_rays * NMF_BS0_PER_RAY);
-  w.cap_rays0 = cap((double)chunk * NMF_BRAY_CAP_PER_RAY);
-  w.cap_surv1 = cap((double)w.n_rays1 * NMF_SURV1_PER_RAY);
-  w.cap_bs1 = cap((double)w.n_rays1 * NMF_BS1_PER_RAY);
-  w.cap_rays1 = maxre > 0 ? s->max_brdf_rays1 + 1024 : 0;
-  w.counters_base = take(0);
-  w.n_surv = (int*)take(2 * sizeof(int));
-  w.n_bs = (int*)take(2 * sizeof(int));
-  w.ray_count0 = (int*)take(nc * sizeof(int));
-  w.ray_count1 = (int*)take(nc * sizeof(int));
-  w.n_samples0 = (int*)take(nc * sizeof(int));
-  w.n_samples1 = (int*)take(nc * sizeof(int));
-  w.n_cand = (int*)take(nc * sizeof(int));
-  w.n_sec = (int*)take(nc * sizeof(int));
-  w.score_sum = (unsigned long long*)take(nc * sizeof(unsigned long long));
-  w.wsum1 = (double*)take(nc * sizeof(double));
-  w.error = (unsigned*)take(sizeof(unsigned));
-  w.stat4 = (float*)take((size_t)nc * 4 * sizeof(float));
-  w.tile_start0 = (int*)take((nc + 1) * sizeof(int));
-  w.tile_start1 = (int*)take((nc + 1) * sizeof(int));
-  w.accum0 = (float*)take((size_t)n_rays * A_N * sizeof(float));
-  w.accum1 = (float*)take((size_t)w.n_rays1 * 4 * sizeof(float));
-  w.counters_bytes = off;   // everything up to here is zeroed at the start of a call
-  w.tmin0 = (float*)take((size_t)n_rays * 4);
-  w.acc0 = (float*)take((size_t)n_rays * 4);
-  w.depth0 = (float*)take((size_t)n_rays * 4);
-  w.termk0 = (int*)take((size_t)n_rays * 4);
-  w.nvalid0 = (int*)take((size_t)n_rays * 4);
-  w.surv0 = (Surv*)take((size_t)w.cap_surv0 * sizeof(Surv));
-  if (s->model == 0) {
-    w.bs0 = (BSample*)take((size_t)w.cap_bs0 * sizeof(BSample));
-    w.red0 = (float4*)take((size_t)w.cap_bs0 * 2 * sizeof(float4));
-    w.brays0 = (BRay*)take((size_t)nc * w.cap_rays0 * sizeof(BRay));
-    w.owner0 = (uint32_t*)take((size_t)nc * w.cap_rays0 * 4);
-    w.scu0 = (float2*)take((size_t)nc * w.cap_rays0 * sizeof(float2));
-    w.rays1 = (float*)take((size_t)w.n_rays1 * 6 * 4);
-    w.mip1 = (float*)take((size_t)w.n_rays1 * 4);
-    w.key1 = (uint64_t*)take((size_t)w.n_rays1 * 8);
-    w.tmin1 = (float*)take((size_t)w.n_rays1 * 4);
-    w.acc1 = (float*)take((size_t)w.n_rays1 * 4);
-    w.nvalid1 = (int*)take((size_t)w.n_rays1 * 4);
-    w.rgb1 = (float*)take((size_t)w.n_rays1 * 4 * 4);
-    w.surv1 = (Surv*)take((size_t)w.cap_surv1 * sizeof(Surv));
-    w.bs1 = (BSample*)take((size_t)w.cap_bs1 * sizeof(BSample));
-    w.brays1 = (BRay*)take((size_t)nc * w.cap_rays1 * sizeof(BRay));
-    w.owner1 = (uint32_t*)take((size_t)nc * w.cap_rays1 * 4);
-  }
-  w.zvals0 = w.zvals1 = nullptr; w.whole0 = nullptr; w.n_kept = nullptr;
-  if (train) {
-    w.zvals0 = (float*)take((size_t)n_rays * s->n_steps * 4);
-    w.zvals1 = (float*)take((size_t)w.n_rays1 * s->n_steps * 4);
-    w.whole0 = (uint8_t*)take((size_t)n_rays);
-    w.n_kept = (int*)take(2 * sizeof(int));
-  }
-  w.total = off;
-}
+#include "nmf_render_ws.cuh"
 
 // ================================================================================================
 // k_march: samplers/alphagrid.py:131-207,278-370 + fields/tensoRF.py:392-400 + tensor_nerf.py:19-35
@@ -176,6 +41,8 @@ struct MarchArgs {
   Surv* surv; int* n_surv; int cap_surv; unsigned* error;
   float* zvals;            // train mode: (n, n_steps) jittered distances (level 0: read, level 1: written here)
   const uint8_t* whole;    // train mode, level 0: rays kept by the dynamic batch truncation
+  // train mode: every valid sample is kept for the reverse pass (csrc/nmf_mf_train.cu)
+  VSmp* vs; float* vdw; int* vbase; int* n_vs; int cap_vs; uint32_t* survv;
 };
 
 // The 8-corner occupancy test of a step that lies exactly on a lattice plane.  Rare (a handful per thousand rays), so it
@@ -288,6 +155,12 @@ __global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchA
     __syncwarp();
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cand += __shfl_xor_sync(FULL, cand, off);
+    int vb = 0;
+    if (TRAIN && a.vs) {       // the ray's range in the valid-sample list kept for the reverse pass
+      if (lane == 0) { vb = nv ? atomicAdd(a.n_vs, nv) : 0; a.vbase[ray] = vb; }
+      vb = __shfl_sync(FULL, vb, 0);
+      if (nv && vb + nv > a.cap_vs) { if (lane == 0) atomicOr(a.error, NMF_DEV_E_VSAMPLES); vb = -1; }
+    }
     // ---- pass B: density of the valid samples (4 lanes per sample), transmittance, weights ----
     const int sub = lane & 3, sj = lane >> 2;
     const float wcut = a.skip_eps > 0.f ? a.skip_eps / (float)max(nv, 1) : 0.f;
@@ -317,9 +190,15 @@ __global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchA
       }
       float excl = __shfl_up_sync(FULL, incl, 4);
       if (lane < 4) excl = 1.f;
-      const float w = alpha * (T * excl);
+      const float Tex = T * excl;
+      const float w = alpha * Tex;
       T *= __shfl_sync(FULL, incl, 31);
       const bool mine = active && sub == 0;
+      if (TRAIN && a.vs && mine && vb >= 0) {
+        VSmp v; v.k = (uint32_t)k; v.f = f; v.alpha = alpha; v.T = Tex;
+        a.vs[vb + j] = v;
+        a.vdw[vb + j] = 0.f;
+      }
       if (mine) {
         acc += w;
         depth += w * z;
@@ -336,6 +215,7 @@ __global__ void __launch_bounds__(256, 4) k_march(const NmfScene s, const MarchA
           if (idx < a.cap_surv) {
             Surv sv; sv.ray = (uint32_t)ray; sv.step = (uint32_t)k; sv.w = w;
             a.surv[idx] = sv;
+            if (TRAIN && a.vs) a.survv[idx] = vb >= 0 ? (uint32_t)(vb + j) : 0u;
           } else {
             atomicOr(a.error, NMF_DEV_E_SURVIVORS);
           }
@@ -390,6 +270,7 @@ struct ShadeArgs {
   float4* red;              // level 0: per bounce sample {w, count, ray, flags | rgb sum}
   const float* zvals; int n_steps;   // train mode: jittered distances (n, n_steps)
   float min_rough;          // train mode: Microfacet.min_rough (models/microfacet.py:361-363)
+  const uint32_t* survv; int* survslot;   // train mode: survivor -> valid-sample index (in), survivor -> bounce-sample slot (out)
 };
 
 // Two phases per warp, 32 surviving samples at a time:
@@ -594,6 +475,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       }
     }
     BSample* b = a.bs + (slot >= 0 ? slot : 0);
+    if (TRAIN && a.survslot && active) a.survslot[si] = slot;
     float* acc = LEVEL == 0 ? a.accum + (size_t)ray * A_N : nullptr;
     // roughness head (render_modules.py:553-560; r2 = r1, microfacet.py:360)
     float lin = s_headb[9];
@@ -644,7 +526,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       q[3] = make_float4(hs[0], hs[1], hs[2], __uint_as_float((uint32_t)ray));
       q[4] = make_float4(hs[3], hs[4], hs[5], __uint_as_float((uint32_t)roff));
       q[5] = make_float4(hs[6], hs[7], hs[8], __uint_as_float(xn[2] < 0.f ? 1u : 0u));
-      b->key = skey; b->chunk = (uint32_t)chunk; b->pad = 0;
+      b->key = skey; b->chunk = (uint32_t)chunk; b->pad = (TRAIN && a.survv) ? a.survv[si] : 0u;
       if (LEVEL == 0) {
         a.red[2 * slot] = make_float4(w, __int_as_float(count), __uint_as_float((uint32_t)ray), __uint_as_float(xn[2] < 0.f ? 1u : 0u));
         a.red[2 * slot + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -693,7 +575,6 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
 // BRDF MLP 66 -> 64 -> 64 -> 4 (modules/brdf.py:73-120,237-239), one row per thread; weights in shared
 // memory (transposed, so that the 32 lanes broadcast-read 16 bytes of one weight row at a time)
 // ================================================================================================
-#define MLP_THREADS 128
 #define MLP_SMEM_FLOATS (66 * 64 + 64 + 64 * 64 + 64 + 64 * 4 + 4 + 66 * MLP_THREADS)
 
 __device__ __forceinline__ void mlp_load_weights(const NmfScene& s, float* sm) {
@@ -769,27 +650,6 @@ __device__ __forceinline__ void mlp_simt(const float* sm, float* xcol, const flo
 // ================================================================================================
 // k_bounce: brdf_samplers/base.py:11-20, ggx.py:61-268, models/microfacet.py:367-472 (+ :561-613 at level 1)
 // ================================================================================================
-// Segments = runs of lanes that share `key` (bounce rays of one sample are consecutive).  seg_setup finds, with one
-// ballot, whether this lane starts a run and the last lane of its run; seg_sum3 then leaves the run's total in its
-// first lane using value shuffles only.  All 32 lanes must call both.
-struct Seg { bool head; int last; };
-__device__ __forceinline__ Seg seg_setup(uint32_t key, int lane) {
-  Seg g;
-  const uint32_t prev = __shfl_up_sync(FULL, key, 1);
-  g.head = lane == 0 || prev != key;
-  const unsigned heads = __ballot_sync(FULL, g.head);
-  const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
-  g.last = above ? __ffs(above) - 2 : 31;
-  return g;
-}
-__device__ __forceinline__ void seg_sum3(float (&v)[3], const Seg& g, int lane) {
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const float a0 = __shfl_down_sync(FULL, v[0], off), a1 = __shfl_down_sync(FULL, v[1], off), a2 = __shfl_down_sync(FULL, v[2], off);
-    if (lane + off <= g.last) { v[0] += a0; v[1] += a1; v[2] += a2; }
-  }
-}
-
 struct BounceArgs {
   const BSample* bs; BRay* brays; const uint32_t* owner; const int* ray_count; int cap_rays;
   unsigned long long* score_sum; float2* scu;     // level 0: retrace scores
@@ -1477,7 +1337,7 @@ static NmfImages stage_images(const NmfImages& o, int stage) {
 
 static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* rays, const NmfImages* out,
                        const NmfCounters* counters, void* workspace, size_t workspace_bytes, void* stream_, const StagedCopy* sc,
-                       const NmfRenderTrain* tr = nullptr) {
+                       const NmfRenderTrain* tr = nullptr, WS* ws_out = nullptr) {
   int st = check_scene(scene);
   if (st) return st;
   if (!rp || !rays || !out || !workspace || rp->n_rays <= 0 || rp->chunk <= 0) return NMF_E_ARG;
@@ -1492,6 +1352,7 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
   if (tr && (s.model != 0 || rp->n_rays > rp->chunk || !tr->whole_valid || !tr->n_kept)) return NMF_E_UNSUPPORTED;
   carve(w, scene, rp->n_rays, rp->chunk, (char*)workspace, rp->cap_scale, tr != nullptr);
   if (w.total > workspace_bytes) return NMF_E_WORKSPACE;
+  if (ws_out) *ws_out = w;
   const int n = rp->n_rays, nc = w.n_chunks;
   CK(cudaMemsetAsync(w.counters_base, 0, w.counters_bytes, stream));
   prof_mark(0, stream);
@@ -1503,6 +1364,7 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
   m0.n_samples = w.n_samples0; m0.n_cand = w.n_cand; m0.wsum = nullptr;
   m0.surv = w.surv0; m0.n_surv = w.n_surv; m0.cap_surv = w.cap_surv0; m0.error = w.error;
   m0.zvals = w.zvals0; m0.whole = tr ? tr->whole_valid : nullptr;
+  if (tr) { m0.vs = w.vs0; m0.vdw = w.vdw0; m0.vbase = w.vbase0; m0.n_vs = w.n_vs; m0.cap_vs = w.cap_vs0; m0.survv = w.survv0; }
   static int g_march0 = 0, g_march1 = 0, g_inc0 = 0, g_inc1 = 0;
   if (!g_march0) {
     g_march0 = resident_grid(k_march<0, 0>, 256, 0); g_march1 = resident_grid(k_march<1, 0>, 256, 0);
@@ -1555,6 +1417,7 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
     h0.bs = w.bs0; h0.n_bs = w.n_bs; h0.cap_bs = w.cap_bs0; h0.ray_count = w.ray_count0; h0.cap_rays = w.cap_rays0;
     h0.owner = w.owner0; h0.error = w.error; h0.red = w.red0;
     h0.zvals = w.zvals0; h0.n_steps = s.n_steps; h0.min_rough = tr ? tr->min_rough : 0.f;
+    if (tr) { h0.survv = w.survv0; h0.survslot = w.survslot0; }
     if (tr) k_shade<0, 1><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h0);
     else k_shade<0, 0><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h0);
     CKL();
@@ -1589,6 +1452,7 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
       m1.n_samples = w.n_samples1; m1.n_cand = w.n_cand; m1.wsum = w.wsum1;
       m1.surv = w.surv1; m1.n_surv = w.n_surv + 1; m1.cap_surv = w.cap_surv1; m1.error = w.error;
       m1.zvals = w.zvals1;
+      if (tr) { m1.vs = w.vs1; m1.vdw = w.vdw1; m1.vbase = w.vbase1; m1.n_vs = w.n_vs + 1; m1.cap_vs = w.cap_vs1; m1.survv = w.survv1; }
       if (tr) k_march<1, 1><<<min(4 * g_march1, blocks_for(w.n_rays1, 8, 1 << 20)), 256, 0, stream>>>(s, m1);
       else k_march<1, 0><<<min(4 * g_march1, blocks_for(w.n_rays1, 8, 1 << 20)), 256, 0, stream>>>(s, m1);
       CKL();
@@ -1599,6 +1463,7 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
       h1.bs = w.bs1; h1.n_bs = w.n_bs + 1; h1.cap_bs = w.cap_bs1; h1.ray_count = w.ray_count1; h1.cap_rays = w.cap_rays1;
       h1.owner = w.owner1; h1.n_samples = w.n_samples1; h1.wsum = w.wsum1; h1.error = w.error;
       h1.zvals = w.zvals1; h1.n_steps = s.n_steps; h1.min_rough = tr ? tr->min_rough : 0.f;
+      if (tr) { h1.survv = w.survv1; h1.survslot = w.survslot1; }
       if (tr) k_shade<1, 1><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h1);
       else k_shade<1, 0><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h1);
       CKL();
@@ -1674,6 +1539,15 @@ extern "C" int nmf_render_rays_train(const NmfScene* scene, const NmfRender* rp,
                                      size_t workspace_bytes, void* stream_) {
   if (!tr) return NMF_E_ARG;
   return render_impl(scene, rp, rays, out, counters, workspace, workspace_bytes, stream_, nullptr, tr);
+}
+
+// the training forward for csrc/nmf_mf_train.cu: same call, and the carved workspace comes back so that the reverse pass
+// can read the records the forward left behind
+int nmf_render_impl_train(const NmfScene* scene, const NmfRender* rp, const NmfRenderTrain* tr, const float* rays,
+                          const NmfImages* out, const NmfCounters* counters, void* workspace, size_t workspace_bytes,
+                          void* stream_, WS* ws_out) {
+  if (!tr) return NMF_E_ARG;
+  return render_impl(scene, rp, rays, out, counters, workspace, workspace_bytes, stream_, nullptr, tr, ws_out);
 }
 
 extern "C" int nmf_render_rays_host(const NmfScene* scene, const NmfRender* rp, const float* rays_host, float* rays_dev,

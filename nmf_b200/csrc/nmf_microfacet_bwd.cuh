@@ -560,30 +560,39 @@ inline void nmf_env_map_grad_finish(float* gsat, int h, int w, const float* g_to
 // environment directions move with V; the BRDF weight does not (its encodings are detached, microfacet.py:461-472), nor do
 // the heads, the irradiance or the sample position.
 // ------------------------------------------------------------------------------------------------
+// One bounce ray of the above: d comb / d (tangent of V) with the BRDF weight `bw` given (it does not move with V);
+// comb = F inc bw + (1 - F) diffuse.  Shared by the host restatement below and k_mf_tangent1 (csrc/nmf_mf_train.cu).
+NMF_HD void nmf_bounce_ray_tangent(const NmfScene& s, NmfDual3 V, nmf_v3 N, const float* R0, const float* diffuse, float rough,
+                                   float u1, float u2, float mip, const float* bw, float* comb, float* dcomb) {
+  const NmfGGXdr dg = nmf_ggx_sample_dual3(u1, u2, V, nmf_d3k(N), nmf_dk(rough));
+  float inc[3], dinc[3];
+  const NmfDual3 Ld = nmf_d3(nmf_dmk(dg.L.x, dg.dL.x), nmf_dmk(dg.L.y, dg.dL.y), nmf_dmk(dg.L.z, dg.dL.z));
+  nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, Ld, mip, inc, dinc);
+  const NmfDual3 Hd = nmf_d3(nmf_dmk(dg.H.x, dg.dH.x), nmf_dmk(dg.H.y, dg.dH.y), nmf_dmk(dg.H.z, dg.dH.z));
+  NmfDual vh = nmf_ddot(V, Hd);
+  if (vh.v < 0.f) vh = nmf_dmk(-vh.v, -vh.d);                          // |v.h|
+  const NmfDual mm = nmf_dclamp(nmf_dk(1.0f) - vh, 0.0f, 1.0f);
+  const NmfDual m2 = mm * mm, m5 = m2 * m2 * mm;
+  for (int c = 0; c < 3; ++c) {
+    const NmfDual F = nmf_dk(R0[c]) + (1.0f - R0[c]) * m5;
+    const NmfDual v = F * nmf_dmk(inc[c], dinc[c]) * bw[c] + (nmf_dk(1.0f) - F) * diffuse[c];
+    comb[c] = v.v; dcomb[c] = v.d;
+  }
+}
 NMF_HD void nmf_bounce_sample_tangent(const NmfScene& s, const float* nfeat, NmfDual3 V, nmf_v3 N, const float* R0, const float* diffuse,
                                       float rough, const float* u, int m, float* refl, float* drefl) {
   const nmf_v3 Vv = nmf_mk3(V.x.v, V.y.v, V.z.v);
-  NmfDual acc[3] = {nmf_dk(0.f), nmf_dk(0.f), nmf_dk(0.f)};
+  float acc[3] = {0.f, 0.f, 0.f}, dacc[3] = {0.f, 0.f, 0.f};
   for (int j = 0; j < m; ++j) {
     const float u1 = u[2 * j], u2 = u[2 * j + 1];
     const NmfGGX fw = nmf_ggx_sample(u1, u2, Vv, N, rough);
-    const NmfGGXdr dg = nmf_ggx_sample_dual3(u1, u2, V, nmf_d3k(N), nmf_dk(rough));
     const float mip = -logf((float)m) - fw.logpdf;
-    float x[66], bw[3], inc[3], dinc[3];
+    float x[66], bw[3], comb[3], dcomb[3];
     nmf_brdf_input(nfeat, fw.half_l, fw.diff_l, rough, x);
     nmf_brdf_row_fwd_bwd(x, s.brdf_w0t, s.brdf_b0, s.brdf_w1t, s.brdf_b1, s.brdf_w2t, s.brdf_b2, s.brdf_bias, nullptr, bw, nullptr,
                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-    const NmfDual3 Ld = nmf_d3(nmf_dmk(dg.L.x, dg.dL.x), nmf_dmk(dg.L.y, dg.dL.y), nmf_dmk(dg.L.z, dg.dL.z));
-    nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, Ld, mip, inc, dinc);
-    const NmfDual3 Hd = nmf_d3(nmf_dmk(dg.H.x, dg.dH.x), nmf_dmk(dg.H.y, dg.dH.y), nmf_dmk(dg.H.z, dg.dH.z));
-    NmfDual vh = nmf_ddot(V, Hd);
-    if (vh.v < 0.f) vh = nmf_dmk(-vh.v, -vh.d);                          // |v.h|
-    const NmfDual mm = nmf_dclamp(nmf_dk(1.0f) - vh, 0.0f, 1.0f);
-    const NmfDual m2 = mm * mm, m5 = m2 * m2 * mm;
-    for (int c = 0; c < 3; ++c) {
-      const NmfDual F = nmf_dk(R0[c]) + (1.0f - R0[c]) * m5;
-      acc[c] = acc[c] + F * nmf_dmk(inc[c], dinc[c]) * bw[c] + (nmf_dk(1.0f) - F) * diffuse[c];
-    }
+    nmf_bounce_ray_tangent(s, V, N, R0, diffuse, rough, u1, u2, mip, bw, comb, dcomb);
+    for (int c = 0; c < 3; ++c) { acc[c] += comb[c]; dacc[c] += dcomb[c]; }
   }
-  for (int c = 0; c < 3; ++c) { refl[c] = acc[c].v / (float)m; drefl[c] = acc[c].d / (float)m; }
+  for (int c = 0; c < 3; ++c) { refl[c] = acc[c] / (float)m; drefl[c] = dacc[c] / (float)m; }
 }

@@ -152,6 +152,150 @@ def train_plain(scene, rays, gt, focal=1.0, seed=0, ray_id0=0, ray_ids=None, max
         return out
 
 
+MICROFACET_PARAM_KEYS = ([f"rf.density_rf.app_plane.{p}" for p in range(3)] + [f"rf.density_rf.app_line.{p}" for p in range(3)] +
+                         [f"rf.app_rf.app_plane.{p}" for p in range(3)] + [f"rf.app_rf.app_line.{p}" for p in range(3)] +
+                         ["rf.basis_mat.weight"] +
+                         [f"model.diffuse_module.{h}_mlp.0.{w}" for h in ("diffuse", "tint", "f0", "roughness") for w in ("weight", "bias")] +
+                         [f"model.brdf.mlp.{i}.{w}" for i in (0, 2, 4) for w in ("weight", "bias")] +
+                         ["bg_module.bg_mat", "bg_module.mipbias", "bg_module.brightness", "bg_module.mul"])
+HEAD_ROWS = {"diffuse": slice(0, 3), "tint": slice(3, 6), "f0": slice(6, 9), "roughness": slice(9, 11)}
+
+
+class MicrofacetGradBuffers:
+    """Gradient buffers of nmf_train_microfacet (struct NmfMicrofacetGrads) for one scene geometry.  Every buffer
+    ACCUMULATES over the sub-batches of an optimiser step; `finish` runs the two whole-image passes (environment map,
+    normal stencil adjoint) once per step, `reference_views` hands the result out under the reference's state_dict keys."""
+
+    def __init__(self, scene):
+        from .scene import derivative_stencils
+        dev, s = scene.device, scene.c
+        self.scene = scene
+        self.t = {}
+        self.c = _lib.NmfMicrofacetGrads()
+        z = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)
+        for p in range(3):
+            h, w, n = s.plane_h[p], s.plane_w[p], s.line_n[p]
+            for name, t, arr in ((f"d_plane{p}", z(h, w, 16), self.c.d_plane), (f"d_line{p}", z(n, 16), self.c.d_line),
+                                 (f"a_plane{p}", z(h, w, 24), self.c.a_plane), (f"a_line{p}", z(n, 24), self.c.a_line),
+                                 (f"gpack{p}", z(h, w, 48), self.c.normals.gpack), (f"glpack{p}", z(n, 4, 8), self.c.normals.glpack)):
+                self.t[name] = t
+                arr[p] = t.data_ptr()
+        self.eh, self.ew = int(s.env_h), int(s.env_w)
+        for name, shape in (("basis_t", (72, 24)), ("head_w", (11, 24)), ("head_b", (11,)), ("w0t", (66, 64)), ("b0", (64,)),
+                            ("w1t", (64, 64)), ("b1", (64,)), ("w2t", (64, 4)), ("b2", (4,)),
+                            ("gsat", (self.eh * self.ew * 4 + 8,)), ("d_mipbias", (1,))):
+            self.t[name] = z(*shape)
+            setattr(self.c, name, self.t[name].data_ptr())
+        self.t["d_bg"] = z(3, self.eh, self.ew)
+        self.t["d_env_scalars"] = z(2)                   # d brightness, d mul
+        kx, ky = derivative_stencils()
+        self.kx = kx.reshape(25).to(device=dev, dtype=torch.float32).contiguous()
+        self.ky = ky.reshape(25).to(device=dev, dtype=torch.float32).contiguous()
+        self.finished = False
+
+    def zero_(self):
+        for t in self.t.values():
+            t.zero_()
+        self.finished = False
+
+    def finish(self, bg_mat, brightness, mul):
+        """Once per optimiser step, after the last sub-batch: the adjoint of the environment's double cumsum + activation
+        (nmf_env_lookup_bwd_finish -> d bg_mat, d brightness, d mul) and of the 5x5 smoothed-difference stencil
+        (nmf_vm_normals_bwd_finish, added into the density-factor gradients)."""
+        if self.finished:
+            raise _lib.NmfError("MicrofacetGradBuffers.finish: already finished (zero_() starts the next step)")
+        L, dev = _lib.lib(), self.scene.device
+        bg = _f32(bg_mat.reshape(3, self.eh, self.ew), dev)
+        br, mu = (float(v.detach()) if torch.is_tensor(v) else float(v) for v in (brightness, mul))
+        with torch.cuda.device(dev):
+            sc = self.t["d_env_scalars"]
+            _lib.check(L.nmf_env_lookup_bwd_finish(_p(self.t["gsat"]), self.eh, self.ew, _p(bg), br, mu, _p(self.t["d_bg"]),
+                                                   _p(sc[0:1]), _p(sc[1:2]), _stream()), "nmf_env_lookup_bwd_finish")
+            pp = (C.c_void_p * 3)(*[self.t[f"d_plane{p}"].data_ptr() for p in range(3)])
+            lp = (C.c_void_p * 3)(*[self.t[f"d_line{p}"].data_ptr() for p in range(3)])
+            _lib.check(L.nmf_vm_normals_bwd_finish(self.scene.ref(), C.byref(self.c.normals), _p(self.kx), _p(self.ky), pp, lp,
+                                                   _stream()), "nmf_vm_normals_bwd_finish")
+        self.finished = True
+
+    def reference_views(self):
+        """{reference state_dict key: gradient in the parameter's own shape} (strided views; call `finish` first)."""
+        g = {}
+        for p in range(3):
+            g[f"rf.density_rf.app_plane.{p}"] = self.t[f"d_plane{p}"].permute(2, 0, 1)[None]
+            g[f"rf.density_rf.app_line.{p}"] = self.t[f"d_line{p}"].t()[None, :, :, None]
+            g[f"rf.app_rf.app_plane.{p}"] = self.t[f"a_plane{p}"].permute(2, 0, 1)[None]
+            g[f"rf.app_rf.app_line.{p}"] = self.t[f"a_line{p}"].t()[None, :, :, None]
+        g["rf.basis_mat.weight"] = self.t["basis_t"].t()
+        for h, rows in HEAD_ROWS.items():
+            g[f"model.diffuse_module.{h}_mlp.0.weight"] = self.t["head_w"][rows]
+            g[f"model.diffuse_module.{h}_mlp.0.bias"] = self.t["head_b"][rows]
+        for i, li in enumerate((0, 2, 4)):
+            g[f"model.brdf.mlp.{li}.weight"] = self.t[f"w{i}t"].t()
+            g[f"model.brdf.mlp.{li}.bias"] = self.t[f"b{i}"]
+        g["bg_module.bg_mat"] = self.t["d_bg"][None]
+        g["bg_module.mipbias"] = self.t["d_mipbias"][0]
+        g["bg_module.brightness"] = self.t["d_env_scalars"][0]
+        g["bg_module.mul"] = self.t["d_env_scalars"][1]
+        return g
+
+
+def train_microfacet(scene, rays, gt, focal=1.0, seed=0, ray_id0=0, max_samples=-1, min_rough=0.0, lambda_pred=3e-4,
+                     lambda_ori=0.1, detach_N=True, grads=None, zero_grads=True, buffers=None, check_errors=True):
+    """One fused training forward + backward of model=microfacet_tensorf2 on a ray batch (nmf_train_microfacet): the
+    forward of TensorNeRF.forward(is_train=True), the loss of train.py:586-657 and the hand-written reverse pass of every
+    stage.  rays (B,>=6), gt (B,3) on the GPU (gt row i belongs to ray i; the kept rays are a prefix).  Gradients accumulate
+    into `grads` (MicrofacetGradBuffers; zeroed first when zero_grads) and still need `grads.finish(...)` once per
+    optimiser step.  Returns dict(loss_photo, sum_acc, ori_loss, n_rays, n_samples, whole_valid, rgb_map, acc_map, grads,
+    buffers, statistics)."""
+    from . import ops
+    if scene.hp["model"] != "microfacet":
+        raise _lib.NmfError("train_microfacet: a 'microfacet' DeviceScene is required (model=tensorf trains through train_plain)")
+    r = _f32(rays[:, :6], scene.device)
+    g = _f32(gt.reshape(-1, 3), scene.device)
+    B = r.shape[0]
+    if B == 0 or g.shape[0] != B:
+        raise _lib.NmfError("train_microfacet: rays (B,6) and gt (B,3) with B > 0 expected")
+    if grads is None:
+        grads = MicrofacetGradBuffers(scene)
+    elif zero_grads:
+        grads.zero_()
+    if buffers is None or not getattr(buffers, "train", False) or buffers.n_rays != B:
+        buffers = ops.RenderBuffers(scene, B, B, ops.TRAIN_KEYS, cap_scale=2.0, train=True)
+    if not hasattr(buffers, "loss3"):
+        buffers.loss3 = torch.zeros(3, dtype=torch.float64, device=scene.device)
+    while True:
+        rp = _lib.NmfRender(n_rays=B, chunk=B, focal=float(focal), seed=int(seed), ray_id0=int(ray_id0), skip_eps=0.0, t_cut=0.0,
+                            white_bg=1, cap_scale=buffers.cap_scale)
+        tr = _lib.NmfRenderTrain(max_samples=int(max_samples), min_rough=float(min_rough),
+                                 whole_valid=buffers.whole_valid.data_ptr(), n_kept=buffers.n_kept.data_ptr())
+        tp = _lib.NmfMicrofacetTrain(lambda_pred=float(lambda_pred), lambda_ori=float(lambda_ori), detach_N=int(bool(detach_N)),
+                                     loss=buffers.loss3.data_ptr())
+        with torch.cuda.device(scene.device):
+            st = _lib.lib().nmf_train_microfacet(scene.ref(), C.byref(rp), C.byref(tr), C.byref(tp), _p(r), _p(g), C.byref(grads.c),
+                                                 C.byref(buffers.c_images), C.byref(buffers.c_counters),
+                                                 C.c_void_p(buffers.ws_ptr), buffers.ws_bytes, _stream())
+        _lib.check(st, "nmf_train_microfacet")
+        out = dict(buffers=buffers, grads=grads, loss=buffers.loss3, n_kept=buffers.n_kept)
+        if not check_errors:
+            return out
+        try:
+            stats = ops.read_counters(buffers, B, B)           # synchronises
+        except _lib.NmfOverflow:
+            if buffers.cap_scale >= 32 or not zero_grads:
+                raise                                          # (accumulated gradients cannot be rolled back)
+            loss3 = buffers.loss3
+            buffers = ops.RenderBuffers(scene, B, B, ops.TRAIN_KEYS, cap_scale=buffers.cap_scale * 2, train=True)
+            buffers.loss3 = loss3
+            grads.zero_()
+            continue
+        kept, m0 = buffers.n_kept.tolist()
+        loss = buffers.loss3.tolist()
+        out.update(loss_photo=loss[0], sum_acc=loss[1], ori_loss=loss[2], n_rays=kept, n_samples=stats["n_samples"][0],
+                   whole_valid=buffers.whole_valid[:B].bool(), rgb_map=buffers.images["rgb_map"][:kept],
+                   acc_map=buffers.images["acc_map"][:kept], statistics=stats["statistics"][0], counters=stats)
+        return out
+
+
 # configs/model/tensorf.yaml:69-111 (`params:`), the values train.py reads for model=tensorf
 REFERENCE_PARAMS = dict(L1_weight_initial=8e-5, clip_grad=10.0, weight_decay=1e-6, eps=1e-15, betas=(0.9, 0.99),
                         starting_batch_size=100, min_batch_size=4096, max_batch_size=32000, target_num_samples=400000,

@@ -1,0 +1,145 @@
+"""GPU: the reverse pass of the MICROFACET model (BASELINE configs #3 / #4) through the C ABI
+(nmf_train_microfacet) against torch autograd through the oracle's training forward.
+
+The oracle's loss and the gradient of every parameter are pinned to the UNMODIFIED reference by oracle/check_train.py
+(tests/golden/microfacet_*_train*.pt, replayed by tests/test_oracle_golden.py); here the oracle consumes the keyed random
+numbers the kernels draw (KeyedRNG), so sample counts are compared exactly and gradients to a stated tolerance
+(relative L2 per parameter: 5e-3, 2e-2 for the density factors whose gradient divides by 1 - alpha + 1e-10 and, with
+detach_N off, runs through the 5x5 stencil adjoint; 1.5e-2 for the scalar mipbias, a sum of cancelling box-size terms)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import device_scene, load_fixture, oracle_scene
+
+pytestmark = pytest.mark.gpu
+
+LAM_PRED, LAM_ORI = 3e-4, 0.1          # configs/model/microfacet_tensorf2.yaml:209,212
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from nmf_b200 import _lib
+    _lib.lib()          # raises if the extension is missing: no fallback
+    return torch.device("cuda:0")
+
+
+def oracle_grads(fix, rays, gt, seed, id0, detach_N, max_samples, min_rough=0.0, **hp):
+    from oracle import keyed_rng as KR
+    from oracle import nmf_oracle as O
+    osc = oracle_scene(fix, requires_grad=True, min_rough=min_rough, **hp)
+    keys = KR.primary_ray_keys(seed, np.arange(id0, id0 + rays.shape[0]).astype(np.uint64))
+    ims, st = O.render_chunk(osc, rays, fix["focal"], KR.KeyedRNG(), keys, draw_debug=False, is_train=True, detach_N=detach_N,
+                             max_samples=max_samples)
+    whole = st["whole_valid"]
+    photo = ((ims["rgb_map"].clip(0, 1) - gt[whole].clip(0, 1)) ** 2).sum()
+    (photo + LAM_PRED * st["prediction_loss"] + LAM_ORI * st["ori_loss"]).backward()
+    return osc, ims, st, float(photo.detach())
+
+
+def compare_grads(got, P, tol=5e-3, tol_density=2e-2, tol_scalar=1.5e-2, min_checked=20):
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
+    report = {}
+    for k, p in P.items():
+        if k not in got:
+            continue
+        g = got[k].detach().cpu().double().reshape(p.shape) if p.dim() else got[k].detach().cpu().double().reshape(())
+        if p.grad is None or float(p.grad.abs().max()) == 0.0:
+            assert float(g.abs().max()) < 1e-6, (k, float(g.abs().max()))
+            continue
+        report[k] = rel(g, p.grad.double())
+    assert len(report) >= min_checked, (len(report), sorted(report))
+    lim = lambda k: tol_density if "density_rf" in k else (tol_scalar if k in ("bg_module.mipbias", "bg_module.brightness", "bg_module.mul") else tol)
+    bad = {k: v for k, v in report.items() if v > lim(k)}
+    return report, bad
+
+
+CASES = [
+    # name, n rays, detach_N, max_samples fraction, min_rough, retrace, mlp
+    ("microfacet_g40", 96, True, None, 0.0, False, "fp32"),
+    ("microfacet_noncubic", 96, False, 0.6, 0.0, False, "fp32"),
+    ("microfacet_g40", 24, True, None, 0.0, True, "fp32"),
+    ("microfacet_g40", 24, False, None, 0.1, True, "fp32"),
+    ("microfacet_noncubic", 24, False, None, 0.0, True, "fp32"),
+    ("microfacet_g40", 96, False, None, 0.0, False, "f16"),
+    ("microfacet_g40", 24, False, None, 0.0, True, "f16"),
+]
+
+
+@pytest.mark.parametrize("name,n,detach_N,frac,min_rough,retrace,mlp", CASES)
+def test_microfacet_train_step_matches_oracle_gradients(env, name, n, detach_N, frac, min_rough, retrace, mlp):
+    """Loss, sample counts and the gradient of EVERY parameter of one nmf_train_microfacet call: one shading level
+    (max_retrace_rays = ()) and with every bounce ray re-traced (max_retrace_rays above their number: the no_grad top-k
+    selection is the identity), detach_N on / off, with the dynamic batch truncation and min_rough, fp32 and tcgen05 fp16
+    forward MLP (the latter with a looser tolerance: the forward BRDF weights carry ~1e-3 of fp16 rounding)."""
+    from nmf_b200 import train
+    from oracle import keyed_rng as KR
+    from oracle import nmf_oracle as O
+    fix = load_fixture(name)
+    hp = dict(max_retrace_rays=(8192,), max_brdf_rays=(650000, 20000)) if retrace else dict(max_retrace_rays=())
+    rays = fix["rays"][40:40 + n].contiguous()
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
+    seed, id0 = 21, 300
+    ms = -1
+    if frac is not None:
+        keys = KR.primary_ray_keys(seed, np.arange(id0, id0 + n).astype(np.uint64))
+        _, valid, _, _, _ = O.sample_rays(oracle_scene(fix), rays, fix["focal"], None, True, KR.KeyedRNG(), keys, -1)
+        ms = int(int(valid.sum()) * frac)
+    osc, ims, st, photo = oracle_grads(fix, rays, gt, seed, id0, detach_N, ms, min_rough=min_rough, **hp)
+    dsc = device_scene(fix, env, mlp=mlp, **hp)
+    out = train.train_microfacet(dsc, rays.cuda(), gt.cuda(), focal=fix["focal"], seed=seed, ray_id0=id0, max_samples=ms,
+                                 min_rough=min_rough, lambda_pred=LAM_PRED, lambda_ori=LAM_ORI, detach_N=detach_N)
+    kept = int(st["whole_valid"].sum())
+    assert out["n_rays"] == kept and (frac is None or 0 < kept < n)
+    assert torch.equal(out["whole_valid"].cpu(), st["whole_valid"])
+    assert out["n_samples"][0] == st["n_samples"][0]
+    if retrace:
+        assert len(st["n_samples"]) == 2 and st["n_samples"][1] > 500
+        assert abs(out["n_samples"][1] - st["n_samples"][1]) <= max(8, 0.002 * st["n_samples"][1]), (out["n_samples"], st["n_samples"])
+        assert out["counters"]["n_retrace"][0] == out["counters"]["n_bounce_rays0"][0]      # every bounce ray was re-traced
+    loose = mlp == "f16"
+    assert float((out["rgb_map"].cpu() - ims["rgb_map"].detach()).abs().max()) < (2e-3 if loose else 3e-4)
+    assert abs(out["loss_photo"] - photo) <= (2e-3 if loose else 2e-4) * max(1.0, photo)
+    assert abs(2 * out["sum_acc"] - float(st["prediction_loss"])) <= 1e-4 * float(st["prediction_loss"])
+    assert abs(out["ori_loss"] - float(st["ori_loss"])) <= 2e-3 * float(st["ori_loss"]) + 1e-9
+    g = out["grads"]
+    g.finish(dsc_bg(fix), *env_scalars(fix))
+    got = g.reference_views()
+    scale = 4.0 if loose else 1.0
+    report, bad = compare_grads(got, osc.params, tol=5e-3 * scale, tol_density=2e-2 * scale, tol_scalar=1.5e-2 * scale)
+    print(name, "detach_N" if detach_N else "live_N", "retrace" if retrace else "env", mlp, {k: f"{v:.1e}" for k, v in report.items()})
+    assert not bad, bad
+
+
+def dsc_bg(fix):
+    return torch.as_tensor(fix["state"]["bg_module.bg_mat"]).float().cuda()
+
+
+def env_scalars(fix):
+    st = fix["state"]
+    return float(st.get("bg_module.brightness", 0.0)), float(st.get("bg_module.mul", 1.0))
+
+
+def test_microfacet_train_step_accumulates_and_is_linear(env):
+    """Size-independent properties at a larger batch: two sub-batches accumulated into one set of buffers equal the sum of
+    the two separate calls (gradients are sums over rays), and the gradients are linear in the upstream (a second call with
+    the ground truth mirrored around the render has the opposite photometric gradient where no clip is active)."""
+    from nmf_b200 import train
+    fix = load_fixture("microfacet_g56_ship")
+    dsc = device_scene(fix, env)
+    rays = fix["rays"][:1024].contiguous().cuda()
+    gt = torch.rand(1024, 3, generator=torch.Generator().manual_seed(1)).cuda()
+    a = train.train_microfacet(dsc, rays[:512], gt[:512], focal=fix["focal"], seed=3, ray_id0=0, detach_N=False)
+    ga = {k: v.clone() for k, v in a["grads"].t.items()}
+    b = train.train_microfacet(dsc, rays[512:], gt[512:], focal=fix["focal"], seed=3, ray_id0=512, detach_N=False)
+    gb = {k: v.clone() for k, v in b["grads"].t.items()}
+    acc = train.MicrofacetGradBuffers(dsc)
+    train.train_microfacet(dsc, rays[:512], gt[:512], focal=fix["focal"], seed=3, ray_id0=0, detach_N=False, grads=acc, zero_grads=True)
+    train.train_microfacet(dsc, rays[512:], gt[512:], focal=fix["focal"], seed=3, ray_id0=512, detach_N=False, grads=acc, zero_grads=False)
+    for k in ("a_plane0", "d_plane1", "basis_t", "head_w", "w0t", "w1t", "gsat", "gpack2"):
+        ref = ga[k] + gb[k]
+        err = float((acc.t[k] - ref).abs().max())
+        assert err <= 2e-4 * float(ref.abs().max()) + 1e-9, (k, err, float(ref.abs().max()))
+        assert float(ref.abs().max()) > 0, k
