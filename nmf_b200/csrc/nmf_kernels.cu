@@ -1830,7 +1830,10 @@ __global__ void k_dense_alpha(const NmfScene s, int gx, int gy, int gz, float* a
   f += __shfl_xor_sync(FULL, f, 1);
   f += __shfl_xor_sync(FULL, f, 2);
   if (active && sub == 0) {
-    const float sigma = nmf_feature2density(f, s.density_shift);
+    // alphagrid.py:209-224 compute_alpha: where the CURRENT mask samples to 0 the density is not evaluated (sigma = 0), so
+    // a rebuild can only shrink the occupied set (up to the 3^3 dilation that follows)
+    const bool masked_out = s.has_occ && !nmf_occupied(s.occ_vox, s.occ_cell, s.ow, s.oh, s.od, s.opitch, xn[0], xn[1], xn[2]);
+    const float sigma = masked_out ? 0.f : nmf_feature2density(f, s.density_shift);
     alpha[i] = 1.0f - expf(-sigma * s.stepsize);                         // alphagrid.py:222 (no distance_scale)
   }
 }

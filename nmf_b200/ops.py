@@ -276,7 +276,7 @@ def image_sq_error(rgb, gt, pixel_ids=None):
 class RenderBuffers:
     """Output images, counters and scratch for batches of up to `n_rays` rays (grow-only cache per scene)."""
 
-    def __init__(self, scene, n_rays, chunk, keys, cap_scale=1.0, train=False):
+    def __init__(self, scene, n_rays, chunk, keys, cap_scale=1.0, train=False, min_ws_bytes=0):
         dev = scene.device
         self.train = train
         self.n_rays, self.chunk, self.cap_scale, self.keys = n_rays, chunk, float(cap_scale), list(keys)
@@ -301,6 +301,7 @@ class RenderBuffers:
             nbytes = _lib.lib().nmf_workspace_bytes_scaled(scene.ref(), n_rays, chunk, self.cap_scale)
         if nbytes == 0:
             raise _lib.NmfError("nmf_workspace_bytes: bad arguments")
+        nbytes = max(int(nbytes), int(min_ws_bytes))
         self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
         off = (-self.workspace.data_ptr()) % 256
         self.ws_ptr = self.workspace.data_ptr() + off

@@ -702,6 +702,7 @@ class TensorNeRF(nn.Module):
         self.lr_scale, self.hdr, self.eval_batch_size = lr_scale, hdr, eval_batch_size
         self.recur_stepmul, self.recur_alpha_thres = recur_stepmul, recur_alpha_thres
         self.near_far = list(near_far)
+        self.bg_noise, self.bg_noise_decay = bg_noise, bg_noise_decay
         self.skip_eps, self.t_cut, self.seed, self.mlp = ops.DEFAULT_SKIP_EPS, ops.DEFAULT_T_CUT, 20211200, "f16"
         self._scene, self._scene_key, self._bufs, self._calls = None, None, None, 0
         self._train_bufs = None
@@ -717,8 +718,15 @@ class TensorNeRF(nn.Module):
         return g
 
     def check_schedule(self, iter, batch_mul):
-        self.sampler.check_schedule(iter, batch_mul, self.rf)
-        return self.rf.check_schedule(iter, batch_mul)
+        """modules/tensor_nerf.py:177-195: the model's, the sampler's and the field's schedules; a True from any of them
+        means the caller re-creates the optimiser (train.py:806-813) and the sampler re-reads stepsize / nSamples."""
+        r = bool(self.model.check_schedule(iter, batch_mul))
+        r |= bool(self.sampler.check_schedule(iter, batch_mul, self.rf))
+        r |= bool(self.rf.check_schedule(iter, batch_mul))
+        if r:
+            self.sampler.update(self.rf, init=True)
+        self.bg_noise *= self.bg_noise_decay
+        return r
 
     def save(self, path, config):
         """modules/tensor_nerf.py:120-134: same wire format as the reference"""
@@ -775,40 +783,75 @@ class TensorNeRF(nn.Module):
         stats["envmap_reg"] = [env_reg] * len(st["statistics"])
         return ims, stats
 
-    def train_step(self, rays, gt, focal=1.0, ray_ids=None, lambda_pred=0.0):
-        """Forward + backward of one training iteration (train.py:540-700) in ONE fused device call (nmf_train_plain): the
-        training forward of modules/tensor_nerf.py:210-674 (jittered sampling, dynamic batch truncation), the photometric
-        loss of train.py:597-601 (+ lambda_pred * prediction_loss) and the hand-written backward.  Accumulates into the
-        `.grad` of every parameter (a SUM over rays; the caller divides by the batch size like train.py:709) and returns
-        (loss, statistics).  Covers model=tensorf; the microfacet backward is the rest of SURVEY 8f row 1."""
+    def train_step(self, rays, gt, focal=1.0, ray_ids=None, lambda_pred=0.0, lambda_ori=0.0):
+        """Forward + backward of one training iteration (train.py:540-712) in ONE fused device call: the training forward of
+        modules/tensor_nerf.py:210-674 (jittered sampling, dynamic batch truncation), the photometric loss of train.py:597-601
+        + lambda_pred * prediction_loss + lambda_ori * ori_loss, and the hand-written backward (nmf_train_plain for
+        model=tensorf, nmf_train_microfacet for model=microfacet_tensorf2: both shading levels, detach_N as scheduled).
+        Accumulates into the `.grad` of every parameter (a SUM over rays; the caller divides by the batch size like
+        train.py:709) and returns (loss, images, statistics).  No autograd graph is involved."""
         from . import train
         sc = self.scene()
-        if sc.hp["model"] != "plain":
-            raise NotImplementedError("TensorNeRF.train_step: the fused backward covers model=tensorf (SURVEY 8f row 1)")
-        out = train.train_plain(sc, rays.to(self.get_device()), gt.to(self.get_device()), focal=focal,
+        dev = self.get_device()
+        if sc.hp["model"] == "microfacet":
+            return self._train_step_microfacet(sc, rays.to(dev), gt.to(dev), focal, lambda_pred, lambda_ori)
+        out = train.train_plain(sc, rays.to(dev), gt.to(dev), focal=focal,
                                 seed=self.seed + self._calls, ray_ids=ray_ids, max_samples=self.sampler.max_samples,
                                 lambda_pred=lambda_pred, buffers=self._train_bufs)
         self._train_bufs = out["buffers"]
         self._calls += 1
-        params = dict(self.named_parameters())
-        for k, g in out["grads"].reference_layout().items():
-            p = params[k]
-            if p.grad is None:
-                p.grad = g.view_as(p).clone()
-            else:
-                p.grad.add_(g.view_as(p))
+        self._add_grads(out["grads"].reference_layout())
         stats = dict(recur=0, whole_valid=out["whole_valid"], n_samples=[out["n_samples"]],
                      prediction_loss=2.0 * out["sum_acc"], ori_loss=0.0, diffuse_reg=0.0, brdf_reg=0.0, distortion_loss=0.0,
                      envmap_reg=self._envmap_reg())
         images = dict(rgb_map=out["rgb_map"][:out["n_rays"]], acc_map=out["acc_map"][:out["n_rays"]])
         return out["loss_photo"] + lambda_pred * stats["prediction_loss"], images, stats
 
+    def _add_grads(self, grads):
+        params = dict(self.named_parameters())
+        for k, g in grads.items():
+            p = params.get(k)
+            if p is None:
+                continue
+            g = g.reshape(p.shape).to(p.dtype)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.add_(g)
+
+    def _train_step_microfacet(self, sc, rays, gt, focal, lambda_pred, lambda_ori):
+        from . import train
+        if self.model.std != 0:
+            raise NotImplementedError("Microfacet.std != 0 (material-head noise, render_modules.py:556-558) is not built")
+        if self.model.rays_per_ray != self.model.test_rays_per_ray:
+            raise NotImplementedError("rays_per_ray != test_rays_per_ray")
+        g = getattr(self, "_mf_grads", None)
+        if g is None or g.t["gpack0"].shape != sc.keep["dpack0"].shape or g.ew != int(sc.c.env_w) or g.t["gsat"].device != sc.device:
+            g = train.MicrofacetGradBuffers(sc)
+        g.scene = sc
+        self._mf_grads = g
+        n = rays.shape[0]
+        out = train.train_microfacet(sc, rays, gt, focal=focal, seed=self.seed, ray_id0=self._calls * n,
+                                     max_samples=self.sampler.max_samples, min_rough=self.model.min_rough,
+                                     lambda_pred=lambda_pred, lambda_ori=lambda_ori, detach_N=self.model.detach_N, grads=g,
+                                     zero_grads=True, buffers=self._render_train_bufs)
+        self._render_train_bufs = out["buffers"]
+        self._calls += 1
+        bg = self.bg_module
+        g.finish(bg.bg_mat.detach(), bg.brightness.detach(), bg.mul.detach())
+        self._add_grads(g.reference_views())
+        stats = dict(recur=0, whole_valid=out["whole_valid"], n_samples=list(out["n_samples"]), envmap_reg=self._envmap_reg())
+        stats.update(out["statistics"])
+        images = dict(rgb_map=out["rgb_map"], acc_map=out["acc_map"])
+        loss = out["loss_photo"] + lambda_pred * 2.0 * out["sum_acc"] + lambda_ori * out["ori_loss"]
+        return loss, images, stats
+
     @torch.no_grad()
     def forward_train(self, rays, focal, ray_id0=None):
         """TensorNeRF.forward(is_train=True, draw_debug=False) (modules/tensor_nerf.py:210-674) of the microfacet model
         for one ray batch, through nmf_render_rays_train: jittered steps (also in the re-traced rays), the dynamic batch
         truncation (statistics["whole_valid"], rows of the kept rays only), min_rough, the A19 regulariser inputs.
-        Forward only -- no autograd graph is built and the microfacet backward kernels do not exist yet."""
+        Forward only (what an eval of the training statistics needs); `train_step` is the forward + backward call."""
         sc = self.scene()
         if sc.hp["model"] != "microfacet":
             raise NotImplementedError("forward_train: model=tensorf trains through TensorNeRF.train_step")
@@ -854,14 +897,29 @@ class TensorNeRF(nn.Module):
 
     @staticmethod
     def load(ckpt, config=None, near_far=None, **kwargs):
-        """modules/tensor_nerf.py:136-175: rebuild from a reference-format checkpoint {config, state_dict}."""
+        """modules/tensor_nerf.py:136-175: rebuild from a reference-format checkpoint {config, state_dict}.  With an
+        external `config` (both reference entry points pass args.model.arch, train.py:80,245) the calibrated biases -- plain
+        attributes, not in the state_dict -- are copied over from the checkpoint's own config (tensor_nerf.py:138-146)."""
         from . import config as C
-        cfg = ckpt["config"] if config is None else config
         state = ckpt["state_dict"]
         aabb = state["rf.aabb"]
-        cfg = C.to_plain(cfg)
+        own = C.to_plain(ckpt["config"]) if ckpt.get("config") is not None else None
+        cfg = own if config is None else C.to_plain(config)
+        if config is not None and own is not None:
+            def get(d, path):
+                for k in path:
+                    if not isinstance(d, dict) or k not in d:
+                        return None
+                    d = d[k]
+                return d
+            for path in (("model", "brdf", "bias"), ("model", "diffuse_module", "diffuse_bias"),
+                         ("model", "diffuse_module", "roughness_bias")):
+                v = get(own, path)
+                dst = get(cfg, path[:-1])
+                if v is not None and isinstance(dst, dict):
+                    dst[path[-1]] = v
         cfg["rf"]["grid_size"] = state["rf.grid_size"].tolist()
-        t = C.instantiate(cfg)(aabb=aabb, near_far=near_far if near_far is not None else [2, 6])
+        t = C.instantiate(cfg)(aabb=aabb, near_far=near_far if near_far is not None else [1, 6])
         if "sampler.alphaMask.alpha_volume" in state:
             vol = state["sampler.alphaMask.alpha_volume"]
             t.sampler.alphaMask = AlphaGridMask(aabb, vol.reshape(vol.shape[-3:]))

@@ -261,6 +261,20 @@ class DeviceScene:
         self._pack_factors(state, derivatives=False)
         self._pack_plain_mlp(state)
 
+    def refresh_microfacet(self, state):
+        """After an optimiser step of model=microfacet_tensorf2: re-packs the factors (with their smoothed-difference
+        planes), the material heads / BRDF MLP operands and the environment tables (SAT, pole rows, SH irradiance) from the
+        updated parameters; the occupancy is left alone (the reference rebuilds it on its schedule only)."""
+        if self.hp["model"] != "microfacet":
+            raise _lib.NmfError("refresh_microfacet: microfacet scenes only")
+        self._pack_factors(state, derivatives=True)
+        keep_sobol = self.keep.get("sobol")
+        self._pack_shading(state)
+        if "sobol" not in self.keep and keep_sobol is not None:
+            self._ptr(self.c, "sobol", keep_sobol)
+        if "bg_module.bg_mat" in state:
+            self._set_env(state, None)
+
     @classmethod
     def env_only(cls, bg_mat, mipbias=1.0, brightness=0.0, mul=1.0, device="cuda"):
         """A scene that only carries the environment tables (for the IntegralEquirect plugin used on its own)."""

@@ -259,8 +259,14 @@ def train_microfacet(scene, rays, gt, focal=1.0, seed=0, ray_id0=0, max_samples=
         grads = MicrofacetGradBuffers(scene)
     elif zero_grads:
         grads.zero_()
-    if buffers is None or not getattr(buffers, "train", False) or buffers.n_rays != B:
-        buffers = ops.RenderBuffers(scene, B, B, ops.TRAIN_KEYS, cap_scale=2.0, train=True)
+    # scratch is grow-only: the batch size follows the adaptive controller (train.py:616-626) and the re-trace budget
+    # moves (models/microfacet.py:241-268), so the buffers are re-created only when they are too small, with headroom
+    cap_scale = 2.0 if buffers is None else buffers.cap_scale
+    need = _lib.lib().nmf_render_train_workspace_bytes(scene.ref(), B, cap_scale)
+    if buffers is None or not getattr(buffers, "train", False) or buffers.n_rays < B or buffers.ws_bytes < need:
+        nr = B if buffers is None else max(B, buffers.n_rays)
+        buffers = ops.RenderBuffers(scene, nr, nr, ops.TRAIN_KEYS, cap_scale=cap_scale, train=True,
+                                    min_ws_bytes=need if buffers is None else int(need * 1.25))
     if not hasattr(buffers, "loss3"):
         buffers.loss3 = torch.zeros(3, dtype=torch.float64, device=scene.device)
     while True:
@@ -284,7 +290,8 @@ def train_microfacet(scene, rays, gt, focal=1.0, seed=0, ray_id0=0, max_samples=
             if buffers.cap_scale >= 32 or not zero_grads:
                 raise                                          # (accumulated gradients cannot be rolled back)
             loss3 = buffers.loss3
-            buffers = ops.RenderBuffers(scene, B, B, ops.TRAIN_KEYS, cap_scale=buffers.cap_scale * 2, train=True)
+            buffers = ops.RenderBuffers(scene, buffers.n_rays, buffers.n_rays, ops.TRAIN_KEYS, cap_scale=buffers.cap_scale * 2,
+                                        train=True)
             buffers.loss3 = loss3
             grads.zero_()
             continue
@@ -344,7 +351,7 @@ class FusedAdam:
     coefficient is read from device memory: no host synchronisation).  `groups`: [{"params": [...], "lr": base_lr}]."""
 
     def __init__(self, groups, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0, clip_grad=None, lr_lambda=None, flat_grad=None):
-        self.groups = [dict(params=list(g["params"]), lr=float(g["lr"])) for g in groups]
+        self.groups = [dict(params=list(g["params"]), lr=float(g["lr"]), betas=g.get("betas")) for g in groups]
         self.betas, self.eps, self.weight_decay = (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.clip_grad = float(clip_grad) if clip_grad is not None and clip_grad > 0 else 0.0
         self.lr_lambda, self.flat_grad = lr_lambda, flat_grad
@@ -403,7 +410,8 @@ class FusedAdam:
             lam = self.lr_factor()                      # LambdaLR: update k (1-based) runs at base_lr * lambda(k - 1)
             self.t += 1
             for g in self.groups:
-                a = _lib.NmfAdam(lr=g["lr"] * lam, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                b1, b2 = self.betas if g.get("betas") is None else (float(g["betas"][0]), float(g["betas"][1]))
+                a = _lib.NmfAdam(lr=g["lr"] * lam, beta1=b1, beta2=b2, eps=self.eps,
                                  weight_decay=self.weight_decay, step=self.t, grad_scale=float(grad_scale),
                                  max_norm=self.clip_grad)
                 for run, n, m, v in g["runs"]:
@@ -453,14 +461,14 @@ class PlainTrainer:
         from .distributed import FlatGradBucket
         from .scene import DeviceScene
         self.device = torch.device(device)
-        self.meta = dict(aabb=aabb, near_far=near_far, grid_size=grid_size, hp=dict(hp, model="plain"))
+        self.meta = dict(aabb=aabb, near_far=near_far, grid_size=grid_size, hp=dict(hp, model=self.MODEL))
         self.alpha_volume = alpha_volume
         self.state = {k: torch.as_tensor(v).detach().clone().to(self.device) for k, v in state.items()}
-        self.params = self._flat_params({k: self.state[k].float() for k in PLAIN_PARAM_KEYS})
         self.lr_grid, self.lr_net = lr_grid, lr_net
+        self.params = self._flat_params({k: self.state[k].float() for k in self.PARAM_KEYS})
         self._FlatGradBucket = FlatGradBucket
         self.max_samples, self.lambda_pred, self.seed = max_samples, lambda_pred, seed
-        self.hparams = None if params is None else dict(REFERENCE_PARAMS, **params)
+        self.hparams = None if params is None else dict(self.DEFAULT_PARAMS, **params)
         self.l1_weight = 0.0 if params is None else float(self.hparams["L1_weight_initial"])
         self.l1_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.iteration = 0
@@ -470,14 +478,23 @@ class PlainTrainer:
         self._make_optimizer()
         self.repack()
 
+    PARAM_KEYS = PLAIN_PARAM_KEYS
+    MODEL = "plain"
+    DEFAULT_PARAMS = REFERENCE_PARAMS
+
     @staticmethod
     def _is_grid(k):
         return k.startswith("rf.") and "basis" not in k
 
+    def _group_defs(self):
+        """[(keys, lr, betas or None)] in flat-buffer order: every optimiser group is one contiguous segment."""
+        return [([k for k in self.PARAM_KEYS if self._is_grid(k)], self.lr_grid, None),
+                ([k for k in self.PARAM_KEYS if not self._is_grid(k)], self.lr_net, None)]
+
     def _flat_params(self, tensors):
         """Every parameter is a view of ONE flat fp32 buffer, the factor (grid) group first, then the network group --
         the same order as the flat gradient bucket, so that an optimiser group is one contiguous segment."""
-        order = [k for k in PLAIN_PARAM_KEYS if self._is_grid(k)] + [k for k in PLAIN_PARAM_KEYS if not self._is_grid(k)]
+        order = [k for keys, _, _ in self._group_defs() for k in keys]
         flat = torch.empty(sum(tensors[k].numel() for k in order), dtype=torch.float32, device=self.device)
         out, off = {}, 0
         for k in order:
@@ -490,10 +507,9 @@ class PlainTrainer:
         return out
 
     def _make_optimizer(self):
-        grid = [p for k, p in self.params.items() if self._is_grid(k)]
-        net = [p for k, p in self.params.items() if not self._is_grid(k)]
-        self.bucket = self._FlatGradBucket(grid + net)
-        groups = [dict(params=grid, lr=self.lr_grid), dict(params=net, lr=self.lr_net)]
+        defs = self._group_defs()
+        self.bucket = self._FlatGradBucket([self.params[k] for keys, _, _ in defs for k in keys])
+        groups = [dict(params=[self.params[k] for k in keys], lr=lr, betas=betas) for keys, lr, betas in defs]
         if self.hparams is None:
             self.optimizer = FusedAdam(groups, betas=(0.9, 0.99), flat_grad=self.bucket.flat)
         else:
@@ -540,7 +556,13 @@ class PlainTrainer:
             self.scene = self._DeviceScene(st, m["aabb"], m["near_far"], m["grid_size"], alpha_volume=self.alpha_volume,
                                            device=self.device, **m["hp"])
         else:
-            self.scene.refresh_plain(st)
+            self._refresh_scene(st)
+
+    def _refresh_scene(self, st):
+        self.scene.refresh_plain(st)
+
+    def _on_reinit(self):
+        """train.py:806-813 after the optimiser was re-created (model.reset_counter for the microfacet model)."""
 
     def accumulate(self, rays, gt, ray_ids=None, first=True):
         """Forward + backward of one ray sub-batch (the body of the `while num_remaining > 0` loop, train.py:509-712):
@@ -643,6 +665,7 @@ class PlainTrainer:
                        grid=list(self.meta["grid_size"]))
             if self.check_schedule(it, upsamp_list, n_voxel_list, update_list):
                 num_rays, prev = h["starting_batch_size"], None                         # train.py:810-812
+                self._on_reinit()
                 rec["reinit"] = True
             history.append(rec)
             if callback is not None:
@@ -774,3 +797,170 @@ def benchmark_microfacet_forward(grid=300, n_rays=4096, steps=20, device="cuda:0
                 kept_rays=st["n_kept"], n_samples=st["n_samples"], n_retrace=st["n_retrace"][0],
                 n_bounce_rays=[st["n_bounce_rays0"][0], st["n_bounce_rays1"][0]], ms_per_step=ms,
                 kept_rays_per_s=st["n_kept"] / ms * 1e3, note="includes the counter read-back (one host sync per step)")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# model=microfacet_tensorf2 (BASELINE configs #3 / #4)
+# ------------------------------------------------------------------------------------------------------------
+# configs/model/microfacet_tensorf2.yaml:192-240 (`params:`), the values train.py reads for this model
+MICROFACET_REFERENCE_PARAMS = dict(L1_weight_initial=8e-5, clip_grad=None, weight_decay=0.0, eps=1e-8, betas=(0.9, 0.99),
+                                   starting_batch_size=100, min_batch_size=4096, max_batch_size=8000,
+                                   target_num_samples=200000, n_iters=30000, batch_size=4096, lr_init=1.0, lr_final=1e-3,
+                                   lr_delay_mult=0.1, lr_delay_steps=100, pred_lambda=3e-4, ori_lambda=0.1)
+
+
+class MicrofacetTrainer(PlainTrainer):
+    """The optimiser loop of train.py:497-813 for model=microfacet_tensorf2: every sub-batch is one nmf_train_microfacet
+    call (forward + loss + reverse pass on the device, no autograd), the gradients of all sub-batches of an iteration
+    accumulate in MicrofacetGradBuffers, are finished once (environment-map and stencil adjoints), all-reduced as ONE flat
+    bucket when torch.distributed is initialised and applied by FusedAdam with the reference's
+    optimiser groups (fields/tensoRF.py:298-313, models/microfacet.py get_optparam_groups, modules/integral_equirect.py
+    get_optparam_groups); the model's own schedule (min_rough decay, detach_N, the adaptive re-trace budget,
+    models/microfacet.py:112-121, 241-268) runs between iterations.  fixed_bg=True is train.py:267-284 (config #3 with
+    backgrounds/forest.th): the map, its brightness and its scale are not trained (lr 0), mipbias still is."""
+    PARAM_KEYS = MICROFACET_PARAM_KEYS
+    MODEL = "microfacet"
+    DEFAULT_PARAMS = MICROFACET_REFERENCE_PARAMS
+
+    def __init__(self, state, aabb, near_far, grid_size, alpha_volume=None, device="cuda", lr_grid=2e-2, lr_net=1e-3,
+                 lr_heads=1e-3, lr_brdf=1e-3, lr_bg=0.02, lr_mipbias=1e-4, lr_brightness=0.0, lr_mul=0.0, bg_betas=(0.9, 0.99),
+                 mul_betas=(0.9, 0.9), fixed_bg=False, max_samples=200000, lambda_pred=3e-4, lambda_ori=0.1, seed=0, params=None,
+                 min_rough_start=0.0, min_rough_decay=0.999, detach_N_iters=0, target_num_samples=(1000000,), **hp):
+        self.lr_heads, self.lr_brdf = lr_heads, lr_brdf
+        self.lr_bg, self.lr_mipbias, self.lr_brightness, self.lr_mul = lr_bg, lr_mipbias, lr_brightness, lr_mul
+        if fixed_bg:
+            self.lr_bg = self.lr_brightness = self.lr_mul = 0.0
+        self.bg_betas, self.mul_betas = tuple(bg_betas), tuple(mul_betas)
+        self.lambda_ori = lambda_ori
+        self.min_rough, self.min_rough_decay = float(min_rough_start), float(min_rough_decay)
+        self.detach_N, self.detach_N_iters = True, int(detach_N_iters)
+        self.target_num_samples = list(target_num_samples)
+        self.grads, self.ratio_list, self._subs = None, None, 0
+        state = dict(state)
+        for k, d in (("bg_module.mipbias", 1.0), ("bg_module.brightness", 0.0), ("bg_module.mul", 1.0)):
+            state[k] = torch.as_tensor(state.get(k, d), dtype=torch.float32)
+        super().__init__(state, aabb, near_far, grid_size, alpha_volume=alpha_volume, device=device, lr_grid=lr_grid, lr_net=lr_net,
+                         max_samples=max_samples, lambda_pred=lambda_pred, seed=seed, params=params, **hp)
+        self.start_max_retrace = list(self.scene.hp["max_retrace_rays"])
+
+    def _group_defs(self):
+        K = self.PARAM_KEYS
+        sel = lambda f: [k for k in K if f(k)]
+        return [(sel(self._is_grid), self.lr_grid, None),
+                (["rf.basis_mat.weight"], self.lr_net, (0.9, 0.99)),
+                (sel(lambda k: k.startswith("model.diffuse_module.")), self.lr_heads, None),
+                (sel(lambda k: k.startswith("model.brdf.")), self.lr_brdf, None),
+                (["bg_module.bg_mat"], self.lr_bg, self.bg_betas),
+                (["bg_module.mipbias"], self.lr_mipbias, None),
+                (["bg_module.brightness"], self.lr_brightness, None),
+                (["bg_module.mul"], self.lr_mul, self.mul_betas)]
+
+    def _refresh_scene(self, st):
+        self.scene.refresh_microfacet(st)
+
+    def _on_reinit(self):
+        self.scene.update_hyper(max_retrace_rays=tuple(self.start_max_retrace))      # Microfacet.reset_counter
+        self.ratio_list = None
+
+    def upsample(self, grid_size, rebuild_occupancy=True):
+        super().upsample(grid_size, rebuild_occupancy)
+        self.grads = None
+
+    def update_n_samples(self, n_samples1):
+        """Microfacet.update_n_samples (models/microfacet.py:241-268, train.py:627): the re-trace budget follows
+        target_num_samples * min(recent re-traced rays per secondary sample), capped by max_brdf_rays[0]."""
+        hp = self.scene.hp
+        cur = list(hp["max_retrace_rays"])
+        if len(cur) != 1:
+            return
+        ratio = (cur[0] / n_samples1) if n_samples1 > 0 else 1e-3
+        self.ratio_list = [ratio, 1e-3] if self.ratio_list is None else ([ratio] + self.ratio_list)[:20]
+        new = min(int(self.target_num_samples[0] * min(self.ratio_list) + 1), int(hp["max_brdf_rays"][0]))
+        if new != cur[0]:
+            self.scene.update_hyper(max_retrace_rays=(new,))
+
+    def accumulate(self, rays, gt, ray_ids=None, first=True):
+        """One sub-batch (train.py:509-712): gradients accumulate on the device (MicrofacetGradBuffers)."""
+        if self.grads is None:
+            self.grads = MicrofacetGradBuffers(self.scene)
+        if first:
+            self.grads.zero_()
+            self._subs = 0
+        id0 = (self.seed * 7919 + self._calls) << 20
+        out = train_microfacet(self.scene, rays, gt, seed=self.seed + self._calls, ray_id0=id0, max_samples=self.max_samples,
+                               min_rough=self.min_rough, lambda_pred=self.lambda_pred, lambda_ori=self.lambda_ori,
+                               detach_N=self.detach_N, grads=self.grads, zero_grads=False, buffers=self.buffers)
+        self._calls += 1
+        self._subs += 1
+        self.buffers = out["buffers"]
+        ns = out["n_samples"]
+        out["n_samples_all"] = list(ns)
+        out["n_samples"] = ns[0]
+        if len(ns) > 1 and self.scene.c.max_retrace > 0:
+            self.update_n_samples(ns[1])
+        return out
+
+    def apply(self, n_rays_local, loss_local=0.0, normaliser=None):
+        import torch.distributed as dist
+        p = self.params
+        self.grads.finish(p["bg_module.bg_mat"].data, p["bg_module.brightness"].data, p["bg_module.mul"].data)
+        views = self.grads.reference_views()
+        for k, q in p.items():
+            q.grad.copy_(views[k].reshape(q.shape))
+        if self.l1_weight > 0:            # train.py:675-678 adds the density L1 term to EVERY sub-batch's loss
+            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            self.l1_sum.zero_()
+            for k, q in p.items():
+                if ".density_rf." in k:
+                    l1_reg(q.data, self.l1_weight * self._subs / world, q.grad, self.l1_sum)
+        return super().apply(n_rays_local, loss_local, normaliser)
+
+    def check_schedule(self, iteration, upsamp_list=(), n_voxel_list=(), update_list=()):
+        """TensorNeRF.check_schedule (modules/tensor_nerf.py:177-195): the model's schedule first
+        (models/microfacet.py:112-121), then the sampler's occupancy update and the field's upsampling."""
+        if iteration % 10 == 0:
+            self.min_rough *= self.min_rough_decay
+        if iteration > self.detach_N_iters:
+            self.detach_N = False
+        return super().check_schedule(iteration, upsamp_list, n_voxel_list, update_list)
+
+
+def benchmark_microfacet_train(grid=300, n_rays=4096, steps=20, device="cuda:0", max_retrace=1000, detach_N=False, mlp="f16",
+                               env="synthetic"):
+    """Times nmf_train_microfacet (forward + loss + reverse pass of microfacet_tensorf2, BASELINE config #3's shape:
+    G = 300, 4096-ray batches truncated at max_samples = 200000, one re-traced level) with CUDA events, phase by phase
+    from the kernel launch list when `profile`.  Synthetic scene; gt = the eval render of the same scene."""
+    from . import ops, synthetic
+    from .scene import DeviceScene
+    dev = torch.device(device)
+    state, meta = synthetic.make_scene("materials", grid_size=grid)
+    sc = DeviceScene(state, meta["aabb"], meta["near_far"], meta["grid_size"], device=dev, model="microfacet", mlp=mlp,
+                     max_retrace_rays=(max_retrace,))
+    sc.update_alpha_mask()
+    H = W = 800
+    focal = synthetic.focal_for(W)
+    pose = synthetic.hemisphere_poses(4)[1]
+    pix = torch.randperm(H * W, generator=torch.Generator().manual_seed(0))[:n_rays]
+    rays = synthetic.camera_rays(pose, H, W, focal)[pix].contiguous().to(dev)
+    gt = ops.render_rays(sc, rays, focal, chunk=n_rays, skip_eps=0.0, t_cut=0.0)[0]["rgb_map"].clone()
+    out = train_microfacet(sc, rays, gt, focal=focal, seed=1, max_samples=200000, detach_N=detach_N)
+    bufs, grads = out["buffers"], out["grads"]
+    for i in range(3):
+        train_microfacet(sc, rays, gt, focal=focal, seed=2 + i, max_samples=200000, detach_N=detach_N, grads=grads, buffers=bufs,
+                         check_errors=False)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for i in range(steps):
+        train_microfacet(sc, rays, gt, focal=focal, seed=5 + i, max_samples=200000, detach_N=detach_N, grads=grads, buffers=bufs,
+                         check_errors=False)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / max(steps, 1)
+    fwd = benchmark_microfacet_forward(grid, n_rays, steps, device) if max_retrace == 1000 else None
+    c = out["counters"]
+    return dict(what="nmf_train_microfacet: forward + loss + reverse pass, microfacet_tensorf2 (SURVEY 8f row 1, config #3 shape)",
+                grid=grid, rays=n_rays, kept_rays=out["n_rays"], n_samples=out["n_samples"], max_retrace=max_retrace,
+                n_retrace=c["n_retrace"][0], n_bounce_rays=[c["n_bounce_rays0"][0], c["n_bounce_rays1"][0]], detach_N=bool(detach_N),
+                mlp=mlp, ms_per_step=ms, kept_rays_per_s=out["n_rays"] / ms * 1e3,
+                forward_only_ms=None if fwd is None else fwd["ms_per_step"])

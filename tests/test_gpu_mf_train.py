@@ -65,6 +65,10 @@ CASES = [
     ("microfacet_noncubic", 24, False, None, 0.0, True, "fp32"),
     ("microfacet_g40", 96, False, None, 0.0, False, "f16"),
     ("microfacet_g40", 24, False, None, 0.0, True, "f16"),
+    # rays cast from INSIDE the object (near = 0.05): they leave through back-facing surfaces, so ori_loss > 0 and its
+    # gradient (to the weights and, through the normal, to the density factors) is a material part of the step
+    ("inside:microfacet_g40", 64, True, None, 0.0, False, "fp32"),
+    ("inside:microfacet_noncubic", 64, False, None, 0.0, False, "fp32"),
 ]
 
 
@@ -77,9 +81,15 @@ def test_microfacet_train_step_matches_oracle_gradients(env, name, n, detach_N, 
     from nmf_b200 import train
     from oracle import keyed_rng as KR
     from oracle import nmf_oracle as O
-    fix = load_fixture(name)
+    inside = name.startswith("inside:")
+    fix = load_fixture(name.split(":")[-1])
     hp = dict(max_retrace_rays=(8192,), max_brdf_rays=(650000, 20000)) if retrace else dict(max_retrace_rays=())
     rays = fix["rays"][40:40 + n].contiguous()
+    if inside:
+        fix = dict(fix, near_far=(0.05, 6.0))
+        gen = torch.Generator().manual_seed(11)
+        d = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+        rays = torch.cat([0.05 * torch.randn(n, 3, generator=gen), d], dim=1).contiguous()
     gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
     seed, id0 = 21, 300
     ms = -1
@@ -104,6 +114,7 @@ def test_microfacet_train_step_matches_oracle_gradients(env, name, n, detach_N, 
     assert abs(out["loss_photo"] - photo) <= (2e-3 if loose else 2e-4) * max(1.0, photo)
     assert abs(2 * out["sum_acc"] - float(st["prediction_loss"])) <= 1e-4 * float(st["prediction_loss"])
     assert abs(out["ori_loss"] - float(st["ori_loss"])) <= 2e-3 * float(st["ori_loss"]) + 1e-9
+    assert (float(st["ori_loss"]) > 1e-3) == inside, float(st["ori_loss"])
     g = out["grads"]
     g.finish(dsc_bg(fix), *env_scalars(fix))
     got = g.reference_views()
@@ -124,20 +135,21 @@ def env_scalars(fix):
 
 def test_microfacet_train_step_accumulates_and_is_linear(env):
     """Size-independent properties at a larger batch: two sub-batches accumulated into one set of buffers equal the sum of
-    the two separate calls (gradients are sums over rays), and the gradients are linear in the upstream (a second call with
-    the ground truth mirrored around the render has the opposite photometric gradient where no clip is active)."""
+    the two separate calls (gradients are sums over rays; the selection of re-traced rays is per call, as in the reference)."""
     from nmf_b200 import train
     fix = load_fixture("microfacet_g56_ship")
     dsc = device_scene(fix, env)
-    rays = fix["rays"][:1024].contiguous().cuda()
-    gt = torch.rand(1024, 3, generator=torch.Generator().manual_seed(1)).cuda()
-    a = train.train_microfacet(dsc, rays[:512], gt[:512], focal=fix["focal"], seed=3, ray_id0=0, detach_N=False)
+    rays = fix["rays"].contiguous().cuda()
+    n = rays.shape[0]
+    h = n // 2
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(1)).cuda()
+    a = train.train_microfacet(dsc, rays[:h], gt[:h], focal=fix["focal"], seed=3, ray_id0=0, detach_N=False)
     ga = {k: v.clone() for k, v in a["grads"].t.items()}
-    b = train.train_microfacet(dsc, rays[512:], gt[512:], focal=fix["focal"], seed=3, ray_id0=512, detach_N=False)
+    b = train.train_microfacet(dsc, rays[h:], gt[h:], focal=fix["focal"], seed=3, ray_id0=h, detach_N=False)
     gb = {k: v.clone() for k, v in b["grads"].t.items()}
     acc = train.MicrofacetGradBuffers(dsc)
-    train.train_microfacet(dsc, rays[:512], gt[:512], focal=fix["focal"], seed=3, ray_id0=0, detach_N=False, grads=acc, zero_grads=True)
-    train.train_microfacet(dsc, rays[512:], gt[512:], focal=fix["focal"], seed=3, ray_id0=512, detach_N=False, grads=acc, zero_grads=False)
+    train.train_microfacet(dsc, rays[:h], gt[:h], focal=fix["focal"], seed=3, ray_id0=0, detach_N=False, grads=acc, zero_grads=True)
+    train.train_microfacet(dsc, rays[h:], gt[h:], focal=fix["focal"], seed=3, ray_id0=h, detach_N=False, grads=acc, zero_grads=False)
     for k in ("a_plane0", "d_plane1", "basis_t", "head_w", "w0t", "w1t", "gsat", "gpack2"):
         ref = ga[k] + gb[k]
         err = float((acc.t[k] - ref).abs().max())

@@ -345,8 +345,14 @@ def test_microfacet_train_forward_plugin(env):
     t._calls = 0
     ev2, _ = t(rays, fix["focal"])
     assert torch.allclose(ev2["rgb_map"], ev, atol=1e-5)
-    with pytest.raises(NotImplementedError):
-        t.train_step(rays, torch.zeros(256, 3).cuda())
+    # train_step = forward + reverse pass on the device (nmf_train_microfacet): every trained parameter gets a gradient
+    t.zero_grad()
+    loss, ims2, st2 = t.train_step(rays, torch.rand(256, 3, generator=torch.Generator().manual_seed(0)).cuda(), focal=fix["focal"],
+                                   lambda_pred=3e-4, lambda_ori=0.1)
+    assert np.isfinite(loss) and loss > 0 and ims2["rgb_map"].shape[0] == int(st2["whole_valid"].sum())
+    missing = [k for k, p in t.named_parameters() if (p.grad is None or float(p.grad.abs().max()) == 0.0)
+               and "tint_mlp" not in k and "dbasis" not in k]
+    assert not missing, missing
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -521,3 +527,32 @@ def test_fit_schedule_events(env):
     assert tr.params["rf.density_rf.app_plane.0"].shape[-2:] == (want[1], want[0])
     assert tuple(tr.alpha_volume.shape) == (want[2], want[1], want[0])          # rebuilt at iteration 5, new resolution
     assert all(np.isfinite(h["mse"]) for h in hist) and hist[-1]["mse"] < 1e-2
+
+
+def test_microfacet_trainer_fits_a_teacher(env):
+    """MicrofacetTrainer (the loop of train.py:497-813 for model=microfacet_tensorf2 on nmf_train_microfacet + FusedAdam):
+    from perturbed appearance / material / BRDF weights, a few dozen iterations on rays rendered from the unperturbed
+    scene bring the photometric loss down; the schedule state (detach_N, min_rough, re-trace budget) moves as the
+    reference's does."""
+    from nmf_b200 import ops, train
+    fix = load_fixture("microfacet_g40")
+    G = fix["grid_size"]
+    teacher = device_scene(fix, env)
+    rays = fix["rays"].cuda()
+    gt = ops.render_rays(teacher, rays, fix["focal"], chunk=rays.shape[0], skip_eps=0.0, t_cut=0.0, seed=5)[0]["rgb_map"].clone()
+    g = torch.Generator().manual_seed(2)
+    st = {k: v.clone() for k, v in fix["state"].items()}
+    for k in train.MICROFACET_PARAM_KEYS:
+        if "app_rf" in k or "diffuse_module" in k or "brdf.mlp" in k:
+            st[k] = st[k] + 0.3 * st[k].abs().mean() * torch.randn(st[k].shape, generator=g)
+    tr = train.MicrofacetTrainer(st, fix["aabb"], fix["near_far"], [G] * 3, alpha_volume=fix["alpha_volume"], device=env,
+                                 max_samples=-1, min_rough_start=0.2, seed=3)
+    assert tr.detach_N and tr.min_rough == 0.2
+    mse = []
+    for it in range(40):
+        out = tr.step(rays, gt)
+        mse.append(out["mse"])
+        tr.check_schedule(it)
+    assert not tr.detach_N and tr.min_rough < 0.2                      # models/microfacet.py:112-121
+    assert np.isfinite(mse).all() and np.mean(mse[-5:]) < 0.6 * np.mean(mse[:3]), (mse[:3], mse[-5:])
+    assert tr.scene.hp["max_retrace_rays"][0] != 1000                   # the adaptive re-trace budget moved (microfacet.py:241-268)
