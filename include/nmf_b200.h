@@ -241,8 +241,10 @@ int nmf_brdf_mlp(const NmfScene* scene, const float* feat, const float* half_loc
 int nmf_material_heads(const NmfScene* scene, const float* feat, int n, float* albedo, float* tint, float* f0,
                        float* r1, float* r2, void* stream);
 /* occupancy rebuild, alpha stage of AlphaGridSampler.getDenseAlpha (samplers/alphagrid.py:209-247):
- * alpha[z][y][x] = 1 - exp(-sigma(lattice point) * stepsize) on a (gz,gy,gx) lattice spanning the aabb */
-int nmf_dense_alpha(const NmfScene* scene, int gx, int gy, int gz, float* alpha, void* stream);
+ * alpha[z][y][x] = 1 - exp(-sigma(lattice point) * stepsize) on a (gz,gy,gx) lattice spanning the aabb; sigma = 0 where the
+ * scene's CURRENT occupancy samples to 0 (compute_alpha, :209-224).  lins (device, optional): gx + gy + gz floats, the
+ * caller's torch.linspace(0, 1, g) of the three axes (x | y | z) -- NULL: an emulation of ATen's scalar formula */
+int nmf_dense_alpha(const NmfScene* scene, int gx, int gy, int gz, const float* lins, float* alpha, void* stream);
 
 /* ---- the callers either side of the path ---- */
 

@@ -163,7 +163,7 @@ def lib():
         "nmf_ggx_sample": (I, [P, P, P, P, I, P, P, P, P, P]),
         "nmf_brdf_mlp": (I, [SP, P, P, P, P, I, P, P]),
         "nmf_material_heads": (I, [SP, P, I, P, P, P, P, P, P]),
-        "nmf_dense_alpha": (I, [SP, I, I, I, P, P]),
+        "nmf_dense_alpha": (I, [SP, I, I, I, P, P, P]),
         "nmf_generate_rays": (I, [P, I, I, F, F, F, F, P, I, P, P]),
         "nmf_image_sq_error": (I, [P, P, P, I, P, P]),
         "nmf_sample_rays_train": (I, [SP, P, I, F, C.c_uint64, C.c_uint64, P, I, P, P, P, P, P, P]),

@@ -1806,7 +1806,7 @@ extern "C" int nmf_material_heads(const NmfScene* scene, const float* feat, int 
   return NMF_OK;
 }
 // samplers/alphagrid.py:209-247: alpha on the (gz,gy,gx) lattice; lattice point = aabb0*(1-s) + aabb1*s, s = linspace(0,1,g)
-__global__ void k_dense_alpha(const NmfScene s, int gx, int gy, int gz, float* alpha) {
+__global__ void k_dense_alpha(const NmfScene s, int gx, int gy, int gz, const float* __restrict__ lins, float* alpha) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = t >> 2;
   const int sub = (int)(t & 3);
@@ -1819,7 +1819,10 @@ __global__ void k_dense_alpha(const NmfScene s, int gx, int gy, int gz, float* a
     const float step = 1.0f / (float)(g - 1);
     return i < g / 2 ? NMF_MUL(step, (float)i) : NMF_SUB(1.0f, NMF_MUL(step, (float)(g - 1 - i)));
   };
-  const float sx = lin(x, gx), sy = lin(y, gy), sz = lin(z, gz);
+  // `lins`: the caller's own torch.linspace(0, 1, g) per axis (x | y | z).  ATen's CPU linspace is vectorised, so its bits
+  // depend on the host ISA; a sample that lies exactly on a plane of the current mask's lattice sees one voxel or eight
+  // depending on the last bit, so the reference's coordinates are taken as they are rather than re-derived
+  const float sx = lins ? lins[x] : lin(x, gx), sy = lins ? lins[gx + y] : lin(y, gy), sz = lins ? lins[gx + gy + z] : lin(z, gz);
   float p[3], xn[3];
   p[0] = NMF_ADD(NMF_MUL(s.aabb0[0], NMF_SUB(1.0f, sx)), NMF_MUL(s.aabb1[0], sx));
   p[1] = NMF_ADD(NMF_MUL(s.aabb0[1], NMF_SUB(1.0f, sy)), NMF_MUL(s.aabb1[1], sy));
@@ -1837,12 +1840,12 @@ __global__ void k_dense_alpha(const NmfScene s, int gx, int gy, int gz, float* a
     alpha[i] = 1.0f - expf(-sigma * s.stepsize);                         // alphagrid.py:222 (no distance_scale)
   }
 }
-extern "C" int nmf_dense_alpha(const NmfScene* scene, int gx, int gy, int gz, float* alpha, void* stream) {
+extern "C" int nmf_dense_alpha(const NmfScene* scene, int gx, int gy, int gz, const float* lins, float* alpha, void* stream) {
   int st = check_scene(scene);
   if (st) return st;
   if (!alpha || gx < 2 || gy < 2 || gz < 2) return NMF_E_ARG;
   const long long total = (long long)gx * gy * gz * 4;
-  k_dense_alpha<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*scene, gx, gy, gz, alpha);
+  k_dense_alpha<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*scene, gx, gy, gz, lins, alpha);
   CKL();
   return NMF_OK;
 }

@@ -228,7 +228,9 @@ def material_heads_bwd(scene, feat, g_albedo, g_f0, g_rough, d_head_w=None, d_he
 def dense_alpha(scene, grid_size):
     gx, gy, gz = (int(g) for g in grid_size)
     out = torch.empty(gz, gy, gx, device=scene.device)
-    _lib.check(_lib.lib().nmf_dense_alpha(scene.ref(), gx, gy, gz, _p(out), _stream()), "nmf_dense_alpha")
+    # samplers/alphagrid.py:230-236: the lattice coordinates are torch.linspace tensors made on the host
+    lins = torch.cat([torch.linspace(0, 1, g) for g in (gx, gy, gz)]).to(scene.device)
+    _lib.check(_lib.lib().nmf_dense_alpha(scene.ref(), gx, gy, gz, _p(lins), _p(out), _stream()), "nmf_dense_alpha")
     return out
 
 

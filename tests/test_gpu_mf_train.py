@@ -4,8 +4,9 @@
 The oracle's loss and the gradient of every parameter are pinned to the UNMODIFIED reference by oracle/check_train.py
 (tests/golden/microfacet_*_train*.pt, replayed by tests/test_oracle_golden.py); here the oracle consumes the keyed random
 numbers the kernels draw (KeyedRNG), so sample counts are compared exactly and gradients to a stated tolerance
-(relative L2 per parameter: 5e-3, 2e-2 for the density factors whose gradient divides by 1 - alpha + 1e-10 and, with
-detach_N off, runs through the 5x5 stencil adjoint; 1.5e-2 for the scalar mipbias, a sum of cancelling box-size terms)."""
+(relative L2 per parameter: 3e-3, 5e-3 for the density factors whose gradient divides by 1 - alpha + 1e-10 and, with
+detach_N off, runs through the 5x5 stencil adjoint; 1.5e-2 for the scalar mipbias, a sum of cancelling box-size terms;
+measured on a B200: 1e-5 .. 1e-3, mipbias 7e-5 .. 3.5e-3; x4 with the fp16 tensor-core forward MLP)."""
 import numpy as np
 import pytest
 import torch
@@ -119,7 +120,7 @@ def test_microfacet_train_step_matches_oracle_gradients(env, name, n, detach_N, 
     g.finish(dsc_bg(fix), *env_scalars(fix))
     got = g.reference_views()
     scale = 4.0 if loose else 1.0
-    report, bad = compare_grads(got, osc.params, tol=5e-3 * scale, tol_density=2e-2 * scale, tol_scalar=1.5e-2 * scale)
+    report, bad = compare_grads(got, osc.params, tol=3e-3 * scale, tol_density=5e-3 * scale, tol_scalar=1.5e-2 * scale)
     print(name, "detach_N" if detach_N else "live_N", "retrace" if retrace else "env", mlp, {k: f"{v:.1e}" for k, v in report.items()})
     assert not bad, bad
 
@@ -150,7 +151,7 @@ def test_microfacet_train_step_accumulates_and_is_linear(env):
     acc = train.MicrofacetGradBuffers(dsc)
     train.train_microfacet(dsc, rays[:h], gt[:h], focal=fix["focal"], seed=3, ray_id0=0, detach_N=False, grads=acc, zero_grads=True)
     train.train_microfacet(dsc, rays[h:], gt[h:], focal=fix["focal"], seed=3, ray_id0=h, detach_N=False, grads=acc, zero_grads=False)
-    for k in ("a_plane0", "d_plane1", "basis_t", "head_w", "w0t", "w1t", "gsat", "gpack2"):
+    for k in ("a_plane0", "a_line2", "d_plane0", "d_line0", "basis_t", "head_w", "w0t", "w1t", "b2", "gsat", "gpack0"):
         ref = ga[k] + gb[k]
         err = float((acc.t[k] - ref).abs().max())
         assert err <= 2e-4 * float(ref.abs().max()) + 1e-9, (k, err, float(ref.abs().max()))

@@ -37,26 +37,29 @@ def test_update_alpha_mask_respects_the_existing_mask(model):
     from oracle import nmf_oracle as O
     from conftest import oracle_scene as mk
     fix, osc, t = model
+    t.sampler.alphaMask = None
     t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
     first = t.sampler.alphaMask.alpha_volume.reshape(-1).cpu().clone()
     state = {k: v.clone() for k, v in fix["state"].items()}
     for p in range(3):                                   # raise the density feature everywhere
         state[f"rf.density_rf.app_plane.{p}"] = state[f"rf.density_rf.app_plane.{p}"].abs() + 0.5
         state[f"rf.density_rf.app_line.{p}"] = state[f"rf.density_rf.app_line.{p}"].abs() + 0.5
-    with torch.no_grad():
-        t.load_state_dict(state, strict=False)
-    t.invalidate()
-    t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
-    second = t.sampler.alphaMask.alpha_volume.reshape(-1).cpu()
+    try:
+        with torch.no_grad():
+            t.load_state_dict(state, strict=False)
+        t.invalidate()
+        t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
+        second = t.sampler.alphaMask.alpha_volume.reshape(-1).cpu()
+    finally:
+        with torch.no_grad():
+            t.load_state_dict(fix["state"], strict=False)
+        t.invalidate()
+        t.sampler.alphaMask = None
     osc2 = mk(dict(fix, state=state))
     ref = O.build_alpha_volume(osc2, use_existing_mask=True).reshape(-1)
     full = O.build_alpha_volume(osc2, use_existing_mask=False).reshape(-1)
     assert torch.equal(second, ref), int((second != ref).sum())
     assert int(full.sum()) > int(ref.sum()) and int(second.sum()) < second.numel()       # the mask mattered
-    with torch.no_grad():
-        t.load_state_dict(fix["state"], strict=False)
-    t.invalidate()
-    t.sampler.alphaMask = None
     t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
     assert torch.equal(t.sampler.alphaMask.alpha_volume.reshape(-1).cpu(), first)
 

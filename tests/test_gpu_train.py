@@ -351,7 +351,8 @@ def test_microfacet_train_forward_plugin(env):
                                    lambda_pred=3e-4, lambda_ori=0.1)
     assert np.isfinite(loss) and loss > 0 and ims2["rgb_map"].shape[0] == int(st2["whole_valid"].sum())
     missing = [k for k, p in t.named_parameters() if (p.grad is None or float(p.grad.abs().max()) == 0.0)
-               and "tint_mlp" not in k and "dbasis" not in k]
+               and "tint_mlp" not in k and "dbasis" not in k
+               and not (("density_rf" in k) and k[-1] in "12")]      # this fixture's density lives in plane / line 0 only
     assert not missing, missing
 
 
