@@ -3,10 +3,13 @@
 800x800 image = 640 000 rays in 4096-ray chunks) on N B200s.   python bench.py --gpus N --steps K --warmup W
 
 A "step" is one full pass of the hot path over one synthetic 800x800 image (157 chunks).  `value` is timed with
-the rays resident in HBM; `e2e` goes through the reference-facing API (nmf_b200.renderer.chunk_renderer ->
-nmf_render_rays_host) with pinned HOST rays in and every output map copied back to the host inside the timed
-region.  `--impl reference` times the reference algorithm on the host cores (the oracle port of the reference's
-PyTorch path; the reference itself is not installable on the GPU box) on a bounded sample of the same workload.
+the rays resident in HBM; `e2e` goes through the C-ABI host-buffer call (renderer.HostRenderer -> nmf_render_rays_host)
+with pinned HOST rays in and every output map copied back to the host inside the timed region; `e2e_plugin` is the same
+through the plugin stack a reference user calls (config.build_model -> TensorNeRF -> renderer.chunk_renderer(
+render2completion=True)).  `--impl reference` times the reference algorithm on the host cores (the oracle port of the
+reference's PyTorch path, GPU-free: no CUDA library is mapped) on a bounded sample of the same workload;
+`--impl reference-cuda` times the UNMODIFIED reference (baseline/_ref, staged by __graft_entry__.build()) through its own
+PyTorch-CUDA path on the same B200 -- the renderer the >= 10x target of BASELINE.json is defined against.
 """
 import argparse
 import json
@@ -33,7 +36,10 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
+    ap.add_argument("--ref-chunks", type=int, default=12, help="chunks of the image the reference-cuda leg renders")
+    ap.add_argument("--no-refcuda", action="store_true", help="skip the reference_cuda leg of the b200 arm")
+    ap.add_argument("--sustain-s", type=float, default=5.0, help="seconds of back-to-back steps for the `sustained` key (0 = skip)")
     ap.add_argument("--grid", type=int, default=300)
     ap.add_argument("--res", type=int, default=800)
     ap.add_argument("--chunk", type=int, default=4096)
@@ -146,7 +152,7 @@ def run_reference(a):
     if rank != 0:
         return
     state, meta, rays, focal = workload(a, 0)
-    alpha = reference_alpha_volume(state, meta)
+    alpha = reference_alpha_volume(state, meta, a)
     from oracle import keyed_rng, nmf_oracle
     torch.set_num_threads(os.cpu_count())
     sc = nmf_oracle.Scene(state, meta["aabb"], meta["near_far"], meta["grid_size"], alpha_volume=alpha)
@@ -172,19 +178,82 @@ def run_reference(a):
     emit(line)
 
 
-def reference_alpha_volume(state, meta):
-    """Occupancy volume for the CPU arm.  With a GPU present it is built by the CUDA path (parity-tested against the
-    oracle's rebuild); without one the oracle rebuilds it itself (slow at G=300)."""
-    if torch.cuda.is_available():
-        from nmf_b200.scene import DeviceScene
-        sc = DeviceScene(state, meta["aabb"], meta["near_far"], meta["grid_size"], device="cuda:0")
-        vol = sc.update_alpha_mask().cpu()
-        del sc
-        torch.cuda.empty_cache()
-        return vol
+def reference_alpha_volume(state, meta, a=None):
+    """Occupancy volume for the CPU arm, GPU-free: the copy the ORACLE computed at build time
+    (oracle/_cache, __graft_entry__.stage_reference) or, failing that, the oracle's own rebuild here (~20 s at G=300)."""
+    import numpy as np
+    cache = os.path.join(ROOT, "oracle", "_cache", f"alpha_{a.scene if a else 'lego'}_g{a.grid if a else 300}.pt")
+    if os.path.exists(cache):
+        d = torch.load(cache, weights_only=False)
+        n = int(np.prod(d["shape"]))
+        return torch.from_numpy(np.unpackbits(d["bits"].numpy())[:n].reshape(d["shape"])).float()
     from oracle import nmf_oracle
     sc = nmf_oracle.Scene(state, meta["aabb"], meta["near_far"], meta["grid_size"])
     return nmf_oracle.build_alpha_volume(sc)
+
+
+def reference_cuda(a, state, meta, rays, focal, n_chunks):
+    """The UNMODIFIED reference (TensorNeRF + its plugins, imported from baseline/_ref or /root/reference through
+    oracle/ref_harness.py's stub modules) on the GPU through its own PyTorch-CUDA path: the loop of renderer.chunk_renderer
+    (renderer.py:72-104: one forward per 4096-ray chunk, every output copied to the host), CUDA-event timed per chunk.
+    Returns a dict or {"unavailable": why}."""
+    root = None
+    for c in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(c, "modules")):
+            root = c
+            break
+    if root is None:
+        return {"unavailable": "reference tree not staged (baseline/_ref is written by __graft_entry__.build() where /root/reference exists)"}
+    if not torch.cuda.is_available():
+        return {"unavailable": "no CUDA device"}
+    os.environ["NMF_REFERENCE_ROOT"] = root
+    try:
+        from oracle import ref_harness
+        ref_harness.REFERENCE_ROOT = root
+        dev = torch.device("cuda", torch.cuda.current_device())
+        gs = [int(g) for g in meta["grid_size"]]
+        t = ref_harness.build_reference_model(meta["aabb"], list(meta["near_far"]), grid_size=gs, bg_resolution=meta["bg_resolution"])
+        t.load_state_dict({k: v for k, v in state.items()}, strict=False)
+        t = t.to(dev)
+        t.sampler.update(t.rf, init=True)
+        t.sampler.updateAlphaMask(t.rf, t.rf.grid_size)
+        t.eval()
+        torch.manual_seed(20211200)
+        times = []
+        with torch.no_grad():
+            for c in range(n_chunks + 2):
+                r = rays[(c % 64) * a.chunk:(c % 64 + 1) * a.chunk].to(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ims, stats = t(r, focal, is_train=False, ndc_ray=False, N_samples=-1)
+                host = {k: v.cpu() for k, v in ims.items() if torch.is_tensor(v)}        # renderer.py:88-97
+                e1.record()
+                torch.cuda.synchronize(dev)
+                if c >= 2:
+                    times.append(e0.elapsed_time(e1))
+        times.sort()
+        med = times[len(times) // 2]
+        return {"value": a.chunk / (med * 1e-3), "unit": UNIT, "ms_per_chunk_median": med, "ms_per_chunk_mean": sum(times) / len(times),
+                "chunks": n_chunks, "n_samples_last": [int(x) for x in stats["n_samples"]], "root": os.path.relpath(root, ROOT) if root.startswith(ROOT) else root,
+                "what": "unmodified reference TensorNeRF.forward per 4096-ray chunk on cuda + D2H of every output (its chunk_renderer loop), "
+                        "CUDA events, median over chunks after 2 warm-up chunks"}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
+def run_reference_cuda(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    state, meta, rays, focal = workload(a, 0)
+    r = reference_cuda(a, state, meta, rays, focal, max(a.steps, 1) * 4)
+    if "unavailable" in r:
+        emit({"impl": "reference-cuda", "unavailable": r["unavailable"]})
+        return
+    emit({"impl": "reference-cuda", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+          "ms_per_step": r["ms_per_chunk_median"] * math.ceil(rays.shape[0] / a.chunk), "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(a, rays.shape[0]), "reference_cuda": r,
+          "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": a.chunk * 24, "d2h_bytes_per_step": None}, "gpu_launches": 0})
 
 
 def config_dict(a, n_rays):
@@ -222,6 +291,8 @@ def main():
     _claim_stdout()
     if a.impl == "reference":
         return run_reference(a)
+    if a.impl == "reference-cuda":
+        return run_reference_cuda(a)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -287,10 +358,34 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
 
-    times = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    # ---- e2e_plugin: the same image through the plugin stack a reference user calls (config.build_model ->
+    # TensorNeRF -> renderer.chunk_renderer(render2completion=True): H2D of the rays, one launch sequence, D2H of every map)
+    plug_ms, plug_err = None, None
+    try:
+        plug_ms = plugin_e2e(a, state, meta, alpha, rays_pinned, focal, dev, barrier)
+    except Exception as e:                          # the extra leg never takes the bench line down
+        plug_err = f"{type(e).__name__}: {e}"[:200]
+
+    # ---- sustained: back-to-back device-resident steps for >= --sustain-s seconds (clocks sag under seconds-long load) ----
+    sus = None
+    if a.sustain_s > 0:
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_sus = max(a.steps, int(math.ceil(a.sustain_s * 1e3 / max(ms / a.steps, 1e-3))))
+        with ClockSampler(local) as clk2:
+            s0.record()
+            for _ in range(n_sus):
+                step()
+            s1.record()
+            barrier()
+        sus = (s0.elapsed_time(s1), n_sus, clk2.summary())
+
+    times = torch.tensor([ms, e2e_ms, plug_ms or 0.0, sus[0] if sus else 0.0], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(times[0]), float(times[1])
+    plug_ms = float(times[2]) if plug_ms else None
+    extra_n = multi_gpu_extras(a, dist, rank, world, dev, state, meta, alpha, focal, barrier) if dist is not None else None
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -319,40 +414,61 @@ def main():
     dom = max(("march0", "shade0"), key=lambda k: kernels[k]["ms"])
     traffic, capture = ncu_traffic(f"k_{dom[:-1]}<0>")
     n_bray = sum(stats["n_bounce_rays0"]) + sum(stats["n_bounce_rays1"])
-    mlp_ms = phase_acc["bounce0"] + phase_acc["bounce1"]
+    mlp_ms = phase_acc["bounce0"] + phase_acc["bounce1"]          # k_tile_prefix + k_bounce<L> only (k_incoming<1> has its own phase)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1600.0)))
-    roof = {"bound": "hbm", "kernel": f"k_{dom[:-1]}<0>", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "traffic_capture": capture, "peak_source": peak_src,
-            "note": "achieved = algorithmic bytes of SURVEY 8d (reference layouts, no reuse, every valid sample) / measured "
-                    "launch time; the factor planes are L2-resident (traffic << algorithmic bytes) and samples below the "
-                    "weight cut are not shaded, so frac > 1 is cache reuse + pruning, not an HBM rate",
+    # the gather kernels' factor set is L2-resident: their ceiling is the rate of independent 16-byte taps the L2 serves,
+    # measured here (nmf_bench_gather over a 78 MB set = the factor set of G=300), not the HBM copy rate
+    l2_peak = ops.gather_peak(78 << 20)
+    dram_gather = ops.gather_peak(8 << 30, taps=32)
+    touched = kernels[dom]["touched"] or kernels[dom]["bytes"]
+    t_dom = kernels[dom]["ms"] * 1e-3
+    roof = {"bound": "l2", "kernel": f"k_{dom[:-1]}<0>", "achieved": touched / t_dom / 1e9, "peak": l2_peak, "unit": "GB/s",
+            "frac": touched / t_dom / 1e9 / l2_peak,
+            "peak_source": "measured in this run: nmf_bench_gather, independent random 16-byte loads over a 78 MB (L2-resident) set",
+            "achieved_note": "bytes of the taps the kernel actually issues (16-byte factor taps of the samples it shades) / "
+                             "CUDA-event launch time",
+            "traffic": traffic, "traffic_capture": capture,
+            "dram": {"achieved": (traffic / t_dom / 1e9) if traffic else None, "peak": peak, "frac": (traffic / t_dom / 1e9 / peak) if traffic else None,
+                     "peak_source": peak_src, "random_16B_gather_GBps": dram_gather,
+                     "note": "real DRAM bytes per launch (ncu) / launch time: the factor planes stay in L2"},
+            "hbm_reference_equivalent": {"achieved": kernels[dom]["gbs"], "peak": peak, "frac": kernels[dom]["gbs"] / peak,
+                                         "note": "SURVEY 8d algorithmic bytes (reference layouts, no reuse, EVERY valid sample) / launch "
+                                                 "time; > 1 = L2 reuse + samples below the weight cut are not shaded -- not an HBM rate"},
             "mlp": {"bound": "tensor", "kernel": "k_bounce<0>+k_bounce<1>", "flop_per_ray": 17152, "rays": n_bray,
                     "achieved": 17152.0 * n_bray / max(mlp_ms, 1e-9) / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": 17152.0 * n_bray / max(mlp_ms, 1e-9) / 1e9 / tf_peak, "ms": mlp_ms,
-                    "note": "fp16 tcgen05 GEMMs of the 66-64-64-4 BRDF MLP; the kernels also sample GGX, encode and look up the environment"},
-            "launch_ms": kernels[dom]["ms"], "algorithmic_bytes_per_launch": kernels[dom]["bytes"],
+                    "frac": 17152.0 * n_bray / max(mlp_ms, 1e-9) / 1e9 / tf_peak, "ms": mlp_ms, "operands": "fp16, fp32 accumulate (tcgen05)",
+                    "note": "tcgen05 GEMMs of the 66-64-64-4 BRDF MLP; the kernels also draw the GGX samples and encode them"},
+            "launch_ms": kernels[dom]["ms"], "algorithmic_bytes_per_launch": kernels[dom]["bytes"], "touched_bytes_per_launch": touched,
             "march_plus_query": {"ms": fused_ms, "algorithmic_bytes": (B_CAND * cand + (B_DENSITY + B_APP + B_NORMAL) * (M0 + M1)),
                                  "achieved": (B_CAND * cand + (B_DENSITY + B_APP + B_NORMAL) * (M0 + M1)) / max(fused_ms, 1e-9) / 1e6,
-                                 "frac": (B_CAND * cand + (B_DENSITY + B_APP + B_NORMAL) * (M0 + M1)) / max(fused_ms, 1e-9) / 1e6 / peak},
+                                 "frac_of_hbm_copy": (B_CAND * cand + (B_DENSITY + B_APP + B_NORMAL) * (M0 + M1)) / max(fused_ms, 1e-9) / 1e6 / peak},
             "whole_step": {"algorithmic_bytes": fused_bytes, "achieved": fused_bytes / (ms / a.steps) / 1e6,
-                           "frac": fused_bytes / (ms / a.steps) / 1e6 / peak},
+                           "frac_of_hbm_copy": fused_bytes / (ms / a.steps) / 1e6 / peak},
             "per_kernel": {k: {"ms": round(d["ms"], 4), "GBps_algorithmic": round(d["gbs"], 1),
-                               "GBps_touched": (round(d["touched"] / (d["ms"] * 1e-3) / 1e9, 1) if d["touched"] and d["ms"] > 0 else None)}
+                               "GBps_touched": (round(d["touched"] / (d["ms"] * 1e-3) / 1e9, 1) if d["touched"] and d["ms"] > 0 else None),
+                               "frac_of_l2_gather": (round(d["touched"] / (d["ms"] * 1e-3) / 1e9 / l2_peak, 3) if d["touched"] and d["ms"] > 0 else None)}
                            for k, d in kernels.items()},
             "phase_ms": {k: round(v, 4) for k, v in phase_acc.items()},
             "phase_note": "CUDA-event phase times averaged over the e2e (host-buffer) steps: same kernels as the device-resident "
                           "steps; 'finish' there also holds the last staged device-to-host copies (k_finish0 itself: ~40 us)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(a, n), "clocks": clk.summary(),
+            "dtype": "f32", "dtype_note": "fp32 everywhere except the operands of the BRDF-MLP GEMMs (fp16, fp32 accumulate in TMEM)",
+            "data": "synthetic", "config": config_dict(a, n), "clocks": clk.summary(),
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
-                    "ms_per_step": e2e_ms / a.steps},
-            "gpu_launches": 15 * a.steps, "roofline": roof,
+                    "ms_per_step": e2e_ms / a.steps, "api": "renderer.HostRenderer.render -> nmf_render_rays_host (C ABI, host buffers)"},
+            "e2e_plugin": ({"value": world * n * a.steps / (plug_ms / 1e3), "unit": UNIT, "ms_per_step": plug_ms / a.steps,
+                            "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": host.d2h_bytes,
+                            "api": "config.build_model -> TensorNeRF -> renderer.chunk_renderer(render2completion=True)"}
+                           if plug_ms else {"error": plug_err}),
+            "sustained": ({"value": world * n * sus[1] / (float(times[3]) / 1e3), "unit": UNIT, "seconds": float(times[3]) / 1e3, "steps": sus[1],
+                           "clocks": sus[2]} if sus else None),
+            "gpu_launches": 16 * a.steps, "roofline": roof,
             "samples": {"valid_primary": M0, "valid_secondary": M1, "candidates": cand, "shaded_primary": sh0,
                         "shaded_secondary": sh1, "bounce_rays0": sum(stats["n_bounce_rays0"]),
                         "bounce_rays1": sum(stats["n_bounce_rays1"]), "retraced": n1}}
@@ -371,13 +487,90 @@ def main():
         try:
             from nmf_b200 import train
             dev_s = f"cuda:{torch.cuda.current_device()}"
-            line["train_step"] = train.benchmark_plain(a.grid, 4096, steps=10, iters=8, device=dev_s)
-            line["train_forward_microfacet"] = train.benchmark_microfacet_forward(a.grid, 4096, steps=10, device=dev_s)
+            line["train_step"] = train.benchmark_microfacet_train(a.grid, 4096, steps=10, device=dev_s)
+            line["train_step_plain"] = train.benchmark_plain(a.grid, 4096, steps=10, iters=8, device=dev_s)
         except Exception as e:                      # never lets the extra entry take the bench line down
             line["train_step"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    if extra_n is not None:
+        line.update(extra_n)
+    if not a.no_refcuda and world == 1:
+        line["reference_cuda"] = reference_cuda(a, state, meta, rays_host, focal, a.ref_chunks)
+        if "value" in line["reference_cuda"]:
+            line["reference_cuda"]["ratio_e2e"] = e2e_v / line["reference_cuda"]["value"]
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def plugin_e2e(a, state, meta, alpha, rays_pinned, focal, dev, barrier):
+    """ms for a.steps images through the reference-facing plugin stack (host rays in, host maps out)."""
+    from nmf_b200 import config, renderer
+    gs = meta["grid_size"]
+    t, _ = config.build_model([f"field.grid_size=[{gs[0]},{gs[1]},{gs[2]}]", f"model.arch.bg_module.bg_resolution={meta['bg_resolution']}"],
+                              aabb=meta["aabb"], near_far=list(meta["near_far"]))
+    t.load_state_dict(state, strict=False)
+    t = t.to(dev).eval()
+    t.sampler.update(t.rf, init=True)
+    from nmf_b200.plugins import AlphaGridMask
+    t.sampler.alphaMask = AlphaGridMask(t.rf.aabb, alpha.to(dev))
+    run = lambda: renderer.chunk_renderer(rays_pinned.to(dev, non_blocking=True), t, focal, keys=None, chunk=a.chunk, render2completion=True)
+    for _ in range(2):
+        run()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        run()
+    torch.cuda.synchronize()
+    return 1e3 * (time.perf_counter() - t0)
+
+
+def multi_gpu_extras(a, dist, rank, world, dev, state, meta, alpha, focal, barrier):
+    """N > 1 only -- measurements that can fail:
+      strong_scaling  ONE 800x800 image sharded over the ranks by distributed.shard_chunks (whole chunks, global ray ids),
+                      gathered on rank 0 with NCCL, timed end to end (max over ranks)
+      train_sharded   a ray-sharded nmf_train_microfacet step per rank + ONE flat fp32 gradient all-reduce (NCCL) + FusedAdam,
+                      with the all-reduce time and its bus bandwidth broken out"""
+    from nmf_b200 import distributed, ops, synthetic, train
+    from nmf_b200.scene import DeviceScene
+    out = {}
+    try:
+        scene = DeviceScene(state, meta["aabb"], meta["near_far"], meta["grid_size"], alpha_volume=alpha, device=dev)
+        poses = synthetic.hemisphere_poses(200, seed=1)
+        rays_all = synthetic.camera_rays(poses[0], a.res, a.res, focal)
+        perm = torch.randperm(rays_all.shape[0], generator=torch.Generator().manual_seed(20211200))
+        rays_all = rays_all[perm].contiguous().to(dev)
+        n = rays_all.shape[0]
+        lo, hi = distributed.shard_chunks(n, a.chunk, rank, world)
+        mine = rays_all[lo:hi].contiguous()
+        bufs = ops.RenderBuffers(scene, max(hi - lo, 1), a.chunk, ["rgb_map", "acc_map", "depth"])
+        counts = [distributed.shard_chunks(n, a.chunk, r, world) for r in range(world)]
+        gather = [torch.empty(c[1] - c[0], 3, device=dev) for c in counts] if rank == 0 else None
+
+        def one():
+            ims, _ = ops.render_rays(scene, mine, focal, chunk=a.chunk, seed=20211200, ray_id0=lo, buffers=bufs, check_errors=False)
+            dist.gather(ims["rgb_map"].contiguous(), gather, dst=0)
+        for _ in range(2):
+            one()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            one()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["strong_scaling"] = {"value": n * a.steps / (float(t[0]) / 1e3), "unit": UNIT, "ms_per_image": float(t[0]) / a.steps,
+                                 "what": "one 800x800 image sharded by whole chunks over the ranks, rgb gathered on rank 0 (NCCL), max over ranks"}
+        del bufs
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["strong_scaling"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    try:
+        out["train_sharded"] = train.benchmark_sharded_train(a.grid, 4096, steps=10, device=dev)
+    except Exception as e:
+        out["train_sharded"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return out
 
 
 if __name__ == "__main__":

@@ -187,9 +187,9 @@ int nmf_abi_version(void);
 
 /* Optional phase timing for bench.py / profiling: when enabled, nmf_render_rays records a CUDA event on the caller's
  * stream after each phase; nmf_profile_read (after the stream is synchronised) returns the elapsed milliseconds of
- * the NMF_N_PHASES phases of the LAST call: march0, shade0, bounce0, select, march1, shade1, bounce1, finish1,
+ * the NMF_N_PHASES phases of the LAST call: march0, shade0, bounce0, select, march1, shade1, bounce1, incoming1, finish1,
  * incoming0, reduce0, finish. */
-#define NMF_N_PHASES 11
+#define NMF_N_PHASES 12
 int nmf_profile_enable(int on);
 int nmf_profile_read(float* ms, int n);
 const char* nmf_profile_phase_name(int i);
@@ -452,6 +452,12 @@ int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp, const NmfRe
  * F.interpolate(mode="bilinear", align_corners=True) of every factor.  src (C,H,W) -> dst (C,H2,W2), both in the
  * reference's own parameter layout (a line (1,C,N,1) is H = N, W = 1). */
 int nmf_upsample_bilinear(const float* src, int C, int H, int W, float* dst, int H2, int W2, void* stream);
+
+/* Measurement helper (bench.py): `n_threads` threads (a multiple of 256) each issue `taps` (a multiple of 8) independent
+ * pseudo-random 16-byte loads over `buf` (n_elems float4) and write one float4 of `sink` (n_threads float4).  Timed by the
+ * caller; bytes = n_threads * taps * 16.  With an L2-resident buffer this is the gather ceiling k_march / k_shade are
+ * reported against (their factor set is L2-resident: the HBM copy rate is not their roofline). */
+int nmf_bench_gather(const void* buf, size_t n_elems, int taps, int n_threads, void* sink, void* stream);
 
 #ifdef __cplusplus
 }

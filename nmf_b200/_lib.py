@@ -118,7 +118,7 @@ class NmfOverflow(NmfError):
 _ERRORS = {-1: "NMF_E_ARG (null pointer or non-positive size)",
            -2: "NMF_E_UNSUPPORTED (shape outside what the kernels are compiled for)",
            -3: "NMF_E_WORKSPACE (workspace too small)"}
-N_PHASES = 11
+N_PHASES = 12
 DEV_ERRORS = {1: "surviving-sample list overflowed", 2: "bounce-sample list overflowed",
               4: "a chunk's bounce-ray region overflowed", 8: "the valid-sample list of the reverse pass overflowed"}
 
@@ -182,6 +182,7 @@ def lib():
         "nmf_render_rays_train": (I, [SP, RP, C.POINTER(NmfRenderTrain), P, IP, CP, P, C.c_size_t, P]),
         "nmf_train_microfacet": (I, [SP, RP, C.POINTER(NmfRenderTrain), C.POINTER(NmfMicrofacetTrain), P, P,
                                      C.POINTER(NmfMicrofacetGrads), IP, CP, P, C.c_size_t, P]),
+        "nmf_bench_gather": (I, [P, C.c_size_t, I, I, P, P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
                                 C.c_size_t, P]),
     }
@@ -200,4 +201,4 @@ EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_pr
             "nmf_sample_rays_train", "nmf_train_workspace_bytes", "nmf_train_plain", "nmf_upsample_bilinear",
             "nmf_render_train_workspace_bytes", "nmf_render_rays_train", "nmf_l1_reg", "nmf_grad_sq_norm", "nmf_adam_step",
             "nmf_env_lookup_bwd_scatter", "nmf_env_lookup_bwd_finish", "nmf_env_lookup_bwd_mipbias", "nmf_vm_normals_bwd_scatter",
-            "nmf_vm_normals_bwd_finish", "nmf_material_heads_bwd", "nmf_train_microfacet"]
+            "nmf_vm_normals_bwd_finish", "nmf_material_heads_bwd", "nmf_train_microfacet", "nmf_bench_gather"]

@@ -1257,7 +1257,7 @@ static int check_scene(const NmfScene* s) {
 
 // ---- optional phase timing: CUDA events recorded on the caller's stream between the phases ----
 static const char* g_phase_names[NMF_N_PHASES] = {"march0", "shade0", "bounce0", "select", "march1", "shade1", "bounce1",
-                                                   "finish1", "incoming0", "reduce0", "finish"};
+                                                   "incoming1", "finish1", "incoming0", "reduce0", "finish"};
 static cudaEvent_t g_ev[NMF_N_PHASES + 1];
 static bool g_ev_made = false, g_prof_on = false, g_ev_rec[NMF_N_PHASES + 1];
 static void prof_mark(int i, cudaStream_t st) {
@@ -1474,23 +1474,24 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
       if (tcm) k_bounce<1, 1><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b1);
       else k_bounce<1, 0><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b1);
       CKL();
+      prof_mark(7, stream);
       IncomingArgs i1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr, 0, w.accum1, w.tile_start1, nc, nullptr};
       k_incoming<1><<<g_inc1, MLP_THREADS, 0, stream>>>(s, i1);
       CKL();
-      prof_mark(7, stream);
+      prof_mark(8, stream);
       k_finish1<<<(w.n_rays1 + 127) / 128, 128, 0, stream>>>(s, w.rays1, w.mip1, w.acc1, w.accum1, w.n_sec, s.max_retrace,
                                                            w.n_rays1, w.rgb1);
       CKL();
-      prof_mark(8, stream);
+      prof_mark(9, stream);
     }
     IncomingArgs ia = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.rgb1, s.max_retrace, w.accum0, w.tile_start0, nc, w.red0};
     k_incoming<0><<<g_inc0, MLP_THREADS, 0, stream>>>(s, ia);
     CKL();
-    prof_mark(9, stream);
+    prof_mark(10, stream);
     ReduceArgs r0 = {w.red0, w.n_bs, w.cap_bs0, w.accum0};
     k_reduce0<<<sm_count() * 4, 256, 0, stream>>>(r0);
     CKL();
-    prof_mark(10, stream);
+    prof_mark(11, stream);
   } else {
     const size_t smem = (135 + 128) * 128 * sizeof(float);
     static bool attr_done2 = false;
@@ -1518,7 +1519,7 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
     k_export_counters<<<(nc + 127) / 128 > 0 ? (nc + 127) / 128 : 1, 128, 0, stream>>>(w, *counters, s.model);
     CKL();
   }
-  prof_mark(11, stream);
+  prof_mark(12, stream);
   return NMF_OK;
 }
 

@@ -417,3 +417,25 @@ def profile_read():
     arr = (C.c_float * _lib.N_PHASES)()
     _lib.check(L.nmf_profile_read(arr, _lib.N_PHASES), "nmf_profile_read")
     return {L.nmf_profile_phase_name(i).decode(): float(arr[i]) for i in range(_lib.N_PHASES)}
+
+
+def gather_peak(set_bytes=78 << 20, taps=64, threads=148 * 2048, reps=5):
+    """Measured ceiling of independent 16-byte random gathers over a resident set of `set_bytes` (nmf_bench_gather, CUDA
+    events, best of `reps`): GB/s = threads * taps * 16 / time.  78 MB = the factor set of G = 300 (L2-resident)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = set_bytes // 16
+    buf = torch.rand(n, 4, device=dev)
+    threads = (threads + 255) // 256 * 256
+    sink = torch.empty(threads, 4, device=dev)
+    L = _lib.lib()
+    best = None
+    for i in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(L.nmf_bench_gather(_p(buf), n, taps, threads, _p(sink), _stream()), "nmf_bench_gather")
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if i >= 2 and (best is None or ms < best):
+            best = ms
+    return threads * taps * 16 / (best * 1e-3) / 1e9

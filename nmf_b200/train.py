@@ -964,3 +964,65 @@ def benchmark_microfacet_train(grid=300, n_rays=4096, steps=20, device="cuda:0",
                 n_retrace=c["n_retrace"][0], n_bounce_rays=[c["n_bounce_rays0"][0], c["n_bounce_rays1"][0]], detach_N=bool(detach_N),
                 mlp=mlp, ms_per_step=ms, kept_rays_per_s=out["n_rays"] / ms * 1e3,
                 forward_only_ms=None if fwd is None else fwd["ms_per_step"])
+
+
+def benchmark_sharded_train(grid=300, n_rays=4096, steps=10, device="cuda:0", scene_name="ship"):
+    """BASELINE config #4 (ship 800x800, ray-batch sharded, NCCL gradient all-reduce): every rank runs one
+    MicrofacetTrainer iteration on ITS OWN 4096 rays (weak scaling of the batch: the global batch is world x 4096) --
+    nmf_train_microfacet, finish, ONE flat fp32 all-reduce, FusedAdam, re-pack -- and the phases are timed with CUDA
+    events (max over ranks).  Needs torch.distributed initialised (NCCL); world = 1 works too (no collective)."""
+    import torch.distributed as dist
+    from . import ops, synthetic
+    dev = torch.device(device)
+    on = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+    state, meta = synthetic.make_scene(scene_name, grid_size=grid)
+    tr = MicrofacetTrainer(state, meta["aabb"], meta["near_far"], meta["grid_size"], device=dev, max_samples=200000, seed=7,
+                           params=dict(MICROFACET_REFERENCE_PARAMS))
+    tr.alpha_volume = tr.scene.update_alpha_mask()
+    H = W = 800
+    focal = synthetic.focal_for(W)
+    pose = synthetic.hemisphere_poses(8)[1 + rank % 6]
+    pix = torch.randperm(H * W, generator=torch.Generator().manual_seed(rank))[:n_rays]
+    rays = synthetic.camera_rays(pose, H, W, focal)[pix].contiguous().to(dev)
+    gt = ops.render_rays(tr.scene, rays, focal, chunk=n_rays, skip_eps=0.0, t_cut=0.0)[0]["rgb_map"].clone()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    acc = dict(step=0.0, allreduce=0.0, update=0.0, total=0.0)
+    kept = 0
+    for it in range(steps + 3):
+        e = [ev() for _ in range(5)]
+        if on:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e[0].record()
+        out = tr.accumulate(rays, gt, first=True)
+        p = tr.params
+        tr.grads.finish(p["bg_module.bg_mat"].data, p["bg_module.brightness"].data, p["bg_module.mul"].data)
+        views = tr.grads.reference_views()
+        for k, q in p.items():
+            q.grad.copy_(views[k].reshape(q.shape))
+        e[1].record()
+        tr.bucket.allreduce(scale=1.0)
+        e[2].record()
+        tr.optimizer.step(grad_scale=1.0 / (world * n_rays))
+        tr.repack(rebuild=False)
+        e[3].record()
+        torch.cuda.synchronize(dev)
+        if it >= 3:
+            acc["step"] += e[0].elapsed_time(e[1]); acc["allreduce"] += e[1].elapsed_time(e[2])
+            acc["update"] += e[2].elapsed_time(e[3]); acc["total"] += e[0].elapsed_time(e[3])
+            kept += out["n_rays"]
+    t = torch.tensor([acc[k] / steps for k in ("step", "allreduce", "update", "total")] + [float(kept) / steps], device=dev, dtype=torch.float64)
+    if on and world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm[:4], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[4:], op=dist.ReduceOp.SUM)
+        t[:4] = tm[:4]
+    nbytes = tr.bucket.flat.numel() * 4
+    ar_ms = float(t[1])
+    return dict(what="ray-sharded training iteration of microfacet_tensorf2 (config #4 shape): nmf_train_microfacet per rank + one "
+                     "flat fp32 all-reduce + FusedAdam + re-pack; CUDA events, max over ranks",
+                world=world, grid=grid, rays_per_rank=n_rays, kept_rays_global=float(t[4]), ms_fwd_bwd=float(t[0]), ms_allreduce=ar_ms,
+                ms_update_repack=float(t[2]), ms_total=float(t[3]), allreduce_bytes=nbytes,
+                allreduce_busbw_GBps=(2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
+                allreduce_share=ar_ms / max(float(t[3]), 1e-9), kept_rays_per_s=float(t[4]) / (float(t[3]) * 1e-3))
