@@ -423,18 +423,21 @@ def main():
     tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1600.0)))
     # the gather kernels' factor set is L2-resident: their ceiling is the rate of independent 16-byte taps the L2 serves,
     # measured here (nmf_bench_gather over a 78 MB set = the factor set of G=300), not the HBM copy rate
-    l2_peak = ops.gather_peak(78 << 20)
-    dram_gather = ops.gather_peak(8 << 30, taps=32)
+    l2_by_seg = {16 * g: ops.gather_peak(78 << 20, group=g) for g in (1, 4, 8)}
+    l2_peak = l2_by_seg[128]
+    dram_gather = ops.gather_peak(8 << 30, taps=32, group=4)
     touched = kernels[dom]["touched"] or kernels[dom]["bytes"]
     t_dom = kernels[dom]["ms"] * 1e-3
     roof = {"bound": "l2", "kernel": f"k_{dom[:-1]}<0>", "achieved": touched / t_dom / 1e9, "peak": l2_peak, "unit": "GB/s",
             "frac": touched / t_dom / 1e9 / l2_peak,
-            "peak_source": "measured in this run: nmf_bench_gather, independent random 16-byte loads over a 78 MB (L2-resident) set",
+            "peak_source": "measured in this run: nmf_bench_gather, independent random 128-byte segments (8 lanes x 16 B) over a 78 MB "
+                           "(L2-resident) set; l2_gather_GBps_by_segment_bytes has the 16- and 64-byte figures",
+            "l2_gather_GBps_by_segment_bytes": l2_by_seg,
             "achieved_note": "bytes of the taps the kernel actually issues (16-byte factor taps of the samples it shades) / "
                              "CUDA-event launch time",
             "traffic": traffic, "traffic_capture": capture,
             "dram": {"achieved": (traffic / t_dom / 1e9) if traffic else None, "peak": peak, "frac": (traffic / t_dom / 1e9 / peak) if traffic else None,
-                     "peak_source": peak_src, "random_16B_gather_GBps": dram_gather,
+                     "peak_source": peak_src, "random_64B_gather_GBps": dram_gather,
                      "note": "real DRAM bytes per launch (ncu) / launch time: the factor planes stay in L2"},
             "hbm_reference_equivalent": {"achieved": kernels[dom]["gbs"], "peak": peak, "frac": kernels[dom]["gbs"] / peak,
                                          "note": "SURVEY 8d algorithmic bytes (reference layouts, no reuse, EVERY valid sample) / launch "

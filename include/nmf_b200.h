@@ -454,10 +454,12 @@ int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp, const NmfRe
 int nmf_upsample_bilinear(const float* src, int C, int H, int W, float* dst, int H2, int W2, void* stream);
 
 /* Measurement helper (bench.py): `n_threads` threads (a multiple of 256) each issue `taps` (a multiple of 8) independent
- * pseudo-random 16-byte loads over `buf` (n_elems float4) and write one float4 of `sink` (n_threads float4).  Timed by the
- * caller; bytes = n_threads * taps * 16.  With an L2-resident buffer this is the gather ceiling k_march / k_shade are
- * reported against (their factor set is L2-resident: the HBM copy rate is not their roofline). */
-int nmf_bench_gather(const void* buf, size_t n_elems, int taps, int n_threads, void* sink, void* stream);
+ * 16-byte loads over `buf` (n_elems float4) and write one float4 of `sink` (n_threads float4); `group` (1, 2, 4, 8)
+ * consecutive lanes read consecutive pieces of one pseudo-random segment of 16 * group bytes (the granularity of the
+ * kernels' texel taps).  Timed by the caller; bytes = n_threads * taps * 16.  With an L2-resident buffer this is the
+ * gather ceiling k_march / k_shade are reported against (their factor set is L2-resident: the HBM copy rate is not
+ * their roofline). */
+int nmf_bench_gather(const void* buf, size_t n_elems, int taps, int group, int n_threads, void* sink, void* stream);
 
 #ifdef __cplusplus
 }

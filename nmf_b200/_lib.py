@@ -182,7 +182,7 @@ def lib():
         "nmf_render_rays_train": (I, [SP, RP, C.POINTER(NmfRenderTrain), P, IP, CP, P, C.c_size_t, P]),
         "nmf_train_microfacet": (I, [SP, RP, C.POINTER(NmfRenderTrain), C.POINTER(NmfMicrofacetTrain), P, P,
                                      C.POINTER(NmfMicrofacetGrads), IP, CP, P, C.c_size_t, P]),
-        "nmf_bench_gather": (I, [P, C.c_size_t, I, I, P, P]),
+        "nmf_bench_gather": (I, [P, C.c_size_t, I, I, I, P, P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
                                 C.c_size_t, P]),
     }

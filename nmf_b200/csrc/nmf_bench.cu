@@ -10,16 +10,22 @@
 
 #include "../../include/nmf_b200.h"
 
-__global__ void __launch_bounds__(256) k_bench_gather(const float4* __restrict__ buf, unsigned long long n_elems, int taps, float4* sink) {
+// `group` consecutive lanes (1, 2, 4 or 8) read consecutive 16-byte pieces of ONE random segment of 16 * group bytes --
+// the granularity of the kernels' taps: a density texel is 64 bytes (4 lanes), an appearance texel 96, a derivative-packed
+// texel pair 384 (8 lanes x three 128-byte pieces).  group = 1 is the worst case (half of every 32-byte sector is wasted).
+__global__ void __launch_bounds__(256) k_bench_gather(const float4* __restrict__ buf, unsigned long long n_elems, int taps, int group,
+                                                      float4* sink) {
   const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long h = tid * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+  const unsigned long long gid = tid / (unsigned)group, sub = tid % (unsigned)group;
+  const unsigned long long n_seg = n_elems / (unsigned)group;
+  unsigned long long h = gid * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = 0; i < taps; i += 8) {
     float4 v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
-      v[j] = __ldg(buf + (h % n_elems));
+      v[j] = __ldg(buf + (h % n_seg) * (unsigned)group + sub);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
@@ -27,9 +33,10 @@ __global__ void __launch_bounds__(256) k_bench_gather(const float4* __restrict__
   sink[tid] = acc;
 }
 
-extern "C" int nmf_bench_gather(const void* buf, size_t n_elems, int taps, int n_threads, void* sink, void* stream) {
-  if (!buf || !sink || n_elems == 0 || taps <= 0 || (taps & 7) || n_threads <= 0 || (n_threads & 255)) return NMF_E_ARG;
-  k_bench_gather<<<n_threads / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)buf, (unsigned long long)n_elems, taps, (float4*)sink);
+extern "C" int nmf_bench_gather(const void* buf, size_t n_elems, int taps, int group, int n_threads, void* sink, void* stream) {
+  if (!buf || !sink || n_elems < 8 || taps <= 0 || (taps & 7) || n_threads <= 0 || (n_threads & 255)) return NMF_E_ARG;
+  if (group != 1 && group != 2 && group != 4 && group != 8) return NMF_E_ARG;
+  k_bench_gather<<<n_threads / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)buf, (unsigned long long)n_elems, taps, group, (float4*)sink);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? NMF_OK : (int)e;
 }

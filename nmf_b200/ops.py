@@ -419,9 +419,10 @@ def profile_read():
     return {L.nmf_profile_phase_name(i).decode(): float(arr[i]) for i in range(_lib.N_PHASES)}
 
 
-def gather_peak(set_bytes=78 << 20, taps=64, threads=148 * 2048, reps=5):
-    """Measured ceiling of independent 16-byte random gathers over a resident set of `set_bytes` (nmf_bench_gather, CUDA
-    events, best of `reps`): GB/s = threads * taps * 16 / time.  78 MB = the factor set of G = 300 (L2-resident)."""
+def gather_peak(set_bytes=78 << 20, taps=64, threads=148 * 2048, reps=5, group=1):
+    """Measured ceiling of independent random gathers over a resident set of `set_bytes` (nmf_bench_gather, CUDA events,
+    best of `reps`): `group` lanes read one random segment of 16 * group bytes; GB/s = threads * taps * 16 / time.
+    78 MB = the factor set of G = 300 (L2-resident)."""
     dev = torch.device("cuda", torch.cuda.current_device())
     n = set_bytes // 16
     buf = torch.rand(n, 4, device=dev)
@@ -432,7 +433,7 @@ def gather_peak(set_bytes=78 << 20, taps=64, threads=148 * 2048, reps=5):
     for i in range(reps + 2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(L.nmf_bench_gather(_p(buf), n, taps, threads, _p(sink), _stream()), "nmf_bench_gather")
+        _lib.check(L.nmf_bench_gather(_p(buf), n, taps, int(group), threads, _p(sink), _stream()), "nmf_bench_gather")
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)

@@ -759,7 +759,9 @@ class TensorNeRF(nn.Module):
     @torch.no_grad()
     def render_chunks(self, rays, focal, chunk=4096, ray_id0=0, is_train=False, ndc_ray=False, N_samples=-1, **kw):
         """All chunks of `rays` in one asynchronous launch sequence (the B200-first replacement of the per-chunk host
-        loop of renderer.py:72-104).  Returns (images, statistics) with the keys of TensorNeRF.forward."""
+        loop of renderer.py:72-104).  Returns (images, statistics) with the keys of TensorNeRF.forward.  The images are
+        BORROWED views of this module's persistent output buffers: the next render call overwrites them (forward and
+        renderer.chunk_renderer hand out copies, like the reference's fresh tensors)."""
         if ndc_ray:
             raise NotImplementedError("TensorNeRF: only the non-NDC render path is implemented")
         if is_train:
@@ -869,7 +871,7 @@ class TensorNeRF(nn.Module):
         stats = dict(recur=0, whole_valid=st["whole_valid"].to(rays.device), n_samples=list(st["n_samples"]),
                      n_retrace=st["n_retrace"][0], envmap_reg=self._envmap_reg())
         stats.update(st["statistics"])
-        return ims, stats
+        return {k: v.clone() for k, v in ims.items()}, stats
 
     def _envmap_reg(self):
         """modules/tensor_nerf.py:606-610: (bg_module.mean_color().mean() - 0.05).clip(min=0)"""
@@ -890,6 +892,7 @@ class TensorNeRF(nn.Module):
             return self.forward_train(rays, focal)
         ims, stats = self.render_chunks(rays, focal, chunk=rays.shape[0], ray_id0=self._calls * rays.shape[0],
                                         is_train=is_train, ndc_ray=ndc_ray)
+        ims = {k: v.clone() for k, v in ims.items()}      # fresh tensors, like the reference (render_chunks lends its buffers)
         self._calls += 1
         for k in ("n_samples", "ori_loss", "diffuse_reg", "brdf_reg", "prediction_loss", "distortion_loss", "envmap_reg"):
             stats[k] = stats[k][0]

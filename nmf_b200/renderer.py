@@ -41,7 +41,7 @@ class HostRenderer:
         if n > self.max_rays or rays_host.shape[1] != 6:
             raise _lib.NmfError("ray list larger than the renderer was sized for")
         rp = _lib.NmfRender(n_rays=n, chunk=self.chunk, focal=float(focal), seed=int(seed), ray_id0=int(ray_id0),
-                            skip_eps=float(skip_eps), t_cut=float(t_cut), white_bg=1)
+                            skip_eps=float(skip_eps), t_cut=float(t_cut), white_bg=1, cap_scale=self.bufs.cap_scale)
         st = _lib.lib().nmf_render_rays_host(self.scene.ref(), C.byref(rp), C.c_void_p(rays_host.data_ptr()),
                                              C.c_void_p(self.rays_dev.data_ptr()), C.byref(self.c_host),
                                              C.byref(self.bufs.c_images), C.byref(self.c_host_counters),
@@ -51,7 +51,12 @@ class HostRenderer:
         torch.cuda.current_stream().synchronize()
         err = int(self.host_counters["error"][0])
         if err:
-            raise _lib.NmfError("nmf_render_rays_host: " + "; ".join(m for b, m in _lib.DEV_ERRORS.items() if err & b))
+            # a scratch list was too small for this scene: grow it like ops.render_rays does and render again
+            if self.bufs.cap_scale >= 16:
+                raise _lib.NmfOverflow("nmf_render_rays_host: " + "; ".join(m for b, m in _lib.DEV_ERRORS.items() if err & b))
+            old = self.bufs
+            self.bufs = ops.RenderBuffers(self.scene, self.max_rays, self.chunk, self.keys, cap_scale=old.cap_scale * 2)
+            return self.render(rays_host, focal, seed=seed, ray_id0=ray_id0, skip_eps=skip_eps, t_cut=t_cut)
         nc = (n + self.chunk - 1) // self.chunk
         self.h2d_bytes = n * 24
         self.d2h_bytes = sum(v[:n].numel() * v.element_size() for v in self.host_images.values()) + 4 * (6 * nc + 3)
@@ -62,16 +67,48 @@ class HostRenderer:
         return {k: v[:n] for k, v in self.host_images.items()}, stats
 
 
-def chunk_renderer(rays, tensorf, focal, keys=("rgb_map",), chunk=4096, render2completion=False, **kwargs):
+class _PinnedRing:
+    """Two rotating sets of pinned host buffers for the outputs of chunk_renderer(render2completion=True): the device ->
+    host copies are asynchronous (one stream sync per image instead of one blocking pageable copy per map), and a result
+    stays valid until the call after next.  (The reference returns fresh pageable tensors; pass fresh=True for that.)"""
+
+    def __init__(self):
+        self.sets, self.turn = [{}, {}], 0
+
+    def take(self, key, like, n):
+        cur = self.sets[self.turn]
+        t = cur.get(key)
+        if t is None or t.shape[0] < n or t.shape[1:] != like.shape[1:] or t.dtype != like.dtype:
+            t = torch.empty((n,) + tuple(like.shape[1:]), dtype=like.dtype).pin_memory()
+            cur[key] = t
+        return t[:n]
+
+    def advance(self):
+        self.turn ^= 1
+
+
+def chunk_renderer(rays, tensorf, focal, keys=("rgb_map",), chunk=4096, render2completion=False, fresh=False, **kwargs):
     """renderer.chunk_renderer (renderer.py:56-106): renders `rays` in chunks of `chunk` with `tensorf` and collects
-    `keys` (None = everything) from the image and statistics dicts.  Device rays -> device outputs; with
-    render2completion=True outputs are returned on the host like the reference's eval path (renderer.py:71,88-97).
-    In eval mode whole_valid is all-True (no dynamic truncation), so one pass completes every chunk."""
+    `keys` (None = everything) from the image and statistics dicts.  Device rays -> device outputs (fresh tensors, as in the
+    reference); with render2completion=True outputs are returned on the host like the reference's eval path
+    (renderer.py:71,88-97) -- in pinned buffers that stay valid until the call after next, or fresh pageable tensors with
+    fresh=True.  In eval mode whole_valid is all-True (no dynamic truncation), so one pass completes every chunk."""
     ims, stats = tensorf.render_chunks(rays, focal, chunk=chunk, **kwargs)
     out_i, out_s = {}, {}
-    for k, v in ims.items():
-        if keys is None or k in keys:
-            out_i[k] = v.cpu() if render2completion else v
+    sel = {k: v for k, v in ims.items() if keys is None or k in keys}
+    if render2completion and not fresh:
+        ring = getattr(tensorf, "_host_ring", None)
+        if ring is None:
+            ring = tensorf._host_ring = _PinnedRing()
+        for k, v in sel.items():
+            h = ring.take(k, v, v.shape[0])
+            h.copy_(v, non_blocking=True)
+            out_i[k] = h
+        ring.advance()
+        torch.cuda.current_stream().synchronize()
+    else:
+        for k, v in sel.items():
+            out_i[k] = v.cpu() if render2completion else v.clone()
     for k, v in stats.items():
         if keys is None or k in keys:
             out_s[k] = v

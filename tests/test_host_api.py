@@ -28,14 +28,15 @@ def test_struct_mirror_matches_header_size():
     """ctypes mirror of NmfScene / NmfRender vs the C compiler's layout"""
     import subprocess, tempfile
     from nmf_b200 import _lib
-    src = '#include <stdio.h>\n#include "nmf_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(NmfScene), sizeof(NmfRender), sizeof(NmfImages), sizeof(NmfCounters), sizeof(NmfPlainGrads), sizeof(NmfTrain), sizeof(NmfTrainOut));return 0;}'
+    src = '#include <stdio.h>\n#include "nmf_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(NmfScene), sizeof(NmfRender), sizeof(NmfImages), sizeof(NmfCounters), sizeof(NmfPlainGrads), sizeof(NmfTrain), sizeof(NmfTrainOut), sizeof(NmfMicrofacetGrads), sizeof(NmfMicrofacetTrain), sizeof(NmfRenderTrain), sizeof(NmfNormalGrads));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
     assert sizes == [ctypes.sizeof(_lib.NmfScene), ctypes.sizeof(_lib.NmfRender), ctypes.sizeof(_lib.NmfImages),
                      ctypes.sizeof(_lib.NmfCounters), ctypes.sizeof(_lib.NmfPlainGrads), ctypes.sizeof(_lib.NmfTrain),
-                     ctypes.sizeof(_lib.NmfTrainOut)]
+                     ctypes.sizeof(_lib.NmfTrainOut), ctypes.sizeof(_lib.NmfMicrofacetGrads), ctypes.sizeof(_lib.NmfMicrofacetTrain),
+                     ctypes.sizeof(_lib.NmfRenderTrain), ctypes.sizeof(_lib.NmfNormalGrads)]
 
 
 def test_missing_library_fails_loudly(monkeypatch):
@@ -261,3 +262,89 @@ def test_backward_header_compiles_for_the_device(tmp_path):
                         "-I", os.path.join(ROOT, "nmf_b200", "csrc"), "-I", os.path.join(ROOT, "include"), "-c", src,
                         "-o", str(tmp_path / "probe.o")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_composition_root_schedule_reaches_every_plugin():
+    """TensorNeRF.check_schedule (modules/tensor_nerf.py:177-195): the model's schedule runs through the composition root
+    (min_rough decay, detach_N, std), the sampler's occupancy update and the field's upsampling are OR-ed, a True re-reads the
+    sampler's stepsize / nSamples (sampler.update(rf, init=True)) and bg_noise decays.  CPU: the field's resize kernel is
+    replaced by the reference's own F.interpolate for this test (the CUDA resize is pinned against it in the GPU suite)."""
+    import torch.nn.functional as F
+    from nmf_b200 import config, ops
+    t, _ = config.build_model(["field.grid_size=[16,16,16]", "model.arch.bg_module.bg_resolution=16",
+                               "model.arch.model.min_rough_start=0.5", "model.arch.model.detach_N_iters=3",
+                               "model.arch.sampler.update_list=[]", "model.arch.bg_noise=0.5"])
+    t.sampler.update(t.rf, init=True)
+    step0, n0 = float(t.sampler.stepsize), int(t.sampler.nSamples)
+    first_up = int(t.rf.upsamp_list[0])
+    orig = ops.upsample_bilinear
+    ops.upsample_bilinear = lambda src, size: F.interpolate(src, size=tuple(int(v) for v in size), mode="bilinear", align_corners=True)
+    try:
+        seen = []
+        for it in range(first_up + 1):
+            seen.append(t.check_schedule(it, 1))
+    finally:
+        ops.upsample_bilinear = orig
+    assert seen[:first_up] == [False] * first_up and seen[first_up] is True
+    n_dec = len(range(0, first_up + 1, 10))
+    assert abs(t.model.min_rough - 0.5 * t.model.min_rough_decay ** n_dec) < 1e-9          # models/microfacet.py:113-114
+    assert t.model.detach_N is False                                                        # iter > detach_N_iters (:115-116)
+    assert abs(t.bg_noise - 0.5 * t.bg_noise_decay ** (first_up + 1)) < 1e-9                # tensor_nerf.py:184
+    assert int(t.rf.grid_size[0]) > 16
+    assert float(t.sampler.stepsize) < step0 and int(t.sampler.nSamples) > n0               # re-read after the upsampling
+    assert float(t.sampler.stepsize) == float(t.rf.stepsize) and int(t.sampler.nSamples) == int(t.rf.nSamples)
+
+
+def test_load_takes_the_calibrated_biases_from_the_checkpoint(tmp_path):
+    """TensorNeRF.load with an EXTERNAL config (train.py:80,245 pass args.model.arch): brdf.bias, diffuse_bias and
+    roughness_bias are plain attributes, not in the state_dict, and come from ckpt['config'] (tensor_nerf.py:138-146);
+    the default near_far is [1, 6] (:156)."""
+    from nmf_b200 import config, plugins
+    over = ["field.grid_size=[12,12,12]", "model.arch.bg_module.bg_resolution=16"]
+    t, cfg = config.build_model(over)
+    t.model.brdf.bias, t.model.diffuse_module.diffuse_bias, t.model.diffuse_module.roughness_bias = 0.37, -1.25, 0.6
+    arch = config.to_plain(cfg.model.arch)
+    arch["model"]["brdf"]["bias"], arch["model"]["diffuse_module"]["diffuse_bias"] = 0.37, -1.25
+    arch["model"]["diffuse_module"]["roughness_bias"] = 0.6
+    path = str(tmp_path / "ckpt.th")
+    t.save(path, arch)
+    ckpt = torch.load(path, weights_only=False)
+    fresh = config.to_plain(config.compose(over).model.arch)                                # uncalibrated biases
+    fresh["rf"] = config.to_plain(config.compose(over).field)
+    assert fresh["model"]["brdf"]["bias"] != 0.37
+    u = plugins.TensorNeRF.load(ckpt, config=fresh)
+    assert u.model.brdf.bias == 0.37 and u.model.diffuse_module.diffuse_bias == -1.25 and u.model.diffuse_module.roughness_bias == 0.6
+    assert list(u.near_far) == [1, 6] and list(u.sampler.near_far) == [1, 6]
+    w = plugins.TensorNeRF.load(ckpt)                                                       # the checkpoint's own config
+    assert w.model.brdf.bias == 0.37
+    for (k, a), (_, b) in zip(t.state_dict().items(), u.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_microfacet_trainer_groups_mirror_the_reference_optimiser():
+    """The flat parameter buffer of MicrofacetTrainer: every reference parameter appears once, optimiser groups are
+    contiguous segments with the learning rates / betas of the reference's get_optparam_groups (fields/tensoRF.py:298-313,
+    models/microfacet.py, modules/integral_equirect.py; configs/model/microfacet_tensorf2.yaml:104-156); fixed_bg freezes the
+    map, its brightness and scale (train.py:267-284)."""
+    from nmf_b200 import train
+    keys = train.MICROFACET_PARAM_KEYS
+    assert len(keys) == len(set(keys)) == 31
+
+    class Probe(train.MicrofacetTrainer):
+        def __init__(self, **kw):
+            self.lr_grid, self.lr_net, self.lr_heads, self.lr_brdf = 2e-2, 1e-3, 1e-3, 1e-3
+            self.lr_bg, self.lr_mipbias, self.lr_brightness, self.lr_mul = 0.02, 1e-4, 0.0, 0.0
+            self.bg_betas, self.mul_betas = (0.9, 0.99), (0.9, 0.9)
+            for k, v in kw.items():
+                setattr(self, k, v)
+    defs = Probe()._group_defs()
+    flat = [k for ks, _, _ in defs for k in ks]
+    assert sorted(flat) == sorted(keys)
+    by = {k: (lr, b) for ks, lr, b in defs for k in ks}
+    assert by["rf.density_rf.app_plane.0"][0] == 2e-2 and by["rf.app_rf.app_line.2"][0] == 2e-2
+    assert by["rf.basis_mat.weight"] == (1e-3, (0.9, 0.99))
+    assert by["model.brdf.mlp.2.weight"][0] == 1e-3 and by["model.diffuse_module.f0_mlp.0.bias"][0] == 1e-3
+    assert by["bg_module.bg_mat"] == (0.02, (0.9, 0.99)) and by["bg_module.mipbias"][0] == 1e-4
+    assert by["bg_module.mul"] == (0.0, (0.9, 0.9)) and by["bg_module.brightness"][0] == 0.0
+    p = train.MICROFACET_REFERENCE_PARAMS
+    assert p["clip_grad"] is None and p["eps"] == 1e-8 and p["max_batch_size"] == 8000 and p["target_num_samples"] == 200000
