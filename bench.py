@@ -300,8 +300,9 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=150))
     from nmf_b200 import _lib, ops, renderer
     from nmf_b200.scene import DeviceScene
     _lib.lib()
@@ -546,12 +547,12 @@ def multi_gpu_extras(a, dist, rank, world, dev, state, meta, alpha, focal, barri
         lo, hi = distributed.shard_chunks(n, a.chunk, rank, world)
         mine = rays_all[lo:hi].contiguous()
         bufs = ops.RenderBuffers(scene, max(hi - lo, 1), a.chunk, ["rgb_map", "acc_map", "depth"])
-        counts = [distributed.shard_chunks(n, a.chunk, r, world) for r in range(world)]
-        gather = [torch.empty(c[1] - c[0], 3, device=dev) for c in counts] if rank == 0 else None
+        counts = [c[1] - c[0] for c in (distributed.shard_chunks(n, a.chunk, r, world) for r in range(world))]
+        stage = [None]
 
         def one():
             ims, _ = ops.render_rays(scene, mine, focal, chunk=a.chunk, seed=20211200, ray_id0=lo, buffers=bufs, check_errors=False)
-            dist.gather(ims["rgb_map"].contiguous(), gather, dst=0)
+            _, stage[0] = distributed.gather_ragged(ims["rgb_map"], counts, rank, world, buffers=stage[0])
         for _ in range(2):
             one()
         barrier()

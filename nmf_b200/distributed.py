@@ -38,6 +38,24 @@ def render_sharded(render_fn, rays, chunk, rank=None, world=None, gather=True, g
     return {k: torch.cat([p[k] for p in parts if p], dim=0) for k in keys}
 
 
+def gather_ragged(t, counts, rank, world, buffers=None, group=None):
+    """Gathers per-rank row blocks of different lengths on rank 0 with ONE collective: every rank pads its (counts[rank], C)
+    block to max(counts) rows (dist.gather needs equal shapes).  Returns (the concatenated (sum(counts), C) tensor on rank 0,
+    None elsewhere; the staging buffers to pass back in on the next call).  Works with NCCL (device tensors) and gloo."""
+    import torch.distributed as dist
+    m = max(counts)
+    if buffers is None:
+        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        buffers = (pad, parts)
+    pad, parts = buffers
+    pad[:t.shape[0]].copy_(t)
+    dist.gather(pad, parts, dst=0, group=group)
+    if rank != 0:
+        return None, buffers
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0), buffers
+
+
 class FlatGradBucket:
     """The one collective of ray-sharded training (BASELINE config #4): every rank renders its own
     rays, back-propagates locally, then ONE all-reduce(SUM) over a single flat fp32 buffer that aliases every parameter's

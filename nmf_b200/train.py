@@ -604,9 +604,9 @@ class PlainTrainer:
         self.iteration += 1
         return float(tot[0]), float(tot[1])
 
-    def step(self, rays, gt, ray_ids=None):
+    def step(self, rays, gt, ray_ids=None, **kw):
         """One iteration on this rank's rays: one sub-batch, normalised by the global number of kept rays."""
-        out = self.accumulate(rays, gt, ray_ids=ray_ids, first=True)
+        out = self.accumulate(rays, gt, ray_ids=ray_ids, first=True, **kw)
         n, loss = self.apply(out["n_rays"], out["loss_photo"])
         out["mse"] = loss / max(3.0 * n, 1.0)
         return out
@@ -879,14 +879,17 @@ class MicrofacetTrainer(PlainTrainer):
         if new != cur[0]:
             self.scene.update_hyper(max_retrace_rays=(new,))
 
-    def accumulate(self, rays, gt, ray_ids=None, first=True):
-        """One sub-batch (train.py:509-712): gradients accumulate on the device (MicrofacetGradBuffers)."""
+    def accumulate(self, rays, gt, ray_ids=None, first=True, ray_id0=None):
+        """One sub-batch (train.py:509-712): gradients accumulate on the device (MicrofacetGradBuffers).  ray_id0: global id
+        of rays[0] for the keyed jitter (default: a fresh id range per call); ray-sharded ranks that pass the global offset
+        of their slice draw the numbers a single-GPU pass over the whole batch would."""
         if self.grads is None:
             self.grads = MicrofacetGradBuffers(self.scene)
+        self.grads.scene = self.scene
         if first:
             self.grads.zero_()
             self._subs = 0
-        id0 = (self.seed * 7919 + self._calls) << 20
+        id0 = ((self.seed * 7919 + self._calls) << 20) if ray_id0 is None else int(ray_id0)
         out = train_microfacet(self.scene, rays, gt, seed=self.seed + self._calls, ray_id0=id0, max_samples=self.max_samples,
                                min_rough=self.min_rough, lambda_pred=self.lambda_pred, lambda_ori=self.lambda_ori,
                                detach_N=self.detach_N, grads=self.grads, zero_grads=False, buffers=self.buffers)

@@ -171,6 +171,37 @@ def _grad_worker(rank, world, port, tmp):
     dist.destroy_process_group()
 
 
+def _ragged_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from nmf_b200 import distributed
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    n, chunk = 10 * 7 + 3, 7                                       # 11 chunks over 2 ranks: 6 + 5 (uneven)
+    full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)
+    spans = [distributed.shard_chunks(n, chunk, r, world) for r in range(world)]
+    counts = [b - a for a, b in spans]
+    lo, hi = spans[rank]
+    bufs = None
+    for rep in range(2):                                           # staging buffers are reused on the second call
+        got, bufs = distributed.gather_ragged(full[lo:hi] + rep, counts, rank, world, buffers=bufs)
+        if rank == 0:
+            assert torch.equal(got, full + rep)
+        else:
+            assert got is None
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        torch.save(dict(counts=counts), out)
+
+
+def test_gather_ragged_two_ranks(tmp_path):
+    """the strong-scaling leg of bench.py (one image sharded by whole chunks, gathered on rank 0): uneven shards, one
+    collective per image; world_size 2 over gloo"""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r.pt")
+    mp.spawn(_ragged_worker, args=(2, 29755, out), nprocs=2, join=True)
+    assert torch.load(out)["counts"] == [42, 31]
+
+
 def test_flat_gradient_bucket_allreduce(tmp_path):
     """world_size-2 gloo run of the single gradient all-reduce of ray-sharded training."""
     import torch.multiprocessing as mp
