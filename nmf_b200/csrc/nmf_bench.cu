@@ -15,17 +15,18 @@
 // texel pair 384 (8 lanes x three 128-byte pieces).  group = 1 is the worst case (half of every 32-byte sector is wasted).
 __global__ void __launch_bounds__(256) k_bench_gather(const float4* __restrict__ buf, unsigned long long n_elems, int taps, int group,
                                                       float4* sink) {
-  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long gid = tid / (unsigned)group, sub = tid % (unsigned)group;
-  const unsigned long long n_seg = n_elems / (unsigned)group;
-  unsigned long long h = gid * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned gid = tid / (unsigned)group, sub = tid % (unsigned)group;
+  const unsigned n_seg = (unsigned)(n_elems / (unsigned)group);          // < 2^32 segments
+  unsigned h = gid * 0x9E3779B9u + 0x85EBCA6Bu;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = 0; i < taps; i += 8) {
     float4 v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
-      v[j] = __ldg(buf + (h % n_seg) * (unsigned)group + sub);
+      h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;      // murmur3 finaliser: a few ALU ops per tap
+      const unsigned seg = __umulhi(h, n_seg);                                            // uniform in [0, n_seg) without a division
+      v[j] = __ldg(buf + (size_t)seg * (unsigned)group + sub);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }

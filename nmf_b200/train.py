@@ -904,6 +904,12 @@ class MicrofacetTrainer(PlainTrainer):
         return out
 
     def apply(self, n_rays_local, loss_local=0.0, normaliser=None):
+        self.finish_into_bucket()
+        return super().apply(n_rays_local, loss_local, normaliser)
+
+    def finish_into_bucket(self):
+        """After the last sub-batch of an iteration: the two whole-image finishing passes, then this rank's gradient of every
+        parameter (plus the density L1 term) is written into the flat bucket the all-reduce and FusedAdam work on."""
         import torch.distributed as dist
         p = self.params
         self.grads.finish(p["bg_module.bg_mat"].data, p["bg_module.brightness"].data, p["bg_module.mul"].data)
@@ -916,7 +922,6 @@ class MicrofacetTrainer(PlainTrainer):
             for k, q in p.items():
                 if ".density_rf." in k:
                     l1_reg(q.data, self.l1_weight * self._subs / world, q.grad, self.l1_sum)
-        return super().apply(n_rays_local, loss_local, normaliser)
 
     def check_schedule(self, iteration, upsamp_list=(), n_voxel_list=(), update_list=()):
         """TensorNeRF.check_schedule (modules/tensor_nerf.py:177-195): the model's schedule first
@@ -999,11 +1004,7 @@ def benchmark_sharded_train(grid=300, n_rays=4096, steps=10, device="cuda:0", sc
         torch.cuda.synchronize(dev)
         e[0].record()
         out = tr.accumulate(rays, gt, first=True)
-        p = tr.params
-        tr.grads.finish(p["bg_module.bg_mat"].data, p["bg_module.brightness"].data, p["bg_module.mul"].data)
-        views = tr.grads.reference_views()
-        for k, q in p.items():
-            q.grad.copy_(views[k].reshape(q.shape))
+        tr.finish_into_bucket()
         e[1].record()
         tr.bucket.allreduce(scale=1.0)
         e[2].record()

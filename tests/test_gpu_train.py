@@ -255,42 +255,56 @@ def _ddp_worker_mf(rank, world, port, tmp):
                                          device=dev, seed=3, max_samples=-1, max_retrace_rays=(), mlp="fp32")
     lo, hi = rank * n // world, (rank + 1) * n // world
     tr = mk()
+    # (1) the invariant: the all-reduced flat gradient of the sharded batch IS the gradient of the whole batch
+    tr._calls = 0
+    tr.accumulate(rays[lo:hi].to(dev), gt[lo:hi].to(dev), first=True, ray_id0=lo)
+    tr.finish_into_bucket()
+    tr.bucket.allreduce(scale=1.0)
+    g_sharded = tr.bucket.flat.detach().cpu().clone()
+    # (2) a few optimiser iterations run in lock-step on both ranks
+    mse = []
     for it in range(4):
-        tr._calls = it                                   # same seed per iteration on every rank
-        tr.step(rays[lo:hi].to(dev), gt[lo:hi].to(dev), ray_id0=1000 * it + lo)
+        tr._calls = it
+        mse.append(tr.step(rays[lo:hi].to(dev), gt[lo:hi].to(dev), ray_id0=1000 * it + lo)["mse"])
         tr.check_schedule(it)
-    sharded = {k: p.detach().cpu() for k, p in tr.params.items()}
+    flat = tr.flat_params.detach().clone()
+    other = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(other, flat)
+    same = all(torch.equal(o, flat) for o in other)                 # replicas stay bit-identical: same reduced gradient, same update
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
         single = mk()
-        for it in range(4):
-            single._calls = it
-            single.step(rays.to(dev), gt.to(dev), ray_id0=1000 * it)
-            single.check_schedule(it)
-        worst = {}
+        single._calls = 0
+        single.accumulate(rays.to(dev), gt.to(dev), first=True, ray_id0=0)
+        single.finish_into_bucket()
+        g_single = single.bucket.flat.detach().cpu()
+        rel, off = {}, 0
         for k, p in single.params.items():
-            d = (sharded[k] - p.detach().cpu()).abs().reshape(-1)
-            worst[k] = (float(d.max()), float(torch.quantile(d, 0.99)) if d.numel() > 1 else float(d.max()))
-        torch.save(worst, tmp)
+            a, b = g_sharded[off:off + p.numel()], g_single[off:off + p.numel()]
+            off += p.numel()
+            if float(b.abs().max()) > 0:
+                rel[k] = float((a - b).norm() / b.norm())
+        torch.save(dict(rel=rel, same=same, mse=mse), tmp)
 
 
 def test_microfacet_ray_sharded_training_two_gpus(env, tmp_path):
-    """BASELINE config #4 (ray-batch sharded microfacet training, ONE flat NCCL gradient all-reduce per iteration): two ranks
-    on disjoint halves of the batch end at the parameters of the single-GPU run on all rays after 4 Adam iterations (keyed
-    random numbers: every ray draws the same jitter, bounce counts and directions wherever it is rendered)."""
+    """BASELINE config #4 (ray-batch sharded microfacet training, ONE flat NCCL gradient all-reduce per iteration): the
+    all-reduced gradient of two ranks on disjoint halves of the batch equals the single-GPU gradient of the whole batch
+    (keyed random numbers: every ray draws the same jitter, bounce counts and directions wherever it is rendered; relative
+    L2 per parameter < 1e-4: only the order of the fp32 atomic sums differs), and the replicas stay bit-identical over
+    optimiser iterations.  (Parameters after Adam are NOT compared across world sizes: Adam moves an entry whose gradient
+    is accumulation noise -- most texels of the environment map -- by +-lr whatever its magnitude.)"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
     out = str(tmp_path / "worst_mf.pt")
     mp.spawn(_ddp_worker_mf, args=(2, 29741, out), nprocs=2, join=True)
-    worst = torch.load(out)
-    print(worst)
-    # Adam normalises the step to ~lr * sign(g): an entry whose gradient is accumulation-order noise (texels of the map the
-    # lookups cancel on, factors outside the object) may move the other way by lr (0.02) per iteration on either run.  So:
-    # the bulk of every parameter (99 % quantile) agrees to a small fraction of one step, the maximum to within the 4 steps.
-    assert max(q for _, q in worst.values()) < 2e-4, worst
-    assert max(m for m, _ in worst.values()) < 4 * 0.02 + 1e-3, worst
+    res = torch.load(out)
+    print(res)
+    assert res["same"]
+    assert len(res["rel"]) >= 20 and max(res["rel"].values()) < 1e-4, res["rel"]
+    assert all(m == m and m < 1.0 for m in res["mse"])
 
 
 def test_upsample_schedule(env):
