@@ -674,11 +674,16 @@ class IntegralEquirect(nn.Module):
 
     @torch.no_grad()
     def get_spherical_harmonics(self, G, mipval=-5):
-        """integral_equirect.py:324-360: (coeffs (9,3), conv_coeffs (9,3))"""
+        """integral_equirect.py:324-360: (coeffs (9,3), conv_coeffs / pi (9,3)) -- the second value already carries the 1 / pi
+        of the Lambertian BRDF, as the reference returns it (:359)."""
         sc = self.scene()
-        conv = sc.sh_irradiance(G, mipval) * math.pi
-        al2 = torch.tensor([math.pi] + [2 * math.pi / 3] * 3 + [math.pi / 4] * 5, device=conv.device).reshape(-1, 1)
-        return conv / al2, conv
+        conv_pi = sc.sh_irradiance(G, mipval)                    # sh_A * coeffs / pi, in the kernels' basis (nmf_sh9)
+        # modules/sh.py:67-73 has all-positive degree-2 constants; nmf_sh9 carries a minus on the yz and xz terms (the same
+        # sign in projection and evaluation, so E(n) is identical): hand the coefficients out in the reference's convention
+        sign = torch.tensor([1, 1, 1, 1, 1, -1, 1, -1, 1], device=conv_pi.device, dtype=conv_pi.dtype).reshape(-1, 1)
+        conv_pi = conv_pi * sign
+        al2 = torch.tensor([math.pi] + [2 * math.pi / 3] * 3 + [math.pi / 4] * 5, device=conv_pi.device).reshape(-1, 1)
+        return conv_pi * math.pi / al2, conv_pi
 
 
 # ------------------------------------------------------------------------------------------------------------

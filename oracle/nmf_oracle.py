@@ -493,6 +493,33 @@ def sh_irradiance_coeffs(sc, rng=None, G=100, mipval=-5.0):
     return out
 
 
+class EnvScene:
+    """Environment-only scene (an IntegralEquirect state_dict: bg_mat, mipbias, brightness, mul) for env_lookup /
+    sh_irradiance_coeffs -- e.g. backgrounds/forest.th, which is 1024 x 2048 and carries non-trivial scalars."""
+
+    def __init__(self, sd, **hp):
+        self.hp = dict(DEFAULT_HP)
+        self.hp.update(hp)
+        self.requires_grad, self.params = False, {}
+        self.bg_mat = torch.as_tensor(sd["bg_mat"]).detach().float().reshape(1, 3, *sd["bg_mat"].shape[-2:])
+        f64 = lambda k, d: torch.as_tensor(sd.get(k, d)).detach().to(torch.float64)
+        self.mipbias, self.brightness, self.mul = f64("mipbias", 1.0), f64("brightness", 0.0), f64("mul", 1.0)
+        self._env = self._sh = None
+
+
+def env_lookup_state(sd, dirs, sa):
+    """IntegralEquirect(state_dict).forward(dirs, sa)"""
+    return env_lookup(EnvScene(sd), dirs, sa.reshape(-1, 1) if sa.dim() == 1 else sa)
+
+
+def sh_conv_state(sd, G=100):
+    """IntegralEquirect(state_dict).get_spherical_harmonics(G)[1] (clamped-cosine-convolved coefficients / pi, :359), in
+    the REFERENCE's basis convention: modules/sh.py:67-73 has all-positive degree-2 constants, sh9 here carries a minus on
+    the yz / xz terms (same sign in projection and evaluation: the irradiance E(n) is identical)."""
+    sign = torch.tensor([1, 1, 1, 1, 1, -1, 1, -1, 1.0]).reshape(-1, 1)
+    return sh_irradiance_coeffs(EnvScene(sd), G=G) * sign
+
+
 # --------------------------------------------------------------------------------------------
 # A9  bounce counts                                                  modules/pt_selectors.py:5-60
 # --------------------------------------------------------------------------------------------

@@ -76,6 +76,13 @@ def test_env_and_irradiance(case):
     err = (out - ref).abs() / (ref.abs() + 1e-2)
     # fp32 SAT corner differences cancel catastrophically for sub-pixel boxes (hard part 4)
     assert err.max() < 5e-2 and err.mean() < 2e-4, (err.max(), err.mean())
+    # the poles, the +-pi seam and the axes: regular-sized boxes there are well conditioned, a wrong wrap / pole box is O(1)
+    big = mip[:6] > -6
+    assert float(err[:6][big].max() if big.any() else 0.0) < 1e-4, err[:6]
+    mip6 = torch.tensor([-2.0, -1.0, -3.0, -3.0, -2.5, -4.0])
+    o6 = ops.env_lookup(dsc, d[:6].cuda(), mip6.cuda()).cpu()
+    r6 = O.env_lookup(osc, d[:6], mip6)
+    assert float(((o6 - r6).abs() / (r6.abs() + 1e-2)).max()) < 1e-4
     conv = dsc.keep["sh_conv"].cpu()
     assert torch.allclose(conv, O.sh_irradiance_coeffs(osc), rtol=1e-4, atol=1e-4)  # sums of 5000 O(1) terms
 
