@@ -181,6 +181,41 @@ def test_render_matches_oracle(case, skip):
     assert not bad, bad
 
 
+def test_estimator_has_the_reference_distribution(env):
+    """The CUDA path draws keyed random numbers, the reference torch's global generator, so single renders are compared
+    through the oracle's two RNG modes.  This test pins the ESTIMATOR: the mean over 48 keyed seeds of the CUDA render equals
+    the mean over 48 seeds of the UNMODIFIED reference (tests/golden/microfacet_g40_meanimage.pt,
+    oracle/make_golden_meanimage.py) within Monte-Carlo error, per ray and channel, for every stochastic radiance map
+    (bounce counts, Sobol offsets, feature noise, re-trace selection, environment lookups all enter it)."""
+    from nmf_b200 import ops
+    fix = load_fixture("microfacet_g40")
+    gold = load_fixture("microfacet_g40_meanimage")
+    dsc = device_scene(fix, env, mlp="fp32")
+    n, S = gold["n_rays"], gold["n_seeds"]
+    rays = fix["rays"][:n].contiguous().cuda()
+    acc = {}
+    for s in range(S):
+        ims, _ = ops.render_rays(dsc, rays, fix["focal"], chunk=n, seed=500 + s, skip_eps=0.0, t_cut=0.0)
+        for k in ("rgb_map", "spec", "diffuse", "tint"):
+            acc.setdefault(k, []).append(ims[k].float().cpu().clone())
+    report = {}
+    for k, v in acc.items():
+        st = torch.stack(v)
+        mean, std = st.mean(0), st.std(0)
+        rm, rs = gold[k + "_mean"], gold[k + "_std"]
+        if float(rs.max()) == 0.0:                                   # a deterministic map (diffuse = albedo * E(n))
+            assert float((mean - rm).abs().max()) < 5e-4, k
+            continue
+        se = torch.sqrt((std ** 2 + rs ** 2) / S + 1e-10)
+        z = ((mean - rm) / se).reshape(-1)
+        report[k] = (float(z.abs().mean()), float(z.abs().max()), float((mean - rm).abs().mean()), float(rs.mean()))
+        # |z| ~ half-normal under the null: mean 0.80; a biased estimator (wrong pdf, wrong Fresnel weight, wrong selection
+        # probability ...) shifts every entry the same way and shows up in the mean |z| and in the mean signed difference
+        assert float(z.abs().mean()) < 1.15 and float((z.abs() > 4.5).float().mean()) < 0.005, (k, report[k])
+        assert abs(float((mean - rm).mean())) < 4 * float(rs.mean()) / (S * n) ** 0.5 + 2e-4, (k, float((mean - rm).mean()))
+    print(report)
+
+
 def test_render_is_order_independent(case):
     """keyed RNG: a ray's pixel does not depend on which launch / position in the batch it has (up to the
     chunk-global retrace selection, which is disabled here by using one chunk for both orders)."""

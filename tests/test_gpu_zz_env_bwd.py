@@ -79,6 +79,39 @@ def test_env_map_gradient_on_device(env, name):
     assert float(acc.gsat.abs().sum()) == 0.0 and float(acc.d_mipbias) == 0.0      # ready for the next optimiser step
 
 
+def test_mipbias_gradient_at_the_production_map_size(env):
+    """d loss / d mipbias at 512 x 1024 (the size of configs/model/microfacet_tensorf2.yaml; the white-noise map of the test
+    above makes the bias gradient cancellation noise on both sides and is not judged there).  Here the case is well
+    conditioned and therefore JUDGED: a band-limited map (a 64 x 128 random field, bicubically upsampled: features of 8 texels), boxes of one texel and
+    more (solid angles in [-7, 0]: the level clamp at 0 is open for most lookups), and a one-signed upstream, so the terms
+    add instead of cancelling.  Reference: torch autograd through the oracle's lookup in the same fp32 arithmetic."""
+    from nmf_b200 import ops
+    from oracle import nmf_oracle as O
+    fix = load_fixture("microfacet_g40")
+    g = torch.Generator().manual_seed(21)
+    low = torch.randn(1, 3, 64, 128, generator=g) * 1.0 - 0.3
+    fix["state"]["bg_module.bg_mat"] = torch.nn.functional.interpolate(low, size=(512, 1024), mode="bicubic", align_corners=True)
+    osc = oracle_scene(fix, requires_grad=True)
+    dsc = device_scene(fix, env)
+    n = 60000
+    d = O.unit(torch.randn(n, 3, generator=g))
+    sa = torch.rand(n, generator=g) * 7 - 7
+    up = torch.rand(n, 3, generator=g) + 0.1                       # one-signed
+    (O.env_lookup(osc, d, sa) * up).sum().backward()
+    ref = float(osc.params["bg_module.mipbias"].grad)
+    acc = ops.EnvMapGrad(dsc)
+    acc.scatter(d.cuda(), sa.cuda(), up.cuda())
+    d_bg, d_br, d_mul, d_mb = acc.finish(osc.bg_mat.detach().cuda(), float(osc.brightness.detach()), float(osc.mul.detach()))
+    assert abs(ref) > 1.0, ref                                     # a material gradient, not noise
+    print("d_mipbias", float(d_mb), ref)
+    assert abs(float(d_mb) - ref) < 1e-2 * abs(ref), (float(d_mb), ref)
+    for got, key in ((d_br, "bg_module.brightness"), (d_mul, "bg_module.mul")):
+        r = float(osc.params[key].grad)
+        assert abs(float(got) - r) < 2e-3 * abs(r), (key, float(got), r)
+    want = osc.params["bg_module.bg_mat"].grad.float()
+    assert float((d_bg.cpu() - want).norm() / want.norm()) < 2e-3
+
+
 def test_env_map_gradient_is_linear_and_skips_zero_upstream(env):
     """Size-independent properties: the reverse pass is linear in the upstream gradient, and lookups with a zero upstream
     leave the map gradient untouched."""
