@@ -157,11 +157,28 @@ def test_forest_environment_on_device(which):
     env = env.cuda()
     assert env.bg_resolution == sd["bg_mat"].shape[-2] and abs(float(env.mipbias) - float(sd["mipbias"])) < 1e-12
     out = env(fix["dirs"].cuda(), fix["mip"].cuda().reshape(-1, 1)).cpu()
+    # Tolerance from the conditioning of the reference's own formulation: a box integral is a difference of four fp32 SAT
+    # corners of magnitude up to S_max (the total of exp(bg) / 1000), scaled by 1000 / size, so ONE ulp of a corner is
+    # unit_i = eps * S_max * 1000 / size_i of radiance.  The reference itself sits at max 2.4 / mean 0.32 units from the fp64
+    # evaluation of the same formula on this map (measured with the oracle); the CUDA taps round differently (FMA
+    # contraction), so both sides are a few units apart: |cuda - reference| <= 8 units + 1e-4 |reference| per lookup, mean
+    # below one unit.  (Relative to the VALUE this is O(1) for sub-texel boxes on an HDR map -- in the reference as well.)
+    from oracle import nmf_oracle as O
+    sc = O.EnvScene(sd)
+    h, w = sc.bg_mat.shape[-2:]
+    lw, lh = O.env_mip_levels(sc, fix["dirs"], fix["mip"].reshape(-1, 1))
+    size = ((2 ** lw / h / 2) / 2 * w * (2 ** lh / h) / 2 * h).reshape(-1)
+    unit = 1.1920929e-07 * float(O.env_tables(sc)[1].abs().max()) * 1000.0 / size
+    aerr = (out - ref).abs().max(dim=1).values
+    k = (aerr - 1e-4 * ref.abs().max(dim=1).values).clamp(min=0) / unit
+    print(which, "SAT lookup error in conditioning units: max %.2f mean %.3f" % (float(k.max()), float(k.mean())))
+    assert float(k.max()) < 8.0 and float(k.mean()) < 1.0, (float(k.max()), float(k.mean()))
+    # boxes of a few texels and more are well conditioned: there the agreement is tight, and the poles / seam / axis probes
+    # (first 10) would be O(1) off with a wrong wrap-around or pole box
+    well = size > 16
     err = (out - ref).abs() / (ref.abs() + 1e-2)
-    # sub-texel boxes difference four SAT corners of magnitude ~1e3 x the result: 2e-2 worst case at 1024 x 2048; the
-    # poles, the seam and the axis directions (first 10 probes) are pinned tightly -- a wrong wrap box would be O(1) there
-    assert float(err.max()) < 5e-2 and float(err.mean()) < 3e-4, (float(err.max()), float(err.mean()))
-    assert float(err[:10].max()) < 2e-3, err[:10].max(dim=1).values
+    assert float(err[well].max()) < 2e-2 and float(err[well].mean()) < 2e-4, (float(err[well].max()), float(err[well].mean()))
+    assert float(k[:10].max()) < 8.0 and float(err[:10][well[:10]].max() if bool(well[:10].any()) else 0.0) < 2e-3
     _, conv = env.get_spherical_harmonics(100)
     assert float((conv.cpu() - sh).abs().max()) <= 5e-4 * float(sh.abs().max())
     # a panorama-derived environment goes through the same slot (relight.env_from_panorama, config #5's other maps)
