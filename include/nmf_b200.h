@@ -453,6 +453,28 @@ int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp, const NmfRe
  * reference's own parameter layout (a line (1,C,N,1) is H = N, W = 1). */
 int nmf_upsample_bilinear(const float* src, int C, int H, int W, float* dst, int H2, int W2, void* stream);
 
+/* ---- scene re-pack: rebuilt from the parameters after every optimiser step of a training run (csrc/nmf_repack.cu) ---- */
+
+/* One factor in the reference's layout -- a plane (1,C,H,W) or a line (1,C,N,1) passed as H = N, W = 1 -- into the
+ * channel-last gather layouts of NmfScene: val [H][W][C] and, for the density factors (C = 16), pack = [H][W][val | dx | dy]
+ * (lines: [N][4][val4 | dy4]) with the smoothed-difference planes of modules/grid_sample_Cinf.py:218-242 (5x5
+ * cross-correlation with kx25 / ky25, zero padding 2).  val or pack may be NULL. */
+int nmf_pack_factor(const float* src, int C, int H, int W, const float* kx25, const float* ky25, float* val, float* pack,
+                    void* stream);
+
+/* IntegralEquirect tables (modules/integral_equirect.py:263-273, 431-433, 498-502): act = exp(min(brightness + mul *
+ * bg_mat, 20)) (optional out, (3,h,w)), sat4 [h][w][4] = cumsum_x(cumsum_y(act / 1000)) with fp64 accumulation and a
+ * rounding to fp32 after each scan (ATen's CPU cumsum), pole_sums[6] (device, fp64) = sums of the first / last row of act
+ * per channel.  scratch_c1: 3*h*w floats. */
+int nmf_env_build_sat(const float* bg_mat, int h, int w, float brightness, float mul, float* scratch_c1, float* act,
+                      float* sat4, double* pole_sums, void* stream);
+
+/* AlphaGridSampler.updateAlphaMask after the dense alpha (samplers/alphagrid.py:256-261): clamp, 3^3 max-pool (padding 1),
+ * threshold -> the occupancy bit-fields of NmfScene (vox, cell: gz*gy*pitch/32 words each; coarse: optional,
+ * ceil(gx/8)*ceil(gy/8)*ceil(gz/8) bits) and, optionally, the 0/1 float volume (gz,gy,gx) the reference keeps. */
+int nmf_occupancy_from_alpha(const float* alpha, int gx, int gy, int gz, float thres, int pitch, uint32_t* vox, uint32_t* cell,
+                             uint32_t* coarse, float* volume, void* stream);
+
 /* Measurement helper (bench.py): `n_threads` threads (a multiple of 256) each issue `taps` (a multiple of 8) independent
  * 16-byte loads over `buf` (n_elems float4) and write one float4 of `sink` (n_threads float4); `group` (1, 2, 4, 8)
  * consecutive lanes read consecutive pieces of one pseudo-random segment of 16 * group bytes (the granularity of the

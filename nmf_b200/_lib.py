@@ -182,6 +182,9 @@ def lib():
         "nmf_render_rays_train": (I, [SP, RP, C.POINTER(NmfRenderTrain), P, IP, CP, P, C.c_size_t, P]),
         "nmf_train_microfacet": (I, [SP, RP, C.POINTER(NmfRenderTrain), C.POINTER(NmfMicrofacetTrain), P, P,
                                      C.POINTER(NmfMicrofacetGrads), IP, CP, P, C.c_size_t, P]),
+        "nmf_pack_factor": (I, [P, I, I, I, P, P, P, P, P]),
+        "nmf_env_build_sat": (I, [P, I, I, F, F, P, P, P, P, P]),
+        "nmf_occupancy_from_alpha": (I, [P, I, I, I, F, I, P, P, P, P, P]),
         "nmf_bench_gather": (I, [P, C.c_size_t, I, I, I, P, P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
                                 C.c_size_t, P]),
@@ -201,4 +204,5 @@ EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_pr
             "nmf_sample_rays_train", "nmf_train_workspace_bytes", "nmf_train_plain", "nmf_upsample_bilinear",
             "nmf_render_train_workspace_bytes", "nmf_render_rays_train", "nmf_l1_reg", "nmf_grad_sq_norm", "nmf_adam_step",
             "nmf_env_lookup_bwd_scatter", "nmf_env_lookup_bwd_finish", "nmf_env_lookup_bwd_mipbias", "nmf_vm_normals_bwd_scatter",
-            "nmf_vm_normals_bwd_finish", "nmf_material_heads_bwd", "nmf_train_microfacet", "nmf_bench_gather"]
+            "nmf_vm_normals_bwd_finish", "nmf_material_heads_bwd", "nmf_train_microfacet", "nmf_bench_gather", "nmf_pack_factor", "nmf_env_build_sat",
+            "nmf_occupancy_from_alpha"]

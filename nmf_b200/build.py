@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnmf_b200.so")
-SOURCES = ["nmf_kernels.cu", "nmf_train.cu", "nmf_env_bwd.cu", "nmf_normals_bwd.cu", "nmf_shade_bwd.cu", "nmf_mf_train.cu", "nmf_bench.cu"]
-DEPS = ["nmf_bench.cu", "nmf_kernels.cu", "nmf_train.cu", "nmf_env_bwd.cu", "nmf_normals_bwd.cu", "nmf_shade_bwd.cu", "nmf_mf_train.cu", "nmf_render_ws.cuh", "nmf_microfacet_bwd.cuh", "nmf_train.cuh", "nmf_mlp_tc.cuh", "nmf_math.cuh", "nmf_field.cuh", os.path.join("..", "..", "include", "nmf_b200.h")]
+SOURCES = ["nmf_kernels.cu", "nmf_train.cu", "nmf_env_bwd.cu", "nmf_normals_bwd.cu", "nmf_shade_bwd.cu", "nmf_mf_train.cu", "nmf_bench.cu", "nmf_repack.cu"]
+DEPS = ["nmf_bench.cu", "nmf_repack.cu", "nmf_kernels.cu", "nmf_train.cu", "nmf_env_bwd.cu", "nmf_normals_bwd.cu", "nmf_shade_bwd.cu", "nmf_mf_train.cu", "nmf_render_ws.cuh", "nmf_microfacet_bwd.cuh", "nmf_train.cuh", "nmf_mlp_tc.cuh", "nmf_math.cuh", "nmf_field.cuh", os.path.join("..", "..", "include", "nmf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--threads", "6"]
 

@@ -475,7 +475,9 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       }
     }
     BSample* b = a.bs + (slot >= 0 ? slot : 0);
-    if (TRAIN && a.survslot && active) a.survslot[si] = slot;
+    // survivor -> bounce-sample slot for the reverse pass; -2 = no bounce sample but a back-facing normal (the orientation
+    // loss still has a gradient there), -1 = nothing to do
+    if (TRAIN && a.survslot && active) a.survslot[si] = slot >= 0 ? slot : (vn < 0.f ? -2 : -1);
     float* acc = LEVEL == 0 ? a.accum + (size_t)ray * A_N : nullptr;
     // roughness head (render_modules.py:553-560; r2 = r1, microfacet.py:360)
     float lin = s_headb[9];

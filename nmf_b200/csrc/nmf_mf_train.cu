@@ -603,7 +603,8 @@ __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const 
     for (int i = 0; i < 24; ++i) { fr[i] = 0.f; dfr[i] = 0.f; }
 #pragma unroll
     for (int i = 0; i < 11; ++i) dl[i] = 0.f;
-    if (si < n) {
+    const int slot = si < n ? a.survslot[si] : -1;      // -1: nothing to differentiate (no bounce rays, front-facing normal)
+    if (slot != -1 && !(LEVEL == 1 && slot == -2)) {
       const Surv sv = a.surv[si];
       const int ray = (int)sv.ray, k = (int)sv.step;
       float o[3], d[3], p[3], xn[3];
@@ -626,7 +627,6 @@ __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const 
         const float k2 = a.lambda_ori * sv.w * 2.0f * vn;
         dn[0] = k2 * V.x; dn[1] = k2 * V.y; dn[2] = k2 * V.z;
       }
-      const int slot = a.survslot[si];
       if (slot >= 0) {
         const float* G = a.bgrad + (size_t)slot * NMF_BGRAD;
         float coef[72];
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const 
         if (dgrad[0] != 0.f || dgrad[1] != 0.f || dgrad[2] != 0.f) {
           float* gp[3] = {a.g.gpack[0], a.g.gpack[1], a.g.gpack[2]};
           float* gl[3] = {a.g.glpack[0], a.g.glpack[1], a.g.glpack[2]};
-          nmf_normal_bwd(s, tp, dgrad, gp, gl);
+          nmf_normal_bwd4(s, tp, dgrad, gp, gl);
         }
       }
     } else {

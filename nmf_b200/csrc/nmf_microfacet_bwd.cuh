@@ -483,6 +483,46 @@ NMF_HD void nmf_normal_bwd(const NmfScene& s, const NmfTaps& t, const float* dgr
   }
 }
 
+// The same scatter with 16-byte accumulates (device: red.global.add.v4.f32): channel groups of 4 are contiguous in both
+// gradient images, so a sample issues 192 vector atomics instead of 768 scalar ones.  Used by k_mf_sample_bwd; equal to
+// nmf_normal_bwd up to the order of the additions (the GPU gradient-parity tests cover it).
+NMF_HD nmf_f4 nmf_f4_axpby(float a, nmf_f4 x, float b, nmf_f4 y) {
+  nmf_f4 o; o.x = a * x.x + b * y.x; o.y = a * x.y + b * y.y; o.z = a * x.z + b * y.z; o.w = a * x.w + b * y.w; return o;
+}
+NMF_HD void nmf_normal_bwd4(const NmfScene& s, const NmfTaps& t, const float* dgrad, float* const* gpack, float* const* glpack) {
+  for (int p = 0; p < 3; ++p) {
+    const int w = s.plane_w[p];
+    const NmfLerp& lx = t.px[p]; const NmfLerp& ly = t.py[p]; const NmfLerp& ll = t.pl[p];
+    const float g0 = dgrad[NMF_MAT0(p)], g1 = dgrad[NMF_MAT1(p)], gv = dgrad[NMF_VEC(p)];
+    const size_t tex[4] = {(size_t)ly.i0 * w + lx.i0, (size_t)ly.i0 * w + lx.i1, (size_t)ly.i1 * w + lx.i0, (size_t)ly.i1 * w + lx.i1};
+    const float tw[4] = {ly.w0 * lx.w0, ly.w0 * lx.w1, ly.w1 * lx.w0, ly.w1 * lx.w1};
+    for (int g = 0; g < 4; ++g) {
+      nmf_f4 pc = nmf_f4_zero(), dpx = nmf_f4_zero(), dpy = nmf_f4_zero();
+      for (int q = 0; q < 4; ++q) {
+        if (tw[q] == 0.f) continue;
+        const float* e = s.dpack[p] + tex[q] * 48 + 4 * g;
+        nmf_f4_fma(pc, NMF_LD4(e), tw[q]); nmf_f4_fma(dpx, NMF_LD4(e + 16), tw[q]); nmf_f4_fma(dpy, NMF_LD4(e + 32), tw[q]);
+      }
+      const float* a0 = s.lpack[p] + (size_t)ll.i0 * 32 + 8 * g;
+      const float* a1 = s.lpack[p] + (size_t)ll.i1 * 32 + 8 * g;
+      nmf_f4 lc = nmf_f4_zero(), dly = nmf_f4_zero();
+      if (ll.w0 != 0.f) { nmf_f4_fma(lc, NMF_LD4(a0), ll.w0); nmf_f4_fma(dly, NMF_LD4(a0 + 4), ll.w0); }
+      if (ll.w1 != 0.f) { nmf_f4_fma(lc, NMF_LD4(a1), ll.w1); nmf_f4_fma(dly, NMF_LD4(a1 + 4), ll.w1); }
+      const nmf_f4 d_lc = nmf_f4_axpby(g0, dpx, g1, dpy);
+      for (int q = 0; q < 4; ++q) {
+        float* e = gpack[p] + tex[q] * 48 + 4 * g;
+        nmf_acc4(e, dly, tw[q] * gv);            // d value plane  = gv * line'
+        nmf_acc4(e + 16, lc, tw[q] * g0);        // d dx plane     = g0 * line
+        nmf_acc4(e + 32, lc, tw[q] * g1);        // d dy plane     = g1 * line
+      }
+      float* b0 = glpack[p] + (size_t)ll.i0 * 32 + 8 * g;
+      float* b1 = glpack[p] + (size_t)ll.i1 * 32 + 8 * g;
+      nmf_acc4(b0, d_lc, ll.w0); nmf_acc4(b0 + 4, pc, ll.w0 * gv);
+      nmf_acc4(b1, d_lc, ll.w1); nmf_acc4(b1 + 4, pc, ll.w1 * gv);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Finishing pass of the normal path: the gradient images scattered by nmf_normal_bwd hold d loss / d (value | dx | dy) per
 // texel; the dx / dy planes are cross-correlations of the density plane with the 5x5 smoothed-difference stencils

@@ -1,0 +1,259 @@
+// nmf_b200 -- scene re-pack kernels: what has to be rebuilt from the parameters after every optimiser step of a training
+// run (once per ITERATION), hand-written instead of cuDNN / torch scans:
+//   k_pack_plane / k_pack_line   reference-layout factors (1,C,H,W) / (1,C,N,1) -> the channel-last gather layouts of
+//                                NmfScene, with the smoothed-difference planes of modules/grid_sample_Cinf.py:218-242 (a 5x5
+//                                cross-correlation of the WHOLE plane, zero padding 2; the reference recomputes it inside every
+//                                compute_normals call) -- the forward twin of k_normals_bwd_planes (csrc/nmf_normals_bwd.cu)
+//   k_env_act_scan_y, k_env_scan_x   modules/integral_equirect.py:263-273, 431-433: act = exp(min(brightness + mul * bg, 20)),
+//                                SAT = cumsum_x(cumsum_y(act / 1000)) with ATen's CPU semantics (fp64 accumulation, every prefix
+//                                rounded to fp32 after EACH of the two scans), channel-last [h][w][4]; pole-row means
+//   k_occ_pool_pack, k_occ_cells, k_occ_coarse   samplers/alphagrid.py:249-276: 3^3 max-pool + threshold of the dense alpha
+//                                lattice -> voxel bit-field, per-cell OR of the 8 corners, conservative coarse field
+// All of them stream their input once; bytes per element are stated at each kernel.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nmf_b200.h"
+
+#define FULLM 0xffffffffu
+#define CKL() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+// thread per (texel, channel), channel fastest: 4 B read (+ 2 x 25 cached taps) / 4 or 16 B written per element
+template <int C>
+__global__ void __launch_bounds__(256) k_pack_plane(const float* __restrict__ src, int H, int W, const float* __restrict__ kx25,
+                                                    const float* __restrict__ ky25, float* __restrict__ val, float* __restrict__ pack) {
+  __shared__ float kx[25], ky[25];
+  if (pack && threadIdx.x < 25) { kx[threadIdx.x] = kx25[threadIdx.x]; ky[threadIdx.x] = ky25[threadIdx.x]; }
+  __syncthreads();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t texel = idx / C;
+  const int c = (int)(idx - texel * C);
+  if (texel >= (size_t)H * W) return;
+  const int y = (int)(texel / W), x = (int)(texel - (size_t)y * W);
+  const float* p = src + (size_t)c * H * W;
+  const float v = p[(size_t)y * W + x];
+  if (val) val[texel * C + c] = v;
+  if (pack) {
+    float dx = 0.f, dy = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int yy = y + i - 2;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int xx = x + j - 2;
+        if (xx < 0 || xx >= W) continue;
+        const float s = p[(size_t)yy * W + xx];
+        dx = fmaf(kx[i * 5 + j], s, dx);
+        dy = fmaf(ky[i * 5 + j], s, dy);
+      }
+    }
+    float* o = pack + texel * (3 * C);
+    o[c] = v; o[C + c] = dx; o[2 * C + c] = dy;
+  }
+}
+// lines are (N, 1) images: only the centre column of the stencil meets data.  lpack: [n][4][val4 | dy4]
+__global__ void k_pack_line(const float* __restrict__ src, int C, int N, const float* __restrict__ ky25, float* __restrict__ val,
+                            float* __restrict__ pack) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = idx / C, c = idx - n * C;
+  if (n >= N) return;
+  const float* p = src + (size_t)c * N;
+  const float v = p[n];
+  if (val) val[(size_t)n * C + c] = v;
+  if (pack) {
+    float dy = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int nn = n + i - 2;
+      if (nn >= 0 && nn < N) dy = fmaf(ky25[i * 5 + 2], p[nn], dy);
+    }
+    const int lo = (c >> 2) * 8 + (c & 3);
+    pack[(size_t)n * 32 + lo] = v;
+    pack[(size_t)n * 32 + lo + 4] = dy;
+  }
+}
+
+extern "C" int nmf_pack_factor(const float* src, int C, int H, int W, const float* kx25, const float* ky25, float* val, float* pack,
+                               void* stream) {
+  if (!src || (!val && !pack) || H <= 0 || W <= 0 || (C != 16 && C != 24)) return NMF_E_ARG;
+  if (pack && (C != 16 || !kx25 || !ky25)) return NMF_E_ARG;
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (W == 1) {                     // a line (1,C,N,1)
+    k_pack_line<<<(H * C + 255) / 256, 256, 0, cs>>>(src, C, H, ky25, val, pack);
+  } else {
+    const size_t n = (size_t)H * W * C;
+    if (C == 16) k_pack_plane<16><<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(src, H, W, kx25, ky25, val, pack);
+    else k_pack_plane<24><<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(src, H, W, kx25, ky25, val, pack);
+  }
+  CKL();
+  return NMF_OK;
+}
+
+// ---- environment: activation + summed-area table ----
+// pass 1: one thread per (channel, column): act, and the running sum over rows in fp64, rounded to fp32 per prefix
+// (torch.cumsum(act / 1000, dim=2) on the CPU).  c1: (3, h, w) fp32 scratch.  Also the pole-row sums (first / last row).
+__global__ void k_env_act_scan_y(const float* __restrict__ bg, int h, int w, float brightness, float mul, float* __restrict__ c1,
+                                 float* __restrict__ act_out, double* __restrict__ pole) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = idx / w, x = idx - k * w;
+  double top = 0.0, bot = 0.0;
+  if (k < 3) {
+    double run = 0.0;
+    for (int y = 0; y < h; ++y) {
+      const size_t o = ((size_t)k * h + y) * w + x;
+      const float a = expf(fminf(__fadd_rn(brightness, __fmul_rn(mul, bg[o])), 20.0f));   // two roundings, like the two torch ops
+      if (act_out) act_out[o] = a;
+      if (y == 0) top = (double)a;
+      if (y == h - 1) bot = (double)a;
+      run += (double)(a / 1000.0f);
+      c1[o] = (float)run;
+    }
+  }
+  // pole rows: mean over the row (integral_equirect.py:498-502) -- warp sum, one atomic per warp and channel
+  const int k0 = __shfl_sync(FULLM, k, 0);
+  const bool uniform = __all_sync(FULLM, k == k0);
+  if (uniform && k0 < 3) {
+    for (int o = 16; o; o >>= 1) { top += __shfl_xor_sync(FULLM, top, o); bot += __shfl_xor_sync(FULLM, bot, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(pole + k0, top); atomicAdd(pole + 3 + k0, bot); }
+  } else if (k < 3) {
+    atomicAdd(pole + k, top); atomicAdd(pole + 3 + k, bot);
+  }
+}
+// pass 2: one warp per (channel, row): inclusive scan over x in fp64 (chunks of 32 with a carried total), rounded to fp32,
+// written channel-last.  sat: [h][w][4]
+__global__ void __launch_bounds__(256) k_env_scan_x(const float* __restrict__ c1, int h, int w, float* __restrict__ sat) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // k * h + y
+  if (row >= 3 * h) return;
+  const int k = row / h, y = row - k * h;
+  const float* p = c1 + (size_t)row * w;
+  double carry = 0.0;
+  for (int x0 = 0; x0 < w; x0 += 32) {
+    const int x = x0 + lane;
+    double v = x < w ? (double)p[x] : 0.0;
+    for (int off = 1; off < 32; off <<= 1) {
+      const double u = __shfl_up_sync(FULLM, v, off);
+      if (lane >= off) v += u;
+    }
+    v += carry;
+    carry = __shfl_sync(FULLM, v, 31);
+    if (x < w) sat[((size_t)y * w + x) * 4 + k] = (float)v;
+  }
+}
+__global__ void k_env_pad(float* __restrict__ sat, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sat[i * 4 + 3] = 0.f;
+}
+
+extern "C" int nmf_env_build_sat(const float* bg_mat, int h, int w, float brightness, float mul, float* scratch_c1, float* act,
+                                 float* sat4, double* pole_sums, void* stream) {
+  if (!bg_mat || !scratch_c1 || !sat4 || !pole_sums || h <= 0 || w <= 0) return NMF_E_ARG;
+  cudaStream_t cs = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(pole_sums, 0, 6 * sizeof(double), cs);
+  if (e != cudaSuccess) return (int)e;
+  k_env_act_scan_y<<<(3 * w + 127) / 128, 128, 0, cs>>>(bg_mat, h, w, brightness, mul, scratch_c1, act, pole_sums);
+  CKL();
+  k_env_scan_x<<<(3 * h * 32 + 255) / 256, 256, 0, cs>>>(scratch_c1, h, w, sat4);
+  CKL();
+  const size_t n = (size_t)h * w;
+  k_env_pad<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(sat4, n);
+  CKL();
+  return NMF_OK;
+}
+
+// ---- occupancy: 3^3 max-pool (padding 1) of clamp(alpha, 0, 1), threshold, bit-fields ----
+// one thread per 32-voxel word of the voxel field: 27 x 32 cached reads of alpha per word.  vox: bit (z*gy + y)*pitch + x
+__global__ void __launch_bounds__(256) k_occ_pool_pack(const float* __restrict__ alpha, int gx, int gy, int gz, int pitch, float thres,
+                                                       uint32_t* __restrict__ vox, float* __restrict__ vol) {
+  const size_t wi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int wpr = pitch >> 5;
+  const size_t n_words = (size_t)gz * gy * wpr;
+  if (wi >= n_words) return;
+  const int xw = (int)(wi % wpr);
+  const int y = (int)((wi / wpr) % gy), z = (int)(wi / ((size_t)wpr * gy));
+  uint32_t bits = 0;
+  for (int b = 0; b < 32; ++b) {
+    const int x = xw * 32 + b;
+    if (x >= gx) break;
+    float m = 0.f;
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int zz = z + dz;
+      if (zz < 0 || zz >= gz) continue;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= gy) continue;
+        const float* r = alpha + ((size_t)zz * gy + yy) * gx;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int xx = x + dx;
+          if (xx < 0 || xx >= gx) continue;
+          m = fmaxf(m, fminf(fmaxf(r[xx], 0.f), 1.f));
+        }
+      }
+    }
+    const bool on = m >= thres;
+    if (on) bits |= 1u << b;
+    if (vol) vol[((size_t)z * gy + y) * gx + x] = on ? 1.f : 0.f;
+  }
+  vox[wi] = bits;
+}
+// cell (x, y, z) = OR of the voxels (x..x+1, y..y+1, z..z+1) that exist: word-parallel (shift by one bit + neighbour word)
+__global__ void __launch_bounds__(256) k_occ_cells(const uint32_t* __restrict__ vox, int gy, int gz, int pitch, uint32_t* __restrict__ cell) {
+  const size_t wi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int wpr = pitch >> 5;
+  const size_t n_words = (size_t)gz * gy * wpr;
+  if (wi >= n_words) return;
+  const int xw = (int)(wi % wpr);
+  const int y = (int)((wi / wpr) % gy), z = (int)(wi / ((size_t)wpr * gy));
+  uint32_t acc = 0;
+  for (int dz = 0; dz <= 1; ++dz) {
+    if (z + dz >= gz) continue;
+    for (int dy = 0; dy <= 1; ++dy) {
+      if (y + dy >= gy) continue;
+      const size_t base = ((size_t)(z + dz) * gy + (y + dy)) * wpr + xw;
+      const uint32_t a = vox[base];
+      const uint32_t nxt = xw + 1 < wpr ? vox[base + 1] : 0u;
+      acc |= a | (a >> 1) | (nxt << 31);
+    }
+  }
+  cell[wi] = acc;
+}
+// coarse cell c (8 fine cells per axis) is set iff a voxel with index in [8c-1, 8c+9] on every axis is set
+__global__ void __launch_bounds__(256) k_occ_coarse(const uint32_t* __restrict__ vox, int gx, int gy, int gz, int pitch, int cw, int ch,
+                                                    int cd, uint32_t* __restrict__ coarse) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = c < cw * ch * cd;
+  bool on = false;
+  if (in) {
+    const int cx = c % cw, cy = (c / cw) % ch, cz = c / (cw * ch);
+    const int x0 = max(8 * cx - 1, 0), x1 = min(8 * cx + 9, gx - 1);
+    for (int z = max(8 * cz - 1, 0); z <= min(8 * cz + 9, gz - 1) && !on; ++z)
+      for (int y = max(8 * cy - 1, 0); y <= min(8 * cy + 9, gy - 1) && !on; ++y) {
+        const size_t row = ((size_t)z * gy + y) * (size_t)pitch;
+        for (int x = x0; x <= x1; ++x) {
+          const size_t i = row + x;
+          if ((vox[i >> 5] >> (i & 31)) & 1u) { on = true; break; }
+        }
+      }
+  }
+  const unsigned m = __ballot_sync(FULLM, on);
+  if ((threadIdx.x & 31) == 0 && (c >> 5) < (cw * ch * cd + 31) / 32) coarse[c >> 5] = m;
+}
+
+extern "C" int nmf_occupancy_from_alpha(const float* alpha, int gx, int gy, int gz, float thres, int pitch, uint32_t* vox,
+                                        uint32_t* cell, uint32_t* coarse, float* volume, void* stream) {
+  if (!alpha || !vox || !cell || gx < 2 || gy < 2 || gz < 2 || pitch < gx || (pitch & 31)) return NMF_E_ARG;
+  cudaStream_t cs = (cudaStream_t)stream;
+  const size_t n_words = (size_t)gz * gy * (pitch >> 5);
+  k_occ_pool_pack<<<(unsigned)((n_words + 255) / 256), 256, 0, cs>>>(alpha, gx, gy, gz, pitch, thres, vox, volume);
+  CKL();
+  k_occ_cells<<<(unsigned)((n_words + 255) / 256), 256, 0, cs>>>(vox, gy, gz, pitch, cell);
+  CKL();
+  if (coarse) {
+    const int cw = (gx + 7) / 8, ch = (gy + 7) / 8, cd = (gz + 7) / 8;
+    const int n = cw * ch * cd;
+    k_occ_coarse<<<((n + 31) / 32 * 32 + 255) / 256, 256, 0, cs>>>(vox, gx, gy, gz, pitch, cw, ch, cd, coarse);
+    CKL();
+  }
+  return NMF_OK;
+}

@@ -203,8 +203,56 @@ class DeviceScene:
             setattr(self.c, name, t.data_ptr())
         return t
 
+    def _pack_factors_cuda(self, state, derivatives=True):
+        """_pack_factors on a CUDA device: nmf_pack_factor (csrc/nmf_repack.cu) writes the channel-last buffers and the
+        smoothed-difference planes straight from the reference-layout parameters, in place when the shapes are unchanged."""
+        from .ops import _p, _stream
+        s, dev = self.c, self.device
+        L = _lib.lib()
+        f32 = lambda t: torch.as_tensor(t).detach().to(device=dev, dtype=torch.float32).contiguous()
+        if "kx25" not in self.keep:
+            kx, ky = derivative_stencils()
+            self.keep["kx25"], self.keep["ky25"] = f32(kx.reshape(25)), f32(ky.reshape(25))
+
+        def buf(name, shape, arr, p):
+            old = self.keep.get(f"{name}{p}")
+            if old is None or tuple(old.shape) != tuple(shape):
+                old = torch.empty(*shape, device=dev, dtype=torch.float32)
+                self.keep[f"{name}{p}"] = old
+            arr[p] = old.data_ptr()
+            return old
+        with torch.cuda.device(dev):
+            for p in range(3):
+                dp, dl = f32(state[f"rf.density_rf.app_plane.{p}"]), f32(state[f"rf.density_rf.app_line.{p}"])
+                ap, al = f32(state[f"rf.app_rf.app_plane.{p}"]), f32(state[f"rf.app_rf.app_line.{p}"])
+                if dp.shape[1] != 16 or ap.shape[1] != 24:
+                    raise _lib.NmfError("kernels are compiled for density_n_comp=16, appearance_n_comp=24")
+                H, W, N = dp.shape[2], dp.shape[3], dl.shape[2]
+                s.plane_w[p], s.plane_h[p], s.line_n[p] = W, H, N
+                dval, lval = buf("dval", (H, W, 16), s.dval, p), buf("lval", (N, 16), s.lval, p)
+                aval, alval = buf("aval", (H, W, 24), s.aval, p), buf("alval", (N, 24), s.alval, p)
+                if derivatives:
+                    dpack, lpack = buf("dpack", (H, W, 48), s.dpack, p), buf("lpack", (N, 4, 8), s.lpack, p)
+                else:
+                    dpack = lpack = None
+                    for name, arr in (("dpack", s.dpack), ("lpack", s.lpack)):
+                        self.keep.pop(f"{name}{p}", None)
+                        arr[p] = None
+                kx, ky = _p(self.keep["kx25"]), _p(self.keep["ky25"])
+                for src, C, h, w, val, pack in ((dp, 16, H, W, dval, dpack), (dl, 16, N, 1, lval, lpack),
+                                                (ap, 24, H, W, aval, None), (al, 24, N, 1, alval, None)):
+                    _lib.check(L.nmf_pack_factor(_p(src), C, h, w, kx, ky, _p(val), _p(pack), _stream()), "nmf_pack_factor")
+        basis = f32(state["rf.basis_mat.weight"])
+        if tuple(basis.shape) != (24, 72):
+            raise _lib.NmfError("kernels are compiled for app_dim=24")
+        self._put("basis_t", basis.t())
+
     def _pack_factors(self, state, derivatives=True):
-        """Reference-layout factors (1,C,H,W) / (1,C,N,1) -> the channel-last buffers of DESIGN.md section 2."""
+        """Reference-layout factors (1,C,H,W) / (1,C,N,1) -> the channel-last buffers of DESIGN.md section 2.  On a CUDA
+        device the hand-written re-pack kernels do it (this runs once per optimiser step in training); the torch version
+        below serves CPU-side containers (the host checks of tests/hostcheck) and is the kernels' reference in the tests."""
+        if self.device.type == "cuda" and not getattr(self, "_torch_pack", False):
+            return self._pack_factors_cuda(state, derivatives)
         s, dev = self.c, self.device
         f32 = lambda t: torch.as_tensor(t).detach().to(device=dev, dtype=torch.float32).contiguous()
         if derivatives:
@@ -293,14 +341,29 @@ class DeviceScene:
         bg = f32(state["bg_module.bg_mat"])
         to64 = lambda k, d: torch.as_tensor(state.get(k, d)).detach().to(device=dev, dtype=torch.float64)
         brightness, mul = to64("bg_module.brightness", 0.0), to64("bg_module.mul", 1.0)
-        act, sat = build_sat(bg, brightness, mul)
         eh, ew = bg.shape[-2], bg.shape[-1]
-        sat4 = torch.zeros(eh, ew, 4, device=dev, dtype=torch.float32)
-        sat4[..., :3] = sat[0].permute(1, 2, 0)
-        self._ptr(s, "env_sat", sat4.contiguous())
+        if dev.type == "cuda" and not getattr(self, "_torch_pack", False):
+            from .ops import _p, _stream
+            sat4 = self.keep.get("env_sat")
+            if sat4 is None or tuple(sat4.shape) != (eh, ew, 4):
+                sat4 = torch.empty(eh, ew, 4, device=dev, dtype=torch.float32)
+                self.keep["env_c1"] = torch.empty(3, eh, ew, device=dev, dtype=torch.float32)
+                self.keep["env_pole"] = torch.zeros(6, device=dev, dtype=torch.float64)
+            act = None
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().nmf_env_build_sat(_p(bg), eh, ew, float(brightness), float(mul), _p(self.keep["env_c1"]), None,
+                                                        _p(sat4), _p(self.keep["env_pole"]), _stream()), "nmf_env_build_sat")
+            pole = (self.keep["env_pole"] / ew).float()
+            top, bot = pole[:3], pole[3:]
+        else:
+            act, sat = build_sat(bg, brightness, mul)
+            sat4 = torch.zeros(eh, ew, 4, device=dev, dtype=torch.float32)
+            sat4[..., :3] = sat[0].permute(1, 2, 0)
+            sat4 = sat4.contiguous()
+            top, bot = act[0, :, 0, :].mean(dim=-1), act[0, :, -1, :].mean(dim=-1)
+        self._ptr(s, "env_sat", sat4)
         s.env_h, s.env_w = eh, ew
         s.env_mipbias = float(to64("bg_module.mipbias", 1.0))
-        top, bot = act[0, :, 0, :].mean(dim=-1), act[0, :, -1, :].mean(dim=-1)
         for i in range(3):
             s.env_top[i] = float(top[i])
             s.env_bot[i] = float(bot[i])
@@ -361,10 +424,39 @@ class DeviceScene:
         nmf_dense_alpha), 3^3 max-pool dilation, threshold -> 0/1 volume (Gz,Gy,Gx); installs it as the occupancy."""
         from . import ops
         gs = self.grid_size if grid_size is None else [int(g) for g in grid_size]
-        alpha = ops.dense_alpha(self, gs).clamp(0, 1)[None, None]
-        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1)[0, 0]
-        vol = (alpha >= self.hp["alpha_mask_thres"]).float()
-        self.set_alpha_volume(vol)
+        alpha = ops.dense_alpha(self, gs)
+        if self.device.type != "cuda" or getattr(self, "_torch_pack", False):
+            alpha = F.max_pool3d(alpha.clamp(0, 1)[None, None], kernel_size=3, padding=1, stride=1)[0, 0]
+            vol = (alpha >= self.hp["alpha_mask_thres"]).float()
+            self.set_alpha_volume(vol)
+            return vol
+        # pool + threshold + the three bit-fields in hand-written kernels (csrc/nmf_repack.cu)
+        from .ops import _p, _stream
+        gx, gy, gz = gs
+        dev, s = self.device, self.c
+        pitch = (gx + 31) // 32 * 32
+        n_words = gz * gy * (pitch // 32)
+        vox = torch.empty(n_words, dtype=torch.int32, device=dev)
+        cell = torch.empty(n_words, dtype=torch.int32, device=dev)
+        vol = torch.empty(gz, gy, gx, device=dev)
+        cdim = [(n + 7) // 8 for n in (gx, gy, gz)]
+        cwords = (cdim[0] * cdim[1] * cdim[2] + 31) // 32
+        coarse = torch.zeros(cwords, dtype=torch.int32, device=dev) if cwords <= 2048 else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().nmf_occupancy_from_alpha(_p(alpha), gx, gy, gz, float(self.hp["alpha_mask_thres"]), pitch, _p(vox),
+                                                           _p(cell), _p(coarse), _p(vol), _stream()), "nmf_occupancy_from_alpha")
+        self.keep["occ_vox"], self.keep["occ_cell"] = vox, cell
+        s.occ_vox, s.occ_cell = vox.data_ptr(), cell.data_ptr()
+        s.ow, s.oh, s.od, s.opitch, s.has_occ = gx, gy, gz, pitch, 1
+        s.occ_coarse, s.ocw, s.och, s.ocd = None, 0, 0, 0
+        if coarse is not None:
+            self.keep["occ_coarse"] = coarse
+            s.occ_coarse = coarse.data_ptr()
+            s.ocw, s.och, s.ocd = cdim
+            size = (self.aabb[1] - self.aabb[0]).cpu()
+            for i, n in enumerate((gx, gy, gz)):
+                s.occ_scale[i] = float((n - 1) / float(size[i]))
+        self.alpha_volume = vol > 0
         return vol
 
     def sh_irradiance(self, G=100, mipval=-5.0):

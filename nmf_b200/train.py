@@ -172,30 +172,37 @@ class MicrofacetGradBuffers:
         self.scene = scene
         self.t = {}
         self.c = _lib.NmfMicrofacetGrads()
-        z = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)
+        self.eh, self.ew = int(s.env_h), int(s.env_w)
+        # every buffer is a view of ONE flat allocation (16-byte aligned segments): zero_() is a single fill per step
+        specs = []
         for p in range(3):
             h, w, n = s.plane_h[p], s.plane_w[p], s.line_n[p]
-            for name, t, arr in ((f"d_plane{p}", z(h, w, 16), self.c.d_plane), (f"d_line{p}", z(n, 16), self.c.d_line),
-                                 (f"a_plane{p}", z(h, w, 24), self.c.a_plane), (f"a_line{p}", z(n, 24), self.c.a_line),
-                                 (f"gpack{p}", z(h, w, 48), self.c.normals.gpack), (f"glpack{p}", z(n, 4, 8), self.c.normals.glpack)):
-                self.t[name] = t
-                arr[p] = t.data_ptr()
-        self.eh, self.ew = int(s.env_h), int(s.env_w)
-        for name, shape in (("basis_t", (72, 24)), ("head_w", (11, 24)), ("head_b", (11,)), ("w0t", (66, 64)), ("b0", (64,)),
-                            ("w1t", (64, 64)), ("b1", (64,)), ("w2t", (64, 4)), ("b2", (4,)),
-                            ("gsat", (self.eh * self.ew * 4 + 8,)), ("d_mipbias", (1,))):
-            self.t[name] = z(*shape)
-            setattr(self.c, name, self.t[name].data_ptr())
-        self.t["d_bg"] = z(3, self.eh, self.ew)
-        self.t["d_env_scalars"] = z(2)                   # d brightness, d mul
+            specs += [(f"d_plane{p}", (h, w, 16)), (f"d_line{p}", (n, 16)), (f"a_plane{p}", (h, w, 24)), (f"a_line{p}", (n, 24)),
+                      (f"gpack{p}", (h, w, 48)), (f"glpack{p}", (n, 4, 8))]
+        specs += [("basis_t", (72, 24)), ("head_w", (11, 24)), ("head_b", (11,)), ("w0t", (66, 64)), ("b0", (64,)),
+                  ("w1t", (64, 64)), ("b1", (64,)), ("w2t", (64, 4)), ("b2", (4,)), ("gsat", (self.eh * self.ew * 4 + 8,)),
+                  ("d_mipbias", (1,)), ("d_bg", (3, self.eh, self.ew)), ("d_env_scalars", (2,))]
+        numel = lambda shape: int(math.prod(shape))
+        total = sum((numel(sh) + 3) // 4 * 4 for _, sh in specs)
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        for name, sh in specs:
+            self.t[name] = self.flat[off:off + numel(sh)].view(*sh)
+            off += (numel(sh) + 3) // 4 * 4
+        arrays = dict(d_plane=self.c.d_plane, d_line=self.c.d_line, a_plane=self.c.a_plane, a_line=self.c.a_line,
+                      gpack=self.c.normals.gpack, glpack=self.c.normals.glpack)
+        for name, t in self.t.items():
+            if name[:-1] in arrays and name[-1] in "012":
+                arrays[name[:-1]][int(name[-1])] = t.data_ptr()
+            elif name not in ("d_bg", "d_env_scalars"):
+                setattr(self.c, name, t.data_ptr())
         kx, ky = derivative_stencils()
         self.kx = kx.reshape(25).to(device=dev, dtype=torch.float32).contiguous()
         self.ky = ky.reshape(25).to(device=dev, dtype=torch.float32).contiguous()
         self.finished = False
 
     def zero_(self):
-        for t in self.t.values():
-            t.zero_()
+        self.flat.zero_()
         self.finished = False
 
     def finish(self, bg_mat, brightness, mul):

@@ -268,3 +268,46 @@ def test_calibrate_matches_reference_biases(model):
     torch.manual_seed(3)
     brdf.calibrate(h["feat"].cuda(), torch.tensor(h["brightness"]))
     assert abs(brdf.bias - b["bias"]) < 0.05, (brdf.bias, b["bias"])
+
+
+@pytest.mark.parametrize("name", ["microfacet_g40", "microfacet_noncubic", "forest"])
+def test_repack_kernels_match_the_torch_pack(name):
+    """csrc/nmf_repack.cu (what a training run rebuilds from the parameters after EVERY optimiser step) against the torch
+    restatement of the reference ops it replaces: factor layouts bit-equal, smoothed-difference planes vs F.conv2d
+    (modules/grid_sample_Cinf.py:218-242), the summed-area table vs the fp64-accumulated double cumsum
+    (modules/integral_equirect.py:431-433) incl. an HDR map with non-trivial brightness / mul (forest-derived), the pole rows,
+    and the occupancy bit-fields (voxels, cell OR, coarse) + 0/1 volume vs max_pool3d + threshold (samplers/alphagrid.py:256-261)."""
+    from conftest import device_scene, load_fixture
+    from nmf_b200.scene import DeviceScene
+    fix = load_fixture("microfacet_g40" if name == "forest" else name)
+    if name == "forest":
+        fe = load_fixture("forest_env")
+        fix = dict(fix, state=dict(fix["state"]))
+        for k, v in fe["small_state"].items():
+            fix["state"]["bg_module." + k] = v
+        fix["state"]["bg_module.brightness"] = torch.tensor(1.3, dtype=torch.float64)
+        fix["state"]["bg_module.mul"] = torch.tensor(1.7, dtype=torch.float64)
+    a = device_scene(fix, "cuda:0")
+    DeviceScene._torch_pack = True
+    try:
+        b = device_scene(fix, "cuda:0")
+        vol_b = b.update_alpha_mask()
+    finally:
+        del DeviceScene._torch_pack
+    vol_a = a.update_alpha_mask()
+    for p in range(3):
+        for k in ("dval", "lval", "aval", "alval"):
+            assert torch.equal(a.keep[f"{k}{p}"], b.keep[f"{k}{p}"]), (k, p)
+        for k in ("dpack", "lpack"):
+            x, y = a.keep[f"{k}{p}"], b.keep[f"{k}{p}"].reshape(a.keep[f"{k}{p}"].shape)
+            assert float((x - y).abs().max()) <= 2e-6 * max(1.0, float(y.abs().max())), (k, p, float((x - y).abs().max()))
+    sa, sb = a.keep["env_sat"], b.keep["env_sat"]
+    rel = float(((sa - sb).abs() / (sb.abs() + 1e-6)).max())
+    assert rel < 3e-7, rel                                     # at most the last bit of a prefix (fp64 scan order)
+    for i in range(3):
+        assert abs(a.c.env_top[i] - b.c.env_top[i]) <= 1e-5 * abs(b.c.env_top[i]) and abs(a.c.env_bot[i] - b.c.env_bot[i]) <= 1e-5 * abs(b.c.env_bot[i])
+    assert torch.equal(vol_a, vol_b)
+    for k in ("occ_vox", "occ_cell", "occ_coarse"):
+        assert torch.equal(a.keep[k], b.keep[k]), k
+    assert (a.c.ow, a.c.oh, a.c.od, a.c.opitch, a.c.ocw, a.c.och, a.c.ocd) == (b.c.ow, b.c.oh, b.c.od, b.c.opitch, b.c.ocw, b.c.och, b.c.ocd)
+    assert torch.allclose(a.keep["sh_conv"], b.keep["sh_conv"], rtol=1e-4, atol=1e-5)
