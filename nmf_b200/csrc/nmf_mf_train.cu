@@ -19,8 +19,9 @@
 //   k_mf_mlp_bwd       128 bounce rays per tile: BRDF MLP recomputed in fp32, walked back; the weight gradients are tile
 //                      contractions over the rays kept in registers across the CTA's tiles (one flush per CTA), d feature
 //                      segment-summed to the sample
-//   k_mf_sample_bwd<L> per surviving sample: material heads, basis_mat (tile contractions), appearance factors, the normal path
+//   k_mf_sample_bwd<L> per bounce sample: material heads, basis_mat (tile contractions), appearance factors, the normal path
 //                      (orientation loss; bounce direction once detach_N is off) into the derivative-plane gradient images
+//   k_mf_ori_bwd       survivors without a bounce sample but a back-facing normal: orientation loss only
 //   k_mf_composite_bwd<L> warp per ray over ALL its valid samples: reverse scan, softplus', density factors
 // Gradients ACCUMULATE into NmfMicrofacetGrads (the caller zeroes them once per optimiser step and finishes the environment and
 // normal images with nmf_env_lookup_bwd_finish / nmf_vm_normals_bwd_finish).
@@ -575,9 +576,10 @@ struct MfGradPtrs {
   float* gpack[3]; float* glpack[3];
 };
 struct MfSampleBwdArgs {
-  const float* rays; const float* zvals; int n_steps; const Surv* surv; const int* n_surv; int cap_surv;
+  const BSample* bs; const int* n_bs; int cap_bs;             // the bounce samples (dense: every thread has work)
+  const float* rays; const float* zvals; int n_steps; const Surv* surv; const int* n_surv; int cap_surv;   // k_mf_ori_bwd
   const uint32_t* survv; const int* survslot; const float* bgrad; float* vdw;
-  float lambda_ori; int detach_N; float min_rough; MfGradPtrs g;
+  float lambda_ori; int detach_N; float min_rough; MfGradPtrs g; int cap_vs;
 };
 #define SB_T 128
 #define SB_FS 25
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const 
   for (int q = t; q < 11 * 24; q += SB_T) sW[q] = s.head_w[q];
   if (t < 11) sB[t] = s.head_b[t];
   __syncthreads();
-  const int n = min(*a.n_surv, a.cap_surv);
+  const int n = min(*a.n_bs, a.cap_bs);
   for (int base = blockIdx.x * SB_T; base < n; base += gridDim.x * SB_T) {
     const int si = base + t;
     float* fr = F + t * SB_FS; float* dl = DL + t * 12; float* co = CO + t * SB_CS; float* dfr = DF + t * SB_FS;
@@ -603,28 +605,28 @@ __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const 
     for (int i = 0; i < 24; ++i) { fr[i] = 0.f; dfr[i] = 0.f; }
 #pragma unroll
     for (int i = 0; i < 11; ++i) dl[i] = 0.f;
-    const int slot = si < n ? a.survslot[si] : -1;      // -1: nothing to differentiate (no bounce rays, front-facing normal)
-    if (slot != -1 && !(LEVEL == 1 && slot == -2)) {
-      const Surv sv = a.surv[si];
-      const int ray = (int)sv.ray, k = (int)sv.step;
-      float o[3], d[3], p[3], xn[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) { o[i] = __ldg(a.rays + (size_t)ray * 6 + i); d[i] = __ldg(a.rays + (size_t)ray * 6 + 3 + i); }
-      nmf_step_pos(o, d, a.zvals[(size_t)ray * a.n_steps + k], p);
+    const int slot = si < n ? si : -1;
+    // (a slot whose ray range did not fit was never written: the call reports the overflow; its stale record is skipped)
+    if (slot >= 0 && __float_as_int(((const float4*)a.bs[slot].N)->w) > 0 && a.bs[slot].pad < (uint32_t)a.cap_vs) {
+      const BSample* b = a.bs + slot;
+      const float4 q0 = *(const float4*)b->pos, q1 = *(const float4*)b->V;
+      const float p[3] = {q0.x, q0.y, q0.z};
+      const float w_s = q0.w;
+      float xn[3];
       nmf_normalize_xyz(s, p, xn);
       const NmfTaps tp = nmf_vm_taps(s, xn);
       float grad[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) nmf_normal_lane(s, tp, l, grad);
       const nmf_v3 nrm = nmf_normal_from_grad(s, grad);
-      const nmf_v3 V = nmf_mk3(-d[0], -d[1], -d[2]);
+      const nmf_v3 V = nmf_mk3(q1.x, q1.y, q1.z);
       const float vn = nmf_dot(V, nrm);
       const float sgn = vn > 0.f ? 1.f : (vn < 0.f ? -1.f : 0.f);
       float dn[3] = {0.f, 0.f, 0.f};
       if (LEVEL == 0 && a.lambda_ori != 0.f && vn < 0.f) {
         // ori_lambda * sum w min(v.n, 0)^2 (tensor_nerf.py:573-583): to the weight and, through the normal, to the density factors
-        atomicAdd(a.vdw + a.survv[si], a.lambda_ori * vn * vn);
-        const float k2 = a.lambda_ori * sv.w * 2.0f * vn;
+        atomicAdd(a.vdw + b->pad, a.lambda_ori * vn * vn);
+        const float k2 = a.lambda_ori * w_s * 2.0f * vn;
         dn[0] = k2 * V.x; dn[1] = k2 * V.y; dn[2] = k2 * V.z;
       }
       if (slot >= 0) {
@@ -727,6 +729,40 @@ __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const 
       if (acc != 0.f) atomicAdd(a.g.basis_t + idx, acc);
     }
     __syncthreads();
+  }
+}
+
+// survivors WITHOUT a bounce sample whose normal faces away from the viewer (marked -2 by k_shade): only the orientation loss
+// reaches them (tensor_nerf.py:573-583).  Rare once a scene has formed; thread per survivor with an early exit.
+__global__ void __launch_bounds__(128) k_mf_ori_bwd(const NmfScene s, const MfSampleBwdArgs a) {
+  const int n = min(*a.n_surv, a.cap_surv);
+  for (int si = blockIdx.x * blockDim.x + threadIdx.x; si < n; si += gridDim.x * blockDim.x) {
+    if (a.survslot[si] != -2) continue;
+    const Surv sv = a.surv[si];
+    const int ray = (int)sv.ray, k = (int)sv.step;
+    float o[3], d[3], p[3], xn[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { o[i] = __ldg(a.rays + (size_t)ray * 6 + i); d[i] = __ldg(a.rays + (size_t)ray * 6 + 3 + i); }
+    nmf_step_pos(o, d, a.zvals[(size_t)ray * a.n_steps + k], p);
+    nmf_normalize_xyz(s, p, xn);
+    const NmfTaps tp = nmf_vm_taps(s, xn);
+    float grad[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int l = 0; l < 8; ++l) nmf_normal_lane(s, tp, l, grad);
+    const nmf_v3 nrm = nmf_normal_from_grad(s, grad);
+    const nmf_v3 V = nmf_mk3(-d[0], -d[1], -d[2]);
+    const float vn = nmf_dot(V, nrm);
+    if (!(vn < 0.f)) continue;
+    atomicAdd(a.vdw + a.survv[si], a.lambda_ori * vn * vn);
+    const float k2 = a.lambda_ori * sv.w * 2.0f * vn;
+    const float dn[3] = {k2 * V.x, k2 * V.y, k2 * V.z};
+    float dgrad[3];
+    nmf_normal_vec_bwd(s, grad, dn, dgrad);
+    if (dgrad[0] != 0.f || dgrad[1] != 0.f || dgrad[2] != 0.f) {
+      float* gp[3] = {a.g.gpack[0], a.g.gpack[1], a.g.gpack[2]};
+      float* gl[3] = {a.g.glpack[0], a.g.glpack[1], a.g.glpack[2]};
+      nmf_normal_bwd4(s, tp, dgrad, gp, gl);
+    }
   }
 }
 
@@ -873,13 +909,17 @@ extern "C" int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp_i
     gp.a_line[p] = grads->a_line[p]; gp.gpack[p] = grads->normals.gpack[p]; gp.glpack[p] = grads->normals.glpack[p];
   }
   gp.basis_t = grads->basis_t; gp.head_w = grads->head_w; gp.head_b = grads->head_b;
-  MfSampleBwdArgs s0 = {rays, w.zvals0, s.n_steps, w.surv0, w.n_surv, w.cap_surv0, w.survv0, w.survslot0, w.bgrad0, w.vdw0,
-                        tp->lambda_ori, tp->detach_N, tr->min_rough, gp};
+  MfSampleBwdArgs s0 = {w.bs0, w.n_bs, w.cap_bs0, rays, w.zvals0, s.n_steps, w.surv0, w.n_surv, w.cap_surv0, w.survv0, w.survslot0,
+                        w.bgrad0, w.vdw0, tp->lambda_ori, tp->detach_N, tr->min_rough, gp, w.cap_vs0};
   k_mf_sample_bwd<0><<<m_sm_count() * 2, SB_T, SB_FLOATS * sizeof(float), cs>>>(s, s0);
   CKL();
+  if (tp->lambda_ori != 0.f) {
+    k_mf_ori_bwd<<<m_sm_count() * 4, 128, 0, cs>>>(s, s0);
+    CKL();
+  }
   if (retrace) {
-    MfSampleBwdArgs s1 = {w.rays1, w.zvals1, s.n_steps, w.surv1, w.n_surv + 1, w.cap_surv1, w.survv1, w.survslot1, w.bgrad1, w.vdw1,
-                          0.f, tp->detach_N, tr->min_rough, gp};
+    MfSampleBwdArgs s1 = {w.bs1, w.n_bs + 1, w.cap_bs1, w.rays1, w.zvals1, s.n_steps, w.surv1, w.n_surv + 1, w.cap_surv1, w.survv1,
+                          w.survslot1, w.bgrad1, w.vdw1, 0.f, tp->detach_N, tr->min_rough, gp, w.cap_vs1};
     k_mf_sample_bwd<1><<<m_sm_count() * 2, SB_T, SB_FLOATS * sizeof(float), cs>>>(s, s1);
     CKL();
   }
