@@ -133,6 +133,11 @@ typedef struct NmfScene {
   const void* brdf_w1u;
   const void* brdf_w2u;
   int mlp_mode;            /* 0 = tcgen05 kind::f16 (fp16 operands, fp32 accumulate), 1 = fp32 SIMT */
+  /* the same three weight tiles in BF16 for the reverse pass (csrc/nmf_mlp_tc_bwd.cuh: gradients need fp32's exponent
+   * range); optional: NULL selects the fp32 reverse kernel */
+  const void* brdf_w0b;
+  const void* brdf_w1b;
+  const void* brdf_w2b;
 } NmfScene;
 
 /* per-call render parameters */

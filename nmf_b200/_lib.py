@@ -40,6 +40,7 @@ class NmfScene(C.Structure):
         ("plain_w0", C.c_void_p), ("plain_w1", C.c_void_p),
         ("rays_per_ray", C.c_int), ("max_brdf_rays1", C.c_int), ("max_retrace", C.c_int), ("model", C.c_int),
         ("brdf_w0u", C.c_void_p), ("brdf_w1u", C.c_void_p), ("brdf_w2u", C.c_void_p), ("mlp_mode", C.c_int),
+        ("brdf_w0b", C.c_void_p), ("brdf_w1b", C.c_void_p), ("brdf_w2b", C.c_void_p),
     ]
 
 

@@ -29,6 +29,7 @@
 
 #include "nmf_render_ws.cuh"
 #include "nmf_microfacet_bwd.cuh"
+#include "nmf_mlp_tc_bwd.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 #define CKL() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
@@ -567,6 +568,202 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mf_mlp_bwd(const NmfScene s,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// BRDF MLP backward on tcgen05 (csrc/nmf_mlp_tc_bwd.cuh): BF16 operands, fp32 accumulators in TMEM, weight gradients
+// accumulated in TMEM over all tiles of the CTA.  scene.mlp_mode == 0 selects it; the fp32 kernel above is mlp_mode == 1.
+// ------------------------------------------------------------------------------------------------
+struct MfMlpTcArgs {
+  const BSample* bs; const uint32_t* owner; const int* ray_count; int cap_rays; const int* tile_start; int n_chunks;
+  const float4* dout; float* bgrad;
+  float* w0t; float* b0; float* w1t; float* b1; float* w2t; float* b2;
+  const void* w0b; const void* w1b; const void* w2b;
+};
+__global__ void __launch_bounds__(MLP_THREADS, 1) k_mf_mlp_bwd_tc(const NmfScene s, const MfMlpTcArgs a) {
+  extern __shared__ __align__(128) char tsm[];
+  TbMlp tc;
+  tb_init(tc, tsm, a.w0b, a.w1b, a.w2b);
+  const int t = threadIdx.x, lane = t & 31;
+  const uint32_t taddr = tc.tmem + ((uint32_t)(t & ~31) << 16);
+  uint4* xrow = (uint4*)(tsm + TB_OFF_X) + t;          // + chunk * 128
+  uint4* h1row = (uint4*)(tsm + TB_OFF_H1) + t;
+  uint4* h2row = (uint4*)(tsm + TB_OFF_H2) + t;
+  uint4* g2row = (uint4*)(tsm + TB_OFF_G2) + t;
+  uint4* g1row = (uint4*)(tsm + TB_OFF_G1) + t;
+  uint4* gorow = (uint4*)(tsm + TB_OFF_GO) + t;
+  const int n_tiles = a.tile_start[a.n_chunks];
+  bool first = true;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int chunk, n, r;
+    mf_locate(a.tile_start, a.n_chunks, a.ray_count, a.cap_rays, tile, t, chunk, n, r);
+    const uint32_t key = r < n ? a.owner[(size_t)chunk * a.cap_rays + r] : NMF_NO_OWNER;
+    const bool active = key != NMF_NO_OWNER;
+    // ---- this ray's input row (BF16) and output gradient ----
+    float x[TC_K0];
+#pragma unroll
+    for (int i = 0; i < TC_K0; ++i) x[i] = 0.f;
+    float4 dout = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+      const BSample* b = a.bs + key;
+      const float4 q1 = *(const float4*)b->V, q2 = *(const float4*)b->N, q4 = *(const float4*)b->diffuse;
+      const nmf_v3 V = nmf_mk3(q1.x, q1.y, q1.z), N = nmf_mk3(q2.x, q2.y, q2.z);
+      const int j = r - (int)__float_as_uint(q4.w);
+      const float4* fq = (const float4*)b->frame;
+      const float4 f0 = fq[0], f1 = fq[1], f2 = fq[2], f3 = fq[3], f4 = fq[4], f5 = fq[5];
+      NmfGGXFrame fr;
+      fr.t = nmf_mk3(f0.x, f0.y, f0.z); fr.b = nmf_mk3(f0.w, f1.x, f1.y); fr.V_l = nmf_mk3(f1.z, f1.w, f2.x);
+      fr.Vs = nmf_mk3(f2.y, f2.z, f2.w); fr.T1 = nmf_mk3(f3.x, f3.y, f3.z); fr.T2 = nmf_mk3(f3.w, f4.x, f4.y);
+      fr.a = f4.z;
+      const float u1 = nmf_wrap01(__ldg(s.sobol + 2 * j) + f5.y), u2 = nmf_wrap01(__ldg(s.sobol + 2 * j + 1) + f5.z);
+      const NmfGGX g = nmf_ggx_sample_f(fr, u1, u2, V, N, q1.w);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float4 f = *(const float4*)(b->feat + 4 * i);
+        x[4 * i] = f.x; x[4 * i + 1] = f.y; x[4 * i + 2] = f.z; x[4 * i + 3] = f.w;
+      }
+      nmf_ish18_s(g.half_l, f4.w, f5.x, &x[24]);
+      x[42] = g.half_l.x; x[43] = g.half_l.y; x[44] = g.half_l.z;
+      nmf_ish18_s(g.diff_l, f4.w, f5.x, &x[45]);
+      x[63] = g.diff_l.x; x[64] = g.diff_l.y; x[65] = g.diff_l.z;
+      x[TC_ONE] = 1.f;
+      dout = a.dout[(size_t)chunk * a.cap_rays + r];
+    }
+#pragma unroll
+    for (int kc = 0; kc < TC_KC; ++kc) {
+      uint4 v;
+      v.x = tb_pack(x[8 * kc], x[8 * kc + 1]); v.y = tb_pack(x[8 * kc + 2], x[8 * kc + 3]);
+      v.z = tb_pack(x[8 * kc + 4], x[8 * kc + 5]); v.w = tb_pack(x[8 * kc + 6], x[8 * kc + 7]);
+      xrow[kc * TC_ROWS] = v;
+      if (kc >= 8) { h1row[kc * TC_ROWS] = v; h2row[kc * TC_ROWS] = v; }      // x64, x65, the constant 1 (biases), zeros
+    }
+    gorow[0] = make_uint4(tb_pack(dout.x, dout.y), tb_pack(dout.z, 0.f), 0u, 0u);
+    gorow[TC_ROWS] = make_uint4(0u, 0u, 0u, 0u);
+    // ---- forward, layer 1 ----
+    tb_publish();
+    if (t == 0) { tc_fence_after(); tb_gemm_kk(tc, TB_COL_D, TB_OFF_X, TB_OFF_W0, 64, TC_KC / 2); tc_commit(tc_smem_u32(tsm + TB_OFF_BAR)); }
+    tb_wait(tc);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float h[32];
+      tc_ld32(taddr + TB_COL_D + 32 * half, h);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        h1row[(4 * half + q) * TC_ROWS] = make_uint4(tb_pack_relu(h[8 * q], h[8 * q + 1]), tb_pack_relu(h[8 * q + 2], h[8 * q + 3]),
+                                                      tb_pack_relu(h[8 * q + 4], h[8 * q + 5]), tb_pack_relu(h[8 * q + 6], h[8 * q + 7]));
+    }
+    // ---- forward, layer 2 ----
+    tb_publish();
+    if (t == 0) { tc_fence_after(); tb_gemm_kk(tc, TB_COL_D, TB_OFF_H1, TB_OFF_W1, 64, TC_KC / 2); tc_commit(tc_smem_u32(tsm + TB_OFF_BAR)); }
+    tb_wait(tc);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float h[32];
+      tc_ld32(taddr + TB_COL_D + 32 * half, h);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        h2row[(4 * half + q) * TC_ROWS] = make_uint4(tb_pack_relu(h[8 * q], h[8 * q + 1]), tb_pack_relu(h[8 * q + 2], h[8 * q + 3]),
+                                                      tb_pack_relu(h[8 * q + 4], h[8 * q + 5]), tb_pack_relu(h[8 * q + 6], h[8 * q + 7]));
+    }
+    // ---- d H2 = dOut W2 (masked below);  d W2^T += H2^T dOut ----
+    tb_publish();
+    if (t == 0) {
+      tc_fence_after();
+      tb_gemm_data(tc, TB_COL_D, TB_OFF_GO, TB_OFF_W2, 16, 64, 1);
+      tb_gemm_wgrad(tc, TB_COL_W2, TB_OFF_H2, TB_OFF_GO, 16, first);
+      tc_commit(tc_smem_u32(tsm + TB_OFF_BAR));
+    }
+    tb_wait(tc);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float h[32];
+      tc_ld32(taddr + TB_COL_D + 32 * half, h);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 m = h2row[(4 * half + q) * TC_ROWS];          // relu mask: the forward activation of this ray
+        const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          o[e] = tb_pack(tb_lo(mm[e]) > 0.f ? h[8 * q + 2 * e] : 0.f, tb_hi(mm[e]) > 0.f ? h[8 * q + 2 * e + 1] : 0.f);
+        g2row[(4 * half + q) * TC_ROWS] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    // ---- d H1 = dH2 W1 (masked below);  d W1^T += H1^T dH2 ----
+    tb_publish();
+    if (t == 0) {
+      tc_fence_after();
+      tb_gemm_data(tc, TB_COL_D, TB_OFF_G2, TB_OFF_W1, 64, 64, 4);
+      tb_gemm_wgrad(tc, TB_COL_W1, TB_OFF_H1, TB_OFF_G2, 64, first);
+      tc_commit(tc_smem_u32(tsm + TB_OFF_BAR));
+    }
+    tb_wait(tc);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float h[32];
+      tc_ld32(taddr + TB_COL_D + 32 * half, h);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 m = h1row[(4 * half + q) * TC_ROWS];
+        const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          o[e] = tb_pack(tb_lo(mm[e]) > 0.f ? h[8 * q + 2 * e] : 0.f, tb_hi(mm[e]) > 0.f ? h[8 * q + 2 * e + 1] : 0.f);
+        g1row[(4 * half + q) * TC_ROWS] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    // ---- d X[:, :32] = dH1 W0;  d W0^T += X^T dH1 ----
+    tb_publish();
+    if (t == 0) {
+      tc_fence_after();
+      tb_gemm_data(tc, TB_COL_D, TB_OFF_G1, TB_OFF_W0, 64, 32, 4);
+      tb_gemm_wgrad(tc, TB_COL_W0, TB_OFF_X, TB_OFF_G1, 64, first);
+      tc_commit(tc_smem_u32(tsm + TB_OFF_BAR));
+    }
+    tb_wait(tc);
+    first = false;
+    {
+      float df[32];
+      tc_ld32(taddr + TB_COL_D, df);
+      const Seg seg = seg_setup(key, lane);
+#pragma unroll
+      for (int k3 = 0; k3 < 8; ++k3) {
+        float v[3] = {active ? df[3 * k3] : 0.f, active ? df[3 * k3 + 1] : 0.f, active ? df[3 * k3 + 2] : 0.f};
+        seg_sum3(v, seg, lane);
+        if (active && seg.head) {
+          float* G = a.bgrad + (size_t)key * NMF_BGRAD + 10 + 3 * k3;
+          atomicAdd(G, v[0]); atomicAdd(G + 1, v[1]); atomicAdd(G + 2, v[2]);
+        }
+      }
+    }
+    // the next tile's stores to the operand tiles are ordered behind this tile's MMAs by the commit / wait above, and behind
+    // every thread's TMEM reads by the tb_publish() barrier that precedes the next MMA
+  }
+  // ---- weight gradients: lane = input index (row 66 = the bias), one atomic per weight per CTA ----
+  if (!first) {
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if ((t & ~31) < TC_ONE + 1) {          // warp-uniform: tcgen05.ld is warp-collective (.sync.aligned)
+      float* dst0 = t < 66 ? a.w0t + (size_t)t * 64 : (t == TC_ONE ? a.b0 : nullptr);
+      float* dst1 = t < 64 ? a.w1t + (size_t)t * 64 : (t == TC_ONE ? a.b1 : nullptr);
+      float* dst2 = t < 64 ? a.w2t + (size_t)t * 4 : (t == TC_ONE ? a.b2 : nullptr);
+      float g[32];
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        tc_ld32(taddr + TB_COL_W0 + 32 * half, g);
+        if (dst0) for (int i = 0; i < 32; ++i) if (g[i] != 0.f) atomicAdd(dst0 + 32 * half + i, g[i]);
+        tc_ld32(taddr + TB_COL_W1 + 32 * half, g);
+        if (dst1) for (int i = 0; i < 32; ++i) if (g[i] != 0.f) atomicAdd(dst1 + 32 * half + i, g[i]);
+      }
+      float g4[4];
+      tc_ld4(taddr + TB_COL_W2, g4);
+      if (dst2) for (int i = 0; i < 3; ++i) if (g4[i] != 0.f) atomicAdd(dst2 + i, g4[i]);
+    }
+  }
+  tb_free(tc);
+}
+
 // ------------------------------------------------------------------------------------------------
 // per surviving sample: material heads, basis_mat, appearance factors, normals
 // (modules/render_modules.py:519-574, fields/tensoRF.py:402-405, fields/tensor_base.py:107-129, tensor_nerf.py:573-583)
@@ -889,18 +1086,28 @@ extern "C" int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp_i
   static bool attr_done = false;
   if (!attr_done) {
     CK(cudaFuncSetAttribute(k_mf_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MB_FLOATS * sizeof(float))));
+    CK(cudaFuncSetAttribute(k_mf_mlp_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_mf_sample_bwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB_FLOATS * sizeof(float))));
     CK(cudaFuncSetAttribute(k_mf_sample_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB_FLOATS * sizeof(float))));
     attr_done = true;
   }
-  MfMlpArgs ma0 = {w.bs0, w.owner0, w.ray_count0, w.cap_rays0, w.tile_start0, nc, w.dout0, w.bgrad0,
-                   grads->w0t, grads->b0, grads->w1t, grads->b1, grads->w2t, grads->b2};
-  k_mf_mlp_bwd<<<m_sm_count(), MLP_THREADS, MB_FLOATS * sizeof(float), cs>>>(s, ma0);
-  CKL();
-  if (retrace) {
-    MfMlpArgs ma1 = {w.bs1, w.owner1, w.ray_count1, w.cap_rays1, w.tile_start1, nc, w.dout1, w.bgrad1,
-                     grads->w0t, grads->b0, grads->w1t, grads->b1, grads->w2t, grads->b2};
-    k_mf_mlp_bwd<<<m_sm_count(), MLP_THREADS, MB_FLOATS * sizeof(float), cs>>>(s, ma1);
+  const bool tc_bwd = s.mlp_mode == 0 && s.brdf_w0b && s.brdf_w1b && s.brdf_w2b;
+  for (int lvl = 0; lvl < (retrace ? 2 : 1); ++lvl) {
+    const BSample* bs = lvl ? w.bs1 : w.bs0;
+    const uint32_t* owner = lvl ? w.owner1 : w.owner0;
+    const int* rc = lvl ? w.ray_count1 : w.ray_count0;
+    const int cap = lvl ? w.cap_rays1 : w.cap_rays0;
+    const int* ts = lvl ? w.tile_start1 : w.tile_start0;
+    const float4* dout = lvl ? w.dout1 : w.dout0;
+    float* bgrad = lvl ? w.bgrad1 : w.bgrad0;
+    if (tc_bwd) {
+      MfMlpTcArgs ma = {bs, owner, rc, cap, ts, nc, dout, bgrad, grads->w0t, grads->b0, grads->w1t, grads->b1, grads->w2t, grads->b2,
+                        s.brdf_w0b, s.brdf_w1b, s.brdf_w2b};
+      k_mf_mlp_bwd_tc<<<m_sm_count(), MLP_THREADS, TB_SMEM_BYTES, cs>>>(s, ma);
+    } else {
+      MfMlpArgs ma = {bs, owner, rc, cap, ts, nc, dout, bgrad, grads->w0t, grads->b0, grads->w1t, grads->b1, grads->w2t, grads->b2};
+      k_mf_mlp_bwd<<<m_sm_count(), MLP_THREADS, MB_FLOATS * sizeof(float), cs>>>(s, ma);
+    }
     CKL();
   }
   MfGradPtrs gp;

@@ -165,6 +165,8 @@ class DeviceScene:
                 wp[:w.shape[0], :w.shape[1]] = w
                 wp[:w.shape[0], 66] = self.keep[f"brdf_b{i}"]
                 self._ptr(s, f"brdf_w{i}u", wp.half().view(rows, 10, 8).permute(1, 0, 2).contiguous())
+                # the same tile in BF16 for the reverse pass (csrc/nmf_mlp_tc_bwd.cuh)
+                self._ptr(s, f"brdf_w{i}b", wp.bfloat16().view(rows, 10, 8).permute(1, 0, 2).contiguous())
             if self.hp.get("mlp", "f16") not in ("f16", "fp32"):
                 raise _lib.NmfError("mlp must be 'f16' (tcgen05, fp16 operands / fp32 accumulate) or 'fp32' (SIMT)")
             s.mlp_mode = 0 if self.hp.get("mlp", "f16") == "f16" else 1

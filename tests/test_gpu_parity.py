@@ -127,6 +127,7 @@ FLOAT_TOL = {  # key: (abs err on >= 99% of pixels, mean abs err, MAX abs err ov
 
 def compare_images(ims, ref, tol=FLOAT_TOL):
     report = {}
+    tol = {k: (v if len(v) == 3 else (v[0], v[1], 5 * v[0])) for k, v in tol.items()}     # (q99, mean, max); max defaults to 5 x q99
     for k, (tmax, tmean, tall) in tol.items():
         if k not in ref:
             continue
