@@ -26,6 +26,7 @@
 // Gradients ACCUMULATE into NmfMicrofacetGrads (the caller zeroes them once per optimiser step and finishes the environment and
 // normal images with nmf_env_lookup_bwd_finish / nmf_vm_normals_bwd_finish).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "nmf_render_ws.cuh"
 #include "nmf_microfacet_bwd.cuh"
@@ -579,6 +580,7 @@ struct MfMlpTcArgs {
   float* w0t; float* b0; float* w1t; float* b1; float* w2t; float* b2;
   const void* w0b; const void* w1b; const void* w2b;
 };
+template <int MIXED>
 __global__ void __launch_bounds__(MLP_THREADS, 1) k_mf_mlp_bwd_tc(const NmfScene s, const MfMlpTcArgs a) {
   extern __shared__ __align__(128) char tsm[];
   TbMlp tc;
@@ -631,8 +633,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mf_mlp_bwd_tc(const NmfScene
 #pragma unroll
     for (int kc = 0; kc < TC_KC; ++kc) {
       uint4 v;
-      v.x = tb_pack(x[8 * kc], x[8 * kc + 1]); v.y = tb_pack(x[8 * kc + 2], x[8 * kc + 3]);
-      v.z = tb_pack(x[8 * kc + 4], x[8 * kc + 5]); v.w = tb_pack(x[8 * kc + 6], x[8 * kc + 7]);
+      if (MIXED) {
+        v.x = tc_pack(x[8 * kc], x[8 * kc + 1]); v.y = tc_pack(x[8 * kc + 2], x[8 * kc + 3]);
+        v.z = tc_pack(x[8 * kc + 4], x[8 * kc + 5]); v.w = tc_pack(x[8 * kc + 6], x[8 * kc + 7]);
+      } else {
+        v.x = tb_pack(x[8 * kc], x[8 * kc + 1]); v.y = tb_pack(x[8 * kc + 2], x[8 * kc + 3]);
+        v.z = tb_pack(x[8 * kc + 4], x[8 * kc + 5]); v.w = tb_pack(x[8 * kc + 6], x[8 * kc + 7]);
+      }
       xrow[kc * TC_ROWS] = v;
       if (kc >= 8) { h1row[kc * TC_ROWS] = v; h2row[kc * TC_ROWS] = v; }      // x64, x65, the constant 1 (biases), zeros
     }
@@ -640,7 +647,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mf_mlp_bwd_tc(const NmfScene
     gorow[TC_ROWS] = make_uint4(0u, 0u, 0u, 0u);
     // ---- forward, layer 1 ----
     tb_publish();
-    if (t == 0) { tc_fence_after(); tb_gemm_kk(tc, TB_COL_D, TB_OFF_X, TB_OFF_W0, 64, TC_KC / 2); tc_commit(tc_smem_u32(tsm + TB_OFF_BAR)); }
+    if (t == 0) { tc_fence_after(); tb_gemm_kk<MIXED>(tc, TB_COL_D, TB_OFF_X, TB_OFF_W0, 64, TC_KC / 2); tc_commit(tc_smem_u32(tsm + TB_OFF_BAR)); }
     tb_wait(tc);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -648,12 +655,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mf_mlp_bwd_tc(const NmfScene
       tc_ld32(taddr + TB_COL_D + 32 * half, h);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        h1row[(4 * half + q) * TC_ROWS] = make_uint4(tb_pack_relu(h[8 * q], h[8 * q + 1]), tb_pack_relu(h[8 * q + 2], h[8 * q + 3]),
-                                                      tb_pack_relu(h[8 * q + 4], h[8 * q + 5]), tb_pack_relu(h[8 * q + 6], h[8 * q + 7]));
+        h1row[(4 * half + q) * TC_ROWS] = MIXED
+            ? make_uint4(tc_pack_relu(h[8 * q], h[8 * q + 1]), tc_pack_relu(h[8 * q + 2], h[8 * q + 3]),
+                         tc_pack_relu(h[8 * q + 4], h[8 * q + 5]), tc_pack_relu(h[8 * q + 6], h[8 * q + 7]))
+            : make_uint4(tb_pack_relu(h[8 * q], h[8 * q + 1]), tb_pack_relu(h[8 * q + 2], h[8 * q + 3]),
+                         tb_pack_relu(h[8 * q + 4], h[8 * q + 5]), tb_pack_relu(h[8 * q + 6], h[8 * q + 7]));
     }
     // ---- forward, layer 2 ----
     tb_publish();
-    if (t == 0) { tc_fence_after(); tb_gemm_kk(tc, TB_COL_D, TB_OFF_H1, TB_OFF_W1, 64, TC_KC / 2); tc_commit(tc_smem_u32(tsm + TB_OFF_BAR)); }
+    if (t == 0) { tc_fence_after(); tb_gemm_kk<MIXED>(tc, TB_COL_D, TB_OFF_H1, TB_OFF_W1, 64, TC_KC / 2); tc_commit(tc_smem_u32(tsm + TB_OFF_BAR)); }
     tb_wait(tc);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -661,15 +671,18 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mf_mlp_bwd_tc(const NmfScene
       tc_ld32(taddr + TB_COL_D + 32 * half, h);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        h2row[(4 * half + q) * TC_ROWS] = make_uint4(tb_pack_relu(h[8 * q], h[8 * q + 1]), tb_pack_relu(h[8 * q + 2], h[8 * q + 3]),
-                                                      tb_pack_relu(h[8 * q + 4], h[8 * q + 5]), tb_pack_relu(h[8 * q + 6], h[8 * q + 7]));
+        h2row[(4 * half + q) * TC_ROWS] = MIXED
+            ? make_uint4(tc_pack_relu(h[8 * q], h[8 * q + 1]), tc_pack_relu(h[8 * q + 2], h[8 * q + 3]),
+                         tc_pack_relu(h[8 * q + 4], h[8 * q + 5]), tc_pack_relu(h[8 * q + 6], h[8 * q + 7]))
+            : make_uint4(tb_pack_relu(h[8 * q], h[8 * q + 1]), tb_pack_relu(h[8 * q + 2], h[8 * q + 3]),
+                         tb_pack_relu(h[8 * q + 4], h[8 * q + 5]), tb_pack_relu(h[8 * q + 6], h[8 * q + 7]));
     }
     // ---- d H2 = dOut W2 (masked below);  d W2^T += H2^T dOut ----
     tb_publish();
     if (t == 0) {
       tc_fence_after();
-      tb_gemm_data(tc, TB_COL_D, TB_OFF_GO, TB_OFF_W2, 16, 64, 1);
-      tb_gemm_wgrad(tc, TB_COL_W2, TB_OFF_H2, TB_OFF_GO, 16, first);
+      tb_gemm_data<MIXED>(tc, TB_COL_D, TB_OFF_GO, TB_OFF_W2, 16, 64, 1);
+      tb_gemm_wgrad<MIXED>(tc, TB_COL_W2, TB_OFF_H2, TB_OFF_GO, 16, first);
       tc_commit(tc_smem_u32(tsm + TB_OFF_BAR));
     }
     tb_wait(tc);
@@ -684,7 +697,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mf_mlp_bwd_tc(const NmfScene
         uint32_t o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          o[e] = tb_pack(tb_lo(mm[e]) > 0.f ? h[8 * q + 2 * e] : 0.f, tb_hi(mm[e]) > 0.f ? h[8 * q + 2 * e + 1] : 0.f);
+          o[e] = tb_pack((mm[e] & 0x7fffu) != 0u ? h[8 * q + 2 * e] : 0.f, (mm[e] & 0x7fff0000u) != 0u ? h[8 * q + 2 * e + 1] : 0.f);
         g2row[(4 * half + q) * TC_ROWS] = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
@@ -692,8 +705,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mf_mlp_bwd_tc(const NmfScene
     tb_publish();
     if (t == 0) {
       tc_fence_after();
-      tb_gemm_data(tc, TB_COL_D, TB_OFF_G2, TB_OFF_W1, 64, 64, 4);
-      tb_gemm_wgrad(tc, TB_COL_W1, TB_OFF_H1, TB_OFF_G2, 64, first);
+      tb_gemm_data<MIXED>(tc, TB_COL_D, TB_OFF_G2, TB_OFF_W1, 64, 64, 4);
+      tb_gemm_wgrad<MIXED>(tc, TB_COL_W1, TB_OFF_H1, TB_OFF_G2, 64, first);
       tc_commit(tc_smem_u32(tsm + TB_OFF_BAR));
     }
     tb_wait(tc);
@@ -708,7 +721,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mf_mlp_bwd_tc(const NmfScene
         uint32_t o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          o[e] = tb_pack(tb_lo(mm[e]) > 0.f ? h[8 * q + 2 * e] : 0.f, tb_hi(mm[e]) > 0.f ? h[8 * q + 2 * e + 1] : 0.f);
+          o[e] = tb_pack((mm[e] & 0x7fffu) != 0u ? h[8 * q + 2 * e] : 0.f, (mm[e] & 0x7fff0000u) != 0u ? h[8 * q + 2 * e + 1] : 0.f);
         g1row[(4 * half + q) * TC_ROWS] = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
@@ -716,8 +729,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mf_mlp_bwd_tc(const NmfScene
     tb_publish();
     if (t == 0) {
       tc_fence_after();
-      tb_gemm_data(tc, TB_COL_D, TB_OFF_G1, TB_OFF_W0, 64, 32, 4);
-      tb_gemm_wgrad(tc, TB_COL_W0, TB_OFF_X, TB_OFF_G1, 64, first);
+      tb_gemm_data<MIXED>(tc, TB_COL_D, TB_OFF_G1, TB_OFF_W0, 64, 32, 4);
+      tb_gemm_wgrad<MIXED>(tc, TB_COL_W0, TB_OFF_X, TB_OFF_G1, 64, first);
       tc_commit(tc_smem_u32(tsm + TB_OFF_BAR));
     }
     tb_wait(tc);
@@ -1086,12 +1099,16 @@ extern "C" int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp_i
   static bool attr_done = false;
   if (!attr_done) {
     CK(cudaFuncSetAttribute(k_mf_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MB_FLOATS * sizeof(float))));
-    CK(cudaFuncSetAttribute(k_mf_mlp_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_mf_mlp_bwd_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_mf_mlp_bwd_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_mf_sample_bwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB_FLOATS * sizeof(float))));
     CK(cudaFuncSetAttribute(k_mf_sample_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB_FLOATS * sizeof(float))));
     attr_done = true;
   }
   const bool tc_bwd = s.mlp_mode == 0 && s.brdf_w0b && s.brdf_w1b && s.brdf_w2b;
+  // operand formats of the tcgen05 reverse kernel: 1 (default) = FP16 activations / weights + BF16 gradients, 0 = all BF16
+  static int tc_mixed = -1;
+  if (tc_mixed < 0) { const char* e = getenv("NMF_TC_BWD_MIXED"); tc_mixed = (e && e[0] == '0') ? 0 : 1; }
   for (int lvl = 0; lvl < (retrace ? 2 : 1); ++lvl) {
     const BSample* bs = lvl ? w.bs1 : w.bs0;
     const uint32_t* owner = lvl ? w.owner1 : w.owner0;
@@ -1102,8 +1119,9 @@ extern "C" int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp_i
     float* bgrad = lvl ? w.bgrad1 : w.bgrad0;
     if (tc_bwd) {
       MfMlpTcArgs ma = {bs, owner, rc, cap, ts, nc, dout, bgrad, grads->w0t, grads->b0, grads->w1t, grads->b1, grads->w2t, grads->b2,
-                        s.brdf_w0b, s.brdf_w1b, s.brdf_w2b};
-      k_mf_mlp_bwd_tc<<<m_sm_count(), MLP_THREADS, TB_SMEM_BYTES, cs>>>(s, ma);
+                        tc_mixed ? s.brdf_w0u : s.brdf_w0b, tc_mixed ? s.brdf_w1u : s.brdf_w1b, tc_mixed ? s.brdf_w2u : s.brdf_w2b};
+      if (tc_mixed) k_mf_mlp_bwd_tc<1><<<m_sm_count(), MLP_THREADS, TB_SMEM_BYTES, cs>>>(s, ma);
+      else k_mf_mlp_bwd_tc<0><<<m_sm_count(), MLP_THREADS, TB_SMEM_BYTES, cs>>>(s, ma);
     } else {
       MfMlpArgs ma = {bs, owner, rc, cap, ts, nc, dout, bgrad, grads->w0t, grads->b0, grads->w1t, grads->b1, grads->w2t, grads->b2};
       k_mf_mlp_bwd<<<m_sm_count(), MLP_THREADS, MB_FLOATS * sizeof(float), cs>>>(s, ma);

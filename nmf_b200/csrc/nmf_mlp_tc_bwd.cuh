@@ -43,9 +43,10 @@
 #define TB_COL_W1 128       // d W1^T
 #define TB_COL_W2 192       // d W2^T (16 columns)
 
-// kind::f16 instruction descriptor: D = fp32, A = B = BF16 (format 1), a_major bit 15, b_major bit 16 (1 = MN-major)
-#define TB_IDESC(N, AMN, BMN) ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AMN) << 15) | ((uint32_t)(BMN) << 16) | \
-                               (((uint32_t)(N) >> 3) << 17) | ((128u >> 4) << 24))
+// kind::f16 instruction descriptor: D = fp32, A / B format 0 = F16, 1 = BF16 (bits 7..9 / 10..12), a_major bit 15, b_major
+// bit 16 (1 = MN-major), N >> 3 at bit 17, M >> 4 at bit 24
+#define TB_IDESC(N, AMN, BMN, AF, BF) ((1u << 4) | ((uint32_t)(AF) << 7) | ((uint32_t)(BF) << 10) | ((uint32_t)(AMN) << 15) | \
+                                       ((uint32_t)(BMN) << 16) | (((uint32_t)(N) >> 3) << 17) | ((128u >> 4) << 24))
 
 __device__ __forceinline__ uint32_t tb_pack(float lo, float hi) {
   uint32_t r;
@@ -116,26 +117,31 @@ __device__ __forceinline__ void tb_wait(TbMlp& c) {
 
 // D[128 x n] (+)= A[128 x 16 kchunks...] * B^T, both K-major: activation tile at a_off (K chunks k0 .. k0 + 2 nk), weight tile at
 // w_off with `rows` rows
+// MIXED = 1: activations and weights are the forward's FP16 tiles (the recomputed forward is then bit-identical to
+// k_bounce's, and the weights keep 11 mantissa bits), gradients BF16 (fp32's exponent range); MIXED = 0: everything BF16.
+template <int MIXED>
 __device__ __forceinline__ void tb_gemm_kk(const TbMlp& c, uint32_t col, uint32_t a_off, uint32_t w_off, uint32_t rows, int nk2) {
   const uint32_t a = tc_smem_u32(c.sm + a_off), w = tc_smem_u32(c.sm + w_off);
   for (int k = 0; k < nk2; ++k)
     tc_mma(c.tmem + col, tc_desc(a + k * 2 * (TC_ROWS * 16), TC_ROWS * 16, 128), tc_desc(w + k * 2 * (rows * 16), rows * 16, 128),
-           TB_IDESC(rows, 0, 0), k > 0);
+           TB_IDESC(rows, 0, 0, MIXED ? 0 : 1, MIXED ? 0 : 1), k > 0);
 }
 // D[128 x n] = G[128 x K] * W  with W = a forward weight tile [rows = K][80] read MN-major (mn = input column 0 .. n-1)
+template <int MIXED>
 __device__ __forceinline__ void tb_gemm_data(const TbMlp& c, uint32_t col, uint32_t g_off, uint32_t w_off, uint32_t rows, uint32_t n,
                                              int nk2) {
   const uint32_t g = tc_smem_u32(c.sm + g_off), w = tc_smem_u32(c.sm + w_off);
   // weight tile: (mn = column, k = row) at (mn/8) * rows*16 + (k/8) * 128 + (k%8) * 16: SBO = rows * 16, LBO = 128
   for (int k = 0; k < nk2; ++k)
     tc_mma(c.tmem + col, tc_desc(g + k * 2 * (TC_ROWS * 16), TC_ROWS * 16, 128), tc_desc(w + k * 256, 128, rows * 16),
-           TB_IDESC(n, 0, 1), k > 0);
+           TB_IDESC(n, 0, 1, 1, MIXED ? 0 : 1), k > 0);
 }
 // D[128 (80 real) x n] += T^T * G over the 128 rays: T = activation tile at t_off (mn = its column), G = gradient tile at g_off
 // (mn = its column 0 .. n-1), both MN-major with SBO = 2048 (8-column groups), LBO = 128 (8-ray groups); 8 MMAs of K = 16 rays
+template <int MIXED>
 __device__ __forceinline__ void tb_gemm_wgrad(const TbMlp& c, uint32_t col, uint32_t t_off, uint32_t g_off, uint32_t n, bool first) {
   const uint32_t t = tc_smem_u32(c.sm + t_off), g = tc_smem_u32(c.sm + g_off);
   for (int k = 0; k < 8; ++k)
-    tc_mma(c.tmem + col, tc_desc(t + k * 256, 128, TC_ROWS * 16), tc_desc(g + k * 256, 128, TC_ROWS * 16), TB_IDESC(n, 1, 1),
+    tc_mma(c.tmem + col, tc_desc(t + k * 256, 128, TC_ROWS * 16), tc_desc(g + k * 256, 128, TC_ROWS * 16), TB_IDESC(n, 1, 1, MIXED ? 0 : 1, 1),
            !(first && k == 0));
 }
