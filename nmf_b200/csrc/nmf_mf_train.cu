@@ -1106,9 +1106,11 @@ extern "C" int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp_i
     attr_done = true;
   }
   const bool tc_bwd = s.mlp_mode == 0 && s.brdf_w0b && s.brdf_w1b && s.brdf_w2b;
-  // operand formats of the tcgen05 reverse kernel: 1 (default) = FP16 activations / weights + BF16 gradients, 0 = all BF16
+  // operand formats of the tcgen05 reverse kernel: all BF16.  (FP16 activations / weights with BF16 gradients in one MMA --
+  // a_format != b_format -- was tried on a B200: the launch faults, kind::f16 wants both operands in one format.  The
+  // instantiation is kept behind NMF_TC_BWD_MIXED=1 only as the record of that experiment.)
   static int tc_mixed = -1;
-  if (tc_mixed < 0) { const char* e = getenv("NMF_TC_BWD_MIXED"); tc_mixed = (e && e[0] == '0') ? 0 : 1; }
+  if (tc_mixed < 0) { const char* e = getenv("NMF_TC_BWD_MIXED"); tc_mixed = (e && e[0] == '1') ? 1 : 0; }
   for (int lvl = 0; lvl < (retrace ? 2 : 1); ++lvl) {
     const BSample* bs = lvl ? w.bs1 : w.bs0;
     const uint32_t* owner = lvl ? w.owner1 : w.owner0;

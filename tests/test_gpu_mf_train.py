@@ -40,7 +40,7 @@ def oracle_grads(fix, rays, gt, seed, id0, detach_N, max_samples, min_rough=0.0,
     return osc, ims, st, float(photo.detach())
 
 
-def compare_grads(got, P, tol=5e-3, tol_density=2e-2, tol_scalar=1.5e-2, min_checked=20):
+def compare_grads(got, P, tol=5e-3, tol_density=2e-2, tol_scalar=1.5e-2, min_checked=20, tol_brdf=None):
     rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
     report = {}
     for k, p in P.items():
@@ -52,7 +52,9 @@ def compare_grads(got, P, tol=5e-3, tol_density=2e-2, tol_scalar=1.5e-2, min_che
             continue
         report[k] = rel(g, p.grad.double())
     assert len(report) >= min_checked, (len(report), sorted(report))
-    lim = lambda k: tol_density if "density_rf" in k else (tol_scalar if k in ("bg_module.mipbias", "bg_module.brightness", "bg_module.mul") else tol)
+    lim = lambda k: (tol_density if "density_rf" in k else
+                     (tol_scalar if k in ("bg_module.mipbias", "bg_module.brightness", "bg_module.mul") else
+                      (tol_brdf if (tol_brdf is not None and k.startswith("model.brdf.")) else tol)))
     bad = {k: v for k, v in report.items() if v > lim(k)}
     return report, bad
 
@@ -120,7 +122,10 @@ def test_microfacet_train_step_matches_oracle_gradients(env, name, n, detach_N, 
     g.finish(dsc_bg(fix), *env_scalars(fix))
     got = g.reference_views()
     scale = 4.0 if loose else 1.0
-    report, bad = compare_grads(got, osc.params, tol=3e-3 * scale, tol_density=5e-3 * scale, tol_scalar=1.5e-2 * scale)
+    # tcgen05 reverse MLP (mlp="f16"): BF16 operands (8 mantissa bits) through a three-GEMM chain -- measured 2e-3 (last
+    # layer) .. 1.3e-2 (first layer) on the BRDF weights, 2.8e-3 on what flows on into the appearance factors
+    report, bad = compare_grads(got, osc.params, tol=3e-3 * scale, tol_density=5e-3 * scale, tol_scalar=1.5e-2 * scale,
+                                tol_brdf=2.5e-2 if loose else None)
     print(name, "detach_N" if detach_N else "live_N", "retrace" if retrace else "env", mlp, {k: f"{v:.1e}" for k, v in report.items()})
     assert not bad, bad
 
