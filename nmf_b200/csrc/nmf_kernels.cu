@@ -283,6 +283,10 @@ struct ShadeArgs {
 //           bounce-sample record -- nothing here is computed redundantly by the lanes of a group
 // The kernel is bound by L1 data-pipe wavefronts (profiles/), which is what this structure minimises: a scalar GEMV
 // re-reads both operands from shared memory for every 3 FMAs, the MMA fragments are read once per 8 samples.
+#ifndef NMF_SHADE_UNROLL
+#define NMF_SHADE_UNROLL 1     // experiments: NMF_NVCC_EXTRA=-DNMF_SHADE_UNROLL=2 (build.py)
+#endif
+constexpr int kShadeUnroll = NMF_SHADE_UNROLL;
 #define SHADE_COEF_LD 76       // floats per staged coefficient row: A-fragment reads (row g, col t) are conflict-free
 #define SHADE_FEAT_LD 27       // 24 features + normal per parked sample: lane-per-sample reads are conflict-free
 #define SHADE_SMEM_FLOATS (2 * 72 * 24 + 11 * 24 + 16 + 32 + 8 * 8 * SHADE_COEF_LD + 8 * 32 * SHADE_FEAT_LD)
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
       row[0] = xn[0]; row[1] = xn[1]; row[2] = xn[2];
     }
     __syncwarp();
-#pragma unroll 1
+#pragma unroll kShadeUnroll
     for (int round = 0; round < 8; ++round) {
       float xn[3];
       {
@@ -657,11 +661,14 @@ struct BounceArgs {
   unsigned long long* score_sum; float2* scu;     // level 0: retrace scores
   const int* tile_start;    // [n_chunks + 1] exclusive prefix of the chunks' 128-ray tile counts (k_tile_prefix)
   int n_chunks;
+  const int2* tile_desc;    // [n_tiles] (chunk, first ray) per tile
 };
 
 // tile_start[c] = number of 128-ray tiles in the bounce-ray regions of chunks < c, so that a persistent grid can
-// walk one flat, evenly sized work list instead of a (tiles x chunks) grid with ragged rows
-__global__ void __launch_bounds__(1024) k_tile_prefix(const int* ray_count, int cap_rays, int n_chunks, int* tile_start) {
+// walk one flat, evenly sized work list instead of a (tiles x chunks) grid with ragged rows; tile_desc[t] = (chunk, first
+// ray of the tile within the chunk's region): the consumers read it two tiles ahead instead of searching tile_start (a
+// chain of dependent loads that nothing can overlap: capture K, profiles/r02_b_ncu_summary.md)
+__global__ void __launch_bounds__(1024) k_tile_prefix(const int* ray_count, int cap_rays, int n_chunks, int* tile_start, int2* tile_desc) {
   __shared__ int s_part[1024];
   const int per = (n_chunks + 1023) / 1024;
   const int c0 = threadIdx.x * per;
@@ -681,7 +688,48 @@ __global__ void __launch_bounds__(1024) k_tile_prefix(const int* ray_count, int 
     run += (min(ray_count[c], cap_rays) + MLP_THREADS - 1) / MLP_THREADS;
   }
   if (threadIdx.x == 1023) tile_start[n_chunks] = s_part[1023];
+  __syncthreads();                 // tile_start (global, written by this block) is visible to the block
+  // descriptors: a warp per chunk, lanes across its tiles
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < n_chunks; c += 32) {
+    const int t0 = tile_start[c], nt = (min(ray_count[c], cap_rays) + MLP_THREADS - 1) / MLP_THREADS;
+    for (int k = lane; k < nt; k += 32) tile_desc[t0 + k] = make_int2(c, k * MLP_THREADS);
+  }
 }
+
+// The persistent bounce-ray kernels walk tiles blockIdx.x, + gridDim.x, ...  TileWalk keeps the chain descriptor -> owner
+// off the critical path: the descriptor is loaded two tiles ahead, the owner (whose address needs the descriptor) one tile
+// ahead, so that neither load is consumed in the iteration that issues it.
+struct TileWalk {
+  int2 d_next;            // descriptor of tile + gridDim.x
+  int chunk, n, r;        // current tile
+  uint32_t slot;          // owner of this thread's ray in the current tile
+  int chunk_n, n_n, r_n;  // next tile
+  uint32_t slot_n;
+};
+__device__ __forceinline__ void tw_fetch(const int2 d, const int* ray_count, int cap_rays, const uint32_t* owner, int& chunk, int& n, int& r,
+                                         uint32_t& slot) {
+  chunk = d.x;
+  n = min(__ldg(ray_count + chunk), cap_rays);
+  r = d.y + threadIdx.x;
+  slot = r < n ? __ldg(owner + (size_t)chunk * cap_rays + r) : NMF_NO_OWNER;
+}
+__device__ __forceinline__ void tw_begin(TileWalk& t, const int2* desc, int n_tiles, const int* ray_count, int cap_rays, const uint32_t* owner) {
+  const int tile = blockIdx.x, g = gridDim.x;
+  t.chunk = t.n = t.r = 0; t.slot = NMF_NO_OWNER;
+  t.d_next = make_int2(0, 0);
+  if (tile < n_tiles) tw_fetch(__ldg(desc + tile), ray_count, cap_rays, owner, t.chunk, t.n, t.r, t.slot);
+  if (tile + g < n_tiles) t.d_next = __ldg(desc + tile + g);
+}
+// at the top of iteration `tile`: issue the next tile's owner load and the descriptor load of the tile after it
+__device__ __forceinline__ void tw_issue(TileWalk& t, int tile, const int2* desc, int n_tiles, const int* ray_count, int cap_rays,
+                                         const uint32_t* owner) {
+  const int g = gridDim.x;
+  t.chunk_n = t.n_n = t.r_n = 0; t.slot_n = NMF_NO_OWNER;
+  if (tile + g < n_tiles) tw_fetch(t.d_next, ray_count, cap_rays, owner, t.chunk_n, t.n_n, t.r_n, t.slot_n);
+  t.d_next = tile + 2 * g < n_tiles ? __ldg(desc + tile + 2 * g) : make_int2(0, 0);
+}
+__device__ __forceinline__ void tw_advance(TileWalk& t) { t.chunk = t.chunk_n; t.n = t.n_n; t.r = t.r_n; t.slot = t.slot_n; }
 
 template <int LEVEL, int TC>
 __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfScene s, const BounceArgs a) {
@@ -696,35 +744,12 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
     xcol = sm + (MLP_SMEM_FLOATS - 66 * MLP_THREADS) + threadIdx.x;
   }
   const int n_tiles = a.tile_start[a.n_chunks];
-  // (chunk, ray index, owning bounce sample) of this thread in a tile; the NEXT tile's are looked up one iteration
-  // ahead and its sample record is prefetched, so that the dependent chain tile -> owner -> record is off the critical
-  // path of the tile that uses it
-  auto locate = [&](int tile, int& chunk, int& n, int& r, uint32_t& slot) {
-    int lo = 0, hi = a.n_chunks;                      // last c with tile_start[c] <= tile
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(a.tile_start + mid) <= tile) lo = mid; else hi = mid;
-    }
-    chunk = lo;
-    n = min(a.ray_count[chunk], a.cap_rays);
-    r = (tile - __ldg(a.tile_start + chunk)) * MLP_THREADS + threadIdx.x;
-    slot = r < n ? a.owner[(size_t)chunk * a.cap_rays + r] : NMF_NO_OWNER;
-  };
-  int chunk = 0, n = 0, r = 0;
-  uint32_t slot = NMF_NO_OWNER;
-  if ((int)blockIdx.x < n_tiles) locate(blockIdx.x, chunk, n, r, slot);
+  TileWalk tw;
+  tw_begin(tw, a.tile_desc, n_tiles, a.ray_count, a.cap_rays, a.owner);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    int chunk_next = 0, n_next = 0, r_next = 0;
-    uint32_t slot_next = NMF_NO_OWNER;
-    if (tile + (int)gridDim.x < n_tiles) {
-      locate(tile + gridDim.x, chunk_next, n_next, r_next, slot_next);
-      if (slot_next != NMF_NO_OWNER) {
-        const char* rec = (const char*)(a.bs + slot_next);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 128));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 256));
-      }
-    }
+    tw_issue(tw, tile, a.tile_desc, n_tiles, a.ray_count, a.cap_rays, a.owner);
+    const int chunk = tw.chunk, n = tw.n, r = tw.r;
+    uint32_t slot = tw.slot;
     BRay* region = a.brays + (size_t)chunk * a.cap_rays;
     const bool active = slot != NMF_NO_OWNER;
     if (!active) slot = 0u;
@@ -757,6 +782,12 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
     if (TC) tc_mlp_forward(tc, x, s.brdf_bias, bw);      // all 128 threads: the tile is one tensor-core GEMM
     else if (active) mlp_simt(sm, xcol, x, s.brdf_bias, bw);
     const float mip = -logf((float)count) - g.logpdf;                    // microfacet.py:445-448
+    if (tw.slot_n != NMF_NO_OWNER) {            // the next tile's sample record: its owner arrived under the MLP above
+      const char* rec = (const char*)(a.bs + tw.slot_n);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 128));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 256));
+    }
     if (LEVEL == 0) {
       float sc = 0.f;
       if (active) {
@@ -782,7 +813,7 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
       *(float4*)o->L = make_float4(g.L.x, g.L.y, g.L.z, mip);
       *(float4*)o->bw = make_float4(bw[0], bw[1], bw[2], __int_as_float(-1));
     }
-    chunk = chunk_next; n = n_next; r = r_next; slot = slot_next;
+    tw_advance(tw);
   }
   if (TC) tc_mlp_free(tc);
 }
@@ -799,6 +830,7 @@ struct SelectArgs {
 
 __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
   __shared__ unsigned hist[2048];
+  __shared__ unsigned warp_tot[32];
   __shared__ unsigned sh_prefix, sh_need, sh_slot, sh_eq;
   const int chunk = blockIdx.x;
   const int n = min(a.ray_count[chunk], a.cap_rays);
@@ -841,15 +873,42 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) {
-      unsigned cum = 0;
-      int b = bins - 1;
-      for (; b > 0; --b) {
-        if (cum + hist[b] >= need) break;
-        cum += hist[b];
+    // largest bin b whose suffix count reaches `need` (b = 0 if none does): block-wide scan over the bins in descending
+    // order, two bins per thread (a serial walk by one thread cost ~30 us per pass: 2048 dependent shared loads)
+    {
+      const int i0 = 2 * threadIdx.x;                                // descending position: bin = bins - 1 - i
+      const unsigned h0 = i0 < bins ? hist[bins - 1 - i0] : 0u, h1 = i0 + 1 < bins ? hist[bins - 2 - i0] : 0u;
+      unsigned incl = h0 + h1;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned v = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += v;
       }
-      sh_prefix = (prefix << (pass == 0 ? 0 : (pass == 1 ? 11 : 10))) | (unsigned)b;
-      sh_need = need - cum;
+      if (lane == 31) warp_tot[threadIdx.x >> 5] = incl;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        unsigned t = warp_tot[threadIdx.x];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const unsigned v = __shfl_up_sync(FULL, t, off);
+          if (lane >= off) t += v;
+        }
+        warp_tot[threadIdx.x] = t;                                    // inclusive totals of the warps
+        if (threadIdx.x == 31) {                                      // default: nothing reaches `need` -> bin 0
+          sh_prefix = prefix << (pass == 0 ? 0 : (pass == 1 ? 11 : 10));
+          sh_need = need - (t - hist[0]);
+        }
+      }
+      __syncthreads();
+      const unsigned excl = incl - (h0 + h1) + ((threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0u);
+      int hit = -1;
+      unsigned cum = 0;
+      if (i0 < bins - 1 && excl < need && need <= excl + h0) { hit = bins - 1 - i0; cum = excl; }
+      else if (i0 + 1 < bins - 1 && excl + h0 < need && need <= excl + h0 + h1) { hit = bins - 2 - i0; cum = excl + h0; }
+      if (hit > 0) {
+        sh_prefix = (prefix << (pass == 0 ? 0 : (pass == 1 ? 11 : 10))) | (unsigned)hit;
+        sh_need = need - cum;
+      }
     }
     __syncthreads();
     prefix = sh_prefix;
@@ -925,28 +984,35 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
 // ================================================================================================
 struct IncomingArgs {
   const BSample* bs; const BRay* brays; const uint32_t* owner; const int* ray_count; int cap_rays; const float* rgb1; int max_retrace;
-  float* accum; const int* tile_start; int n_chunks; float4* red;
+  float* accum; const int* tile_start; int n_chunks; float4* red; const int2* tile_desc;
 };
 template <int LEVEL>
 __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, const IncomingArgs a) {
   const int n_tiles = a.tile_start[a.n_chunks];
   const int lane = threadIdx.x & 31;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    int lo = 0, hi = a.n_chunks;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(a.tile_start + mid) <= tile) lo = mid; else hi = mid;
+  TileWalk tw;
+  tw_begin(tw, a.tile_desc, n_tiles, a.ray_count, a.cap_rays, a.owner);
+  // the ray record's address needs only the tile descriptor: it is loaded one tile ahead (these records stream from DRAM,
+  // written by k_bounce ~3 GB earlier) and the next tile's sample record is pulled into the L2 at the end of the iteration
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 q0 = zero4, q1 = zero4;
+  if (tw.r < tw.n) {
+    const BRay* o = a.brays + (size_t)tw.chunk * a.cap_rays + tw.r;
+    q0 = *(const float4*)o->L; q1 = *(const float4*)o->bw;
+  }
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tw_advance(tw)) {
+    tw_issue(tw, tile, a.tile_desc, n_tiles, a.ray_count, a.cap_rays, a.owner);
+    float4 q0n = zero4, q1n = zero4;
+    if (tw.r_n < tw.n_n) {
+      const BRay* o = a.brays + (size_t)tw.chunk_n * a.cap_rays + tw.r_n;
+      q0n = __ldcs((const float4*)o->L); q1n = __ldcs((const float4*)o->bw);
     }
-    const int chunk = lo;
-    const int n = min(a.ray_count[chunk], a.cap_rays);
-    const int r = (tile - __ldg(a.tile_start + chunk)) * MLP_THREADS + threadIdx.x;
-    uint32_t key = r < n ? a.owner[(size_t)chunk * a.cap_rays + r] : NMF_NO_OWNER;
+    const int chunk = tw.chunk;
+    const uint32_t key = tw.slot;
     const bool active = key != NMF_NO_OWNER;
     float comb[3] = {0.f, 0.f, 0.f}, inc[3] = {0.f, 0.f, 0.f}, bw[3] = {0.f, 0.f, 0.f};
     const BSample* b = a.bs;
     if (active) {
-      const BRay* o = a.brays + (size_t)chunk * a.cap_rays + r;
-      const float4 q0 = *(const float4*)o->L, q1 = *(const float4*)o->bw;
       const int slot = LEVEL == 0 ? __float_as_int(q1.w) : -1;
       b = a.bs + key;
       const nmf_v3 L = nmf_mk3(q0.x, q0.y, q0.z);
@@ -991,6 +1057,12 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
         atomicAdd(acc, sw * comb[0]); atomicAdd(acc + 1, sw * comb[1]); atomicAdd(acc + 2, sw * comb[2]);
       }
     }
+    if (tw.slot_n != NMF_NO_OWNER) {
+      const char* rec = (const char*)(a.bs + tw.slot_n);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));          // V, f0, diffuse, fresn: bytes 16 .. 95
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 64));
+    }
+    q0 = q0n; q1 = q1n;
   }
 }
 
@@ -1434,9 +1506,9 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
 
     // persistent grid over the flat tile list: 5 CTAs per SM with the fp16 operand tiles, 3 with the fp32 SIMT staging
     const int gb = sm_count() * (tcm ? 5 : 3);
-    k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count0, w.cap_rays0, nc, w.tile_start0);
+    k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count0, w.cap_rays0, nc, w.tile_start0, w.tile_desc0);
     CKL();
-    BounceArgs b0 = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.score_sum, w.scu0, w.tile_start0, nc};
+    BounceArgs b0 = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.score_sum, w.scu0, w.tile_start0, nc, w.tile_desc0};
     if (tcm) k_bounce<0, 1><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b0);
     else k_bounce<0, 0><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b0);
     CKL();
@@ -1470,14 +1542,14 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
       else k_shade<1, 0><<<sm_count() * 3, 256, SHADE_SMEM_FLOATS * sizeof(float), stream>>>(s, h1);
       CKL();
       prof_mark(6, stream);
-      k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count1, w.cap_rays1, nc, w.tile_start1);
+      k_tile_prefix<<<1, 1024, 0, stream>>>(w.ray_count1, w.cap_rays1, nc, w.tile_start1, w.tile_desc1);
       CKL();
-      BounceArgs b1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr, nullptr, w.tile_start1, nc};
+      BounceArgs b1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr, nullptr, w.tile_start1, nc, w.tile_desc1};
       if (tcm) k_bounce<1, 1><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b1);
       else k_bounce<1, 0><<<gb, MLP_THREADS, mlp_smem, stream>>>(s, b1);
       CKL();
       prof_mark(7, stream);
-      IncomingArgs i1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr, 0, w.accum1, w.tile_start1, nc, nullptr};
+      IncomingArgs i1 = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, nullptr, 0, w.accum1, w.tile_start1, nc, nullptr, w.tile_desc1};
       k_incoming<1><<<g_inc1, MLP_THREADS, 0, stream>>>(s, i1);
       CKL();
       prof_mark(8, stream);
@@ -1486,7 +1558,7 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
       CKL();
       prof_mark(9, stream);
     }
-    IncomingArgs ia = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.rgb1, s.max_retrace, w.accum0, w.tile_start0, nc, w.red0};
+    IncomingArgs ia = {w.bs0, w.brays0, w.owner0, w.ray_count0, w.cap_rays0, w.rgb1, s.max_retrace, w.accum0, w.tile_start0, nc, w.red0, w.tile_desc0};
     k_incoming<0><<<g_inc0, MLP_THREADS, 0, stream>>>(s, ia);
     CKL();
     prof_mark(10, stream);

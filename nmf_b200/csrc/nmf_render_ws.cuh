@@ -60,6 +60,8 @@ struct WS {
   float* stat4;       // [n_chunks][4] A19 statistics: sum of w*min(v.n,0)^2, of the diffuse map, of the sample tints, of acc
   int* tile_start0;   // [n_chunks + 1]
   int* tile_start1;   // [n_chunks + 1]
+  int2* tile_desc0;   // [n_chunks * ceil(cap_rays0 / 128)] (chunk, first ray) of every 128-ray tile (k_tile_prefix)
+  int2* tile_desc1;
   size_t counters_bytes;
   char* counters_base;
   // level 0
@@ -88,6 +90,7 @@ struct WS {
   size_t total;
 };
 
+#define MLP_THREADS 128            // bounce rays per tile (one tcgen05 M = 128 tile / one thread per ray)
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static inline void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* base, float cap_scale = 1.0f, bool train = false) {
@@ -147,6 +150,8 @@ static inline void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* 
     w.bs1 = (BSample*)take((size_t)w.cap_bs1 * sizeof(BSample));
     w.brays1 = (BRay*)take((size_t)nc * w.cap_rays1 * sizeof(BRay));
     w.owner1 = (uint32_t*)take((size_t)nc * w.cap_rays1 * 4);
+    w.tile_desc0 = (int2*)take((size_t)nc * ((w.cap_rays0 + MLP_THREADS - 1) / MLP_THREADS) * sizeof(int2));
+    w.tile_desc1 = (int2*)take((size_t)nc * ((w.cap_rays1 + MLP_THREADS - 1) / MLP_THREADS) * sizeof(int2));
   }
   w.zvals0 = w.zvals1 = nullptr; w.whole0 = nullptr; w.n_kept = nullptr;
   w.vs0 = w.vs1 = nullptr; w.vdw0 = w.vdw1 = nullptr; w.vbase0 = w.vbase1 = nullptr; w.cap_vs0 = w.cap_vs1 = 0;
@@ -183,8 +188,6 @@ static inline void carve(WS& w, const NmfScene* s, int n_rays, int chunk, char* 
   }
   w.total = off;
 }
-
-#define MLP_THREADS 128            // bounce rays per tile (one tcgen05 M = 128 tile / one thread per ray)
 
 #ifdef __CUDACC__
 // Segments = runs of lanes that share `key` (bounce rays of one sample are consecutive).  seg_setup finds, with one
