@@ -480,6 +480,19 @@ int nmf_env_build_sat(const float* bg_mat, int h, int w, float brightness, float
 int nmf_occupancy_from_alpha(const float* alpha, int gx, int gy, int gz, float thres, int pitch, uint32_t* vox, uint32_t* cell,
                              uint32_t* coarse, float* volume, void* stream);
 
+/* Gradient hand-over after a training step: the kernels accumulate gradients channel-last ([texel][channel]); the
+ * reference's parameters are channel-first ((1,C,H,W) planes, (1,C,N,1) lines, (out,in) linear weights; fields/tensoRF.py:
+ * 42-75, modules/brdf.py:73-120).  One launch moves every tensor: job j writes dst[c * n + i] = src[i * c + ch] (c = 1: a copy).
+ * jobs_dev: device array.  c <= 64. */
+typedef struct NmfTransposeJob {
+  const float* src;
+  float* dst;
+  uint64_t n;      /* rows of src (texels) */
+  int32_t c;       /* columns of src (channels) */
+  int32_t pad;
+} NmfTransposeJob;
+int nmf_transpose_batch(const NmfTransposeJob* jobs_dev, int n_jobs, int blocks_per_job, void* stream);
+
 /* Measurement helper (bench.py): `n_threads` threads (a multiple of 256) each issue `taps` (a multiple of 8) independent
  * 16-byte loads over `buf` (n_elems float4) and write one float4 of `sink` (n_threads float4); `group` (1, 2, 4, 8)
  * consecutive lanes read consecutive pieces of one pseudo-random segment of 16 * group bytes (the granularity of the

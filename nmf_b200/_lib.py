@@ -70,6 +70,10 @@ class NmfMicrofacetGrads(C.Structure):
                 ("normals", NmfNormalGrads)]
 
 
+class NmfTransposeJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_uint64), ("c", C.c_int32), ("pad", C.c_int32)]
+
+
 class NmfMicrofacetTrain(C.Structure):
     _fields_ = [("lambda_pred", C.c_float), ("lambda_ori", C.c_float), ("detach_N", C.c_int), ("loss", C.c_void_p)]
 
@@ -187,6 +191,7 @@ def lib():
         "nmf_env_build_sat": (I, [P, I, I, F, F, P, P, P, P, P]),
         "nmf_occupancy_from_alpha": (I, [P, I, I, I, F, I, P, P, P, P, P]),
         "nmf_bench_gather": (I, [P, C.c_size_t, I, I, I, P, P]),
+        "nmf_transpose_batch": (I, [P, I, I, P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
                                 C.c_size_t, P]),
     }
@@ -206,4 +211,4 @@ EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_pr
             "nmf_render_train_workspace_bytes", "nmf_render_rays_train", "nmf_l1_reg", "nmf_grad_sq_norm", "nmf_adam_step",
             "nmf_env_lookup_bwd_scatter", "nmf_env_lookup_bwd_finish", "nmf_env_lookup_bwd_mipbias", "nmf_vm_normals_bwd_scatter",
             "nmf_vm_normals_bwd_finish", "nmf_material_heads_bwd", "nmf_train_microfacet", "nmf_bench_gather", "nmf_pack_factor", "nmf_env_build_sat",
-            "nmf_occupancy_from_alpha"]
+            "nmf_occupancy_from_alpha", "nmf_transpose_batch"]

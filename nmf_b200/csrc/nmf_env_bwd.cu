@@ -58,31 +58,52 @@ __global__ void __launch_bounds__(SCAN_T) k_env_bwd_scan_x(float4* __restrict__ 
   }
 }
 
-// One thread per (column x, channel k): walks the rows bottom to top (loads do not depend on the running sum, so they pipeline),
-// adds the pole-row means and applies d act -> d bg_mat / d brightness / d mul where the clip at 20 is open.
-__global__ void k_env_bwd_finish(const float* __restrict__ gsat, int h, int w, const float* __restrict__ g_top,
-                                 const float* __restrict__ g_bot, const float* __restrict__ bg, float brightness, float mul,
-                                 float* __restrict__ d_bg, float* d_brightness, float* d_mul) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int x = idx / 3, k = idx - 3 * x;
+// Reverse prefix sum along y.  CTA = 16 columns x 16 row segments, a thread owns one column segment with all three channels
+// (float4 rows): segment totals meet in shared memory, then the segment is walked bottom to top with the carry of everything
+// below it, the pole-row means are added and d act -> d bg_mat / d brightness / d mul is applied where the clip at 20 is
+// open.  (One thread per (column, channel) walking all rows took 524 us at 512 x 1024: 3072 threads on 148 SMs.)
+#define ENVB_SEG 16
+__global__ void __launch_bounds__(256) k_env_bwd_finish(const float* __restrict__ gsat, int h, int w, const float* __restrict__ g_top,
+                                                        const float* __restrict__ g_bot, const float* __restrict__ bg, float brightness,
+                                                        float mul, float* __restrict__ d_bg, float* d_brightness, float* d_mul) {
+  __shared__ float tot[ENVB_SEG][16][3];
+  const int col = threadIdx.x & 15, seg = threadIdx.x >> 4;
+  const int x = blockIdx.x * 16 + col;
+  const int R = (h + ENVB_SEG - 1) / ENVB_SEG;
+  const int y0 = seg * R, y1 = min(y0 + R, h);
+  const float4* g4 = (const float4*)gsat;
+  float run[3] = {0.f, 0.f, 0.f};
+  if (x < w)
+    for (int y = y1 - 1; y >= y0; --y) {
+      const float4 v = g4[(size_t)y * w + x];
+      run[0] += v.x; run[1] += v.y; run[2] += v.z;
+    }
+  for (int k = 0; k < 3; ++k) tot[seg][col][k] = run[k];
+  __syncthreads();
   float sb = 0.f, sm = 0.f;
   if (x < w) {
-    const float top = g_top[k] / (float)w, bot = g_bot[k] / (float)w;
-    float run = 0.f;
-#pragma unroll 8
-    for (int y = h - 1; y >= 0; --y) {
-      run += gsat[((size_t)y * w + x) * 4 + k];
-      float d = run;
-      if (y == 0) d += top;
-      if (y == h - 1) d += bot;
-      const size_t o = ((size_t)k * h + y) * w + x;
-      const float b = bg[o];
-      const float pre = brightness + mul * b;
-      if (pre <= 20.0f) {
-        const float da = d * expf(pre);
-        d_bg[o] += da * mul;
-        sb += da;
-        sm += da * b;
+    for (int k = 0; k < 3; ++k) run[k] = 0.f;
+    for (int sgm = ENVB_SEG - 1; sgm > seg; --sgm)
+      for (int k = 0; k < 3; ++k) run[k] += tot[sgm][col][k];
+    const float top[3] = {g_top[0] / (float)w, g_top[1] / (float)w, g_top[2] / (float)w};
+    const float bot[3] = {g_bot[0] / (float)w, g_bot[1] / (float)w, g_bot[2] / (float)w};
+    for (int y = y1 - 1; y >= y0; --y) {
+      const float4 v = g4[(size_t)y * w + x];
+      run[0] += v.x; run[1] += v.y; run[2] += v.z;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float d = run[k];
+        if (y == 0) d += top[k];
+        if (y == h - 1) d += bot[k];
+        const size_t o = ((size_t)k * h + y) * w + x;
+        const float b = bg[o];
+        const float pre = brightness + mul * b;
+        if (pre <= 20.0f) {
+          const float da = d * expf(pre);
+          d_bg[o] += da * mul;
+          sb += da;
+          sm += da * b;
+        }
       }
     }
   }
@@ -142,8 +163,7 @@ extern "C" int nmf_env_lookup_bwd_finish(float* gsat, int h, int w, const float*
   const float* poles = gsat + (size_t)h * w * 4;
   k_env_bwd_scan_x<<<h, SCAN_T, 0, (cudaStream_t)stream>>>((float4*)gsat, w);
   CKL();
-  const int nt = 3 * w;
-  k_env_bwd_finish<<<(nt + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gsat, h, w, poles, poles + 4, bg_mat, brightness, mul, d_bg_mat,
+  k_env_bwd_finish<<<(w + 15) / 16, 256, 0, (cudaStream_t)stream>>>(gsat, h, w, poles, poles + 4, bg_mat, brightness, mul, d_bg_mat,
                                                                        d_brightness, d_mul);
   CKL();
   return NMF_OK;

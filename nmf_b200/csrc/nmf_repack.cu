@@ -91,33 +91,37 @@ extern "C" int nmf_pack_factor(const float* src, int C, int H, int W, const floa
 }
 
 // ---- environment: activation + summed-area table ----
-// pass 1: one thread per (channel, column): act, and the running sum over rows in fp64, rounded to fp32 per prefix
-// (torch.cumsum(act / 1000, dim=2) on the CPU).  c1: (3, h, w) fp32 scratch.  Also the pole-row sums (first / last row).
-__global__ void k_env_act_scan_y(const float* __restrict__ bg, int h, int w, float brightness, float mul, float* __restrict__ c1,
-                                 float* __restrict__ act_out, double* __restrict__ pole) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = idx / w, x = idx - k * w;
-  double top = 0.0, bot = 0.0;
-  if (k < 3) {
-    double run = 0.0;
-    for (int y = 0; y < h; ++y) {
-      const size_t o = ((size_t)k * h + y) * w + x;
-      const float a = expf(fminf(__fadd_rn(brightness, __fmul_rn(mul, bg[o])), 20.0f));   // two roundings, like the two torch ops
-      if (act_out) act_out[o] = a;
-      if (y == 0) top = (double)a;
-      if (y == h - 1) bot = (double)a;
-      run += (double)(a / 1000.0f);
-      c1[o] = (float)run;
-    }
-  }
-  // pole rows: mean over the row (integral_equirect.py:498-502) -- warp sum, one atomic per warp and channel
-  const int k0 = __shfl_sync(FULLM, k, 0);
-  const bool uniform = __all_sync(FULLM, k == k0);
-  if (uniform && k0 < 3) {
-    for (int o = 16; o; o >>= 1) { top += __shfl_xor_sync(FULLM, top, o); bot += __shfl_xor_sync(FULLM, bot, o); }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(pole + k0, top); atomicAdd(pole + 3 + k0, bot); }
-  } else if (k < 3) {
-    atomicAdd(pole + k, top); atomicAdd(pole + 3 + k, bot);
+// pass 1: act and the running sum over rows in fp64, rounded to fp32 per prefix (torch.cumsum(act / 1000, dim=2) on the
+// CPU).  CTA = 16 columns x 16 row segments of one channel: every thread sums its segment, the segment totals meet in
+// shared memory, then the thread walks its rows again with the carry of the segments above (fp64 sums of <= 2048 fp32
+// values: any association agrees with the sequential sum to 1e-16 relative, i.e. the same fp32 after rounding; a single
+// thread per column walking all rows took 259 us at 512 x 1024).  c1: (3, h, w) fp32 scratch.  Also the pole-row sums.
+#define ENV_SEG 16
+__global__ void __launch_bounds__(256) k_env_act_scan_y(const float* __restrict__ bg, int h, int w, float brightness, float mul,
+                                                        float* __restrict__ c1, float* __restrict__ act_out, double* __restrict__ pole) {
+  __shared__ double tot[ENV_SEG][16];
+  const int col = threadIdx.x & 15, seg = threadIdx.x >> 4;
+  const int cpb = (w + 15) / 16;                       // CTAs per channel
+  const int k = blockIdx.x / cpb, x = (blockIdx.x - k * cpb) * 16 + col;
+  const int R = (h + ENV_SEG - 1) / ENV_SEG;
+  const int y0 = seg * R, y1 = min(y0 + R, h);
+  auto act = [&](size_t o) { return expf(fminf(__fadd_rn(brightness, __fmul_rn(mul, bg[o])), 20.0f)); };   // two roundings, like the two torch ops
+  double run = 0.0;
+  if (x < w)
+    for (int y = y0; y < y1; ++y) run += (double)(act(((size_t)k * h + y) * w + x) / 1000.0f);
+  tot[seg][col] = run;
+  __syncthreads();
+  if (x >= w) return;
+  run = 0.0;
+  for (int sgm = 0; sgm < seg; ++sgm) run += tot[sgm][col];
+  for (int y = y0; y < y1; ++y) {
+    const size_t o = ((size_t)k * h + y) * w + x;
+    const float a = act(o);
+    if (act_out) act_out[o] = a;
+    if (y == 0) atomicAdd(pole + k, (double)a);        // pole rows: mean over the row (integral_equirect.py:498-502)
+    if (y == h - 1) atomicAdd(pole + 3 + k, (double)a);
+    run += (double)(a / 1000.0f);
+    c1[o] = (float)run;
   }
 }
 // pass 2: one warp per (channel, row): inclusive scan over x in fp64 (chunks of 32 with a carried total), rounded to fp32,
@@ -152,7 +156,7 @@ extern "C" int nmf_env_build_sat(const float* bg_mat, int h, int w, float bright
   cudaStream_t cs = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(pole_sums, 0, 6 * sizeof(double), cs);
   if (e != cudaSuccess) return (int)e;
-  k_env_act_scan_y<<<(3 * w + 127) / 128, 128, 0, cs>>>(bg_mat, h, w, brightness, mul, scratch_c1, act, pole_sums);
+  k_env_act_scan_y<<<3 * ((w + 15) / 16), 256, 0, cs>>>(bg_mat, h, w, brightness, mul, scratch_c1, act, pole_sums);
   CKL();
   k_env_scan_x<<<(3 * h * 32 + 255) / 256, 256, 0, cs>>>(scratch_c1, h, w, sat4);
   CKL();
@@ -255,5 +259,39 @@ extern "C" int nmf_occupancy_from_alpha(const float* alpha, int gx, int gy, int 
     k_occ_coarse<<<((n + 31) / 32 * 32 + 255) / 256, 256, 0, cs>>>(vox, gx, gy, gz, pitch, cw, ch, cd, coarse);
     CKL();
   }
+  return NMF_OK;
+}
+
+// ---- gradient hand-over: channel-last kernel layouts -> the reference's parameter layouts, all tensors in ONE launch ----
+// job j: dst[c * n + i] = src[i * c_dim + c]  (c_dim = 1: a plain copy).  blockIdx.y = job; a CTA moves tiles of 128 rows
+// through shared memory so that both the reads and the writes are coalesced.  (31 torch copy_ launches cost 0.38 ms of
+// host time per training iteration.)
+#define TRB_ROWS 128
+#define TRB_MAXC 64
+__global__ void __launch_bounds__(256) k_transpose_batch(const NmfTransposeJob* __restrict__ jobs) {
+  __shared__ float tile[TRB_ROWS * (TRB_MAXC + 1)];
+  const NmfTransposeJob jb = jobs[blockIdx.y];
+  const int C = jb.c, ld = C + 1;
+  const size_t n = jb.n;
+  if (C == 1) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) jb.dst[i] = jb.src[i];
+    return;
+  }
+  for (size_t r0 = (size_t)blockIdx.x * TRB_ROWS; r0 < n; r0 += (size_t)gridDim.x * TRB_ROWS) {
+    const int rows = (int)min((size_t)TRB_ROWS, n - r0);
+    const float* sp = jb.src + r0 * C;
+    for (int i = threadIdx.x; i < rows * C; i += 256) tile[(i / C) * ld + (i % C)] = sp[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * C; i += 256) {
+      const int c = i / rows, r = i - c * rows;
+      jb.dst[(size_t)c * n + r0 + r] = tile[r * ld + c];
+    }
+    __syncthreads();
+  }
+}
+extern "C" int nmf_transpose_batch(const NmfTransposeJob* jobs_dev, int n_jobs, int blocks_per_job, void* stream) {
+  if (!jobs_dev || n_jobs <= 0 || blocks_per_job <= 0) return NMF_E_ARG;
+  k_transpose_batch<<<dim3((unsigned)blocks_per_job, (unsigned)n_jobs), 256, 0, (cudaStream_t)stream>>>(jobs_dev);
+  CKL();
   return NMF_OK;
 }

@@ -289,16 +289,28 @@ class RenderBuffers:
             dt = torch.int64 if k == "surf_width" else torch.float32
             self.images[k] = torch.empty((n_rays,) + IMAGE_SHAPES[k], dtype=dt, device=dev)
             setattr(self.c_images, k, self.images[k].data_ptr())
+        # every counter (and the training step's loss sums / kept counts) is a view of ONE flat 4-byte-word buffer, so that
+        # the host reads them all with a single device-to-host copy (read_counters) instead of one copy per counter
         self.counters = {}
         self.c_counters = _lib.NmfCounters()
+        sizes = [("loss3", 6), ("n_kept", 2)]          # loss3: three doubles, first = 8-byte aligned
         for k in _lib.COUNTER_FIELDS:
-            n = 2 if k == "n_shaded" else (1 if k == "error" else (4 * self.n_chunks if k == "stat4" else self.n_chunks))
-            self.counters[k] = torch.zeros(n, dtype=torch.float32 if k == "stat4" else torch.int32, device=dev)
+            sizes.append((k, 2 if k == "n_shaded" else (1 if k == "error" else (4 * self.n_chunks if k == "stat4" else self.n_chunks))))
+        self.counter_slices, off = {}, 0
+        for k, n in sizes:
+            self.counter_slices[k] = (off, n)
+            off += (n + 3) // 4 * 4
+        self.counter_flat = torch.zeros(off, dtype=torch.int32, device=dev)
+        for k in _lib.COUNTER_FIELDS:
+            o, n = self.counter_slices[k]
+            v = self.counter_flat[o:o + n]
+            self.counters[k] = v.view(torch.float32) if k == "stat4" else v
             setattr(self.c_counters, k, self.counters[k].data_ptr())
+        self.loss3 = self.counter_flat[0:6].view(torch.float64)
+        self.n_kept = self.counter_flat[self.counter_slices["n_kept"][0]:][:2]
         if train:     # one forward call per batch (chunk = n_rays) + the train-mode distance rows
             nbytes = _lib.lib().nmf_render_train_workspace_bytes(scene.ref(), n_rays, self.cap_scale)
             self.whole_valid = torch.zeros(n_rays, dtype=torch.uint8, device=dev)
-            self.n_kept = torch.zeros(2, dtype=torch.int32, device=dev)
         else:
             nbytes = _lib.lib().nmf_workspace_bytes_scaled(scene.ref(), n_rays, chunk, self.cap_scale)
         if nbytes == 0:
@@ -372,7 +384,7 @@ def render_rays_train(scene, rays, focal, seed=0, ray_id0=0, max_samples=-1, min
                 raise
             buffers = RenderBuffers(scene, n, n, TRAIN_KEYS, cap_scale=buffers.cap_scale * 2, train=True)
             continue
-        kept, m0 = buffers.n_kept.tolist()
+        kept, m0 = host_n_kept(buffers)
         stats.update(buffers=buffers, whole_valid=buffers.whole_valid[:n].bool(), n_kept=kept,
                      n_samples=stats["n_samples"][0], statistics=stats["statistics"][0])
         assert stats["n_samples"][0] == m0, "kept-sample count of the truncation and of the march disagree"
@@ -382,7 +394,12 @@ def render_rays_train(scene, rays, focal, seed=0, ray_id0=0, max_samples=-1, min
 def read_counters(buffers, n, chunk):
     """Synchronises; raises when a device-side list overflowed (results would be incomplete)."""
     nc = (n + chunk - 1) // chunk
-    c = {k: v.cpu() for k, v in buffers.counters.items()}
+    host = buffers.counter_flat.cpu()                  # the one synchronising copy
+    buffers.host_counters = host
+    c = {}
+    for k in _lib.COUNTER_FIELDS:
+        o, m = buffers.counter_slices[k]
+        c[k] = host[o:o + m].view(torch.float32) if k == "stat4" else host[o:o + m]
     err = int(c["error"][0])
     if err:
         msgs = [m for bit, m in _lib.DEV_ERRORS.items() if err & bit]
@@ -392,6 +409,17 @@ def read_counters(buffers, n, chunk):
     out["n_samples"] = [[a, b] for a, b in zip(out["n_samples0"], out["n_samples1"])]
     out["statistics"] = chunk_statistics(c["stat4"][:4 * nc].reshape(nc, 4), out["n_samples0"])
     return out
+
+
+def host_n_kept(buffers):
+    """(kept rays, kept samples) of the last train-mode call, from the host copy read_counters took."""
+    o, m = buffers.counter_slices["n_kept"]
+    return buffers.host_counters[o:o + m].tolist()
+
+
+def host_loss3(buffers):
+    """(photometric sum, sum of acc, orientation sum) of the last nmf_train_microfacet call, from read_counters' host copy."""
+    return buffers.host_counters[0:6].view(torch.float64).tolist()
 
 
 def chunk_statistics(stat4, n_samples0, envmap_reg=None):

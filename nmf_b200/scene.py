@@ -311,7 +311,7 @@ class DeviceScene:
         self._pack_factors(state, derivatives=False)
         self._pack_plain_mlp(state)
 
-    def refresh_microfacet(self, state):
+    def refresh_microfacet(self, state, env_scalars=None):
         """After an optimiser step of model=microfacet_tensorf2: re-packs the factors (with their smoothed-difference
         planes), the material heads / BRDF MLP operands and the environment tables (SAT, pole rows, SH irradiance) from the
         updated parameters; the occupancy is left alone (the reference rebuilds it on its schedule only)."""
@@ -323,6 +323,9 @@ class DeviceScene:
         if "sobol" not in self.keep and keep_sobol is not None:
             self._ptr(self.c, "sobol", keep_sobol)
         if "bg_module.bg_mat" in state:
+            if env_scalars is not None:       # host copies of brightness / mul / mipbias, fetched AFTER the packing kernels
+                state = dict(state)           # above are queued (the fetch synchronises)
+                state.update(env_scalars())
             self._set_env(state, None)
 
     @classmethod
@@ -342,9 +345,15 @@ class DeviceScene:
         f32 = lambda t: torch.as_tensor(t).detach().to(device=dev, dtype=torch.float32).contiguous()
         bg = f32(state["bg_module.bg_mat"])
         to64 = lambda k, d: torch.as_tensor(state.get(k, d)).detach().to(device=dev, dtype=torch.float64)
-        brightness, mul = to64("bg_module.brightness", 0.0), to64("bg_module.mul", 1.0)
+
+        def hostf(k, d):          # python floats pass through without a device round trip (the trainer caches them per step)
+            v = state.get(k, d)
+            return float(v.detach()) if torch.is_tensor(v) else float(v)
         eh, ew = bg.shape[-2], bg.shape[-1]
-        if dev.type == "cuda" and not getattr(self, "_torch_pack", False):
+        cuda_pack = dev.type == "cuda" and not getattr(self, "_torch_pack", False)
+        brightness, mul = (hostf("bg_module.brightness", 0.0), hostf("bg_module.mul", 1.0)) if cuda_pack else \
+            (to64("bg_module.brightness", 0.0), to64("bg_module.mul", 1.0))
+        if cuda_pack:
             from .ops import _p, _stream
             sat4 = self.keep.get("env_sat")
             if sat4 is None or tuple(sat4.shape) != (eh, ew, 4):
@@ -355,7 +364,7 @@ class DeviceScene:
             with torch.cuda.device(dev):
                 _lib.check(_lib.lib().nmf_env_build_sat(_p(bg), eh, ew, float(brightness), float(mul), _p(self.keep["env_c1"]), None,
                                                         _p(sat4), _p(self.keep["env_pole"]), _stream()), "nmf_env_build_sat")
-            pole = (self.keep["env_pole"] / ew).float()
+            pole = (self.keep["env_pole"] / ew).float().cpu()          # ONE device-to-host copy for the six pole means
             top, bot = pole[:3], pole[3:]
         else:
             act, sat = build_sat(bg, brightness, mul)
@@ -365,7 +374,7 @@ class DeviceScene:
             top, bot = act[0, :, 0, :].mean(dim=-1), act[0, :, -1, :].mean(dim=-1)
         self._ptr(s, "env_sat", sat4)
         s.env_h, s.env_w = eh, ew
-        s.env_mipbias = float(to64("bg_module.mipbias", 1.0))
+        s.env_mipbias = hostf("bg_module.mipbias", 1.0)
         for i in range(3):
             s.env_top[i] = float(top[i])
             s.env_bot[i] = float(bot[i])
@@ -466,22 +475,29 @@ class DeviceScene:
         (sh.py:149-157), divided by pi (models/microfacet.py:304-316): (9,3).  Uses the CUDA env lookup."""
         from . import ops
         dev = self.device
-        _t = torch.linspace(0, math.pi, G // 2)
-        _p = torch.linspace(0, 2 * math.pi, G)
-        theta, phi = torch.meshgrid(_t, _p, indexing="ij")
-        dirs = torch.stack([torch.sin(theta) * torch.cos(phi), torch.sin(theta) * torch.sin(phi), torch.cos(theta)],
-                           dim=-1).reshape(-1, 3).to(dev)
-        n = dirs.shape[0]
-        bg = ops.env_lookup(self, dirs, torch.full((n,), mipval, device=dev))
-        x, y, z = dirs.unbind(-1)
-        c2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
-        ev = torch.stack([torch.full_like(x, 0.28209479177387814), 0.4886025119029199 * y, 0.4886025119029199 * z,
-                          0.4886025119029199 * x, c2[0] * (x * y), c2[1] * (y * z), c2[2] * (3 * (z * z) - 1),
-                          c2[3] * (x * z), c2[4] * (x * x - y * y)], dim=-1)
-        st = torch.sin(theta).reshape(n, 1, 1).to(dev)
-        coeffs = 2 * math.pi ** 2 * (bg.reshape(n, 1, 3) * ev.reshape(n, -1, 1) * st).mean(dim=0)
-        al2 = torch.tensor([math.pi] + [2 * math.pi / 3] * 3 + [math.pi / 4] * 5, device=dev)
-        return al2.reshape(-1, 1) * coeffs / math.pi
+        cache = self.keep.get("_sh_quadrature")
+        if cache is None or cache[0] != (G, mipval):
+            # the quadrature is constant: directions, mip level and the (n, 9) weight matrix = SH basis * sin(theta) *
+            # 2 pi^2 / n * the clamped-cosine lobe / pi are built once per scene; every later call is one lookup + one GEMM
+            _t = torch.linspace(0, math.pi, G // 2)
+            _p = torch.linspace(0, 2 * math.pi, G)
+            theta, phi = torch.meshgrid(_t, _p, indexing="ij")
+            dirs = torch.stack([torch.sin(theta) * torch.cos(phi), torch.sin(theta) * torch.sin(phi), torch.cos(theta)],
+                               dim=-1).reshape(-1, 3).to(dev)
+            n = dirs.shape[0]
+            x, y, z = dirs.unbind(-1)
+            c2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+            ev = torch.stack([torch.full_like(x, 0.28209479177387814), 0.4886025119029199 * y, 0.4886025119029199 * z,
+                              0.4886025119029199 * x, c2[0] * (x * y), c2[1] * (y * z), c2[2] * (3 * (z * z) - 1),
+                              c2[3] * (x * z), c2[4] * (x * x - y * y)], dim=-1)
+            st = torch.sin(theta).reshape(n, 1).to(dev)
+            al2 = torch.tensor([math.pi] + [2 * math.pi / 3] * 3 + [math.pi / 4] * 5, device=dev)
+            wq = (ev * st * (2 * math.pi ** 2 / n)) * (al2 / math.pi).reshape(1, 9)
+            cache = ((G, mipval), dirs.contiguous(), torch.full((n,), mipval, device=dev), wq.t().contiguous())
+            self.keep["_sh_quadrature"] = cache
+        _, dirs, mip, wq_t = cache
+        bg = ops.env_lookup(self, dirs, mip)
+        return wq_t @ bg.reshape(-1, 3)
 
     def ref(self):
         return C.byref(self.c)

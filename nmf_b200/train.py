@@ -245,6 +245,40 @@ class MicrofacetGradBuffers:
         g["bg_module.mul"] = self.t["d_env_scalars"][1]
         return g
 
+    def copy_into(self, grads_by_key):
+        """Writes every gradient into `grads_by_key[key]` (contiguous tensors in the reference's parameter shapes, e.g. the
+        views of the flat all-reduce bucket) with ONE nmf_transpose_batch launch; the job table is built once per set of
+        destination pointers and lives on the device."""
+        import numpy as np
+        src = {}
+        for p in range(3):
+            src[f"rf.density_rf.app_plane.{p}"] = (self.t[f"d_plane{p}"], 16)
+            src[f"rf.density_rf.app_line.{p}"] = (self.t[f"d_line{p}"], 16)
+            src[f"rf.app_rf.app_plane.{p}"] = (self.t[f"a_plane{p}"], 24)
+            src[f"rf.app_rf.app_line.{p}"] = (self.t[f"a_line{p}"], 24)
+        src["rf.basis_mat.weight"] = (self.t["basis_t"], 24)
+        for h, rows in HEAD_ROWS.items():
+            src[f"model.diffuse_module.{h}_mlp.0.weight"] = (self.t["head_w"][rows], 1)
+            src[f"model.diffuse_module.{h}_mlp.0.bias"] = (self.t["head_b"][rows], 1)
+        for i, li in enumerate((0, 2, 4)):
+            src[f"model.brdf.mlp.{li}.weight"] = (self.t[f"w{i}t"], self.t[f"w{i}t"].shape[1])
+            src[f"model.brdf.mlp.{li}.bias"] = (self.t[f"b{i}"], 1)
+        src["bg_module.bg_mat"] = (self.t["d_bg"], 1)
+        src["bg_module.mipbias"] = (self.t["d_mipbias"][0:1], 1)
+        src["bg_module.brightness"] = (self.t["d_env_scalars"][0:1], 1)
+        src["bg_module.mul"] = (self.t["d_env_scalars"][1:2], 1)
+        sig = tuple((k, grads_by_key[k].data_ptr()) for k in sorted(grads_by_key))
+        if getattr(self, "_jobs_sig", None) != sig:
+            jobs = (_lib.NmfTransposeJob * len(grads_by_key))()
+            for j, (k, dst) in enumerate(sorted(grads_by_key.items())):
+                t, c = src[k]
+                assert dst.is_contiguous() and t.is_contiguous() and dst.numel() == t.numel() and dst.dtype == torch.float32, k
+                jobs[j].src, jobs[j].dst, jobs[j].n, jobs[j].c = t.data_ptr(), dst.data_ptr(), t.numel() // c, c
+            raw = torch.from_numpy(np.frombuffer(bytes(jobs), dtype=np.uint8).copy())
+            self._jobs_dev, self._jobs_n, self._jobs_sig = raw.to(self.scene.device), len(grads_by_key), sig
+        with torch.cuda.device(self.scene.device):
+            _lib.check(_lib.lib().nmf_transpose_batch(_p(self._jobs_dev), self._jobs_n, 128, _stream()), "nmf_transpose_batch")
+
 
 def train_microfacet(scene, rays, gt, focal=1.0, seed=0, ray_id0=0, max_samples=-1, min_rough=0.0, lambda_pred=3e-4,
                      lambda_ori=0.1, detach_N=True, grads=None, zero_grads=True, buffers=None, check_errors=True):
@@ -274,8 +308,6 @@ def train_microfacet(scene, rays, gt, focal=1.0, seed=0, ray_id0=0, max_samples=
         nr = B if buffers is None else max(B, buffers.n_rays)
         buffers = ops.RenderBuffers(scene, nr, nr, ops.TRAIN_KEYS, cap_scale=cap_scale, train=True,
                                     min_ws_bytes=need if buffers is None else int(need * 1.25))
-    if not hasattr(buffers, "loss3"):
-        buffers.loss3 = torch.zeros(3, dtype=torch.float64, device=scene.device)
     while True:
         rp = _lib.NmfRender(n_rays=B, chunk=B, focal=float(focal), seed=int(seed), ray_id0=int(ray_id0), skip_eps=0.0, t_cut=0.0,
                             white_bg=1, cap_scale=buffers.cap_scale)
@@ -288,26 +320,39 @@ def train_microfacet(scene, rays, gt, focal=1.0, seed=0, ray_id0=0, max_samples=
                                                  C.byref(buffers.c_images), C.byref(buffers.c_counters),
                                                  C.c_void_p(buffers.ws_ptr), buffers.ws_bytes, _stream())
         _lib.check(st, "nmf_train_microfacet")
-        out = dict(buffers=buffers, grads=grads, loss=buffers.loss3, n_kept=buffers.n_kept)
+        out = dict(buffers=buffers, grads=grads, loss=buffers.loss3, n_kept=buffers.n_kept, n_batch=B)
         if not check_errors:
-            return out
+            return out                                         # the caller reads back later: train_microfacet_readback
         try:
             stats = ops.read_counters(buffers, B, B)           # synchronises
         except _lib.NmfOverflow:
             if buffers.cap_scale >= 32 or not zero_grads:
                 raise                                          # (accumulated gradients cannot be rolled back)
-            loss3 = buffers.loss3
             buffers = ops.RenderBuffers(scene, buffers.n_rays, buffers.n_rays, ops.TRAIN_KEYS, cap_scale=buffers.cap_scale * 2,
                                         train=True)
-            buffers.loss3 = loss3
             grads.zero_()
             continue
-        kept, m0 = buffers.n_kept.tolist()
-        loss = buffers.loss3.tolist()
-        out.update(loss_photo=loss[0], sum_acc=loss[1], ori_loss=loss[2], n_rays=kept, n_samples=stats["n_samples"][0],
-                   whole_valid=buffers.whole_valid[:B].bool(), rgb_map=buffers.images["rgb_map"][:kept],
-                   acc_map=buffers.images["acc_map"][:kept], statistics=stats["statistics"][0], counters=stats)
-        return out
+        return _mf_fill_out(out, buffers, stats, B)
+
+
+def _mf_fill_out(out, buffers, stats, B):
+    from . import ops
+    kept, m0 = ops.host_n_kept(buffers)
+    loss = ops.host_loss3(buffers)
+    out.update(loss_photo=loss[0], sum_acc=loss[1], ori_loss=loss[2], n_rays=kept, n_samples=stats["n_samples"][0],
+               whole_valid=buffers.whole_valid[:B].bool(), rgb_map=buffers.images["rgb_map"][:kept],
+               acc_map=buffers.images["acc_map"][:kept], statistics=stats["statistics"][0], counters=stats)
+    return out
+
+
+def train_microfacet_readback(out):
+    """Second half of train_microfacet(check_errors=False): ONE synchronising device-to-host copy of the counters, loss sums
+    and kept counts; raises NmfOverflow when a device-side list overflowed (the accumulated gradients are then incomplete:
+    the caller zeroes them and repeats the call with larger buffers)."""
+    from . import ops
+    B = out["n_batch"]
+    stats = ops.read_counters(out["buffers"], B, B)
+    return _mf_fill_out(out, out["buffers"], stats, B)
 
 
 # configs/model/tensorf.yaml:69-111 (`params:`), the values train.py reads for model=tensorf
@@ -862,8 +907,23 @@ class MicrofacetTrainer(PlainTrainer):
                 (["bg_module.brightness"], self.lr_brightness, None),
                 (["bg_module.mul"], self.lr_mul, self.mul_betas)]
 
+    ENV_SCALARS = ("bg_module.brightness", "bg_module.mul", "bg_module.mipbias")
+
+    def _env_host(self, refresh=False):
+        """(brightness, mul, mipbias) as python floats: they are kernel arguments by value, so each change needs them on the
+        host -- ONE device-to-host copy per optimiser step instead of one per use."""
+        if refresh or getattr(self, "_env_host_cache", None) is None:
+            v = torch.stack([self.params[k].detach().reshape(()).float() for k in self.ENV_SCALARS]).tolist()
+            self._env_host_cache = dict(zip(self.ENV_SCALARS, v))
+        return self._env_host_cache
+
+    def repack(self, rebuild=True):
+        if rebuild:
+            self._env_host_cache = None
+        super().repack(rebuild)
+
     def _refresh_scene(self, st):
-        self.scene.refresh_microfacet(st)
+        self.scene.refresh_microfacet(st, env_scalars=lambda: self._env_host(refresh=True))
 
     def _on_reinit(self):
         self.scene.update_hyper(max_retrace_rays=tuple(self.start_max_retrace))      # Microfacet.reset_counter
@@ -914,15 +974,52 @@ class MicrofacetTrainer(PlainTrainer):
         self.finish_into_bucket()
         return super().apply(n_rays_local, loss_local, normaliser)
 
+    def step(self, rays, gt, ray_ids=None, ray_id0=None, **kw):
+        """One iteration with ONE sub-batch, ordered so that the host's launch work overlaps the device: the training step,
+        the finishing passes and the gradient hand-over are queued back to back, THEN the counters are read (first sync:
+        overflow check, kept rays = the loss normaliser, losses), then all-reduce + FusedAdam + re-pack; the second sync
+        (environment scalars, needed by value for the next forward) comes after the packing kernels are queued."""
+        if self.grads is None:
+            self.grads = MicrofacetGradBuffers(self.scene)
+        self.grads.scene = self.scene
+        id0 = ((self.seed * 7919 + self._calls) << 20) if ray_id0 is None else int(ray_id0)
+        buffers = self.buffers
+        while True:
+            self.grads.zero_()
+            self._subs = 1
+            out = train_microfacet(self.scene, rays, gt, seed=self.seed + self._calls, ray_id0=id0, max_samples=self.max_samples,
+                                   min_rough=self.min_rough, lambda_pred=self.lambda_pred, lambda_ori=self.lambda_ori,
+                                   detach_N=self.detach_N, grads=self.grads, zero_grads=False, buffers=buffers, check_errors=False, **kw)
+            buffers = out["buffers"]
+            self.finish_into_bucket()                  # speculative: overwritten by the repeat if a list overflowed
+            try:
+                train_microfacet_readback(out)
+                break
+            except _lib.NmfOverflow:
+                from . import ops
+                if buffers.cap_scale >= 32:
+                    raise
+                buffers = ops.RenderBuffers(self.scene, buffers.n_rays, buffers.n_rays, ops.TRAIN_KEYS, cap_scale=buffers.cap_scale * 2,
+                                            train=True)
+        self._calls += 1
+        self.buffers = buffers
+        ns = out["n_samples"]
+        out["n_samples_all"] = list(ns)
+        out["n_samples"] = ns[0]
+        if len(ns) > 1 and self.scene.c.max_retrace > 0:
+            self.update_n_samples(ns[1])
+        n, loss = PlainTrainer.apply(self, out["n_rays"], out["loss_photo"])
+        out["mse"] = loss / max(3.0 * n, 1.0)
+        return out
+
     def finish_into_bucket(self):
         """After the last sub-batch of an iteration: the two whole-image finishing passes, then this rank's gradient of every
         parameter (plus the density L1 term) is written into the flat bucket the all-reduce and FusedAdam work on."""
         import torch.distributed as dist
         p = self.params
-        self.grads.finish(p["bg_module.bg_mat"].data, p["bg_module.brightness"].data, p["bg_module.mul"].data)
-        views = self.grads.reference_views()
-        for k, q in p.items():
-            q.grad.copy_(views[k].reshape(q.shape))
+        eh = self._env_host()
+        self.grads.finish(p["bg_module.bg_mat"].data, eh["bg_module.brightness"], eh["bg_module.mul"])
+        self.grads.copy_into({k: q.grad for k, q in p.items()})
         if self.l1_weight > 0:            # train.py:675-678 adds the density L1 term to EVERY sub-batch's loss
             world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
             self.l1_sum.zero_()

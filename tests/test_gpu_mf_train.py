@@ -161,3 +161,23 @@ def test_microfacet_train_step_accumulates_and_is_linear(env):
         err = float((acc.t[k] - ref).abs().max())
         assert err <= 2e-4 * float(ref.abs().max()) + 1e-9, (k, err, float(ref.abs().max()))
         assert float(ref.abs().max()) > 0, k
+
+
+def test_gradient_hand_over_in_one_launch_matches_the_views(env):
+    """nmf_transpose_batch (channel-last kernel layouts -> the reference's parameter layouts, every tensor in one launch)
+    writes exactly what copying MicrofacetGradBuffers.reference_views() tensor by tensor writes: bit-equal."""
+    from nmf_b200 import train
+    fix = load_fixture("microfacet_noncubic")
+    dsc = device_scene(fix, env)
+    rays = fix["rays"][:128].contiguous().cuda()
+    gt = torch.rand(128, 3, generator=torch.Generator().manual_seed(2)).cuda()
+    out = train.train_microfacet(dsc, rays, gt, focal=fix["focal"], seed=1, detach_N=False)
+    g = out["grads"]
+    g.finish(dsc_bg(fix), *env_scalars(fix))
+    views = g.reference_views()
+    dst = {k: torch.full(tuple(v.shape), float("nan"), device="cuda") for k, v in views.items()}
+    g.copy_into(dst)
+    assert len(dst) == 31
+    for k, v in views.items():
+        assert torch.equal(dst[k], v.contiguous()), k
+    assert sum(float(v.abs().max()) > 0 for v in views.values()) >= 25

@@ -17,6 +17,7 @@ state, meta = synthetic.make_scene("lego", grid_size=a.grid)
 tr = train.MicrofacetTrainer(state, meta["aabb"], meta["near_far"], meta["grid_size"], device=dev, max_samples=200000, seed=7,
                              params=dict(train.MICROFACET_REFERENCE_PARAMS))
 tr.alpha_volume = tr.scene.update_alpha_mask()
+tr.update_n_samples = lambda n: None          # fixed re-trace budget (the adaptive controller would move it to ~38 000 after 20 iterations)
 H = W = 800
 focal = synthetic.focal_for(W)
 pose = synthetic.hemisphere_poses(8)[1]
@@ -34,14 +35,11 @@ for it in range(a.steps + 3):
     rec = it >= 3
     ms, out = timed(lambda: tr.accumulate(rays, gt, first=True));
     if rec: add("accumulate (zero + nmf_train_microfacet)", ms)
-    ms, _ = timed(lambda: tr.grads.finish(p["bg_module.bg_mat"].data, p["bg_module.brightness"].data, p["bg_module.mul"].data))
+    eh = tr._env_host()
+    ms, _ = timed(lambda: tr.grads.finish(p["bg_module.bg_mat"].data, eh["bg_module.brightness"], eh["bg_module.mul"]))
     if rec: add("grads.finish (env scans, stencil adjoint)", ms)
-    def to_bucket():
-        views = tr.grads.reference_views()
-        for k, q in p.items():
-            q.grad.copy_(views[k].reshape(q.shape))
-    ms, _ = timed(to_bucket)
-    if rec: add("reference_views -> bucket copies", ms)
+    ms, _ = timed(lambda: tr.grads.copy_into({k: q.grad for k, q in p.items()}))
+    if rec: add("gradient hand-over -> bucket (nmf_transpose_batch)", ms)
     def l1():
         if tr.l1_weight > 0:
             tr.l1_sum.zero_()
@@ -53,6 +51,8 @@ for it in range(a.steps + 3):
     ms, _ = timed(lambda: tr.optimizer.step(grad_scale=1.0 / a.rays))
     if rec: add("FusedAdam", ms)
     st = dict(tr.state); st.update({k: q.detach() for k, q in p.items()})
+    ms, _ = timed(lambda: st.update(tr._env_host(refresh=True)))
+    if rec: add("env scalars -> host (one copy)", ms)
     ms, _ = timed(lambda: tr.scene._pack_factors(st, derivatives=True))
     if rec: add("repack: factors", ms)
     ms, _ = timed(lambda: tr.scene._pack_shading(st))
@@ -60,13 +60,19 @@ for it in range(a.steps + 3):
     ms, _ = timed(lambda: tr.scene._set_env(st, None))
     if rec: add("repack: env", ms)
 parts = {k: round(v / a.steps, 4) for k, v in parts.items()}
-# un-instrumented iteration, CUDA events and wall clock
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-torch.cuda.synchronize(); t0 = time.perf_counter(); ev[0].record()
-for it in range(a.steps):
-    tr.step(rays, gt, focal=focal) if False else None
-    out = tr.accumulate(rays, gt, first=True); tr.finish_into_bucket(); tr.bucket.allreduce(scale=1.0)
-    tr.optimizer.step(grad_scale=1.0 / a.rays); tr.repack(rebuild=False)
-ev[1].record(); torch.cuda.synchronize()
-print(json.dumps({"parts_wall_ms_with_sync": parts, "sum_parts": round(sum(parts.values()), 3),
-                  "iteration_event_ms": ev[0].elapsed_time(ev[1]) / a.steps, "iteration_wall_ms": (time.perf_counter() - t0) * 1e3 / a.steps}))
+# un-instrumented iterations, CUDA events and wall clock
+def loop(body):
+    for _ in range(3): body()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize(); t0 = time.perf_counter(); ev[0].record()
+    for it in range(a.steps): body()
+    ev[1].record(); torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / a.steps, (time.perf_counter() - t0) * 1e3 / a.steps
+
+def serial():
+    out = tr.accumulate(rays, gt, first=True); tr.apply(out["n_rays"], out["loss_photo"])
+ev_serial, wall_serial = loop(serial)
+ev_step, wall_step = loop(lambda: tr.step(rays, gt))
+print(json.dumps({"max_retrace": list(tr.scene.hp["max_retrace_rays"]), "parts_wall_ms_with_sync": parts, "sum_parts": round(sum(parts.values()), 3),
+                  "iteration_serial_event_ms": ev_serial, "iteration_serial_wall_ms": wall_serial,
+                  "iteration_step_event_ms": ev_step, "iteration_step_wall_ms": wall_step}))
