@@ -1082,7 +1082,8 @@ def benchmark_sharded_train(grid=300, n_rays=4096, steps=10, device="cuda:0", sc
     """BASELINE config #4 (ship 800x800, ray-batch sharded, NCCL gradient all-reduce): every rank runs one
     MicrofacetTrainer iteration on ITS OWN 4096 rays (weak scaling of the batch: the global batch is world x 4096) --
     nmf_train_microfacet, finish, ONE flat fp32 all-reduce, FusedAdam, re-pack -- and the phases are timed with CUDA
-    events (max over ranks).  Needs torch.distributed initialised (NCCL); world = 1 works too (no collective)."""
+    events (max over ranks; a 4-byte collective in front of the gradient all-reduce takes the arrival skew of the ranks, which
+    render different views, into the forward + backward interval).  Needs torch.distributed initialised (NCCL); world = 1 works too (no collective)."""
     import torch.distributed as dist
     from . import ops, synthetic
     dev = torch.device(device)
@@ -1101,6 +1102,7 @@ def benchmark_sharded_train(grid=300, n_rays=4096, steps=10, device="cuda:0", sc
     ev = lambda: torch.cuda.Event(enable_timing=True)
     acc = dict(step=0.0, allreduce=0.0, update=0.0, total=0.0)
     kept = 0
+    skew = torch.zeros(1, device=dev)
     for it in range(steps + 3):
         e = [ev() for _ in range(5)]
         if on:
@@ -1109,7 +1111,9 @@ def benchmark_sharded_train(grid=300, n_rays=4096, steps=10, device="cuda:0", sc
         e[0].record()
         out = tr.accumulate(rays, gt, first=True)
         tr.finish_into_bucket()
-        e[1].record()
+        if on and world > 1:
+            dist.all_reduce(skew)         # 4-byte collective: absorbs the ranks' arrival skew (they render different views),
+        e[1].record()                     # so that the next interval is the gradient all-reduce itself, not the wait for the slowest rank
         tr.bucket.allreduce(scale=1.0)
         e[2].record()
         tr.optimizer.step(grad_scale=1.0 / (world * n_rays))
