@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NMF_ABI_VERSION 8
+#define NMF_ABI_VERSION 9
 
 #define NMF_OK 0
 #define NMF_E_ARG (-1)          /* null pointer / non-positive size                                   */
@@ -138,6 +138,11 @@ typedef struct NmfScene {
   const void* brdf_w0b;
   const void* brdf_w1b;
   const void* brdf_w2b;
+  /* optional (NULL = not used): the summed-area table with BOTH x-taps of a bilinear lookup in one record,
+   * [h][w][8] = { S(y,x).rgb, 0, S(y,min(x+1,w-1)).rgb, 0 }: one aligned 32-byte load (LDG.256) per row of a lookup corner
+   * instead of two 16-byte loads -- the environment kernels are bound by L1 data-pipe wavefronts, one per lane-load.
+   * Built by nmf_env_pair_sat; costs h*w*32 bytes of L2 footprint, so the host only builds it for maps up to 512 x 1024. */
+  const float* env_sat2;
 } NmfScene;
 
 /* per-call render parameters */
@@ -471,6 +476,7 @@ int nmf_pack_factor(const float* src, int C, int H, int W, const float* kx25, co
  * bg_mat, 20)) (optional out, (3,h,w)), sat4 [h][w][4] = cumsum_x(cumsum_y(act / 1000)) with fp64 accumulation and a
  * rounding to fp32 after each scan (ATen's CPU cumsum), pole_sums[6] (device, fp64) = sums of the first / last row of act
  * per channel.  scratch_c1: 3*h*w floats. */
+int nmf_env_pair_sat(const float* sat4, int h, int w, float* sat8, void* stream);    /* NmfScene.env_sat2 from sat4 */
 int nmf_env_build_sat(const float* bg_mat, int h, int w, float brightness, float mul, float* scratch_c1, float* act,
                       float* sat4, double* pole_sums, void* stream);
 

@@ -41,6 +41,7 @@ class NmfScene(C.Structure):
         ("rays_per_ray", C.c_int), ("max_brdf_rays1", C.c_int), ("max_retrace", C.c_int), ("model", C.c_int),
         ("brdf_w0u", C.c_void_p), ("brdf_w1u", C.c_void_p), ("brdf_w2u", C.c_void_p), ("mlp_mode", C.c_int),
         ("brdf_w0b", C.c_void_p), ("brdf_w1b", C.c_void_p), ("brdf_w2b", C.c_void_p),
+        ("env_sat2", C.c_void_p),
     ]
 
 
@@ -192,6 +193,7 @@ def lib():
         "nmf_occupancy_from_alpha": (I, [P, I, I, I, F, I, P, P, P, P, P]),
         "nmf_bench_gather": (I, [P, C.c_size_t, I, I, I, P, P]),
         "nmf_transpose_batch": (I, [P, I, I, P]),
+        "nmf_env_pair_sat": (I, [P, I, I, P, P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
                                 C.c_size_t, P]),
     }
@@ -199,7 +201,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    assert L.nmf_abi_version() == 8, "libnmf_b200.so ABI mismatch: rebuild"
+    assert L.nmf_abi_version() == 9, "libnmf_b200.so ABI mismatch: rebuild"
     _lib = L
     return L
 
@@ -211,4 +213,4 @@ EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_pr
             "nmf_render_train_workspace_bytes", "nmf_render_rays_train", "nmf_l1_reg", "nmf_grad_sq_norm", "nmf_adam_step",
             "nmf_env_lookup_bwd_scatter", "nmf_env_lookup_bwd_finish", "nmf_env_lookup_bwd_mipbias", "nmf_vm_normals_bwd_scatter",
             "nmf_vm_normals_bwd_finish", "nmf_material_heads_bwd", "nmf_train_microfacet", "nmf_bench_gather", "nmf_pack_factor", "nmf_env_build_sat",
-            "nmf_occupancy_from_alpha", "nmf_transpose_batch"]
+            "nmf_occupancy_from_alpha", "nmf_transpose_batch", "nmf_env_pair_sat"]

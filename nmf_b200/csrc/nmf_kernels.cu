@@ -18,6 +18,7 @@
 //   k_finish0      per ray: tonemap, background, auxiliary maps, per-chunk A19 statistics (in three stages when the
 //                  caller wants host buffers: maps leave for the host as soon as they are final)
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include "nmf_field.cuh"
 #include "nmf_mlp_tc.cuh"
@@ -828,24 +829,44 @@ struct SelectArgs {
   float* rays1; float* mip1; uint64_t* key1;
 };
 
+// A thread-block CLUSTER per chunk (1, 2, 4 or 8 CTAs, chosen so that few chunks still fill the GPU: a training batch is
+// ONE chunk of ~100 k bounce rays): every CTA histograms its share of the rays, the histograms are summed through
+// distributed shared memory, every CTA scans the sum redundantly (same threshold everywhere); the tie list, the tie
+// counter and the output-slot counter live in CTA 0's shared memory and are reached with DSMEM atomics.
+// USE_CL = 0: one CTA per chunk, launched without a cluster (many chunks: a cluster of one only adds barrier cost).
+template <int USE_CL>
 __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
-  __shared__ unsigned hist[2048];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned CL = USE_CL ? cluster.num_blocks() : 1u, rank = USE_CL ? cluster.block_rank() : 0u;
+  auto csync = [&]() { if (USE_CL) cluster.sync(); else __syncthreads(); };
+  __shared__ unsigned hist[2048];      // this CTA's histogram (read by the whole cluster)
+  __shared__ unsigned hsum[2048];      // the cluster's histogram (private copy)
   __shared__ unsigned warp_tot[32];
   __shared__ unsigned sh_prefix, sh_need, sh_slot, sh_eq;
-  const int chunk = blockIdx.x;
+  __shared__ unsigned long long tie_key[NMF_TIE_CAP];
+  __shared__ unsigned long long tie_cut;
+  const int chunk = blockIdx.x / CL;
   const int n = min(a.ray_count[chunk], a.cap_rays);
   const int n_re = min(n, a.max_retrace);
-  if (threadIdx.x == 0) a.n_sec[chunk] = n_re;
-  if (n_re == 0) return;
+  if (threadIdx.x == 0 && rank == 0) a.n_sec[chunk] = n_re;
+  if (n_re == 0) return;               // the whole cluster leaves together
   BRay* region = a.brays + (size_t)chunk * a.cap_rays;
   float2* scu = a.scu + (size_t)chunk * a.cap_rays;
   const float total = (float)((double)a.score_sum[chunk] * (1.0 / 4294967296.0));
   const int lane = threadIdx.x & 31;
+  const int stride = (int)CL * 1024, first = (int)rank * 1024 + threadIdx.x;
+  unsigned* sh_slot0 = USE_CL ? cluster.map_shared_rank(&sh_slot, 0) : &sh_slot;
+  unsigned* sh_eq0 = USE_CL ? cluster.map_shared_rank(&sh_eq, 0) : &sh_eq;
+  unsigned long long* tie_key0 = USE_CL ? cluster.map_shared_rank(tie_key, 0) : tie_key;
+  unsigned long long* tie_cut0 = USE_CL ? cluster.map_shared_rank(&tie_cut, 0) : &tie_cut;
+  const unsigned* hs = USE_CL ? hsum : hist;      // the histogram the threshold scan reads
   // pass 0: final score = cc / sum * n_re + U(ray key)   (microfacet.py:504-506); histogram of its top 11 bits.
   // The scores crowd into a handful of exponent bins, so equal bins of a warp are merged into one shared atomic.
   for (int i = threadIdx.x; i < 2048; i += 1024) hist[i] = 0;
+  if (threadIdx.x == 0) { sh_slot = 0; sh_eq = 0; tie_cut = ~0ull; }
   __syncthreads();
-  for (int r0 = 0; r0 < n; r0 += 1024) {
+  for (int r0 = (int)rank * 1024; r0 < n; r0 += stride) {
     const int r = r0 + threadIdx.x;
     unsigned bin = 0xFFFFFFFFu;
     if (r < n) {
@@ -857,7 +878,6 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
     const unsigned m = __match_any_sync(FULL, bin);
     if (r < n && lane == __ffs(m) - 1) atomicAdd(&hist[bin], (unsigned)__popc(m));
   }
-  __syncthreads();
   unsigned prefix = 0, need = (unsigned)n_re;
   // digit 0: bits 31..21, digit 1: bits 20..10, digit 2: bits 9..0
   for (int pass = 0; pass < 3; ++pass) {
@@ -867,17 +887,25 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
       for (int i = threadIdx.x; i < 2048; i += 1024) hist[i] = 0;
       __syncthreads();
       const unsigned hi_shift = pass == 1 ? 21 : 10;
-      for (int r = threadIdx.x; r < n; r += 1024) {
+      for (int r = first; r < n; r += stride) {
         const unsigned bits = __float_as_uint(scu[r].x);
         if ((bits >> hi_shift) == prefix) atomicAdd(&hist[(bits >> shift) & (bins - 1)], 1u);
       }
-      __syncthreads();
+    }
+    csync();                           // every CTA's histogram is complete (also orders the block's own shared writes)
+    if (USE_CL) {
+      for (int i = threadIdx.x; i < bins; i += 1024) {
+        unsigned v = 0;
+        for (unsigned c = 0; c < CL; ++c) v += cluster.map_shared_rank(hist, c)[i];
+        hsum[i] = v;
+      }
+      cluster.sync();                  // all remote reads of `hist` are done before anyone clears it again
     }
     // largest bin b whose suffix count reaches `need` (b = 0 if none does): block-wide scan over the bins in descending
     // order, two bins per thread (a serial walk by one thread cost ~30 us per pass: 2048 dependent shared loads)
     {
       const int i0 = 2 * threadIdx.x;                                // descending position: bin = bins - 1 - i
-      const unsigned h0 = i0 < bins ? hist[bins - 1 - i0] : 0u, h1 = i0 + 1 < bins ? hist[bins - 2 - i0] : 0u;
+      const unsigned h0 = i0 < bins ? hs[bins - 1 - i0] : 0u, h1 = i0 + 1 < bins ? hs[bins - 2 - i0] : 0u;
       unsigned incl = h0 + h1;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
@@ -896,7 +924,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
         warp_tot[threadIdx.x] = t;                                    // inclusive totals of the warps
         if (threadIdx.x == 31) {                                      // default: nothing reaches `need` -> bin 0
           sh_prefix = prefix << (pass == 0 ? 0 : (pass == 1 ? 11 : 10));
-          sh_need = need - (t - hist[0]);
+          sh_need = need - (t - hs[0]);
         }
       }
       __syncthreads();
@@ -918,10 +946,6 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
   // prefix now holds the full 32-bit pattern of the threshold; `need` = how many of the rays equal to it are taken.
   // Scores are sums with a 24-bit uniform, so exact ties at the threshold do occur; they are broken by the rays' keys
   // (a property of the ray, not of its position in the list), which keeps the selection reproducible run to run.
-  __shared__ unsigned long long tie_key[NMF_TIE_CAP];
-  __shared__ unsigned long long tie_cut;
-  if (threadIdx.x == 0) { sh_slot = 0; sh_eq = 0; tie_cut = ~0ull; }
-  __syncthreads();
   const unsigned thr = prefix;
   auto ray_key = [&](int r) -> unsigned long long {
     const uint32_t own = a.owner[(size_t)chunk * a.cap_rays + r];
@@ -929,33 +953,36 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
     const BSample* b = a.bs + own;
     return (unsigned long long)nmf_mix64(b->key, (uint64_t)(r - (int)b->roff) + NMF_STREAM_RAY0);
   };
-  for (int r = threadIdx.x; r < n; r += 1024) {
+  for (int r = first; r < n; r += stride) {
     if (__float_as_uint(scu[r].x) == thr) {
-      const unsigned e = atomicAdd(&sh_eq, 1u);
-      if (e < NMF_TIE_CAP) tie_key[e] = ray_key(r);
+      const unsigned e = atomicAdd(sh_eq0, 1u);
+      if (e < NMF_TIE_CAP) tie_key0[e] = ray_key(r);
     }
   }
-  __syncthreads();
-  const unsigned n_tie = sh_eq;
-  __syncthreads();            // every thread holds the tie count before thread 0 reuses the counter below (racecheck)
+  csync();
+  const unsigned n_tie = *sh_eq0;
+  csync();             // every thread of the cluster holds the tie count before CTA 0 reuses the counter below (racecheck)
   const bool by_key = n_tie > need && n_tie <= NMF_TIE_CAP;      // otherwise all ties are taken, or (absurdly many) first come
-  if (by_key && threadIdx.x == 0) {
-    // the `need` smallest keys win: selection sort over a handful of entries
-    for (unsigned i = 0; i < need; ++i) {
-      unsigned m = i;
-      for (unsigned j = i + 1; j < n_tie; ++j) if (tie_key[j] < tie_key[m]) m = j;
-      const unsigned long long t = tie_key[i]; tie_key[i] = tie_key[m]; tie_key[m] = t;
+  if (rank == 0 && threadIdx.x == 0) {
+    if (by_key) {
+      // the `need` smallest keys win: selection sort over a handful of entries
+      for (unsigned i = 0; i < need; ++i) {
+        unsigned m = i;
+        for (unsigned j = i + 1; j < n_tie; ++j) if (tie_key[j] < tie_key[m]) m = j;
+        const unsigned long long t = tie_key[i]; tie_key[i] = tie_key[m]; tie_key[m] = t;
+      }
+      tie_cut = tie_key[need - 1];
     }
-    tie_cut = tie_key[need - 1];
+    sh_eq = 0;
   }
-  if (threadIdx.x == 0) sh_eq = 0;
-  __syncthreads();
-  for (int r = threadIdx.x; r < n; r += 1024) {
+  csync();
+  const unsigned long long cut = *tie_cut0;
+  for (int r = first; r < n; r += stride) {
     const unsigned bits = __float_as_uint(scu[r].x);
     bool take = bits > thr;
-    if (bits == thr) take = by_key ? ray_key(r) <= tie_cut : atomicAdd(&sh_eq, 1u) < need;
+    if (bits == thr) take = by_key ? ray_key(r) <= cut : atomicAdd(sh_eq0, 1u) < need;
     if (take) {
-      const unsigned sl = atomicAdd(&sh_slot, 1u);
+      const unsigned sl = atomicAdd(sh_slot0, 1u);
       if (sl < (unsigned)n_re) {
         BRay* o = region + r;
         const uint32_t own = a.owner[(size_t)chunk * a.cap_rays + r];
@@ -974,6 +1001,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs a) {
       }
     }
   }
+  csync();             // CTA 0's shared memory must outlive every remote access
 }
 
 // ================================================================================================
@@ -1020,7 +1048,8 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
         const float* src = a.rgb1 + ((size_t)chunk * (size_t)a.max_retrace + (size_t)slot) * 4;
         inc[0] = src[0]; inc[1] = src[1]; inc[2] = src[2];
       } else {
-        nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, L, q0.w, inc);
+        if (s.env_sat2) nmf_env_lookup1_pair(s.env_sat2, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, L, q0.w, inc);
+        else nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot, L, q0.w, inc);
       }
       const float4 qv = *(const float4*)b->V, q3 = *(const float4*)b->f0, q4 = *(const float4*)b->diffuse;
       const nmf_v3 H = nmf_unit(nmf_mk3((qv.x + L.x) / 2.0f, (qv.y + L.y) / 2.0f, (qv.z + L.z) / 2.0f));
@@ -1516,7 +1545,21 @@ static int render_impl(const NmfScene* scene, const NmfRender* rp, const float* 
 
     if (s.max_retrace > 0) {
       SelectArgs sa = {w.bs0, w.brays0, w.owner0, w.scu0, w.ray_count0, w.cap_rays0, w.score_sum, s.max_retrace, w.n_sec, w.rays1, w.mip1, w.key1};
-      k_select<<<nc, 1024, 0, stream>>>(sa);
+      {
+        // cluster size: enough CTAs to fill the GPU when there are few chunks (training: one chunk)
+        const unsigned cl = nc <= 18 ? 8u : (nc <= 37 ? 4u : (nc <= 74 ? 2u : 1u));
+        if (cl == 1u) {
+          k_select<0><<<nc, 1024, 0, stream>>>(sa);
+        } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)nc * cl); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_select<1>, sa));
+        }
+      }
       CKL();
       prof_mark(4, stream);
       MarchArgs m1 = {};

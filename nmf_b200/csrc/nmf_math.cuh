@@ -426,6 +426,46 @@ struct NmfSatTap {
 #endif
   }
 };
+// The same tap from the PAIRED table ([h][w][8]: texel x and its right neighbour in one 32-byte record): one 256-bit load
+// per row.  Same values, same arithmetic order as NmfSatTap -- only the number of load instructions (= L1 wavefronts per
+// lane) is halved.
+struct NmfSatTap2 {
+  const float* sat8; int h, w;
+  NMF_HD void operator()(float px, float py, float sign, float* acc) const {
+    px = nmf_clampf(px, -1.0f, 1.0f);
+    py = nmf_clampf(py, -1.0f, 1.0f);
+    float ix = (px + 1.0f) * 0.5f * (float)(w - 1), iy = (py + 1.0f) * 0.5f * (float)(h - 1);
+    float fx = floorf(ix), fy = floorf(iy);
+    int x0 = (int)fx, y0 = (int)fy;
+    float tx = ix - fx, ty = iy - fy;
+    int y1 = y0 + 1 < h ? y0 + 1 : y0;                                   // the clamped tap has weight 0
+    float w00 = (1.0f - tx) * (1.0f - ty), w10 = tx * (1.0f - ty), w01 = (1.0f - tx) * ty, w11 = tx * ty;
+    const float* r0 = sat8 + ((size_t)y0 * w + x0) * 8;
+    const float* r1 = sat8 + ((size_t)y1 * w + x0) * 8;
+#ifdef __CUDA_ARCH__
+    float a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3, d0, d1, d2, d3;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3), "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "l"(r0));
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(c0), "=f"(c1), "=f"(c2), "=f"(c3), "=f"(d0), "=f"(d1), "=f"(d2), "=f"(d3) : "l"(r1));
+    acc[0] += sign * (a0 * w00 + b0 * w10 + c0 * w01 + d0 * w11);
+    acc[1] += sign * (a1 * w00 + b1 * w10 + c1 * w01 + d1 * w11);
+    acc[2] += sign * (a2 * w00 + b2 * w10 + c2 * w01 + d2 * w11);
+#else
+    for (int k = 0; k < 3; ++k) acc[k] += sign * (r0[k] * w00 + r0[4 + k] * w10 + r1[k] * w01 + r1[4 + k] * w11);
+#endif
+  }
+};
+NMF_HD void nmf_env_lookup1_pair(const float* sat8, int h, int w, float mipbias, const float* top, const float* bot,
+                                 nmf_v3 dir, float sa, float* rgb) {
+  NmfEnvBox bx = nmf_env_box(dir, sa, h, w, mipbias);
+  NmfSatTap2 tap; tap.sat8 = sat8; tap.h = h; tap.w = w;
+  nmf_env_integrate(tap, bx, rgb);
+  rgb[0] *= 1000.0f; rgb[1] *= 1000.0f; rgb[2] *= 1000.0f;
+  float cutoff = 1.0f - 2.0f / (float)h * 3.0f;
+  if (bx.cy > cutoff) { rgb[0] = bot[0]; rgb[1] = bot[1]; rgb[2] = bot[2]; }
+  if (bx.cy < -cutoff) { rgb[0] = top[0]; rgb[1] = top[1]; rgb[2] = top[2]; }
+}
 // IntegralEquirect.forward for one direction (integral_equirect.py:409-504)
 NMF_HD void nmf_env_lookup1(const float* sat, int h, int w, float mipbias, const float* top, const float* bot,
                             nmf_v3 dir, float sa, float* rgb) {

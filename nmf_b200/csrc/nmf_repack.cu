@@ -150,6 +150,22 @@ __global__ void k_env_pad(float* __restrict__ sat, size_t n) {
   if (i < n) sat[i * 4 + 3] = 0.f;
 }
 
+// sat8[y][x] = { sat4[y][x], sat4[y][min(x + 1, w - 1)] }: both x-taps of a bilinear lookup in one aligned 32-byte record
+__global__ void k_env_pair(const float4* __restrict__ sat4, int w, size_t n, float4* __restrict__ sat8) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = (int)(i % (size_t)w);
+  sat8[2 * i] = sat4[i];
+  sat8[2 * i + 1] = sat4[x + 1 < w ? i + 1 : i];
+}
+extern "C" int nmf_env_pair_sat(const float* sat4, int h, int w, float* sat8, void* stream) {
+  if (!sat4 || !sat8 || h <= 0 || w <= 0) return NMF_E_ARG;
+  const size_t n = (size_t)h * w;
+  k_env_pair<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)sat4, w, n, (float4*)sat8);
+  CKL();
+  return NMF_OK;
+}
+
 extern "C" int nmf_env_build_sat(const float* bg_mat, int h, int w, float brightness, float mul, float* scratch_c1, float* act,
                                  float* sat4, double* pole_sums, void* stream) {
   if (!bg_mat || !scratch_c1 || !sat4 || !pole_sums || h <= 0 || w <= 0) return NMF_E_ARG;

@@ -364,9 +364,22 @@ class DeviceScene:
             with torch.cuda.device(dev):
                 _lib.check(_lib.lib().nmf_env_build_sat(_p(bg), eh, ew, float(brightness), float(mul), _p(self.keep["env_c1"]), None,
                                                         _p(sat4), _p(self.keep["env_pole"]), _stream()), "nmf_env_build_sat")
+            # paired table for the forward lookups (NmfScene.env_sat2): only while it fits the L2 next to the factor set
+            if eh * ew <= 512 * 1024:
+                sat8 = self.keep.get("env_sat2")
+                if sat8 is None or tuple(sat8.shape) != (eh, ew, 8):
+                    sat8 = torch.empty(eh, ew, 8, device=dev, dtype=torch.float32)
+                with torch.cuda.device(dev):
+                    _lib.check(_lib.lib().nmf_env_pair_sat(_p(sat4), eh, ew, _p(sat8), _stream()), "nmf_env_pair_sat")
+                self._ptr(s, "env_sat2", sat8)
+            else:
+                self.keep.pop("env_sat2", None)
+                s.env_sat2 = None
             pole = (self.keep["env_pole"] / ew).float().cpu()          # ONE device-to-host copy for the six pole means
             top, bot = pole[:3], pole[3:]
         else:
+            self.keep.pop("env_sat2", None)
+            s.env_sat2 = None
             act, sat = build_sat(bg, brightness, mul)
             sat4 = torch.zeros(eh, ew, 4, device=dev, dtype=torch.float32)
             sat4[..., :3] = sat[0].permute(1, 2, 0)

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     from nmf_b200 import _lib
     assert sorted(_lib.EXPORTED) == declared
     L.nmf_abi_version.restype = ctypes.c_int
-    assert L.nmf_abi_version() == 8
+    assert L.nmf_abi_version() == 9
 
 
 def test_struct_mirror_matches_header_size():
