@@ -28,6 +28,7 @@ extern "C" {
 #endif
 
 #define NMF_ABI_VERSION 9
+#define NMF_APP_STRIDE 24      /* floats per appearance texel; 32 (a 128-byte texel) was measured: no gain, +9 MB of L2 footprint */
 
 #define NMF_OK 0
 #define NMF_E_ARG (-1)          /* null pointer / non-positive size                                   */
@@ -88,7 +89,10 @@ typedef struct NmfScene {
   const float* dpack[3];
   const float* lval[3];
   const float* lpack[3];
-  /* appearance factors: [h][w][24], [n][24]; basis_t: [72][24] = rf.basis_mat.weight transposed (tensoRF.py:293) */
+  /* appearance factors: [h][w][NMF_APP_STRIDE], [n][NMF_APP_STRIDE] (24 channels per texel; the stride is a build-time constant
+   * so that padded texels can be tried: 128-byte texels never straddle a line, which removes a third of the L1 wavefronts of
+   * these taps, but k_shade did not get faster -- profiles/r02_d_*); basis_t: [72][24] = rf.basis_mat.weight transposed
+   * (tensoRF.py:293) */
   const float* aval[3];
   const float* alval[3];
   const float* basis_t;
@@ -466,7 +470,8 @@ int nmf_upsample_bilinear(const float* src, int C, int H, int W, float* dst, int
 /* ---- scene re-pack: rebuilt from the parameters after every optimiser step of a training run (csrc/nmf_repack.cu) ---- */
 
 /* One factor in the reference's layout -- a plane (1,C,H,W) or a line (1,C,N,1) passed as H = N, W = 1 -- into the
- * channel-last gather layouts of NmfScene: val [H][W][C] and, for the density factors (C = 16), pack = [H][W][val | dx | dy]
+ * channel-last gather layouts of NmfScene: val [H][W][C] (C = 24: [H][W][NMF_APP_STRIDE], padding untouched) and, for the
+ * density factors (C = 16), pack = [H][W][val | dx | dy]
  * (lines: [N][4][val4 | dy4]) with the smoothed-difference planes of modules/grid_sample_Cinf.py:218-242 (5x5
  * cross-correlation with kx25 / ky25, zero padding 2).  val or pack may be NULL. */
 int nmf_pack_factor(const float* src, int C, int H, int W, const float* kx25, const float* ky25, float* val, float* pack,

@@ -18,6 +18,16 @@ NMF_HD nmf_f4 nmf_ld4(const float* p) {
 #endif
 }
 #define NMF_LD4(p) nmf_ld4(p)
+// two adjacent 16-byte groups (32-byte aligned) as ONE 256-bit load (LDG.E.256): half the load instructions, and with them
+// half the L1 data-pipe wavefronts, of two nmf_ld4 calls -- the gather kernels are bound by that pipe
+NMF_HD void nmf_ld8(const float* p, nmf_f4& a, nmf_f4& b) {
+#ifdef __CUDA_ARCH__
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+  a = *(const nmf_f4*)p; b = *(const nmf_f4*)(p + 4);
+#endif
+}
 
 NMF_HD nmf_f4 nmf_f4_zero() { nmf_f4 r; r.x = r.y = r.z = r.w = 0.f; return r; }
 NMF_HD void nmf_f4_fma(nmf_f4& a, nmf_f4 v, float w) { a.x += v.x * w; a.y += v.y * w; a.z += v.z * w; a.w += v.w * w; }
@@ -96,8 +106,8 @@ NMF_HD float nmf_density_group(const NmfScene& s, const NmfTaps& t, int g) {
 }
 // appearance coefficients, channels 4g..4g+3 (g < 6) of plane p (tensoRF.py:402-405 before basis_mat)
 NMF_HD nmf_f4 nmf_app_group(const NmfScene& s, const NmfTaps& t, int p, int g) {
-  nmf_f4 pv = nmf_bilerp4(s.aval[p], s.plane_w[p], 24, 4 * g, t.px[p], t.py[p]);
-  nmf_f4 lv = nmf_lerp4(s.alval[p], 24, 4 * g, t.pl[p]);
+  nmf_f4 pv = nmf_bilerp4(s.aval[p], s.plane_w[p], NMF_APP_STRIDE, 4 * g, t.px[p], t.py[p]);
+  nmf_f4 lv = nmf_lerp4(s.alval[p], NMF_APP_STRIDE, 4 * g, t.pl[p]);
   nmf_f4 o; o.x = pv.x * lv.x; o.y = pv.y * lv.y; o.z = pv.z * lv.z; o.w = pv.w * lv.w;
   return o;
 }
@@ -131,8 +141,13 @@ NMF_HD void nmf_normal_lane(const NmfScene& s, const NmfTaps& t, int l, float* g
     const float* l0 = s.lpack[p] + (size_t)ll.i0 * 32 + 8 * g;
     const float* l1 = s.lpack[p] + (size_t)ll.i1 * 32 + 8 * g;
     nmf_f4 lv = nmf_f4_zero(), ld = nmf_f4_zero();
-    nmf_f4_fma(lv, NMF_LD4(l0), ll.w0); nmf_f4_fma(ld, NMF_LD4(l0 + 4), ll.w0);
-    nmf_f4_fma(lv, NMF_LD4(l1), ll.w1); nmf_f4_fma(ld, NMF_LD4(l1 + 4), ll.w1);
+    {
+      nmf_f4 v0, d0, v1, d1;                       // (val4 | dy4) of a line texel are 32 contiguous, 32-byte aligned bytes
+      nmf_ld8(l0, v0, d0);
+      nmf_ld8(l1, v1, d1);
+      nmf_f4_fma(lv, v0, ll.w0); nmf_f4_fma(ld, d0, ll.w0);
+      nmf_f4_fma(lv, v1, ll.w1); nmf_f4_fma(ld, d1, ll.w1);
+    }
     const float* r0 = s.dpack[p] + ((size_t)ly.i0 * w + px.base) * 48 + 4 * l;
     const float* r1 = s.dpack[p] + ((size_t)ly.i1 * w + px.base) * 48 + 4 * l;
     nmf_f4 a0 = nmf_f4_zero(), a1 = nmf_f4_zero(), a2 = nmf_f4_zero();

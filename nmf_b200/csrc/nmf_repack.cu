@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) k_pack_plane(const float* __restrict__ sr
   const int y = (int)(texel / W), x = (int)(texel - (size_t)y * W);
   const float* p = src + (size_t)c * H * W;
   const float v = p[(size_t)y * W + x];
-  if (val) val[texel * C + c] = v;
+  if (val) val[texel * (C == 24 ? NMF_APP_STRIDE : C) + c] = v;
   if (pack) {
     float dx = 0.f, dy = 0.f;
 #pragma unroll
@@ -60,7 +60,7 @@ __global__ void k_pack_line(const float* __restrict__ src, int C, int N, const f
   if (n >= N) return;
   const float* p = src + (size_t)c * N;
   const float v = p[n];
-  if (val) val[(size_t)n * C + c] = v;
+  if (val) val[(size_t)n * (C == 24 ? NMF_APP_STRIDE : C) + c] = v;
   if (pack) {
     float dy = 0.f;
 #pragma unroll

@@ -35,10 +35,11 @@ NMF_HD nmf_f4 nmf_f4_mul(nmf_f4 a, nmf_f4 b) { nmf_f4 o; o.x = a.x * b.x; o.y = 
 
 // Backward of one channel group (4 channels at float offset `off`) of one plane/line pair:
 //   coef = bilerp(plane)(u, v) * lerp(line)(w);   d plane taps += dc * line * bilinear weight, d line taps += dc * plane * weight
-NMF_HD void nmf_vm_bwd_group(const float* plane, const float* line, float* gplane, float* gline, int w, int stride, int off,
+// vstride: floats per texel of the VALUE buffers (appearance: NMF_APP_STRIDE), stride: of the gradient buffers ([..][C])
+NMF_HD void nmf_vm_bwd_group(const float* plane, const float* line, float* gplane, float* gline, int w, int vstride, int stride, int off,
                              const NmfLerp& lx, const NmfLerp& ly, const NmfLerp& ll, nmf_f4 dc) {
-  const nmf_f4 pv = nmf_bilerp4(plane, w, stride, off, lx, ly);
-  const nmf_f4 lv = nmf_lerp4(line, stride, off, ll);
+  const nmf_f4 pv = nmf_bilerp4(plane, w, vstride, off, lx, ly);
+  const nmf_f4 lv = nmf_lerp4(line, vstride, off, ll);
   const nmf_f4 dpv = nmf_f4_mul(dc, lv), dlv = nmf_f4_mul(dc, pv);
   float* r0 = gplane + (size_t)ly.i0 * w * stride + off;
   float* r1 = gplane + (size_t)ly.i1 * w * stride + off;
@@ -54,14 +55,14 @@ NMF_HD void nmf_density_bwd(const NmfScene& s, const NmfTaps& t, float df, float
   nmf_f4 dc; dc.x = dc.y = dc.z = dc.w = df;
   for (int p = 0; p < 3; ++p)
     for (int g = 0; g < 4; ++g)
-      nmf_vm_bwd_group(s.dval[p], s.lval[p], gplane[p], gline[p], s.plane_w[p], 16, 4 * g, t.px[p], t.py[p], t.pl[p], dc);
+      nmf_vm_bwd_group(s.dval[p], s.lval[p], gplane[p], gline[p], s.plane_w[p], 16, 16, 4 * g, t.px[p], t.py[p], t.pl[p], dc);
 }
 // dcoef: gradient of the 72 appearance products (before basis_mat)
 NMF_HD void nmf_app_bwd(const NmfScene& s, const NmfTaps& t, const float* dcoef, float* const* gplane, float* const* gline) {
   for (int p = 0; p < 3; ++p)
     for (int g = 0; g < 6; ++g) {
       nmf_f4 dc; dc.x = dcoef[p * 24 + 4 * g]; dc.y = dcoef[p * 24 + 4 * g + 1]; dc.z = dcoef[p * 24 + 4 * g + 2]; dc.w = dcoef[p * 24 + 4 * g + 3];
-      nmf_vm_bwd_group(s.aval[p], s.alval[p], gplane[p], gline[p], s.plane_w[p], 24, 4 * g, t.px[p], t.py[p], t.pl[p], dc);
+      nmf_vm_bwd_group(s.aval[p], s.alval[p], gplane[p], gline[p], s.plane_w[p], NMF_APP_STRIDE, 24, 4 * g, t.px[p], t.py[p], t.pl[p], dc);
     }
 }
 NMF_HD void nmf_app_coef(const NmfScene& s, const NmfTaps& t, float* coef) {

@@ -21,6 +21,8 @@ from . import _lib
 MAT_MODE = ((0, 1), (0, 2), (1, 2))   # fields/tensoRF.py:40
 VEC_MODE = (2, 1, 0)                  # fields/tensoRF.py:41
 
+APP_STRIDE = 24        # floats per appearance texel (= include/nmf_b200.h NMF_APP_STRIDE)
+
 DEFAULT_HP = dict(
     distance_scale=25.0, density_shift=-4.0, step_ratio=0.5,                 # configs/field/tensorf.yaml
     rays_per_ray=128, max_brdf_rays=(650000, 450000), max_retrace_rays=(1000,), anoise=0.25,
@@ -219,7 +221,7 @@ class DeviceScene:
         def buf(name, shape, arr, p):
             old = self.keep.get(f"{name}{p}")
             if old is None or tuple(old.shape) != tuple(shape):
-                old = torch.empty(*shape, device=dev, dtype=torch.float32)
+                old = torch.zeros(*shape, device=dev, dtype=torch.float32)       # (padding channels stay zero)
                 self.keep[f"{name}{p}"] = old
             arr[p] = old.data_ptr()
             return old
@@ -232,7 +234,7 @@ class DeviceScene:
                 H, W, N = dp.shape[2], dp.shape[3], dl.shape[2]
                 s.plane_w[p], s.plane_h[p], s.line_n[p] = W, H, N
                 dval, lval = buf("dval", (H, W, 16), s.dval, p), buf("lval", (N, 16), s.lval, p)
-                aval, alval = buf("aval", (H, W, 24), s.aval, p), buf("alval", (N, 24), s.alval, p)
+                aval, alval = buf("aval", (H, W, APP_STRIDE), s.aval, p), buf("alval", (N, APP_STRIDE), s.alval, p)
                 if derivatives:
                     dpack, lpack = buf("dpack", (H, W, 48), s.dpack, p), buf("lpack", (N, 4, 8), s.lpack, p)
                 else:
@@ -274,8 +276,8 @@ class DeviceScene:
             dval = dp[0].permute(1, 2, 0)                                                # (H,W,16)
             lval = dl[0, :, :, 0].permute(1, 0)                                          # (N,16)
             packed = [("dval", dval, s.dval), ("lval", lval, s.lval),
-                      ("aval", ap[0].permute(1, 2, 0), s.aval),                          # (H,W,24)
-                      ("alval", al[0, :, :, 0].permute(1, 0), s.alval)]                  # (N,24)
+                      ("aval", F.pad(ap[0].permute(1, 2, 0), (0, APP_STRIDE - 24)), s.aval),          # (H,W,APP_STRIDE)
+                      ("alval", F.pad(al[0, :, :, 0].permute(1, 0), (0, APP_STRIDE - 24)), s.alval)]  # (N,APP_STRIDE)
             if derivatives:
                 pdx, pdy = conv(dp, kx)[0].permute(1, 2, 0), conv(dp, ky)[0].permute(1, 2, 0)
                 ldy = conv(dl, ky)[0, :, :, 0].permute(1, 0)
