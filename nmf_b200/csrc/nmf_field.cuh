@@ -33,6 +33,18 @@ NMF_HD nmf_f4 nmf_f4_zero() { nmf_f4 r; r.x = r.y = r.z = r.w = 0.f; return r; }
 NMF_HD void nmf_f4_fma(nmf_f4& a, nmf_f4 v, float w) { a.x += v.x * w; a.y += v.y * w; a.z += v.z * w; a.w += v.w * w; }
 NMF_HD float nmf_f4_dot(nmf_f4 a, nmf_f4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
+// two 16-byte groups to a 32-byte aligned address as ONE 256-bit store
+NMF_HD void nmf_st8(float* p, nmf_f4 a, nmf_f4 b) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+#else
+  *(nmf_f4*)p = a; *(nmf_f4*)(p + 4) = b;
+#endif
+}
+// (plain-cached variant of nmf_ld8 for data written earlier in the same launch sequence is not needed: records are
+// produced by one kernel and consumed by the next, so the read-only path is safe)
+
 // matMode / vecMode of fields/tensoRF.py:40-41
 #define NMF_MAT0(p) ((p) == 2 ? 1 : 0)
 #define NMF_MAT1(p) ((p) == 0 ? 1 : 2)

@@ -525,30 +525,20 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
     if (slot >= 0) {
       const float sgn = vn > 0.f ? 1.f : (vn < 0.f ? -1.f : 0.f);        // microfacet.py:354-356
       const nmf_v3 Nf = nmf_mk3(nrm.x * sgn, nrm.y * sgn, nrm.z * sgn);
-      float4* q = (float4*)b;
-      q[0] = make_float4(p[0], p[1], p[2], w);
+      float* q = (float*)b;                                                // ten 256-bit stores (see BSample)
       const float rough_b = TRAIN ? fmaxf(rough, a.min_rough) : rough;     // microfacet.py:361-363 (bounce rays only)
-      q[1] = make_float4(V.x, V.y, V.z, rough_b);
-      q[2] = make_float4(Nf.x, Nf.y, Nf.z, __int_as_float(count));
-      q[3] = make_float4(hs[0], hs[1], hs[2], __uint_as_float((uint32_t)ray));
-      q[4] = make_float4(hs[3], hs[4], hs[5], __uint_as_float((uint32_t)roff));
-      q[5] = make_float4(hs[6], hs[7], hs[8], __uint_as_float(xn[2] < 0.f ? 1u : 0u));
-      b->key = skey; b->chunk = (uint32_t)chunk; b->pad = (TRAIN && a.survv) ? a.survv[si] : 0u;
-      if (LEVEL == 0) {
-        a.red[2 * slot] = make_float4(w, __int_as_float(count), __uint_as_float((uint32_t)ray), __uint_as_float(xn[2] < 0.f ? 1u : 0u));
-        a.red[2 * slot + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      nmf_st8(q, make_float4(p[0], p[1], p[2], w), make_float4(V.x, V.y, V.z, rough_b));
+      nmf_st8(q + 8, make_float4(Nf.x, Nf.y, Nf.z, __int_as_float(count)), make_float4(hs[0], hs[1], hs[2], __uint_as_float((uint32_t)ray)));
+      nmf_st8(q + 16, make_float4(hs[3], hs[4], hs[5], __uint_as_float((uint32_t)roff)),
+              make_float4(hs[6], hs[7], hs[8], __uint_as_float(xn[2] < 0.f ? 1u : 0u)));
+      if (LEVEL == 0)
+        nmf_st8((float*)(a.red + 2 * slot),
+                make_float4(w, __int_as_float(count), __uint_as_float((uint32_t)ray), __uint_as_float(xn[2] < 0.f ? 1u : 0u)),
+                make_float4(0.f, 0.f, 0.f, 0.f));
       // per-sample part of the GGX sampler and of the ISH encodings, shared by all bounce rays of the sample
       const NmfGGXFrame fr = nmf_ggx_frame(V, Nf, rough_b);
       float s1, s2;
       nmf_ish_scales(rough_b, &s1, &s2);
-      float4* fq = (float4*)b->frame;
-      fq[0] = make_float4(fr.t.x, fr.t.y, fr.t.z, fr.b.x);
-      fq[1] = make_float4(fr.b.y, fr.b.z, fr.V_l.x, fr.V_l.y);
-      fq[2] = make_float4(fr.V_l.z, fr.Vs.x, fr.Vs.y, fr.Vs.z);
-      fq[3] = make_float4(fr.T1.x, fr.T1.y, fr.T1.z, fr.T2.x);
-      fq[4] = make_float4(fr.T2.y, fr.T2.z, fr.a, s1);
-      fq[5] = make_float4(s2, 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_U), 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_V), 0.f);
       // appearance feature + noise (microfacet.py:297, keyed Box-Muller), one feature per trip of a rolled loop
       const uint64_t nseed = nmf_noise_seed(skey);
 #pragma unroll 1
@@ -558,8 +548,17 @@ __global__ void __launch_bounds__(256, 3) k_shade(const NmfScene s, const ShadeA
         fs[2 * i] += s.anoise * n0;
         fs[2 * i + 1] += s.anoise * n1;
       }
-#pragma unroll
-      for (int i = 0; i < 6; ++i) *(float4*)(b->feat + 4 * i) = make_float4(fs[4 * i], fs[4 * i + 1], fs[4 * i + 2], fs[4 * i + 3]);
+      const uint32_t vsi = (TRAIN && a.survv) ? a.survv[si] : 0u;
+      nmf_st8(q + 24, make_float4(__uint_as_float((uint32_t)(skey & 0xffffffffull)), __uint_as_float((uint32_t)(skey >> 32)),
+                                  __uint_as_float((uint32_t)chunk), __uint_as_float(vsi)),
+              make_float4(fs[0], fs[1], fs[2], fs[3]));
+      nmf_st8(q + 32, make_float4(fs[4], fs[5], fs[6], fs[7]), make_float4(fs[8], fs[9], fs[10], fs[11]));
+      nmf_st8(q + 40, make_float4(fs[12], fs[13], fs[14], fs[15]), make_float4(fs[16], fs[17], fs[18], fs[19]));
+      nmf_st8(q + 48, make_float4(fs[20], fs[21], fs[22], fs[23]), make_float4(fr.t.x, fr.t.y, fr.t.z, fr.b.x));
+      nmf_st8(q + 56, make_float4(fr.b.y, fr.b.z, fr.V_l.x, fr.V_l.y), make_float4(fr.V_l.z, fr.Vs.x, fr.Vs.y, fr.Vs.z));
+      nmf_st8(q + 64, make_float4(fr.T1.x, fr.T1.y, fr.T1.z, fr.T2.x), make_float4(fr.T2.y, fr.T2.z, fr.a, s1));
+      nmf_st8(q + 72, make_float4(s2, 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_U), 0.25f * nmf_uniform(skey, NMF_STREAM_OFF_V), 0.f),
+              make_float4(0.f, 0.f, 0.f, 0.f));
     }
     // ray -> bounce-sample map of the allocated ranges, written by the whole warp.  A sample whose allocation failed
     // (a list overflowed: the call reports an error) marks its rays with NMF_NO_OWNER so that no consumer follows a
@@ -757,13 +756,22 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
     if (LEVEL == 0 && r < n && !active) a.scu[(size_t)chunk * a.cap_rays + r] = make_float2(0.f, 0.f);
     const BSample* b = a.bs + slot;
     const int j = active ? r - (int)b->roff : 0;
-    const float4 q0 = *(const float4*)b->pos, q1 = *(const float4*)b->V, q2 = *(const float4*)b->N;
+    // the record in nine 256-bit loads (BSample: ten 32-byte pairs; diffuse|fresn is not needed here)
+    const float* rb = (const float*)b;
+    float4 q0, q1, q2, qx, kb, ft[6], f0, f1, f2, f3, f4, f5;
+    nmf_ld8(rb, q0, q1);                 // pos, w | V, rough
+    nmf_ld8(rb + 8, q2, qx);             // N, count | (f0)
+    nmf_ld8(rb + 24, kb, ft[0]);         // key, chunk, pad | feat 0..3
+    nmf_ld8(rb + 32, ft[1], ft[2]);
+    nmf_ld8(rb + 40, ft[3], ft[4]);
+    nmf_ld8(rb + 48, ft[5], f0);         // feat 20..23 | frame 0..3
+    nmf_ld8(rb + 56, f1, f2);
+    nmf_ld8(rb + 64, f3, f4);
+    nmf_ld8(rb + 72, f5, qx);
     const nmf_v3 V = nmf_mk3(q1.x, q1.y, q1.z), N = nmf_mk3(q2.x, q2.y, q2.z);
     const float rough = q1.w, w = q0.w;
     const int count = max(__float_as_int(q2.w), 1);
-    const uint64_t skey = b->key;
-    const float4* fq = (const float4*)b->frame;
-    const float4 f0 = fq[0], f1 = fq[1], f2 = fq[2], f3 = fq[3], f4 = fq[4], f5 = fq[5];
+    const uint64_t skey = (uint64_t)__float_as_uint(kb.x) | ((uint64_t)__float_as_uint(kb.y) << 32);
     NmfGGXFrame fr;
     fr.t = nmf_mk3(f0.x, f0.y, f0.z); fr.b = nmf_mk3(f0.w, f1.x, f1.y); fr.V_l = nmf_mk3(f1.z, f1.w, f2.x);
     fr.Vs = nmf_mk3(f2.y, f2.z, f2.w); fr.T1 = nmf_mk3(f3.x, f3.y, f3.z); fr.T2 = nmf_mk3(f3.w, f4.x, f4.y);
@@ -774,10 +782,7 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
     const NmfGGX g = nmf_ggx_sample_f(fr, u1, u2, V, N, rough);
     float x[TC_K0];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const float4 f = *(const float4*)(b->feat + 4 * i);
-      x[4 * i] = f.x; x[4 * i + 1] = f.y; x[4 * i + 2] = f.z; x[4 * i + 3] = f.w;
-    }
+    for (int i = 0; i < 6; ++i) { x[4 * i] = ft[i].x; x[4 * i + 1] = ft[i].y; x[4 * i + 2] = ft[i].z; x[4 * i + 3] = ft[i].w; }
     mlp_encode_s(x, g.half_l, g.diff_l, ish1, ish2);
     float bw[3];
     if (TC) tc_mlp_forward(tc, x, s.brdf_bias, bw);      // all 128 threads: the tile is one tensor-core GEMM

@@ -17,7 +17,10 @@
 
 struct Surv { uint32_t ray; uint32_t step; float w; };
 
-struct __align__(16) BSample {
+// 320 bytes = ten 32-byte pairs, 32-byte aligned: k_shade writes a record with ten 256-bit stores and k_bounce reads it with
+// nine 256-bit loads (pairs: pos|V, N|f0, diffuse|fresn, key..|feat0, feat1|feat2, feat3|feat4, feat5|frame0, frame1|frame2,
+// frame3|frame4, frame5|tail) -- half the load / store instructions per lane, i.e. half the L1 wavefronts of the record traffic
+struct __align__(32) BSample {
   float pos[3]; float w;
   float V[3]; float rough;
   float N[3]; int count;
@@ -30,7 +33,9 @@ struct __align__(16) BSample {
   // frame[0..17] = t, b, V_l, Vs, T1, T2 (nmf_ggx_frame), [18] = a, [19..20] = ISH scales s1, s2, [21..22] = the
   // per-sample Sobol offsets 0.25 * U (brdf_samplers/base.py:16-19)
   float frame[24];
+  float tail[4];      // padding to 320 bytes
 };
+static_assert(sizeof(BSample) == 320, "BSample is ten 32-byte pairs");
 
 // train mode: one record per VALID sample of a kept ray (also the zero-weight ones: the compositing backward needs them all)
 struct __align__(16) VSmp { uint32_t k; float f; float alpha; float T; };
