@@ -33,6 +33,16 @@ NMF_HD nmf_f4 nmf_f4_zero() { nmf_f4 r; r.x = r.y = r.z = r.w = 0.f; return r; }
 NMF_HD void nmf_f4_fma(nmf_f4& a, nmf_f4 v, float w) { a.x += v.x * w; a.y += v.y * w; a.z += v.z * w; a.w += v.w * w; }
 NMF_HD float nmf_f4_dot(nmf_f4 a, nmf_f4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
+// the same for records that are read exactly once (bounce-ray records): evict-first, so that they do not displace the
+// summed-area table and the factor planes in L1 / L2
+NMF_HD void nmf_ld8_stream(const float* p, nmf_f4& a, nmf_f4& b) {
+#ifdef __CUDA_ARCH__
+  asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+  a = *(const nmf_f4*)p; b = *(const nmf_f4*)(p + 4);
+#endif
+}
 // two 16-byte groups to a 32-byte aligned address as ONE 256-bit store
 NMF_HD void nmf_st8(float* p, nmf_f4 a, nmf_f4 b) {
 #ifdef __CUDA_ARCH__

@@ -802,8 +802,7 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
         const float per_ray = fmaxf(bw[0], fmaxf(bw[1], bw[2])) * (nmf_dot(V, N) > 0.f ? 1.f : 0.f) * pdf;
         sc = per_ray * (w / ((float)count + 1e-8f));
         BRay* o = region + r;
-        *(float4*)o->L = make_float4(g.L.x, g.L.y, g.L.z, mip);
-        *(float4*)o->bw = make_float4(bw[0], bw[1], bw[2], __int_as_float(-1));
+        nmf_st8((float*)o, make_float4(g.L.x, g.L.y, g.L.z, mip), make_float4(bw[0], bw[1], bw[2], __int_as_float(-1)));
         const uint64_t rkey = nmf_mix64(skey, (uint64_t)j + NMF_STREAM_RAY0);
         a.scu[(size_t)chunk * a.cap_rays + r] = make_float2(sc, nmf_uniform(rkey, NMF_STREAM_TIE));
       }
@@ -816,8 +815,7 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
       // (Doing the lookup here saved the 32-byte record but ran 15 % slower: this kernel sits at its register and
       // shared-memory occupancy limit, the lookup kernel does not.)
       BRay* o = region + r;
-      *(float4*)o->L = make_float4(g.L.x, g.L.y, g.L.z, mip);
-      *(float4*)o->bw = make_float4(bw[0], bw[1], bw[2], __int_as_float(-1));
+      nmf_st8((float*)o, make_float4(g.L.x, g.L.y, g.L.z, mip), make_float4(bw[0], bw[1], bw[2], __int_as_float(-1)));
     }
     tw_advance(tw);
   }
@@ -1031,14 +1029,14 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
   float4 q0 = zero4, q1 = zero4;
   if (tw.r < tw.n) {
     const BRay* o = a.brays + (size_t)tw.chunk * a.cap_rays + tw.r;
-    q0 = *(const float4*)o->L; q1 = *(const float4*)o->bw;
+    nmf_ld8((const float*)o, q0, q1);
   }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tw_advance(tw)) {
     tw_issue(tw, tile, a.tile_desc, n_tiles, a.ray_count, a.cap_rays, a.owner);
     float4 q0n = zero4, q1n = zero4;
     if (tw.r_n < tw.n_n) {
       const BRay* o = a.brays + (size_t)tw.chunk_n * a.cap_rays + tw.r_n;
-      q0n = __ldcs((const float4*)o->L); q1n = __ldcs((const float4*)o->bw);
+      q0n = __ldcs((const float4*)o->L); q1n = __ldcs((const float4*)o->bw);      // (one 256-bit load measured slower here)
     }
     const int chunk = tw.chunk;
     const uint32_t key = tw.slot;
@@ -1108,7 +1106,8 @@ struct ReduceArgs { const float4* red; const int* n_bs; int cap_bs; float* accum
 __global__ void __launch_bounds__(256) k_reduce0(const ReduceArgs a) {
   const int n = min(*a.n_bs, a.cap_bs);
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-    const float4 hdr = a.red[2 * (size_t)i], sum = a.red[2 * (size_t)i + 1];      // one 32-byte sector per sample
+    float4 hdr, sum;                                                              // one 32-byte sector per sample, one load
+    nmf_ld8((const float*)(a.red + 2 * (size_t)i), hdr, sum);
     if (__float_as_int(hdr.y) <= 0) continue;                                       // dropped sample (overflow case only)
     const float w = hdr.x, inv = 1.0f / (float)__float_as_int(hdr.y);
     float* acc = a.accum + (size_t)__float_as_uint(hdr.z) * A_N;

@@ -40,7 +40,7 @@ static_assert(sizeof(BSample) == 320, "BSample is ten 32-byte pairs");
 // train mode: one record per VALID sample of a kept ray (also the zero-weight ones: the compositing backward needs them all)
 struct __align__(16) VSmp { uint32_t k; float f; float alpha; float T; };
 
-struct __align__(16) BRay {     // bounce ray record handed from k_bounce to k_incoming
+struct __align__(32) BRay {     // bounce ray record handed from k_bounce to k_incoming: one 256-bit store, one 256-bit load
   float L[3]; float mip;
   float bw[3]; int slot;        // slot: index of the secondary ray that re-traces it, -1 = environment
 };
