@@ -785,8 +785,15 @@ __global__ void __launch_bounds__(MLP_THREADS, TC ? 5 : 1) k_bounce(const NmfSce
     for (int i = 0; i < 6; ++i) { x[4 * i] = ft[i].x; x[4 * i + 1] = ft[i].y; x[4 * i + 2] = ft[i].z; x[4 * i + 3] = ft[i].w; }
     mlp_encode_s(x, g.half_l, g.diff_l, ish1, ish2);
     float bw[3];
+#ifdef NMF_BOUNCE_NO_MLP      // experiment only (NMF_NVCC_EXTRA): the kernel without its MLP, to see what the SIMT part alone costs
+    { float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < TC_ONE; ++i) acc += x[i];
+      bw[0] = bw[1] = bw[2] = 1.0f / (1.0f + expf(-acc)); }
+#else
     if (TC) tc_mlp_forward(tc, x, s.brdf_bias, bw);      // all 128 threads: the tile is one tensor-core GEMM
     else if (active) mlp_simt(sm, xcol, x, s.brdf_bias, bw);
+#endif
     const float mip = -logf((float)count) - g.logpdf;                    // microfacet.py:445-448
     if (tw.slot_n != NMF_NO_OWNER) {            // the next tile's sample record: its owner arrived under the MLP above
       const char* rec = (const char*)(a.bs + tw.slot_n);
