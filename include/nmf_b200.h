@@ -491,6 +491,28 @@ int nmf_env_build_sat(const float* bg_mat, int h, int w, float brightness, float
 int nmf_occupancy_from_alpha(const float* alpha, int gx, int gy, int gz, float thres, int pitch, uint32_t* vox, uint32_t* cell,
                              uint32_t* coarse, float* volume, void* stream);
 
+/* Material heads and BRDF MLP of NmfScene from the reference's parameters in one launch (after every optimiser step):
+ * w[i] / b[i] = model.brdf.mlp.{0,2,4}.weight (n_out, n_in) / bias (modules/brdf.py:73-120; 64x66, 64x64, 4x64); outputs:
+ * wt[i] = the transposed fp32 weights (brdf_w{i}t), bo[i] = bias copies (brdf_b{i}), w16[i] / wbf[i] = the tensor-core operand
+ * tiles brdf_w{i}u (fp16) / brdf_w{i}b (bf16): [80/8][rows][8], rows = 64, 64, 16, bias in input column 66, zero padding.
+ * head_w[h] / head_b[h] = model.diffuse_module.{diffuse,tint,f0,roughness}_mlp.0.weight (rows,24) / bias
+ * (modules/render_modules.py:519-574), concatenated into head_w_out [11][24] / head_b_out [11].  NULL w[i] / head_w[h]: skipped. */
+typedef struct NmfShadingPack {
+  const float* w[3];
+  const float* b[3];
+  int32_t n_out[3], n_in[3];
+  const float* head_w[4];
+  const float* head_b[4];
+  int32_t head_rows[4];
+  float* wt[3];
+  float* bo[3];
+  void* w16[3];
+  void* wbf[3];
+  float* head_w_out;
+  float* head_b_out;
+} NmfShadingPack;
+int nmf_pack_shading(const NmfShadingPack* p, void* stream);
+
 /* Gradient hand-over after a training step: the kernels accumulate gradients channel-last ([texel][channel]); the
  * reference's parameters are channel-first ((1,C,H,W) planes, (1,C,N,1) lines, (out,in) linear weights; fields/tensoRF.py:
  * 42-75, modules/brdf.py:73-120).  One launch moves every tensor: job j writes dst[c * n + i] = src[i * c + ch] (c = 1: a copy).

@@ -71,6 +71,13 @@ class NmfMicrofacetGrads(C.Structure):
                 ("normals", NmfNormalGrads)]
 
 
+class NmfShadingPack(C.Structure):
+    _fields_ = [("w", C.c_void_p * 3), ("b", C.c_void_p * 3), ("n_out", C.c_int32 * 3), ("n_in", C.c_int32 * 3),
+                ("head_w", C.c_void_p * 4), ("head_b", C.c_void_p * 4), ("head_rows", C.c_int32 * 4),
+                ("wt", C.c_void_p * 3), ("bo", C.c_void_p * 3), ("w16", C.c_void_p * 3), ("wbf", C.c_void_p * 3),
+                ("head_w_out", C.c_void_p), ("head_b_out", C.c_void_p)]
+
+
 class NmfTransposeJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_uint64), ("c", C.c_int32), ("pad", C.c_int32)]
 
@@ -194,6 +201,7 @@ def lib():
         "nmf_bench_gather": (I, [P, C.c_size_t, I, I, I, P, P]),
         "nmf_transpose_batch": (I, [P, I, I, P]),
         "nmf_env_pair_sat": (I, [P, I, I, P, P]),
+        "nmf_pack_shading": (I, [C.POINTER(NmfShadingPack), P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
                                 C.c_size_t, P]),
     }
@@ -213,4 +221,4 @@ EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_pr
             "nmf_render_train_workspace_bytes", "nmf_render_rays_train", "nmf_l1_reg", "nmf_grad_sq_norm", "nmf_adam_step",
             "nmf_env_lookup_bwd_scatter", "nmf_env_lookup_bwd_finish", "nmf_env_lookup_bwd_mipbias", "nmf_vm_normals_bwd_scatter",
             "nmf_vm_normals_bwd_finish", "nmf_material_heads_bwd", "nmf_train_microfacet", "nmf_bench_gather", "nmf_pack_factor", "nmf_env_build_sat",
-            "nmf_occupancy_from_alpha", "nmf_transpose_batch", "nmf_env_pair_sat"]
+            "nmf_occupancy_from_alpha", "nmf_transpose_batch", "nmf_env_pair_sat", "nmf_pack_shading"]

@@ -11,6 +11,8 @@
 //                                lattice -> voxel bit-field, per-cell OR of the 8 corners, conservative coarse field
 // All of them stream their input once; bytes per element are stated at each kernel.
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 #include "../../include/nmf_b200.h"
@@ -308,6 +310,51 @@ __global__ void __launch_bounds__(256) k_transpose_batch(const NmfTransposeJob* 
 extern "C" int nmf_transpose_batch(const NmfTransposeJob* jobs_dev, int n_jobs, int blocks_per_job, void* stream) {
   if (!jobs_dev || n_jobs <= 0 || blocks_per_job <= 0) return NMF_E_ARG;
   k_transpose_batch<<<dim3((unsigned)blocks_per_job, (unsigned)n_jobs), 256, 0, (cudaStream_t)stream>>>(jobs_dev);
+  CKL();
+  return NMF_OK;
+}
+
+// ---- material heads + BRDF MLP operands (modules/render_modules.py:519-574, modules/brdf.py:73-120) in ONE launch ----
+// per layer i: wt[k][o] = W[o][k] (fp32, for the SIMT paths), bias copy, and the tensor-core tiles: W (rows out, K in) ->
+// [K/8][rows][8] with K zero-padded to 80, the bias in column 66 (it multiplies the constant-1 input), rows padded to
+// 64 / 64 / 16 -- once in fp16 (forward, csrc/nmf_mlp_tc.cuh) and once in bf16 (reverse pass, csrc/nmf_mlp_tc_bwd.cuh).
+// (The torch version of this was ~40 small launches and 0.3 ms of host time per training iteration.)
+__global__ void __launch_bounds__(256) k_pack_shading(const NmfShadingPack a) {
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = 0; i < 3; ++i) {
+    const int O = a.n_out[i], K = a.n_in[i], rows = i == 2 ? 16 : 64;
+    if (!a.w[i]) continue;
+    for (int e = t0; e < O * K; e += stride) {
+      const int o = e / K, k = e - o * K;
+      a.wt[i][(size_t)k * O + o] = a.w[i][e];
+    }
+    for (int e = t0; e < O; e += stride) a.bo[i][e] = a.b[i][e];
+    for (int e = t0; e < rows * 80; e += stride) {
+      const int r = e / 80, k = e - r * 80;
+      float v = 0.f;
+      if (r < O) v = k < K ? a.w[i][(size_t)r * K + k] : (k == 66 ? a.b[i][r] : 0.f);
+      const size_t q = (size_t)(k >> 3) * rows * 8 + (size_t)r * 8 + (k & 7);
+      if (a.w16[i]) ((__half*)a.w16[i])[q] = __float2half_rn(v);
+      if (a.wbf[i]) ((__nv_bfloat16*)a.wbf[i])[q] = __float2bfloat16_rn(v);
+    }
+  }
+  int row0 = 0;
+  for (int h = 0; h < 4; ++h) {
+    const int R = a.head_rows[h];
+    if (a.head_w[h]) {
+      for (int e = t0; e < R * 24; e += stride) a.head_w_out[row0 * 24 + e] = a.head_w[h][e];
+      for (int e = t0; e < R; e += stride) a.head_b_out[row0 + e] = a.head_b[h][e];
+    }
+    row0 += R;
+  }
+}
+extern "C" int nmf_pack_shading(const NmfShadingPack* p, void* stream) {
+  if (!p) return NMF_E_ARG;
+  for (int i = 0; i < 3; ++i)
+    if (p->w[i] && (!p->b[i] || !p->wt[i] || !p->bo[i] || p->n_in[i] > 66 || p->n_out[i] > (i == 2 ? 16 : 64))) return NMF_E_ARG;
+  for (int h = 0; h < 4; ++h)
+    if (p->head_w[h] && (!p->head_b[h] || !p->head_w_out || !p->head_b_out)) return NMF_E_ARG;
+  k_pack_shading<<<16, 256, 0, (cudaStream_t)stream>>>(*p);
   CKL();
   return NMF_OK;
 }

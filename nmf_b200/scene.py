@@ -147,6 +147,8 @@ class DeviceScene:
         """Material heads (render_modules.py:519-574) and the BRDF MLP (modules/brdf.py:177-261) + the Sobol table."""
         dev, s = self.device, self.c
         g = lambda k: torch.as_tensor(state[k]).detach().to(device=dev, dtype=torch.float32).contiguous()
+        if dev.type == "cuda" and not getattr(self, "_torch_pack", False):
+            return self._pack_shading_cuda(state, g, heads, brdf)
         if heads:
             hw = torch.cat([g(f"model.diffuse_module.{h}_mlp.0.weight") for h in ("diffuse", "tint", "f0", "roughness")])
             hb = torch.cat([g(f"model.diffuse_module.{h}_mlp.0.bias") for h in ("diffuse", "tint", "f0", "roughness")])
@@ -176,6 +178,49 @@ class DeviceScene:
                 sob = g("model.brdf_sampler.angs")
                 assert sob.shape[0] >= 400 and sob.shape[1] == 2
                 self._ptr(s, "sobol", sob)
+
+    def _pack_shading_cuda(self, state, g, heads, brdf):
+        """_pack_shading as ONE nmf_pack_shading launch into persistent buffers (the NmfScene pointers stay valid across the
+        optimiser steps of a training run)."""
+        from .ops import _stream
+        dev, s = self.device, self.c
+        pk = _lib.NmfShadingPack()
+        hold = []                                   # keeps the (possibly converted) sources alive until the launch is queued
+
+        def out(name, shape, dtype=torch.float32):
+            t = self.keep.get(name)
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+                t = torch.zeros(*shape, device=dev, dtype=dtype)
+                self._ptr(s, name, t)
+            return t
+        if heads:
+            hw, hb = out("head_w", (11, 24)), out("head_b", (11,))
+            pk.head_w_out, pk.head_b_out = hw.data_ptr(), hb.data_ptr()
+            for i, (h, rows) in enumerate((("diffuse", 3), ("tint", 3), ("f0", 3), ("roughness", 2))):
+                w, b = g(f"model.diffuse_module.{h}_mlp.0.weight"), g(f"model.diffuse_module.{h}_mlp.0.bias")
+                assert tuple(w.shape) == (rows, 24), w.shape
+                hold += [w, b]
+                pk.head_w[i], pk.head_b[i], pk.head_rows[i] = w.data_ptr(), b.data_ptr(), rows
+        if brdf:
+            for i, (li, o, k, rows) in enumerate(((0, 64, 66, 64), (2, 64, 64, 64), (4, 4, 64, 16))):
+                w, b = g(f"model.brdf.mlp.{li}.weight"), g(f"model.brdf.mlp.{li}.bias")
+                assert tuple(w.shape) == (o, k), w.shape
+                hold += [w, b]
+                pk.w[i], pk.b[i], pk.n_out[i], pk.n_in[i] = w.data_ptr(), b.data_ptr(), o, k
+                pk.wt[i] = out(f"brdf_w{i}t", (k, o)).data_ptr()
+                pk.bo[i] = out(f"brdf_b{i}", (o,)).data_ptr()
+                pk.w16[i] = out(f"brdf_w{i}u", (10, rows, 8), torch.float16).data_ptr()
+                pk.wbf[i] = out(f"brdf_w{i}b", (10, rows, 8), torch.bfloat16).data_ptr()
+            if self.hp.get("mlp", "f16") not in ("f16", "fp32"):
+                raise _lib.NmfError("mlp must be 'f16' (tcgen05, fp16 operands / fp32 accumulate) or 'fp32' (SIMT)")
+            s.mlp_mode = 0 if self.hp.get("mlp", "f16") == "f16" else 1
+            if "model.brdf_sampler.angs" in state:
+                sob = g("model.brdf_sampler.angs")
+                assert sob.shape[0] >= 400 and sob.shape[1] == 2
+                if "sobol" not in self.keep or self.keep["sobol"].data_ptr() != sob.data_ptr():
+                    self._ptr(s, "sobol", sob)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().nmf_pack_shading(C.byref(pk), _stream()), "nmf_pack_shading")
 
     @classmethod
     def shading_only(cls, state, device="cuda", heads=True, brdf=True, **hp):

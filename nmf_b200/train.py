@@ -974,44 +974,6 @@ class MicrofacetTrainer(PlainTrainer):
         self.finish_into_bucket()
         return super().apply(n_rays_local, loss_local, normaliser)
 
-    def step(self, rays, gt, ray_ids=None, ray_id0=None, **kw):
-        """One iteration with ONE sub-batch, ordered so that the host's launch work overlaps the device: the training step,
-        the finishing passes and the gradient hand-over are queued back to back, THEN the counters are read (first sync:
-        overflow check, kept rays = the loss normaliser, losses), then all-reduce + FusedAdam + re-pack; the second sync
-        (environment scalars, needed by value for the next forward) comes after the packing kernels are queued."""
-        if self.grads is None:
-            self.grads = MicrofacetGradBuffers(self.scene)
-        self.grads.scene = self.scene
-        id0 = ((self.seed * 7919 + self._calls) << 20) if ray_id0 is None else int(ray_id0)
-        buffers = self.buffers
-        while True:
-            self.grads.zero_()
-            self._subs = 1
-            out = train_microfacet(self.scene, rays, gt, seed=self.seed + self._calls, ray_id0=id0, max_samples=self.max_samples,
-                                   min_rough=self.min_rough, lambda_pred=self.lambda_pred, lambda_ori=self.lambda_ori,
-                                   detach_N=self.detach_N, grads=self.grads, zero_grads=False, buffers=buffers, check_errors=False, **kw)
-            buffers = out["buffers"]
-            self.finish_into_bucket()                  # speculative: overwritten by the repeat if a list overflowed
-            try:
-                train_microfacet_readback(out)
-                break
-            except _lib.NmfOverflow:
-                from . import ops
-                if buffers.cap_scale >= 32:
-                    raise
-                buffers = ops.RenderBuffers(self.scene, buffers.n_rays, buffers.n_rays, ops.TRAIN_KEYS, cap_scale=buffers.cap_scale * 2,
-                                            train=True)
-        self._calls += 1
-        self.buffers = buffers
-        ns = out["n_samples"]
-        out["n_samples_all"] = list(ns)
-        out["n_samples"] = ns[0]
-        if len(ns) > 1 and self.scene.c.max_retrace > 0:
-            self.update_n_samples(ns[1])
-        n, loss = PlainTrainer.apply(self, out["n_rays"], out["loss_photo"])
-        out["mse"] = loss / max(3.0 * n, 1.0)
-        return out
-
     def finish_into_bucket(self):
         """After the last sub-batch of an iteration: the two whole-image finishing passes, then this rank's gradient of every
         parameter (plus the density L1 term) is written into the flat bucket the all-reduce and FusedAdam work on."""

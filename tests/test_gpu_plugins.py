@@ -301,6 +301,9 @@ def test_repack_kernels_match_the_torch_pack(name):
         for k in ("dpack", "lpack"):
             x, y = a.keep[f"{k}{p}"], b.keep[f"{k}{p}"].reshape(a.keep[f"{k}{p}"].shape)
             assert float((x - y).abs().max()) <= 2e-6 * max(1.0, float(y.abs().max())), (k, p, float((x - y).abs().max()))
+    # material heads and BRDF MLP operands (nmf_pack_shading): fp32 copies, fp16 and bf16 tensor-core tiles, bit-equal
+    for k in ["head_w", "head_b"] + [f"brdf_{n}{i}{sfx}" for i in range(3) for n, sfx in (("w", "t"), ("b", ""), ("w", "u"), ("w", "b"))]:
+        assert a.keep[k].dtype == b.keep[k].dtype and torch.equal(a.keep[k], b.keep[k].reshape(a.keep[k].shape)), k
     sa, sb = a.keep["env_sat"], b.keep["env_sat"]
     rel = float(((sa - sb).abs() / (sb.abs() + 1e-6)).max())
     assert rel < 3e-7, rel                                     # at most the last bit of a prefix (fp64 scan order)
