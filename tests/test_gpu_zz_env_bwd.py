@@ -251,7 +251,7 @@ def test_material_heads_gradient_on_device(env, n):
 def test_standalone_device_check(env):
     """tests/hostcheck/devcheck (built by __graft_entry__.build): the reverse-pass kernels against their host restatements on
     random inputs, straight through the C ABI without Python -- the check that first ran them on a B200
-    (profiles/r01_h_devcheck_reverse_kernels.log)."""
+    (log of the current kernels: profiles/r02_g_devcheck_reverse_kernels.log)."""
     import os
     import subprocess
     exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck", "devcheck")
