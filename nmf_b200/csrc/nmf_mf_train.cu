@@ -50,6 +50,18 @@ static int m_sm_count() {
   return m_sms;
 }
 
+// persistent grids are sized to exactly one resident wave (SMs x CTAs that fit): the tile lists of a training batch are short
+// (1-3 tiles per CTA), so a grid larger than the resident set costs a whole extra round of tiles on the SMs that get a late CTA
+template <class K>
+static int m_resident(K kernel, int threads, size_t smem, int* cache) {
+  if (!*cache) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+    *cache = nb * m_sm_count();
+  }
+  return *cache;
+}
+
 template <int N>
 __device__ __forceinline__ void seg_sumN(float (&v)[N], const Seg& g, int lane) {
 #pragma unroll
@@ -792,6 +804,10 @@ struct MfSampleBwdArgs {
   float lambda_ori; int detach_N; float min_rough; MfGradPtrs g; int cap_vs;
 };
 #define SB_T 128
+#ifndef NMF_SB_UNROLL
+#define NMF_SB_UNROLL 1        // gather groups of the normal in flight per thread (experiments: NMF_NVCC_EXTRA=-DNMF_SB_UNROLL=2)
+#endif
+constexpr int kSbUnroll = NMF_SB_UNROLL;
 #define SB_FS 25
 #define SB_CS 73
 #define SB_FLOATS (11 * 24 + 12 + SB_T * (SB_FS + 12 + SB_CS + SB_FS))
@@ -826,7 +842,7 @@ __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const 
       nmf_normalize_xyz(s, p, xn);
       const NmfTaps tp = nmf_vm_taps(s, xn);
       float grad[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
+#pragma unroll kSbUnroll
       for (int l = 0; l < 8; ++l) nmf_normal_lane(s, tp, l, grad);
       const nmf_v3 nrm = nmf_normal_from_grad(s, grad);
       const nmf_v3 V = nmf_mk3(q1.x, q1.y, q1.z);
@@ -1070,10 +1086,10 @@ extern "C" int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp_i
   MfLossArgs la = {w.accum0, w.acc0, tr->whole_valid, gt, n, tp->lambda_pred, w.g_lin0, tp->loss, w.stat4};
   k_mf_loss<<<(n + 255) / 256, 256, 0, cs>>>(la);
   CKL();
-  const int grid_tiles = m_sm_count() * 4;
+  static int g_tang = 0, g_bb0 = 0, g_bb1 = 0, g_sb0 = 0, g_sb1 = 0, g_ori = 0;
   if (retrace) {
     MfTangArgs ta = {w.bs1, w.brays1, w.owner1, w.ray_count1, w.cap_rays1, w.tile_start1, nc, w.jac1};
-    k_mf_tangent1<<<grid_tiles, MLP_THREADS, 0, cs>>>(s, ta);
+    k_mf_tangent1<<<m_resident(k_mf_tangent1, MLP_THREADS, 0, &g_tang), MLP_THREADS, 0, cs>>>(s, ta);
     CKL();
     k_mf_sec_tangent<<<(w.n_rays1 + 127) / 128, 128, 0, cs>>>(s, w.rays1, w.mip1, w.acc1, w.n_sec, s.max_retrace, w.n_rays1, w.jac1);
     CKL();
@@ -1083,7 +1099,7 @@ extern "C" int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp_i
   b0.tile_start = w.tile_start0; b0.n_chunks = nc; b0.g_lin = w.g_lin0; b0.rgb1 = w.rgb1; b0.jac1 = w.jac1; b0.g_lin1 = w.g_lin1;
   b0.max_retrace = s.max_retrace; b0.bgrad = w.bgrad0; b0.vdw = w.vdw0; b0.dout = w.dout0; b0.gsat = grads->gsat;
   b0.d_mipbias = grads->d_mipbias; b0.detach_N = tp->detach_N;
-  k_mf_bounce_bwd<0><<<grid_tiles, MLP_THREADS, 0, cs>>>(s, b0);
+  k_mf_bounce_bwd<0><<<m_resident(k_mf_bounce_bwd<0>, MLP_THREADS, 0, &g_bb0), MLP_THREADS, 0, cs>>>(s, b0);
   CKL();
   if (retrace) {
     k_mf_sec_bwd<<<(w.n_rays1 + 127) / 128, 128, 0, cs>>>(s, w.rays1, w.mip1, w.acc1, w.n_sec, s.max_retrace, w.n_rays1, w.g_lin1,
@@ -1093,7 +1109,7 @@ extern "C" int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp_i
     b1.bs = w.bs1; b1.brays = w.brays1; b1.owner = w.owner1; b1.ray_count = w.ray_count1; b1.cap_rays = w.cap_rays1;
     b1.tile_start = w.tile_start1; b1.n_chunks = nc; b1.g_lin = w.g_lin1; b1.bgrad = w.bgrad1; b1.vdw = w.vdw1; b1.dout = w.dout1;
     b1.gsat = grads->gsat; b1.d_mipbias = grads->d_mipbias; b1.detach_N = tp->detach_N;
-    k_mf_bounce_bwd<1><<<grid_tiles, MLP_THREADS, 0, cs>>>(s, b1);
+    k_mf_bounce_bwd<1><<<m_resident(k_mf_bounce_bwd<1>, MLP_THREADS, 0, &g_bb1), MLP_THREADS, 0, cs>>>(s, b1);
     CKL();
   }
   static bool attr_done = false;
@@ -1138,16 +1154,16 @@ extern "C" int nmf_train_microfacet(const NmfScene* scene, const NmfRender* rp_i
   gp.basis_t = grads->basis_t; gp.head_w = grads->head_w; gp.head_b = grads->head_b;
   MfSampleBwdArgs s0 = {w.bs0, w.n_bs, w.cap_bs0, rays, w.zvals0, s.n_steps, w.surv0, w.n_surv, w.cap_surv0, w.survv0, w.survslot0,
                         w.bgrad0, w.vdw0, tp->lambda_ori, tp->detach_N, tr->min_rough, gp, w.cap_vs0};
-  k_mf_sample_bwd<0><<<m_sm_count() * 2, SB_T, SB_FLOATS * sizeof(float), cs>>>(s, s0);
+  k_mf_sample_bwd<0><<<m_resident(k_mf_sample_bwd<0>, SB_T, SB_FLOATS * sizeof(float), &g_sb0), SB_T, SB_FLOATS * sizeof(float), cs>>>(s, s0);
   CKL();
   if (tp->lambda_ori != 0.f) {
-    k_mf_ori_bwd<<<m_sm_count() * 4, 128, 0, cs>>>(s, s0);
+    k_mf_ori_bwd<<<m_resident(k_mf_ori_bwd, 128, 0, &g_ori), 128, 0, cs>>>(s, s0);
     CKL();
   }
   if (retrace) {
     MfSampleBwdArgs s1 = {w.bs1, w.n_bs + 1, w.cap_bs1, w.rays1, w.zvals1, s.n_steps, w.surv1, w.n_surv + 1, w.cap_surv1, w.survv1,
                           w.survslot1, w.bgrad1, w.vdw1, 0.f, tp->detach_N, tr->min_rough, gp, w.cap_vs1};
-    k_mf_sample_bwd<1><<<m_sm_count() * 2, SB_T, SB_FLOATS * sizeof(float), cs>>>(s, s1);
+    k_mf_sample_bwd<1><<<m_resident(k_mf_sample_bwd<1>, SB_T, SB_FLOATS * sizeof(float), &g_sb1), SB_T, SB_FLOATS * sizeof(float), cs>>>(s, s1);
     CKL();
   }
   MfCompArgs c0 = {};
