@@ -181,3 +181,27 @@ def test_gradient_hand_over_in_one_launch_matches_the_views(env):
     for k, v in views.items():
         assert torch.equal(dst[k], v.contiguous()), k
     assert sum(float(v.abs().max()) > 0 for v in views.values()) >= 25
+
+
+def test_microfacet_train_step_edge_batches(env):
+    """Edge cases of one nmf_train_microfacet call: a batch whose rays all miss the box (no samples: the loss is the photometric
+    term against the white background, every gradient is exactly zero, nothing overflows or divides by zero), a single ray, and
+    a batch size that is not a multiple of anything (ragged tiles everywhere)."""
+    from nmf_b200 import train
+    fix = load_fixture("microfacet_g40")
+    dsc = device_scene(fix, env, max_retrace_rays=(64,), max_brdf_rays=(650000, 20000))
+    n = 37
+    o = torch.tensor([0.0, 0.0, 4.0]).repeat(n, 1)
+    d = torch.nn.functional.normalize(torch.tensor([0.0, 0.0, 1.0]) + 0.01 * torch.randn(n, 3, generator=torch.Generator().manual_seed(0)), dim=-1)
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(1))
+    out = train.train_microfacet(dsc, torch.cat([o, d], 1).cuda(), gt.cuda(), focal=fix["focal"], seed=1)
+    assert out["n_samples"][0] == 0 and out["n_rays"] == n
+    assert abs(out["loss_photo"] - float(((1.0 - gt) ** 2).sum())) < 1e-4
+    assert all(float(v.abs().max()) == 0.0 for k, v in out["grads"].t.items() if k != "gsat"), \
+        [k for k, v in out["grads"].t.items() if float(v.abs().max()) != 0.0]
+    for m in (1, 131):
+        rays = fix["rays"][:m].contiguous().cuda()
+        g1 = torch.rand(m, 3, generator=torch.Generator().manual_seed(2)).cuda()
+        o1 = train.train_microfacet(dsc, rays, g1, focal=fix["focal"], seed=1, detach_N=False)
+        assert o1["n_rays"] == m and o1["rgb_map"].shape == (m, 3) and bool(torch.isfinite(o1["rgb_map"]).all())
+        assert all(bool(torch.isfinite(v).all()) for v in o1["grads"].t.values())
