@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NMF_ABI_VERSION 9
+#define NMF_ABI_VERSION 10
 #define NMF_APP_STRIDE 24      /* floats per appearance texel; 32 (a 128-byte texel) was measured: no gain, +9 MB of L2 footprint */
 
 #define NMF_OK 0
@@ -147,6 +147,9 @@ typedef struct NmfScene {
    * instead of two 16-byte loads -- the environment kernels are bound by L1 data-pipe wavefronts, one per lane-load.
    * Built by nmf_env_pair_sat; costs h*w*32 bytes of L2 footprint, so the host only builds it for maps up to 512 x 1024. */
   const float* env_sat2;
+  /* optional (NULL = use env_mipbias / env_top / env_bot above): 7 device floats { mipbias, top rgb, bottom rgb } written by
+   * nmf_env_build_sat_dev -- the per-step values of a training run stay on the device (no host round trip per iteration) */
+  const float* env_dyn;
 } NmfScene;
 
 /* per-call render parameters */
@@ -372,6 +375,10 @@ typedef struct NmfAdam {
   int step;
   float grad_scale;        /* 1 / lbatch_size (train.py:709) */
   float max_norm;          /* params.clip_grad; <= 0: off */
+  /* optional device memory { grad_scale, skip }: when not NULL the loss normaliser is read from control[0] instead of
+   * grad_scale (the number of kept rays of a training step stays on the device) and control[1] != 0 turns the whole update into
+   * a no-op (a device-side list overflowed during the step: the host repeats the iteration with larger buffers) */
+  const float* control;
 } NmfAdam;
 int nmf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const NmfAdam* adam,
                   const double* sq_norm, void* stream);
@@ -388,6 +395,10 @@ int nmf_env_lookup_bwd_scatter(const NmfScene* scene, const float* dirs, const f
  * d_mul[0] += ... (device scalars).  bg_mat is the (3,h,w) parameter, brightness / mul its scalar parameters. */
 int nmf_env_lookup_bwd_finish(float* gsat, int h, int w, const float* bg_mat, float brightness, float mul,
                               float* d_bg_mat, float* d_brightness, float* d_mul, void* stream);
+/* The same with the parameters read from device memory: scalars_dev = { brightness, mul, mipbias } (fp32), so that a training
+ * iteration never needs them on the host. */
+int nmf_env_lookup_bwd_finish_dev(float* gsat, int h, int w, const float* bg_mat, const float* scalars_dev, float* d_bg_mat,
+                                  float* d_brightness, float* d_mul, void* stream);
 
 /* d loss / d IntegralEquirect.mipbias of a batch of lookups (the box size moves with the bias: sa2mip,
  * integral_equirect.py:373-397): d_mipbias[0] (device float) += sum_i g_i . d rgb_i / d mipbias. */
@@ -482,6 +493,10 @@ int nmf_pack_factor(const float* src, int C, int H, int W, const float* kx25, co
  * rounding to fp32 after each scan (ATen's CPU cumsum), pole_sums[6] (device, fp64) = sums of the first / last row of act
  * per channel.  scratch_c1: 3*h*w floats. */
 int nmf_env_pair_sat(const float* sat4, int h, int w, float* sat8, void* stream);    /* NmfScene.env_sat2 from sat4 */
+/* nmf_env_build_sat with device-resident parameters: scalars_dev = { brightness, mul, mipbias } (fp32 device memory); also writes
+ * env_dyn[7] = { mipbias, pole_sums[0..2] / w, pole_sums[3..5] / w } = what NmfScene.env_dyn points at. */
+int nmf_env_build_sat_dev(const float* bg_mat, int h, int w, const float* scalars_dev, float* scratch_c1, float* act, float* sat4,
+                          double* pole_sums, float* env_dyn, void* stream);
 int nmf_env_build_sat(const float* bg_mat, int h, int w, float brightness, float mul, float* scratch_c1, float* act,
                       float* sat4, double* pole_sums, void* stream);
 

@@ -41,7 +41,7 @@ class NmfScene(C.Structure):
         ("rays_per_ray", C.c_int), ("max_brdf_rays1", C.c_int), ("max_retrace", C.c_int), ("model", C.c_int),
         ("brdf_w0u", C.c_void_p), ("brdf_w1u", C.c_void_p), ("brdf_w2u", C.c_void_p), ("mlp_mode", C.c_int),
         ("brdf_w0b", C.c_void_p), ("brdf_w1b", C.c_void_p), ("brdf_w2b", C.c_void_p),
-        ("env_sat2", C.c_void_p),
+        ("env_sat2", C.c_void_p), ("env_dyn", C.c_void_p),
     ]
 
 
@@ -99,7 +99,8 @@ class NmfTrainOut(C.Structure):
 
 class NmfAdam(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("weight_decay", C.c_float), ("step", C.c_int), ("grad_scale", C.c_float), ("max_norm", C.c_float)]
+                ("weight_decay", C.c_float), ("step", C.c_int), ("grad_scale", C.c_float), ("max_norm", C.c_float),
+                ("control", C.c_void_p)]
 
 
 class NmfRenderTrain(C.Structure):
@@ -202,6 +203,8 @@ def lib():
         "nmf_transpose_batch": (I, [P, I, I, P]),
         "nmf_env_pair_sat": (I, [P, I, I, P, P]),
         "nmf_pack_shading": (I, [C.POINTER(NmfShadingPack), P]),
+        "nmf_env_build_sat_dev": (I, [P, I, I, P, P, P, P, P, P, P]),
+        "nmf_env_lookup_bwd_finish_dev": (I, [P, I, I, P, P, P, P, P, P]),
         "nmf_train_plain": (I, [SP, C.POINTER(NmfTrain), P, P, C.POINTER(NmfPlainGrads), C.POINTER(NmfTrainOut), P,
                                 C.c_size_t, P]),
     }
@@ -209,7 +212,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    assert L.nmf_abi_version() == 9, "libnmf_b200.so ABI mismatch: rebuild"
+    assert L.nmf_abi_version() == 10, "libnmf_b200.so ABI mismatch: rebuild"
     _lib = L
     return L
 
@@ -221,4 +224,4 @@ EXPORTED = ["nmf_abi_version", "nmf_profile_enable", "nmf_profile_read", "nmf_pr
             "nmf_render_train_workspace_bytes", "nmf_render_rays_train", "nmf_l1_reg", "nmf_grad_sq_norm", "nmf_adam_step",
             "nmf_env_lookup_bwd_scatter", "nmf_env_lookup_bwd_finish", "nmf_env_lookup_bwd_mipbias", "nmf_vm_normals_bwd_scatter",
             "nmf_vm_normals_bwd_finish", "nmf_material_heads_bwd", "nmf_train_microfacet", "nmf_bench_gather", "nmf_pack_factor", "nmf_env_build_sat",
-            "nmf_occupancy_from_alpha", "nmf_transpose_batch", "nmf_env_pair_sat", "nmf_pack_shading"]
+            "nmf_occupancy_from_alpha", "nmf_transpose_batch", "nmf_env_pair_sat", "nmf_pack_shading", "nmf_env_build_sat_dev", "nmf_env_lookup_bwd_finish_dev"]

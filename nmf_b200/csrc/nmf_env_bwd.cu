@@ -23,7 +23,7 @@ __global__ void k_env_bwd_scatter(const NmfScene s, const float* __restrict__ di
   if (i >= n) return;
   const float gi[3] = {g[3 * i], g[3 * i + 1], g[3 * i + 2]};
   if (gi[0] == 0.f && gi[1] == 0.f && gi[2] == 0.f) return;
-  nmf_env_lookup1_bwd_map(gsat, s.env_h, s.env_w, s.env_mipbias, nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), mip[i], gi,
+  nmf_env_lookup1_bwd_map(gsat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), mip[i], gi,
                           g_top, g_bot);
 }
 
@@ -65,8 +65,10 @@ __global__ void __launch_bounds__(SCAN_T) k_env_bwd_scan_x(float4* __restrict__ 
 #define ENVB_SEG 16
 __global__ void __launch_bounds__(256) k_env_bwd_finish(const float* __restrict__ gsat, int h, int w, const float* __restrict__ g_top,
                                                         const float* __restrict__ g_bot, const float* __restrict__ bg, float brightness,
-                                                        float mul, float* __restrict__ d_bg, float* d_brightness, float* d_mul) {
+                                                        float mul, const float* __restrict__ scalars_dev, float* __restrict__ d_bg,
+                                                        float* d_brightness, float* d_mul) {
   __shared__ float tot[ENVB_SEG][16][3];
+  if (scalars_dev) { brightness = scalars_dev[0]; mul = scalars_dev[1]; }      // device-resident parameters (training)
   const int col = threadIdx.x & 15, seg = threadIdx.x >> 4;
   const int x = blockIdx.x * 16 + col;
   const int R = (h + ENVB_SEG - 1) / ENVB_SEG;
@@ -129,7 +131,7 @@ __global__ void k_env_bwd_mipbias(const NmfScene s, const float* __restrict__ di
     const float gi[3] = {g[3 * i], g[3 * i + 1], g[3 * i + 2]};
     if (gi[0] != 0.f || gi[1] != 0.f || gi[2] != 0.f) {
       float rgb[3], d[3];
-      nmf_env_lookup1_dmipbias(s.env_sat, s.env_h, s.env_w, s.env_mipbias, s.env_top, s.env_bot,
+      nmf_env_lookup1_dmipbias(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s),
                                nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), mip[i], rgb, d);
       acc = gi[0] * d[0] + gi[1] * d[1] + gi[2] * d[2];
     }
@@ -157,14 +159,24 @@ extern "C" int nmf_env_lookup_bwd_scatter(const NmfScene* scene, const float* di
   return NMF_OK;
 }
 
-extern "C" int nmf_env_lookup_bwd_finish(float* gsat, int h, int w, const float* bg_mat, float brightness, float mul, float* d_bg_mat,
-                                       float* d_brightness, float* d_mul, void* stream) {
+static int env_bwd_finish_impl(float* gsat, int h, int w, const float* bg_mat, float brightness, float mul, const float* scalars_dev,
+                               float* d_bg_mat, float* d_brightness, float* d_mul, void* stream) {
   if (!gsat || !bg_mat || !d_bg_mat || h <= 0 || w <= 0) return NMF_E_ARG;
   const float* poles = gsat + (size_t)h * w * 4;
   k_env_bwd_scan_x<<<h, SCAN_T, 0, (cudaStream_t)stream>>>((float4*)gsat, w);
   CKL();
-  k_env_bwd_finish<<<(w + 15) / 16, 256, 0, (cudaStream_t)stream>>>(gsat, h, w, poles, poles + 4, bg_mat, brightness, mul, d_bg_mat,
-                                                                       d_brightness, d_mul);
+  k_env_bwd_finish<<<(w + 15) / 16, 256, 0, (cudaStream_t)stream>>>(gsat, h, w, poles, poles + 4, bg_mat, brightness, mul, scalars_dev,
+                                                                       d_bg_mat, d_brightness, d_mul);
   CKL();
   return NMF_OK;
+}
+extern "C" int nmf_env_lookup_bwd_finish(float* gsat, int h, int w, const float* bg_mat, float brightness, float mul, float* d_bg_mat,
+                                       float* d_brightness, float* d_mul, void* stream) {
+  return env_bwd_finish_impl(gsat, h, w, bg_mat, brightness, mul, nullptr, d_bg_mat, d_brightness, d_mul, stream);
+}
+// the same with brightness / mul read from device memory (scalars_dev = { brightness, mul, ... }): no host copy of the parameters
+extern "C" int nmf_env_lookup_bwd_finish_dev(float* gsat, int h, int w, const float* bg_mat, const float* scalars_dev, float* d_bg_mat,
+                                           float* d_brightness, float* d_mul, void* stream) {
+  if (!scalars_dev) return NMF_E_ARG;
+  return env_bwd_finish_impl(gsat, h, w, bg_mat, 0.f, 1.f, scalars_dev, d_bg_mat, d_brightness, d_mul, stream);
 }

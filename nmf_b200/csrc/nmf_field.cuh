@@ -5,6 +5,12 @@
 #include "../../include/nmf_b200.h"
 #include "nmf_math.cuh"
 
+// The three environment quantities that change with every optimiser step (mipbias and the pole-row means) are read from
+// device memory when NmfScene.env_dyn is set, so that a training iteration does not need them on the host
+#define NMF_ENV_MIPBIAS(s) ((s).env_dyn ? (s).env_dyn[0] : (s).env_mipbias)
+#define NMF_ENV_TOP(s) ((s).env_dyn ? (s).env_dyn + 1 : (s).env_top)
+#define NMF_ENV_BOT(s) ((s).env_dyn ? (s).env_dyn + 4 : (s).env_bot)
+
 #ifdef __CUDACC__
 typedef float4 nmf_f4;
 #else

@@ -100,8 +100,10 @@ extern "C" int nmf_pack_factor(const float* src, int C, int H, int W, const floa
 // thread per column walking all rows took 259 us at 512 x 1024).  c1: (3, h, w) fp32 scratch.  Also the pole-row sums.
 #define ENV_SEG 16
 __global__ void __launch_bounds__(256) k_env_act_scan_y(const float* __restrict__ bg, int h, int w, float brightness, float mul,
-                                                        float* __restrict__ c1, float* __restrict__ act_out, double* __restrict__ pole) {
+                                                        const float* __restrict__ scalars_dev, float* __restrict__ c1,
+                                                        float* __restrict__ act_out, double* __restrict__ pole) {
   __shared__ double tot[ENV_SEG][16];
+  if (scalars_dev) { brightness = scalars_dev[0]; mul = scalars_dev[1]; }      // device-resident parameters (training)
   const int col = threadIdx.x & 15, seg = threadIdx.x >> 4;
   const int cpb = (w + 15) / 16;                       // CTAs per channel
   const int k = blockIdx.x / cpb, x = (blockIdx.x - k * cpb) * 16 + col;
@@ -168,19 +170,40 @@ extern "C" int nmf_env_pair_sat(const float* sat4, int h, int w, float* sat8, vo
   return NMF_OK;
 }
 
+// env_dyn = { mipbias, top rgb, bottom rgb }: what NmfScene.env_dyn points at
+__global__ void k_env_dyn_finish(const double* __restrict__ pole, int w, const float* __restrict__ scalars_dev, float* __restrict__ env_dyn) {
+  const int t = threadIdx.x;
+  if (t == 0) env_dyn[0] = scalars_dev[2];
+  if (t < 6) env_dyn[1 + t] = (float)(pole[t] / (double)w);
+}
+static int env_build_sat_impl(const float* bg_mat, int h, int w, float brightness, float mul, const float* scalars_dev, float* scratch_c1,
+                              float* act, float* sat4, double* pole_sums, float* env_dyn, void* stream);
 extern "C" int nmf_env_build_sat(const float* bg_mat, int h, int w, float brightness, float mul, float* scratch_c1, float* act,
                                  float* sat4, double* pole_sums, void* stream) {
+  return env_build_sat_impl(bg_mat, h, w, brightness, mul, nullptr, scratch_c1, act, sat4, pole_sums, nullptr, stream);
+}
+extern "C" int nmf_env_build_sat_dev(const float* bg_mat, int h, int w, const float* scalars_dev, float* scratch_c1, float* act,
+                                     float* sat4, double* pole_sums, float* env_dyn, void* stream) {
+  if (!scalars_dev || !env_dyn) return NMF_E_ARG;
+  return env_build_sat_impl(bg_mat, h, w, 0.f, 1.f, scalars_dev, scratch_c1, act, sat4, pole_sums, env_dyn, stream);
+}
+static int env_build_sat_impl(const float* bg_mat, int h, int w, float brightness, float mul, const float* scalars_dev, float* scratch_c1,
+                              float* act, float* sat4, double* pole_sums, float* env_dyn, void* stream) {
   if (!bg_mat || !scratch_c1 || !sat4 || !pole_sums || h <= 0 || w <= 0) return NMF_E_ARG;
   cudaStream_t cs = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(pole_sums, 0, 6 * sizeof(double), cs);
   if (e != cudaSuccess) return (int)e;
-  k_env_act_scan_y<<<3 * ((w + 15) / 16), 256, 0, cs>>>(bg_mat, h, w, brightness, mul, scratch_c1, act, pole_sums);
+  k_env_act_scan_y<<<3 * ((w + 15) / 16), 256, 0, cs>>>(bg_mat, h, w, brightness, mul, scalars_dev, scratch_c1, act, pole_sums);
   CKL();
   k_env_scan_x<<<(3 * h * 32 + 255) / 256, 256, 0, cs>>>(scratch_c1, h, w, sat4);
   CKL();
   const size_t n = (size_t)h * w;
   k_env_pad<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(sat4, n);
   CKL();
+  if (env_dyn) {
+    k_env_dyn_finish<<<1, 32, 0, cs>>>(pole_sums, w, scalars_dev, env_dyn);
+    CKL();
+  }
   return NMF_OK;
 }
 

@@ -709,8 +709,11 @@ __global__ void __launch_bounds__(256) k_sq_norm(const float* __restrict__ g, si
 }
 
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                              float* __restrict__ v, size_t n, const NmfAdamScalars h, const double* sq_norm) {
-  const float gmul = h.grad_scale * (sq_norm ? nmf_clip_coef(*sq_norm, h.grad_scale, h.max_norm) : 1.0f);
+                                              float* __restrict__ v, size_t n, const NmfAdamScalars h, const double* sq_norm,
+                                              const float* __restrict__ control) {
+  if (control && control[1] != 0.f) return;                       // the step overflowed a list: no update (NmfAdam.control)
+  const float gs = control ? control[0] : h.grad_scale;
+  const float gmul = gs * (sq_norm ? nmf_clip_coef(*sq_norm, gs, h.max_norm) : 1.0f);
   const bool al = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
   const size_t n4 = al ? n / 4 : 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -760,7 +763,7 @@ extern "C" int nmf_adam_step(float* param, const float* grad, float* exp_avg, fl
   h.bc2_sqrt = (float)sqrt(1.0 - pow(b2, (double)a->step));
   h.grad_scale = a->grad_scale;
   h.max_norm = a->max_norm;
-  k_adam<<<stream_grid(n, 8), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, h, sq_norm);
+  k_adam<<<stream_grid(n, 8), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, h, sq_norm, a->control);
   CKL();
   return NMF_OK;
 }

@@ -358,7 +358,7 @@ class DeviceScene:
         self._pack_factors(state, derivatives=False)
         self._pack_plain_mlp(state)
 
-    def refresh_microfacet(self, state, env_scalars=None):
+    def refresh_microfacet(self, state, env_scalars=None, dev_scalars=None):
         """After an optimiser step of model=microfacet_tensorf2: re-packs the factors (with their smoothed-difference
         planes), the material heads / BRDF MLP operands and the environment tables (SAT, pole rows, SH irradiance) from the
         updated parameters; the occupancy is left alone (the reference rebuilds it on its schedule only)."""
@@ -370,6 +370,8 @@ class DeviceScene:
         if "sobol" not in self.keep and keep_sobol is not None:
             self._ptr(self.c, "sobol", keep_sobol)
         if "bg_module.bg_mat" in state:
+            if dev_scalars is not None:       # [brightness, mul, mipbias] stay on the device: no host round trip at all
+                return self._set_env(state, None, dev_scalars=dev_scalars)
             if env_scalars is not None:       # host copies of brightness / mul / mipbias, fetched AFTER the packing kernels
                 state = dict(state)           # above are queued (the fetch synchronises)
                 state.update(env_scalars())
@@ -387,7 +389,7 @@ class DeviceScene:
                        "bg_module.mul": mul}, None)
         return self
 
-    def _set_env(self, state, sh_conv):
+    def _set_env(self, state, sh_conv, dev_scalars=None):
         s, dev, model = self.c, self.device, self.hp["model"]
         f32 = lambda t: torch.as_tensor(t).detach().to(device=dev, dtype=torch.float32).contiguous()
         bg = f32(state["bg_module.bg_mat"])
@@ -398,6 +400,9 @@ class DeviceScene:
             return float(v.detach()) if torch.is_tensor(v) else float(v)
         eh, ew = bg.shape[-2], bg.shape[-1]
         cuda_pack = dev.type == "cuda" and not getattr(self, "_torch_pack", False)
+        if dev_scalars is not None and cuda_pack:
+            return self._set_env_device(bg, dev_scalars, sh_conv)
+        s.env_dyn = None                              # host mode: the kernels read env_mipbias / env_top / env_bot
         brightness, mul = (hostf("bg_module.brightness", 0.0), hostf("bg_module.mul", 1.0)) if cuda_pack else \
             (to64("bg_module.brightness", 0.0), to64("bg_module.mul", 1.0))
         if cuda_pack:
@@ -443,6 +448,47 @@ class DeviceScene:
             if sh_conv is None:
                 sh_conv = self.sh_irradiance()
             self._ptr(s, "sh_conv", f32(sh_conv))
+
+    def _set_env_device(self, bg, dev_scalars, sh_conv=None):
+        """_set_env without any host round trip (training): dev_scalars = fp32 device tensor [brightness, mul, mipbias]; the
+        tables are built by nmf_env_build_sat_dev, the three quantities the kernels otherwise take by value (mipbias, the pole-row
+        means) are left in device memory (NmfScene.env_dyn)."""
+        from .ops import _p, _stream
+        s, dev = self.c, self.device
+        eh, ew = bg.shape[-2], bg.shape[-1]
+        sat4 = self.keep.get("env_sat")
+        if sat4 is None or tuple(sat4.shape) != (eh, ew, 4) or "env_c1" not in self.keep:
+            sat4 = torch.empty(eh, ew, 4, device=dev, dtype=torch.float32)
+            self.keep["env_c1"] = torch.empty(3, eh, ew, device=dev, dtype=torch.float32)
+            self.keep["env_pole"] = torch.zeros(6, device=dev, dtype=torch.float64)
+        dyn = self.keep.get("env_dyn")
+        if dyn is None:
+            dyn = torch.zeros(8, device=dev, dtype=torch.float32)
+        sc = dev_scalars.detach().to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().nmf_env_build_sat_dev(_p(bg), eh, ew, _p(sc), _p(self.keep["env_c1"]), None, _p(sat4),
+                                                        _p(self.keep["env_pole"]), _p(dyn), _stream()), "nmf_env_build_sat_dev")
+            if eh * ew <= 512 * 1024:
+                sat8 = self.keep.get("env_sat2")
+                if sat8 is None or tuple(sat8.shape) != (eh, ew, 8):
+                    sat8 = torch.empty(eh, ew, 8, device=dev, dtype=torch.float32)
+                _lib.check(_lib.lib().nmf_env_pair_sat(_p(sat4), eh, ew, _p(sat8), _stream()), "nmf_env_pair_sat")
+                self._ptr(s, "env_sat2", sat8)
+            else:
+                self.keep.pop("env_sat2", None)
+                s.env_sat2 = None
+        self._ptr(s, "env_sat", sat4)
+        self._ptr(s, "env_dyn", dyn)
+        s.env_h, s.env_w = eh, ew
+        self.env_act = None
+        if self.hp["model"] == "microfacet":
+            if sh_conv is None:
+                sh_conv = self.sh_irradiance()
+            old = self.keep.get("sh_conv")
+            if old is not None and old.shape == sh_conv.shape and old.dtype == torch.float32:
+                old.copy_(sh_conv)
+            else:
+                self._ptr(s, "sh_conv", sh_conv.float().contiguous())
 
     def _ptr(self, s, name, t):
         self.keep[name] = t

@@ -205,7 +205,7 @@ class MicrofacetGradBuffers:
         self.flat.zero_()
         self.finished = False
 
-    def finish(self, bg_mat, brightness, mul):
+    def finish(self, bg_mat, brightness, mul, scalars_dev=None):
         """Once per optimiser step, after the last sub-batch: the adjoint of the environment's double cumsum + activation
         (nmf_env_lookup_bwd_finish -> d bg_mat, d brightness, d mul) and of the 5x5 smoothed-difference stencil
         (nmf_vm_normals_bwd_finish, added into the density-factor gradients)."""
@@ -213,11 +213,16 @@ class MicrofacetGradBuffers:
             raise _lib.NmfError("MicrofacetGradBuffers.finish: already finished (zero_() starts the next step)")
         L, dev = _lib.lib(), self.scene.device
         bg = _f32(bg_mat.reshape(3, self.eh, self.ew), dev)
-        br, mu = (float(v.detach()) if torch.is_tensor(v) else float(v) for v in (brightness, mul))
         with torch.cuda.device(dev):
             sc = self.t["d_env_scalars"]
-            _lib.check(L.nmf_env_lookup_bwd_finish(_p(self.t["gsat"]), self.eh, self.ew, _p(bg), br, mu, _p(self.t["d_bg"]),
-                                                   _p(sc[0:1]), _p(sc[1:2]), _stream()), "nmf_env_lookup_bwd_finish")
+            if scalars_dev is not None:       # [brightness, mul, ...] as fp32 device memory: no host copy of the parameters
+                sd = scalars_dev.detach().to(device=dev, dtype=torch.float32).contiguous()
+                _lib.check(L.nmf_env_lookup_bwd_finish_dev(_p(self.t["gsat"]), self.eh, self.ew, _p(bg), _p(sd), _p(self.t["d_bg"]),
+                                                           _p(sc[0:1]), _p(sc[1:2]), _stream()), "nmf_env_lookup_bwd_finish_dev")
+            else:
+                br, mu = (float(v.detach()) if torch.is_tensor(v) else float(v) for v in (brightness, mul))
+                _lib.check(L.nmf_env_lookup_bwd_finish(_p(self.t["gsat"]), self.eh, self.ew, _p(bg), br, mu, _p(self.t["d_bg"]),
+                                                       _p(sc[0:1]), _p(sc[1:2]), _stream()), "nmf_env_lookup_bwd_finish")
             pp = (C.c_void_p * 3)(*[self.t[f"d_plane{p}"].data_ptr() for p in range(3)])
             lp = (C.c_void_p * 3)(*[self.t[f"d_line{p}"].data_ptr() for p in range(3)])
             _lib.check(L.nmf_vm_normals_bwd_finish(self.scene.ref(), C.byref(self.c.normals), _p(self.kx), _p(self.ky), pp, lp,
@@ -445,7 +450,9 @@ class FusedAdam:
     def n_launches(self):
         return sum(len(g["runs"]) for g in self.groups) + (1 if self.clip_grad > 0 else 0)
 
-    def step(self, grad_scale=1.0):
+    def step(self, grad_scale=1.0, control=None):
+        """control: optional fp32 device tensor [grad_scale, skip] (NmfAdam.control): the loss normaliser is read from device
+        memory and skip != 0 makes the whole update a no-op (the caller then also takes back the step count: `self.t -= 1`)."""
         L = _lib.lib()
         with torch.cuda.device(self.device):
             st = _stream()
@@ -465,7 +472,7 @@ class FusedAdam:
                 b1, b2 = self.betas if g.get("betas") is None else (float(g["betas"][0]), float(g["betas"][1]))
                 a = _lib.NmfAdam(lr=g["lr"] * lam, beta1=b1, beta2=b2, eps=self.eps,
                                  weight_decay=self.weight_decay, step=self.t, grad_scale=float(grad_scale),
-                                 max_norm=self.clip_grad)
+                                 max_norm=self.clip_grad, control=None if control is None else control.data_ptr())
                 for run, n, m, v in g["runs"]:
                     if run[0].grad is None:
                         continue
@@ -922,8 +929,13 @@ class MicrofacetTrainer(PlainTrainer):
             self._env_host_cache = None
         super().repack(rebuild)
 
+    def _env_dev(self):
+        """[brightness, mul, mipbias] as one fp32 device tensor (one small gather launch, no synchronisation)."""
+        return torch.stack([self.params[k].detach().reshape(()).float() for k in self.ENV_SCALARS])
+
     def _refresh_scene(self, st):
-        self.scene.refresh_microfacet(st, env_scalars=lambda: self._env_host(refresh=True))
+        self._env_host_cache = None
+        self.scene.refresh_microfacet(st, dev_scalars=self._env_dev())
 
     def _on_reinit(self):
         self.scene.update_hyper(max_retrace_rays=tuple(self.start_max_retrace))      # Microfacet.reset_counter
@@ -974,13 +986,66 @@ class MicrofacetTrainer(PlainTrainer):
         self.finish_into_bucket()
         return super().apply(n_rays_local, loss_local, normaliser)
 
+    def step(self, rays, gt, ray_ids=None, ray_id0=None, **kw):
+        """One iteration with ONE sub-batch and ONE host synchronisation, at its end: the step, the finishing passes, the
+        gradient hand-over, the all-reduce, FusedAdam and the scene re-pack are queued back to back, so the host's launch work
+        overlaps the device.  What the host used to wait for stays on the device: the loss normaliser (global number of kept
+        rays) and the overflow flag go to the optimiser through NmfAdam.control, the environment scalars through
+        NmfScene.env_dyn.  If a device-side list overflowed (on any rank) the update was a no-op; the iteration is repeated
+        with larger buffers."""
+        import torch.distributed as dist
+        from . import ops
+        on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self.grads is None:
+            self.grads = MicrofacetGradBuffers(self.scene)
+        self.grads.scene = self.scene
+        id0 = ((self.seed * 7919 + self._calls) << 20) if ray_id0 is None else int(ray_id0)
+        while True:
+            self.grads.zero_()
+            self._subs = 1
+            out = train_microfacet(self.scene, rays, gt, seed=self.seed + self._calls, ray_id0=id0, max_samples=self.max_samples,
+                                   min_rough=self.min_rough, lambda_pred=self.lambda_pred, lambda_ori=self.lambda_ori,
+                                   detach_N=self.detach_N, grads=self.grads, zero_grads=False, buffers=self.buffers,
+                                   check_errors=False, **kw)
+            buffers = self.buffers = out["buffers"]
+            self.finish_into_bucket()
+            tot = torch.stack([buffers.n_kept[0].double(), buffers.loss3[0], buffers.counters["error"][0].double()])
+            if on:
+                dist.all_reduce(tot)                          # global kept rays, loss, overflow flag
+            self.bucket.allreduce(scale=1.0)                  # one flat fp32 all-reduce (NCCL on GPUs)
+            control = torch.stack([1.0 / tot[0].clamp(min=1.0), (tot[2] != 0).double()]).float()
+            self.optimizer.step(grad_scale=1.0, control=control)
+            self.repack(rebuild=False)
+            overflow = False
+            try:
+                train_microfacet_readback(out)                # the iteration's one synchronisation
+            except _lib.NmfOverflow:
+                overflow = True
+                if buffers.cap_scale >= 32:
+                    raise
+                self.buffers = ops.RenderBuffers(self.scene, buffers.n_rays, buffers.n_rays, ops.TRAIN_KEYS,
+                                                 cap_scale=buffers.cap_scale * 2, train=True)
+            n_glob, loss_glob, err_glob = tot.tolist()
+            if overflow or err_glob != 0:                     # the update was skipped on every rank: take the step count back
+                self.optimizer.t -= 1
+                continue
+            break
+        self._calls += 1
+        self.iteration += 1
+        ns = out["n_samples"]
+        out["n_samples_all"] = list(ns)
+        out["n_samples"] = ns[0]
+        if len(ns) > 1 and self.scene.c.max_retrace > 0:
+            self.update_n_samples(ns[1])
+        out["mse"] = loss_glob / max(3.0 * n_glob, 1.0)
+        return out
+
     def finish_into_bucket(self):
         """After the last sub-batch of an iteration: the two whole-image finishing passes, then this rank's gradient of every
         parameter (plus the density L1 term) is written into the flat bucket the all-reduce and FusedAdam work on."""
         import torch.distributed as dist
         p = self.params
-        eh = self._env_host()
-        self.grads.finish(p["bg_module.bg_mat"].data, eh["bg_module.brightness"], eh["bg_module.mul"])
+        self.grads.finish(p["bg_module.bg_mat"].data, None, None, scalars_dev=self._env_dev())
         self.grads.copy_into({k: q.grad for k, q in p.items()})
         if self.l1_weight > 0:            # train.py:675-678 adds the density L1 term to EVERY sub-batch's loss
             world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1

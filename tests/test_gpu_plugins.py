@@ -315,3 +315,47 @@ def test_repack_kernels_match_the_torch_pack(name):
     assert (a.c.ow, a.c.oh, a.c.od, a.c.opitch, a.c.ocw, a.c.och, a.c.ocd) == (b.c.ow, b.c.oh, b.c.od, b.c.opitch, b.c.ocw, b.c.och, b.c.ocd)
     # 5000 lookups at mip -5 over tables that may differ in the last bit of a prefix (sub-texel boxes on an HDR map amplify it)
     assert float((a.keep["sh_conv"] - b.keep["sh_conv"]).abs().max()) <= 1e-3 * float(b.keep["sh_conv"].abs().max())
+
+
+def test_device_resident_environment_scalars_match_the_host_path():
+    """NmfScene.env_dyn (mipbias and the pole-row means read from device memory, tables built by nmf_env_build_sat_dev from
+    device-resident brightness / mul / mipbias) against the host path that passes them by value: the same tables bit for bit,
+    the same render, the same environment-map gradient finishing pass."""
+    from conftest import device_scene, load_fixture
+    from nmf_b200 import ops, train
+    fix = load_fixture("microfacet_g40")
+    fix = dict(fix, state=dict(fix["state"]))
+    fix["state"]["bg_module.brightness"] = torch.tensor(0.4, dtype=torch.float64)
+    fix["state"]["bg_module.mul"] = torch.tensor(1.3, dtype=torch.float64)
+    fix["state"]["bg_module.mipbias"] = torch.tensor(0.7, dtype=torch.float64)
+    a = device_scene(fix, "cuda:0")
+    b = device_scene(fix, "cuda:0")
+    sc = torch.tensor([0.4, 1.3, 0.7], device="cuda")
+    st = {k: torch.as_tensor(v) for k, v in fix["state"].items()}
+    b._set_env(st, None, dev_scalars=sc)
+    assert b.c.env_dyn and not a.c.env_dyn
+    assert torch.equal(a.keep["env_sat"], b.keep["env_sat"])
+    dyn = b.keep["env_dyn"].cpu()
+    assert abs(float(dyn[0]) - a.c.env_mipbias) < 1e-7
+    for i in range(3):
+        assert abs(float(dyn[1 + i]) - a.c.env_top[i]) <= 1e-6 * abs(a.c.env_top[i])
+        assert abs(float(dyn[4 + i]) - a.c.env_bot[i]) <= 1e-6 * abs(a.c.env_bot[i])
+    assert torch.allclose(a.keep["sh_conv"], b.keep["sh_conv"], rtol=1e-6, atol=1e-7)
+    rays = fix["rays"][:256].cuda()
+    ia, _ = ops.render_rays(a, rays, fix["focal"], chunk=128, seed=3)
+    ib, _ = ops.render_rays(b, rays, fix["focal"], chunk=128, seed=3)
+    assert float((ia["rgb_map"] - ib["rgb_map"]).abs().max()) <= 2e-6
+    # directions at the poles exercise env_top / env_bot read through the pointer
+    d = torch.tensor([[0.0, 0.0, 1.0], [0.0, 0.0, -1.0], [1e-3, 0.0, 1.0], [0.3, 0.2, -0.9]], device="cuda")
+    d = torch.nn.functional.normalize(d, dim=-1)
+    mip = torch.full((4,), -3.0, device="cuda")
+    assert torch.allclose(ops.env_lookup(a, d, mip), ops.env_lookup(b, d, mip), rtol=1e-6, atol=1e-7)
+    # the gradient finishing pass with device scalars
+    ga, gb = train.MicrofacetGradBuffers(a), train.MicrofacetGradBuffers(b)
+    noise = torch.randn(ga.t["gsat"].shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    ga.t["gsat"].copy_(noise); gb.t["gsat"].copy_(noise)
+    bg = torch.as_tensor(fix["state"]["bg_module.bg_mat"]).float().cuda()
+    ga.finish(bg, 0.4, 1.3)
+    gb.finish(bg, None, None, scalars_dev=sc)
+    assert torch.equal(ga.t["d_bg"], gb.t["d_bg"])
+    assert torch.allclose(ga.t["d_env_scalars"], gb.t["d_env_scalars"], rtol=1e-5)      # sums of per-warp atomics: order varies

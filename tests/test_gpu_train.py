@@ -628,3 +628,35 @@ def test_microfacet_trainer_fits_a_teacher(env):
     assert not tr.detach_N and tr.min_rough < 0.2                      # models/microfacet.py:112-121
     assert np.isfinite(mse).all() and np.mean(mse[-5:]) < 0.6 * np.mean(mse[:3]), (mse[:3], mse[-5:])
     assert tr.scene.hp["max_retrace_rays"][0] != 1000                   # the adaptive re-trace budget moved (microfacet.py:241-268)
+
+
+def test_microfacet_step_repeats_an_overflowed_iteration(env):
+    """MicrofacetTrainer.step has ONE host synchronisation, at its end: the loss normaliser and the overflow flag reach FusedAdam
+    through device memory (NmfAdam.control).  With scratch lists that are far too small the first pass overflows, the update is a
+    no-op on the device, and the repeated iteration (larger lists, same random numbers) produces the gradients and the step count
+    of a trainer that never overflowed; both agree with the serial accumulate + apply path."""
+    from nmf_b200 import ops, train
+    fix = load_fixture("microfacet_g40")
+    G = fix["grid_size"]
+    rays = fix["rays"].cuda()
+    gt = torch.rand(rays.shape[0], 3, generator=torch.Generator().manual_seed(4)).cuda()
+    mk = lambda: train.MicrofacetTrainer({k: v.clone() for k, v in fix["state"].items()}, fix["aabb"], fix["near_far"], [G] * 3,
+                                         alpha_volume=fix["alpha_volume"], device=env, max_samples=-1, seed=3)
+    a, b, c = mk(), mk(), mk()
+    n = rays.shape[0]
+    b.buffers = ops.RenderBuffers(b.scene, n, n, ops.TRAIN_KEYS, cap_scale=0.02, train=True)
+    oa, ob = a.step(rays, gt), b.step(rays, gt)
+    assert b.buffers.cap_scale > 0.02 and a.optimizer.t == b.optimizer.t == 1 and a.iteration == b.iteration == 1
+    assert oa["n_rays"] == ob["n_rays"] and oa["n_samples"] == ob["n_samples"] and abs(oa["mse"] - ob["mse"]) <= 1e-5 * oa["mse"]
+    oc = c.accumulate(rays, gt, first=True)                      # the serial path: synchronises after the step
+    c.apply(oc["n_rays"], oc["loss_photo"])
+    rel = lambda x, y: float((x - y).norm() / (y.norm() + 1e-20))
+    for k, q in a.params.items():              # gradients per parameter (fp32 atomics: only the summation order differs run to run)
+        if float(q.grad.abs().max()) == 0.0:
+            continue
+        tol = 2e-2 if q.numel() == 1 else 1e-3          # the 0-dim environment scalars are sums of cancelling terms
+        assert rel(b.params[k].grad, q.grad) < tol and rel(c.params[k].grad, q.grad) < tol, (k, rel(b.params[k].grad, q.grad), rel(c.params[k].grad, q.grad))
+    for k in ("rf.app_rf.app_plane.0", "model.brdf.mlp.0.weight", "bg_module.mipbias"):
+        assert bool(torch.isfinite(b.params[k]).all())
+        assert float((a.params[k] - c.params[k]).abs().max()) <= 2.1 * a.optimizer.groups[0]["lr"]        # Adam: at most +-lr apart per step
+    assert a.scene.c.env_dyn and abs(float(a.scene.keep["env_dyn"][0]) - float(a.params["bg_module.mipbias"])) < 1e-7

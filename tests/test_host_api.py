@@ -21,19 +21,19 @@ def test_library_exports_every_declared_symbol():
     from nmf_b200 import _lib
     assert sorted(_lib.EXPORTED) == declared
     L.nmf_abi_version.restype = ctypes.c_int
-    assert L.nmf_abi_version() == 9
+    assert L.nmf_abi_version() == 10
 
 
 def test_struct_mirror_matches_header_size():
     """ctypes mirror of NmfScene / NmfRender vs the C compiler's layout"""
     import subprocess, tempfile
     from nmf_b200 import _lib
-    src = '#include <stdio.h>\n#include "nmf_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(NmfScene), sizeof(NmfRender), sizeof(NmfImages), sizeof(NmfCounters), sizeof(NmfPlainGrads), sizeof(NmfTrain), sizeof(NmfTrainOut), sizeof(NmfMicrofacetGrads), sizeof(NmfMicrofacetTrain), sizeof(NmfRenderTrain), sizeof(NmfNormalGrads));return 0;}'
+    src = '#include <stdio.h>\n#include "nmf_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(NmfAdam), sizeof(NmfShadingPack), sizeof(NmfTransposeJob), sizeof(NmfScene), sizeof(NmfRender), sizeof(NmfImages), sizeof(NmfCounters), sizeof(NmfPlainGrads), sizeof(NmfTrain), sizeof(NmfTrainOut), sizeof(NmfMicrofacetGrads), sizeof(NmfMicrofacetTrain), sizeof(NmfRenderTrain), sizeof(NmfNormalGrads));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
-    assert sizes == [ctypes.sizeof(_lib.NmfScene), ctypes.sizeof(_lib.NmfRender), ctypes.sizeof(_lib.NmfImages),
+    assert sizes == [ctypes.sizeof(_lib.NmfAdam), ctypes.sizeof(_lib.NmfShadingPack), ctypes.sizeof(_lib.NmfTransposeJob), ctypes.sizeof(_lib.NmfScene), ctypes.sizeof(_lib.NmfRender), ctypes.sizeof(_lib.NmfImages),
                      ctypes.sizeof(_lib.NmfCounters), ctypes.sizeof(_lib.NmfPlainGrads), ctypes.sizeof(_lib.NmfTrain),
                      ctypes.sizeof(_lib.NmfTrainOut), ctypes.sizeof(_lib.NmfMicrofacetGrads), ctypes.sizeof(_lib.NmfMicrofacetTrain),
                      ctypes.sizeof(_lib.NmfRenderTrain), ctypes.sizeof(_lib.NmfNormalGrads)]

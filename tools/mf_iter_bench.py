@@ -35,8 +35,7 @@ for it in range(a.steps + 3):
     rec = it >= 3
     ms, out = timed(lambda: tr.accumulate(rays, gt, first=True));
     if rec: add("accumulate (zero + nmf_train_microfacet)", ms)
-    eh = tr._env_host()
-    ms, _ = timed(lambda: tr.grads.finish(p["bg_module.bg_mat"].data, eh["bg_module.brightness"], eh["bg_module.mul"]))
+    ms, _ = timed(lambda: tr.grads.finish(p["bg_module.bg_mat"].data, None, None, scalars_dev=tr._env_dev()))
     if rec: add("grads.finish (env scans, stencil adjoint)", ms)
     ms, _ = timed(lambda: tr.grads.copy_into({k: q.grad for k, q in p.items()}))
     if rec: add("gradient hand-over -> bucket (nmf_transpose_batch)", ms)
@@ -51,13 +50,11 @@ for it in range(a.steps + 3):
     ms, _ = timed(lambda: tr.optimizer.step(grad_scale=1.0 / a.rays))
     if rec: add("FusedAdam", ms)
     st = dict(tr.state); st.update({k: q.detach() for k, q in p.items()})
-    ms, _ = timed(lambda: st.update(tr._env_host(refresh=True)))
-    if rec: add("env scalars -> host (one copy)", ms)
     ms, _ = timed(lambda: tr.scene._pack_factors(st, derivatives=True))
     if rec: add("repack: factors", ms)
     ms, _ = timed(lambda: tr.scene._pack_shading(st))
     if rec: add("repack: shading", ms)
-    ms, _ = timed(lambda: tr.scene._set_env(st, None))
+    ms, _ = timed(lambda: tr.scene._set_env(st, None, dev_scalars=tr._env_dev()))
     if rec: add("repack: env", ms)
 parts = {k: round(v / a.steps, 4) for k, v in parts.items()}
 # un-instrumented iterations, CUDA events and wall clock
