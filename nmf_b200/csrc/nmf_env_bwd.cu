@@ -6,8 +6,9 @@
 //                                  (nmf_env_lookup1_bwd_map, host-checked against autograd in tests/test_hostmath.py);
 //                                  fp32 atomics into an [h][w][4] image that stays L2-resident (8 MB at 512 x 1024)
 //              k_env_bwd_scan_x    reverse inclusive prefix sum along x, one CTA per map row (adjoint of cumsum over x)
-//              k_env_bwd_finish    reverse prefix sum along y fused with the pole-row means and the exp activation's chain rule:
-//                                  d bg_mat (accumulated), d brightness, d mul -- one thread per (column, channel), coalesced rows
+//              k_env_bwd_finish    reverse prefix sum along y (16 row segments per column, segment totals through shared memory)
+//                                  fused with the pole-row means and the exp activation's chain rule: d bg_mat (accumulated),
+//                                  d brightness, d mul; brightness / mul by value or from device memory (training)
 // Both passes stream the 8 MB image once: HBM/L2-bound, 2 x (read + write) of h*w*16 bytes + the (3,h,w) parameter and gradient.
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -8,10 +8,11 @@
 //   k_shade<0>     per warp, 32 survivors: gather phase (8 lanes per sample: appearance taps, 3xTF32 mma.sync basis
 //                  contraction, smoothed-gradient normal) + shade phase (1 lane per sample: material heads, SH
 //                  irradiance, bounce count, debug maps, A19 sums, bounce-sample record incl. the per-sample GGX frame)
-//   k_tile_prefix  flat list of 128-ray tiles over the per-chunk bounce-ray regions
+//   k_tile_prefix  flat list of 128-ray tiles over the per-chunk bounce-ray regions + per-tile descriptors (TileWalk)
 //   k_bounce<0>    persistent CTAs, thread per bounce ray: Sobol + GGX VNDF sample, ISH encodings, BRDF MLP on
 //                  tcgen05 (fp16 operands, TMEM accumulators, TMA-staged weights), retrace score
-//   k_select       CTA per chunk: radix-select of the top max_retrace scores -> secondary rays
+//   k_select       per chunk (a CTA, or a thread-block cluster with DSMEM histograms when there are few chunks):
+//                  radix-select of the top max_retrace scores -> secondary rays
 //   k_march<1>, k_shade<1>, k_bounce<1>, k_incoming<1>, k_finish1: the retraced rays (recur = 1)
 //   k_incoming<0>  per primary bounce ray: retraced radiance or environment lookup, Fresnel mix, per-sample sums
 //   k_reduce0      per bounce sample: mean over its rays, composite into the pixel

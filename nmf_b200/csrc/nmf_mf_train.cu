@@ -213,7 +213,10 @@ struct MfBounceBwdArgs {
   float* gsat; float* d_mipbias; int detach_N;
 };
 template <int LEVEL>
-__global__ void __launch_bounds__(MLP_THREADS) k_mf_bounce_bwd(const NmfScene s, const MfBounceBwdArgs a) {
+#ifndef NMF_BB_MINBLOCKS
+#define NMF_BB_MINBLOCKS 1      // experiments: NMF_NVCC_EXTRA=-DNMF_BB_MINBLOCKS=4 caps the kernel at 128 registers
+#endif
+__global__ void __launch_bounds__(MLP_THREADS, NMF_BB_MINBLOCKS) k_mf_bounce_bwd(const NmfScene s, const MfBounceBwdArgs a) {
   const int n_tiles = a.tile_start[a.n_chunks];
   const int lane = threadIdx.x & 31;
   float* g_top = a.gsat + (size_t)s.env_h * s.env_w * 4;
