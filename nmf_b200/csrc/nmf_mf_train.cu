@@ -813,7 +813,7 @@ struct MfSampleBwdArgs {
 constexpr int kSbUnroll = NMF_SB_UNROLL;
 #define SB_FS 25
 #define SB_CS 73
-#define SB_FLOATS (11 * 24 + 12 + SB_T * (SB_FS + 12 + SB_CS + SB_FS))
+#define SB_FLOATS (11 * 24 + 12 + SB_T * (SB_FS + 12 + SB_CS + SB_FS) + 72 * 24)
 template <int LEVEL>
 __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const MfSampleBwdArgs a) {
   extern __shared__ __align__(16) float ssm[];
@@ -822,9 +822,11 @@ __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const 
   float* DL = F + SB_T * SB_FS;          // [128][12] d loss / d head pre-activations
   float* CO = DL + SB_T * 12;            // [128][73] appearance coefficients
   float* DF = CO + SB_T * SB_CS;         // [128][25] d loss / d feature
+  float* BT = DF + SB_T * SB_FS;         // [72][24] basis_t: the two 24 x 72 matrix-vector products read it as broadcast float4 rows
   const int t = threadIdx.x;
   for (int q = t; q < 11 * 24; q += SB_T) sW[q] = s.head_w[q];
   if (t < 11) sB[t] = s.head_b[t];
+  for (int q = t; q < 72 * 24; q += SB_T) BT[q] = s.basis_t[q];
   __syncthreads();
   const int n = min(*a.n_bs, a.cap_bs);
   for (int base = blockIdx.x * SB_T; base < n; base += gridDim.x * SB_T) {
@@ -864,15 +866,23 @@ __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const 
         nmf_app_coef(s, tp, coef);
 #pragma unroll 1
         for (int j = 0; j < 72; ++j) co[j] = coef[j];
+        // feat = basis_t^T coef (tensoRF.py:405): register-blocked -- one broadcast float4 row piece of basis_t per 4 FMAs, the
+        // 72 coefficients and 24 outputs statically indexed (a rolled output loop kept both operands in local / global memory:
+        // two L1 loads per FMA, 13 stall cycles per issued instruction)
         float feat[24];
-#pragma unroll 1
-        for (int oo = 0; oo < 24; ++oo) {
-          float acc = 0.f;
-#pragma unroll 8
-          for (int j = 0; j < 72; ++j) acc += __ldg(s.basis_t + j * 24 + oo) * coef[j];
-          feat[oo] = acc;
-          fr[oo] = acc;
+#pragma unroll
+        for (int oo = 0; oo < 24; ++oo) feat[oo] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 72; ++j) {
+          const float cj = coef[j];
+#pragma unroll
+          for (int q4 = 0; q4 < 6; ++q4) {
+            const float4 b4 = *(const float4*)(BT + j * 24 + 4 * q4);
+            feat[4 * q4] += b4.x * cj; feat[4 * q4 + 1] += b4.y * cj; feat[4 * q4 + 2] += b4.z * cj; feat[4 * q4 + 3] += b4.w * cj;
+          }
         }
+#pragma unroll
+        for (int oo = 0; oo < 24; ++oo) fr[oo] = feat[oo];
         float sh[9];
         nmf_sh9(nrm, sh);
         float g_alb[3], dR0[3];
@@ -906,11 +916,14 @@ __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const 
           dfr[kk] = acc;
         }
         float dcoef[72];
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 72; ++j) {
           float acc = 0.f;
 #pragma unroll
-          for (int oo = 0; oo < 24; ++oo) acc += __ldg(s.basis_t + j * 24 + oo) * df[oo];
+          for (int q4 = 0; q4 < 6; ++q4) {
+            const float4 b4 = *(const float4*)(BT + j * 24 + 4 * q4);
+            acc += b4.x * df[4 * q4] + b4.y * df[4 * q4 + 1] + b4.z * df[4 * q4 + 2] + b4.w * df[4 * q4 + 3];
+          }
           dcoef[j] = acc;
         }
         float* ap[3] = {a.g.a_plane[0], a.g.a_plane[1], a.g.a_plane[2]};
@@ -935,27 +948,45 @@ __global__ void __launch_bounds__(SB_T) k_mf_sample_bwd(const NmfScene s, const 
       for (int j = 0; j < 72; ++j) co[j] = 0.f;
     }
     __syncthreads();
-    // tile contractions: d head_w[h][k] = sum_j dlin_j[h] feat_j[k];  d basis_t[jj][oo] = sum_j coef_j[jj] dfeat_j[oo]
-    for (int idx = t; idx < 11 * 24 + 11; idx += SB_T) {
-      float acc = 0.f;
-      if (idx < 11 * 24) {
-        const int h = idx / 24, kk = idx - 24 * h;
-#pragma unroll 8
-        for (int j = 0; j < SB_T; ++j) acc += DL[j * 12 + h] * F[j * SB_FS + kk];
-        if (acc != 0.f) atomicAdd(a.g.head_w + idx, acc);
-      } else {
-        const int h = idx - 11 * 24;
-#pragma unroll 8
-        for (int j = 0; j < SB_T; ++j) acc += DL[j * 12 + h];
-        if (acc != 0.f) atomicAdd(a.g.head_b + h, acc);
+    // tile contractions: d head_w[h][k] = sum_j dlin_j[h] feat_j[k];  d basis_t[jj][oo] = sum_j coef_j[jj] dfeat_j[oo].
+    // Threads 0..95 own a 3 x 6 register block of d basis_t each (9 shared loads per 18 FMAs; one output per thread and trip
+    // cost 2 loads per FMA), threads 96..127 the 275 head outputs.
+    if (t < 96) {
+      const int jb = (t >> 2) * 3, ob = (t & 3) * 6;
+      float acc[3][6];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[r][q] = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < SB_T; ++j) {
+        const float c0 = CO[j * SB_CS + jb], c1 = CO[j * SB_CS + jb + 1], c2 = CO[j * SB_CS + jb + 2];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const float d = DF[j * SB_FS + ob + q];
+          acc[0][q] += c0 * d; acc[1][q] += c1 * d; acc[2][q] += c2 * d;
+        }
       }
-    }
-    for (int idx = t; idx < 72 * 24; idx += SB_T) {
-      const int jj = idx / 24, oo = idx - 24 * jj;
-      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+          if (acc[r][q] != 0.f) atomicAdd(a.g.basis_t + (jb + r) * 24 + ob + q, acc[r][q]);
+    } else {
+      for (int idx = t - 96; idx < 11 * 24 + 11; idx += 32) {
+        float acc = 0.f;
+        if (idx < 11 * 24) {
+          const int h = idx / 24, kk = idx - 24 * h;
 #pragma unroll 8
-      for (int j = 0; j < SB_T; ++j) acc += CO[j * SB_CS + jj] * DF[j * SB_FS + oo];
-      if (acc != 0.f) atomicAdd(a.g.basis_t + idx, acc);
+          for (int j = 0; j < SB_T; ++j) acc += DL[j * 12 + h] * F[j * SB_FS + kk];
+          if (acc != 0.f) atomicAdd(a.g.head_w + idx, acc);
+        } else {
+          const int h = idx - 11 * 24;
+#pragma unroll 8
+          for (int j = 0; j < SB_T; ++j) acc += DL[j * 12 + h];
+          if (acc != 0.f) atomicAdd(a.g.head_b + h, acc);
+        }
+      }
     }
     __syncthreads();
   }
