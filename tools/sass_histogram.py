@@ -1,5 +1,6 @@
 """Per-kernel SASS opcode histograms of libnmf_b200.so (cuobjdump -sass), the evidence for "Blackwell-native" claims:
-UTCHMMA / UTCBAR / LDTM (tcgen05 MMA, commit, TMEM loads), UBLKCP (TMA bulk copies), HMMA (legacy mma.sync), RED / ATOMG.
+UTCHMMA / UTCBAR / LDTM (tcgen05 MMA, commit, TMEM loads), UBLKCP (TMA bulk copies), HMMA (legacy mma.sync), RED / ATOMG,
+LDG.256 / STG.256 (256-bit global accesses, counted in addition to LDG / STG), UCGABAR_ARV (thread-block cluster barrier).
 usage: python tools/sass_histogram.py [out_dir]   -> profiles/sass/<kernel>.txt + profiles/sass/SUMMARY.md"""
 import collections
 import os
@@ -22,9 +23,12 @@ for line in txt.splitlines():
         continue
     m = re.match(r"\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+(?:\.[A-Z0-9_]+)*)", line)
     if m and cur:
-        kernels[cur][m.group(1).split(".")[0]] += 1
+        op = m.group(1)
+        kernels[cur][op.split(".")[0]] += 1
+        if re.match(r"(LDG|STG)\..*\b256\b", op):                     # 256-bit global loads / stores (new on sm_100)
+            kernels[cur][op.split(".")[0] + ".256"] += 1
 KEY = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "HMMA", "RED", "REDG", "ATOMG", "ATOM", "LDG", "STG", "LDS", "STS",
-       "SHFL", "FFMA", "MUFU", "BAR", "SYNCS"]
+       "SHFL", "FFMA", "MUFU", "BAR", "SYNCS", "LDG.256", "STG.256", "UCGABAR_ARV"]
 rows = []
 for mangled, c in sorted(kernels.items()):
     name = demangle(mangled)
