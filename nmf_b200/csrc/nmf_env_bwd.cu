@@ -20,11 +20,12 @@
 
 __global__ void k_env_bwd_scatter(const NmfScene s, const float* __restrict__ dirs, const float* __restrict__ mip,
                                   const float* __restrict__ g, int n, float* gsat, float* g_top, float* g_bot) {
+  const NmfEnvDyn ed = nmf_env_dyn_load(s);     // mipbias and pole means: by value or from NmfScene.env_dyn
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gi[3] = {g[3 * i], g[3 * i + 1], g[3 * i + 2]};
   if (gi[0] == 0.f && gi[1] == 0.f && gi[2] == 0.f) return;
-  nmf_env_lookup1_bwd_map(gsat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), mip[i], gi,
+  nmf_env_lookup1_bwd_map(gsat, s.env_h, s.env_w, ed.mipbias, nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), mip[i], gi,
                           g_top, g_bot);
 }
 
@@ -126,13 +127,14 @@ __global__ void __launch_bounds__(256) k_env_bwd_finish(const float* __restrict_
 // the taps' bilinear weights and 1 / size with it), dotted with the upstream; warp sum, one atomic per warp.
 __global__ void k_env_bwd_mipbias(const NmfScene s, const float* __restrict__ dirs, const float* __restrict__ mip,
                                   const float* __restrict__ g, int n, float* d_mipbias) {
+  const NmfEnvDyn ed = nmf_env_dyn_load(s);     // mipbias and pole means: by value or from NmfScene.env_dyn
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float acc = 0.f;
   if (i < n) {
     const float gi[3] = {g[3 * i], g[3 * i + 1], g[3 * i + 2]};
     if (gi[0] != 0.f || gi[1] != 0.f || gi[2] != 0.f) {
       float rgb[3], d[3];
-      nmf_env_lookup1_dmipbias(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s),
+      nmf_env_lookup1_dmipbias(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot,
                                nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), mip[i], rgb, d);
       acc = gi[0] * d[0] + gi[1] * d[1] + gi[2] * d[2];
     }

@@ -6,10 +6,23 @@
 #include "nmf_math.cuh"
 
 // The three environment quantities that change with every optimiser step (mipbias and the pole-row means) are read from
-// device memory when NmfScene.env_dyn is set, so that a training iteration does not need them on the host
-#define NMF_ENV_MIPBIAS(s) ((s).env_dyn ? (s).env_dyn[0] : (s).env_mipbias)
-#define NMF_ENV_TOP(s) ((s).env_dyn ? (s).env_dyn + 1 : (s).env_top)
-#define NMF_ENV_BOT(s) ((s).env_dyn ? (s).env_dyn + 4 : (s).env_bot)
+// device memory when NmfScene.env_dyn is set, so that a training iteration does not need them on the host.  They are
+// loaded ONCE per kernel into a local struct (forming pointers into the by-value kernel parameter cost 10-15 % on the
+// environment kernels: the parameter block had to be addressable)
+struct NmfEnvDyn { float mipbias, top[3], bot[3]; };
+NMF_HD NmfEnvDyn nmf_env_dyn_load(const NmfScene& s) {
+  NmfEnvDyn e;
+  if (s.env_dyn) {
+    e.mipbias = s.env_dyn[0];
+    e.top[0] = s.env_dyn[1]; e.top[1] = s.env_dyn[2]; e.top[2] = s.env_dyn[3];
+    e.bot[0] = s.env_dyn[4]; e.bot[1] = s.env_dyn[5]; e.bot[2] = s.env_dyn[6];
+  } else {
+    e.mipbias = s.env_mipbias;
+    e.top[0] = s.env_top[0]; e.top[1] = s.env_top[1]; e.top[2] = s.env_top[2];
+    e.bot[0] = s.env_bot[0]; e.bot[1] = s.env_bot[1]; e.bot[2] = s.env_bot[2];
+  }
+  return e;
+}
 
 #ifdef __CUDACC__
 typedef float4 nmf_f4;

@@ -1027,6 +1027,7 @@ struct IncomingArgs {
 };
 template <int LEVEL>
 __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, const IncomingArgs a) {
+  const NmfEnvDyn ed = nmf_env_dyn_load(s);     // mipbias and pole means: by value or from NmfScene.env_dyn
   const int n_tiles = a.tile_start[a.n_chunks];
   const int lane = threadIdx.x & 31;
   TileWalk tw;
@@ -1059,8 +1060,8 @@ __global__ void __launch_bounds__(MLP_THREADS) k_incoming(const NmfScene s, cons
         const float* src = a.rgb1 + ((size_t)chunk * (size_t)a.max_retrace + (size_t)slot) * 4;
         inc[0] = src[0]; inc[1] = src[1]; inc[2] = src[2];
       } else {
-        if (s.env_sat2) nmf_env_lookup1_pair(s.env_sat2, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s), L, q0.w, inc);
-        else nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s), L, q0.w, inc);
+        if (s.env_sat2) nmf_env_lookup1_pair(s.env_sat2, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot, L, q0.w, inc);
+        else nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot, L, q0.w, inc);
       }
       const float4 qv = *(const float4*)b->V, q3 = *(const float4*)b->f0, q4 = *(const float4*)b->diffuse;
       const nmf_v3 H = nmf_unit(nmf_mk3((qv.x + L.x) / 2.0f, (qv.y + L.y) / 2.0f, (qv.z + L.z) / 2.0f));
@@ -1132,12 +1133,13 @@ __global__ void __launch_bounds__(256) k_reduce0(const ReduceArgs a) {
 // retraced rays: linear radiance + (1 - acc) * env(d, mip)   (tensor_nerf.py:460-468, 657-659 with tonemap=False)
 __global__ void k_finish1(const NmfScene s, const float* rays1, const float* mip1, const float* acc1, const float* accum1,
                           const int* n_sec, int max_retrace, int n, float* rgb1) {
+  const NmfEnvDyn ed = nmf_env_dyn_load(s);     // mipbias and pole means: by value or from NmfScene.env_dyn
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int chunk = i / max_retrace;
   if (i - chunk * max_retrace >= n_sec[chunk]) return;
   float bg[3];
-  nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s),
+  nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot,
                   nmf_mk3(rays1[6 * i + 3], rays1[6 * i + 4], rays1[6 * i + 5]), mip1[i], bg);
   const float t = 1.0f - acc1[i];
   rgb1[4 * i] = accum1[4 * i] + t * bg[0];
@@ -1834,10 +1836,11 @@ extern "C" int nmf_vm_normals(const NmfScene* scene, const float* xyz, int n, in
   return NMF_OK;
 }
 __global__ void k_env_lookup(const NmfScene s, const float* dirs, const float* mip, int n, float* out) {
+  const NmfEnvDyn ed = nmf_env_dyn_load(s);     // mipbias and pole means: by value or from NmfScene.env_dyn
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float rgb[3];
-  nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s),
+  nmf_env_lookup1(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot,
                   nmf_mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), mip[i], rgb);
   out[3 * i] = rgb[0]; out[3 * i + 1] = rgb[1]; out[3 * i + 2] = rgb[2];
 }

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(MLP_THREADS) k_mf_tangent1(const NmfScene s, c
 }
 __global__ void k_mf_sec_tangent(const NmfScene s, const float* rays1, const float* mip1, const float* acc1, const int* n_sec,
                                  int max_retrace, int n, float* jac1) {
+  const NmfEnvDyn ed = nmf_env_dyn_load(s);     // mipbias and pole means: by value or from NmfScene.env_dyn
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int chunk = i / max_retrace;
@@ -197,7 +198,7 @@ __global__ void k_mf_sec_tangent(const NmfScene s, const float* rays1, const flo
     NmfDual3 Dd = nmf_d3k(d);
     if (c == 0) Dd.x.d = 1.0f; else if (c == 1) Dd.y.d = 1.0f; else Dd.z.d = 1.0f;
     float bg[3], dbg[3];
-    nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s), Dd, mip1[i], bg, dbg);
+    nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot, Dd, mip1[i], bg, dbg);
     for (int k = 0; k < 3; ++k) jac1[(size_t)i * 12 + 3 * c + k] += t * dbg[k];
   }
 }
@@ -214,9 +215,10 @@ struct MfBounceBwdArgs {
 };
 template <int LEVEL>
 #ifndef NMF_BB_MINBLOCKS
-#define NMF_BB_MINBLOCKS 1      // experiments: NMF_NVCC_EXTRA=-DNMF_BB_MINBLOCKS=4 caps the kernel at 128 registers
+#define NMF_BB_MINBLOCKS 3      // 168 registers: 3 CTAs per SM (uncapped the kernel takes 212 and runs 15 % slower); 4 or 5 change nothing
 #endif
 __global__ void __launch_bounds__(MLP_THREADS, NMF_BB_MINBLOCKS) k_mf_bounce_bwd(const NmfScene s, const MfBounceBwdArgs a) {
+  const NmfEnvDyn ed = nmf_env_dyn_load(s);     // mipbias and pole means: by value or from NmfScene.env_dyn
   const int n_tiles = a.tile_start[a.n_chunks];
   const int lane = threadIdx.x & 31;
   float* g_top = a.gsat + (size_t)s.env_h * s.env_w * 4;
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(MLP_THREADS, NMF_BB_MINBLOCKS) k_mf_bounce_bwd
         for (int k = 0; k < 3; ++k) tang[k] = J[k] * dg.dL.x + J[3 + k] * dg.dL.y + J[6 + k] * dg.dL.z;
       } else {
         const NmfDual3 Ld = nmf_d3(nmf_dmk(dg.L.x, dg.dL.x), nmf_dmk(dg.L.y, dg.dL.y), nmf_dmk(dg.L.z, dg.dL.z));
-        nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s), Ld, mip, inc, tang);
+        nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot, Ld, mip, inc, tang);
       }
       const float vh = nmf_dot(m.V, dg.H);
       const float cost = fabsf(vh), svh = vh > 0.f ? 1.0f : (vh < 0.f ? -1.0f : 0.f);
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(MLP_THREADS, NMF_BB_MINBLOCKS) k_mf_bounce_bwd
           } else {
             const NmfDual3 Ln = nmf_d3(nmf_dmk(dn.L.x, dn.dL.x), nmf_dmk(dn.L.y, dn.dL.y), nmf_dmk(dn.L.z, dn.dL.z));
             float inc_n[3];
-            nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s), Ln, mip, inc_n, tn);
+            nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot, Ln, mip, inc_n, tn);
           }
           red[7 + c] = dcost * svh * nmf_dot(m.V, dn.dH) + a_inc[0] * tn[0] + a_inc[1] * tn[1] + a_inc[2] * tn[2];
         }
@@ -301,9 +303,9 @@ __global__ void __launch_bounds__(MLP_THREADS, NMF_BB_MINBLOCKS) k_mf_bounce_bwd
         float* g1 = a.g_lin1 + ((size_t)chunk * (size_t)a.max_retrace + (size_t)rslot) * 4;
         g1[0] = a_inc[0]; g1[1] = a_inc[1]; g1[2] = a_inc[2];
       } else if (a_inc[0] != 0.f || a_inc[1] != 0.f || a_inc[2] != 0.f) {
-        nmf_env_lookup1_bwd_map(a.gsat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), dg.L, mip, a_inc, g_top, g_bot);
+        nmf_env_lookup1_bwd_map(a.gsat, s.env_h, s.env_w, ed.mipbias, dg.L, mip, a_inc, g_top, g_bot);
         float rgb[3], dmb[3];
-        nmf_env_lookup1_dmipbias(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s), dg.L, mip, rgb, dmb);
+        nmf_env_lookup1_dmipbias(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot, dg.L, mip, rgb, dmb);
         mb = a_inc[0] * dmb[0] + a_inc[1] * dmb[1] + a_inc[2] * dmb[2];
       }
     }
@@ -325,6 +327,7 @@ __global__ void __launch_bounds__(MLP_THREADS, NMF_BB_MINBLOCKS) k_mf_bounce_bwd
 // gradient into the map, and the upstream of the ray's samples: d weight base = -g . bg
 __global__ void k_mf_sec_bwd(const NmfScene s, const float* rays1, const float* mip1, const float* acc1, const int* n_sec,
                              int max_retrace, int n, float* g_lin1, float* gsat, float* d_mipbias) {
+  const NmfEnvDyn ed = nmf_env_dyn_load(s);     // mipbias and pole means: by value or from NmfScene.env_dyn
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float mb = 0.f;
   if (i < n) {
@@ -334,13 +337,13 @@ __global__ void k_mf_sec_bwd(const NmfScene s, const float* rays1, const float* 
       const float a_inc[3] = {g[0], g[1], g[2]};
       const nmf_v3 d = nmf_mk3(rays1[6 * (size_t)i + 3], rays1[6 * (size_t)i + 4], rays1[6 * (size_t)i + 5]);
       float bg[3], dmb[3];
-      nmf_env_lookup1_dmipbias(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s), d, mip1[i], bg, dmb);
+      nmf_env_lookup1_dmipbias(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot, d, mip1[i], bg, dmb);
       g[3] = -(a_inc[0] * bg[0] + a_inc[1] * bg[1] + a_inc[2] * bg[2]);
       const float t = 1.0f - acc1[i];
       const float gb[3] = {t * a_inc[0], t * a_inc[1], t * a_inc[2]};
       if (gb[0] != 0.f || gb[1] != 0.f || gb[2] != 0.f) {
         float* g_top = gsat + (size_t)s.env_h * s.env_w * 4;
-        nmf_env_lookup1_bwd_map(gsat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), d, mip1[i], gb, g_top, g_top + 4);
+        nmf_env_lookup1_bwd_map(gsat, s.env_h, s.env_w, ed.mipbias, d, mip1[i], gb, g_top, g_top + 4);
         mb = gb[0] * dmb[0] + gb[1] * dmb[1] + gb[2] * dmb[2];
       }
     }

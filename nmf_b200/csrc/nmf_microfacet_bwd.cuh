@@ -391,6 +391,7 @@ struct NmfBrdfGrads { float* w0t; float* b0; float* w1t; float* b1; float* w2t; 
 NMF_HD void nmf_bounce_sample_bwd(const NmfScene& s, const float* nfeat, nmf_v3 V, nmf_v3 N, const float* R0, const float* diffuse,
                                   float rough, const float* u, int m, const float* g, float* dR0, float* ddiffuse, float* drough,
                                   float* dfeat, NmfBrdfGrads bg, float* gsat, float* g_top, float* g_bot, float* dN = nullptr) {
+  const NmfEnvDyn ed = nmf_env_dyn_load(s);     // mipbias and pole means: by value or from NmfScene.env_dyn
   const float inv_m = 1.0f / (float)m;
   float gm[3] = {g[0] * inv_m, g[1] * inv_m, g[2] * inv_m};
   for (int c = 0; c < 3; ++c) { dR0[c] = 0.f; ddiffuse[c] = 0.f; }
@@ -405,7 +406,7 @@ NMF_HD void nmf_bounce_sample_bwd(const NmfScene& s, const float* nfeat, nmf_v3 
     float x[66], bw[3], inc[3], dinc_dr[3];
     nmf_brdf_input(nfeat, fw.half_l, fw.diff_l, rough, x);
     const NmfDual3 Ld = nmf_d3(nmf_dmk(dg.L.x, dg.dL.x), nmf_dmk(dg.L.y, dg.dL.y), nmf_dmk(dg.L.z, dg.dL.z));
-    nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s), Ld, mip, inc, dinc_dr);
+    nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot, Ld, mip, inc, dinc_dr);
     // forward value of the BRDF weight first (g = NULL), then the mix backward, then the MLP backward with d bw
     nmf_brdf_row_fwd_bwd(x, s.brdf_w0t, s.brdf_b0, s.brdf_w1t, s.brdf_b1, s.brdf_w2t, s.brdf_b2, s.brdf_bias, nullptr, bw, nullptr,
                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -421,7 +422,7 @@ NMF_HD void nmf_bounce_sample_bwd(const NmfScene& s, const float* nfeat, nmf_v3 
         const NmfGGXdr dn = nmf_ggx_sample_dN(u1, u2, V, N, rough, c);
         const NmfDual3 Ln = nmf_d3(nmf_dmk(dn.L.x, dn.dL.x), nmf_dmk(dn.L.y, dn.dL.y), nmf_dmk(dn.L.z, dn.dL.z));
         float inc_n[3], dinc_dn[3];
-        nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s), Ln, mip, inc_n, dinc_dn);
+        nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot, Ln, mip, inc_n, dinc_dn);
         float acc = dcost * svh * nmf_dot(V, dn.dH);
         for (int k = 0; k < 3; ++k) acc += a_inc[k] * dinc_dn[k];
         dN[c] += acc;
@@ -430,7 +431,7 @@ NMF_HD void nmf_bounce_sample_bwd(const NmfScene& s, const float* nfeat, nmf_v3 
     float bw2[3];
     nmf_brdf_row_fwd_bwd(x, s.brdf_w0t, s.brdf_b0, s.brdf_w1t, s.brdf_b1, s.brdf_w2t, s.brdf_b2, s.brdf_bias, a_bw, bw2, bg.w0t, bg.b0,
                          bg.w1t, bg.b1, bg.w2t, bg.b2, dfeat);
-    nmf_env_lookup1_bwd_map(gsat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), dg.L, mip, a_inc, g_top, g_bot);
+    nmf_env_lookup1_bwd_map(gsat, s.env_h, s.env_w, ed.mipbias, dg.L, mip, a_inc, g_top, g_bot);
   }
   *drough = dr;
 }
@@ -604,10 +605,11 @@ inline void nmf_env_map_grad_finish(float* gsat, int h, int w, const float* g_to
 // comb = F inc bw + (1 - F) diffuse.  Shared by the host restatement below and k_mf_tangent1 (csrc/nmf_mf_train.cu).
 NMF_HD void nmf_bounce_ray_tangent(const NmfScene& s, NmfDual3 V, nmf_v3 N, const float* R0, const float* diffuse, float rough,
                                    float u1, float u2, float mip, const float* bw, float* comb, float* dcomb) {
+  const NmfEnvDyn ed = nmf_env_dyn_load(s);     // mipbias and pole means: by value or from NmfScene.env_dyn
   const NmfGGXdr dg = nmf_ggx_sample_dual3(u1, u2, V, nmf_d3k(N), nmf_dk(rough));
   float inc[3], dinc[3];
   const NmfDual3 Ld = nmf_d3(nmf_dmk(dg.L.x, dg.dL.x), nmf_dmk(dg.L.y, dg.dL.y), nmf_dmk(dg.L.z, dg.dL.z));
-  nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, NMF_ENV_MIPBIAS(s), NMF_ENV_TOP(s), NMF_ENV_BOT(s), Ld, mip, inc, dinc);
+  nmf_env_lookup1_d(s.env_sat, s.env_h, s.env_w, ed.mipbias, ed.top, ed.bot, Ld, mip, inc, dinc);
   const NmfDual3 Hd = nmf_d3(nmf_dmk(dg.H.x, dg.dH.x), nmf_dmk(dg.H.y, dg.dH.y), nmf_dmk(dg.H.z, dg.dH.z));
   NmfDual vh = nmf_ddot(V, Hd);
   if (vh.v < 0.f) vh = nmf_dmk(-vh.v, -vh.d);                          // |v.h|
